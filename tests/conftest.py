@@ -1,0 +1,30 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden.npz"))
+    return {k: g[k] for k in g.files}
+
+
+@pytest.fixture(scope="session")
+def pcm_song(golden):
+    """data/s16_mono_22_5kHz.flac as ffmpeg's f32le (bit-exact, see make_golden.py)."""
+    return golden["pcm_s16_mono"].astype(np.float32) / np.float32(32768.0)
+
+
+@pytest.fixture(scope="session")
+def pcm_piano(golden):
+    return golden["pcm_piano"].astype(np.float32) / np.float32(32768.0)
