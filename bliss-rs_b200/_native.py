@@ -1,0 +1,280 @@
+"""ctypes binding of libbliss_b200.so (include/bliss_b200.h).
+
+There is no fallback of any kind: if the shared library is missing, or no CUDA
+device is visible, every call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libbliss_b200.so")
+
+N_KERNELS = 10
+METRIC_MAHALANOBIS = 0
+METRIC_COSINE = 2
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class Taps(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "centroid", "rolloff", "flatness", "flux", "thresholded", "bpms", "n_bpms",
+        "loudness_chunks", "zero_crossings", "stft8192", "n_peaks", "tuning", "chroma",
+        "interval_features")]
+
+
+_lib = None
+_inited_device = None
+
+# every symbol include/bliss_b200.h declares
+SYMBOLS = [
+    "bliss_b200_init", "bliss_b200_shutdown", "bliss_b200_set_workspace_limit", "bliss_b200_strerror",
+    "bliss_b200_last_error", "bliss_b200_feature_count", "bliss_b200_analyze", "bliss_b200_analyze_batch",
+    "bliss_b200_analyze_batch_device", "bliss_b200_feature_weights", "bliss_b200_distance",
+    "bliss_b200_distance_matrix", "bliss_b200_distance_matrix_device", "bliss_b200_closest_to_songs",
+    "bliss_b200_song_to_song", "bliss_b200_stft512_mag_device", "bliss_b200_analyze_taps",
+    "bliss_b200_set_profiling", "bliss_b200_get_profile", "bliss_b200_kernel_name",
+    "bliss_b200_launch_count",
+]
+
+
+def load():
+    """dlopen the library and declare the prototypes (no device needed)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise NativeError(
+            "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(the CUDA extension is the only implementation; there is no CPU fallback)" % SO_PATH)
+    L = C.CDLL(SO_PATH)
+    vp, u64p, i32p, u32p, f32p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int32), \
+        C.POINTER(C.c_uint32), C.POINTER(C.c_float)
+    L.bliss_b200_init.argtypes = [C.c_int]
+    L.bliss_b200_shutdown.restype = None
+    L.bliss_b200_set_workspace_limit.argtypes = [C.c_uint64]
+    L.bliss_b200_strerror.argtypes = [C.c_int]
+    L.bliss_b200_strerror.restype = C.c_char_p
+    L.bliss_b200_last_error.restype = C.c_char_p
+    L.bliss_b200_feature_count.argtypes = [C.c_uint16]
+    L.bliss_b200_feature_count.restype = C.c_uint32
+    L.bliss_b200_analyze.argtypes = [vp, C.c_uint64, C.c_uint16, vp]
+    L.bliss_b200_analyze_batch.argtypes = [vp, u64p, C.c_uint32, C.c_uint16, vp, i32p]
+    L.bliss_b200_analyze_batch_device.argtypes = [vp, u64p, u64p, C.c_uint32, C.c_uint16, vp, i32p, vp]
+    L.bliss_b200_feature_weights.argtypes = [C.c_uint16, vp]
+    L.bliss_b200_distance.argtypes = [vp, vp, C.c_uint32, C.c_int, vp, f32p]
+    L.bliss_b200_distance_matrix.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp]
+    L.bliss_b200_distance_matrix_device.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_int, vp,
+                                                    vp, vp]
+    L.bliss_b200_closest_to_songs.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, vp]
+    L.bliss_b200_song_to_song.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp]
+    L.bliss_b200_stft512_mag_device.argtypes = [vp, u64p, u64p, C.c_uint32, vp, u64p, vp]
+    L.bliss_b200_analyze_taps.argtypes = [vp, C.c_uint64, C.c_uint16, vp, C.POINTER(Taps)]
+    L.bliss_b200_set_profiling.argtypes = [C.c_int]
+    L.bliss_b200_get_profile.argtypes = [C.POINTER(C.c_double), u64p]
+    L.bliss_b200_kernel_name.argtypes = [C.c_int]
+    L.bliss_b200_kernel_name.restype = C.c_char_p
+    L.bliss_b200_launch_count.restype = C.c_uint64
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc < 0:
+        L = load()
+        raise NativeError("%s: %s" % (L.bliss_b200_strerror(rc).decode(), L.bliss_b200_last_error().decode()))
+    return rc
+
+
+def init(device=None):
+    """bliss_b200_init on `device` (default: $LOCAL_RANK or 0).  Raises without a GPU."""
+    global _inited_device
+    L = load()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if _inited_device is None else _inited_device
+    if _inited_device == device:
+        return L
+    check(L.bliss_b200_init(int(device)))
+    _inited_device = device
+    return L
+
+
+def lib():
+    return init()
+
+
+def feature_count(version=2):
+    return int(load().bliss_b200_feature_count(version))
+
+
+def kernel_names():
+    L = load()
+    return [L.bliss_b200_kernel_name(i).decode() for i in range(N_KERNELS)]
+
+
+def get_profile():
+    L = lib()
+    ms = (C.c_double * N_KERNELS)()
+    ln = (C.c_uint64 * N_KERNELS)()
+    check(L.bliss_b200_get_profile(ms, ln))
+    return list(ms), list(ln)
+
+
+def set_profiling(on):
+    check(lib().bliss_b200_set_profiling(1 if on else 0))
+
+
+def launch_count():
+    return int(load().bliss_b200_launch_count())
+
+
+def _f32c(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def analyze_batch(pcms, version=2):
+    """list of 1-D float32 host arrays -> (status int32[n], features float32[n, dim])"""
+    L = lib()
+    pcms = [_f32c(p) for p in pcms]
+    n = len(pcms)
+    dim = feature_count(version)
+    out = np.zeros((n, dim), np.float32)
+    status = np.zeros(n, np.int32)
+    if n == 0:
+        return status, out
+    ptrs = (C.c_void_p * n)(*[p.ctypes.data if p.size else None for p in pcms])
+    lens = (C.c_uint64 * n)(*[p.size for p in pcms])
+    check(L.bliss_b200_analyze_batch(ptrs, lens, n, version, out.ctypes.data,
+                                     status.ctypes.data_as(C.POINTER(C.c_int32))))
+    return status, out
+
+
+def analyze_batch_ptrs(ptrs, lens, version, out, status):
+    """raw form used by bench.py: ptrs/lens are ctypes arrays over pinned host buffers"""
+    L = lib()
+    check(L.bliss_b200_analyze_batch(ptrs, lens, len(lens), version, out.ctypes.data,
+                                     status.ctypes.data_as(C.POINTER(C.c_int32))))
+
+
+def analyze(pcm, version=2):
+    L = lib()
+    pcm = _f32c(pcm)
+    out = np.zeros(feature_count(version), np.float32)
+    rc = check(L.bliss_b200_analyze(pcm.ctypes.data if pcm.size else None, pcm.size, version, out.ctypes.data))
+    return rc, out
+
+
+def analyze_batch_device(d_pcm_ptr, offsets, n_samples, version, d_out_ptr, stream_ptr=None):
+    """device-resident PCM; offsets / n_samples: sequences of ints. Returns status int32[n]."""
+    L = lib()
+    n = len(n_samples)
+    off = (C.c_uint64 * n)(*[int(o) for o in offsets])
+    ln = (C.c_uint64 * n)(*[int(v) for v in n_samples])
+    status = (C.c_int32 * n)()
+    check(L.bliss_b200_analyze_batch_device(d_pcm_ptr, off, ln, n, version, d_out_ptr, status, stream_ptr))
+    return np.array(status[:], np.int32)
+
+
+def stft512_mag_device(d_pcm_ptr, offsets, n_samples, d_mags_ptr, stream_ptr=None):
+    L = lib()
+    n = len(n_samples)
+    off = (C.c_uint64 * n)(*[int(o) for o in offsets])
+    ln = (C.c_uint64 * n)(*[int(v) for v in n_samples])
+    fo = (C.c_uint64 * (n + 1))()
+    check(L.bliss_b200_stft512_mag_device(d_pcm_ptr, off, ln, n, d_mags_ptr, fo, stream_ptr))
+    return np.array(fo[:], np.uint64)
+
+
+def analyze_taps(pcm, version=2):
+    """Analyse one song and return (status, features, dict of intermediate arrays)."""
+    L = lib()
+    pcm = _f32c(pcm)
+    n = pcm.size
+    out = np.zeros(feature_count(version), np.float32)
+    if n < 8192:
+        rc = check(L.bliss_b200_analyze_taps(pcm.ctypes.data if n else None, n, version, out.ctypes.data, None))
+        return rc, out, {}
+    n_s, n_t = (n - 512) // 128 + 1, (n - 512) // 256 + 1
+    n_c = int(np.ceil(np.float32(n) / np.float32(2205)))
+    a = {
+        "centroid": np.zeros(n_s, np.float32), "rolloff": np.zeros(n_s, np.float32),
+        "flatness": np.zeros(n_s, np.float32), "flux": np.zeros(n_t, np.float32),
+        "thresholded": np.zeros(n_t, np.float32), "bpms": np.zeros(n_t // 16 + 16, np.float32),
+        "n_bpms": np.zeros(1, np.uint32), "loudness_chunks": np.zeros((n + 1023) // 1024, np.float32),
+        "zero_crossings": np.zeros(1, np.uint32), "stft8192": np.zeros((n_c, 4097), np.float32),
+        "n_peaks": np.zeros(1, np.uint64), "tuning": np.zeros(1, np.float64),
+        "chroma": np.zeros((n_c, 12), np.float64), "interval_features": np.zeros(10, np.float64),
+    }
+    t = Taps(**{k: v.ctypes.data for k, v in a.items()})
+    rc = check(L.bliss_b200_analyze_taps(pcm.ctypes.data, n, version, out.ctypes.data, C.byref(t)))
+    a["bpms"] = a["bpms"][:int(a["n_bpms"][0])]
+    return rc, out, a
+
+
+def feature_weights(version=2):
+    dim = feature_count(version)
+    m = np.zeros((dim, dim), np.float32)
+    check(load().bliss_b200_feature_weights(version, m.ctypes.data))
+    return m
+
+
+def _metric_args(metric, m, dim):
+    if m is not None:
+        m = _f32c(m)
+        assert m.shape == (dim, dim)
+    return metric, m, (m.ctypes.data if m is not None else None)
+
+
+def distance(a, b, metric=METRIC_MAHALANOBIS, m=None):
+    L = lib()
+    a, b = _f32c(a), _f32c(b)
+    assert a.shape == b.shape and a.ndim == 1
+    metric, m, mp = _metric_args(metric, m, a.size)
+    out = C.c_float(0)
+    check(L.bliss_b200_distance(a.ctypes.data, b.ctypes.data, a.size, metric, mp, C.byref(out)))
+    return np.float32(out.value)
+
+
+def distance_matrix(rows, cols, metric=METRIC_MAHALANOBIS, m=None):
+    L = lib()
+    rows, cols = _f32c(np.atleast_2d(rows)), _f32c(np.atleast_2d(cols))
+    dim = rows.shape[1]
+    metric, m, mp = _metric_args(metric, m, dim)
+    out = np.zeros((rows.shape[0], cols.shape[0]), np.float32)
+    check(L.bliss_b200_distance_matrix(rows.ctypes.data, rows.shape[0], cols.ctypes.data, cols.shape[0], dim,
+                                       metric, mp, out.ctypes.data))
+    return out
+
+
+def distance_matrix_device(d_rows, n_rows, d_cols, n_cols, dim, d_out, metric=METRIC_MAHALANOBIS, m=None,
+                           stream_ptr=None):
+    L = lib()
+    metric, m, mp = _metric_args(metric, m, dim)
+    check(L.bliss_b200_distance_matrix_device(d_rows, n_rows, d_cols, n_cols, dim, metric, mp, d_out, stream_ptr))
+
+
+def closest_to_songs(seeds, cands, metric=METRIC_MAHALANOBIS, m=None):
+    L = lib()
+    seeds, cands = _f32c(np.atleast_2d(seeds)), _f32c(np.atleast_2d(cands))
+    dim = cands.shape[1]
+    metric, m, mp = _metric_args(metric, m, dim)
+    order = np.zeros(cands.shape[0], np.uint32)
+    keys = np.zeros(cands.shape[0], np.float32)
+    check(L.bliss_b200_closest_to_songs(seeds.ctypes.data, seeds.shape[0], cands.ctypes.data, cands.shape[0],
+                                        dim, metric, mp, order.ctypes.data, keys.ctypes.data))
+    return order, keys
+
+
+def song_to_song(seeds, cands, metric=METRIC_MAHALANOBIS, m=None):
+    L = lib()
+    seeds, cands = _f32c(np.atleast_2d(seeds)), _f32c(np.atleast_2d(cands))
+    dim = cands.shape[1]
+    metric, m, mp = _metric_args(metric, m, dim)
+    order = np.zeros(cands.shape[0], np.uint32)
+    check(L.bliss_b200_song_to_song(seeds.ctypes.data, seeds.shape[0], cands.ctypes.data, cands.shape[0], dim,
+                                    metric, mp, order.ctypes.data))
+    return order

@@ -1,0 +1,528 @@
+// chroma.cu -- the chroma chain of ChromaDesc::do_ / get_values (src/chroma.rs:73-132):
+//   K3  reflect-padded 8192-point Hann STFT (utils.rs:26-64) + pip_track (chroma.rs:269-331)
+//   K4  estimate_tuning / pitch_tuning (chroma.rs:334-391): exact median + 100-bin histogram
+//   K5  chroma_stft contraction 12 x 4097 . 4097 x frames in f64 (chroma.rs:393-412)
+//       fused with normalize_feature_sequence / extract_interval_features (:137-188)
+//   plus the table of all 100 possible chroma filterbanks (chroma.rs:197-267).
+#include "common.cuh"
+#include "fft8192.cuh"
+
+namespace bliss {
+
+// ---------------------------------------------------------------------------
+// chroma filterbank for every tuning the estimator can return:
+// tuning(idx) = (-50 + 100*0.01*idx)/100, idx = 0..99 (chroma.rs:357-358).
+// Layout: table[idx][bin][12] f64 (the 12 chroma weights of one bin contiguous).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double tuning_of(int idx) { return (-50. + (100. * 0.01 * (double)idx)) / 100.; }
+
+__device__ __forceinline__ double freq_bin(int i, double a440) {
+    // Array::linspace(0, 22050, 8193)[i] / (a440/16) -> log2 * 12   (chroma.rs:210-214, utils.rs:119-129)
+    const double stepf = (double)SAMPLE_RATE / 8192.0;
+    double f = 0. + stepf * (double)i;
+    f /= a440 / 16.;
+    return log2(f) * 12.0;
+}
+
+__global__ void chroma_filter_table_kernel(double *__restrict__ table) {
+    const int idx = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= CH_BINS) return;
+    const double tuning = tuning_of(idx);
+    const double a440 = 440.0 * pow(2.0, tuning / 12.0);
+    const double fb1 = freq_bin(1, a440);
+    const double fb = (i == 0) ? fb1 - 1.5 * 12.0 : freq_bin(i, a440);
+    const double fbn = freq_bin(i + 1, a440);  // i+1 <= 4097 < 8193 always exists
+    double bw = fbn - fb;
+    bw = (bw <= 1.) ? 1. : bw;
+    double w[12];
+    double ss = 0.;
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        double d = -(double)r + fb;
+        d = fmod(d + 6.0 + 10. * 12.0, 12.0) - 6.0;
+        d = d / bw;
+        w[r] = exp(-0.5 * (2. * d) * (2. * d));
+        ss += w[r] * w[r];
+    }
+    ss = sqrt(ss);
+    if (ss < 2.2250738585072014e-308) ss = 1.;
+    double g = (fb / 12.0 - 5.0) / 2.0;
+    g = exp(-0.5 * (g * g));
+    double *o = table + ((size_t)idx * CH_BINS + i) * 12;
+#pragma unroll
+    for (int r = 0; r < 12; r++) o[r] = w[(r + 3) % 12] / ss * g;  // np.roll(-3): b[r] = wts[(r+3)%12]
+}
+
+int launch_chroma_filter_table(double *table, cudaStream_t st) {
+    dim3 grid((CH_BINS + 127) / 128, 100);
+    chroma_filter_table_kernel<<<grid, 128, 0, st>>>(table);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------
+// K3: one CTA per pair of chroma frames.
+// ---------------------------------------------------------------------------
+constexpr int K3_THREADS = 256;
+
+__global__ void __launch_bounds__(K3_THREADS, 2)
+stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
+                const unsigned int *__restrict__ pair_prefix, int n_songs,
+                const float *__restrict__ hann, const cpx *__restrict__ tw,
+                float *__restrict__ mags, double *__restrict__ cand_mag,
+                unsigned char *__restrict__ cand_bin, unsigned int *__restrict__ cand_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cpx *buf = reinterpret_cast<cpx *>(smem_raw);
+    __shared__ float s_red[2][K3_THREADS / 32];
+    __shared__ unsigned int s_scan[K3_THREADS / 32];
+    __shared__ unsigned int s_base;
+
+    const int tid = threadIdx.x;
+    // song lookup
+    int lo = 0, hi = n_songs;
+    const unsigned int item = blockIdx.x;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (pair_prefix[mid] <= item) lo = mid; else hi = mid;
+    }
+    const int si = lo;
+    const SongDesc sd = songs[si];
+    const int fA = 2 * (int)(item - pair_prefix[si]);
+    const bool hasB = (fA + 1) < (int)sd.n_c_comp;
+    const float *x = pcm + sd.pcm_off;
+    const int n = (int)sd.n;
+
+    // pass 1 straight from global memory: z[m] = hann[m] * (xA[m] + i xB[m])
+    const long long pA = (long long)CH_HOP * fA;
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        const int b = tid + 256 * h;
+        cpx v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int m = b + 512 * q;
+            const float w = __ldg(hann + m);
+            const float a = f8k::padded_sample(x, n, pA + m);
+            const float bb = hasB ? f8k::padded_sample(x, n, pA + CH_HOP + m) : 0.f;
+            v[q] = cpx{a * w, bb * w};
+        }
+        f8k::pass1_store(b, v, tw, buf);
+    }
+    __syncthreads();
+    f8k::pass2(tid, tw, buf);
+    f8k::pass2(tid + 256, tw, buf);
+    __syncthreads();
+    f8k::pass3(tid, buf);
+    __syncthreads();
+
+    // natural-order magnitudes: thread owns bins tid + 256*m, m = 0..16
+    float ma[17], mb[17];
+    float mxa = 0.f, mxb = 0.f;
+#pragma unroll
+    for (int m = 0; m < 17; m++) {
+        const int k = tid + 256 * m;
+        ma[m] = 0.f;
+        mb[m] = 0.f;
+        if (k <= 4096) {
+            const cpx zk = buf[f8k::pad(f8k::xpos(k))];
+            const cpx zm = buf[f8k::pad(f8k::xpos((8192 - k) & 8191))];
+            f8k::untangle_mag(zk, zm, ma[m], mb[m]);
+            mxa = fmaxf(mxa, ma[m]);
+            mxb = fmaxf(mxb, mb[m]);
+        }
+    }
+    __syncthreads();  // everyone has read buf; reuse it for the magnitudes
+    float *sA = reinterpret_cast<float *>(smem_raw);
+    float *sB = sA + CH_STRIDE;
+    float *gA = mags + (sd.mag_off + (unsigned long long)fA) * CH_STRIDE;
+    float *gB = gA + CH_STRIDE;
+#pragma unroll
+    for (int m = 0; m < 17; m++) {
+        const int k = tid + 256 * m;
+        if (k <= 4096) {
+            sA[k] = ma[m];
+            sB[k] = mb[m];
+            gA[k] = ma[m];
+            if (hasB) gB[k] = mb[m];
+        }
+    }
+    // frame maxima (pip_track's ref_value = 0.1 * max over all bins, chroma.rs:289-293)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, o));
+        mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, o));
+    }
+    if ((tid & 31) == 0) {
+        s_red[0][tid >> 5] = mxa;
+        s_red[1][tid >> 5] = mxb;
+    }
+    __syncthreads();
+    float fmax_a = s_red[0][0], fmax_b = s_red[1][0];
+#pragma unroll
+    for (int w = 1; w < K3_THREADS / 32; w++) {
+        fmax_a = fmaxf(fmax_a, s_red[0][w]);
+        fmax_b = fmaxf(fmax_b, s_red[1][w]);
+    }
+
+    // pip_track on centre bins 57..1483 (beginning = 56, end = 1486 for n_fft = 8192)
+    const int nframes_here = hasB ? 2 : 1;
+    for (int fr = 0; fr < nframes_here; fr++) {
+        const float *sm = fr ? sB : sA;
+        const double ref = 0.1 * (double)(fr ? fmax_b : fmax_a);
+        double cm[6];
+        unsigned char cb[6];
+        int cnt = 0;
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+            const int c = 57 + tid + 256 * m;
+            if (c <= 1483) {
+                const double before = (double)sm[c - 1], elem = (double)sm[c], after = (double)sm[c + 1];
+                if (elem > ref && after <= elem && before < elem) {
+                    const double avg = 0.5 * (after - before);
+                    double shift = 2. * elem - after - before;
+                    if (fabs(shift) < 2.2250738585072014e-308) shift += 1.;
+                    shift = avg / shift;
+                    const double pitch = ((double)c + shift) * (double)SAMPLE_RATE / 8192.0;
+                    const double mg = elem + 0.5 * avg * shift;
+                    // pitch_tuning's residue bin (chroma.rs:342-348), tuning 0, 12 bins/octave
+                    double v = pitch / (440.0 / 16.);
+                    v = log2(v);
+                    v = fmod(12.0 * v, 1.0);
+                    if (v >= 0.5) v -= 1.;
+                    int idx = (int)((v - -0.5) / 0.01);
+                    idx = idx < 0 ? 0 : (idx > 99 ? 99 : idx);
+                    if (pitch > 0.) {
+                        cm[cnt] = mg;
+                        cb[cnt] = (unsigned char)idx;
+                        cnt++;
+                    }
+                }
+            }
+        }
+        // block-exclusive scan of cnt, one global reservation per frame
+        unsigned int incl = (unsigned)cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((tid & 31) >= o) incl += t;
+        }
+        __syncthreads();
+        if ((tid & 31) == 31) s_scan[tid >> 5] = incl;
+        __syncthreads();
+        unsigned int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < K3_THREADS / 32; w++) {
+            if (w < (tid >> 5)) woff += s_scan[w];
+            tot += s_scan[w];
+        }
+        if (tid == 0) s_base = tot ? atomicAdd(cand_count + si, tot) : 0u;
+        __syncthreads();
+        const unsigned long long dst = sd.cand_off + s_base + woff + (incl - (unsigned)cnt);
+        for (int q = 0; q < cnt; q++) {
+            cand_mag[dst + q] = cm[q];
+            cand_bin[dst + q] = cb[q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4: one CTA per song.  threshold = Midpoint median of the candidate magnitudes
+// (exact radix select on the f64 bit patterns: all values are positive), then the
+// 100-bin histogram of the residues of candidates with mag >= threshold, argmax =
+// first maximum.  Writes the tuning INDEX (tuning = (-50 + idx)/100).
+// ---------------------------------------------------------------------------
+constexpr int K4_THREADS = 1024;
+
+__device__ __forceinline__ void hist_add(unsigned int *hist, unsigned int bucket, bool active) {
+    // warp-aggregated shared-memory histogram update
+    const unsigned int act = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    const unsigned int peers = __match_any_sync(act, bucket);
+    const int leader = __ffs(peers) - 1;
+    if ((int)(threadIdx.x & 31) == leader) atomicAdd(hist + bucket, (unsigned)__popc(peers));
+}
+
+__global__ void __launch_bounds__(K4_THREADS)
+tuning_kernel(const double *__restrict__ cand_mag, const unsigned char *__restrict__ cand_bin,
+              const unsigned int *__restrict__ cand_count, const SongDesc *__restrict__ songs,
+              int *__restrict__ tuning_idx) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix, s_vhi;
+    __shared__ unsigned int s_rank, s_cle;
+    const SongDesc sd = songs[blockIdx.x];
+    const int tid = threadIdx.x;
+    const unsigned int n = sd.valid ? cand_count[blockIdx.x] : 0u;
+    if (n == 0) {  // estimate_tuning returns 0 when pip_track finds nothing (chroma.rs:377-379)
+        if (tid == 0) tuning_idx[blockIdx.x] = 50;
+        return;
+    }
+    const unsigned long long *keys = reinterpret_cast<const unsigned long long *>(cand_mag + sd.cand_off);
+    const unsigned char *bins = cand_bin + sd.cand_off;
+    const unsigned int r_lo = (n - 1) / 2, r_hi = n / 2;  // floor / ceil of (n-1)*0.5
+
+    if (tid == 0) { s_prefix = 0ull; s_rank = r_lo; }
+    unsigned long long mask = 0ull;
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned int n_round = (n + K4_THREADS - 1) / K4_THREADS * K4_THREADS;
+        for (unsigned int i = tid; i < n_round; i += K4_THREADS) {
+            bool act = false;
+            unsigned int bucket = 0;
+            if (i < n) {
+                const unsigned long long k = keys[i];
+                act = (k & mask) == prefix;
+                bucket = (unsigned int)((k >> shift) & 255ull);
+            }
+            hist_add(hist, bucket, act);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int rank = s_rank, cum = 0;
+            int b = 0;
+            for (; b < 256; b++) {
+                if (cum + hist[b] > rank) break;
+                cum += hist[b];
+            }
+            s_rank = rank - cum;
+            s_prefix = prefix | ((unsigned long long)b << shift);
+        }
+        mask |= 255ull << shift;
+        __syncthreads();
+    }
+    const unsigned long long vlo = s_prefix;
+    // higher order statistic: equal to vlo when enough duplicates, else the next larger key
+    if (tid == 0) { s_cle = 0; s_vhi = ~0ull; }
+    __syncthreads();
+    if (r_hi != r_lo) {
+        unsigned int cle = 0;
+        unsigned long long mn = ~0ull;
+        for (unsigned int i = tid; i < n; i += K4_THREADS) {
+            const unsigned long long k = keys[i];
+            cle += (k <= vlo) ? 1u : 0u;
+            if (k > vlo && k < mn) mn = k;
+        }
+        cle = __reduce_add_sync(0xffffffffu, cle);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, mn, o);
+            mn = t < mn ? t : mn;
+        }
+        if ((tid & 31) == 0) {
+            atomicAdd(&s_cle, cle);
+            atomicMin(&s_vhi, mn);
+        }
+    }
+    __syncthreads();
+    unsigned long long vhi = vlo;
+    if (r_hi != r_lo && s_cle < r_hi + 1) vhi = s_vhi;
+    const double lower = __longlong_as_double((long long)vlo), higher = __longlong_as_double((long long)vhi);
+    const double thr = lower + (higher - lower) / 2.;  // ndarray-stats Midpoint
+
+    // histogram of residues with mag >= thr (chroma.rs:385-390 -> pitch_tuning :348-356)
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    {
+        const unsigned int n_round = (n + K4_THREADS - 1) / K4_THREADS * K4_THREADS;
+        const double *mg = cand_mag + sd.cand_off;
+        for (unsigned int i = tid; i < n_round; i += K4_THREADS) {
+            bool act = false;
+            unsigned int bucket = 0;
+            if (i < n) {
+                act = mg[i] >= thr;
+                bucket = bins[i];
+            }
+            hist_add(hist, bucket, act);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int best = 0;
+        for (int b = 1; b < 100; b++)
+            if (hist[b] > hist[best]) best = b;
+        tuning_idx[blockIdx.x] = best;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K5: chroma contraction + interval features, thread per frame, 128 frames per CTA.
+// ---------------------------------------------------------------------------
+constexpr int K5_FRAMES = 128;
+constexpr int K5_KT = 32;
+
+// Interval / triad templates of chroma.rs:139-152 given as the offsets of their ones:
+// dyads {0,d} d=1..6, major {0,4,7}, minor {0,3,7}, diminished {0,3,6}, augmented {0,4,8}.
+__host__ __device__ constexpr int tmpl_off(int t, int i) {
+    return i == 0 ? 0
+         : t < 6  ? (i == 1 ? t + 1 : -1)
+         : t == 6 ? (i == 1 ? 4 : 7)
+         : t == 7 ? (i == 1 ? 3 : 7)
+         : t == 8 ? (i == 1 ? 3 : 6)
+                  : (i == 1 ? 4 : 8);
+}
+__host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+// product over the template rolled right by S (rotate_right, chroma.rs:164-165),
+// factors taken in ascending pitch-class order like `x.product()` over the row
+template <int T, int S>
+__device__ __forceinline__ double tmpl_term(const double (&e)[12]) {
+    constexpr int p0 = (tmpl_off(T, 0) + S) % 12, p1 = (tmpl_off(T, 1) + S) % 12;
+    if constexpr (tmpl_off(T, 2) < 0) {
+        constexpr int a = cmin(p0, p1), b = cmax(p0, p1);
+        return (1. * e[a]) * e[b];
+    } else {
+        constexpr int p2 = (tmpl_off(T, 2) + S) % 12;
+        constexpr int a = cmin(p0, cmin(p1, p2)), c = cmax(p0, cmax(p1, p2)), b = p0 + p1 + p2 - a - c;
+        return ((1. * e[a]) * e[b]) * e[c];
+    }
+}
+template <int T, int S>
+__device__ __forceinline__ void tmpl_sum(const double (&e)[12], double &f) {
+    if constexpr (S < 12) {
+        f += tmpl_term<T, S>(e);
+        tmpl_sum<T, S + 1>(e, f);
+    }
+}
+template <int T>
+__device__ __forceinline__ void tmpl_all(const double (&e)[12], double (&feat)[10]) {
+    if constexpr (T < 10) {
+        double f = 0.;
+        tmpl_sum<T, 0>(e, f);
+        feat[T] = f;
+        tmpl_all<T + 1>(e, feat);
+    }
+}
+
+__global__ void __launch_bounds__(K5_FRAMES)
+chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs,
+              const unsigned int *__restrict__ tile_prefix, int n_songs,
+              const double *__restrict__ filt_table, const int *__restrict__ tuning_idx,
+              double *__restrict__ tile_partials /*[tiles][10]*/, double *__restrict__ chroma_dbg) {
+    __shared__ float s_s[K5_KT][K5_FRAMES + 1];
+    __shared__ __align__(16) double s_w[K5_KT][12];
+    __shared__ double s_red[K5_FRAMES / 32][10];
+
+    const int tid = threadIdx.x;
+    int lo = 0, hi = n_songs;
+    const unsigned int item = blockIdx.x;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (tile_prefix[mid] <= item) lo = mid; else hi = mid;
+    }
+    const int si = lo;
+    const SongDesc sd = songs[si];
+    const int tile = (int)(item - tile_prefix[si]);
+    const int f0 = tile * K5_FRAMES;
+    const int nf = min(K5_FRAMES, (int)sd.n_c - f0);  // frames of this tile
+    const double *W = filt_table + (size_t)tuning_idx[si] * CH_BINS * 12;
+    const float *S = mags + (sd.mag_off + (unsigned long long)f0) * CH_STRIDE;
+    const int my_frame = f0 + tid;
+    const bool mine = tid < nf;
+
+    double acc[12];
+#pragma unroll
+    for (int c = 0; c < 12; c++) acc[c] = 0.;
+
+    for (int k0 = 0; k0 < CH_BINS; k0 += K5_KT) {
+        const int kt = min(K5_KT, CH_BINS - k0);
+        __syncthreads();
+        // stage S[frames][k0..k0+kt) transposed; rows beyond n_c_comp are zero (utils.rs:27-31)
+        for (int e = tid; e < K5_FRAMES * K5_KT; e += K5_FRAMES) {
+            const int fr = e / K5_KT, kk = e % K5_KT;
+            float v = 0.f;
+            if (fr < nf && kk < kt && (f0 + fr) < (int)sd.n_c_comp) v = __ldg(S + (size_t)fr * CH_STRIDE + k0 + kk);
+            s_s[kk][fr] = v;
+        }
+        for (int e = tid; e < K5_KT * 12; e += K5_FRAMES) {
+            const int kk = e / 12;
+            (&s_w[0][0])[e] = (kk < kt) ? W[(size_t)k0 * 12 + e] : 0.;
+        }
+        __syncthreads();
+        if (mine) {
+            for (int kk = 0; kk < kt; kk++) {
+                const double s = (double)s_s[kk][tid];
+                const double s2 = s * s;  // spectrum.mapv_inplace(|x| x*x), chroma.rs:400
+#pragma unroll
+                for (int c = 0; c < 12; c++) acc[c] += s_w[kk][c] * s2;
+            }
+        }
+    }
+    // L1 column normalisation (chroma.rs:404-410)
+    double feat[10];
+#pragma unroll
+    for (int t = 0; t < 10; t++) feat[t] = 0.;
+    if (mine) {
+        double sum = 0.;
+#pragma unroll
+        for (int c = 0; c < 12; c++) sum += fabs(acc[c]);
+        if (sum < 2.2250738585072014e-308) sum = 1.;
+        double e[12];
+        double esum = 0.;
+#pragma unroll
+        for (int c = 0; c < 12; c++) {
+            const double ch = acc[c] / sum;
+            if (chroma_dbg) chroma_dbg[((size_t)sd.c_tile_off * K5_FRAMES + (size_t)my_frame) * 12 + c] = ch;
+            e[c] = exp(ch * 15.);  // chroma_interval_features, chroma.rs:138
+            esum += fabs(e[c]);
+        }
+        if (esum < 0.0001) esum = 1.;  // normalize_feature_sequence, chroma.rs:177-188
+#pragma unroll
+        for (int c = 0; c < 12; c++) e[c] = e[c] / esum;
+        // extract_interval_features, chroma.rs:157-175: product over the rolled template, sum over 12 shifts
+        tmpl_all<0>(e, feat);
+    }
+    // sum the tile's frames (mean_axis over frames finishes in the summary kernel)
+#pragma unroll
+    for (int t = 0; t < 10; t++) {
+        double v = feat[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) s_red[tid >> 5][t] = v;
+    }
+    __syncthreads();
+    if (tid < 10) {
+        double v = 0.;
+#pragma unroll
+        for (int w = 0; w < K5_FRAMES / 32; w++) v += s_red[w][tid];
+        tile_partials[((size_t)sd.c_tile_off + tile) * 10 + tid] = v;
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------
+size_t stft8192_smem_bytes() { return sizeof(cpx) * f8k::BUF_CPX; }
+
+int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int *pair_prefix, int n_songs,
+                    unsigned int total_pairs, const float *hann, const cpx *tw, float *mags,
+                    double *cand_mag, unsigned char *cand_bin, unsigned int *cand_count, cudaStream_t st) {
+    if (total_pairs == 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(stft8192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)stft8192_smem_bytes());
+        attr_set = true;
+    }
+    stft8192_kernel<<<total_pairs, K3_THREADS, stft8192_smem_bytes(), st>>>(
+        pcm, songs, pair_prefix, n_songs, hann, tw, mags, cand_mag, cand_bin, cand_count);
+    return 1;
+}
+
+int launch_tuning(const double *cand_mag, const unsigned char *cand_bin, const unsigned int *cand_count,
+                  const SongDesc *songs, int n_songs, int *tuning_idx, cudaStream_t st) {
+    if (n_songs == 0) return 0;
+    tuning_kernel<<<n_songs, K4_THREADS, 0, st>>>(cand_mag, cand_bin, cand_count, songs, tuning_idx);
+    return 1;
+}
+
+int launch_chroma(const float *mags, const SongDesc *songs, const unsigned int *tile_prefix, int n_songs,
+                  unsigned int total_tiles, const double *filt_table, const int *tuning_idx,
+                  double *tile_partials, double *chroma_dbg, cudaStream_t st) {
+    if (total_tiles == 0) return 0;
+    chroma_kernel<<<total_tiles, K5_FRAMES, 0, st>>>(mags, songs, tile_prefix, n_songs, filt_table,
+                                                     tuning_idx, tile_partials, chroma_dbg);
+    return 1;
+}
+
+}  // namespace bliss

@@ -1,0 +1,52 @@
+// common.cuh -- shared declarations of the B200 analysis pipeline.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fft_regs.cuh"
+
+namespace bliss {
+
+constexpr int SAMPLE_RATE = 22050;        // src/lib.rs:143
+constexpr int PV_WIN = 512;               // SpectralDesc / BPMDesc WINDOW_SIZE (timbral.rs:40, temporal.rs:40)
+constexpr int PV_HOP_TIMBRAL = 128;       // timbral.rs:41
+constexpr int PV_HOP_TEMPO = 256;         // temporal.rs:41
+constexpr int CH_WIN = 8192;              // chroma.rs:39
+constexpr int CH_HOP = 2205;              // chroma.rs:74
+constexpr int CH_BINS = 4097;
+constexpr int CH_STRIDE = 4104;           // padded row of the magnitude spill (16 B aligned rows)
+constexpr int CH_MAX_PEAKS = 714;         // max local maxima among centre bins 57..1483
+constexpr int LOUD_WIN = 1024;            // misc.rs:44
+constexpr int MIN_SAMPLES = 8192;         // song/mod.rs:417-430
+
+// One entry per song of the wave currently on the device.  All offsets are in
+// elements of the array they index.
+struct SongDesc {
+    unsigned long long pcm_off;   // into the PCM buffer (samples)
+    unsigned long long mag_off;   // into the 8192-STFT magnitude spill (rows of CH_STRIDE floats)
+    unsigned long long cand_off;  // into the pip-track candidate arrays
+    unsigned int n;               // samples
+    unsigned int n_s;             // timbral frames  (n-512)/128+1        song/mod.rs:458-463
+    unsigned int n_t;             // tempo frames    (n-512)/256+1        song/mod.rs:435-441
+    unsigned int n_c;             // chroma frames   ceil(n/2205) in f32  utils.rs:30
+    unsigned int n_c_comp;        // chroma frames actually transformed (zip truncation, utils.rs:44-47)
+    unsigned int n_l;             // loudness chunks ceil(n/1024)         song/mod.rs:478
+    unsigned int s_off;           // into per-timbral-frame arrays
+    unsigned int t_off;           // into per-tempo-frame arrays
+    unsigned int l_off;           // into loudness chunk array
+    unsigned int e_off;           // into 256-sample block energies
+    unsigned int c_tile_off;      // into chroma tile partials
+    unsigned int bpm_off;         // into the bpm list
+    unsigned int valid;           // 0 => too short, skipped everywhere
+    unsigned int pad_;
+};
+
+struct PvocTables {   // device pointers
+    const float *win;     // [512] hanningz, aubio.rs:150-154
+    const cpx *twA;       // [16][32]  W512^(lane*k1)
+};
+
+// ---- kernel launchers (each returns the number of kernels launched) --------
+struct WaveBuffers;
+
+}  // namespace bliss

@@ -1,0 +1,241 @@
+// distance.cu -- K10: feature-vector distances of src/playlist.rs on the device.
+//   mahalanobis_distance  sqrt((a-b)^T M (a-b))   playlist.rs:140-142  (default metric lib.rs:168-178)
+//   euclidean_distance    M = I                   playlist.rs:65-71
+//   cosine_distance       1 - a.b/(|a||b|)        playlist.rs:76-79
+//   closest_to_songs keys: sum over seeds         playlist.rs:56-58, 256-270
+// f32 throughout, accumulated in the order ndarray uses (unrolled_dot: 8 partial
+// sums) so that the reference's exact-equality tests (lib.rs:273-291,
+// playlist.rs:1009-1108) hold bit for bit.  The direct (a-b)^2 form is kept on
+// purpose: the GEMM form |a|^2+|b|^2-2ab cancels for the near-duplicates that
+// dedup_playlist thresholds at 0.05 (playlist.rs:381-382).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace bliss {
+
+constexpr int MAX_DIM = 64;
+
+// ndarray numeric_util::unrolled_dot order
+template <typename FA, typename FB>
+__device__ __forceinline__ float unrolled_dot(FA xa, FB xb, int len) {
+    float p[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int i = 0;
+    for (; i + 8 <= len; i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) p[k] = __fadd_rn(p[k], __fmul_rn(xa(i + k), xb(i + k)));
+    }
+    float sum = 0.f;
+    sum = __fadd_rn(sum, __fadd_rn(p[0], p[4]));
+    sum = __fadd_rn(sum, __fadd_rn(p[1], p[5]));
+    sum = __fadd_rn(sum, __fadd_rn(p[2], p[6]));
+    sum = __fadd_rn(sum, __fadd_rn(p[3], p[7]));
+    for (; i < len; i++) sum = __fadd_rn(sum, __fmul_rn(xa(i), xb(i)));
+    return sum;
+}
+
+// mode: 0 = diagonal weights w[dim] (identity when w == nullptr), 1 = full matrix m[dim*dim], 2 = cosine
+// DIM > 0: compile-time dimension (registers); DIM == 0: runtime dim <= MAX_DIM.
+template <int DIM>
+__device__ __forceinline__ float pair_distance(const float *a, const float *b, int dim_rt, int mode,
+                                               const float *w_or_m) {
+    const int dim = DIM > 0 ? DIM : dim_rt;
+    if (mode == 2) {
+        const float ab = unrolled_dot([&](int i) { return a[i]; }, [&](int i) { return b[i]; }, dim);
+        const float aa = unrolled_dot([&](int i) { return a[i]; }, [&](int i) { return a[i]; }, dim);
+        const float bb = unrolled_dot([&](int i) { return b[i]; }, [&](int i) { return b[i]; }, dim);
+        return __fsub_rn(1.f, __fdiv_rn(ab, __fmul_rn(__fsqrt_rn(aa), __fsqrt_rn(bb))));
+    }
+    float d[DIM > 0 ? DIM : MAX_DIM], t[DIM > 0 ? DIM : MAX_DIM];
+#pragma unroll
+    for (int i = 0; i < dim; i++) d[i] = __fsub_rn(a[i], b[i]);
+    if (mode == 0) {
+#pragma unroll
+        for (int i = 0; i < dim; i++) t[i] = w_or_m ? __fmul_rn(d[i], w_or_m[i]) : d[i];
+    } else {
+        for (int j = 0; j < dim; j++) {
+            float s = 0.f;
+            for (int i = 0; i < dim; i++) s = __fadd_rn(s, __fmul_rn(d[i], w_or_m[i * dim + j]));
+            t[j] = s;
+        }
+    }
+    const float s = unrolled_dot([&](int i) { return t[i]; }, [&](int i) { return d[i]; }, dim);
+    return __fsqrt_rn(s);
+}
+
+// All-pairs block: out[i][j] = dist(rows[i], cols[j]); CTA tile 32 x 128, thread = 1 row x 4 cols.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+distance_matrix_kernel(const float *__restrict__ rows, unsigned int n_rows,
+                       const float *__restrict__ cols, unsigned int n_cols, int mode,
+                       const float *__restrict__ w_or_m, float *__restrict__ out) {
+    __shared__ float s_a[32][DIM];
+    __shared__ float s_b[128][DIM + 1];
+    __shared__ float s_w[(DIM <= 32) ? DIM * DIM : 1];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const unsigned int r0 = blockIdx.y * 32u, c0 = blockIdx.x * 128u;
+    for (int e = threadIdx.x; e < 32 * DIM; e += 256) {
+        const unsigned int r = r0 + e / DIM;
+        s_a[e / DIM][e % DIM] = r < n_rows ? rows[(size_t)r * DIM + e % DIM] : 0.f;
+    }
+    for (int e = threadIdx.x; e < 128 * DIM; e += 256) {
+        const unsigned int c = c0 + e / DIM;
+        s_b[e / DIM][e % DIM] = c < n_cols ? cols[(size_t)c * DIM + e % DIM] : 0.f;
+    }
+    const float *wm = nullptr;
+    if (w_or_m) {
+        const int nw = (mode == 1) ? DIM * DIM : DIM;
+        if (DIM <= 32) {
+            for (int e = threadIdx.x; e < nw; e += 256) s_w[e] = w_or_m[e];
+            wm = s_w;
+        } else {
+            wm = w_or_m;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        const int lr = ty + 8 * rr;
+        const unsigned int r = r0 + lr;
+        if (r >= n_rows) continue;
+        float res[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) res[q] = pair_distance<DIM>(s_a[lr], s_b[4 * tx + q], DIM, mode, wm);
+        const unsigned int c = c0 + 4u * tx;
+        float *o = out + (size_t)r * n_cols + c;
+        if (c + 3 < n_cols && ((n_cols & 3u) == 0)) {
+            *reinterpret_cast<float4 *>(o) = make_float4(res[0], res[1], res[2], res[3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (c + q < n_cols) o[q] = res[q];
+        }
+    }
+}
+
+// any dim <= MAX_DIM: one thread per output (used for custom metrics on other vector sizes)
+__global__ void __launch_bounds__(256)
+distance_matrix_generic_kernel(const float *__restrict__ rows, unsigned int n_rows,
+                               const float *__restrict__ cols, unsigned int n_cols, int dim, int mode,
+                               const float *__restrict__ w_or_m, float *__restrict__ out) {
+    const unsigned int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= n_cols || r >= n_rows) return;
+    out[(size_t)r * n_cols + c] = pair_distance<0>(rows + (size_t)r * dim, cols + (size_t)c * dim, dim, mode, w_or_m);
+}
+
+// keys[j] = sum_i dist(seed_i, cand_j), seeds visited in order (Iterator::sum, playlist.rs:56-58)
+__global__ void __launch_bounds__(256)
+seed_distance_kernel(const float *__restrict__ seeds, unsigned int n_seeds,
+                     const float *__restrict__ cands, unsigned int n_cands, int dim, int mode,
+                     const float *__restrict__ w_or_m, float *__restrict__ keys) {
+    const unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cands) return;
+    float b[MAX_DIM];
+    for (int i = 0; i < dim; i++) b[i] = cands[(size_t)j * dim + i];
+    float s = 0.f;
+    for (unsigned int i = 0; i < n_seeds; i++)
+        s = __fadd_rn(s, pair_distance<0>(seeds + (size_t)i * dim, b, dim, mode, w_or_m));
+    keys[j] = s;
+}
+
+// composite 64-bit key = (ordered float bits << 32) | index  -> any sort is stable
+__global__ void make_sort_keys_kernel(const float *__restrict__ keys, unsigned int n,
+                                      unsigned long long *__restrict__ out) {
+    const unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    unsigned int u = __float_as_uint(keys[j]);
+    if (u == 0x80000000u) u = 0u;                     // n32: -0.0 == +0.0
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // total order of finite floats
+    out[j] = ((unsigned long long)u << 32) | (unsigned long long)j;
+}
+
+__global__ void unpack_order_kernel(const unsigned long long *__restrict__ sorted, unsigned int n,
+                                    unsigned int *__restrict__ order) {
+    const unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) order[j] = (unsigned int)(sorted[j] & 0xffffffffull);
+}
+
+// argmin (first minimum) over `alive` candidates of dist(cur, cand): one CTA, used by song_to_song
+__global__ void __launch_bounds__(1024)
+nearest_alive_kernel(const float *__restrict__ cur, unsigned int n_cur, const float *__restrict__ cands,
+                     unsigned int n_cands, int dim, int mode, const float *__restrict__ w_or_m,
+                     unsigned char *__restrict__ alive, unsigned int *__restrict__ order,
+                     unsigned int step, float *__restrict__ next_cur) {
+    __shared__ float s_v[32];
+    __shared__ unsigned int s_i[32];
+    float best = INFINITY;
+    unsigned int bi = 0xffffffffu;
+    for (unsigned int j = threadIdx.x; j < n_cands; j += blockDim.x) {
+        if (!alive[j]) continue;
+        float s = 0.f;
+        for (unsigned int i = 0; i < n_cur; i++)
+            s = __fadd_rn(s, pair_distance<0>(cur + (size_t)i * dim, cands + (size_t)j * dim, dim, mode, w_or_m));
+        if (s < best || bi == 0xffffffffu) { best = s; bi = j; }  // first minimum: j ascending per thread
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const unsigned int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi != 0xffffffffu && (bi == 0xffffffffu || ov < best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (unsigned int w = 1; w < blockDim.x / 32; w++) {
+            const float ov = s_v[w];
+            const unsigned int oi = s_i[w];
+            if (oi != 0xffffffffu && (bi == 0xffffffffu || ov < best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+        }
+        order[step] = bi;
+        alive[bi] = 0;
+        for (int i = 0; i < dim; i++) next_cur[i] = cands[(size_t)bi * dim + i];
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------
+int launch_distance_matrix(const float *rows, unsigned int n_rows, const float *cols, unsigned int n_cols,
+                           int dim, int mode, const float *w_or_m, float *out, cudaStream_t st) {
+    if (n_rows == 0 || n_cols == 0) return 0;
+    dim3 grid((n_cols + 127u) / 128u, (n_rows + 31u) / 32u);
+    if (dim == 23) distance_matrix_kernel<23><<<grid, 256, 0, st>>>(rows, n_rows, cols, n_cols, mode, w_or_m, out);
+    else if (dim == 20) distance_matrix_kernel<20><<<grid, 256, 0, st>>>(rows, n_rows, cols, n_cols, mode, w_or_m, out);
+    else if (dim <= MAX_DIM) distance_matrix_generic_kernel<<<dim3((n_cols + 255u) / 256u, n_rows), 256, 0, st>>>(rows, n_rows, cols, n_cols, dim, mode, w_or_m, out);
+    else return -1;
+    return 1;
+}
+
+int launch_seed_distance(const float *seeds, unsigned int n_seeds, const float *cands, unsigned int n_cands,
+                         int dim, int mode, const float *w_or_m, float *keys, cudaStream_t st) {
+    if (n_cands == 0) return 0;
+    seed_distance_kernel<<<(n_cands + 255u) / 256u, 256, 0, st>>>(seeds, n_seeds, cands, n_cands, dim, mode,
+                                                                  w_or_m, keys);
+    return 1;
+}
+
+// stable ascending order of keys -> order[]; tmp buffers supplied by the caller
+size_t sort_temp_bytes(unsigned int n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const unsigned long long *)nullptr,
+                                   (unsigned long long *)nullptr, (int)n);
+    return bytes;
+}
+
+int launch_stable_argsort(const float *keys, unsigned int n, unsigned long long *k_in,
+                          unsigned long long *k_out, void *tmp, size_t tmp_bytes, unsigned int *order,
+                          cudaStream_t st) {
+    if (n == 0) return 0;
+    make_sort_keys_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(keys, n, k_in);
+    cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, k_in, k_out, (int)n, 0, 64, st);
+    unpack_order_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(k_out, n, order);
+    return 3;
+}
+
+int launch_nearest_alive(const float *cur, unsigned int n_cur, const float *cands, unsigned int n_cands,
+                         int dim, int mode, const float *w_or_m, unsigned char *alive, unsigned int *order,
+                         unsigned int step, float *next_cur, cudaStream_t st) {
+    nearest_alive_kernel<<<1, 1024, 0, st>>>(cur, n_cur, cands, n_cands, dim, mode, w_or_m, alive, order, step,
+                                             next_cur);
+    return 1;
+}
+
+}  // namespace bliss

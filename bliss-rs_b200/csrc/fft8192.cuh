@@ -1,0 +1,83 @@
+// fft8192.cuh -- shared-memory 8192-point complex FFT used by the chroma STFT kernel:
+// TWO reflect-padded Hann frames per transform (a + i b), 8192 = 16 x 16 x 32,
+// three in-register radix passes over one in-place buffer (decimation in frequency).
+//
+// After pass 3, X[k] with k = k1 + 16*k2 + 256*k3 lives at logical index
+// 512*k1 + 32*k2 + k3.  Logical index i is stored at pad(i) so that every pass
+// and the natural-order gather of the epilogue are bank-conflict free.
+//
+// Replaces the per-frame rustfft call of utils::stft (src/utils.rs:41-61).
+// __host__ __device__ so tests/cpu_emul can run the passes thread by thread.
+#pragma once
+#include "fft_regs.cuh"
+
+namespace bliss {
+namespace f8k {
+
+constexpr int N = 8192;
+constexpr int BUF_CPX = 8192 + 256 + 16;  // pad(8191) + 1 = 8462 -> round up
+BLISS_HD int pad(int i) { return i + (i >> 5) + (i >> 9); }
+BLISS_HD int xpos(int k) { return 512 * (k & 15) + 32 * ((k >> 4) & 15) + (k >> 8); }
+
+// pass 1: butterfly b in [0,512): v[q] = z[b + 512 q] supplied by the caller
+BLISS_HD void pass1_store(int b, cpx (&v)[16], const cpx *tw /*[8192]*/, cpx *buf) {
+    fft_dif<16>(v);
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        const int k1 = bitrev(s, 4);
+        cpx o = v[s];
+        if (k1 != 0) o = cmul(o, tw[b * k1]);
+        buf[pad(b + 512 * k1)] = o;
+    }
+}
+
+// pass 2: butterfly b in [0,512): block = b>>5 (k1), j = b&31; radix 16 at stride 32
+BLISS_HD void pass2(int b, const cpx *tw, cpx *buf) {
+    const int blk = b >> 5, j = b & 31;
+    const int base = blk * 512 + j;
+    cpx v[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) v[q] = buf[pad(base + 32 * q)];
+    fft_dif<16>(v);
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        const int k2 = bitrev(s, 4);
+        cpx o = v[s];
+        if (k2 != 0) o = cmul(o, tw[16 * j * k2]);
+        buf[pad(base + 32 * k2)] = o;
+    }
+}
+
+// pass 3: butterfly b in [0,256): 32 consecutive logical elements, no twiddle
+BLISS_HD void pass3(int b, cpx *buf) {
+    cpx v[32];
+#pragma unroll
+    for (int q = 0; q < 32; q++) v[q] = buf[pad(32 * b + q)];
+    fft_dif<32>(v);
+#pragma unroll
+    for (int s = 0; s < 32; s++) buf[pad(32 * b + bitrev(s, 5))] = v[s];
+}
+
+// magnitudes of the two real frames packed in Z: see pv::untangle_mag
+BLISS_HD void untangle_mag(cpx zk, cpx zm, float &magA, float &magB) {
+    const float ar = 0.5f * (zk.x + zm.x), ai = 0.5f * (zk.y - zm.y);
+    const float br = 0.5f * (zk.y + zm.y), bi = 0.5f * (zm.x - zk.x);
+#ifdef __CUDA_ARCH__
+    magA = __fsqrt_rn(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
+    magB = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
+#else
+    magA = sqrtf(ar * ar + ai * ai);
+    magB = sqrtf(br * br + bi * bi);
+#endif
+}
+
+// reflect-padded sample (utils.rs:11-24): padded index p in [0, n + 8192)
+BLISS_HD float padded_sample(const float *x, int n, long long p) {
+    long long idx = p - 4096;
+    if (idx < 0) idx = -idx;
+    else if (idx >= n) idx = 2ll * (n - 1) - idx;
+    return x[idx];
+}
+
+}  // namespace f8k
+}  // namespace bliss

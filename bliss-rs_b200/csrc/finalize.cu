@@ -1,0 +1,123 @@
+// finalize.cu -- K9: per-song summariser.  One CTA per song turns the per-frame
+// arrays into the 23 (v2) / 20 (v1) floats of Analysis, in the order of
+// src/song/mod.rs:493-498:
+//   [tempo, zcr, centroid(mean,std), rolloff(mean,std), flatness(mean,std),
+//    loudness(mean,std), chroma x13 (x10 for v1)]
+// Restates SpectralDesc::get_* (timbral.rs:57-122), ZeroCrossingRateDesc::get_value
+// (:248-252), LoudnessDesc::get_value (misc.rs:51-65), ChromaDesc::get_values
+// (chroma.rs:97-132).  Means / population std-devs are accumulated in f64 (the
+// reference's f32 running sums are themselves only ~1e-6 accurate).
+#include "common.cuh"
+
+namespace bliss {
+
+constexpr int K9_THREADS = 256;
+
+__device__ double block_sum(double v, double *s_tmp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.;
+#pragma unroll
+    for (int w = 0; w < K9_THREADS / 32; w++) t += s_tmp[w];
+    return t;
+}
+
+__device__ void mean_std(const float *v, unsigned int n, double *s_tmp, float &mean_f, float &std_f) {
+    double s = 0.;
+    for (unsigned int i = threadIdx.x; i < n; i += K9_THREADS) s += (double)v[i];
+    const double mean = block_sum(s, s_tmp) / (double)n;
+    double q = 0.;
+    for (unsigned int i = threadIdx.x; i < n; i += K9_THREADS) {
+        const double d = (double)v[i] - mean;
+        q += d * d;
+    }
+    const double var = block_sum(q, s_tmp) / (double)n;
+    mean_f = (float)mean;
+    std_f = (float)sqrt(var);
+}
+
+// utils.rs:70-77
+__device__ __forceinline__ float normalize(float value, float min_v, float max_v) {
+    return 2.f * (value - min_v) / (max_v - min_v) - 1.f;
+}
+
+__global__ void __launch_bounds__(K9_THREADS)
+finalize_kernel(const SongDesc *__restrict__ songs, const float *__restrict__ centroid,
+                const float *__restrict__ rolloff, const float *__restrict__ flatness,
+                const float *__restrict__ loud_ms, const unsigned int *__restrict__ zcr_count,
+                const float *__restrict__ tempo_feature, const double *__restrict__ tile_partials,
+                int version, float *__restrict__ out, unsigned int out_base) {
+    __shared__ double s_tmp[K9_THREADS / 32];
+    __shared__ double s_feat[10];
+    const SongDesc sd = songs[blockIdx.x];
+    const int dim = version == 1 ? 20 : 23;
+    float *o = out + ((size_t)out_base + blockIdx.x) * dim;
+    if (!sd.valid) {
+        if (threadIdx.x < dim) o[threadIdx.x] = 0.f;
+        return;
+    }
+    float m, s;
+    const float half_sr = (float)SAMPLE_RATE / 2.f;
+    mean_std(centroid + sd.s_off, sd.n_s, s_tmp, m, s);
+    if (threadIdx.x == 0) { o[2] = normalize(m, 0.f, half_sr); o[3] = normalize(s, 0.f, half_sr); }
+    mean_std(rolloff + sd.s_off, sd.n_s, s_tmp, m, s);
+    if (threadIdx.x == 0) { o[4] = normalize(m, 0.f, half_sr); o[5] = normalize(s, 0.f, half_sr); }
+    mean_std(flatness + sd.s_off, sd.n_s, s_tmp, m, s);
+    if (threadIdx.x == 0) {  // timbral.rs:104-122
+        o[6] = 2.f * (m - 0.f) / (1.f - 0.f) - 1.f;
+        o[7] = 2.f * (s - 0.f) / (1.f - 0.f) - 1.f;
+    }
+    mean_std(loud_ms + sd.l_off, sd.n_l, s_tmp, m, s);
+    if (threadIdx.x == 0) {  // misc.rs:51-65
+        if (m < 1e-9f) m = 1e-9f;
+        if (s < 1e-9f) s = 1e-9f;
+        o[8] = normalize(10.0f * log10f(m), -90.f, 0.f);
+        o[9] = normalize(10.0f * log10f(s), -90.f, 0.f);
+        o[0] = tempo_feature[blockIdx.x];
+        o[1] = normalize((float)zcr_count[blockIdx.x] / (float)sd.n, 0.f, 1.f);
+    }
+    // chroma: mean over frames of the interval features (chroma.rs:154)
+    const unsigned int n_tiles = (sd.n_c + 127u) / 128u;
+    if (threadIdx.x < 10) {
+        double acc = 0.;
+        for (unsigned int t = 0; t < n_tiles; t++) acc += tile_partials[((size_t)sd.c_tile_off + t) * 10 + threadIdx.x];
+        s_feat[threadIdx.x] = acc / (double)sd.n_c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float *c = o + 10;
+        if (version == 1) {  // chroma.rs:128-132
+            for (int i = 0; i < 10; i++) c[i] = 2.f * ((float)s_feat[i] - 0.f) / (0.12f - 0.f) - 1.f;
+        } else {  // chroma.rs:97-126
+            double f[10];
+            for (int i = 0; i < 10; i++) f[i] = s_feat[i];
+            double n1 = 0., n2 = 0.;
+            for (int i = 0; i < 6; i++) n1 += f[i] * f[i];
+            for (int i = 6; i < 10; i++) n2 += f[i] * f[i];
+            n1 = sqrt(n1);
+            n2 = sqrt(n2);
+            if (n1 > 0.) for (int i = 0; i < 6; i++) f[i] /= n1;
+            if (n2 > 0.) for (int i = 6; i < 10; i++) f[i] /= n2;
+            for (int i = 0; i < 10; i++) c[i] = normalize((float)f[i], 0.f, 1.f);
+            c[10] = fminf(2.f * ((float)n1 - 0.f) / (0.25f - 0.f) - 1.f, 1.f);
+            c[11] = fminf(2.f * ((float)n2 - 0.f) / (0.025f - 0.f) - 1.f, 1.f);
+            const double angle = atan2(20. * n2, n1 + 1e-12);
+            c[12] = 2.f * ((float)angle - 0.f) / (1.57079637050628662f - 0.f) - 1.f;
+        }
+    }
+}
+
+int launch_finalize(const SongDesc *songs, int n_songs, const float *centroid, const float *rolloff,
+                    const float *flatness, const float *loud_ms, const unsigned int *zcr_count,
+                    const float *tempo_feature, const double *tile_partials, int version, float *out,
+                    unsigned int out_base, cudaStream_t st) {
+    if (n_songs == 0) return 0;
+    finalize_kernel<<<n_songs, K9_THREADS, 0, st>>>(songs, centroid, rolloff, flatness, loud_ms, zcr_count,
+                                                    tempo_feature, tile_partials, version, out, out_base);
+    return 1;
+}
+
+}  // namespace bliss

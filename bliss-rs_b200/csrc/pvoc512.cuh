@@ -1,0 +1,87 @@
+// pvoc512.cuh -- one warp transforms TWO consecutive 512-sample phase-vocoder
+// frames (timbral frames 2j and 2j+1; the latter is tempo frame j) as ONE complex
+// 512-point FFT: z[n] = w[n] * (xA[n] + i xB[n]).
+//
+//   512 = 16 (in-register, over n1) x 32 (16 in-register + one shuffle radix-2, over n2)
+//   n = n2 + 32*n1,   k = k1 + 16*k2
+//
+// Replaces, per frame: PVoc::do_ (src/aubio.rs:182-264) and PVocTempo::do_
+// (:338-425).  aubio's fvec_shift (:219-229) multiplies bin k by (-1)^k, which
+// leaves every magnitude -- the only thing either caller keeps -- unchanged, so
+// it is dropped here.
+//
+// The phase functions are __host__ __device__ and take the lane explicitly so
+// tests/cpu_emul can run all 32 "lanes" of a warp in a loop on the host.
+#pragma once
+#include "fft_regs.cuh"
+
+namespace bliss {
+namespace pv {
+
+constexpr int ROW = 33;                       // padded row (float2 units) of the 16x32 exchange tile
+constexpr int EXCH_CPX = 584;                 // >= max(16*33, zpos(511)+1 = 575)
+BLISS_HD int zpos(int k) { return k + (k >> 3); }   // padded natural-order position of bin k
+
+// Phase A (lane = n2): r[n1] = z[lane + 32*n1]; radix-16 over n1, twiddle
+// W512^(lane*k1), scatter to S[k1][lane].
+BLISS_HD void phase_a(int lane, cpx (&r)[16], const cpx *twA, cpx *S) {
+    fft_dif<16>(r);
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int k1 = bitrev(q, 4);
+        cpx v = r[q];
+        if (k1 != 0) v = cmul(v, twA[k1 * 32 + lane]);
+        S[k1 * ROW + lane] = v;
+    }
+}
+
+// Phase B, lane = p*16 + k1: gather the parity-p half of row k1.
+BLISS_HD void phase_b_load(int lane, cpx (&u)[16], const cpx *S) {
+    const int k1 = lane & 15, p = lane >> 4;
+#pragma unroll
+    for (int j = 0; j < 16; j++) u[j] = S[k1 * ROW + 2 * j + p];
+}
+
+template <int Q>
+BLISS_HD void tw32_all(cpx (&u)[16]) {
+    if constexpr (Q < 16) {
+        u[Q] = mul_tw<bitrev(Q, 4), 32>(u[Q]);
+        tw32_all<Q + 1>(u);
+    }
+}
+
+// radix-16 over n2' then (odd half only) the W32^k2' twiddle of the final radix-2.
+BLISS_HD void phase_b_fft(int lane, cpx (&u)[16]) {
+    fft_dif<16>(u);
+    if (lane >> 4) tw32_all<0>(u);
+}
+
+// final radix-2 between lane (0,k1) and lane (1,k1): `other` is the partner's value
+// of the same slot.  Even half keeps F0 + W F1 (k2 = k2'), odd half F0 - W F1 (k2 = k2'+16).
+BLISS_HD cpx phase_b_combine(int lane, cpx own, cpx other) {
+    return (lane >> 4) ? csub(other, own) : cadd(own, other);
+}
+
+// bin index held in slot q of lane after the combine
+BLISS_HD int bin_of(int lane, int q) {
+    const int k1 = lane & 15, p = lane >> 4;
+    return k1 + 16 * (bitrev(q, 4) + 16 * p);
+}
+
+// Untangle the two real spectra from Z (complex FFT of a + i b):
+//   A[k] = (Z[k] + conj Z[N-k]) / 2,   B[k] = (Z[k] - conj Z[N-k]) / (2i)
+// and return their magnitudes as `(re*re + im*im).sqrt()` (aubio.rs:248-252).
+BLISS_HD void untangle_mag(cpx zk, cpx zm, float &magA, float &magB) {
+    const float ar = 0.5f * (zk.x + zm.x), ai = 0.5f * (zk.y - zm.y);
+    const float br = 0.5f * (zk.y + zm.y), bi = 0.5f * (zm.x - zk.x);
+#ifdef __CUDA_ARCH__
+    magA = __fsqrt_rn(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
+    magB = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
+#else
+    magA = sqrtf(ar * ar + ai * ai);
+    magB = sqrtf(br * br + bi * bi);
+#endif
+}
+
+}  // namespace pv
+}  // namespace bliss

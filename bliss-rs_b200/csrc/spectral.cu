@@ -1,0 +1,353 @@
+// spectral.cu -- K1: fused 512-point phase-vocoder kernel (timbral descriptors +
+// tempo spectral flux) and K2: time-domain reductions (ZCR, loudness, block energy).
+//
+// K1 replaces, for every song of the wave:
+//   PVoc::do_ / PVocTempo::do_            src/aubio.rs:182-264, 338-425
+//   spectral_centroid / spectral_rolloff  src/aubio.rs:16-58  (+ clamp timbral.rs:184-187)
+//   geometric_mean + flatness             src/utils.rs:101-117, src/timbral.rs:196-208
+//   SpecFlux::do_                         src/aubio.rs:455-467
+// driven as Song::analyze_with_options drives them (src/song/mod.rs:433-468).
+//
+// Data movement: each warp walks a run of consecutive frame pairs of one song and
+// keeps a sliding window of 20 samples per lane in registers, so every PCM sample
+// is fetched from HBM once per run (plus a one-pair halo) with fully coalesced
+// 128-byte warp loads; nothing but 3 floats per frame and 1 float per tempo
+// frame is written back.
+#include "common.cuh"
+#include "pvoc512.cuh"
+
+namespace bliss {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_prod(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ cpx shfl_xor_cpx(cpx v, int m) {
+    return cpx{__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m)};
+}
+
+// lower_bound over the per-song item prefix: largest s with prefix[s] <= item
+__device__ __forceinline__ int find_song(const unsigned int *prefix, int n_songs, unsigned int item) {
+    int lo = 0, hi = n_songs;  // prefix has n_songs+1 entries
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= item) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Per-frame descriptors from the 8 consecutive norms a lane holds (bins 8*lane..8*lane+7).
+// Returns centroid (Hz), rolloff (Hz), flatness to lane 0 (all lanes compute them).
+__device__ __forceinline__ void frame_descriptors(const float (&v)[8], int lane, float &centroid,
+                                                  float &rolloff, float &flatness) {
+    float s1 = 0.f, sw = 0.f;
+    float c[8];
+    float run = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        s1 += v[i];
+        sw += (float)(8 * lane + i) * v[i];
+        run += v[i] * v[i];
+        c[i] = run;
+    }
+    // geometric_mean's per-group product, utils.rs:104-111 (one 8-group per lane)
+    double m = ((double)v[0] * (double)v[1]) * ((double)v[2] * (double)v[3]);
+    m *= 3.273390607896142e150;
+    m *= ((double)v[4] * (double)v[5]) * ((double)v[6] * (double)v[7]);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+    const int zero = __any_sync(0xffffffffu, m == 0.0);
+    int ex = (int)(bits >> 52);
+    double mant = __longlong_as_double((long long)((bits & 0xFFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
+    ex = __reduce_add_sync(0xffffffffu, ex);
+    mant = warp_prod(mant);
+
+    s1 = warp_sum(s1);
+    sw = warp_sum(sw);
+    // inclusive scan of the per-lane energy for the roll-off search (aubio.rs:36-58)
+    float incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const float total = __shfl_sync(0xffffffffu, incl, 31);
+    const float excl = incl - run;
+    const float thr = total * 0.95f;
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) cnt += ((excl + c[i]) < thr) ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    const float freq = (float)SAMPLE_RATE / 512.f;  // bin_to_freq, aubio.rs:68-71
+    float bin = (total == 0.f) ? 0.f : (float)min(cnt + 1, 256);
+    rolloff = freq * bin;
+    centroid = (s1 == 0.f) ? 0.f : freq * fmaxf(sw / s1, 0.f);
+    if (zero) {
+        flatness = 0.f;
+    } else {
+        const float gm = exp2f((log2f((float)mant) + (float)ex) / 256.f - (1023.f + 500.f) / 8.f);
+        flatness = gm / (s1 / 256.f);
+    }
+}
+
+// WITH_DESC: timbral descriptors + flux (the analysis path).
+// WITH_MAGS: materialise the 257 tempo-frame magnitudes (STFT micro-benchmark,
+//            BASELINE.json config 3 = PVocTempo framing: 512 / hop 256).
+template <bool WITH_DESC, bool WITH_MAGS>
+__global__ void __launch_bounds__(256, 2)
+pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
+               const unsigned int *__restrict__ item_prefix, int n_songs, unsigned int total_items,
+               int pairs_per_item, PvocTables tab, float *__restrict__ centroid,
+               float *__restrict__ rolloff, float *__restrict__ flatness, float *__restrict__ flux,
+               float *__restrict__ mags_out) {
+    __shared__ float s_win[512];
+    __shared__ cpx s_twA[16 * 32];
+    __shared__ cpx s_ex[8][pv::EXCH_CPX];
+
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        s_win[i] = tab.win[i];
+        s_twA[i] = tab.twA[i];
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int item = blockIdx.x * 8u + (unsigned)warp;
+    if (item >= total_items) return;
+    const int si = find_song(item_prefix, n_songs, item);
+    const SongDesc sd = songs[si];
+    const int j0 = (int)(item - item_prefix[si]) * pairs_per_item;
+    const int j1 = min(j0 + pairs_per_item, (int)sd.n_t);
+    const float *x = pcm + sd.pcm_off;
+    const int n = (int)sd.n;
+    cpx *S = s_ex[warp];
+
+    float win_a[16];  // w[lane + 32*n1]
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) win_a[n1] = s_win[lane + 32 * n1];
+
+    float old[8];  // previous tempo frame's magnitudes of this lane's bins
+#pragma unroll
+    for (int i = 0; i < 8; i++) old[i] = 0.f;
+    float old256 = 0.f;
+
+    float s[20];  // s[m] = x[256*j - 384 + lane + 32*m]
+    const int jstart = (j0 > 0) ? j0 - 1 : j0;  // halo pair: only to seed `old`
+    {
+        const int base = 256 * jstart - 384 + lane;
+#pragma unroll
+        for (int m = 0; m < 12; m++) {
+            const int idx = base + 32 * m;
+            s[m + 8] = (idx >= 0 && idx < n) ? __ldg(x + idx) : 0.f;
+        }
+    }
+    for (int j = jstart; j < j1; j++) {
+        // slide the window by 256 samples and fetch the 8 new rows
+#pragma unroll
+        for (int m = 0; m < 12; m++) s[m] = s[m + 8];
+        {
+            const int base = 256 * j - 384 + lane + 32 * 12;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int idx = base + 32 * m;
+                s[12 + m] = (idx >= 0 && idx < n) ? __ldg(x + idx) : 0.f;
+            }
+        }
+        cpx r[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) r[n1] = cpx{win_a[n1] * s[n1], win_a[n1] * s[n1 + 4]};
+        pv::phase_a(lane, r, s_twA, S);
+        __syncwarp();
+        pv::phase_b_load(lane, r, S);
+        __syncwarp();
+        pv::phase_b_fft(lane, r);
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const cpx o = shfl_xor_cpx(r[q], 16);
+            const cpx z = pv::phase_b_combine(lane, r[q], o);
+            S[pv::zpos(pv::bin_of(lane, q))] = z;
+        }
+        __syncwarp();
+        // natural-order epilogue: lane owns bins 8*lane .. 8*lane+7 of both frames
+        float ma[8], mb[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int k = 8 * lane + i;
+            const cpx zk = S[pv::zpos(k)];
+            const cpx zm = S[pv::zpos((512 - k) & 511)];
+            pv::untangle_mag(zk, zm, ma[i], mb[i]);
+        }
+        const cpx zn = S[pv::zpos(256)];  // Nyquist: A = |Re|, B = |Im|
+        const float nyq_a = fabsf(zn.x), nyq_b = fabsf(zn.y);
+        if (lane == 0) {  // DC: abs(re), aubio.rs:240 / :403
+            const cpx z0 = S[0];
+            ma[0] = fabsf(z0.x);
+            mb[0] = fabsf(z0.y);
+        }
+        __syncwarp();  // S is rewritten by the next pair's phase A
+
+        const bool emit = (j >= j0);
+        if (WITH_MAGS && emit) {
+            float *o = mags_out + ((size_t)sd.t_off + (size_t)j) * 257u;
+#pragma unroll
+            for (int i = 0; i < 8; i++) o[8 * lane + i] = mb[i];
+            if (lane == 31) o[256] = nyq_b;
+        }
+        if (WITH_DESC) {
+            // SpecFlux over the 257 correct bins of the tempo frame (aubio.rs:455-467)
+            float fl = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                fl += (mb[i] > old[i]) ? (mb[i] - old[i]) : 0.f;
+                old[i] = mb[i];
+            }
+            if (lane == 31) {
+                fl += (nyq_b > old256) ? (nyq_b - old256) : 0.f;
+                old256 = nyq_b;
+            }
+            fl = warp_sum(fl);
+            if (emit) {
+                if (lane == 0) flux[sd.t_off + j] = fl;
+                // timbral norms: the 256-bin cvec with Nyquist stored in slot 255 (aubio.rs:255-261)
+                if (lane == 31) {
+                    ma[7] = nyq_a;
+                    mb[7] = nyq_b;
+                }
+                float c, ro, fa;
+                const int fa_idx = 2 * j, fb_idx = 2 * j + 1;
+                if (fa_idx < (int)sd.n_s) {
+                    frame_descriptors(ma, lane, c, ro, fa);
+                    if (lane == 0) {
+                        centroid[sd.s_off + fa_idx] = c;
+                        rolloff[sd.s_off + fa_idx] = ro;
+                        flatness[sd.s_off + fa_idx] = fa;
+                    }
+                }
+                if (fb_idx < (int)sd.n_s) {
+                    frame_descriptors(mb, lane, c, ro, fa);
+                    if (lane == 0) {
+                        centroid[sd.s_off + fb_idx] = c;
+                        rolloff[sd.s_off + fb_idx] = ro;
+                        flatness[sd.s_off + fb_idx] = fa;
+                    }
+                }
+            }
+        } else if (WITH_MAGS) {
+            (void)nyq_a;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: one warp per 1024-sample loudness chunk.
+//   number_crossings        src/utils.rs:81-95      (one call over the whole song, song/mod.rs:470-474)
+//   level_lin per chunk     src/misc.rs:12-18       (chunks(1024) incl. short tail, song/mod.rs:478)
+//   256-sample block energy -> silence test of Tempo::do_ (aubio.rs:1258-1276, :1431)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+timedomain_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
+                  const unsigned int *__restrict__ chunk_prefix, int n_songs,
+                  unsigned int total_chunks, float *__restrict__ loud_ms,
+                  float *__restrict__ block_energy, unsigned int *__restrict__ zcr_count) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int item = blockIdx.x * 8u + (unsigned)warp;
+    if (item >= total_chunks) return;
+    const int si = find_song(chunk_prefix, n_songs, item);
+    const SongDesc sd = songs[si];
+    const unsigned int ch = item - chunk_prefix[si];
+    const float *x = pcm + sd.pcm_off;
+    const unsigned int n = sd.n;
+    const unsigned int base = ch * 1024u;
+    const unsigned int len = min(1024u, n - base);
+
+    float eb[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned int crossings = 0;
+    float prev_tail = (base > 0) ? __ldg(x + base - 1) : 0.f;  // lane 31's last sample of the previous row
+    const bool has_prev = base > 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const unsigned int p = 4u * lane + 128u * k;
+        float v[4];
+        if (p + 4 <= len && ((sd.pcm_off + base + p) & 3ull) == 0) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(x + base + p));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = (p + i < len) ? __ldg(x + base + p + i) : 0.f;
+        }
+        float e = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) e += v[i] * v[i];
+        eb[k >> 1] += e;
+        // predecessor of v[0]: previous lane's v[3]; lane 0 takes the previous row's tail
+        float pred = __shfl_up_sync(0xffffffffu, v[3], 1);
+        if (lane == 0) pred = prev_tail;
+        const bool first_of_song = (base + p == 0);
+        const bool have_pred = (k > 0) || (lane > 0) || has_prev;
+        float before = pred;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (p + i < len) {
+                const bool valid_pair = (i > 0) || (have_pred && !first_of_song);
+                if (valid_pair && ((before > 0.f) != (v[i] > 0.f))) crossings++;
+            }
+            before = v[i];
+        }
+        prev_tail = __shfl_sync(0xffffffffu, v[3], 31);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; b++) eb[b] = warp_sum(eb[b]);
+    crossings = __reduce_add_sync(0xffffffffu, crossings);
+    if (lane == 0) {
+        loud_ms[sd.l_off + ch] = (eb[0] + eb[1] + eb[2] + eb[3]) / (float)len;
+        if (crossings) atomicAdd(zcr_count + si, crossings);
+    }
+    if (lane < 4) {
+        const unsigned int blk = ch * 4u + lane;
+        if ((blk + 1u) * 256u <= n) {
+            const float e = lane == 0 ? eb[0] : lane == 1 ? eb[1] : lane == 2 ? eb[2] : eb[3];
+            block_energy[sd.e_off + blk] = e;
+        }
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------
+int launch_pvoc512(const float *pcm, const SongDesc *songs, const unsigned int *item_prefix, int n_songs,
+                   unsigned int total_items, int pairs_per_item, PvocTables tab, float *centroid,
+                   float *rolloff, float *flatness, float *flux, cudaStream_t st) {
+    if (total_items == 0) return 0;
+    const unsigned int grid = (total_items + 7u) / 8u;
+    pvoc512_kernel<true, false><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
+                                                      pairs_per_item, tab, centroid, rolloff, flatness,
+                                                      flux, nullptr);
+    return 1;
+}
+
+int launch_stft512_mags(const float *pcm, const SongDesc *songs, const unsigned int *item_prefix,
+                        int n_songs, unsigned int total_items, int pairs_per_item, PvocTables tab,
+                        float *mags, cudaStream_t st) {
+    if (total_items == 0) return 0;
+    const unsigned int grid = (total_items + 7u) / 8u;
+    pvoc512_kernel<false, true><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
+                                                      pairs_per_item, tab, nullptr, nullptr, nullptr,
+                                                      nullptr, mags);
+    return 1;
+}
+
+int launch_timedomain(const float *pcm, const SongDesc *songs, const unsigned int *chunk_prefix,
+                      int n_songs, unsigned int total_chunks, float *loud_ms, float *block_energy,
+                      unsigned int *zcr_count, cudaStream_t st) {
+    if (total_chunks == 0) return 0;
+    const unsigned int grid = (total_chunks + 7u) / 8u;
+    timedomain_kernel<<<grid, 256, 0, st>>>(pcm, songs, chunk_prefix, n_songs, total_chunks, loud_ms,
+                                            block_energy, zcr_count);
+    return 1;
+}
+
+}  // namespace bliss

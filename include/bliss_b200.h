@@ -1,0 +1,155 @@
+/*
+ * bliss_b200.h -- C ABI of the B200-native implementation of bliss-rs's per-song
+ * analysis hot path (Song::analyze over decoded mono f32 22 050 Hz PCM) and of its
+ * feature-vector distances.  This is the drop-in boundary: the entry points below are
+ * what a `#[cfg(feature = "b200")]` build of the crate binds through `extern "C"`
+ * (see INTEGRATION.md for the Rust side).  Plain pointers and sizes only.
+ *
+ * bliss-rs has no FFI / plugin interface of its own: the seam is
+ * the Rust API.  Each entry point cites the Rust item whose body it replaces, paths
+ * relative to the reference checkout (crate bliss-audio 0.13.0).
+ *
+ * Threading: every function is thread-safe; calls on one process serialise on an
+ * internal lock per device context (the reference calls Song::analyze from `cores`
+ * worker threads, src/song/decoder.rs:304-329 -- those workers should instead hand
+ * their decoded buffers to ONE bliss_b200_analyze_batch call).
+ * Ownership: inputs are borrowed for the duration of the call and never written;
+ * outputs are caller-allocated.
+ */
+#ifndef BLISS_B200_H
+#define BLISS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes of the calls ------------------------------------------------ */
+#define BLISS_B200_OK 0
+#define BLISS_B200_E_CUDA (-1)     /* a CUDA runtime call failed; see bliss_b200_last_error() */
+#define BLISS_B200_E_ARG (-2)      /* bad argument (null pointer, misaligned device buffer, bad version ...) */
+#define BLISS_B200_E_NOT_INIT (-3) /* bliss_b200_init() has not been called */
+#define BLISS_B200_E_NOMEM (-4)    /* one song alone does not fit the workspace limit */
+#define BLISS_B200_E_NO_DEVICE (-5) /* no usable CUDA device: there is NO CPU fallback */
+
+/* ---- per-song status (BlissResult<Analysis>) ------------------------------------ */
+#define BLISS_B200_SONG_OK 0
+/* BlissError::AnalysisError("empty or too short song."), src/song/mod.rs:417-430 */
+#define BLISS_B200_SONG_TOO_SHORT 1
+#define BLISS_B200_SONG_INTERNAL 2
+
+/* FeaturesVersion, src/lib.rs:151-186: 2 = Version2 (LATEST, 23 floats), 1 = Version1 (20) */
+#define BLISS_B200_FEATURES_V1 1
+#define BLISS_B200_FEATURES_V2 2
+#define BLISS_B200_SAMPLE_RATE 22050 /* src/lib.rs:143 */
+
+/* Binds this process to CUDA device `device` (>= 0), builds the constant tables
+ * (windows, twiddles, the 100 chroma filterbanks of src/chroma.rs:197-267).
+ * Idempotent for the same device.  Fails with E_NO_DEVICE when no GPU is present. */
+int bliss_b200_init(int device);
+void bliss_b200_shutdown(void);
+/* Upper bound on device scratch memory a call may hold (default: 40% of the device). */
+int bliss_b200_set_workspace_limit(uint64_t bytes);
+
+const char *bliss_b200_strerror(int code);
+const char *bliss_b200_last_error(void);
+/* FeaturesVersion::feature_count, src/lib.rs:181-186 (0 for an unknown version) */
+uint32_t bliss_b200_feature_count(uint16_t features_version);
+
+/* Song::analyze_with_options(sample_array, options), src/song/mod.rs:413-508.
+ * `pcm`: n host floats, mono, 22 050 Hz.  `out`: feature_count floats.
+ * Returns a per-song status (>= 0) or a negative call error. */
+int bliss_b200_analyze(const float *pcm, uint64_t n_samples, uint16_t features_version, float *out);
+
+/* The batching seam of Decoder::analyze_paths_with_options (src/song/decoder.rs:278-332):
+ * n_songs decoded buffers in HOST memory (pinned memory copies fastest), analysed together.
+ * out: n_songs x feature_count, row-major.  status: n_songs entries.  One bad song never
+ * fails the batch (like the reference, which sends errors as items, :319-325). */
+int bliss_b200_analyze_batch(const float *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
+                             uint16_t features_version, float *out, int32_t *status);
+
+/* Same, PCM already resident in device memory: song i is d_pcm[offsets[i] .. offsets[i]+n_samples[i]).
+ * d_pcm must be 16-byte aligned; offsets/n_samples/status are HOST arrays; d_out is a DEVICE
+ * buffer (n_songs x feature_count).  Work is enqueued on `cuda_stream` (a cudaStream_t, may be
+ * NULL for the legacy stream) and the call returns without synchronising.  This is also the
+ * form BlissCueFile::get_songs needs (sub-slices of one decoded buffer, src/cue.rs:208-243). */
+int bliss_b200_analyze_batch_device(const float *d_pcm, const uint64_t *offsets,
+                                    const uint64_t *n_samples, uint32_t n_songs,
+                                    uint16_t features_version, float *d_out, int32_t *status,
+                                    void *cuda_stream);
+
+/* ---- distances, src/playlist.rs ---------------------------------------------------- */
+#define BLISS_B200_METRIC_MAHALANOBIS 0 /* sqrt((a-b)^T M (a-b)), playlist.rs:140-142; M NULL = identity = euclidean_distance :65-71 */
+#define BLISS_B200_METRIC_COSINE 2      /* playlist.rs:76-79 */
+
+/* Weight matrix of FeaturesVersion::feature_weights (src/lib.rs:168-173, :209-234): dim x dim */
+int bliss_b200_feature_weights(uint16_t features_version, float *m);
+
+/* One pair (Analysis::distance / Song::distance, src/song/mod.rs:364-370, :519-521 use the
+ * Mahalanobis metric with feature_weights).  Host pointers.  m: dim x dim row-major or NULL. */
+int bliss_b200_distance(const float *a, const float *b, uint32_t dim, int metric, const float *m,
+                        float *out);
+
+/* All pairs: out[i*n_cols + j] = d(rows[i], cols[j]).  Host pointers. */
+int bliss_b200_distance_matrix(const float *rows, uint32_t n_rows, const float *cols, uint32_t n_cols,
+                               uint32_t dim, int metric, const float *m, float *out);
+/* Device pointers for rows / cols / out (m stays a HOST pointer); enqueued on cuda_stream. */
+int bliss_b200_distance_matrix_device(const float *d_rows, uint32_t n_rows, const float *d_cols,
+                                      uint32_t n_cols, uint32_t dim, int metric, const float *m,
+                                      float *d_out, void *cuda_stream);
+
+/* closest_to_songs (src/playlist.rs:256-270): order[] = candidate indices sorted (stably) by the
+ * sum of distances to the seeds (FunctionDistanceMetric::distance, :56-58); keys (optional,
+ * n_cands floats) receives those sums.  Host pointers. */
+int bliss_b200_closest_to_songs(const float *seeds, uint32_t n_seeds, const float *cands,
+                                uint32_t n_cands, uint32_t dim, int metric, const float *m,
+                                uint32_t *order, float *keys);
+/* song_to_song (src/playlist.rs:272-326): greedy nearest-neighbour chain from the seeds. */
+int bliss_b200_song_to_song(const float *seeds, uint32_t n_seeds, const float *cands, uint32_t n_cands,
+                            uint32_t dim, int metric, const float *m, uint32_t *order);
+
+/* ---- STFT micro-benchmark (BASELINE.json config 3) ----------------------------------- */
+/* 512-point hanningz phase-vocoder STFT, hop 256 (= PVocTempo, src/aubio.rs:338-425): writes
+ * 257 magnitudes per frame; frames of song i start at row frame_offsets_out[i] (host array,
+ * n_songs+1 entries, filled by the call).  d_pcm / d_mags are device buffers. */
+int bliss_b200_stft512_mag_device(const float *d_pcm, const uint64_t *offsets, const uint64_t *n_samples,
+                                  uint32_t n_songs, float *d_mags, uint64_t *frame_offsets_out,
+                                  void *cuda_stream);
+
+/* ---- introspection used by tests / bench ------------------------------------------------ */
+/* Intermediate results of ONE song (host PCM).  Any pointer may be NULL.  Capacities are the
+ * caller's business: centroid/rolloff/flatness n_s = (n-512)/128+1 floats, flux/thresholded
+ * n_t = (n-512)/256+1 floats, bpms n_t/16+16 floats, stft8192 n_c x 4097 floats (n_c =
+ * ceil(n/2205)), chroma n_c x 12 doubles, interval_features 10 doubles. */
+typedef struct {
+    float *centroid, *rolloff, *flatness;
+    float *flux, *thresholded, *bpms;
+    uint32_t *n_bpms;
+    float *loudness_chunks; /* ceil(n/1024) */
+    uint32_t *zero_crossings;
+    float *stft8192;
+    uint64_t *n_peaks;   /* pip_track candidate count */
+    double *tuning;
+    double *chroma;
+    double *interval_features;
+} bliss_b200_taps;
+int bliss_b200_analyze_taps(const float *pcm, uint64_t n_samples, uint16_t features_version, float *out,
+                            const bliss_b200_taps *taps);
+
+/* Per-kernel device time (CUDA events on the launching stream) accumulated while profiling is
+ * on.  Kernel ids: 0 pvoc512, 1 timedomain, 2 stft8192, 3 tuning, 4 chroma, 5 peakpick,
+ * 6 beattrack, 7 finalize, 8 distance, 9 stft512_mags. */
+#define BLISS_B200_N_KERNELS 10
+int bliss_b200_set_profiling(int on);
+/* Synchronises the device, then fills ms[k] / launches[k] and resets the accumulators. */
+int bliss_b200_get_profile(double *ms, uint64_t *launches);
+const char *bliss_b200_kernel_name(int kernel_id);
+/* Total number of this library's kernels launched since init. */
+uint64_t bliss_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

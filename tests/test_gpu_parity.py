@@ -1,0 +1,338 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference's
+golden vectors.  Needs a B200: every test is marked gpu.
+
+Tolerances (stated per BASELINE.json north_star: "feature vectors within 1e-4 rel"):
+features live in [-1, 1], so the bar used is |gpu - oracle| <= 1e-4 * max(1, |oracle|) per
+feature; the golden clip is additionally held to the reference's own 1e-5.
+Discrete stages (roll-off bin, tuning bin, BPM list) are compared exactly or by mismatch rate.
+"""
+import numpy as np
+import pytest
+import torch
+
+import bliss_rs_b200 as B
+from bliss_rs_b200 import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _close(got, want, tol=TOL):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.abs(got - want) <= tol * np.maximum(1.0, np.abs(want))
+
+
+def _report(name, got, want):
+    err = np.abs(np.asarray(got, np.float64) - np.asarray(want, np.float64))
+    print("%s: max abs err %.3e (feature %d)" % (name, err.max(), int(err.argmax())))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    B.native.init(0)
+    yield
+
+
+# ---------------------------------------------------------------- golden clip
+def test_golden_clip_v2(pcm_song, golden):
+    a = B.Song.analyze(pcm_song).as_arr1()
+    _report("gpu vs reference golden (v2)", a, golden["expected_analysis_v2"])
+    assert np.abs(a - golden["expected_analysis_v2"]).max() < 1e-5  # src/song/mod.rs:582-591
+    rc, o = O.analyze(pcm_song, 2)
+    assert _close(a, o).all()
+
+
+def test_golden_clip_v1(pcm_song, golden):
+    opts = B.AnalysisOptions(features_version=B.FeaturesVersion.Version1)
+    a = B.Song.analyze_with_options(pcm_song, opts)
+    assert a.features_version == B.FeaturesVersion.Version1 and a.as_arr1().shape == (20,)
+    assert np.abs(a.as_arr1() - golden["expected_analysis_v1"]).max() < 1e-5  # src/song/mod.rs:619-633
+
+
+def test_too_short_is_an_error(pcm_song):
+    # src/song/mod.rs:543-550
+    for n in (0, 1, 8191):
+        with pytest.raises(B.AnalysisError) as e:
+            B.Song.analyze(pcm_song[:n])
+        assert "empty or too short song." in str(e.value)
+    B.Song.analyze(pcm_song[:8192])
+
+
+# ---------------------------------------------------------------- stage by stage
+def _stage_checks(pcm, label):
+    rc, feats, t = B.native.analyze_taps(pcm, 2)
+    assert rc == 0
+    c, r, f = O.timbral_frames(pcm)
+    tv, flux, thr, bpms = O.tempo(pcm, taps=True)
+    # timbral per-frame values
+    assert t["centroid"].shape == c.shape
+    ce = np.abs(t["centroid"] - c) / np.maximum(1.0, np.abs(c))
+    print(label, "centroid max rel err %.2e" % ce.max())
+    assert ce.max() < 1e-4
+    roll_mismatch = np.mean(t["rolloff"] != r)
+    print(label, "rolloff mismatching frames: %.4f%%" % (100 * roll_mismatch))
+    assert roll_mismatch < 2e-3 and np.abs(t["rolloff"] - r).max() <= 2 * 22050 / 512 + 1e-3
+    fe = np.abs(t["flatness"] - f) / np.maximum(1e-3, np.abs(f))
+    print(label, "flatness max rel err %.2e" % fe.max())
+    assert fe.max() < 2e-4
+    # tempo chain
+    fl = np.abs(t["flux"] - flux) / np.maximum(1e-3, np.abs(flux).max())
+    print(label, "flux max err (rel. to max) %.2e" % fl.max())
+    assert fl.max() < 1e-5
+    te = np.abs(t["thresholded"] - thr) / np.maximum(1e-3, np.abs(thr).max())
+    assert te.max() < 1e-5
+    assert len(t["bpms"]) == len(bpms), (len(t["bpms"]), len(bpms))
+    if len(bpms):
+        assert np.abs(np.sort(t["bpms"]) - np.sort(bpms)).max() < 1e-2
+    # time domain
+    assert int(t["zero_crossings"][0]) == O.number_crossings(pcm)
+    # chroma chain
+    S = O.stft(pcm, 8192, 2205)  # [bins, frames]
+    se = np.abs(t["stft8192"].T - S).max() / S.max()
+    print(label, "stft8192 max err (rel. to max) %.2e" % se)
+    assert se < 2e-6
+    ochroma, otuning, ocm = O.chroma(pcm, 2, want_chroma=True)
+    assert abs(t["tuning"][0] - otuning) < 1e-9, (t["tuning"][0], otuning)
+    p, m = O.pip_track(S, 8192)
+    assert abs(int(t["n_peaks"][0]) - p.size) <= max(2, p.size // 2000)
+    ch = np.abs(t["chroma"].T - ocm).max()
+    print(label, "chroma max abs err %.2e" % ch)
+    assert ch < 2e-5
+    oif = O.chroma_interval_features(ocm)
+    assert np.abs(t["interval_features"] - oif).max() < 1e-6
+    rc, o = O.analyze(pcm, 2)
+    _report(label + " features", feats, o)
+    assert _close(feats, o).all()
+
+
+def test_stages_golden_clip(pcm_song):
+    _stage_checks(pcm_song, "golden")
+
+
+def test_stages_piano(pcm_piano):
+    _stage_checks(pcm_piano, "piano")
+
+
+def test_stages_synthetic_music():
+    x = synth.gen_track(7, 3, 22050 * 20).numpy()
+    _stage_checks(x, "synth")
+
+
+# ---------------------------------------------------------------- batches
+def test_ragged_batch_with_bad_songs(pcm_song, pcm_piano):
+    songs = [pcm_song, pcm_piano[:5000], pcm_piano, np.zeros(0, np.float32), pcm_song[:100003],
+             synth.gen_track(1, 0, 22050 * 9 + 17).numpy()]
+    res = B.analyze_batch(songs)
+    ost, ofe = O.analyze_batch(songs, 2, n_threads=4)
+    for i, (r, st) in enumerate(zip(res, ost)):
+        if st == 1:
+            assert isinstance(r, B.AnalysisError)
+        else:
+            assert isinstance(r, B.Analysis), r
+            _report("batch song %d" % i, r.as_arr1(), ofe[i])
+            assert _close(r.as_arr1(), ofe[i]).all()
+    # order independence / no cross-talk between songs of a wave
+    res2 = B.analyze_batch(list(reversed(songs)))
+    for a, b in zip(res, reversed(res2)):
+        if isinstance(a, B.Analysis):
+            assert np.array_equal(a.as_arr1(), b.as_arr1())
+
+
+def test_synthetic_corpus_parity_and_flip_rate():
+    n_tracks = 12
+    lens = [22050 * 30 + 1000 * i for i in range(n_tracks)]
+    songs = [synth.gen_track(11, i, n).numpy() for i, n in enumerate(lens)]
+    st, feats = B.native.analyze_batch(songs, 2)
+    ost, ofe = O.analyze_batch(songs, 2, n_threads=8)
+    assert (st == 0).all() and (ost == 0).all()
+    err = np.abs(feats - ofe)
+    print("corpus max abs err per feature:", np.array2string(err.max(axis=0), precision=1))
+    tempo_flips = int((err[:, 0] > 1e-3).sum())
+    print("tempo decisions differing: %d / %d" % (tempo_flips, n_tracks))
+    assert tempo_flips == 0
+    assert _close(feats, ofe).all()
+
+
+def test_version1_batch(pcm_song, pcm_piano):
+    st, feats = B.native.analyze_batch([pcm_song, pcm_piano], 1)
+    ost, ofe = O.analyze_batch([pcm_song, pcm_piano], 1)
+    assert feats.shape == (2, 20) and _close(feats, ofe).all()
+
+
+def test_small_workspace_forces_many_waves(pcm_song, pcm_piano):
+    songs = [pcm_song, pcm_piano, pcm_song[:60000], pcm_piano[:90001]] * 3
+    st0, f0 = B.native.analyze_batch(songs, 2)
+    B.native.check(B.native.lib().bliss_b200_set_workspace_limit(24 << 20))
+    try:
+        st1, f1 = B.native.analyze_batch(songs, 2)
+    finally:
+        B.native.check(B.native.lib().bliss_b200_set_workspace_limit(60 << 30))
+    assert np.array_equal(st0, st1) and np.array_equal(f0, f1)
+
+
+# ---------------------------------------------------------------- edge cases of the reference tests
+def test_silence_and_constant():
+    z = np.zeros(22050 * 3, np.float32)
+    a = B.Song.analyze(z).as_arr1()
+    rc, o = O.analyze(z, 2)
+    _report("silence", a, o)
+    assert a[0] == -1.0 and a[1] == -1.0  # no beats (temporal.rs:66-70), no crossings
+    assert np.allclose(a[2:8], -1.0) and np.allclose(a[8:10], -1.0)  # timbral.rs / misc.rs boundaries
+    assert _close(a, o).all()
+    ones = np.ones(22050 * 2, np.float32)
+    a = B.Song.analyze(ones).as_arr1()
+    rc, o = O.analyze(ones, 2)
+    assert abs(a[8] - 1.0) < 1e-6 and abs(a[9] + 1.0) < 1e-6  # misc.rs:98-122
+    assert _close(a, o).all()
+
+
+def test_white_noise_and_alternating():
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(22050 * 10) * 0.2).astype(np.float32)
+    a = B.Song.analyze(x).as_arr1()
+    rc, o = O.analyze(x, 2)
+    _report("white noise", a, o)
+    ok = _close(a, o)
+    assert ok[1:].all(), (a, o)   # everything but tempo must agree; noise has no stable beat
+    alt = np.tile(np.array([-1.0, 1.0], np.float32), 22050)
+    a = B.Song.analyze(alt).as_arr1()
+    rc, o = O.analyze(alt, 2)
+    assert _close(a[1:], o[1:]).all() and a[1] > 0.99  # zcr ~ 1 (timbral.rs:279-285)
+
+
+@pytest.mark.parametrize("zeros,ones,reps,expected", [(22000, 100, 100, -0.416853), (6989, 20, 500, 0.86)])
+def test_tempo_click_tracks(zeros, ones, reps, expected):
+    # src/temporal.rs:122-138 and :141-162 (here through the analyze framing)
+    one = np.r_[np.zeros(zeros), np.ones(ones)].astype(np.float32)
+    x = np.tile(one, reps)
+    a = B.Song.analyze(x).as_arr1()
+    o = O.tempo(x)
+    print("click track tempo gpu %.6f oracle %.6f expected %.6f" % (a[0], o, expected))
+    assert abs(a[0] - o) < 1e-4 and abs(a[0] - expected) < 0.02
+
+
+# ---------------------------------------------------------------- full-size property checks
+def test_three_minute_track_matches_oracle():
+    n = 3969000  # BASELINE config: 3 min at 22 050 Hz
+    x = synth.gen_track(3, 1, n).numpy()
+    a = B.Song.analyze(x).as_arr1()
+    rc, o = O.analyze(x, 2)
+    _report("3-min track", a, o)
+    assert _close(a, o).all()
+    # gain invariance of every descriptor except loudness (linearity of the STFT chain)
+    b = B.Song.analyze((x * np.float32(0.5)).astype(np.float32)).as_arr1()
+    keep = [i for i in range(23) if i not in (8, 9)]
+    assert np.abs(a[keep] - b[keep]).max() < 2e-4
+    # idempotence: same input, same bits
+    assert np.array_equal(a, B.Song.analyze(x).as_arr1())
+
+
+# ---------------------------------------------------------------- device-resident API + STFT micro-benchmark path
+def test_device_api_matches_host_api(pcm_song, pcm_piano):
+    songs = [pcm_song, pcm_piano, pcm_song[:7000], pcm_piano[:50001]]
+    offs, total = [], 0
+    for s in songs:
+        offs.append(total)
+        total += (len(s) + 3) // 4 * 4
+    flat = torch.zeros(total, dtype=torch.float32, device="cuda")
+    for o, s in zip(offs, songs):
+        flat[o:o + len(s)] = torch.from_numpy(s).cuda()
+    out = torch.full((len(songs), 23), 7.0, dtype=torch.float32, device="cuda")
+    st = B.native.analyze_batch_device(flat.data_ptr(), offs, [len(s) for s in songs], 2, out.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    hst, hfe = B.native.analyze_batch(songs, 2)
+    assert list(st) == list(hst) == [0, 0, 1, 0]
+    got = out.cpu().numpy()
+    assert np.array_equal(got[[0, 1, 3]], hfe[[0, 1, 3]]) and (got[2] == 0).all()
+
+
+def test_stft512_magnitudes(pcm_song):
+    x = pcm_song[:60000]
+    n_t = (len(x) - 512) // 256 + 1
+    d = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    mags = torch.zeros((n_t, 257), dtype=torch.float32, device="cuda")
+    fo = B.native.stft512_mag_device(d.data_ptr(), [0], [len(x)], mags.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert list(fo) == [0, n_t]
+    want = O.tempo_norms(x)
+    err = np.abs(mags.cpu().numpy() - want).max() / want.max()
+    print("stft512 max err (rel. to max) %.2e" % err)
+    assert err < 1e-6
+
+
+# ---------------------------------------------------------------- distances (bit-exact vs reference tests / oracle)
+def test_distance_known_answers():
+    a20 = np.array([1.0] * 19 + [0.0], np.float32)
+    b = np.array([0.0] * 16 + [1.0, 0.0, 0.0, 0.0], np.float32)
+    assert B.playlist.euclidean_distance(a20, b) == float(np.float32(4.242640687119285))  # playlist.rs:1079-1092
+    assert B.playlist.euclidean_distance([0.5] * 20, [0.5] * 20) == 0.0
+    assert B.playlist.cosine_distance(a20, b) == float(np.float32(0.7705842661294382))    # playlist.rs:1094-1108
+    b2 = np.array([1.0] + [0.0] * 15 + [1.0, 0.0, 0.0, 0.0], np.float32)
+    m = np.diag([1.0, 1.0] + [0.0] * 18).astype(np.float32)
+    assert B.playlist.mahalanobis_distance(a20, b2, m) == 1.0                              # playlist.rs:1009-1024
+    # lib.rs:273-291
+    assert B.FeaturesVersion.Version1.distance_metric()(np.zeros(20), np.ones(20)) == float(np.float32(4.47213595))
+    assert B.FeaturesVersion.Version2.distance_metric()(np.zeros(23), np.ones(23)) == float(np.float32(3.4999998))
+    # song/mod.rs:772-807
+    s1 = B.Song(analysis=B.Analysis(np.zeros(20), B.FeaturesVersion.Version1))
+    s2 = B.Song(analysis=B.Analysis(np.ones(20), B.FeaturesVersion.Version1))
+    assert s1.distance(s2) == float(np.float32(4.472136))
+
+
+def test_distance_matrix_bit_exact_vs_oracle():
+    rng = np.random.default_rng(0)
+    for dim, ver in ((23, 2), (20, 1)):
+        a = rng.uniform(-1, 1, (70, dim)).astype(np.float32)
+        b = rng.uniform(-1, 1, (133, dim)).astype(np.float32)
+        a[3] = b[5]  # an exact duplicate
+        a[4] = b[6] + np.float32(1e-4)  # a near duplicate (dedup threshold territory)
+        w = O.feature_weights(ver)
+        full = (w + 0.01 * rng.uniform(0, 1, w.shape)).astype(np.float32)
+        full = ((full + full.T) / 2).astype(np.float32)
+        for name, metric, m in (("weights", 0, w), ("euclid", 0, None), ("full", 0, full), ("cosine", 2, None)):
+            got = B.native.distance_matrix(a, b, metric, m)
+            want = np.zeros_like(got)
+            for i in range(a.shape[0]):
+                for j in range(b.shape[0]):
+                    want[i, j] = (O.cosine_distance(a[i], b[j]) if metric == 2 else
+                                  O.euclidean_distance(a[i], b[j]) if m is None else
+                                  O.mahalanobis_distance(a[i], b[j], m))
+            assert np.array_equal(got, want), (name, dim, np.abs(got - want).max())
+        assert B.native.distance_matrix(a, b, 0, None)[3, 5] == 0.0
+
+
+def test_closest_to_songs_and_song_to_song():
+    # playlist.rs:1026-1076 test_mahalanobis_distance_with_songs
+    first = B.Song(path="first", analysis=B.Analysis(np.ones(23)))
+    second = B.Song(path="second", analysis=B.Analysis(np.array([1.5, 5, 6, 5, 6, 6] + [1.0] * 17)))
+    third = B.Song(path="third", analysis=B.Analysis(np.array([5.0] + [1.0] * 22)))
+    dist = B.playlist.mahalanobis_distance_builder(np.diag([1.0] + [0.0] * 22))
+    assert [s.path for s in B.playlist.closest_to_songs([first], [third, second], dist)] == ["second", "third"]
+    rng = np.random.default_rng(1)
+    seeds = rng.uniform(-1, 1, (3, 23)).astype(np.float32)
+    cands = rng.uniform(-1, 1, (2000, 23)).astype(np.float32)
+    cands[100] = cands[50]
+    cands[1999] = cands[50]  # ties must keep input order (stable sort, playlist.rs:267-268)
+    w = O.feature_weights(2)
+    order, keys = B.native.closest_to_songs(seeds, cands, 0, w)
+    oorder, okeys = O.closest_to_songs(seeds, cands, w)
+    assert np.array_equal(keys, okeys) and np.array_equal(order, oorder)
+    pos = {int(v): i for i, v in enumerate(order)}
+    assert pos[50] < pos[100] < pos[1999]
+    so = B.native.song_to_song(seeds[:1], cands[:300], 0, w)
+    assert np.array_equal(so, O.song_to_song(seeds[:1], cands[:300], w))
+    pts = [B.Analysis(np.r_[v, np.zeros(22)]) for v in (10.0, 1.0, 3.0, 2.5)]
+    chain = B.playlist.song_to_song([B.Analysis(np.zeros(23))], pts)
+    assert [float(c.as_arr1()[0]) for c in chain] == [1.0, 2.5, 3.0, 10.0]
+
+
+def test_dedup_playlist():
+    # playlist.rs:343-402: consecutive near-duplicates (< 0.05) and same title+artist are dropped
+    def song(v, title=None, artist=None):
+        return B.Song(title=title, artist=artist, analysis=B.Analysis(np.full(23, v, np.float32)))
+    pl = [song(0.0), song(0.001), song(0.5, "t", "a"), song(0.9, "t", "a"), song(0.9), song(0.0)]
+    kept = list(B.playlist.dedup_playlist(pl))
+    assert [float(s.analysis.as_arr1()[0]) for s in kept] == [0.0, 0.5, 0.9, 0.0]

@@ -1,0 +1,98 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every
+symbol include/bliss_b200.h declares, the host mirror keeps the reference's API
+behaviour, and nothing silently falls back to the CPU when no GPU is present."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import bliss_rs_b200 as B
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as G
+    G.build()
+    hdr = open(os.path.join(ROOT, "include", "bliss_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(bliss_b200_[a-z0-9_]+)\s*\(", hdr)))
+    out = subprocess.check_output(["nm", "-D", "--defined-only", B.native.SO_PATH]).decode()
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert declared and set(declared) <= exported
+    assert sorted(B.native.SYMBOLS) == declared
+
+
+def test_sm100a_code_in_library():
+    out = subprocess.check_output(["cuobjdump", "--list-elf", B.native.SO_PATH]).decode()
+    assert "sm_100a" in out
+
+
+def test_feature_count_and_weights_need_no_device():
+    assert B.native.feature_count(2) == 23 and B.native.feature_count(1) == 20
+    assert B.native.feature_count(7) == 0
+    w = B.FeaturesVersion.Version2.feature_weights()  # src/lib.rs:262-271 test_dimensions_weights
+    assert w.shape == (23, 23) and B.FeaturesVersion.Version1.feature_weights().shape == (20, 20)
+    assert w[0, 0] == 0.25 and w[1, 1] == 1.0 and w[10, 10] == np.float32(3.0 / 13.0)
+    assert np.count_nonzero(w - np.diag(np.diag(w))) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback_without_gpu():
+    with pytest.raises(B.native.NativeError):
+        B.Song.analyze(np.zeros(10000, np.float32))
+    with pytest.raises(B.native.NativeError):
+        B.playlist.euclidean_distance(np.zeros(20), np.ones(20))
+
+
+def test_analysis_type_behaviour():
+    # Analysis::new length check, src/song/mod.rs:326-339
+    with pytest.raises(B.ProviderError):
+        B.Analysis([0.0] * 5, B.FeaturesVersion.Version2)
+    a = B.Analysis(np.arange(23) / 10.0, B.FeaturesVersion.LATEST)
+    # index access, src/song/mod.rs:693-697
+    assert a[B.AnalysisIndex.Tempo] == 0.0 and abs(a[B.AnalysisIndex.Chroma13] - 2.2) < 1e-6
+    with pytest.raises(RuntimeError):  # panics in the reference, src/song/mod.rs:276-278
+        a[B.AnalysisIndexv1.Tempo]
+    v1 = B.Analysis(np.zeros(20), B.FeaturesVersion.Version1)
+    with pytest.raises(RuntimeError):  # src/song/mod.rs:365-367
+        a.distance(v1)
+    assert a.as_vec()[1] == pytest.approx(0.1) and a.as_arr1().dtype == np.float32
+    assert "Analysis (Version 2)" in repr(a) and "Tempo" in repr(a)
+    # FeaturesVersion::try_from, src/lib.rs:195-207
+    assert B.FeaturesVersion.try_from(1) == B.FeaturesVersion.Version1
+    with pytest.raises(B.ProviderError):
+        B.FeaturesVersion.try_from(3)
+    assert len(B.AnalysisIndex) == B.NUMBER_FEATURES == 23 and len(B.AnalysisIndexv1) == 20
+
+
+def test_error_strings():
+    assert str(B.AnalysisError("empty or too short song.")) == \
+        "error happened while analyzing file - empty or too short song."
+    L = B.native.load()
+    assert L.bliss_b200_strerror(1) == b"empty or too short song."
+
+
+def test_decoder_trait_batches_errors_as_items(monkeypatch):
+    calls = []
+
+    class Dec(B.Decoder):
+        BATCH_SONGS = 2
+
+        @classmethod
+        def decode(cls, path):
+            if path == "bad":
+                raise B.DecodingError("nope")
+            return B.PreAnalyzedSong(path=path, title=path, sample_array=np.zeros(9000, np.float32))
+
+    def fake_batch(arrays, opts=None):
+        calls.append(len(arrays))
+        return [B.Analysis(np.zeros(23)) for _ in arrays]
+
+    monkeypatch.setattr(B.song, "analyze_batch", fake_batch)
+    got = list(Dec.analyze_paths(["a", "bad", "b", "c"]))
+    assert [p for p, _ in got] == ["bad", "a", "b", "c"]
+    assert isinstance(got[0][1], B.DecodingError) and isinstance(got[1][1], B.Song)
+    assert calls == [2, 1]
