@@ -431,12 +431,11 @@ int prepare_metric(int metric, const float *m, uint32_t dim, cudaStream_t st, in
     if (diag) {
         std::vector<float> w(dim);
         for (uint32_t i = 0; i < dim; i++) w[i] = m[(size_t)i * dim + i];
+        // pageable source: the runtime stages it before returning, so `w` may go out of scope
         CK(cudaMemcpyAsync(g.metric.p, w.data(), dim * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
     } else {
         mode = 1;
         CK(cudaMemcpyAsync(g.metric.p, m, (size_t)dim * dim * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
     }
     d_w = g.metric.as<float>();
     return 0;

@@ -92,44 +92,84 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     const float *x = pcm + sd.pcm_off;
     const int n = (int)sd.n;
 
-    // pass 1 straight from global memory: z[m] = hann[m] * (xA[m] + i xB[m])
+    // Two real frames ride one complex FFT (A in re, B in im).  The untangling leaks
+    // eps*max(|A|,|B|) of rounding noise into the weaker frame, so when the frames differ a lot in
+    // level (digital silence next to sound) they are transformed one after the other instead:
+    // mode 0 = packed, mode 1 = A alone, mode 2 = B alone (CTA-uniform, rare).
     const long long pA = (long long)CH_HOP * fA;
-#pragma unroll 1
-    for (int h = 0; h < 2; h++) {
-        const int b = tid + 256 * h;
-        cpx v[16];
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const int m = b + 512 * q;
-            const float w = __ldg(hann + m);
-            const float a = f8k::padded_sample(x, n, pA + m);
-            const float bb = hasB ? f8k::padded_sample(x, n, pA + CH_HOP + m) : 0.f;
-            v[q] = cpx{a * w, bb * w};
-        }
-        f8k::pass1_store(b, v, tw, buf);
-    }
-    __syncthreads();
-    f8k::pass2(tid, tw, buf);
-    f8k::pass2(tid + 256, tw, buf);
-    __syncthreads();
-    f8k::pass3(tid, buf);
-    __syncthreads();
-
-    // natural-order magnitudes: thread owns bins tid + 256*m, m = 0..16
     float ma[17], mb[17];
+    int mode = 0;
+    for (;;) {
+        float pka = 0.f, pkb = 0.f;
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const int b = tid + 256 * h;
+            cpx v[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int m = b + 512 * q;
+                const float w = __ldg(hann + m);
+                const float a = f8k::padded_sample(x, n, pA + m) * w;
+                const float bb = hasB ? f8k::padded_sample(x, n, pA + CH_HOP + m) * w : 0.f;
+                pka = fmaxf(pka, fabsf(a));
+                pkb = fmaxf(pkb, fabsf(bb));
+                v[q] = (mode == 0) ? cpx{a, bb} : (mode == 1) ? cpx{a, 0.f} : cpx{bb, 0.f};
+            }
+            f8k::pass1_store(b, v, tw, buf);
+        }
+        if (mode == 0 && hasB) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                pka = fmaxf(pka, __shfl_xor_sync(0xffffffffu, pka, o));
+                pkb = fmaxf(pkb, __shfl_xor_sync(0xffffffffu, pkb, o));
+            }
+            if ((tid & 31) == 0) {
+                s_red[0][tid >> 5] = pka;
+                s_red[1][tid >> 5] = pkb;
+            }
+        }
+        __syncthreads();
+        if (mode == 0 && hasB) {
+            float fa = s_red[0][0], fb = s_red[1][0];
+#pragma unroll
+            for (int w = 1; w < K3_THREADS / 32; w++) {
+                fa = fmaxf(fa, s_red[0][w]);
+                fb = fmaxf(fb, s_red[1][w]);
+            }
+            if (fa > 8.f * fb || fb > 8.f * fa) {
+                mode = 1;
+                __syncthreads();  // s_red / buf are about to be rewritten
+                continue;
+            }
+        }
+        f8k::pass2(tid, tw, buf);
+        f8k::pass2(tid + 256, tw, buf);
+        __syncthreads();
+        f8k::pass3(tid, buf);
+        __syncthreads();
+        // natural-order magnitudes: thread owns bins tid + 256*m, m = 0..16
+#pragma unroll
+        for (int m = 0; m < 17; m++) {
+            const int k = tid + 256 * m;
+            float ta = 0.f, tb = 0.f;
+            if (k <= 4096) {
+                const cpx zk = buf[f8k::pad(f8k::xpos(k))];
+                const cpx zm = buf[f8k::pad(f8k::xpos((8192 - k) & 8191))];
+                f8k::untangle_mag(zk, zm, ta, tb);
+            }
+            if (mode != 2) ma[m] = ta;
+            if (mode == 0) mb[m] = tb;
+            if (mode == 2) mb[m] = ta;
+        }
+        if (mode != 1) break;
+        mode = 2;
+        __syncthreads();  // all reads of buf done before the next transform overwrites it
+    }
     float mxa = 0.f, mxb = 0.f;
 #pragma unroll
     for (int m = 0; m < 17; m++) {
-        const int k = tid + 256 * m;
-        ma[m] = 0.f;
-        mb[m] = 0.f;
-        if (k <= 4096) {
-            const cpx zk = buf[f8k::pad(f8k::xpos(k))];
-            const cpx zm = buf[f8k::pad(f8k::xpos((8192 - k) & 8191))];
-            f8k::untangle_mag(zk, zm, ma[m], mb[m]);
-            mxa = fmaxf(mxa, ma[m]);
-            mxb = fmaxf(mxb, mb[m]);
-        }
+        mxa = fmaxf(mxa, ma[m]);
+        mxb = fmaxf(mxb, mb[m]);
     }
     __syncthreads();  // everyone has read buf; reuse it for the magnitudes
     float *sA = reinterpret_cast<float *>(smem_raw);

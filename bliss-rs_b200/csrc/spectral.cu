@@ -159,38 +159,74 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
                 s[12 + m] = (idx >= 0 && idx < n) ? __ldg(x + idx) : 0.f;
             }
         }
-        cpx r[16];
+        // Packing two real frames into one complex FFT leaks eps*max(|A|,|B|) of rounding noise
+        // into the weaker frame.  When the two frames differ a lot in level (digital silence next
+        // to sound, hard onsets) they are transformed one at a time instead (warp-uniform, rare).
+        float pka = 0.f, pkb = 0.f;
 #pragma unroll
-        for (int n1 = 0; n1 < 16; n1++) r[n1] = cpx{win_a[n1] * s[n1], win_a[n1] * s[n1 + 4]};
-        pv::phase_a(lane, r, s_twA, S);
-        __syncwarp();
-        pv::phase_b_load(lane, r, S);
-        __syncwarp();
-        pv::phase_b_fft(lane, r);
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const cpx o = shfl_xor_cpx(r[q], 16);
-            const cpx z = pv::phase_b_combine(lane, r[q], o);
-            S[pv::zpos(pv::bin_of(lane, q))] = z;
+        for (int n1 = 0; n1 < 16; n1++) {
+            pka = fmaxf(pka, fabsf(win_a[n1] * s[n1]));
+            pkb = fmaxf(pkb, fabsf(win_a[n1] * s[n1 + 4]));
         }
-        __syncwarp();
-        // natural-order epilogue: lane owns bins 8*lane .. 8*lane+7 of both frames
+        pka = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pka)));
+        pkb = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pkb)));
+        const bool split = (pka > 8.f * pkb) || (pkb > 8.f * pka);
+        const int npass = split ? 2 : 1;
         float ma[8], mb[8];
+        float nyq_a = 0.f, nyq_b = 0.f;
+#pragma unroll 1
+        for (int pass = 0; pass < npass; pass++) {
+            cpx r[16];
+            const bool second = split && pass == 1;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int k = 8 * lane + i;
-            const cpx zk = S[pv::zpos(k)];
-            const cpx zm = S[pv::zpos((512 - k) & 511)];
-            pv::untangle_mag(zk, zm, ma[i], mb[i]);
+            for (int n1 = 0; n1 < 16; n1++) {
+                const float re = win_a[n1] * (second ? s[n1 + 4] : s[n1]);
+                const float im = split ? 0.f : win_a[n1] * s[n1 + 4];
+                r[n1] = cpx{re, im};
+            }
+            pv::phase_a(lane, r, s_twA, S);
+            __syncwarp();
+            pv::phase_b_load(lane, r, S);
+            __syncwarp();
+            pv::phase_b_fft(lane, r);
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const cpx o = shfl_xor_cpx(r[q], 16);
+                const cpx z = pv::phase_b_combine(lane, r[q], o);
+                S[pv::zpos(pv::bin_of(lane, q))] = z;
+            }
+            __syncwarp();
+            // natural-order epilogue: lane owns bins 8*lane .. 8*lane+7 of both frames
+            float ta[8], tb[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int k = 8 * lane + i;
+                const cpx zk = S[pv::zpos(k)];
+                const cpx zm = S[pv::zpos((512 - k) & 511)];
+                pv::untangle_mag(zk, zm, ta[i], tb[i]);
+            }
+            const cpx zn = S[pv::zpos(256)];  // Nyquist: A = |Re|, B = |Im|
+            if (lane == 0) {  // DC: abs(re), aubio.rs:240 / :403
+                const cpx z0 = S[0];
+                ta[0] = fabsf(z0.x);
+                tb[0] = fabsf(z0.y);
+            }
+            __syncwarp();  // S is rewritten by the next transform's phase A
+            if (!second) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) ma[i] = ta[i];
+                nyq_a = fabsf(zn.x);
+            }
+            if (!split) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) mb[i] = tb[i];
+                nyq_b = fabsf(zn.y);
+            } else if (second) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) mb[i] = ta[i];
+                nyq_b = fabsf(zn.x);
+            }
         }
-        const cpx zn = S[pv::zpos(256)];  // Nyquist: A = |Re|, B = |Im|
-        const float nyq_a = fabsf(zn.x), nyq_b = fabsf(zn.y);
-        if (lane == 0) {  // DC: abs(re), aubio.rs:240 / :403
-            const cpx z0 = S[0];
-            ma[0] = fabsf(z0.x);
-            mb[0] = fabsf(z0.y);
-        }
-        __syncwarp();  // S is rewritten by the next pair's phase A
 
         const bool emit = (j >= j0);
         if (WITH_MAGS && emit) {

@@ -1,0 +1,251 @@
+// bliss_b200.hpp -- C++17 header-only host mirror of the reference crate's API for the
+// Song::analyze + distance path, on top of the C ABI in bliss_b200.h.  The reference is compiled
+// code (Rust); no Rust toolchain exists in the build image, so this is the compiled-language host
+// side a native application links against (the Rust binding itself is in INTEGRATION.md).
+//
+// Names / argument meaning / error behaviour follow:
+//   FeaturesVersion, BlissError            src/lib.rs:151-249
+//   Analysis, AnalysisOptions, Song        src/song/mod.rs:45-521
+//   PreAnalyzedSong, Decoder               src/song/decoder.rs:34-333
+//   distances, closest_to_songs, ...       src/playlist.rs:65-326
+#pragma once
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <utility>
+#include <variant>
+#include <vector>
+
+#include "bliss_b200.h"
+
+namespace bliss {
+
+constexpr uint32_t SAMPLE_RATE = 22050;  // src/lib.rs:143
+constexpr uint16_t CHANNELS = 1;         // src/lib.rs:140
+constexpr size_t NUMBER_FEATURES = 23;   // AnalysisIndex::COUNT
+
+// src/lib.rs:236-249
+struct BlissError : std::runtime_error {
+    enum Kind { DecodingError, AnalysisError, ProviderError } kind;
+    BlissError(Kind k, const std::string &msg) : std::runtime_error(prefix(k) + msg), kind(k) {}
+    static std::string prefix(Kind k) {
+        return k == DecodingError   ? "error happened while decoding file - "
+               : k == AnalysisError ? "error happened while analyzing file - "
+                                    : "error happened with the music library provider - ";
+    }
+};
+
+enum class FeaturesVersion : uint16_t { Version1 = 1, Version2 = 2 };  // src/lib.rs:151-166
+constexpr FeaturesVersion LATEST = FeaturesVersion::Version2;
+inline size_t feature_count(FeaturesVersion v) { return bliss_b200_feature_count(static_cast<uint16_t>(v)); }
+inline std::vector<float> feature_weights(FeaturesVersion v) {  // src/lib.rs:168-173
+    std::vector<float> m(feature_count(v) * feature_count(v));
+    bliss_b200_feature_weights(static_cast<uint16_t>(v), m.data());
+    return m;
+}
+
+namespace detail {
+inline void ensure_init(int device = 0) {
+    static const int rc = bliss_b200_init(device);
+    if (rc != BLISS_B200_OK)
+        throw BlissError(BlissError::AnalysisError, std::string("b200 backend unavailable (no CPU fallback): ") +
+                                                        bliss_b200_strerror(rc) + ": " + bliss_b200_last_error());
+}
+inline void check_call(int rc) {
+    if (rc < 0)
+        throw BlissError(BlissError::AnalysisError,
+                         std::string("b200 backend: ") + bliss_b200_strerror(rc) + ": " + bliss_b200_last_error());
+}
+inline BlissError status_error(int status) {
+    return status == BLISS_B200_SONG_TOO_SHORT
+               ? BlissError(BlissError::AnalysisError, "empty or too short song.")  // src/song/mod.rs:426-430
+               : BlissError(BlissError::AnalysisError, "b200 backend: internal error");
+}
+}  // namespace detail
+
+// src/song/mod.rs:103-156
+enum class AnalysisIndex : size_t {
+    Tempo, Zcr, MeanSpectralCentroid, StdDeviationSpectralCentroid, MeanSpectralRolloff,
+    StdDeviationSpectralRolloff, MeanSpectralFlatness, StdDeviationSpectralFlatness, MeanLoudness,
+    StdDeviationLoudness, Chroma1, Chroma2, Chroma3, Chroma4, Chroma5, Chroma6, Chroma7, Chroma8, Chroma9,
+    Chroma10, Chroma11, Chroma12, Chroma13
+};
+
+// src/song/mod.rs:252-269
+struct AnalysisOptions {
+    FeaturesVersion features_version = LATEST;
+    unsigned number_cores = std::max(1u, std::thread::hardware_concurrency());
+};
+
+// src/song/mod.rs:240-371
+class Analysis {
+  public:
+    FeaturesVersion features_version;
+    Analysis(std::vector<float> analysis, FeaturesVersion v) : features_version(v), v_(std::move(analysis)) {
+        if (v_.size() != feature_count(v))
+            throw BlissError(BlissError::ProviderError,
+                             "Feature count " + std::to_string(v_.size()) +
+                                 " does not match the expected version feature count " + std::to_string(feature_count(v)));
+    }
+    const std::vector<float> &as_vec() const { return v_; }
+    float operator[](AnalysisIndex i) const {
+        if (features_version != LATEST) throw std::logic_error("Tried to index features with incompatible indexes");
+        return v_[static_cast<size_t>(i)];
+    }
+    // src/song/mod.rs:364-370
+    float distance(const Analysis &other) const {
+        if (features_version != other.features_version)
+            throw std::logic_error("Mismatched features version between two songs or analysis");
+        detail::ensure_init();
+        const auto m = feature_weights(features_version);
+        float d = 0.f;
+        detail::check_call(bliss_b200_distance(v_.data(), other.v_.data(), static_cast<uint32_t>(v_.size()),
+                                               BLISS_B200_METRIC_MAHALANOBIS, m.data(), &d));
+        return d;
+    }
+
+  private:
+    std::vector<float> v_;
+};
+
+// src/song/mod.rs:45-98 (fields the analysis path carries)
+struct Song {
+    std::string path;
+    std::optional<std::string> artist, album_artist, title, album, genre;
+    std::optional<int> track_number, disc_number;
+    double duration_s = 0.;
+    std::optional<Analysis> analysis;
+    FeaturesVersion features_version = LATEST;
+
+    // Song::analyze / analyze_with_options, src/song/mod.rs:403-508
+    static Analysis analyze(const float *samples, size_t n) { return analyze_with_options(samples, n, AnalysisOptions{}); }
+    static Analysis analyze_with_options(const float *samples, size_t n, const AnalysisOptions &o) {
+        detail::ensure_init();
+        std::vector<float> out(feature_count(o.features_version));
+        const int rc = bliss_b200_analyze(samples, n, static_cast<uint16_t>(o.features_version), out.data());
+        detail::check_call(rc);
+        if (rc != BLISS_B200_SONG_OK) throw detail::status_error(rc);
+        return Analysis(std::move(out), o.features_version);
+    }
+    float distance(const Song &other) const { return analysis->distance(*other.analysis); }  // :519-521
+};
+
+using AnalysisResult = std::variant<Analysis, BlissError>;
+
+// The batching seam: many decoded buffers, one GPU call; errors are items (src/song/decoder.rs:319-325).
+inline std::vector<AnalysisResult> analyze_batch(const std::vector<const float *> &pcm, const std::vector<uint64_t> &n,
+                                                 const AnalysisOptions &o = {}) {
+    detail::ensure_init();
+    const size_t dim = feature_count(o.features_version);
+    std::vector<float> out(dim * pcm.size());
+    std::vector<int32_t> status(pcm.size());
+    detail::check_call(bliss_b200_analyze_batch(pcm.data(), n.data(), static_cast<uint32_t>(pcm.size()),
+                                                static_cast<uint16_t>(o.features_version), out.data(), status.data()));
+    std::vector<AnalysisResult> res;
+    res.reserve(pcm.size());
+    for (size_t i = 0; i < pcm.size(); i++) {
+        if (status[i] == BLISS_B200_SONG_OK)
+            res.emplace_back(Analysis(std::vector<float>(out.begin() + i * dim, out.begin() + (i + 1) * dim), o.features_version));
+        else
+            res.emplace_back(detail::status_error(status[i]));
+    }
+    return res;
+}
+
+// src/song/decoder.rs:34-67
+struct PreAnalyzedSong {
+    std::string path;
+    std::optional<std::string> artist, album_artist, title, album, genre;
+    std::optional<int> track_number, disc_number;
+    double duration_s = 0.;
+    std::vector<float> sample_array;  // mono f32le 22 050 Hz
+};
+
+// trait Decoder, src/song/decoder.rs:115-333: implement decode(); the provided functions keep the
+// reference's meaning, with analysis batched onto the GPU.
+class Decoder {
+  public:
+    virtual ~Decoder() = default;
+    virtual PreAnalyzedSong decode(const std::string &path) = 0;  // throws BlissError(DecodingError)
+
+    Song song_from_path(const std::string &path, const AnalysisOptions &o = {}) {
+        PreAnalyzedSong p = decode(path);
+        return to_song(p, Song::analyze_with_options(p.sample_array.data(), p.sample_array.size(), o), o);
+    }
+
+    using PathResult = std::pair<std::string, std::variant<Song, BlissError>>;
+    std::vector<PathResult> analyze_paths(const std::vector<std::string> &paths, const AnalysisOptions &o = {},
+                                          size_t batch_songs = 64) {
+        std::vector<PathResult> out;
+        std::vector<PreAnalyzedSong> batch;
+        auto flush = [&]() {
+            std::vector<const float *> ptrs;
+            std::vector<uint64_t> lens;
+            for (auto &p : batch) { ptrs.push_back(p.sample_array.data()); lens.push_back(p.sample_array.size()); }
+            auto res = analyze_batch(ptrs, lens, o);
+            for (size_t i = 0; i < batch.size(); i++) {
+                if (auto *a = std::get_if<Analysis>(&res[i])) out.emplace_back(batch[i].path, to_song(batch[i], *a, o));
+                else out.emplace_back(batch[i].path, std::get<BlissError>(res[i]));
+            }
+            batch.clear();
+        };
+        for (const auto &path : paths) {
+            try { batch.push_back(decode(path)); }
+            catch (const BlissError &e) { out.emplace_back(path, e); continue; }
+            if (batch.size() >= batch_songs) flush();
+        }
+        if (!batch.empty()) flush();
+        return out;
+    }
+
+  private:
+    static Song to_song(const PreAnalyzedSong &p, Analysis a, const AnalysisOptions &o) {  // decoder.rs:85-100
+        Song s;
+        s.path = p.path; s.artist = p.artist; s.album_artist = p.album_artist; s.title = p.title; s.album = p.album;
+        s.genre = p.genre; s.track_number = p.track_number; s.disc_number = p.disc_number; s.duration_s = p.duration_s;
+        s.analysis = std::move(a);
+        s.features_version = o.features_version;
+        return s;
+    }
+};
+
+// ---- src/playlist.rs ----------------------------------------------------------------------------
+namespace playlist {
+struct Metric {  // what a DistanceMetricBuilder boils down to on the device
+    int metric = BLISS_B200_METRIC_MAHALANOBIS;
+    std::vector<float> m;  // dim*dim, empty = identity (euclidean)
+    const float *mp() const { return m.empty() ? nullptr : m.data(); }
+};
+inline Metric euclidean_distance() { return {}; }                                         // :65-71
+inline Metric cosine_distance() { return {BLISS_B200_METRIC_COSINE, {}}; }                // :76-79
+inline Metric mahalanobis_distance_builder(std::vector<float> m) { return {BLISS_B200_METRIC_MAHALANOBIS, std::move(m)}; }  // :129-131
+
+inline float distance(const std::vector<float> &a, const std::vector<float> &b, const Metric &mt = {}) {
+    detail::ensure_init();
+    float d = 0.f;
+    detail::check_call(bliss_b200_distance(a.data(), b.data(), static_cast<uint32_t>(a.size()), mt.metric, mt.mp(), &d));
+    return d;
+}
+// closest_to_songs, :256-270: returns candidate indices, stable by summed distance to the seeds
+inline std::vector<uint32_t> closest_to_songs(const std::vector<float> &seeds, const std::vector<float> &cands,
+                                              uint32_t dim, const Metric &mt = {}) {
+    detail::ensure_init();
+    std::vector<uint32_t> order(cands.size() / dim);
+    detail::check_call(bliss_b200_closest_to_songs(seeds.data(), static_cast<uint32_t>(seeds.size() / dim), cands.data(),
+                                                   static_cast<uint32_t>(order.size()), dim, mt.metric, mt.mp(),
+                                                   order.data(), nullptr));
+    return order;
+}
+// song_to_song, :272-326
+inline std::vector<uint32_t> song_to_song(const std::vector<float> &seeds, const std::vector<float> &cands, uint32_t dim,
+                                          const Metric &mt = {}) {
+    detail::ensure_init();
+    std::vector<uint32_t> order(cands.size() / dim);
+    detail::check_call(bliss_b200_song_to_song(seeds.data(), static_cast<uint32_t>(seeds.size() / dim), cands.data(),
+                                               static_cast<uint32_t>(order.size()), dim, mt.metric, mt.mp(), order.data()));
+    return order;
+}
+}  // namespace playlist
+}  // namespace bliss
