@@ -178,23 +178,28 @@ def main():
     dim = 23
 
     # ---- synthetic corpus, generated in HBM (not timed) --------------------------------
+    from bliss_rs_b200 import multigpu as M
+    n_total = world * S
+    my_ids = M.shard_round_robin(n_total, world, rank)       # BASELINE config 4: round-robin shards
     lengths = [TRACK_SAMPLES] * S
-    pcm, offs, lens = synth.gen_corpus_flat(BASE_SEED, rank * S, lengths, device=dev)
+    pcm, offs, lens = synth.gen_corpus_flat(BASE_SEED, my_ids, lengths, device=dev)
     feats = torch.zeros((S, dim), dtype=torch.float32, device=dev)
-    all_feats = torch.zeros((world * S, dim), dtype=torch.float32, device=dev)
-    dmat = torch.zeros((S, world * S), dtype=torch.float32, device=dev)
+    all_feats = torch.zeros((n_total, dim), dtype=torch.float32, device=dev)
+    row_lo, row_hi = M.row_block(n_total, world, rank)       # this rank's rows of the all-pairs matrix
+    dmat = torch.zeros((row_hi - row_lo, n_total), dtype=torch.float32, device=dev)
     weights = nat.feature_weights(2)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
         nat.analyze_batch_device(pcm.data_ptr(), offs, lens, 2, feats.data_ptr(), stream)
         if world > 1:
-            dist.all_gather_into_tensor(all_feats, feats)
-            cols = all_feats
+            dist.all_gather_into_tensor(all_feats, feats)        # the ONE collective of the path (NCCL)
+            cols = M.round_robin_to_global(all_feats, world)      # rank-major -> global song order
         else:
             cols = feats
-        nat.distance_matrix_device(feats.data_ptr(), S, cols.data_ptr(), world * S, dim, dmat.data_ptr(),
-                                   nat.METRIC_MAHALANOBIS, weights, stream)
+        rows = cols[row_lo:row_hi]
+        nat.distance_matrix_device(rows.data_ptr(), row_hi - row_lo, cols.data_ptr(), n_total, dim,
+                                   dmat.data_ptr(), nat.METRIC_MAHALANOBIS, weights, stream)
 
     def barrier():
         torch.cuda.synchronize()

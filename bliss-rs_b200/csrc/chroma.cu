@@ -65,6 +65,13 @@ int launch_chroma_filter_table(double *table, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 constexpr int K3_THREADS = 256;
 
+// one pip_track candidate test in f32 (the f64 comparisons of chroma.rs:308 are order
+// preserving on f32-exact values); `ref` stays f64 because 0.1*max is not an f32
+__device__ __forceinline__ bool pip_is_peak(const float *sm, int c, double ref) {
+    const float before = sm[c - 1], elem = sm[c], after = sm[c + 1];
+    return after <= elem && before < elem && (double)elem > ref;
+}
+
 __global__ void __launch_bounds__(K3_THREADS, 2)
 stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
                 const unsigned int *__restrict__ pair_prefix, int n_songs,
@@ -78,7 +85,6 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     __shared__ unsigned int s_base;
 
     const int tid = threadIdx.x;
-    // song lookup
     int lo = 0, hi = n_songs;
     const unsigned int item = blockIdx.x;
     while (hi - lo > 1) {
@@ -91,12 +97,14 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     const bool hasB = (fA + 1) < (int)sd.n_c_comp;
     const float *x = pcm + sd.pcm_off;
     const int n = (int)sd.n;
+    // window A starts at sample s0 = 2205 fA - 4096 (reflect padding of utils.rs:11-24 when outside)
+    const int s0 = CH_HOP * fA - 4096;
+    const bool interior = (s0 >= 0) && (s0 + (hasB ? CH_HOP : 0) + 8191 < n);
 
     // Two real frames ride one complex FFT (A in re, B in im).  The untangling leaks
     // eps*max(|A|,|B|) of rounding noise into the weaker frame, so when the frames differ a lot in
     // level (digital silence next to sound) they are transformed one after the other instead:
     // mode 0 = packed, mode 1 = A alone, mode 2 = B alone (CTA-uniform, rare).
-    const long long pA = (long long)CH_HOP * fA;
     float ma[17], mb[17];
     int mode = 0;
     for (;;) {
@@ -104,13 +112,34 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
             const int b = tid + 256 * h;
+            float wa[16], va[16], vb[16];
+            if (interior) {  // fast path: plain coalesced loads at constant offsets from one base
+                const float *pa = x + s0 + b;
+                const float *ph = hann + b;
+#pragma unroll
+                for (int q = 0; q < 16; q++) wa[q] = __ldg(ph + 512 * q);
+#pragma unroll
+                for (int q = 0; q < 16; q++) va[q] = __ldg(pa + 512 * q);
+                if (hasB) {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) vb[q] = __ldg(pa + CH_HOP + 512 * q);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) vb[q] = 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const int m = b + 512 * q;
+                    wa[q] = __ldg(hann + m);
+                    va[q] = f8k::padded_sample(x, n, (long long)s0 + 4096 + m);
+                    vb[q] = hasB ? f8k::padded_sample(x, n, (long long)s0 + 4096 + CH_HOP + m) : 0.f;
+                }
+            }
             cpx v[16];
 #pragma unroll
             for (int q = 0; q < 16; q++) {
-                const int m = b + 512 * q;
-                const float w = __ldg(hann + m);
-                const float a = f8k::padded_sample(x, n, pA + m) * w;
-                const float bb = hasB ? f8k::padded_sample(x, n, pA + CH_HOP + m) * w : 0.f;
+                const float a = va[q] * wa[q], bb = vb[q] * wa[q];
                 pka = fmaxf(pka, fabsf(a));
                 pkb = fmaxf(pkb, fabsf(bb));
                 v[q] = (mode == 0) ? cpx{a, bb} : (mode == 1) ? cpx{a, 0.f} : cpx{bb, 0.f};
@@ -142,24 +171,27 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
                 continue;
             }
         }
-        f8k::pass2(tid, tw, buf);
-        f8k::pass2(tid + 256, tw, buf);
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) f8k::pass2(tid + 256 * h, tw, buf);
         __syncthreads();
         f8k::pass3(tid, buf);
         __syncthreads();
-        // natural-order magnitudes: thread owns bins tid + 256*m, m = 0..16
+        // natural-order magnitudes: thread owns bins tid + 256*m, m = 0..16 (only tid 0 has m = 16)
+        {
+            const cpx *pk = buf + f8k::xbase(tid);
+            const cpx *pm = (tid == 0) ? buf + 32 : buf + f8k::xbase(256 - tid) + 31;
 #pragma unroll
-        for (int m = 0; m < 17; m++) {
-            const int k = tid + 256 * m;
-            float ta = 0.f, tb = 0.f;
-            if (k <= 4096) {
-                const cpx zk = buf[f8k::pad(f8k::xpos(k))];
-                const cpx zm = buf[f8k::pad(f8k::xpos((8192 - k) & 8191))];
-                f8k::untangle_mag(zk, zm, ta, tb);
+            for (int m = 0; m < 17; m++) {
+                float ta = 0.f, tb = 0.f;
+                if (m < 16 || tid == 0) {
+                    const cpx zk = pk[m];
+                    const cpx zm = (tid == 0 && m == 0) ? zk : pm[-m];
+                    f8k::untangle_mag(zk, zm, ta, tb);
+                }
+                if (mode != 2) ma[m] = ta;
+                if (mode == 0) mb[m] = tb;
+                if (mode == 2) mb[m] = ta;
             }
-            if (mode != 2) ma[m] = ta;
-            if (mode == 0) mb[m] = tb;
-            if (mode == 2) mb[m] = ta;
         }
         if (mode != 1) break;
         mode = 2;
@@ -177,14 +209,18 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     float *gA = mags + (sd.mag_off + (unsigned long long)fA) * CH_STRIDE;
     float *gB = gA + CH_STRIDE;
 #pragma unroll
-    for (int m = 0; m < 17; m++) {
+    for (int m = 0; m < 16; m++) {
         const int k = tid + 256 * m;
-        if (k <= 4096) {
-            sA[k] = ma[m];
-            sB[k] = mb[m];
-            gA[k] = ma[m];
-            if (hasB) gB[k] = mb[m];
-        }
+        sA[k] = ma[m];
+        sB[k] = mb[m];
+        gA[k] = ma[m];
+        if (hasB) gB[k] = mb[m];
+    }
+    if (tid == 0) {
+        sA[4096] = ma[16];
+        sB[4096] = mb[16];
+        gA[4096] = ma[16];
+        if (hasB) gB[4096] = mb[16];
     }
     // frame maxima (pip_track's ref_value = 0.1 * max over all bins, chroma.rs:289-293)
 #pragma unroll
@@ -204,42 +240,20 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
         fmax_b = fmaxf(fmax_b, s_red[1][w]);
     }
 
-    // pip_track on centre bins 57..1483 (beginning = 56, end = 1486 for n_fft = 8192)
+    // pip_track on centre bins 57..1483 (beginning = 56, end = 1486 for n_fft = 8192).
+    // Phase 1 counts this thread's peaks, a block scan reserves the output range, phase 2 emits.
     const int nframes_here = hasB ? 2 : 1;
+#pragma unroll 1
     for (int fr = 0; fr < nframes_here; fr++) {
         const float *sm = fr ? sB : sA;
         const double ref = 0.1 * (double)(fr ? fmax_b : fmax_a);
-        double cm[6];
-        unsigned char cb[6];
-        int cnt = 0;
+        unsigned int flags = 0;
 #pragma unroll
         for (int m = 0; m < 6; m++) {
             const int c = 57 + tid + 256 * m;
-            if (c <= 1483) {
-                const double before = (double)sm[c - 1], elem = (double)sm[c], after = (double)sm[c + 1];
-                if (elem > ref && after <= elem && before < elem) {
-                    const double avg = 0.5 * (after - before);
-                    double shift = 2. * elem - after - before;
-                    if (fabs(shift) < 2.2250738585072014e-308) shift += 1.;
-                    shift = avg / shift;
-                    const double pitch = ((double)c + shift) * (double)SAMPLE_RATE / 8192.0;
-                    const double mg = elem + 0.5 * avg * shift;
-                    // pitch_tuning's residue bin (chroma.rs:342-348), tuning 0, 12 bins/octave
-                    double v = pitch / (440.0 / 16.);
-                    v = log2(v);
-                    v = fmod(12.0 * v, 1.0);
-                    if (v >= 0.5) v -= 1.;
-                    int idx = (int)((v - -0.5) / 0.01);
-                    idx = idx < 0 ? 0 : (idx > 99 ? 99 : idx);
-                    if (pitch > 0.) {
-                        cm[cnt] = mg;
-                        cb[cnt] = (unsigned char)idx;
-                        cnt++;
-                    }
-                }
-            }
+            if (c <= 1483 && pip_is_peak(sm, c, ref)) flags |= 1u << m;
         }
-        // block-exclusive scan of cnt, one global reservation per frame
+        const int cnt = __popc(flags);
         unsigned int incl = (unsigned)cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -257,10 +271,27 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
         }
         if (tid == 0) s_base = tot ? atomicAdd(cand_count + si, tot) : 0u;
         __syncthreads();
-        const unsigned long long dst = sd.cand_off + s_base + woff + (incl - (unsigned)cnt);
-        for (int q = 0; q < cnt; q++) {
-            cand_mag[dst + q] = cm[q];
-            cand_bin[dst + q] = cb[q];
+        unsigned long long dst = sd.cand_off + s_base + woff + (incl - (unsigned)cnt);
+        while (flags) {
+            const int m = __ffs(flags) - 1;
+            flags &= flags - 1;
+            const int c = 57 + tid + 256 * m;
+            const double before = (double)sm[c - 1], elem = (double)sm[c], after = (double)sm[c + 1];
+            const double avg = 0.5 * (after - before);
+            double shift = 2. * elem - after - before;
+            if (fabs(shift) < 2.2250738585072014e-308) shift += 1.;
+            shift = avg / shift;
+            const double pitch = ((double)c + shift) * (double)SAMPLE_RATE / 8192.0;
+            // pitch_tuning's residue bin (chroma.rs:342-348), tuning 0, 12 bins/octave
+            double v = pitch / (440.0 / 16.);
+            v = log2(v);
+            v = fmod(12.0 * v, 1.0);
+            if (v >= 0.5) v -= 1.;
+            int idx = (int)((v - -0.5) / 0.01);
+            idx = idx < 0 ? 0 : (idx > 99 ? 99 : idx);
+            cand_mag[dst] = elem + 0.5 * avg * shift;
+            cand_bin[dst] = (unsigned char)idx;
+            dst++;
         }
     }
 }
@@ -466,27 +497,54 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
 #pragma unroll
     for (int c = 0; c < 12; c++) acc[c] = 0.;
 
+    // Software pipeline: the next k-tile (32 bins x 128 frames of magnitudes + 32 x 12 filter
+    // weights) is fetched into registers while the current one is consumed from shared memory.
+    // Thread t stages column (t & 31) of frames (t >> 5) + 4 i, i = 0..31  -> 128 B per warp per row.
+    const int st_k = tid & 31, st_f = tid >> 5;
+    float pre_s[32];
+    double pre_w[3];
+    auto fetch = [&](int k0) {
+        const int kt = min(K5_KT, CH_BINS - k0);
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            const int fr = st_f + 4 * i;
+            float v = 0.f;
+            // rows beyond n_c_comp are zero (utils.rs:27-31)
+            if (fr < nf && st_k < kt && (f0 + fr) < (int)sd.n_c_comp) v = __ldg(S + (size_t)fr * CH_STRIDE + k0 + st_k);
+            pre_s[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int e = tid + K5_FRAMES * i;  // 384 = 32 x 12 weights
+            pre_w[i] = (e < kt * 12) ? __ldg(W + (size_t)k0 * 12 + e) : 0.;
+        }
+    };
+    fetch(0);
     for (int k0 = 0; k0 < CH_BINS; k0 += K5_KT) {
         const int kt = min(K5_KT, CH_BINS - k0);
-        __syncthreads();
-        // stage S[frames][k0..k0+kt) transposed; rows beyond n_c_comp are zero (utils.rs:27-31)
-        for (int e = tid; e < K5_FRAMES * K5_KT; e += K5_FRAMES) {
-            const int fr = e / K5_KT, kk = e % K5_KT;
-            float v = 0.f;
-            if (fr < nf && kk < kt && (f0 + fr) < (int)sd.n_c_comp) v = __ldg(S + (size_t)fr * CH_STRIDE + k0 + kk);
-            s_s[kk][fr] = v;
-        }
-        for (int e = tid; e < K5_KT * 12; e += K5_FRAMES) {
-            const int kk = e / 12;
-            (&s_w[0][0])[e] = (kk < kt) ? W[(size_t)k0 * 12 + e] : 0.;
-        }
-        __syncthreads();
-        if (mine) {
-            for (int kk = 0; kk < kt; kk++) {
-                const double s = (double)s_s[kk][tid];
-                const double s2 = s * s;  // spectrum.mapv_inplace(|x| x*x), chroma.rs:400
+        __syncthreads();  // previous tile fully consumed
 #pragma unroll
-                for (int c = 0; c < 12; c++) acc[c] += s_w[kk][c] * s2;
+        for (int i = 0; i < 32; i++) s_s[st_k][st_f + 4 * i] = pre_s[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) (&s_w[0][0])[tid + K5_FRAMES * i] = pre_w[i];
+        __syncthreads();
+        if (k0 + K5_KT < CH_BINS) fetch(k0 + K5_KT);
+        if (mine) {
+            if (kt == K5_KT) {
+#pragma unroll 8
+                for (int kk = 0; kk < K5_KT; kk++) {
+                    const double s = (double)s_s[kk][tid];
+                    const double s2 = s * s;  // spectrum.mapv_inplace(|x| x*x), chroma.rs:400
+#pragma unroll
+                    for (int c = 0; c < 12; c++) acc[c] += s_w[kk][c] * s2;
+                }
+            } else {
+                for (int kk = 0; kk < kt; kk++) {
+                    const double s = (double)s_s[kk][tid];
+                    const double s2 = s * s;
+#pragma unroll
+                    for (int c = 0; c < 12; c++) acc[c] += s_w[kk][c] * s2;
+                }
             }
         }
     }

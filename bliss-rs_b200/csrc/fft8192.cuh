@@ -19,44 +19,58 @@ constexpr int BUF_CPX = 8192 + 256 + 16;  // pad(8191) + 1 = 8462 -> round up
 BLISS_HD int pad(int i) { return i + (i >> 5) + (i >> 9); }
 BLISS_HD int xpos(int k) { return 512 * (k & 15) + 32 * ((k >> 4) & 15) + (k >> 8); }
 
+// All three passes address the buffer as  base(thread) + constant * slot, so the index
+// arithmetic is a handful of integer ops per butterfly (pad() is folded in by hand):
+//   pass 1 store : pad(b + 512 k1)        = b + (b>>5)            + 529 k1      (b < 512)
+//   pass 2       : pad(512 blk + j + 32q) = 529 blk + j           + 33 q        (j < 32)
+//   pass 3       : pad(32 b + q)          = 33 b + (b>>4)         + q           (b < 256)
+//   bin k = tid + 256 m lives at            529 (tid&15) + 33 ((tid>>4)&15) + m (xbase(tid) + m)
+
 // pass 1: butterfly b in [0,512): v[q] = z[b + 512 q] supplied by the caller
 BLISS_HD void pass1_store(int b, cpx (&v)[16], const cpx *tw /*[8192]*/, cpx *buf) {
     fft_dif<16>(v);
+    cpx *o = buf + b + (b >> 5);
+    const cpx *t = tw + 0;
 #pragma unroll
     for (int s = 0; s < 16; s++) {
         const int k1 = bitrev(s, 4);
-        cpx o = v[s];
-        if (k1 != 0) o = cmul(o, tw[b * k1]);
-        buf[pad(b + 512 * k1)] = o;
+        cpx r = v[s];
+        if (k1 != 0) r = cmul(r, t[b * k1]);
+        o[529 * k1] = r;
     }
 }
 
 // pass 2: butterfly b in [0,512): block = b>>5 (k1), j = b&31; radix 16 at stride 32
 BLISS_HD void pass2(int b, const cpx *tw, cpx *buf) {
     const int blk = b >> 5, j = b & 31;
-    const int base = blk * 512 + j;
+    cpx *p = buf + 529 * blk + j;
     cpx v[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) v[q] = buf[pad(base + 32 * q)];
+    for (int q = 0; q < 16; q++) v[q] = p[33 * q];
     fft_dif<16>(v);
+    const cpx *t = tw + 0;
 #pragma unroll
     for (int s = 0; s < 16; s++) {
         const int k2 = bitrev(s, 4);
         cpx o = v[s];
-        if (k2 != 0) o = cmul(o, tw[16 * j * k2]);
-        buf[pad(base + 32 * k2)] = o;
+        if (k2 != 0) o = cmul(o, t[(16 * j) * k2]);
+        p[33 * k2] = o;
     }
 }
 
 // pass 3: butterfly b in [0,256): 32 consecutive logical elements, no twiddle
 BLISS_HD void pass3(int b, cpx *buf) {
+    cpx *p = buf + 33 * b + (b >> 4);
     cpx v[32];
 #pragma unroll
-    for (int q = 0; q < 32; q++) v[q] = buf[pad(32 * b + q)];
+    for (int q = 0; q < 32; q++) v[q] = p[q];
     fft_dif<32>(v);
 #pragma unroll
-    for (int s = 0; s < 32; s++) buf[pad(32 * b + bitrev(s, 5))] = v[s];
+    for (int s = 0; s < 32; s++) p[bitrev(s, 5)] = v[s];
 }
+
+// padded position of bin (t + 256 m), t < 256:  xbase(t) + m
+BLISS_HD int xbase(int t) { return 529 * (t & 15) + 33 * ((t >> 4) & 15); }
 
 // magnitudes of the two real frames packed in Z: see pv::untangle_mag
 BLISS_HD void untangle_mag(cpx zk, cpx zm, float &magA, float &magB) {

@@ -152,81 +152,70 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
 #pragma unroll
         for (int m = 0; m < 12; m++) s[m] = s[m + 8];
         {
-            const int base = 256 * j - 384 + lane + 32 * 12;
+            const int base = 256 * j - 384 + lane + 32 * 12;  // >= 0 for every j; < n for valid pairs except j < 1
+            const float *px = x + base;  // 256 j + lane + 32 m <= 256 j + 255 < n for every pair j < n_t
 #pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const int idx = base + 32 * m;
-                s[12 + m] = (idx >= 0 && idx < n) ? __ldg(x + idx) : 0.f;
-            }
+            for (int m = 0; m < 8; m++) s[12 + m] = __ldg(px + 32 * m);
         }
-        // Packing two real frames into one complex FFT leaks eps*max(|A|,|B|) of rounding noise
-        // into the weaker frame.  When the two frames differ a lot in level (digital silence next
-        // to sound, hard onsets) they are transformed one at a time instead (warp-uniform, rare).
+        // Two real frames ride one complex FFT (A in re, B in im); untangling leaks
+        // eps*max(|A|,|B|) of rounding noise into the weaker frame.  B is therefore pre-scaled by a
+        // power of two (exact) to A's level and scaled back afterwards, and a frame whose windowed
+        // samples are all exactly zero (digital silence) is forced to exact zeros, which is what
+        // the reference's separate transforms produce.
         float pka = 0.f, pkb = 0.f;
+        cpx r[16];
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) {
-            pka = fmaxf(pka, fabsf(win_a[n1] * s[n1]));
-            pkb = fmaxf(pkb, fabsf(win_a[n1] * s[n1 + 4]));
+            r[n1] = cpx{win_a[n1] * s[n1], win_a[n1] * s[n1 + 4]};
+            pka = fmaxf(pka, fabsf(r[n1].x));
+            pkb = fmaxf(pkb, fabsf(r[n1].y));
         }
-        pka = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pka)));
-        pkb = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(pkb)));
-        const bool split = (pka > 8.f * pkb) || (pkb > 8.f * pka);
-        const int npass = split ? 2 : 1;
+        const unsigned int ua = __reduce_max_sync(0xffffffffu, __float_as_uint(pka));
+        const unsigned int ub = __reduce_max_sync(0xffffffffu, __float_as_uint(pkb));
+        int sh = (int)(ua >> 23) - (int)(ub >> 23);  // exponent difference of the two peaks
+        sh = (ua == 0u || ub == 0u) ? 0 : max(-60, min(60, sh));
+        const float gscale = __uint_as_float((unsigned)(127 + sh) << 23);
+        const float ginv = __uint_as_float((unsigned)(127 - sh) << 23);
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) r[n1].y *= gscale;
+        pv::phase_a(lane, r, s_twA, S);
+        __syncwarp();
+        pv::phase_b_load(lane, r, S);
+        __syncwarp();
+        pv::phase_b_fft(lane, r);
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const cpx o = shfl_xor_cpx(r[q], 16);
+            const cpx z = pv::phase_b_combine(lane, r[q], o);
+            S[pv::zpos(pv::bin_of(lane, q))] = z;
+        }
+        __syncwarp();
+        // natural-order epilogue: lane owns bins 8*lane .. 8*lane+7 of both frames
         float ma[8], mb[8];
-        float nyq_a = 0.f, nyq_b = 0.f;
-#pragma unroll 1
-        for (int pass = 0; pass < npass; pass++) {
-            cpx r[16];
-            const bool second = split && pass == 1;
 #pragma unroll
-            for (int n1 = 0; n1 < 16; n1++) {
-                const float re = win_a[n1] * (second ? s[n1 + 4] : s[n1]);
-                const float im = split ? 0.f : win_a[n1] * s[n1 + 4];
-                r[n1] = cpx{re, im};
-            }
-            pv::phase_a(lane, r, s_twA, S);
-            __syncwarp();
-            pv::phase_b_load(lane, r, S);
-            __syncwarp();
-            pv::phase_b_fft(lane, r);
-#pragma unroll
-            for (int q = 0; q < 16; q++) {
-                const cpx o = shfl_xor_cpx(r[q], 16);
-                const cpx z = pv::phase_b_combine(lane, r[q], o);
-                S[pv::zpos(pv::bin_of(lane, q))] = z;
-            }
-            __syncwarp();
-            // natural-order epilogue: lane owns bins 8*lane .. 8*lane+7 of both frames
-            float ta[8], tb[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int k = 8 * lane + i;
-                const cpx zk = S[pv::zpos(k)];
-                const cpx zm = S[pv::zpos((512 - k) & 511)];
-                pv::untangle_mag(zk, zm, ta[i], tb[i]);
-            }
-            const cpx zn = S[pv::zpos(256)];  // Nyquist: A = |Re|, B = |Im|
-            if (lane == 0) {  // DC: abs(re), aubio.rs:240 / :403
-                const cpx z0 = S[0];
-                ta[0] = fabsf(z0.x);
-                tb[0] = fabsf(z0.y);
-            }
-            __syncwarp();  // S is rewritten by the next transform's phase A
-            if (!second) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) ma[i] = ta[i];
-                nyq_a = fabsf(zn.x);
-            }
-            if (!split) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) mb[i] = tb[i];
-                nyq_b = fabsf(zn.y);
-            } else if (second) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) mb[i] = ta[i];
-                nyq_b = fabsf(zn.x);
-            }
+        for (int i = 0; i < 8; i++) {
+            const int k = 8 * lane + i;
+            const cpx zk = S[pv::zpos(k)];
+            const cpx zm = S[pv::zpos((512 - k) & 511)];
+            pv::untangle_mag(zk, zm, ma[i], mb[i]);
         }
+        const cpx zn = S[pv::zpos(256)];  // Nyquist: A = |Re|, B = |Im|
+        float nyq_a = fabsf(zn.x), nyq_b = fabsf(zn.y);
+        if (lane == 0) {  // DC: abs(re), aubio.rs:240 / :403
+            const cpx z0 = S[0];
+            ma[0] = fabsf(z0.x);
+            mb[0] = fabsf(z0.y);
+        }
+        __syncwarp();  // S is rewritten by the next pair's phase A
+        const float ka = (ua == 0u) ? 0.f : 1.f;
+        const float kb = (ub == 0u) ? 0.f : ginv;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            ma[i] *= ka;
+            mb[i] *= kb;
+        }
+        nyq_a *= ka;
+        nyq_b *= kb;
 
         const bool emit = (j >= j0);
         if (WITH_MAGS && emit) {
@@ -304,38 +293,46 @@ timedomain_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
 
     float eb[4] = {0.f, 0.f, 0.f, 0.f};
     unsigned int crossings = 0;
-    float prev_tail = (base > 0) ? __ldg(x + base - 1) : 0.f;  // lane 31's last sample of the previous row
+    float prev_tail = (base > 0) ? __ldg(x + base - 1) : 0.f;  // sample just before this chunk
     const bool has_prev = base > 0;
+    // all eight 16-byte loads of the lane are issued before anything consumes them
+    float v[8][4];
+    if (len == 1024u && ((sd.pcm_off + base) & 3ull) == 0) {
+        const float4 *p4 = reinterpret_cast<const float4 *>(x + base) + lane;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float4 t = __ldg(p4 + 32 * k);
+            v[k][0] = t.x; v[k][1] = t.y; v[k][2] = t.z; v[k][3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned int p = 4u * lane + 128u * k;
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[k][i] = (p + i < len) ? __ldg(x + base + p + i) : 0.f;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const unsigned int p = 4u * lane + 128u * k;
-        float v[4];
-        if (p + 4 <= len && ((sd.pcm_off + base + p) & 3ull) == 0) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(x + base + p));
-            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; i++) v[i] = (p + i < len) ? __ldg(x + base + p + i) : 0.f;
-        }
         float e = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; i++) e += v[i] * v[i];
+        for (int i = 0; i < 4; i++) e += v[k][i] * v[k][i];
         eb[k >> 1] += e;
-        // predecessor of v[0]: previous lane's v[3]; lane 0 takes the previous row's tail
-        float pred = __shfl_up_sync(0xffffffffu, v[3], 1);
+        // predecessor of v[k][0]: previous lane's last sample; lane 0 takes the previous row's tail
+        float pred = __shfl_up_sync(0xffffffffu, v[k][3], 1);
         if (lane == 0) pred = prev_tail;
-        const bool first_of_song = (base + p == 0);
         const bool have_pred = (k > 0) || (lane > 0) || has_prev;
         float before = pred;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             if (p + i < len) {
-                const bool valid_pair = (i > 0) || (have_pred && !first_of_song);
-                if (valid_pair && ((before > 0.f) != (v[i] > 0.f))) crossings++;
+                const bool valid_pair = (i > 0) || have_pred;
+                if (valid_pair && ((before > 0.f) != (v[k][i] > 0.f))) crossings++;
             }
-            before = v[i];
+            before = v[k][i];
         }
-        prev_tail = __shfl_sync(0xffffffffu, v[3], 31);
+        prev_tail = __shfl_sync(0xffffffffu, v[k][3], 31);
     }
 #pragma unroll
     for (int b = 0; b < 4; b++) eb[b] = warp_sum(eb[b]);

@@ -65,14 +65,14 @@ def gen_track(base_seed: int, track_id: int, n_samples: int, device="cpu") -> to
     return torch.clamp(x, -1.0, 1.0).contiguous()
 
 
-def gen_corpus_flat(base_seed: int, first_id: int, lengths, device="cpu", align=4):
-    """Concatenates tracks into ONE flat buffer (each start aligned to `align` samples).
-    Returns (pcm [total], offsets list, lengths list)."""
+def gen_corpus_flat(base_seed: int, track_ids, lengths, device="cpu", align=4):
+    """Concatenates tracks `track_ids` into ONE flat buffer (each start aligned to `align`
+    samples).  Returns (pcm [total], offsets list, lengths list)."""
     offsets, total = [], 0
     for n in lengths:
         offsets.append(total)
         total += (int(n) + align - 1) // align * align
     pcm = torch.zeros(max(total, align), device=device, dtype=torch.float32)
     for i, (o, n) in enumerate(zip(offsets, lengths)):
-        pcm[o:o + n] = gen_track(base_seed, first_id + i, int(n), device)
+        pcm[o:o + n] = gen_track(base_seed, int(track_ids[i]), int(n), device)
     return pcm, offsets, [int(n) for n in lengths]

@@ -107,6 +107,16 @@ int main() {
         }
         printf("fft8192 pair: max rel err %.3e\n", err);
         worst = fmax(worst, err);
+        // hand-folded epilogue addressing must agree with pad(xpos(k)) for k and its mirror
+        for (int t = 0; t < 256; t++)
+            for (int m = 0; m < 17; m++) {
+                int k = t + 256 * m;
+                if (k > 4096) continue;
+                if (f8k::xbase(t) + m != f8k::pad(f8k::xpos(k))) { printf("xbase mismatch k=%d\n", k); return 3; }
+                int km = (8192 - k) & 8191;
+                int got = (k == 0) ? f8k::xbase(0) : (t == 0 ? f8k::xbase(0) + 32 - m : f8k::xbase(256 - t) + 31 - m);
+                if (got != f8k::pad(f8k::xpos(km))) { printf("mirror mismatch k=%d\n", k); return 3; }
+            }
         // padding must be injective
         std::vector<int> seen(f8k::BUF_CPX, 0);
         for (int i = 0; i < 8192; i++) {
