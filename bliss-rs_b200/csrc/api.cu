@@ -226,7 +226,7 @@ void plan_wave(const uint64_t *offsets, const uint64_t *n_samples, uint32_t firs
         d.bpm_off = (unsigned int)w.bpms;
         const uint32_t items = d.valid ? (q.n_t + w.pairs_per_item - 1) / w.pairs_per_item : 0;
         w.k1_prefix[i + 1] = w.k1_prefix[i] + items;
-        w.chunk_prefix[i + 1] = w.chunk_prefix[i] + (d.valid ? q.n_l : 0);
+        w.chunk_prefix[i + 1] = w.chunk_prefix[i] + (d.valid ? (q.n_l + 7) / 8 : 0);  // groups of 8 chunks (timedomain_kernel)
         w.t_prefix[i + 1] = w.t_prefix[i] + (d.valid ? q.n_t : 0);
         w.pair_prefix[i + 1] = w.pair_prefix[i] + (d.valid ? q.n_pairs8k : 0);
         w.tile_prefix[i + 1] = w.tile_prefix[i] + (d.valid ? q.n_tiles : 0);

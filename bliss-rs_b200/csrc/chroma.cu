@@ -63,7 +63,7 @@ int launch_chroma_filter_table(double *table, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // K3: one CTA per pair of chroma frames.
 // ---------------------------------------------------------------------------
-constexpr int K3_THREADS = 256;
+constexpr int K3_THREADS = 512;
 
 // one pip_track candidate test in f32 (the f64 comparisons of chroma.rs:308 are order
 // preserving on f32-exact values); `ref` stays f64 because 0.1*max is not an f32
@@ -85,13 +85,8 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     __shared__ unsigned int s_base;
 
     const int tid = threadIdx.x;
-    int lo = 0, hi = n_songs;
     const unsigned int item = blockIdx.x;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (pair_prefix[mid] <= item) lo = mid; else hi = mid;
-    }
-    const int si = lo;
+    const int si = find_song(pair_prefix, n_songs, item);
     const SongDesc sd = songs[si];
     const int fA = 2 * (int)(item - pair_prefix[si]);
     const bool hasB = (fA + 1) < (int)sd.n_c_comp;
@@ -105,44 +100,51 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     // eps*max(|A|,|B|) of rounding noise into the weaker frame, so when the frames differ a lot in
     // level (digital silence next to sound) they are transformed one after the other instead:
     // mode 0 = packed, mode 1 = A alone, mode 2 = B alone (CTA-uniform, rare).
-    float ma[17], mb[17];
+    // Thread t owns bins t + 512 m, m = 0..7; thread 0 also owns bin 4096 (slot 8).
+    float ma[9], mb[9];
+    ma[8] = 0.f;
+    mb[8] = 0.f;
     int mode = 0;
     for (;;) {
         float pka = 0.f, pkb = 0.f;
-#pragma unroll 1
-        for (int h = 0; h < 2; h++) {
-            const int b = tid + 256 * h;
-            float wa[16], va[16], vb[16];
+        {
+            const int b = tid;  // pass-1 butterfly: points b + 512 q
+            cpx v[16];
             if (interior) {  // fast path: plain coalesced loads at constant offsets from one base
                 const float *pa = x + s0 + b;
                 const float *ph = hann + b;
+                float wa[16];
 #pragma unroll
                 for (int q = 0; q < 16; q++) wa[q] = __ldg(ph + 512 * q);
 #pragma unroll
-                for (int q = 0; q < 16; q++) va[q] = __ldg(pa + 512 * q);
+                for (int q = 0; q < 16; q++) v[q].x = __ldg(pa + 512 * q);
                 if (hasB) {
 #pragma unroll
-                    for (int q = 0; q < 16; q++) vb[q] = __ldg(pa + CH_HOP + 512 * q);
+                    for (int q = 0; q < 16; q++) v[q].y = __ldg(pa + CH_HOP + 512 * q);
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 16; q++) vb[q] = 0.f;
+                    for (int q = 0; q < 16; q++) v[q].y = 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    v[q].x *= wa[q];
+                    v[q].y *= wa[q];
                 }
             } else {
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
                     const int m = b + 512 * q;
-                    wa[q] = __ldg(hann + m);
-                    va[q] = f8k::padded_sample(x, n, (long long)s0 + 4096 + m);
-                    vb[q] = hasB ? f8k::padded_sample(x, n, (long long)s0 + 4096 + CH_HOP + m) : 0.f;
+                    const float w = __ldg(hann + m);
+                    v[q].x = w * f8k::padded_sample(x, n, (long long)s0 + 4096 + m);
+                    v[q].y = hasB ? w * f8k::padded_sample(x, n, (long long)s0 + 4096 + CH_HOP + m) : 0.f;
                 }
             }
-            cpx v[16];
 #pragma unroll
             for (int q = 0; q < 16; q++) {
-                const float a = va[q] * wa[q], bb = vb[q] * wa[q];
-                pka = fmaxf(pka, fabsf(a));
-                pkb = fmaxf(pkb, fabsf(bb));
-                v[q] = (mode == 0) ? cpx{a, bb} : (mode == 1) ? cpx{a, 0.f} : cpx{bb, 0.f};
+                pka = fmaxf(pka, fabsf(v[q].x));
+                pkb = fmaxf(pkb, fabsf(v[q].y));
+                if (mode == 1) v[q].y = 0.f;
+                if (mode == 2) v[q] = cpx{v[q].y, 0.f};
             }
             f8k::pass1_store(b, v, tw, buf);
         }
@@ -171,26 +173,32 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
                 continue;
             }
         }
-#pragma unroll 1
-        for (int h = 0; h < 2; h++) f8k::pass2(tid + 256 * h, tw, buf);
+        f8k::pass2(tid, tw, buf);
         __syncthreads();
         f8k::pass3(tid, buf);
         __syncthreads();
-        // natural-order magnitudes: thread owns bins tid + 256*m, m = 0..16 (only tid 0 has m = 16)
+        // natural-order magnitudes with the closing radix-2 folded in (fft8192.cuh):
+        //   X[k] = u0 + u1 (k < 4096),  X[8192 - k] = u0' - u1' at the pair of 4096 - k
         {
-            const cpx *pk = buf + f8k::xbase(tid);
-            const cpx *pm = (tid == 0) ? buf + 32 : buf + f8k::xbase(256 - tid) + 31;
+            const cpx *pk = buf + f8k::ebase(tid);
+            const cpx *pm = (tid == 0) ? buf + f8k::ebase(0) + 32 : buf + f8k::ebase(512 - tid) + 28;
 #pragma unroll
-            for (int m = 0; m < 17; m++) {
-                float ta = 0.f, tb = 0.f;
-                if (m < 16 || tid == 0) {
-                    const cpx zk = pk[m];
-                    const cpx zm = (tid == 0 && m == 0) ? zk : pm[-m];
-                    f8k::untangle_mag(zk, zm, ta, tb);
-                }
+            for (int m = 0; m < 8; m++) {
+                const cpx zk = f8k::pair_sum(pk + 4 * m);
+                const cpx zm = (tid == 0 && m == 0) ? zk : f8k::pair_diff(pm - 4 * m);
+                float ta, tb;
+                f8k::untangle_mag(zk, zm, ta, tb);
                 if (mode != 2) ma[m] = ta;
                 if (mode == 0) mb[m] = tb;
                 if (mode == 2) mb[m] = ta;
+            }
+            if (tid == 0) {  // bin 4096 is its own mirror
+                const cpx z = f8k::pair_diff(buf);
+                float ta, tb;
+                f8k::untangle_mag(z, z, ta, tb);
+                if (mode != 2) ma[8] = ta;
+                if (mode == 0) mb[8] = tb;
+                if (mode == 2) mb[8] = ta;
             }
         }
         if (mode != 1) break;
@@ -199,7 +207,7 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     }
     float mxa = 0.f, mxb = 0.f;
 #pragma unroll
-    for (int m = 0; m < 17; m++) {
+    for (int m = 0; m < 9; m++) {
         mxa = fmaxf(mxa, ma[m]);
         mxb = fmaxf(mxb, mb[m]);
     }
@@ -209,18 +217,18 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     float *gA = mags + (sd.mag_off + (unsigned long long)fA) * CH_STRIDE;
     float *gB = gA + CH_STRIDE;
 #pragma unroll
-    for (int m = 0; m < 16; m++) {
-        const int k = tid + 256 * m;
+    for (int m = 0; m < 8; m++) {
+        const int k = tid + 512 * m;
         sA[k] = ma[m];
         sB[k] = mb[m];
         gA[k] = ma[m];
         if (hasB) gB[k] = mb[m];
     }
     if (tid == 0) {
-        sA[4096] = ma[16];
-        sB[4096] = mb[16];
-        gA[4096] = ma[16];
-        if (hasB) gB[4096] = mb[16];
+        sA[4096] = ma[8];
+        sB[4096] = mb[8];
+        gA[4096] = ma[8];
+        if (hasB) gB[4096] = mb[8];
     }
     // frame maxima (pip_track's ref_value = 0.1 * max over all bins, chroma.rs:289-293)
 #pragma unroll
@@ -249,8 +257,8 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
         const double ref = 0.1 * (double)(fr ? fmax_b : fmax_a);
         unsigned int flags = 0;
 #pragma unroll
-        for (int m = 0; m < 6; m++) {
-            const int c = 57 + tid + 256 * m;
+        for (int m = 0; m < 3; m++) {
+            const int c = 57 + tid + K3_THREADS * m;
             if (c <= 1483 && pip_is_peak(sm, c, ref)) flags |= 1u << m;
         }
         const int cnt = __popc(flags);
@@ -275,7 +283,7 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
         while (flags) {
             const int m = __ffs(flags) - 1;
             flags &= flags - 1;
-            const int c = 57 + tid + 256 * m;
+            const int c = 57 + tid + K3_THREADS * m;
             const double before = (double)sm[c - 1], elem = (double)sm[c], after = (double)sm[c + 1];
             const double avg = 0.5 * (after - before);
             double shift = 2. * elem - after - before;
@@ -477,13 +485,8 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
     __shared__ double s_red[K5_FRAMES / 32][10];
 
     const int tid = threadIdx.x;
-    int lo = 0, hi = n_songs;
     const unsigned int item = blockIdx.x;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (tile_prefix[mid] <= item) lo = mid; else hi = mid;
-    }
-    const int si = lo;
+    const int si = find_song(tile_prefix, n_songs, item);
     const SongDesc sd = songs[si];
     const int tile = (int)(item - tile_prefix[si]);
     const int f0 = tile * K5_FRAMES;

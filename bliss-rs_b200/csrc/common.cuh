@@ -46,6 +46,30 @@ struct PvocTables {   // device pointers
     const cpx *twA;       // [16][32]  W512^(lane*k1)
 };
 
+// Song lookup for flat work lists: largest s with prefix[s] <= item (prefix has n_songs+1
+// entries, prefix[n_songs] = total).  Starts from the proportional guess -- exact for equal-length
+// songs, where it costs one round trip instead of log2(n_songs) dependent loads -- and falls
+// back to bisection when the guess is far off (mixed durations).
+__device__ __forceinline__ int find_song(const unsigned int *__restrict__ prefix, int n_songs,
+                                         unsigned int item) {
+    const unsigned int total = __ldg(prefix + n_songs);
+    int s = (int)(((unsigned long long)item * (unsigned long long)n_songs) / (total ? total : 1u));
+    s = min(max(s, 0), n_songs - 1);
+#pragma unroll 1
+    for (int tries = 0; tries < 4; tries++) {
+        const unsigned int lo = __ldg(prefix + s), hi = __ldg(prefix + s + 1);
+        if (item < lo) s--;
+        else if (item >= hi) s++;
+        else return s;
+    }
+    int lo = 0, hi = n_songs;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(prefix + mid) <= item) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 // ---- kernel launchers (each returns the number of kernels launched) --------
 struct WaveBuffers;
 

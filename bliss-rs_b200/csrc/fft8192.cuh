@@ -58,19 +58,42 @@ BLISS_HD void pass2(int b, const cpx *tw, cpx *buf) {
     }
 }
 
-// pass 3: butterfly b in [0,256): 32 consecutive logical elements, no twiddle
+// pass 3: butterfly b in [0,512): 32-block blk = b & 255, parity j = b >> 8; radix 16 at
+// stride 2 inside the block, twiddle W32^(j k3).  Leaves u_j[k3] at logical 32 blk + 2 k3 + j;
+// the closing radix-2,  X[k1 + 16 k2 + 256 k3 + 4096 k4] = u_0[k3] + (-1)^k4 u_1[k3],  is folded
+// into the epilogue (bin_value below).
+template <int S>
+BLISS_HD void tw32_slots(cpx (&v)[16]) {
+    if constexpr (S < 16) {
+        v[S] = mul_tw<bitrev(S, 4), 32>(v[S]);
+        tw32_slots<S + 1>(v);
+    }
+}
 BLISS_HD void pass3(int b, cpx *buf) {
-    cpx *p = buf + 33 * b + (b >> 4);
-    cpx v[32];
+    const int blk = b & 255, j = b >> 8;
+    cpx *p = buf + 33 * blk + (blk >> 4) + j;
+    cpx v[16];
 #pragma unroll
-    for (int q = 0; q < 32; q++) v[q] = p[q];
-    fft_dif<32>(v);
+    for (int q = 0; q < 16; q++) v[q] = p[2 * q];
+    fft_dif<16>(v);
+    if (j) tw32_slots<0>(v);
 #pragma unroll
-    for (int s = 0; s < 32; s++) p[bitrev(s, 5)] = v[s];
+    for (int s = 0; s < 16; s++) p[2 * bitrev(s, 4)] = v[s];
 }
 
-// padded position of bin (t + 256 m), t < 256:  xbase(t) + m
-BLISS_HD int xbase(int t) { return 529 * (t & 15) + 33 * ((t >> 4) & 15); }
+// padded position of the (u_0, u_1) pair of bin (t + 512 m), t < 512, m < 8:  ebase(t) + 4 m
+BLISS_HD int ebase(int t) { return 529 * (t & 15) + 33 * ((t >> 4) & 15) + 2 * (t >> 8); }
+
+// X[k] for k < 4096 (k4 = 0) and X[k + 4096] (k4 = 1) from the pair at p
+BLISS_HD cpx pair_sum(const cpx *p) { return cadd(p[0], p[1]); }
+BLISS_HD cpx pair_diff(const cpx *p) { return csub(p[0], p[1]); }
+
+// generic (slow) accessor used by the CPU emulation test: X[k], 0 <= k < 8192
+BLISS_HD cpx bin_value(const cpx *buf, int k) {
+    const int k4 = k >> 12, kk = k & 4095;
+    const int pos = pad(512 * (kk & 15) + 32 * ((kk >> 4) & 15) + 2 * (kk >> 8));
+    return k4 ? pair_diff(buf + pos) : pair_sum(buf + pos);
+}
 
 // magnitudes of the two real frames packed in Z: see pv::untangle_mag
 BLISS_HD void untangle_mag(cpx zk, cpx zm, float &magA, float &magB) {

@@ -34,16 +34,6 @@ __device__ __forceinline__ cpx shfl_xor_cpx(cpx v, int m) {
     return cpx{__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m)};
 }
 
-// lower_bound over the per-song item prefix: largest s with prefix[s] <= item
-__device__ __forceinline__ int find_song(const unsigned int *prefix, int n_songs, unsigned int item) {
-    int lo = 0, hi = n_songs;  // prefix has n_songs+1 entries
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (prefix[mid] <= item) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
 // Per-frame descriptors from the 8 consecutive norms a lane holds (bins 8*lane..8*lane+7).
 // Returns centroid (Hz), rolloff (Hz), flatness to lane 0 (all lanes compute them).
 __device__ __forceinline__ void frame_descriptors(const float (&v)[8], int lane, float &centroid,
@@ -275,79 +265,82 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
 //   level_lin per chunk     src/misc.rs:12-18       (chunks(1024) incl. short tail, song/mod.rs:478)
 //   256-sample block energy -> silence test of Tempo::do_ (aubio.rs:1258-1276, :1431)
 // ---------------------------------------------------------------------------
+constexpr int TD_CHUNKS_PER_WARP = 8;
+
 __global__ void __launch_bounds__(256)
 timedomain_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
-                  const unsigned int *__restrict__ chunk_prefix, int n_songs,
-                  unsigned int total_chunks, float *__restrict__ loud_ms,
+                  const unsigned int *__restrict__ group_prefix, int n_songs,
+                  unsigned int total_groups, float *__restrict__ loud_ms,
                   float *__restrict__ block_energy, unsigned int *__restrict__ zcr_count) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned int item = blockIdx.x * 8u + (unsigned)warp;
-    if (item >= total_chunks) return;
-    const int si = find_song(chunk_prefix, n_songs, item);
+    if (item >= total_groups) return;
+    const int si = find_song(group_prefix, n_songs, item);
     const SongDesc sd = songs[si];
-    const unsigned int ch = item - chunk_prefix[si];
+    const unsigned int grp = item - group_prefix[si];
     const float *x = pcm + sd.pcm_off;
     const unsigned int n = sd.n;
-    const unsigned int base = ch * 1024u;
-    const unsigned int len = min(1024u, n - base);
-
-    float eb[4] = {0.f, 0.f, 0.f, 0.f};
     unsigned int crossings = 0;
-    float prev_tail = (base > 0) ? __ldg(x + base - 1) : 0.f;  // sample just before this chunk
-    const bool has_prev = base > 0;
-    // all eight 16-byte loads of the lane are issued before anything consumes them
-    float v[8][4];
-    if (len == 1024u && ((sd.pcm_off + base) & 3ull) == 0) {
-        const float4 *p4 = reinterpret_cast<const float4 *>(x + base) + lane;
+    const unsigned int ch0 = grp * TD_CHUNKS_PER_WARP;
+    float prev_tail = (ch0 > 0) ? __ldg(x + ch0 * 1024u - 1) : 0.f;  // sample just before this run
+#pragma unroll 1
+    for (unsigned int ch = ch0; ch < min(ch0 + TD_CHUNKS_PER_WARP, sd.n_l); ch++) {
+        const unsigned int base = ch * 1024u;
+        const unsigned int len = min(1024u, n - base);
+        const bool has_prev = base > 0;
+        float eb[4] = {0.f, 0.f, 0.f, 0.f};
+        // all eight 16-byte loads of the lane are issued before anything consumes them
+        float v[8][4];
+        if (len == 1024u && ((sd.pcm_off + base) & 3ull) == 0) {
+            const float4 *p4 = reinterpret_cast<const float4 *>(x + base) + lane;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const float4 t = __ldg(p4 + 32 * k);
-            v[k][0] = t.x; v[k][1] = t.y; v[k][2] = t.z; v[k][3] = t.w;
+            for (int k = 0; k < 8; k++) {
+                const float4 t = __ldg(p4 + 32 * k);
+                v[k][0] = t.x; v[k][1] = t.y; v[k][2] = t.z; v[k][3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const unsigned int p = 4u * lane + 128u * k;
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[k][i] = (p + i < len) ? __ldg(x + base + p + i) : 0.f;
+            }
         }
-    } else {
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const unsigned int p = 4u * lane + 128u * k;
+            float e = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; i++) v[k][i] = (p + i < len) ? __ldg(x + base + p + i) : 0.f;
-        }
-    }
+            for (int i = 0; i < 4; i++) e += v[k][i] * v[k][i];
+            eb[k >> 1] += e;
+            // predecessor of v[k][0]: previous lane's last sample; lane 0 takes the previous row's tail
+            float pred = __shfl_up_sync(0xffffffffu, v[k][3], 1);
+            if (lane == 0) pred = prev_tail;
+            const bool have_pred = (k > 0) || (lane > 0) || has_prev;
+            float before = pred;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const unsigned int p = 4u * lane + 128u * k;
-        float e = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; i++) e += v[k][i] * v[k][i];
-        eb[k >> 1] += e;
-        // predecessor of v[k][0]: previous lane's last sample; lane 0 takes the previous row's tail
-        float pred = __shfl_up_sync(0xffffffffu, v[k][3], 1);
-        if (lane == 0) pred = prev_tail;
-        const bool have_pred = (k > 0) || (lane > 0) || has_prev;
-        float before = pred;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (p + i < len) {
-                const bool valid_pair = (i > 0) || have_pred;
-                if (valid_pair && ((before > 0.f) != (v[k][i] > 0.f))) crossings++;
+            for (int i = 0; i < 4; i++) {
+                if (p + i < len) {
+                    const bool valid_pair = (i > 0) || have_pred;
+                    if (valid_pair && ((before > 0.f) != (v[k][i] > 0.f))) crossings++;
+                }
+                before = v[k][i];
             }
-            before = v[k][i];
+            prev_tail = __shfl_sync(0xffffffffu, v[k][3], 31);
         }
-        prev_tail = __shfl_sync(0xffffffffu, v[k][3], 31);
-    }
 #pragma unroll
-    for (int b = 0; b < 4; b++) eb[b] = warp_sum(eb[b]);
-    crossings = __reduce_add_sync(0xffffffffu, crossings);
-    if (lane == 0) {
-        loud_ms[sd.l_off + ch] = (eb[0] + eb[1] + eb[2] + eb[3]) / (float)len;
-        if (crossings) atomicAdd(zcr_count + si, crossings);
-    }
-    if (lane < 4) {
-        const unsigned int blk = ch * 4u + lane;
-        if ((blk + 1u) * 256u <= n) {
-            const float e = lane == 0 ? eb[0] : lane == 1 ? eb[1] : lane == 2 ? eb[2] : eb[3];
-            block_energy[sd.e_off + blk] = e;
+        for (int b = 0; b < 4; b++) eb[b] = warp_sum(eb[b]);
+        if (lane == 0) loud_ms[sd.l_off + ch] = (eb[0] + eb[1] + eb[2] + eb[3]) / (float)len;
+        if (lane < 4) {
+            const unsigned int blk = ch * 4u + lane;
+            if ((blk + 1u) * 256u <= n) {
+                const float e = lane == 0 ? eb[0] : lane == 1 ? eb[1] : lane == 2 ? eb[2] : eb[3];
+                block_energy[sd.e_off + blk] = e;
+            }
         }
     }
+    crossings = __reduce_add_sync(0xffffffffu, crossings);
+    if (lane == 0 && crossings) atomicAdd(zcr_count + si, crossings);
 }
 
 // ---- launchers ---------------------------------------------------------------
@@ -373,12 +366,13 @@ int launch_stft512_mags(const float *pcm, const SongDesc *songs, const unsigned 
     return 1;
 }
 
-int launch_timedomain(const float *pcm, const SongDesc *songs, const unsigned int *chunk_prefix,
-                      int n_songs, unsigned int total_chunks, float *loud_ms, float *block_energy,
+// group_prefix counts groups of TD_CHUNKS_PER_WARP (= 8) loudness chunks per song
+int launch_timedomain(const float *pcm, const SongDesc *songs, const unsigned int *group_prefix,
+                      int n_songs, unsigned int total_groups, float *loud_ms, float *block_energy,
                       unsigned int *zcr_count, cudaStream_t st) {
-    if (total_chunks == 0) return 0;
-    const unsigned int grid = (total_chunks + 7u) / 8u;
-    timedomain_kernel<<<grid, 256, 0, st>>>(pcm, songs, chunk_prefix, n_songs, total_chunks, loud_ms,
+    if (total_groups == 0) return 0;
+    const unsigned int grid = (total_groups + 7u) / 8u;
+    timedomain_kernel<<<grid, 256, 0, st>>>(pcm, songs, group_prefix, n_songs, total_groups, loud_ms,
                                             block_energy, zcr_count);
     return 1;
 }

@@ -25,12 +25,7 @@ peakpick_kernel(const float *__restrict__ flux, const SongDesc *__restrict__ son
                 float *__restrict__ thr_out) {
     const unsigned int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
-    // find song (t_prefix = exclusive prefix of n_t, n_songs+1 entries)
-    int lo = 0, hi = n_songs;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (t_prefix[mid] <= gid) lo = mid; else hi = mid;
-    }
+    const int lo = find_song(t_prefix, n_songs, gid);  // t_prefix = exclusive prefix of n_t
     const SongDesc sd = songs[lo];
     const int t = (int)(gid - t_prefix[lo]);
     const float *of = flux + sd.t_off;

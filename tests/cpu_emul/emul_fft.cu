@@ -91,7 +91,7 @@ int main() {
             f8k::pass1_store(bb, v, tw.data(), buf.data());
         }
         for (int bb = 0; bb < 512; bb++) f8k::pass2(bb, tw.data(), buf.data());
-        for (int bb = 0; bb < 256; bb++) f8k::pass3(bb, buf.data());
+        for (int bb = 0; bb < 512; bb++) f8k::pass3(bb, buf.data());
         // spot-check 200 bins (full f64 DFT of 8192 x 4097 is slow-ish but fine: do all)
         std::vector<double> ma, mb;
         dft_real(a, ma, 8192);
@@ -101,21 +101,23 @@ int main() {
         double err = 0;
         for (int k = 0; k <= 4096; k++) {
             float fa, fb;
-            f8k::untangle_mag(buf[f8k::pad(f8k::xpos(k))], buf[f8k::pad(f8k::xpos((8192 - k) & 8191))], fa, fb);
+            f8k::untangle_mag(f8k::bin_value(buf.data(), k), f8k::bin_value(buf.data(), (8192 - k) & 8191), fa, fb);
             err = fmax(err, fabs(fa - ma[k]) / scale);
             err = fmax(err, fabs(fb - mb[k]) / scale);
         }
         printf("fft8192 pair: max rel err %.3e\n", err);
         worst = fmax(worst, err);
-        // hand-folded epilogue addressing must agree with pad(xpos(k)) for k and its mirror
-        for (int t = 0; t < 256; t++)
-            for (int m = 0; m < 17; m++) {
-                int k = t + 256 * m;
-                if (k > 4096) continue;
-                if (f8k::xbase(t) + m != f8k::pad(f8k::xpos(k))) { printf("xbase mismatch k=%d\n", k); return 3; }
-                int km = (8192 - k) & 8191;
-                int got = (k == 0) ? f8k::xbase(0) : (t == 0 ? f8k::xbase(0) + 32 - m : f8k::xbase(256 - t) + 31 - m);
-                if (got != f8k::pad(f8k::xpos(km))) { printf("mirror mismatch k=%d\n", k); return 3; }
+        // hand-folded epilogue addressing (as the kernel does it) must agree with bin_value()
+        for (int t = 0; t < 512; t++)
+            for (int m = 0; m < 8; m++) {
+                const int k = t + 512 * m;
+                const cpx zk = f8k::pair_sum(buf.data() + f8k::ebase(t) + 4 * m);
+                cpx zm;
+                if (k == 0) zm = zk;
+                else if (t == 0) zm = f8k::pair_diff(buf.data() + f8k::ebase(0) + 4 * (8 - m));
+                else zm = f8k::pair_diff(buf.data() + f8k::ebase(512 - t) + 4 * (7 - m));
+                const cpx rk = f8k::bin_value(buf.data(), k), rm = f8k::bin_value(buf.data(), (8192 - k) & 8191);
+                if (zk.x != rk.x || zk.y != rk.y || zm.x != rm.x || zm.y != rm.y) { printf("epilogue addressing mismatch k=%d\n", k); return 3; }
             }
         // padding must be injective
         std::vector<int> seen(f8k::BUF_CPX, 0);
