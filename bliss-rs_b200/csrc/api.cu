@@ -29,7 +29,7 @@ int launch_beattrack(const float *, const float *, const SongDesc *, int, float 
                      cudaStream_t);
 int launch_chroma_filter_table(double *, cudaStream_t);
 int launch_stft8192(const float *, const SongDesc *, const unsigned int *, int, unsigned int, const float *,
-                    const cpx *, float *, double *, unsigned char *, unsigned int *, cudaStream_t);
+                    const cpx *, const cpx *, float *, double *, unsigned char *, unsigned int *, cudaStream_t);
 int launch_tuning(const double *, const unsigned char *, const unsigned int *, const SongDesc *, int, int *,
                   cudaStream_t);
 int launch_chroma(const float *, const SongDesc *, const unsigned int *, int, unsigned int, const double *,
@@ -106,7 +106,7 @@ struct Ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     size_t ws_limit = 0;
     // constant tables
-    DevBuf t_win512, t_twA, t_hann8k, t_tw8k, t_filt;
+    DevBuf t_win512, t_twA, t_hann8k, t_tw4k, t_tw8k, t_filt;
     // wave scratch
     DevBuf blob;  // SongDesc + prefix arrays
     DevBuf mags, cand_mag, cand_bin, cand_count, cent, roll, flat, flux, thr, loud, eb, zcr, tempo, bpm,
@@ -175,10 +175,10 @@ SongGeom geom_of(uint64_t n) {
     q.n_c_comp = (uint32_t)std::min<uint64_t>(q.n_c, windows);
     q.n_l = (uint32_t)((n + 1023) / 1024);
     q.n_eb = (uint32_t)(n / 256);
-    q.n_pairs8k = (q.n_c_comp + 1) / 2;
+    q.n_pairs8k = q.n_c_comp;  // one CTA per chroma frame
     q.n_tiles = (q.n_c + 127) / 128;
     q.bpm_cap = q.n_t / 16 + 16;
-    const size_t rows = (size_t)q.n_pairs8k * 2;
+    const size_t rows = (size_t)q.n_c_comp;
     q.scratch_bytes = rows * CH_STRIDE * 4 + rows * CH_MAX_PEAKS * 9 + (size_t)q.n_s * 12 + (size_t)q.n_t * 8 +
                       (size_t)q.n_l * 4 + (size_t)q.n_eb * 4 + (size_t)q.n_tiles * 80 + (size_t)q.bpm_cap * 4 + 256;
     return q;
@@ -233,8 +233,8 @@ void plan_wave(const uint64_t *offsets, const uint64_t *n_samples, uint32_t firs
         if (d.valid) {
             w.n_t += q.n_t;
             if (!only_stft512) {
-                w.rows += (size_t)q.n_pairs8k * 2;
-                w.cands += (size_t)q.n_pairs8k * 2 * CH_MAX_PEAKS;
+                w.rows += (size_t)q.n_c_comp;
+                w.cands += (size_t)q.n_c_comp * CH_MAX_PEAKS;
                 w.n_s += q.n_s;
                 w.n_l += q.n_l;
                 w.n_eb += q.n_eb;
@@ -332,7 +332,7 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
                               g.tempo.as<float>(), g.bpm_count.as<unsigned int>(), st)); }
     { ProfScope p(K_STFT8K, st);
       p.done(launch_stft8192(d_pcm, dv.sd, dv.pair_prefix, n, w.pair_prefix[n], g.t_hann8k.as<float>(),
-                             g.t_tw8k.as<cpx>(), g.mags.as<float>(), g.cand_mag.as<double>(),
+                             g.t_tw4k.as<cpx>(), g.t_tw8k.as<cpx>(), g.mags.as<float>(), g.cand_mag.as<double>(),
                              g.cand_bin.as<unsigned char>(), g.cand_count.as<unsigned int>(), st)); }
     { ProfScope p(K_TUNING, st);
       p.done(launch_tuning(g.cand_mag.as<double>(), g.cand_bin.as<unsigned char>(),
@@ -396,8 +396,12 @@ int build_tables() {
     // periodic Hann of utils::stft (utils.rs:36-38)
     std::vector<float> hann(8192);
     for (int i = 0; i < 8192; i++) hann[i] = 0.5f - 0.5f * cosf(2.f * (float)i * PI_F / 8192.f);
-    std::vector<cpx> tw(8192);
-    for (int m = 0; m < 8192; m++) {
+    std::vector<cpx> tw4(4096), tw(256);  // W4096^m (pass twiddles) and W8192^t, t < 256 (real-FFT untangling)
+    for (int m = 0; m < 4096; m++) {
+        const double a = -2.0 * M_PI * (double)m / 4096.0;
+        tw4[m] = cpx{(float)cos(a), (float)sin(a)};
+    }
+    for (int m = 0; m < 256; m++) {
         const double a = -2.0 * M_PI * (double)m / 8192.0;
         tw[m] = cpx{(float)cos(a), (float)sin(a)};
     }
@@ -405,6 +409,8 @@ int build_tables() {
     CK(g.t_twA.ensure(twA.size() * sizeof(cpx)));
     CK(g.t_hann8k.ensure(hann.size() * 4));
     CK(g.t_tw8k.ensure(tw.size() * sizeof(cpx)));
+    CK(g.t_tw4k.ensure(tw4.size() * sizeof(cpx)));
+    CK(cudaMemcpy(g.t_tw4k.p, tw4.data(), tw4.size() * sizeof(cpx), cudaMemcpyHostToDevice));
     CK(g.t_filt.ensure((size_t)100 * CH_BINS * 12 * sizeof(double)));
     CK(cudaMemcpy(g.t_win512.p, win.data(), win.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(g.t_twA.p, twA.data(), twA.size() * sizeof(cpx), cudaMemcpyHostToDevice));
@@ -494,7 +500,7 @@ void bliss_b200_shutdown(void) {
     if (!g.inited) return;
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
-    DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw8k, &g.t_filt, &g.blob, &g.mags, &g.cand_mag,
+    DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw4k, &g.t_tw8k, &g.t_filt, &g.blob, &g.mags, &g.cand_mag,
                      &g.cand_bin, &g.cand_count, &g.cent, &g.roll, &g.flat, &g.flux, &g.thr, &g.loud, &g.eb,
                      &g.zcr, &g.tempo, &g.bpm, &g.bpm_count, &g.tuning, &g.tiles, &g.chroma_dbg, &g.pcm[0],
                      &g.pcm[1], &g.feats, &g.metric, &g.misc[0], &g.misc[1], &g.misc[2], &g.misc[3],

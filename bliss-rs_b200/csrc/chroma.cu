@@ -5,7 +5,7 @@
 //       fused with normalize_feature_sequence / extract_interval_features (:137-188)
 //   plus the table of all 100 possible chroma filterbanks (chroma.rs:197-267).
 #include "common.cuh"
-#include "fft8192.cuh"
+#include "rfft8192.cuh"
 
 namespace bliss {
 
@@ -61,9 +61,10 @@ int launch_chroma_filter_table(double *table, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------
-// K3: one CTA per pair of chroma frames.
+// K3: one CTA (256 threads) per chroma frame: 8192-point real FFT as a 4096-point complex FFT
+// (rfft8192.cuh), magnitudes to the spill buffer, pip_track peaks to the candidate list.
 // ---------------------------------------------------------------------------
-constexpr int K3_THREADS = 512;
+constexpr int K3_THREADS = 256;
 
 // one pip_track candidate test in f32 (the f64 comparisons of chroma.rs:308 are order
 // preserving on f32-exact values); `ref` stays f64 because 0.1*max is not an f32
@@ -72,235 +73,150 @@ __device__ __forceinline__ bool pip_is_peak(const float *sm, int c, double ref) 
     return after <= elem && before < elem && (double)elem > ref;
 }
 
-__global__ void __launch_bounds__(K3_THREADS, 2)
+// magnitudes of bins t + 256 m, m = M..15:  twiddle W8192^(t + 256 m) = W8192^t * W32^m
+template <int M>
+__device__ __forceinline__ void epilogue_bins(const cpx *pk, const cpx *pm, bool t0, const cpx *buf0, cpx wt,
+                                              float (&mag)[17]) {
+    if constexpr (M < 16) {
+        const cpx zk = pk[M];
+        const cpx zm = t0 ? buf0[(16 - M) & 15] : pm[-M];
+        mag[M] = r8k::untangle_mag(zk, zm, mul_tw<M, 32>(wt));
+        epilogue_bins<M + 1>(pk, pm, t0, buf0, wt, mag);
+    }
+}
+
+__global__ void __launch_bounds__(K3_THREADS, 4)
 stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
-                const unsigned int *__restrict__ pair_prefix, int n_songs,
-                const float *__restrict__ hann, const cpx *__restrict__ tw,
-                float *__restrict__ mags, double *__restrict__ cand_mag,
-                unsigned char *__restrict__ cand_bin, unsigned int *__restrict__ cand_count) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cpx *buf = reinterpret_cast<cpx *>(smem_raw);
-    __shared__ float s_red[2][K3_THREADS / 32];
+                const unsigned int *__restrict__ frame_prefix, int n_songs,
+                const float *__restrict__ hann, const cpx *__restrict__ tw4096,
+                const cpx *__restrict__ tw8192, float *__restrict__ mags,
+                double *__restrict__ cand_mag, unsigned char *__restrict__ cand_bin,
+                unsigned int *__restrict__ cand_count) {
+    __shared__ __align__(16) cpx buf[r8k::BUF_CPX];
+    __shared__ float s_red[K3_THREADS / 32];
     __shared__ unsigned int s_scan[K3_THREADS / 32];
     __shared__ unsigned int s_base;
 
     const int tid = threadIdx.x;
     const unsigned int item = blockIdx.x;
-    const int si = find_song(pair_prefix, n_songs, item);
+    const int si = find_song(frame_prefix, n_songs, item);
     const SongDesc sd = songs[si];
-    const int fA = 2 * (int)(item - pair_prefix[si]);
-    const bool hasB = (fA + 1) < (int)sd.n_c_comp;
+    const int f = (int)(item - frame_prefix[si]);
     const float *x = pcm + sd.pcm_off;
     const int n = (int)sd.n;
-    // window A starts at sample s0 = 2205 fA - 4096 (reflect padding of utils.rs:11-24 when outside)
-    const int s0 = CH_HOP * fA - 4096;
-    const bool interior = (s0 >= 0) && (s0 + (hasB ? CH_HOP : 0) + 8191 < n);
+    // the frame covers samples s0 .. s0+8191 of the reflect-padded song (utils.rs:11-24, :44-47)
+    const int s0 = CH_HOP * f - 4096;
+    const bool interior = (s0 >= 0) && (s0 + 8191 < n);
 
-    // Two real frames ride one complex FFT (A in re, B in im).  The untangling leaks
-    // eps*max(|A|,|B|) of rounding noise into the weaker frame, so when the frames differ a lot in
-    // level (digital silence next to sound) they are transformed one after the other instead:
-    // mode 0 = packed, mode 1 = A alone, mode 2 = B alone (CTA-uniform, rare).
-    // Thread t owns bins t + 512 m, m = 0..7; thread 0 also owns bin 4096 (slot 8).
-    float ma[9], mb[9];
-    ma[8] = 0.f;
-    mb[8] = 0.f;
-    int mode = 0;
-    for (;;) {
-        float pka = 0.f, pkb = 0.f;
-        {
-            const int b = tid;  // pass-1 butterfly: points b + 512 q
-            cpx v[16];
-            if (interior) {  // fast path: plain coalesced loads at constant offsets from one base
-                const float *pa = x + s0 + b;
-                const float *ph = hann + b;
-                float wa[16];
-#pragma unroll
-                for (int q = 0; q < 16; q++) wa[q] = __ldg(ph + 512 * q);
-#pragma unroll
-                for (int q = 0; q < 16; q++) v[q].x = __ldg(pa + 512 * q);
-                if (hasB) {
-#pragma unroll
-                    for (int q = 0; q < 16; q++) v[q].y = __ldg(pa + CH_HOP + 512 * q);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 16; q++) v[q].y = 0.f;
-                }
-#pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    v[q].x *= wa[q];
-                    v[q].y *= wa[q];
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    const int m = b + 512 * q;
-                    const float w = __ldg(hann + m);
-                    v[q].x = w * f8k::padded_sample(x, n, (long long)s0 + 4096 + m);
-                    v[q].y = hasB ? w * f8k::padded_sample(x, n, (long long)s0 + 4096 + CH_HOP + m) : 0.f;
-                }
-            }
+    // pass 1 straight from global memory: z[nn] = w[2nn] x[2nn] + i w[2nn+1] x[2nn+1], nn = tid + 256 q
+    {
+        cpx v[16];
+        const float2 *ph = reinterpret_cast<const float2 *>(hann) + tid;
+        if (interior) {
+            const float *pa = x + s0 + 2 * tid;
 #pragma unroll
             for (int q = 0; q < 16; q++) {
-                pka = fmaxf(pka, fabsf(v[q].x));
-                pkb = fmaxf(pkb, fabsf(v[q].y));
-                if (mode == 1) v[q].y = 0.f;
-                if (mode == 2) v[q] = cpx{v[q].y, 0.f};
+                const float2 w = __ldg(ph + 256 * q);
+                v[q] = cpx{__ldg(pa + 512 * q) * w.x, __ldg(pa + 512 * q + 1) * w.y};
             }
-            f8k::pass1_store(b, v, tw, buf);
-        }
-        if (mode == 0 && hasB) {
+        } else {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                pka = fmaxf(pka, __shfl_xor_sync(0xffffffffu, pka, o));
-                pkb = fmaxf(pkb, __shfl_xor_sync(0xffffffffu, pkb, o));
-            }
-            if ((tid & 31) == 0) {
-                s_red[0][tid >> 5] = pka;
-                s_red[1][tid >> 5] = pkb;
+            for (int q = 0; q < 16; q++) {
+                const float2 w = __ldg(ph + 256 * q);
+                const long long i0 = (long long)s0 + 2 * (tid + 256 * q);
+                v[q] = cpx{r8k::reflect_sample(x, n, i0) * w.x, r8k::reflect_sample(x, n, i0 + 1) * w.y};
             }
         }
-        __syncthreads();
-        if (mode == 0 && hasB) {
-            float fa = s_red[0][0], fb = s_red[1][0];
-#pragma unroll
-            for (int w = 1; w < K3_THREADS / 32; w++) {
-                fa = fmaxf(fa, s_red[0][w]);
-                fb = fmaxf(fb, s_red[1][w]);
-            }
-            if (fa > 8.f * fb || fb > 8.f * fa) {
-                mode = 1;
-                __syncthreads();  // s_red / buf are about to be rewritten
-                continue;
-            }
-        }
-        f8k::pass2(tid, tw, buf);
-        __syncthreads();
-        f8k::pass3(tid, buf);
-        __syncthreads();
-        // natural-order magnitudes with the closing radix-2 folded in (fft8192.cuh):
-        //   X[k] = u0 + u1 (k < 4096),  X[8192 - k] = u0' - u1' at the pair of 4096 - k
-        {
-            const cpx *pk = buf + f8k::ebase(tid);
-            const cpx *pm = (tid == 0) ? buf + f8k::ebase(0) + 32 : buf + f8k::ebase(512 - tid) + 28;
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                const cpx zk = f8k::pair_sum(pk + 4 * m);
-                const cpx zm = (tid == 0 && m == 0) ? zk : f8k::pair_diff(pm - 4 * m);
-                float ta, tb;
-                f8k::untangle_mag(zk, zm, ta, tb);
-                if (mode != 2) ma[m] = ta;
-                if (mode == 0) mb[m] = tb;
-                if (mode == 2) mb[m] = ta;
-            }
-            if (tid == 0) {  // bin 4096 is its own mirror
-                const cpx z = f8k::pair_diff(buf);
-                float ta, tb;
-                f8k::untangle_mag(z, z, ta, tb);
-                if (mode != 2) ma[8] = ta;
-                if (mode == 0) mb[8] = tb;
-                if (mode == 2) mb[8] = ta;
-            }
-        }
-        if (mode != 1) break;
-        mode = 2;
-        __syncthreads();  // all reads of buf done before the next transform overwrites it
-    }
-    float mxa = 0.f, mxb = 0.f;
-#pragma unroll
-    for (int m = 0; m < 9; m++) {
-        mxa = fmaxf(mxa, ma[m]);
-        mxb = fmaxf(mxb, mb[m]);
-    }
-    __syncthreads();  // everyone has read buf; reuse it for the magnitudes
-    float *sA = reinterpret_cast<float *>(smem_raw);
-    float *sB = sA + CH_STRIDE;
-    float *gA = mags + (sd.mag_off + (unsigned long long)fA) * CH_STRIDE;
-    float *gB = gA + CH_STRIDE;
-#pragma unroll
-    for (int m = 0; m < 8; m++) {
-        const int k = tid + 512 * m;
-        sA[k] = ma[m];
-        sB[k] = mb[m];
-        gA[k] = ma[m];
-        if (hasB) gB[k] = mb[m];
-    }
-    if (tid == 0) {
-        sA[4096] = ma[8];
-        sB[4096] = mb[8];
-        gA[4096] = ma[8];
-        if (hasB) gB[4096] = mb[8];
-    }
-    // frame maxima (pip_track's ref_value = 0.1 * max over all bins, chroma.rs:289-293)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mxa = fmaxf(mxa, __shfl_xor_sync(0xffffffffu, mxa, o));
-        mxb = fmaxf(mxb, __shfl_xor_sync(0xffffffffu, mxb, o));
-    }
-    if ((tid & 31) == 0) {
-        s_red[0][tid >> 5] = mxa;
-        s_red[1][tid >> 5] = mxb;
+        r8k::pass1_store(tid, v, tw4096, buf);
     }
     __syncthreads();
-    float fmax_a = s_red[0][0], fmax_b = s_red[1][0];
-#pragma unroll
-    for (int w = 1; w < K3_THREADS / 32; w++) {
-        fmax_a = fmaxf(fmax_a, s_red[0][w]);
-        fmax_b = fmaxf(fmax_b, s_red[1][w]);
+    r8k::pass2(tid, tw4096, buf);
+    __syncthreads();
+    r8k::pass3(tid, buf);
+    __syncthreads();
+
+    // natural-order magnitudes: thread owns bins tid + 256 m, m = 0..15; thread 0 also bin 4096
+    float mag[17];
+    mag[16] = 0.f;
+    {
+        const cpx wt = tw8192[tid];
+        const cpx *pk = buf + r8k::zbase(tid);
+        const cpx *pm = buf + r8k::zbase((256 - tid) & 255) + 15;
+        epilogue_bins<0>(pk, pm, tid == 0, buf, wt, mag);
+        if (tid == 0) mag[16] = r8k::untangle_mag(buf[0], buf[0], cpx{-1.f, 0.f});
     }
+    float mx = 0.f;
+#pragma unroll
+    for (int m = 0; m < 17; m++) mx = fmaxf(mx, mag[m]);
+    __syncthreads();  // everyone has read buf; reuse it for the magnitudes
+    float *sm = reinterpret_cast<float *>(buf);
+    float *gm = mags + (sd.mag_off + (unsigned long long)f) * CH_STRIDE;
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+        sm[tid + 256 * m] = mag[m];
+        gm[tid + 256 * m] = mag[m];
+    }
+    if (tid == 0) {
+        sm[4096] = mag[16];
+        gm[4096] = mag[16];
+    }
+    // frame maximum (pip_track's ref_value = 0.1 * max over all bins, chroma.rs:289-293)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    __syncthreads();
+    float fmx = s_red[0];
+#pragma unroll
+    for (int w = 1; w < K3_THREADS / 32; w++) fmx = fmaxf(fmx, s_red[w]);
 
     // pip_track on centre bins 57..1483 (beginning = 56, end = 1486 for n_fft = 8192).
     // Phase 1 counts this thread's peaks, a block scan reserves the output range, phase 2 emits.
-    const int nframes_here = hasB ? 2 : 1;
-#pragma unroll 1
-    for (int fr = 0; fr < nframes_here; fr++) {
-        const float *sm = fr ? sB : sA;
-        const double ref = 0.1 * (double)(fr ? fmax_b : fmax_a);
-        unsigned int flags = 0;
+    const double ref = 0.1 * (double)fmx;
+    unsigned int flags = 0;
 #pragma unroll
-        for (int m = 0; m < 3; m++) {
-            const int c = 57 + tid + K3_THREADS * m;
-            if (c <= 1483 && pip_is_peak(sm, c, ref)) flags |= 1u << m;
-        }
-        const int cnt = __popc(flags);
-        unsigned int incl = (unsigned)cnt;
+    for (int m = 0; m < 6; m++) {
+        const int c = 57 + tid + K3_THREADS * m;
+        if (c <= 1483 && pip_is_peak(sm, c, ref)) flags |= 1u << m;
+    }
+    const int cnt = __popc(flags);
+    unsigned int incl = (unsigned)cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((tid & 31) >= o) incl += t;
-        }
-        __syncthreads();
-        if ((tid & 31) == 31) s_scan[tid >> 5] = incl;
-        __syncthreads();
-        unsigned int woff = 0, tot = 0;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += t;
+    }
+    if ((tid & 31) == 31) s_scan[tid >> 5] = incl;
+    __syncthreads();
+    unsigned int woff = 0, tot = 0;
 #pragma unroll
-        for (int w = 0; w < K3_THREADS / 32; w++) {
-            if (w < (tid >> 5)) woff += s_scan[w];
-            tot += s_scan[w];
-        }
-        if (tid == 0) s_base = tot ? atomicAdd(cand_count + si, tot) : 0u;
-        __syncthreads();
-        unsigned long long dst = sd.cand_off + s_base + woff + (incl - (unsigned)cnt);
-        while (flags) {
-            const int m = __ffs(flags) - 1;
-            flags &= flags - 1;
-            const int c = 57 + tid + K3_THREADS * m;
-            const double before = (double)sm[c - 1], elem = (double)sm[c], after = (double)sm[c + 1];
-            const double avg = 0.5 * (after - before);
-            double shift = 2. * elem - after - before;
-            if (fabs(shift) < 2.2250738585072014e-308) shift += 1.;
-            shift = avg / shift;
-            const double pitch = ((double)c + shift) * (double)SAMPLE_RATE / 8192.0;
-            // pitch_tuning's residue bin (chroma.rs:342-348), tuning 0, 12 bins/octave
-            double v = pitch / (440.0 / 16.);
-            v = log2(v);
-            v = fmod(12.0 * v, 1.0);
-            if (v >= 0.5) v -= 1.;
-            int idx = (int)((v - -0.5) / 0.01);
-            idx = idx < 0 ? 0 : (idx > 99 ? 99 : idx);
-            cand_mag[dst] = elem + 0.5 * avg * shift;
-            cand_bin[dst] = (unsigned char)idx;
-            dst++;
-        }
+    for (int w = 0; w < K3_THREADS / 32; w++) {
+        if (w < (tid >> 5)) woff += s_scan[w];
+        tot += s_scan[w];
+    }
+    if (tot == 0) return;
+    if (tid == 0) s_base = atomicAdd(cand_count + si, tot);
+    __syncthreads();
+    unsigned long long dst = sd.cand_off + s_base + woff + (incl - (unsigned)cnt);
+    while (flags) {
+        const int m = __ffs(flags) - 1;
+        flags &= flags - 1;
+        const int c = 57 + tid + K3_THREADS * m;
+        const double before = (double)sm[c - 1], elem = (double)sm[c], after = (double)sm[c + 1];
+        const double avg = 0.5 * (after - before);
+        double shift = 2. * elem - after - before;
+        if (fabs(shift) < 2.2250738585072014e-308) shift += 1.;
+        shift = avg / shift;
+        const double pitch = ((double)c + shift) * (double)SAMPLE_RATE / 8192.0;
+        // pitch_tuning's residue bin (chroma.rs:342-348), tuning 0, 12 bins/octave
+        double v = pitch / (440.0 / 16.);
+        v = log2(v);
+        v = fmod(12.0 * v, 1.0);
+        if (v >= 0.5) v -= 1.;
+        int idx = (int)((v - -0.5) / 0.01);
+        idx = idx < 0 ? 0 : (idx > 99 ? 99 : idx);
+        cand_mag[dst] = elem + 0.5 * avg * shift;
+        cand_bin[dst] = (unsigned char)idx;
+        dst++;
     }
 }
 
@@ -593,20 +509,13 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
 }
 
 // ---- launchers ---------------------------------------------------------------
-size_t stft8192_smem_bytes() { return sizeof(cpx) * f8k::BUF_CPX; }
-
-int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int *pair_prefix, int n_songs,
-                    unsigned int total_pairs, const float *hann, const cpx *tw, float *mags,
-                    double *cand_mag, unsigned char *cand_bin, unsigned int *cand_count, cudaStream_t st) {
-    if (total_pairs == 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(stft8192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)stft8192_smem_bytes());
-        attr_set = true;
-    }
-    stft8192_kernel<<<total_pairs, K3_THREADS, stft8192_smem_bytes(), st>>>(
-        pcm, songs, pair_prefix, n_songs, hann, tw, mags, cand_mag, cand_bin, cand_count);
+int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int *frame_prefix, int n_songs,
+                    unsigned int total_frames, const float *hann, const cpx *tw4096, const cpx *tw8192,
+                    float *mags, double *cand_mag, unsigned char *cand_bin, unsigned int *cand_count,
+                    cudaStream_t st) {
+    if (total_frames == 0) return 0;
+    stft8192_kernel<<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw4096,
+                                                         tw8192, mags, cand_mag, cand_bin, cand_count);
     return 1;
 }
 

@@ -1,0 +1,99 @@
+// rfft8192.cuh -- 8192-point REAL FFT of one reflect-padded Hann frame, computed as a
+// 4096-point complex FFT of z[n] = x[2n] + i x[2n+1] followed by the real-input untangling
+//   X[k] = (Z[k] + conj Z[N/2-k]) / 2  -  i W_N^k (Z[k] - conj Z[N/2-k]) / 2,   N = 8192.
+// 4096 = 16 x 16 x 16: three in-register radix-16 passes over one in-place shared-memory buffer
+// (decimation in frequency), ONE butterfly per thread per pass with 256 threads, 34 KB per frame.
+//
+// After pass 3, Z[k] with k = k1 + 16 k2 + 256 k3 lives at logical index 256 k1 + 16 k2 + k3;
+// logical index i is stored at pad(i) = i + (i>>4) + (i>>8), which makes every pass and the
+// natural-order gather of the epilogue bank-conflict free.  All addressing is base(thread) +
+// constant * slot (pad() folded in by hand, see the comments at each pass).
+//
+// Replaces the per-frame rustfft call of utils::stft (src/utils.rs:41-61).
+// __host__ __device__ so tests/cpu_emul can run the passes thread by thread.
+#pragma once
+#include "fft_regs.cuh"
+
+namespace bliss {
+namespace r8k {
+
+constexpr int NC = 4096;                       // complex points
+constexpr int BUF_CPX = 4096 + 256 + 16 + 16;  // pad(4095) + 1 = 4366 -> round up
+BLISS_HD int pad(int i) { return i + (i >> 4) + (i >> 8); }
+
+// pass 1: butterfly b in [0,256): v[q] = z[b + 256 q];  pad(b + 256 k1) = b + (b>>4) + 273 k1
+BLISS_HD void pass1_store(int b, cpx (&v)[16], const cpx *tw4096 /*W4096^m, m < 4096*/, cpx *buf) {
+    fft_dif<16>(v);
+    cpx *o = buf + b + (b >> 4);
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        const int k1 = bitrev(s, 4);
+        cpx r = v[s];
+        if (k1 != 0) r = cmul(r, tw4096[b * k1]);
+        o[273 * k1] = r;
+    }
+}
+
+// pass 2: butterfly b in [0,256): blk = b>>4 (k1), j = b&15; radix 16 at stride 16 inside the
+// 256-block;  pad(256 blk + j + 16 q) = 273 blk + j + 17 q;  twiddle W256^(j k2) = W4096^(16 j k2)
+BLISS_HD void pass2(int b, const cpx *tw4096, cpx *buf) {
+    const int blk = b >> 4, j = b & 15;
+    cpx *p = buf + 273 * blk + j;
+    cpx v[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) v[q] = p[17 * q];
+    fft_dif<16>(v);
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        const int k2 = bitrev(s, 4);
+        cpx o = v[s];
+        if (k2 != 0) o = cmul(o, tw4096[(16 * j) * k2]);
+        p[17 * k2] = o;
+    }
+}
+
+// pass 3: butterfly b in [0,256): 16 consecutive logical elements;  pad(16 b + q) = 17 b + (b>>4) + q
+BLISS_HD void pass3(int b, cpx *buf) {
+    cpx *p = buf + 17 * b + (b >> 4);
+    cpx v[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) v[q] = p[q];
+    fft_dif<16>(v);
+#pragma unroll
+    for (int s = 0; s < 16; s++) p[bitrev(s, 4)] = v[s];
+}
+
+// padded position of Z[t + 256 m], t < 256, m < 16:  zbase(t) + m
+BLISS_HD int zbase(int t) { return 273 * (t & 15) + 17 * (t >> 4); }
+
+// generic accessor (CPU emulation test)
+BLISS_HD cpx z_value(const cpx *buf, int k) {
+    return buf[pad(256 * (k & 15) + 16 * ((k >> 4) & 15) + (k >> 8))];
+}
+
+// |X[k]| from Z[k], Z[(4096-k)%4096] and w = W8192^k, as `(re*re + im*im).sqrt()` in f32
+// (src/utils.rs:57-60)
+BLISS_HD float untangle_mag(cpx zk, cpx zm, cpx w) {
+    // E = (Zk + conj Zm)/2, O = (Zk - conj Zm)/2;  X = E - i w O
+    const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
+    const float orr = 0.5f * (zk.x - zm.x), oi = 0.5f * (zk.y + zm.y);
+    // w O
+    const float pr = w.x * orr - w.y * oi, pi = w.x * oi + w.y * orr;
+    // -i (pr + i pi) = pi - i pr
+    const float xr = er + pi, xi = ei - pr;
+#ifdef __CUDA_ARCH__
+    return __fsqrt_rn(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi)));
+#else
+    return sqrtf(xr * xr + xi * xi);
+#endif
+}
+
+// reflect-padded sample (utils.rs:11-24): idx relative to the song, may be < 0 or >= n
+BLISS_HD float reflect_sample(const float *x, int n, long long idx) {
+    if (idx < 0) idx = -idx;
+    else if (idx >= n) idx = 2ll * (n - 1) - idx;
+    return x[idx];
+}
+
+}  // namespace r8k
+}  // namespace bliss

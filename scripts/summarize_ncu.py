@@ -1,0 +1,56 @@
+#!/usr/bin/env python3
+"""Turns an ncu report (.ncu-rep, brought back in gpurun_out/) into the tracked summaries under
+profiles/: one markdown table per capture with duration, DRAM traffic, pipe utilisation, occupancy
+and the PC-sampling stall mix of every kernel of this repo.
+
+  python scripts/summarize_ncu.py gpurun_out/prof_r01.ncu-rep profiles/ncu_r01_full.md [songs]
+"""
+import csv
+import io
+import subprocess
+import sys
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    songs = int(sys.argv[3]) if len(sys.argv) > 3 else None
+    raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], stderr=subprocess.DEVNULL).decode()
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, data = rows[0], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+
+    def g(r, name, default=""):
+        return r[col[name]] if name in col else default
+
+    stall_cols = [i for i, h in enumerate(hdr) if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued")]
+    lines = ["# ncu --set full summary of `%s`" % rep, ""]
+    if songs:
+        lines.append("Workload: bench.py step over %d synthetic 3-min tracks (one launch of each kernel)." % songs)
+        lines.append("")
+    lines.append("| kernel | grid x block | regs | time ms | DRAM rd GB | DRAM wr GB | DRAM % peak | issue active % | "
+                 "warps active % | fma pipe % | fp64 pipe % | smem wavefronts M | bank conflicts M | top stalls |")
+    lines.append("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+    for r in data:
+        name = g(r, "Kernel Name").split("(")[0].replace("void ", "")
+        tot = sum(float(r[i] or 0) for i in stall_cols) or 1.0
+        st = sorted(((float(r[i] or 0) / tot * 100, hdr[i].replace("smsp__pcsamp_warps_issue_stalled_", "")) for i in stall_cols), reverse=True)[:4]
+        f = lambda k, d=2: ("%%.%df" % d) % float(g(r, k, "0") or 0)
+        lines.append("| %s | %s x %s | %s | %s | %s | %s | %s | %s | %s | %s | %s | %.1f | %.1f | %s |" % (
+            name, g(r, "launch__grid_size"), g(r, "launch__block_size"), g(r, "launch__registers_per_thread"),
+            f("gpu__time_duration.sum", 3), f("dram__bytes_read.sum", 3), f("dram__bytes_write.sum", 3),
+            f("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", 1), f("smsp__issue_active.avg.pct_of_peak_sustained_active", 1),
+            f("sm__warps_active.avg.pct_of_peak_sustained_active", 1), f("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", 1),
+            f("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", 1),
+            float(g(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "0") or 0) / 1e6,
+            float(g(r, "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "0") or 0) / 1e6,
+            ", ".join("%s %.0f%%" % (n, v) for v, n in st)))
+    lines.append("")
+    lines.append("Units as printed by `ncu --page raw --csv` (ms, GB = 1e9 bytes). Captured with "
+                 "`--set full --clock-control none --import-source on`; durations under ncu are serialised and "
+                 "cold-cache, compare shares, not absolutes (the timed numbers are in the bench JSON).")
+    open(out, "w").write("\n".join(lines) + "\n")
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()

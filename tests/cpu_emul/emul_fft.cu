@@ -7,7 +7,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "../../bliss-rs_b200/csrc/fft8192.cuh"
+#include "../../bliss-rs_b200/csrc/rfft8192.cuh"
 #include "../../bliss-rs_b200/csrc/pvoc512.cuh"
 
 using namespace bliss;
@@ -72,58 +72,64 @@ int main() {
         printf("fft512 pair: max rel err %.3e\n", err);
         worst = fmax(worst, err);
     }
-    // ---------------- 8192-point, two frames per CTA ----------------
+    // ---------------- 8192-point real FFT as 4096 complex, one frame per CTA ----------------
     {
-        std::vector<cpx> tw(8192);
-        for (int m = 0; m < 8192; m++) {
-            double a = -2.0 * M_PI * (double)m / 8192.0;
+        std::vector<cpx> tw(4096), tw8(256);
+        for (int m = 0; m < 4096; m++) {
+            double a = -2.0 * M_PI * (double)m / 4096.0;
             tw[m] = cpx{(float)cos(a), (float)sin(a)};
         }
-        std::vector<double> a(8192), b(8192);
-        for (int i = 0; i < 8192; i++) {
-            a[i] = (rand() / (double)RAND_MAX - 0.5);
-            b[i] = (rand() / (double)RAND_MAX - 0.5) * 2.0;
+        for (int t = 0; t < 256; t++) {
+            double a = -2.0 * M_PI * (double)t / 8192.0;
+            tw8[t] = cpx{(float)cos(a), (float)sin(a)};
         }
-        std::vector<cpx> buf(f8k::BUF_CPX);
-        for (int bb = 0; bb < 512; bb++) {
+        std::vector<double> a(8192);
+        for (int i = 0; i < 8192; i++) a[i] = (rand() / (double)RAND_MAX - 0.5);
+        std::vector<cpx> buf(r8k::BUF_CPX);
+        for (int bb = 0; bb < 256; bb++) {
             cpx v[16];
-            for (int q = 0; q < 16; q++) v[q] = cpx{(float)a[bb + 512 * q], (float)b[bb + 512 * q]};
-            f8k::pass1_store(bb, v, tw.data(), buf.data());
-        }
-        for (int bb = 0; bb < 512; bb++) f8k::pass2(bb, tw.data(), buf.data());
-        for (int bb = 0; bb < 512; bb++) f8k::pass3(bb, buf.data());
-        // spot-check 200 bins (full f64 DFT of 8192 x 4097 is slow-ish but fine: do all)
-        std::vector<double> ma, mb;
-        dft_real(a, ma, 8192);
-        dft_real(b, mb, 8192);
-        double scale = 0;
-        for (int k = 0; k <= 4096; k++) scale = fmax(scale, fmax(ma[k], mb[k]));
-        double err = 0;
-        for (int k = 0; k <= 4096; k++) {
-            float fa, fb;
-            f8k::untangle_mag(f8k::bin_value(buf.data(), k), f8k::bin_value(buf.data(), (8192 - k) & 8191), fa, fb);
-            err = fmax(err, fabs(fa - ma[k]) / scale);
-            err = fmax(err, fabs(fb - mb[k]) / scale);
-        }
-        printf("fft8192 pair: max rel err %.3e\n", err);
-        worst = fmax(worst, err);
-        // hand-folded epilogue addressing (as the kernel does it) must agree with bin_value()
-        for (int t = 0; t < 512; t++)
-            for (int m = 0; m < 8; m++) {
-                const int k = t + 512 * m;
-                const cpx zk = f8k::pair_sum(buf.data() + f8k::ebase(t) + 4 * m);
-                cpx zm;
-                if (k == 0) zm = zk;
-                else if (t == 0) zm = f8k::pair_diff(buf.data() + f8k::ebase(0) + 4 * (8 - m));
-                else zm = f8k::pair_diff(buf.data() + f8k::ebase(512 - t) + 4 * (7 - m));
-                const cpx rk = f8k::bin_value(buf.data(), k), rm = f8k::bin_value(buf.data(), (8192 - k) & 8191);
-                if (zk.x != rk.x || zk.y != rk.y || zm.x != rm.x || zm.y != rm.y) { printf("epilogue addressing mismatch k=%d\n", k); return 3; }
+            for (int q = 0; q < 16; q++) {
+                const int nn = bb + 256 * q;
+                v[q] = cpx{(float)a[2 * nn], (float)a[2 * nn + 1]};
             }
-        // padding must be injective
-        std::vector<int> seen(f8k::BUF_CPX, 0);
-        for (int i = 0; i < 8192; i++) {
-            int p = f8k::pad(i);
-            if (p >= f8k::BUF_CPX || seen[p]++) { printf("pad collision at %d\n", i); return 2; }
+            r8k::pass1_store(bb, v, tw.data(), buf.data());
+        }
+        for (int bb = 0; bb < 256; bb++) r8k::pass2(bb, tw.data(), buf.data());
+        for (int bb = 0; bb < 256; bb++) r8k::pass3(bb, buf.data());
+        std::vector<double> ma;
+        dft_real(a, ma, 8192);
+        double scale = 0;
+        for (int k = 0; k <= 4096; k++) scale = fmax(scale, ma[k]);
+        double err = 0;
+        // epilogue exactly as the kernel addresses it: thread t owns bins t + 256 m
+        for (int t = 0; t < 256; t++) {
+            const cpx *pk = buf.data() + r8k::zbase(t);
+            for (int m = 0; m < 16; m++) {
+                const int k = t + 256 * m;
+                const cpx zk = pk[m];
+                cpx zm;
+                if (t == 0) zm = buf[r8k::zbase(0) + ((16 - m) & 15)];
+                else zm = buf[r8k::zbase(256 - t) + 15 - m];
+                const cpx chk = r8k::z_value(buf.data(), (4096 - k) & 4095);
+                if (zm.x != chk.x || zm.y != chk.y) { printf("mirror addressing mismatch k=%d\n", k); return 3; }
+                const double ang = -2.0 * M_PI * (double)k / 8192.0;
+                const cpx w = cmul(tw8[t], cpx{(float)cos(-2.0 * M_PI * m / 32.0), (float)sin(-2.0 * M_PI * m / 32.0)});
+                (void)ang;
+                const float mg = r8k::untangle_mag(zk, zm, w);
+                err = fmax(err, fabs(mg - ma[k]) / scale);
+            }
+        }
+        {
+            const cpx z0 = buf[r8k::zbase(0)];
+            const float mg = r8k::untangle_mag(z0, z0, cpx{-1.f, 0.f});
+            err = fmax(err, fabs(mg - ma[4096]) / scale);
+        }
+        printf("rfft8192 (4096 complex): max rel err %.3e\n", err);
+        worst = fmax(worst, err);
+        std::vector<int> seen(r8k::BUF_CPX, 0);
+        for (int i = 0; i < 4096; i++) {
+            int p = r8k::pad(i);
+            if (p >= r8k::BUF_CPX || seen[p]++) { printf("pad collision at %d\n", i); return 2; }
         }
     }
     if (worst > 5e-6) { printf("FAIL\n"); return 1; }
