@@ -29,7 +29,8 @@ int launch_beattrack(const float *, const float *, const SongDesc *, int, float 
                      cudaStream_t);
 int launch_chroma_filter_table(double *, cudaStream_t);
 int launch_stft8192(const float *, const SongDesc *, const unsigned int *, int, unsigned int, const float *,
-                    const cpx *, const cpx *, float *, double *, unsigned char *, unsigned int *, cudaStream_t);
+                    const cpx *, const cpx *, const cpx *, float *, double *, unsigned char *, unsigned int *,
+                    cudaStream_t);
 int launch_tuning(const double *, const unsigned char *, const unsigned int *, const SongDesc *, int, int *,
                   cudaStream_t);
 int launch_chroma(const float *, const SongDesc *, const unsigned int *, int, unsigned int, const double *,
@@ -106,7 +107,7 @@ struct Ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     size_t ws_limit = 0;
     // constant tables
-    DevBuf t_win512, t_twA, t_hann8k, t_tw4k, t_tw8k, t_filt;
+    DevBuf t_win512, t_twA, t_hann8k, t_tw4k, t_tw2, t_tw8k, t_filt;
     // wave scratch
     DevBuf blob;  // SongDesc + prefix arrays
     DevBuf mags, cand_mag, cand_bin, cand_count, cent, roll, flat, flux, thr, loud, eb, zcr, tempo, bpm,
@@ -176,7 +177,7 @@ SongGeom geom_of(uint64_t n) {
     q.n_l = (uint32_t)((n + 1023) / 1024);
     q.n_eb = (uint32_t)(n / 256);
     q.n_pairs8k = q.n_c_comp;  // one CTA per chroma frame
-    q.n_tiles = (q.n_c + 127) / 128;
+    q.n_tiles = (q.n_c + CH_TILE_FRAMES - 1) / CH_TILE_FRAMES;
     q.bpm_cap = q.n_t / 16 + 16;
     const size_t rows = (size_t)q.n_c_comp;
     q.scratch_bytes = rows * CH_STRIDE * 4 + rows * CH_MAX_PEAKS * 9 + (size_t)q.n_s * 12 + (size_t)q.n_t * 8 +
@@ -312,7 +313,7 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
     CK(g.bpm_count.ensure((size_t)n * 4));
     CK(g.tuning.ensure((size_t)n * 4));
     CK(g.tiles.ensure(std::max<size_t>(w.tiles, 1) * 10 * sizeof(double)));
-    if (debug) CK(g.chroma_dbg.ensure(std::max<size_t>(w.tiles, 1) * 128 * 12 * sizeof(double)));
+    if (debug) CK(g.chroma_dbg.ensure(std::max<size_t>(w.tiles, 1) * CH_TILE_FRAMES * 12 * sizeof(double)));
     WaveDev dv;
     int rc = upload_plan(w, st, dv);
     if (rc) return rc;
@@ -332,7 +333,7 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
                               g.tempo.as<float>(), g.bpm_count.as<unsigned int>(), st)); }
     { ProfScope p(K_STFT8K, st);
       p.done(launch_stft8192(d_pcm, dv.sd, dv.pair_prefix, n, w.pair_prefix[n], g.t_hann8k.as<float>(),
-                             g.t_tw4k.as<cpx>(), g.t_tw8k.as<cpx>(), g.mags.as<float>(), g.cand_mag.as<double>(),
+                             g.t_tw4k.as<cpx>(), g.t_tw2.as<cpx>(), g.t_tw8k.as<cpx>(), g.mags.as<float>(), g.cand_mag.as<double>(),
                              g.cand_bin.as<unsigned char>(), g.cand_count.as<unsigned int>(), st)); }
     { ProfScope p(K_TUNING, st);
       p.done(launch_tuning(g.cand_mag.as<double>(), g.cand_bin.as<unsigned char>(),
@@ -396,11 +397,19 @@ int build_tables() {
     // periodic Hann of utils::stft (utils.rs:36-38)
     std::vector<float> hann(8192);
     for (int i = 0; i < 8192; i++) hann[i] = 0.5f - 0.5f * cosf(2.f * (float)i * PI_F / 8192.f);
-    std::vector<cpx> tw4(4096), tw(256);  // W4096^m (pass twiddles) and W8192^t, t < 256 (real-FFT untangling)
-    for (int m = 0; m < 4096; m++) {
-        const double a = -2.0 * M_PI * (double)m / 4096.0;
-        tw4[m] = cpx{(float)cos(a), (float)sin(a)};
-    }
+    // pass-1 twiddles [k1][b] = W4096^(b k1), pass-2 twiddles [k2][j] = W256^(j k2), and W8192^t, t < 256
+    // (real-FFT untangling): rfft8192.cuh
+    std::vector<cpx> tw4(4096), tw2(256), tw(256);
+    for (int k1 = 0; k1 < 16; k1++)
+        for (int b = 0; b < 256; b++) {
+            const double a = -2.0 * M_PI * (double)(b * k1) / 4096.0;
+            tw4[k1 * 256 + b] = cpx{(float)cos(a), (float)sin(a)};
+        }
+    for (int k2 = 0; k2 < 16; k2++)
+        for (int j = 0; j < 16; j++) {
+            const double a = -2.0 * M_PI * (double)(j * k2) / 256.0;
+            tw2[k2 * 16 + j] = cpx{(float)cos(a), (float)sin(a)};
+        }
     for (int m = 0; m < 256; m++) {
         const double a = -2.0 * M_PI * (double)m / 8192.0;
         tw[m] = cpx{(float)cos(a), (float)sin(a)};
@@ -411,6 +420,8 @@ int build_tables() {
     CK(g.t_tw8k.ensure(tw.size() * sizeof(cpx)));
     CK(g.t_tw4k.ensure(tw4.size() * sizeof(cpx)));
     CK(cudaMemcpy(g.t_tw4k.p, tw4.data(), tw4.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+    CK(g.t_tw2.ensure(tw2.size() * sizeof(cpx)));
+    CK(cudaMemcpy(g.t_tw2.p, tw2.data(), tw2.size() * sizeof(cpx), cudaMemcpyHostToDevice));
     CK(g.t_filt.ensure((size_t)100 * CH_BINS * 12 * sizeof(double)));
     CK(cudaMemcpy(g.t_win512.p, win.data(), win.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(g.t_twA.p, twA.data(), twA.size() * sizeof(cpx), cudaMemcpyHostToDevice));
@@ -500,7 +511,7 @@ void bliss_b200_shutdown(void) {
     if (!g.inited) return;
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
-    DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw4k, &g.t_tw8k, &g.t_filt, &g.blob, &g.mags, &g.cand_mag,
+    DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw4k, &g.t_tw2, &g.t_tw8k, &g.t_filt, &g.blob, &g.mags, &g.cand_mag,
                      &g.cand_bin, &g.cand_count, &g.cent, &g.roll, &g.flat, &g.flux, &g.thr, &g.loud, &g.eb,
                      &g.zcr, &g.tempo, &g.bpm, &g.bpm_count, &g.tuning, &g.tiles, &g.chroma_dbg, &g.pcm[0],
                      &g.pcm[1], &g.feats, &g.metric, &g.misc[0], &g.misc[1], &g.misc[2], &g.misc[3],
@@ -551,7 +562,8 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
                                uint16_t ver, float *out, int32_t *status, bool debug) {
     const uint32_t dim = bliss_b200_feature_count(ver);
     CK(g.feats.ensure((size_t)n_songs * dim * 4));
-    const size_t chunk_budget = std::min<size_t>((size_t)2 << 30, std::max<size_t>(g.ws_limit / 8, (size_t)64 << 20));
+    // small chunks keep the copy/compute pipeline's fill and drain short (the path is PCIe-bound)
+    const size_t chunk_budget = std::min<size_t>((size_t)384 << 20, std::max<size_t>(g.ws_limit / 8, (size_t)64 << 20));
     cudaEvent_t ev_copy[2], ev_done[2];
     for (int i = 0; i < 2; i++) {
         CK(cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming));

@@ -88,16 +88,19 @@ __device__ __forceinline__ void epilogue_bins(const cpx *pk, const cpx *pm, bool
 __global__ void __launch_bounds__(K3_THREADS, 4)
 stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
                 const unsigned int *__restrict__ frame_prefix, int n_songs,
-                const float *__restrict__ hann, const cpx *__restrict__ tw4096,
-                const cpx *__restrict__ tw8192, float *__restrict__ mags,
+                const float *__restrict__ hann, const cpx *__restrict__ tw1 /*[16][256] W4096^(b k1)*/,
+                const cpx *__restrict__ tw2g /*[16][16] W256^(j k2)*/, const cpx *__restrict__ tw8192,
+                float *__restrict__ mags,
                 double *__restrict__ cand_mag, unsigned char *__restrict__ cand_bin,
                 unsigned int *__restrict__ cand_count) {
     __shared__ __align__(16) cpx buf[r8k::BUF_CPX];
+    __shared__ cpx s_tw2[256];
     __shared__ float s_red[K3_THREADS / 32];
     __shared__ unsigned int s_scan[K3_THREADS / 32];
     __shared__ unsigned int s_base;
 
     const int tid = threadIdx.x;
+    s_tw2[tid] = tw2g[tid];  // visible after the barrier that follows pass 1
     const unsigned int item = blockIdx.x;
     const int si = find_song(frame_prefix, n_songs, item);
     const SongDesc sd = songs[si];
@@ -127,10 +130,10 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
                 v[q] = cpx{r8k::reflect_sample(x, n, i0) * w.x, r8k::reflect_sample(x, n, i0 + 1) * w.y};
             }
         }
-        r8k::pass1_store(tid, v, tw4096, buf);
+        r8k::pass1_store(tid, v, tw1, buf);
     }
     __syncthreads();
-    r8k::pass2(tid, tw4096, buf);
+    r8k::pass2(tid, s_tw2, buf);
     __syncthreads();
     r8k::pass3(tid, buf);
     __syncthreads();
@@ -344,8 +347,8 @@ tuning_kernel(const double *__restrict__ cand_mag, const unsigned char *__restri
 // ---------------------------------------------------------------------------
 // K5: chroma contraction + interval features, thread per frame, 128 frames per CTA.
 // ---------------------------------------------------------------------------
-constexpr int K5_FRAMES = 128;
-constexpr int K5_KT = 32;
+constexpr int K5_THREADS = 128;            // each thread owns frames tid and tid + 128 of the tile
+constexpr int K5_KT = 16;                  // bins staged per step
 
 // Interval / triad templates of chroma.rs:139-152 given as the offsets of their ones:
 // dyads {0,d} d=1..6, major {0,4,7}, minor {0,3,7}, diminished {0,3,6}, augmented {0,4,8}.
@@ -391,50 +394,74 @@ __device__ __forceinline__ void tmpl_all(const double (&e)[12], double (&feat)[1
     }
 }
 
-__global__ void __launch_bounds__(K5_FRAMES)
+// L1 normalisation, exp(15 x), L1 normalisation again, 120 template products (chroma.rs:137-188, :404-410)
+__device__ __forceinline__ void frame_interval_features(const double (&acc)[12], double (&feat)[10], double *dbg) {
+    double sum = 0.;
+#pragma unroll
+    for (int c = 0; c < 12; c++) sum += fabs(acc[c]);
+    if (sum < 2.2250738585072014e-308) sum = 1.;
+    double e[12];
+    double esum = 0.;
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+        const double ch = acc[c] / sum;
+        if (dbg) dbg[c] = ch;
+        e[c] = exp(ch * 15.);  // chroma_interval_features, chroma.rs:138
+        esum += fabs(e[c]);
+    }
+    if (esum < 0.0001) esum = 1.;  // normalize_feature_sequence, chroma.rs:177-188
+#pragma unroll
+    for (int c = 0; c < 12; c++) e[c] = e[c] / esum;
+    double f[10];
+    tmpl_all<0>(e, f);  // extract_interval_features, chroma.rs:157-175
+#pragma unroll
+    for (int t = 0; t < 10; t++) feat[t] += f[t];
+}
+
+__global__ void __launch_bounds__(K5_THREADS)
 chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs,
               const unsigned int *__restrict__ tile_prefix, int n_songs,
               const double *__restrict__ filt_table, const int *__restrict__ tuning_idx,
               double *__restrict__ tile_partials /*[tiles][10]*/, double *__restrict__ chroma_dbg) {
-    __shared__ float s_s[K5_KT][K5_FRAMES + 1];
+    __shared__ float s_s[K5_KT][CH_TILE_FRAMES + 1];
     __shared__ __align__(16) double s_w[K5_KT][12];
-    __shared__ double s_red[K5_FRAMES / 32][10];
+    __shared__ double s_red[K5_THREADS / 32][10];
 
     const int tid = threadIdx.x;
     const unsigned int item = blockIdx.x;
     const int si = find_song(tile_prefix, n_songs, item);
     const SongDesc sd = songs[si];
     const int tile = (int)(item - tile_prefix[si]);
-    const int f0 = tile * K5_FRAMES;
-    const int nf = min(K5_FRAMES, (int)sd.n_c - f0);  // frames of this tile
+    const int f0 = tile * CH_TILE_FRAMES;
+    const int nf = min(CH_TILE_FRAMES, (int)sd.n_c - f0);  // frames of this tile
     const double *W = filt_table + (size_t)tuning_idx[si] * CH_BINS * 12;
     const float *S = mags + (sd.mag_off + (unsigned long long)f0) * CH_STRIDE;
-    const int my_frame = f0 + tid;
-    const bool mine = tid < nf;
 
-    double acc[12];
+    // thread-owned frames: tid and tid + 128; the 12 filter weights of a bin are read from shared
+    // memory once per bin and used for both frames (halves the LDS traffic per DFMA)
+    double acc0[12], acc1[12];
 #pragma unroll
-    for (int c = 0; c < 12; c++) acc[c] = 0.;
+    for (int c = 0; c < 12; c++) { acc0[c] = 0.; acc1[c] = 0.; }
 
-    // Software pipeline: the next k-tile (32 bins x 128 frames of magnitudes + 32 x 12 filter
-    // weights) is fetched into registers while the current one is consumed from shared memory.
-    // Thread t stages column (t & 31) of frames (t >> 5) + 4 i, i = 0..31  -> 128 B per warp per row.
-    const int st_k = tid & 31, st_f = tid >> 5;
+    // Software pipeline: the next k-tile (16 bins x 256 frames of magnitudes + 16 x 12 weights) is
+    // fetched into registers while the current one is consumed from shared memory.
+    // Thread t stages bin (t & 15) of frames (t >> 4) + 8 i, i = 0..31  -> 64 B per half-warp per row.
+    const int st_k = tid & 15, st_f = tid >> 4;
     float pre_s[32];
-    double pre_w[3];
+    double pre_w[2];
     auto fetch = [&](int k0) {
         const int kt = min(K5_KT, CH_BINS - k0);
 #pragma unroll
         for (int i = 0; i < 32; i++) {
-            const int fr = st_f + 4 * i;
+            const int fr = st_f + 8 * i;
             float v = 0.f;
             // rows beyond n_c_comp are zero (utils.rs:27-31)
             if (fr < nf && st_k < kt && (f0 + fr) < (int)sd.n_c_comp) v = __ldg(S + (size_t)fr * CH_STRIDE + k0 + st_k);
             pre_s[i] = v;
         }
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const int e = tid + K5_FRAMES * i;  // 384 = 32 x 12 weights
+        for (int i = 0; i < 2; i++) {
+            const int e = tid + K5_THREADS * i;  // 192 = 16 x 12 weights
             pre_w[i] = (e < kt * 12) ? __ldg(W + (size_t)k0 * 12 + e) : 0.;
         }
     };
@@ -443,54 +470,33 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
         const int kt = min(K5_KT, CH_BINS - k0);
         __syncthreads();  // previous tile fully consumed
 #pragma unroll
-        for (int i = 0; i < 32; i++) s_s[st_k][st_f + 4 * i] = pre_s[i];
+        for (int i = 0; i < 32; i++) s_s[st_k][st_f + 8 * i] = pre_s[i];
 #pragma unroll
-        for (int i = 0; i < 3; i++) (&s_w[0][0])[tid + K5_FRAMES * i] = pre_w[i];
+        for (int i = 0; i < 2; i++) {
+            const int e = tid + K5_THREADS * i;
+            if (e < K5_KT * 12) (&s_w[0][0])[e] = pre_w[i];
+        }
         __syncthreads();
         if (k0 + K5_KT < CH_BINS) fetch(k0 + K5_KT);
-        if (mine) {
-            if (kt == K5_KT) {
-#pragma unroll 8
-                for (int kk = 0; kk < K5_KT; kk++) {
-                    const double s = (double)s_s[kk][tid];
-                    const double s2 = s * s;  // spectrum.mapv_inplace(|x| x*x), chroma.rs:400
+#pragma unroll 4
+        for (int kk = 0; kk < kt; kk++) {
+            const double a = (double)s_s[kk][tid], b = (double)s_s[kk][tid + 128];
+            const double a2 = a * a, b2 = b * b;  // spectrum.mapv_inplace(|x| x*x), chroma.rs:400
 #pragma unroll
-                    for (int c = 0; c < 12; c++) acc[c] += s_w[kk][c] * s2;
-                }
-            } else {
-                for (int kk = 0; kk < kt; kk++) {
-                    const double s = (double)s_s[kk][tid];
-                    const double s2 = s * s;
-#pragma unroll
-                    for (int c = 0; c < 12; c++) acc[c] += s_w[kk][c] * s2;
-                }
+            for (int c = 0; c < 12; c++) {
+                const double w = s_w[kk][c];
+                acc0[c] += w * a2;
+                acc1[c] += w * b2;
             }
         }
     }
-    // L1 column normalisation (chroma.rs:404-410)
     double feat[10];
 #pragma unroll
     for (int t = 0; t < 10; t++) feat[t] = 0.;
-    if (mine) {
-        double sum = 0.;
-#pragma unroll
-        for (int c = 0; c < 12; c++) sum += fabs(acc[c]);
-        if (sum < 2.2250738585072014e-308) sum = 1.;
-        double e[12];
-        double esum = 0.;
-#pragma unroll
-        for (int c = 0; c < 12; c++) {
-            const double ch = acc[c] / sum;
-            if (chroma_dbg) chroma_dbg[((size_t)sd.c_tile_off * K5_FRAMES + (size_t)my_frame) * 12 + c] = ch;
-            e[c] = exp(ch * 15.);  // chroma_interval_features, chroma.rs:138
-            esum += fabs(e[c]);
-        }
-        if (esum < 0.0001) esum = 1.;  // normalize_feature_sequence, chroma.rs:177-188
-#pragma unroll
-        for (int c = 0; c < 12; c++) e[c] = e[c] / esum;
-        // extract_interval_features, chroma.rs:157-175: product over the rolled template, sum over 12 shifts
-        tmpl_all<0>(e, feat);
-    }
+    if (tid < nf)
+        frame_interval_features(acc0, feat, chroma_dbg ? chroma_dbg + ((size_t)sd.c_tile_off * CH_TILE_FRAMES + f0 + tid) * 12 : nullptr);
+    if (tid + 128 < nf)
+        frame_interval_features(acc1, feat, chroma_dbg ? chroma_dbg + ((size_t)sd.c_tile_off * CH_TILE_FRAMES + f0 + tid + 128) * 12 : nullptr);
     // sum the tile's frames (mean_axis over frames finishes in the summary kernel)
 #pragma unroll
     for (int t = 0; t < 10; t++) {
@@ -503,18 +509,18 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
     if (tid < 10) {
         double v = 0.;
 #pragma unroll
-        for (int w = 0; w < K5_FRAMES / 32; w++) v += s_red[w][tid];
+        for (int w = 0; w < K5_THREADS / 32; w++) v += s_red[w][tid];
         tile_partials[((size_t)sd.c_tile_off + tile) * 10 + tid] = v;
     }
 }
 
 // ---- launchers ---------------------------------------------------------------
 int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int *frame_prefix, int n_songs,
-                    unsigned int total_frames, const float *hann, const cpx *tw4096, const cpx *tw8192,
-                    float *mags, double *cand_mag, unsigned char *cand_bin, unsigned int *cand_count,
-                    cudaStream_t st) {
+                    unsigned int total_frames, const float *hann, const cpx *tw1, const cpx *tw2,
+                    const cpx *tw8192, float *mags, double *cand_mag, unsigned char *cand_bin,
+                    unsigned int *cand_count, cudaStream_t st) {
     if (total_frames == 0) return 0;
-    stft8192_kernel<<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw4096,
+    stft8192_kernel<<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw1, tw2,
                                                          tw8192, mags, cand_mag, cand_bin, cand_count);
     return 1;
 }
@@ -530,7 +536,7 @@ int launch_chroma(const float *mags, const SongDesc *songs, const unsigned int *
                   unsigned int total_tiles, const double *filt_table, const int *tuning_idx,
                   double *tile_partials, double *chroma_dbg, cudaStream_t st) {
     if (total_tiles == 0) return 0;
-    chroma_kernel<<<total_tiles, K5_FRAMES, 0, st>>>(mags, songs, tile_prefix, n_songs, filt_table,
+    chroma_kernel<<<total_tiles, K5_THREADS, 0, st>>>(mags, songs, tile_prefix, n_songs, filt_table,
                                                      tuning_idx, tile_partials, chroma_dbg);
     return 1;
 }

@@ -15,6 +15,7 @@ constexpr int CH_WIN = 8192;              // chroma.rs:39
 constexpr int CH_HOP = 2205;              // chroma.rs:74
 constexpr int CH_BINS = 4097;
 constexpr int CH_STRIDE = 4104;           // padded row of the magnitude spill (16 B aligned rows)
+constexpr int CH_TILE_FRAMES = 256;      // chroma frames per CTA of chroma_kernel (2 per thread)
 constexpr int CH_MAX_PEAKS = 714;         // max local maxima among centre bins 57..1483
 constexpr int LOUD_WIN = 1024;            // misc.rs:44
 constexpr int MIN_SAMPLES = 8192;         // song/mod.rs:417-430

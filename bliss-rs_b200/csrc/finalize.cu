@@ -80,7 +80,7 @@ finalize_kernel(const SongDesc *__restrict__ songs, const float *__restrict__ ce
         o[1] = normalize((float)zcr_count[blockIdx.x] / (float)sd.n, 0.f, 1.f);
     }
     // chroma: mean over frames of the interval features (chroma.rs:154)
-    const unsigned int n_tiles = (sd.n_c + 127u) / 128u;
+    const unsigned int n_tiles = (sd.n_c + CH_TILE_FRAMES - 1u) / CH_TILE_FRAMES;
     if (threadIdx.x < 10) {
         double acc = 0.;
         for (unsigned int t = 0; t < n_tiles; t++) acc += tile_partials[((size_t)sd.c_tile_off + t) * 10 + threadIdx.x];

@@ -71,9 +71,12 @@ BLISS_HD int bin_of(int lane, int q) {
 // Untangle the two real spectra from Z (complex FFT of a + i b):
 //   A[k] = (Z[k] + conj Z[N-k]) / 2,   B[k] = (Z[k] - conj Z[N-k]) / (2i)
 // and return their magnitudes as `(re*re + im*im).sqrt()` (aubio.rs:248-252).
+// SCALE2 = true returns 2|A|, 2|B| (the exact factor 1/2 is folded into a later power-of-two scale).
+template <bool SCALE2 = false>
 BLISS_HD void untangle_mag(cpx zk, cpx zm, float &magA, float &magB) {
-    const float ar = 0.5f * (zk.x + zm.x), ai = 0.5f * (zk.y - zm.y);
-    const float br = 0.5f * (zk.y + zm.y), bi = 0.5f * (zm.x - zk.x);
+    const float h = SCALE2 ? 1.0f : 0.5f;
+    const float ar = h * (zk.x + zm.x), ai = h * (zk.y - zm.y);
+    const float br = h * (zk.y + zm.y), bi = h * (zm.x - zk.x);
 #ifdef __CUDA_ARCH__
     magA = __fsqrt_rn(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
     magB = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));

@@ -21,22 +21,25 @@ constexpr int NC = 4096;                       // complex points
 constexpr int BUF_CPX = 4096 + 256 + 16 + 16;  // pad(4095) + 1 = 4366 -> round up
 BLISS_HD int pad(int i) { return i + (i >> 4) + (i >> 8); }
 
-// pass 1: butterfly b in [0,256): v[q] = z[b + 256 q];  pad(b + 256 k1) = b + (b>>4) + 273 k1
-BLISS_HD void pass1_store(int b, cpx (&v)[16], const cpx *tw4096 /*W4096^m, m < 4096*/, cpx *buf) {
+// pass 1: butterfly b in [0,256): v[q] = z[b + 256 q];  pad(b + 256 k1) = b + (b>>4) + 273 k1.
+// tw1 is laid out [k1][b] = W4096^(b k1) so that the 32 lanes of a warp read 256 contiguous bytes.
+BLISS_HD void pass1_store(int b, cpx (&v)[16], const cpx *tw1 /*[16][256]*/, cpx *buf) {
     fft_dif<16>(v);
     cpx *o = buf + b + (b >> 4);
+    const cpx *t = tw1 + b;
 #pragma unroll
     for (int s = 0; s < 16; s++) {
         const int k1 = bitrev(s, 4);
         cpx r = v[s];
-        if (k1 != 0) r = cmul(r, tw4096[b * k1]);
+        if (k1 != 0) r = cmul(r, t[256 * k1]);
         o[273 * k1] = r;
     }
 }
 
 // pass 2: butterfly b in [0,256): blk = b>>4 (k1), j = b&15; radix 16 at stride 16 inside the
-// 256-block;  pad(256 blk + j + 16 q) = 273 blk + j + 17 q;  twiddle W256^(j k2) = W4096^(16 j k2)
-BLISS_HD void pass2(int b, const cpx *tw4096, cpx *buf) {
+// 256-block;  pad(256 blk + j + 16 q) = 273 blk + j + 17 q;  twiddle tw2[k2][j] = W256^(j k2)
+// (a 2 KB table the kernel keeps in shared memory)
+BLISS_HD void pass2(int b, const cpx *tw2 /*[16][16]*/, cpx *buf) {
     const int blk = b >> 4, j = b & 15;
     cpx *p = buf + 273 * blk + j;
     cpx v[16];
@@ -47,7 +50,7 @@ BLISS_HD void pass2(int b, const cpx *tw4096, cpx *buf) {
     for (int s = 0; s < 16; s++) {
         const int k2 = bitrev(s, 4);
         cpx o = v[s];
-        if (k2 != 0) o = cmul(o, tw4096[(16 * j) * k2]);
+        if (k2 != 0) o = cmul(o, tw2[16 * k2 + j]);
         p[17 * k2] = o;
     }
 }

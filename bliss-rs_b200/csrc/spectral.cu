@@ -166,8 +166,10 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
         sh = (ua == 0u || ub == 0u) ? 0 : max(-60, min(60, sh));
         const float gscale = __uint_as_float((unsigned)(127 + sh) << 23);
         const float ginv = __uint_as_float((unsigned)(127 - sh) << 23);
+        if (sh != 0) {  // warp-uniform; the common case (similar levels) skips the rescale
 #pragma unroll
-        for (int n1 = 0; n1 < 16; n1++) r[n1].y *= gscale;
+            for (int n1 = 0; n1 < 16; n1++) r[n1].y *= gscale;
+        }
         pv::phase_a(lane, r, s_twA, S);
         __syncwarp();
         pv::phase_b_load(lane, r, S);
@@ -187,18 +189,18 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
             const int k = 8 * lane + i;
             const cpx zk = S[pv::zpos(k)];
             const cpx zm = S[pv::zpos((512 - k) & 511)];
-            pv::untangle_mag(zk, zm, ma[i], mb[i]);
+            pv::untangle_mag<true>(zk, zm, ma[i], mb[i]);  // 2|A|, 2|B|: halved by ka / kb below
         }
         const cpx zn = S[pv::zpos(256)];  // Nyquist: A = |Re|, B = |Im|
-        float nyq_a = fabsf(zn.x), nyq_b = fabsf(zn.y);
+        float nyq_a = 2.f * fabsf(zn.x), nyq_b = 2.f * fabsf(zn.y);
         if (lane == 0) {  // DC: abs(re), aubio.rs:240 / :403
             const cpx z0 = S[0];
-            ma[0] = fabsf(z0.x);
-            mb[0] = fabsf(z0.y);
+            ma[0] = 2.f * fabsf(z0.x);
+            mb[0] = 2.f * fabsf(z0.y);
         }
         __syncwarp();  // S is rewritten by the next pair's phase A
-        const float ka = (ua == 0u) ? 0.f : 1.f;
-        const float kb = (ub == 0u) ? 0.f : ginv;
+        const float ka = (ua == 0u) ? 0.f : 0.5f;  // powers of two: exact
+        const float kb = (ub == 0u) ? 0.f : 0.5f * ginv;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             ma[i] *= ka;

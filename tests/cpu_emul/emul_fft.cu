@@ -74,11 +74,17 @@ int main() {
     }
     // ---------------- 8192-point real FFT as 4096 complex, one frame per CTA ----------------
     {
-        std::vector<cpx> tw(4096), tw8(256);
-        for (int m = 0; m < 4096; m++) {
-            double a = -2.0 * M_PI * (double)m / 4096.0;
-            tw[m] = cpx{(float)cos(a), (float)sin(a)};
-        }
+        std::vector<cpx> tw(4096), tw2(256), tw8(256);  // tw: [k1][b] = W4096^(b k1); tw2: [k2][j] = W256^(j k2)
+        for (int k1 = 0; k1 < 16; k1++)
+            for (int b = 0; b < 256; b++) {
+                double a = -2.0 * M_PI * (double)(b * k1) / 4096.0;
+                tw[k1 * 256 + b] = cpx{(float)cos(a), (float)sin(a)};
+            }
+        for (int k2 = 0; k2 < 16; k2++)
+            for (int j = 0; j < 16; j++) {
+                double a = -2.0 * M_PI * (double)(j * k2) / 256.0;
+                tw2[k2 * 16 + j] = cpx{(float)cos(a), (float)sin(a)};
+            }
         for (int t = 0; t < 256; t++) {
             double a = -2.0 * M_PI * (double)t / 8192.0;
             tw8[t] = cpx{(float)cos(a), (float)sin(a)};
@@ -94,7 +100,7 @@ int main() {
             }
             r8k::pass1_store(bb, v, tw.data(), buf.data());
         }
-        for (int bb = 0; bb < 256; bb++) r8k::pass2(bb, tw.data(), buf.data());
+        for (int bb = 0; bb < 256; bb++) r8k::pass2(bb, tw2.data(), buf.data());
         for (int bb = 0; bb < 256; bb++) r8k::pass3(bb, buf.data());
         std::vector<double> ma;
         dft_real(a, ma, 8192);
