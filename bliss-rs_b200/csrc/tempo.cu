@@ -17,8 +17,6 @@
 namespace bliss {
 
 // ------------------------------- K7 ----------------------------------------
-__device__ __forceinline__ float biquad_run7(float (&d)[7]) { return 0.f; }
-
 __global__ void __launch_bounds__(256)
 peakpick_kernel(const float *__restrict__ flux, const SongDesc *__restrict__ songs,
                 const unsigned int *__restrict__ t_prefix, int n_songs, unsigned int total,
@@ -156,7 +154,7 @@ __device__ unsigned int get_timesig(const float *acf, int acflen, int gp) {
     return three > four ? 3u : 4u;
 }
 
-__global__ void __launch_bounds__(BT_THREADS)
+__global__ void __launch_bounds__(BT_THREADS, 4)
 beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_energy,
                  const SongDesc *__restrict__ songs, float *__restrict__ bpm_list,
                  float *__restrict__ tempo_feature, unsigned int *__restrict__ bpm_count) {
@@ -212,8 +210,18 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
         // vec_autocorr, aubio.rs:819-828
         {
             float tmp = 0.f;
-            for (int j = tid; j < winlen; j++) tmp += sh.df[j - tid] * sh.df[j];
-            sh.acf[tid] = tmp / (float)(winlen - tid);
+            const float *a = sh.df, *b = sh.df + tid;
+            const int cnt = winlen - tid;
+            int j = 0;
+            for (; j + 8 <= cnt; j += 8) {  // products first (independent), then the ordered adds
+                float pr[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) pr[u] = a[j + u] * b[j + u];
+#pragma unroll
+                for (int u = 0; u < 8; u++) tmp += pr[u];
+            }
+            for (; j < cnt; j++) tmp += a[j] * b[j];
+            sh.acf[tid] = tmp / (float)cnt;
         }
         __syncthreads();
         // shift-invariant comb filterbank, general model (aubio.rs:992-1003)
