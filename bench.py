@@ -144,7 +144,17 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "songs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+def _emit(line: dict):
+    """The one JSON line goes to the ORIGINAL stdout; everything else any library prints (NCCL's
+    version banner, warnings) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -256,7 +266,11 @@ def main():
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(dom["kernel"])
+            ent = json.load(open(tp)).get(dom["kernel"])
+            # measured DRAM bytes per song (ncu --set full, profiles/) x songs per launch, in GB like `achieved`
+            traffic = {"gb_per_launch": ent["bytes_per_song"] * S / 1e9,
+                       "algorithmic_gb_per_launch": alg.get(dom["kernel"], 0) * S / 1e9,
+                       "source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum)"}
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["algorithmic_gbs"], "peak": peak,
@@ -326,7 +340,7 @@ def main():
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "gpu_launches": int(lz.item()),
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -104,7 +104,8 @@ struct Ctx {
     std::mutex mu;
     bool inited = false;
     int device = -1;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     size_t ws_limit = 0;
     // constant tables
     DevBuf t_win512, t_twA, t_hann8k, t_tw4k, t_tw2, t_tw8k, t_filt;
@@ -320,27 +321,37 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
     CK(cudaMemsetAsync(g.zcr.p, 0, (size_t)n * 4, st));
     CK(cudaMemsetAsync(g.cand_count.p, 0, (size_t)n * 4, st));
 
+    // Two independent chains per wave: the tempo/timbral chain stays on the caller's stream, the chroma
+    // chain runs on a side stream so that its latency-bound kernels (tuning) overlap the other chain's
+    // compute-bound ones and vice versa (beat tracker under the chroma STFT).  Joined before finalize.
+    // (while per-kernel profiling is on, both chains are serialised on `st` so that each kernel's
+    // CUDA-event duration is its own and not inflated by the kernel it would overlap with)
+    cudaStream_t sb = g.profiling ? st : g.side_stream;
+    CK(cudaEventRecord(g.ev_fork, st));
+    CK(cudaStreamWaitEvent(sb, g.ev_fork, 0));
+    { ProfScope p(K_STFT8K, sb);
+      p.done(launch_stft8192(d_pcm, dv.sd, dv.pair_prefix, n, w.pair_prefix[n], g.t_hann8k.as<float>(),
+                             g.t_tw4k.as<cpx>(), g.t_tw2.as<cpx>(), g.t_tw8k.as<cpx>(), g.mags.as<float>(), g.cand_mag.as<double>(),
+                             g.cand_bin.as<unsigned char>(), g.cand_count.as<unsigned int>(), sb)); }
     { ProfScope p(K_TIME, st);
       p.done(launch_timedomain(d_pcm, dv.sd, dv.chunk_prefix, n, w.chunk_prefix[n], g.loud.as<float>(),
                                g.eb.as<float>(), g.zcr.as<unsigned int>(), st)); }
     { ProfScope p(K_PVOC, st);
       p.done(launch_pvoc512(d_pcm, dv.sd, dv.k1_prefix, n, w.k1_prefix[n], (int)w.pairs_per_item, pvoc_tables(),
                             g.cent.as<float>(), g.roll.as<float>(), g.flat.as<float>(), g.flux.as<float>(), st)); }
+    { ProfScope p(K_TUNING, sb);
+      p.done(launch_tuning(g.cand_mag.as<double>(), g.cand_bin.as<unsigned char>(),
+                           g.cand_count.as<unsigned int>(), dv.sd, n, g.tuning.as<int>(), sb)); }
     { ProfScope p(K_PEAK, st);
       p.done(launch_peakpick(g.flux.as<float>(), dv.sd, dv.t_prefix, n, w.t_prefix[n], g.thr.as<float>(), st)); }
+    { ProfScope p(K_CHROMA, sb);
+      p.done(launch_chroma(g.mags.as<float>(), dv.sd, dv.tile_prefix, n, w.tile_prefix[n], g.t_filt.as<double>(),
+                           g.tuning.as<int>(), g.tiles.as<double>(), debug ? g.chroma_dbg.as<double>() : nullptr, sb)); }
     { ProfScope p(K_BEAT, st);
       p.done(launch_beattrack(g.thr.as<float>(), g.eb.as<float>(), dv.sd, n, g.bpm.as<float>(),
                               g.tempo.as<float>(), g.bpm_count.as<unsigned int>(), st)); }
-    { ProfScope p(K_STFT8K, st);
-      p.done(launch_stft8192(d_pcm, dv.sd, dv.pair_prefix, n, w.pair_prefix[n], g.t_hann8k.as<float>(),
-                             g.t_tw4k.as<cpx>(), g.t_tw2.as<cpx>(), g.t_tw8k.as<cpx>(), g.mags.as<float>(), g.cand_mag.as<double>(),
-                             g.cand_bin.as<unsigned char>(), g.cand_count.as<unsigned int>(), st)); }
-    { ProfScope p(K_TUNING, st);
-      p.done(launch_tuning(g.cand_mag.as<double>(), g.cand_bin.as<unsigned char>(),
-                           g.cand_count.as<unsigned int>(), dv.sd, n, g.tuning.as<int>(), st)); }
-    { ProfScope p(K_CHROMA, st);
-      p.done(launch_chroma(g.mags.as<float>(), dv.sd, dv.tile_prefix, n, w.tile_prefix[n], g.t_filt.as<double>(),
-                           g.tuning.as<int>(), g.tiles.as<double>(), debug ? g.chroma_dbg.as<double>() : nullptr, st)); }
+    CK(cudaEventRecord(g.ev_join, sb));
+    CK(cudaStreamWaitEvent(st, g.ev_join, 0));
     { ProfScope p(K_FINAL, st);
       p.done(launch_finalize(dv.sd, n, g.cent.as<float>(), g.roll.as<float>(), g.flat.as<float>(),
                              g.loud.as<float>(), g.zcr.as<unsigned int>(), g.tempo.as<float>(),
@@ -497,6 +508,9 @@ int bliss_b200_init(int device) {
     g.device = device;
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.side_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     g.ws_limit = (size_t)((double)total_b * 0.40);
@@ -531,6 +545,9 @@ void bliss_b200_shutdown(void) {
     g.ev_pool.clear();
     cudaStreamDestroy(g.stream);
     cudaStreamDestroy(g.copy_stream);
+    cudaStreamDestroy(g.side_stream);
+    cudaEventDestroy(g.ev_fork);
+    cudaEventDestroy(g.ev_join);
     g.inited = false;
 }
 

@@ -418,7 +418,7 @@ __device__ __forceinline__ void frame_interval_features(const double (&acc)[12],
     for (int t = 0; t < 10; t++) feat[t] += f[t];
 }
 
-__global__ void __launch_bounds__(K5_THREADS)
+__global__ void __launch_bounds__(K5_THREADS, 3)
 chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs,
               const unsigned int *__restrict__ tile_prefix, int n_songs,
               const double *__restrict__ filt_table, const int *__restrict__ tuning_idx,

@@ -16,6 +16,7 @@
 #include "fft_regs.cuh"
 
 namespace bliss {
+
 namespace pv {
 
 constexpr int ROW = 33;                       // padded row (float2 units) of the 16x32 exchange tile
@@ -78,8 +79,8 @@ BLISS_HD void untangle_mag(cpx zk, cpx zm, float &magA, float &magB) {
     const float ar = h * (zk.x + zm.x), ai = h * (zk.y - zm.y);
     const float br = h * (zk.y + zm.y), bi = h * (zm.x - zk.x);
 #ifdef __CUDA_ARCH__
-    magA = __fsqrt_rn(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
-    magB = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
+    magA = approx_sqrtf(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
+    magB = approx_sqrtf(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
 #else
     magA = sqrtf(ar * ar + ai * ai);
     magB = sqrtf(br * br + bi * bi);

@@ -85,7 +85,7 @@ BLISS_HD float untangle_mag(cpx zk, cpx zm, cpx w) {
     // -i (pr + i pi) = pi - i pr
     const float xr = er + pi, xi = ei - pr;
 #ifdef __CUDA_ARCH__
-    return __fsqrt_rn(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi)));
+    return approx_sqrtf(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi)));
 #else
     return sqrtf(xr * xr + xi * xi);
 #endif

@@ -8,6 +8,7 @@
 #define _GNU_SOURCE
 #include "bliss_oracle.h"
 
+#include <malloc.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
@@ -790,8 +791,11 @@ uint64_t bo_pip_track(const double *S, uint32_t frames, uint32_t n_fft, double *
     }
     uint64_t cnt = 0;
     int rows = end - 3 - beginning;
-    for (int i = 0; i < rows; i++)
-        for (uint32_t j = 0; j < frames; j++) {
+    /* The reference's Zip walks its [bins x frames] view, which is the transpose of a frame-major
+     * buffer (utils.rs:63), along memory order; visiting frame by frame here does the same.  The
+     * order of the emitted peaks is irrelevant downstream (median + histogram). */
+    for (uint32_t j = 0; j < frames; j++)
+        for (int i = 0; i < rows; i++) {
             const double *col = S + (size_t)j * bins;
             double before = col[beginning + i], elem = col[beginning + 1 + i],
                    after = col[beginning + 2 + i];
@@ -1088,6 +1092,10 @@ int bo_analyze_batch(const float *const *pcm, const uint64_t *n, uint32_t n_song
                      float *out, int32_t *status, int n_threads) {
     if (n_threads < 1) n_threads = 1;
     if ((uint32_t)n_threads > n_songs) n_threads = (int)(n_songs ? n_songs : 1);
+    /* keep the per-song 59 MB spectra inside the per-thread arenas instead of mmap/munmap-ing them
+     * for every song: with ~100 worker threads the page-fault / mmap-lock storm otherwise dominates */
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
     get_plan(512);
     get_plan(8192);
     uint32_t chunk = (n_songs + n_threads - 1) / n_threads;
