@@ -27,13 +27,13 @@ int launch_peakpick(const float *, const SongDesc *, const unsigned int *, int, 
                     cudaStream_t);
 int launch_beattrack(const float *, const float *, const SongDesc *, int, float *, float *, unsigned int *,
                      cudaStream_t);
-int launch_chroma_filter_table(double *, cudaStream_t);
+int launch_chroma_filter_table(double *, float *, cudaStream_t);
 int launch_stft8192(const float *, const SongDesc *, const unsigned int *, int, unsigned int, const float *,
                     const cpx *, const cpx *, const cpx *, float *, double *, unsigned char *, unsigned int *,
                     cudaStream_t);
 int launch_tuning(const double *, const unsigned char *, const unsigned int *, const SongDesc *, int, int *,
                   cudaStream_t);
-int launch_chroma(const float *, const SongDesc *, const unsigned int *, int, unsigned int, const double *,
+int launch_chroma(const float *, const SongDesc *, const unsigned int *, int, unsigned int, const float *,
                   const int *, double *, double *, cudaStream_t);
 int launch_finalize(const SongDesc *, int, const float *, const float *, const float *, const float *,
                     const unsigned int *, const float *, const double *, int, float *, unsigned int,
@@ -108,7 +108,7 @@ struct Ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     size_t ws_limit = 0;
     // constant tables
-    DevBuf t_win512, t_twA, t_hann8k, t_tw4k, t_tw2, t_tw8k, t_filt;
+    DevBuf t_win512, t_twA, t_hann8k, t_tw4k, t_tw2, t_tw8k, t_filt, t_filt32;
     // wave scratch
     DevBuf blob;  // SongDesc + prefix arrays
     DevBuf mags, cand_mag, cand_bin, cand_count, cent, roll, flat, flux, thr, loud, eb, zcr, tempo, bpm,
@@ -345,7 +345,7 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
     { ProfScope p(K_PEAK, st);
       p.done(launch_peakpick(g.flux.as<float>(), dv.sd, dv.t_prefix, n, w.t_prefix[n], g.thr.as<float>(), st)); }
     { ProfScope p(K_CHROMA, sb);
-      p.done(launch_chroma(g.mags.as<float>(), dv.sd, dv.tile_prefix, n, w.tile_prefix[n], g.t_filt.as<double>(),
+      p.done(launch_chroma(g.mags.as<float>(), dv.sd, dv.tile_prefix, n, w.tile_prefix[n], g.t_filt32.as<float>(),
                            g.tuning.as<int>(), g.tiles.as<double>(), debug ? g.chroma_dbg.as<double>() : nullptr, sb)); }
     { ProfScope p(K_BEAT, st);
       p.done(launch_beattrack(g.thr.as<float>(), g.eb.as<float>(), dv.sd, n, g.bpm.as<float>(),
@@ -438,7 +438,8 @@ int build_tables() {
     CK(cudaMemcpy(g.t_twA.p, twA.data(), twA.size() * sizeof(cpx), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(g.t_hann8k.p, hann.data(), hann.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(g.t_tw8k.p, tw.data(), tw.size() * sizeof(cpx), cudaMemcpyHostToDevice));
-    g.launches += launch_chroma_filter_table(g.t_filt.as<double>(), g.stream);
+    CK(g.t_filt32.ensure((size_t)100 * CH_BINS * 12 * sizeof(float)));
+    g.launches += launch_chroma_filter_table(g.t_filt.as<double>(), g.t_filt32.as<float>(), g.stream);
     CK(cudaStreamSynchronize(g.stream));
     CK(cudaGetLastError());
     return BLISS_B200_OK;
@@ -525,7 +526,7 @@ void bliss_b200_shutdown(void) {
     if (!g.inited) return;
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
-    DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw4k, &g.t_tw2, &g.t_tw8k, &g.t_filt, &g.blob, &g.mags, &g.cand_mag,
+    DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw4k, &g.t_tw2, &g.t_tw8k, &g.t_filt, &g.t_filt32, &g.blob, &g.mags, &g.cand_mag,
                      &g.cand_bin, &g.cand_count, &g.cent, &g.roll, &g.flat, &g.flux, &g.thr, &g.loud, &g.eb,
                      &g.zcr, &g.tempo, &g.bpm, &g.bpm_count, &g.tuning, &g.tiles, &g.chroma_dbg, &g.pcm[0],
                      &g.pcm[1], &g.feats, &g.metric, &g.misc[0], &g.misc[1], &g.misc[2], &g.misc[3],

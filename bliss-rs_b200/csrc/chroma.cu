@@ -54,10 +54,18 @@ __global__ void chroma_filter_table_kernel(double *__restrict__ table) {
     for (int r = 0; r < 12; r++) o[r] = w[(r + 3) % 12] / ss * g;  // np.roll(-3): b[r] = wts[(r+3)%12]
 }
 
-int launch_chroma_filter_table(double *table, cudaStream_t st) {
+__global__ void f64_to_f32_kernel(const double *__restrict__ in, float *__restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+// builds the f64 table (chroma.rs:197-267 as written) and the f32 copy chroma_kernel multiplies with
+int launch_chroma_filter_table(double *table, float *table32, cudaStream_t st) {
     dim3 grid((CH_BINS + 127) / 128, 100);
     chroma_filter_table_kernel<<<grid, 128, 0, st>>>(table);
-    return 1;
+    const size_t n = (size_t)100 * CH_BINS * 12;
+    f64_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(table, table32, n);
+    return 2;
 }
 
 // ---------------------------------------------------------------------------
@@ -418,13 +426,13 @@ __device__ __forceinline__ void frame_interval_features(const double (&acc)[12],
     for (int t = 0; t < 10; t++) feat[t] += f[t];
 }
 
-__global__ void __launch_bounds__(K5_THREADS, 3)
+__global__ void __launch_bounds__(K5_THREADS)
 chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs,
               const unsigned int *__restrict__ tile_prefix, int n_songs,
-              const double *__restrict__ filt_table, const int *__restrict__ tuning_idx,
+              const float *__restrict__ filt_table, const int *__restrict__ tuning_idx,
               double *__restrict__ tile_partials /*[tiles][10]*/, double *__restrict__ chroma_dbg) {
     __shared__ float s_s[K5_KT][CH_TILE_FRAMES + 1];
-    __shared__ __align__(16) double s_w[K5_KT][12];
+    __shared__ __align__(16) float s_w[K5_KT][12];
     __shared__ double s_red[K5_THREADS / 32][10];
 
     const int tid = threadIdx.x;
@@ -434,11 +442,14 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
     const int tile = (int)(item - tile_prefix[si]);
     const int f0 = tile * CH_TILE_FRAMES;
     const int nf = min(CH_TILE_FRAMES, (int)sd.n_c - f0);  // frames of this tile
-    const double *W = filt_table + (size_t)tuning_idx[si] * CH_BINS * 12;
+    const float *W = filt_table + (size_t)tuning_idx[si] * CH_BINS * 12;
     const float *S = mags + (sd.mag_off + (unsigned long long)f0) * CH_STRIDE;
 
-    // thread-owned frames: tid and tid + 128; the 12 filter weights of a bin are read from shared
-    // memory once per bin and used for both frames (halves the LDS traffic per DFMA)
+    // The reference contracts in f64 (chroma.rs:403, ndarray dot on f64).  Here every 16-bin chunk
+    // is accumulated with f32 FMAs (products of two f32-exact factors, <= 16 additions) and the chunk
+    // sums are added in f64: the result differs from the all-f64 sum by ~1e-7 relative, the level of
+    // the f32 FFT's own rounding, at a third of the FP64-pipe time.
+    // Thread-owned frames: tid and tid + 128; a bin's 12 weights are read once for both frames.
     double acc0[12], acc1[12];
 #pragma unroll
     for (int c = 0; c < 12; c++) { acc0[c] = 0.; acc1[c] = 0.; }
@@ -448,7 +459,7 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
     // Thread t stages bin (t & 15) of frames (t >> 4) + 8 i, i = 0..31  -> 64 B per half-warp per row.
     const int st_k = tid & 15, st_f = tid >> 4;
     float pre_s[32];
-    double pre_w[2];
+    float pre_w[2];
     auto fetch = [&](int k0) {
         const int kt = min(K5_KT, CH_BINS - k0);
 #pragma unroll
@@ -462,12 +473,11 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
 #pragma unroll
         for (int i = 0; i < 2; i++) {
             const int e = tid + K5_THREADS * i;  // 192 = 16 x 12 weights
-            pre_w[i] = (e < kt * 12) ? __ldg(W + (size_t)k0 * 12 + e) : 0.;
+            pre_w[i] = (e < kt * 12) ? __ldg(W + (size_t)k0 * 12 + e) : 0.f;
         }
     };
     fetch(0);
     for (int k0 = 0; k0 < CH_BINS; k0 += K5_KT) {
-        const int kt = min(K5_KT, CH_BINS - k0);
         __syncthreads();  // previous tile fully consumed
 #pragma unroll
         for (int i = 0; i < 32; i++) s_s[st_k][st_f + 8 * i] = pre_s[i];
@@ -478,16 +488,24 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
         }
         __syncthreads();
         if (k0 + K5_KT < CH_BINS) fetch(k0 + K5_KT);
+        float p0[12], p1[12];
+#pragma unroll
+        for (int c = 0; c < 12; c++) { p0[c] = 0.f; p1[c] = 0.f; }
 #pragma unroll 4
-        for (int kk = 0; kk < kt; kk++) {
-            const double a = (double)s_s[kk][tid], b = (double)s_s[kk][tid + 128];
-            const double a2 = a * a, b2 = b * b;  // spectrum.mapv_inplace(|x| x*x), chroma.rs:400
+        for (int kk = 0; kk < K5_KT; kk++) {  // bins past 4096 were staged as zeros
+            const float a = s_s[kk][tid], b = s_s[kk][tid + 128];
+            const float a2 = a * a, b2 = b * b;  // spectrum.mapv_inplace(|x| x*x), chroma.rs:400
 #pragma unroll
             for (int c = 0; c < 12; c++) {
-                const double w = s_w[kk][c];
-                acc0[c] += w * a2;
-                acc1[c] += w * b2;
+                const float w = s_w[kk][c];
+                p0[c] = fmaf(w, a2, p0[c]);
+                p1[c] = fmaf(w, b2, p1[c]);
             }
+        }
+#pragma unroll
+        for (int c = 0; c < 12; c++) {
+            acc0[c] += (double)p0[c];
+            acc1[c] += (double)p1[c];
         }
     }
     double feat[10];
@@ -533,7 +551,7 @@ int launch_tuning(const double *cand_mag, const unsigned char *cand_bin, const u
 }
 
 int launch_chroma(const float *mags, const SongDesc *songs, const unsigned int *tile_prefix, int n_songs,
-                  unsigned int total_tiles, const double *filt_table, const int *tuning_idx,
+                  unsigned int total_tiles, const float *filt_table, const int *tuning_idx,
                   double *tile_partials, double *chroma_dbg, cudaStream_t st) {
     if (total_tiles == 0) return 0;
     chroma_kernel<<<total_tiles, K5_THREADS, 0, st>>>(mags, songs, tile_prefix, n_songs, filt_table,

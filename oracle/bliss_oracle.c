@@ -30,7 +30,12 @@ static fft_plan g_plans[8];
 static int g_nplans = 0;
 static pthread_mutex_t g_plan_mu = PTHREAD_MUTEX_INITIALIZER;
 
+/* Plans are append-only: the hot path scans the published ones without taking the lock (a global
+ * mutex per FFT call serialised the ~50 000 transforms per song of every worker thread). */
 static const fft_plan *get_plan(uint32_t n) {
+    int np = __atomic_load_n(&g_nplans, __ATOMIC_ACQUIRE);
+    for (int i = 0; i < np; i++)
+        if (g_plans[i].n == n) return &g_plans[i];
     pthread_mutex_lock(&g_plan_mu);
     for (int i = 0; i < g_nplans; i++)
         if (g_plans[i].n == n) {
@@ -55,7 +60,7 @@ static const fft_plan *get_plan(uint32_t n) {
         p->tw[2 * k] = (float)cos(a);
         p->tw[2 * k + 1] = (float)sin(a);
     }
-    g_nplans++;
+    __atomic_store_n(&g_nplans, g_nplans + 1, __ATOMIC_RELEASE);
     pthread_mutex_unlock(&g_plan_mu);
     return p;
 }

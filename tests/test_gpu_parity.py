@@ -241,6 +241,28 @@ def test_three_minute_track_matches_oracle():
     assert np.array_equal(a, B.Song.analyze(x).as_arr1())
 
 
+# ---------------------------------------------------------------- BASELINE.json config 5 shape
+def test_mixed_duration_corpus_and_playlist_order():
+    """30 s .. 10 min tracks (Zipf-like), one call; then playlist-from-seed = closest_to_songs
+    ([seed], all, v2 metric) must come out in the oracle's order (stable on ties)."""
+    secs = [30, 30, 45, 600, 60, 30, 210, 120, 30, 75, 30, 300]
+    songs = [synth.gen_track(23, i, 22050 * s_ + 37 * i, device="cuda").cpu().numpy() for i, s_ in enumerate(secs)]
+    st, feats = B.native.analyze_batch(songs, 2)
+    ost, ofe = O.analyze_batch(songs, 2, n_threads=12)
+    assert (st == 0).all() and (ost == 0).all()
+    err = np.abs(feats - ofe)
+    print("mixed-duration corpus: max abs err %.2e (song %d, feature %d)" % (err.max(), *np.unravel_index(err.argmax(), err.shape)))
+    assert _close(feats, ofe).all()
+    w = O.feature_weights(2)
+    order, keys = B.native.closest_to_songs(feats[:1], feats, 0, w)
+    oorder, okeys = O.closest_to_songs(ofe[:1], ofe, w)
+    assert order[0] == 0 and list(order) == list(oorder)
+    # and the sharding used at N>1 keeps every song exactly once, balanced by duration
+    from bliss_rs_b200 import multigpu as M
+    shards = M.shard_longest_first([len(s_) for s_ in songs], 4)
+    assert sorted(i for sh in shards for i in sh) == list(range(len(songs)))
+
+
 # ---------------------------------------------------------------- device-resident API + STFT micro-benchmark path
 def test_device_api_matches_host_api(pcm_song, pcm_piano):
     songs = [pcm_song, pcm_piano, pcm_song[:7000], pcm_piano[:50001]]
