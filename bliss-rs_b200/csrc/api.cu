@@ -177,7 +177,7 @@ SongGeom geom_of(uint64_t n) {
     q.n_c_comp = (uint32_t)std::min<uint64_t>(q.n_c, windows);
     q.n_l = (uint32_t)((n + 1023) / 1024);
     q.n_eb = (uint32_t)(n / 256);
-    q.n_pairs8k = q.n_c_comp;  // one CTA per chroma frame
+    q.n_pairs8k = (q.n_c_comp + 3) / 4;  // stft8192_kernel: one CTA per 4 consecutive chroma frames
     q.n_tiles = (q.n_c + CH_TILE_FRAMES - 1) / CH_TILE_FRAMES;
     q.bpm_cap = q.n_t / 16 + 16;
     const size_t rows = (size_t)q.n_c_comp;
@@ -580,8 +580,20 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
                                uint16_t ver, float *out, int32_t *status, bool debug) {
     const uint32_t dim = bliss_b200_feature_count(ver);
     CK(g.feats.ensure((size_t)n_songs * dim * 4));
-    // small chunks keep the copy/compute pipeline's fill and drain short (the path is PCIe-bound)
-    const size_t chunk_budget = std::min<size_t>((size_t)384 << 20, std::max<size_t>(g.ws_limit / 8, (size_t)64 << 20));
+    // The path is PCIe-bound (15.9 MB per 3-min song), so the copy engine must never idle: chunks of
+    // songs are copied on a side stream while the previous chunk computes.  Chunk sizes ramp up from
+    // 32 MB (short pipeline fill), plateau at 384 MB and ramp down again (short drain).
+    size_t total_bytes = 0;
+    for (uint32_t i = 0; i < n_songs; i++) total_bytes += align_up((size_t)n_samples[i], 4) * 4;
+    const size_t plateau = std::min<size_t>((size_t)384 << 20, std::max<size_t>(g.ws_limit / 8, (size_t)64 << 20));
+    size_t done_bytes = 0;
+    auto chunk_budget_now = [&](int c) -> size_t {
+        size_t up = (size_t)32 << 20;
+        for (int i = 0; i < c && up < plateau; i++) up *= 2;
+        const size_t remaining = total_bytes - std::min(done_bytes, total_bytes);
+        const size_t down = std::max<size_t>(remaining / 2, (size_t)32 << 20);
+        return std::min(std::min(up, plateau), down);
+    };
     cudaEvent_t ev_copy[2], ev_done[2];
     for (int i = 0; i < 2; i++) {
         CK(cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming));
@@ -597,6 +609,7 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
         uint32_t count = 0;
         offs.clear();
         lens.clear();
+        const size_t chunk_budget = chunk_budget_now(c);
         while (first + count < n_songs) {
             const size_t len = align_up((size_t)n_samples[first + count], 4);
             if (count > 0 && (samples + len) * 4 > chunk_budget) break;
@@ -623,6 +636,7 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
         CK(cudaEventRecord(ev_done[b], g.stream));
         used[b] = true;
         first += count;
+        done_bytes += samples * 4;
         c++;
     }
     if (rc == BLISS_B200_OK) {

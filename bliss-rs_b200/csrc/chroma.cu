@@ -73,6 +73,7 @@ int launch_chroma_filter_table(double *table, float *table32, cudaStream_t st) {
 // (rfft8192.cuh), magnitudes to the spill buffer, pip_track peaks to the candidate list.
 // ---------------------------------------------------------------------------
 constexpr int K3_THREADS = 256;
+constexpr int K3_FRAMES_PER_CTA = 4;  // consecutive frames of one song per CTA (amortises the song lookup)
 
 // one pip_track candidate test in f32 (the f64 comparisons of chroma.rs:308 are order
 // preserving on f32-exact values); `ref` stays f64 because 0.1*max is not an f32
@@ -112,9 +113,11 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     const unsigned int item = blockIdx.x;
     const int si = find_song(frame_prefix, n_songs, item);
     const SongDesc sd = songs[si];
-    const int f = (int)(item - frame_prefix[si]);
+    const int fbase = (int)(item - frame_prefix[si]) * K3_FRAMES_PER_CTA;
     const float *x = pcm + sd.pcm_off;
     const int n = (int)sd.n;
+#pragma unroll 1
+    for (int f = fbase; f < min(fbase + K3_FRAMES_PER_CTA, (int)sd.n_c_comp); f++) {
     // the frame covers samples s0 .. s0+8191 of the reflect-padded song (utils.rs:11-24, :44-47)
     const int s0 = CH_HOP * f - 4096;
     const bool interior = (s0 >= 0) && (s0 + 8191 < n);
@@ -204,8 +207,7 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
         if (w < (tid >> 5)) woff += s_scan[w];
         tot += s_scan[w];
     }
-    if (tot == 0) return;
-    if (tid == 0) s_base = atomicAdd(cand_count + si, tot);
+    if (tid == 0 && tot) s_base = atomicAdd(cand_count + si, tot);
     __syncthreads();
     unsigned long long dst = sd.cand_off + s_base + woff + (incl - (unsigned)cnt);
     while (flags) {
@@ -229,6 +231,8 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
         cand_bin[dst] = (unsigned char)idx;
         dst++;
     }
+    __syncthreads();  // the magnitudes in `buf` were read by pip_track; the next frame overwrites them
+    }  // frames of this CTA
 }
 
 // ---------------------------------------------------------------------------
@@ -533,6 +537,7 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
 }
 
 // ---- launchers ---------------------------------------------------------------
+// frame_prefix counts groups of K3_FRAMES_PER_CTA (= 4) frames per song
 int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int *frame_prefix, int n_songs,
                     unsigned int total_frames, const float *hann, const cpx *tw1, const cpx *tw2,
                     const cpx *tw8192, float *mags, double *cand_mag, unsigned char *cand_bin,

@@ -54,7 +54,7 @@ struct PvocTables {   // device pointers
 __device__ __forceinline__ int find_song(const unsigned int *__restrict__ prefix, int n_songs,
                                          unsigned int item) {
     const unsigned int total = __ldg(prefix + n_songs);
-    int s = (int)(((unsigned long long)item * (unsigned long long)n_songs) / (total ? total : 1u));
+    int s = (int)((float)item * ((float)n_songs / (float)(total ? total : 1u)));  // a guess: float is plenty
     s = min(max(s, 0), n_songs - 1);
 #pragma unroll 1
     for (int tries = 0; tries < 4; tries++) {
