@@ -4,6 +4,8 @@
 // result is produced by the kernels in spectral.cu / tempo.cu / chroma.cu /
 // finalize.cu / distance.cu, and every entry point fails loudly without a GPU.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -580,20 +582,21 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
                                uint16_t ver, float *out, int32_t *status, bool debug) {
     const uint32_t dim = bliss_b200_feature_count(ver);
     CK(g.feats.ensure((size_t)n_songs * dim * 4));
-    // The path is PCIe-bound (15.9 MB per 3-min song), so the copy engine must never idle: chunks of
-    // songs are copied on a side stream while the previous chunk computes.  Chunk sizes ramp up from
-    // 32 MB (short pipeline fill), plateau at 384 MB and ramp down again (short drain).
-    size_t total_bytes = 0;
-    for (uint32_t i = 0; i < n_songs; i++) total_bytes += align_up((size_t)n_samples[i], 4) * 4;
-    const size_t plateau = std::min<size_t>((size_t)384 << 20, std::max<size_t>(g.ws_limit / 8, (size_t)64 << 20));
+    // The path is PCIe-bound (15.9 MB per 3-min song): chunks of songs are copied on a side stream while
+    // the previous chunk computes (two device PCM buffers).  Chunk size trades pipeline fill (first
+    // copy is exposed) against the per-chunk latency of the sequential kernels (tuning, beat tracker
+    // ~2 ms whatever the chunk size); BLISS_B200_CHUNK_MB overrides the default for experiments.
+    size_t chunk_mb = 192;
+    if (const char *e = getenv("BLISS_B200_CHUNK_MB")) chunk_mb = (size_t)std::max(8, atoi(e));
+    const size_t chunk_budget = std::min<size_t>(chunk_mb << 20, std::max<size_t>(g.ws_limit / 8, (size_t)64 << 20));
+    const bool trace = getenv("BLISS_B200_TRACE") != nullptr;
+    cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};  // copy begin/end, compute begin/end
+    if (trace) {
+        for (auto &e : tr) CK(cudaEventCreate(&e));
+        CK(cudaEventRecord(tr[0], g.copy_stream));
+        CK(cudaEventRecord(tr[2], g.stream));
+    }
     size_t done_bytes = 0;
-    auto chunk_budget_now = [&](int c) -> size_t {
-        size_t up = (size_t)32 << 20;
-        for (int i = 0; i < c && up < plateau; i++) up *= 2;
-        const size_t remaining = total_bytes - std::min(done_bytes, total_bytes);
-        const size_t down = std::max<size_t>(remaining / 2, (size_t)32 << 20);
-        return std::min(std::min(up, plateau), down);
-    };
     cudaEvent_t ev_copy[2], ev_done[2];
     for (int i = 0; i < 2; i++) {
         CK(cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming));
@@ -609,7 +612,6 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
         uint32_t count = 0;
         offs.clear();
         lens.clear();
-        const size_t chunk_budget = chunk_budget_now(c);
         while (first + count < n_songs) {
             const size_t len = align_up((size_t)n_samples[first + count], 4);
             if (count > 0 && (samples + len) * 4 > chunk_budget) break;
@@ -640,8 +642,22 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
         c++;
     }
     if (rc == BLISS_B200_OK) {
+        if (trace) {
+            CK(cudaEventRecord(tr[1], g.copy_stream));
+            CK(cudaEventRecord(tr[3], g.stream));
+        }
         CK(cudaMemcpyAsync(out, g.feats.p, (size_t)n_songs * dim * 4, cudaMemcpyDeviceToHost, g.stream));
         CK(cudaStreamSynchronize(g.stream));
+        if (trace) {
+            float ms_copy = 0.f, ms_comp = 0.f, ms_all = 0.f;
+            cudaEventElapsedTime(&ms_copy, tr[0], tr[1]);
+            cudaEventElapsedTime(&ms_comp, tr[2], tr[3]);
+            cudaEventElapsedTime(&ms_all, tr[0], tr[3]);
+            fprintf(stderr, "[bliss_b200 trace] songs=%u bytes=%.1f MB chunks=%d chunk_mb=%zu copy_stream=%.2f ms (%.1f GB/s) "
+                            "compute_stream=%.2f ms first_copy->last_kernel=%.2f ms\n",
+                    n_songs, done_bytes / 1e6, c, chunk_mb, ms_copy, done_bytes / 1e6 / ms_copy, ms_comp, ms_all);
+            for (auto &e : tr) cudaEventDestroy(e);
+        }
     } else {
         cudaStreamSynchronize(g.stream);
         cudaStreamSynchronize(g.copy_stream);
