@@ -9,7 +9,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libbliss_b200.so")
+# BLISS_B200_SO selects an experimental build of the same sources (scripts/build_variants.py); tests and
+# the bench default to the in-tree product library
+SO_PATH = os.environ.get("BLISS_B200_SO") or os.path.join(_HERE, "libbliss_b200.so")
 
 N_KERNELS = 10
 METRIC_MAHALANOBIS = 0

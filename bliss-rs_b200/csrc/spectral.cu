@@ -90,8 +90,11 @@ __device__ __forceinline__ void frame_descriptors(const float (&v)[8], int lane,
 // WITH_DESC: timbral descriptors + flux (the analysis path).
 // WITH_MAGS: materialise the 257 tempo-frame magnitudes (STFT micro-benchmark,
 //            BASELINE.json config 3 = PVocTempo framing: 512 / hop 256).
+#ifndef K1_MINBLOCKS
+#define K1_MINBLOCKS 2
+#endif
 template <bool WITH_DESC, bool WITH_MAGS>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, K1_MINBLOCKS)
 pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
                const unsigned int *__restrict__ item_prefix, int n_songs, unsigned int total_items,
                int pairs_per_item, PvocTables tab, float *__restrict__ centroid,

@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Builds experimental variants of libbliss_b200.so (same sources, different -D tuning knobs) into
+bliss-rs_b200/variants/ so that one gpurun call can A/B them:  BLISS_B200_SO=<path> python bench.py ..."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "bliss-rs_b200", "csrc")
+OUT = os.path.join(ROOT, "bliss-rs_b200", "variants")
+SOURCES = ["spectral.cu", "tempo.cu", "chroma.cu", "finalize.cu", "distance.cu", "api.cu"]
+BASE = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+        "-Wno-deprecated-gpu-targets"]
+
+VARIANTS = {
+    "k1mb3": ["-DK1_MINBLOCKS=3"],
+    "k1mb4": ["-DK1_MINBLOCKS=4"],
+}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, defs in VARIANTS.items():
+        objs = []
+        for src in SOURCES:
+            o = os.path.join(OUT, "%s_%s.o" % (name, src[:-3]))
+            cmd = BASE + defs + (["-fmad=false"] if src == "tempo.cu" else []) + ["-c", os.path.join(CSRC, src), "-o", o]
+            subprocess.check_call(cmd)
+            objs.append(o)
+        so = os.path.join(OUT, "libbliss_b200_%s.so" % name)
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", so] + objs + ["-lcudart"])
+        for o in objs:
+            os.remove(o)
+        print(so)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
