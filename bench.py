@@ -32,7 +32,7 @@ if ROOT not in sys.path:
 
 TRACK_SAMPLES = 3 * 60 * 22050          # 3 969 000 samples = 15 876 000 B
 SONGS_PER_GPU = 1024                    # BASELINE.json configs[1]
-E2E_SONGS = 512                         # songs per e2e step (pinned host -> device inside the timed region)
+E2E_SONGS = 256                         # songs per e2e step (pinned host -> device inside the timed region)
 METRIC = "songs/sec (3-min 22050Hz f32 PCM) at 1/2/4/8 B200 vs ref CPU; STFT HBM GB/s"
 BASE_SEED = 20260925
 

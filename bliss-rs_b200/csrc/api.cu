@@ -586,7 +586,7 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
     // the previous chunk computes (two device PCM buffers).  Chunk size trades pipeline fill (first
     // copy is exposed) against the per-chunk latency of the sequential kernels (tuning, beat tracker
     // ~2 ms whatever the chunk size); BLISS_B200_CHUNK_MB overrides the default for experiments.
-    size_t chunk_mb = 192;
+    size_t chunk_mb = 128;
     if (const char *e = getenv("BLISS_B200_CHUNK_MB")) chunk_mb = (size_t)std::max(8, atoi(e));
     const size_t chunk_budget = std::min<size_t>(chunk_mb << 20, std::max<size_t>(g.ws_limit / 8, (size_t)64 << 20));
     const bool trace = getenv("BLISS_B200_TRACE") != nullptr;

@@ -283,6 +283,23 @@ def test_device_api_matches_host_api(pcm_song, pcm_piano):
     assert np.array_equal(got[[0, 1, 3]], hfe[[0, 1, 3]]) and (got[2] == 0).all()
 
 
+def test_cue_style_subslices_of_one_buffer(pcm_song):
+    """BlissCueFile::get_songs (src/cue.rs:208-243) analyses sub-slices of ONE decoded buffer cut at
+    (start_s * 22050) as usize -- arbitrary, unaligned sample offsets; they may even overlap."""
+    d = torch.from_numpy(np.ascontiguousarray(pcm_song)).cuda()
+    cuts = [(0, 88201), (88201, 176403), (100003, 230001), (176403, len(pcm_song))]
+    offs = [a for a, b in cuts]
+    lens = [b - a for a, b in cuts]
+    out = torch.zeros((len(cuts), 23), dtype=torch.float32, device="cuda")
+    st = B.native.analyze_batch_device(d.data_ptr(), offs, lens, 2, out.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert (st == 0).all()
+    got = out.cpu().numpy()
+    for i, (a, b) in enumerate(cuts):
+        rc, want = O.analyze(pcm_song[a:b], 2)
+        assert rc == 0 and _close(got[i], want).all(), (i, np.abs(got[i] - want).max())
+
+
 def test_stft512_magnitudes(pcm_song):
     x = pcm_song[:60000]
     n_t = (len(x) - 512) // 256 + 1
