@@ -234,7 +234,15 @@ def main():
     clocks = sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     lz = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        # per-rank diagnostics (device ms of the timed region, median SM clock, max power) for the scaling analysis
+        mine = torch.tensor([ms, float(clocks.get("sm_mhz") or 0), float(clocks.get("power_w_max") or 0)],
+                            dtype=torch.float64, device=dev)
+        allr = torch.zeros((world, 3), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = {"ms": [round(v, 2) for v in allr[:, 0].tolist()], "sm_mhz": allr[:, 1].tolist(),
+                    "power_w_max": allr[:, 2].tolist()}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(lz, op=dist.ReduceOp.SUM)
     ms = float(t.item())
@@ -337,7 +345,7 @@ def main():
                        "songs_per_gpu": S, "track_samples": TRACK_SAMPLES, "parallelism": "songs sharded %d-way" % world,
                        "l2": "inputs (%.1f GB PCM per GPU) are far larger than the 126 MB L2; no flush needed"
                              % (S * TRACK_SAMPLES * 4 / 1e9)},
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "per_rank": per_rank,
             "gpu_launches": int(lz.item()),
         }
         _emit(line)

@@ -31,9 +31,9 @@ int launch_beattrack(const float *, const float *, const SongDesc *, int, float 
                      cudaStream_t);
 int launch_chroma_filter_table(double *, float *, cudaStream_t);
 int launch_stft8192(const float *, const SongDesc *, const unsigned int *, int, unsigned int, const float *,
-                    const cpx *, const cpx *, const cpx *, float *, double *, unsigned char *, unsigned int *,
+                    const cpx *, const cpx *, const cpx *, float *, double *, double *, unsigned int *,
                     cudaStream_t);
-int launch_tuning(const double *, const unsigned char *, const unsigned int *, const SongDesc *, int, int *,
+int launch_tuning(const double *, const double *, const unsigned int *, const SongDesc *, int, int *,
                   cudaStream_t);
 int launch_chroma(const float *, const SongDesc *, const unsigned int *, int, unsigned int, const float *,
                   const int *, double *, double *, cudaStream_t);
@@ -113,7 +113,7 @@ struct Ctx {
     DevBuf t_win512, t_twA, t_hann8k, t_tw4k, t_tw2, t_tw8k, t_filt, t_filt32;
     // wave scratch
     DevBuf blob;  // SongDesc + prefix arrays
-    DevBuf mags, cand_mag, cand_bin, cand_count, cent, roll, flat, flux, thr, loud, eb, zcr, tempo, bpm,
+    DevBuf mags, cand_mag, cand_pitch, cand_count, cent, roll, flat, flux, thr, loud, eb, zcr, tempo, bpm,
         bpm_count, tuning, tiles, chroma_dbg;
     // host-API staging
     DevBuf pcm[2], feats, metric, misc[6];
@@ -183,7 +183,7 @@ SongGeom geom_of(uint64_t n) {
     q.n_tiles = (q.n_c + CH_TILE_FRAMES - 1) / CH_TILE_FRAMES;
     q.bpm_cap = q.n_t / 16 + 16;
     const size_t rows = (size_t)q.n_c_comp;
-    q.scratch_bytes = rows * CH_STRIDE * 4 + rows * CH_MAX_PEAKS * 9 + (size_t)q.n_s * 12 + (size_t)q.n_t * 8 +
+    q.scratch_bytes = rows * CH_STRIDE * 4 + rows * CH_MAX_PEAKS * 16 + (size_t)q.n_s * 12 + (size_t)q.n_t * 8 +
                       (size_t)q.n_l * 4 + (size_t)q.n_eb * 4 + (size_t)q.n_tiles * 80 + (size_t)q.bpm_cap * 4 + 256;
     return q;
 }
@@ -301,7 +301,7 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
     if (n == 0) return BLISS_B200_OK;
     CK(g.mags.ensure(std::max<size_t>(w.rows, 2) * CH_STRIDE * sizeof(float)));
     CK(g.cand_mag.ensure(std::max<size_t>(w.cands, 1) * sizeof(double)));
-    CK(g.cand_bin.ensure(std::max<size_t>(w.cands, 1)));
+    CK(g.cand_pitch.ensure(std::max<size_t>(w.cands, 1) * sizeof(double)));  // interpolated pitches (f64)
     CK(g.cand_count.ensure((size_t)n * 4));
     CK(g.cent.ensure(std::max<size_t>(w.n_s, 1) * 4));
     CK(g.roll.ensure(std::max<size_t>(w.n_s, 1) * 4));
@@ -334,7 +334,7 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
     { ProfScope p(K_STFT8K, sb);
       p.done(launch_stft8192(d_pcm, dv.sd, dv.pair_prefix, n, w.pair_prefix[n], g.t_hann8k.as<float>(),
                              g.t_tw4k.as<cpx>(), g.t_tw2.as<cpx>(), g.t_tw8k.as<cpx>(), g.mags.as<float>(), g.cand_mag.as<double>(),
-                             g.cand_bin.as<unsigned char>(), g.cand_count.as<unsigned int>(), sb)); }
+                             g.cand_pitch.as<double>(), g.cand_count.as<unsigned int>(), sb)); }
     { ProfScope p(K_TIME, st);
       p.done(launch_timedomain(d_pcm, dv.sd, dv.chunk_prefix, n, w.chunk_prefix[n], g.loud.as<float>(),
                                g.eb.as<float>(), g.zcr.as<unsigned int>(), st)); }
@@ -342,7 +342,7 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
       p.done(launch_pvoc512(d_pcm, dv.sd, dv.k1_prefix, n, w.k1_prefix[n], (int)w.pairs_per_item, pvoc_tables(),
                             g.cent.as<float>(), g.roll.as<float>(), g.flat.as<float>(), g.flux.as<float>(), st)); }
     { ProfScope p(K_TUNING, sb);
-      p.done(launch_tuning(g.cand_mag.as<double>(), g.cand_bin.as<unsigned char>(),
+      p.done(launch_tuning(g.cand_mag.as<double>(), g.cand_pitch.as<double>(),
                            g.cand_count.as<unsigned int>(), dv.sd, n, g.tuning.as<int>(), sb)); }
     { ProfScope p(K_PEAK, st);
       p.done(launch_peakpick(g.flux.as<float>(), dv.sd, dv.t_prefix, n, w.t_prefix[n], g.thr.as<float>(), st)); }
@@ -529,7 +529,7 @@ void bliss_b200_shutdown(void) {
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
     DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw4k, &g.t_tw2, &g.t_tw8k, &g.t_filt, &g.t_filt32, &g.blob, &g.mags, &g.cand_mag,
-                     &g.cand_bin, &g.cand_count, &g.cent, &g.roll, &g.flat, &g.flux, &g.thr, &g.loud, &g.eb,
+                     &g.cand_pitch, &g.cand_count, &g.cent, &g.roll, &g.flat, &g.flux, &g.thr, &g.loud, &g.eb,
                      &g.zcr, &g.tempo, &g.bpm, &g.bpm_count, &g.tuning, &g.tiles, &g.chroma_dbg, &g.pcm[0],
                      &g.pcm[1], &g.feats, &g.metric, &g.misc[0], &g.misc[1], &g.misc[2], &g.misc[3],
                      &g.misc[4], &g.misc[5]};

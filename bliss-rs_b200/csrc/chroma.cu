@@ -100,7 +100,7 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
                 const float *__restrict__ hann, const cpx *__restrict__ tw1 /*[16][256] W4096^(b k1)*/,
                 const cpx *__restrict__ tw2g /*[16][16] W256^(j k2)*/, const cpx *__restrict__ tw8192,
                 float *__restrict__ mags,
-                double *__restrict__ cand_mag, unsigned char *__restrict__ cand_bin,
+                double *__restrict__ cand_mag, double *__restrict__ cand_pitch,
                 unsigned int *__restrict__ cand_count) {
     __shared__ __align__(16) cpx buf[r8k::BUF_CPX];
     __shared__ cpx s_tw2[256];
@@ -219,16 +219,10 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
         double shift = 2. * elem - after - before;
         if (fabs(shift) < 2.2250738585072014e-308) shift += 1.;
         shift = avg / shift;
-        const double pitch = ((double)c + shift) * (double)SAMPLE_RATE / 8192.0;
-        // pitch_tuning's residue bin (chroma.rs:342-348), tuning 0, 12 bins/octave
-        double v = pitch / (440.0 / 16.);
-        v = log2(v);
-        v = fmod(12.0 * v, 1.0);
-        if (v >= 0.5) v -= 1.;
-        int idx = (int)((v - -0.5) / 0.01);
-        idx = idx < 0 ? 0 : (idx > 99 ? 99 : idx);
+        // the residue bin of pitch_tuning (log2 / fmod in f64) is left to tuning_kernel, which is
+        // latency-bound and overlapped; here only the interpolation of chroma.rs:317-326
+        cand_pitch[dst] = ((double)c + shift) * (double)SAMPLE_RATE / 8192.0;
         cand_mag[dst] = elem + 0.5 * avg * shift;
-        cand_bin[dst] = (unsigned char)idx;
         dst++;
     }
     __syncthreads();  // the magnitudes in `buf` were read by pip_track; the next frame overwrites them
@@ -253,7 +247,7 @@ __device__ __forceinline__ void hist_add(unsigned int *hist, unsigned int bucket
 }
 
 __global__ void __launch_bounds__(K4_THREADS)
-tuning_kernel(const double *__restrict__ cand_mag, const unsigned char *__restrict__ cand_bin,
+tuning_kernel(const double *__restrict__ cand_mag, const double *__restrict__ cand_pitch,
               const unsigned int *__restrict__ cand_count, const SongDesc *__restrict__ songs,
               int *__restrict__ tuning_idx) {
     __shared__ unsigned int hist[256];
@@ -267,7 +261,7 @@ tuning_kernel(const double *__restrict__ cand_mag, const unsigned char *__restri
         return;
     }
     const unsigned long long *keys = reinterpret_cast<const unsigned long long *>(cand_mag + sd.cand_off);
-    const unsigned char *bins = cand_bin + sd.cand_off;
+    const double *pitches = cand_pitch + sd.cand_off;
     const unsigned int r_lo = (n - 1) / 2, r_hi = n / 2;  // floor / ceil of (n-1)*0.5
 
     if (tid == 0) { s_prefix = 0ull; s_rank = r_lo; }
@@ -342,7 +336,16 @@ tuning_kernel(const double *__restrict__ cand_mag, const unsigned char *__restri
             unsigned int bucket = 0;
             if (i < n) {
                 act = mg[i] >= thr;
-                bucket = bins[i];
+                if (act) {
+                    // pitch_tuning (chroma.rs:342-348): hz_to_octs with tuning 0, 12 bins/octave, residue in
+                    // [-0.5, 0.5), 100 bins of 0.01
+                    double v = pitches[i] / (440.0 / 16.);
+                    v = log2(v);
+                    v = fmod(12.0 * v, 1.0);
+                    if (v >= 0.5) v -= 1.;
+                    int idx = (int)((v - -0.5) / 0.01);
+                    bucket = (unsigned int)(idx < 0 ? 0 : (idx > 99 ? 99 : idx));
+                }
             }
             hist_add(hist, bucket, act);
         }
@@ -540,18 +543,18 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
 // frame_prefix counts groups of K3_FRAMES_PER_CTA (= 4) frames per song
 int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int *frame_prefix, int n_songs,
                     unsigned int total_frames, const float *hann, const cpx *tw1, const cpx *tw2,
-                    const cpx *tw8192, float *mags, double *cand_mag, unsigned char *cand_bin,
+                    const cpx *tw8192, float *mags, double *cand_mag, double *cand_pitch,
                     unsigned int *cand_count, cudaStream_t st) {
     if (total_frames == 0) return 0;
     stft8192_kernel<<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw1, tw2,
-                                                         tw8192, mags, cand_mag, cand_bin, cand_count);
+                                                         tw8192, mags, cand_mag, cand_pitch, cand_count);
     return 1;
 }
 
-int launch_tuning(const double *cand_mag, const unsigned char *cand_bin, const unsigned int *cand_count,
+int launch_tuning(const double *cand_mag, const double *cand_pitch, const unsigned int *cand_count,
                   const SongDesc *songs, int n_songs, int *tuning_idx, cudaStream_t st) {
     if (n_songs == 0) return 0;
-    tuning_kernel<<<n_songs, K4_THREADS, 0, st>>>(cand_mag, cand_bin, cand_count, songs, tuning_idx);
+    tuning_kernel<<<n_songs, K4_THREADS, 0, st>>>(cand_mag, cand_pitch, cand_count, songs, tuning_idx);
     return 1;
 }
 

@@ -78,16 +78,17 @@ BLISS_HD cpx z_value(const cpx *buf, int k) {
 // (src/utils.rs:57-60)
 BLISS_HD float untangle_mag(cpx zk, cpx zm, cpx w) {
     // E = (Zk + conj Zm)/2, O = (Zk - conj Zm)/2;  X = E - i w O
-    const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
-    const float orr = 0.5f * (zk.x - zm.x), oi = 0.5f * (zk.y + zm.y);
+    // (the two factors 1/2 are applied once to the magnitude: exact, power of two)
+    const float er = zk.x + zm.x, ei = zk.y - zm.y;
+    const float orr = zk.x - zm.x, oi = zk.y + zm.y;
     // w O
     const float pr = w.x * orr - w.y * oi, pi = w.x * oi + w.y * orr;
     // -i (pr + i pi) = pi - i pr
     const float xr = er + pi, xi = ei - pr;
 #ifdef __CUDA_ARCH__
-    return approx_sqrtf(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi)));
+    return 0.5f * approx_sqrtf(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi)));
 #else
-    return sqrtf(xr * xr + xi * xi);
+    return 0.5f * sqrtf(xr * xr + xi * xi);
 #endif
 }
 
