@@ -48,19 +48,21 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  ONE nvidia-smi process
+    (started by rank 0) polls every local GPU of the job: eight pollers at 100 ms would contend on
+    the driver with the ranks' own launches."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, indices):
+        self.indices, self.rows, self.proc = list(indices), [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                ["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -78,21 +80,28 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             pass
-        sm, mx, reasons, pw = [], [], set(), []
+        per = {}
+        reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                g = per.setdefault(int(f[0]), {"sm": [], "mx": [], "pw": []})
+                g["sm"].append(float(f[1])); g["mx"].append(float(f[2])); g["pw"].append(float(f[3]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[3:7]):
+            for nm, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if not per:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(reasons), "samples": 0}
+        med = {k: float(np.median(v["sm"])) for k, v in per.items()}
+        return {"sm_mhz": min(med.values()), "sm_max_mhz": max(max(v["mx"]) for v in per.values()),
+                "power_w_max": max(max(v["pw"]) for v in per.values()),
+                "samples": sum(len(v["sm"]) for v in per.values()), "reasons": sorted(reasons),
+                "per_gpu_sm_mhz_median": {str(k): v for k, v in sorted(med.items())}}
 
 
 def algorithmic_bytes_per_song():
@@ -220,8 +229,9 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(range(world)) if rank == 0 else None  # one node: local GPUs 0..world-1
+    if sampler:
+        sampler.start()
     launches0 = nat.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -231,18 +241,16 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = nat.launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else {}
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     lz = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
     per_rank = None
     if world > 1:
         # per-rank diagnostics (device ms of the timed region, median SM clock, max power) for the scaling analysis
-        mine = torch.tensor([ms, float(clocks.get("sm_mhz") or 0), float(clocks.get("power_w_max") or 0)],
-                            dtype=torch.float64, device=dev)
-        allr = torch.zeros((world, 3), dtype=torch.float64, device=dev)
+        mine = torch.tensor([ms], dtype=torch.float64, device=dev)
+        allr = torch.zeros((world, 1), dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allr, mine)
-        per_rank = {"ms": [round(v, 2) for v in allr[:, 0].tolist()], "sm_mhz": allr[:, 1].tolist(),
-                    "power_w_max": allr[:, 2].tolist()}
+        per_rank = {"ms": [round(v, 2) for v in allr[:, 0].tolist()]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(lz, op=dist.ReduceOp.SUM)
     ms = float(t.item())
