@@ -623,11 +623,20 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
         const int b = c & 1;
         if (used[b]) CK(cudaEventSynchronize(ev_done[b]));  // buffer b free again (also: host may realloc)
         CK(g.pcm[b].ensure(std::max<size_t>(samples, 4) * 4));
-        for (uint32_t i = 0; i < count; i++) {
-            if (lens[i] == 0) continue;
+        for (uint32_t i = 0; i < count;) {
+            if (lens[i] == 0) { i++; continue; }
             if (!pcm[first + i]) { g_last_error = "null pcm pointer"; rc = BLISS_B200_E_ARG; break; }
-            CK(cudaMemcpyAsync(g.pcm[b].as<float>() + offs[i], pcm[first + i], (size_t)lens[i] * 4,
-                               cudaMemcpyHostToDevice, g.copy_stream));
+            // songs that sit back to back in host memory (one big decoded buffer) go as ONE copy
+            uint32_t j = i;
+            size_t run = (size_t)lens[i];
+            while (j + 1 < count && lens[j + 1] > 0 && (lens[j] & 3u) == 0 &&
+                   pcm[first + j + 1] == pcm[first + j] + lens[j]) {
+                j++;
+                run += (size_t)lens[j];
+            }
+            CK(cudaMemcpyAsync(g.pcm[b].as<float>() + offs[i], pcm[first + i], run * 4, cudaMemcpyHostToDevice,
+                               g.copy_stream));
+            i = j + 1;
         }
         if (rc) break;
         CK(cudaEventRecord(ev_copy[b], g.copy_stream));

@@ -263,6 +263,17 @@ def test_mixed_duration_corpus_and_playlist_order():
     assert sorted(i for sh in shards for i in sh) == list(range(len(songs)))
 
 
+def test_song_longer_than_2_pow_24_samples():
+    """utils.rs:30 computes the chroma frame count in f32 ((len as f32 / 2205.).ceil()), exact only below
+    2^24 samples (~12.7 min).  A 13.2-minute track exercises the same f32 formula on both sides."""
+    n = (1 << 24) + 700001
+    x = synth.gen_track(29, 5, n, device="cuda").cpu().numpy()
+    a = B.Song.analyze(x).as_arr1()
+    rc, o = O.analyze(x, 2)
+    _report("13-min track", a, o)
+    assert rc == 0 and _close(a, o).all()
+
+
 # ---------------------------------------------------------------- device-resident API + STFT micro-benchmark path
 def test_device_api_matches_host_api(pcm_song, pcm_piano):
     songs = [pcm_song, pcm_piano, pcm_song[:7000], pcm_piano[:50001]]
