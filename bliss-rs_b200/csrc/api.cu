@@ -116,7 +116,7 @@ struct Ctx {
     DevBuf mags, cand_mag, cand_pitch, cand_count, cent, roll, flat, flux, thr, loud, eb, zcr, tempo, bpm,
         bpm_count, tuning, tiles, chroma_dbg;
     // host-API staging
-    DevBuf pcm[2], feats, metric, misc[6];
+    DevBuf pcm[4], feats, metric, misc[6];
     // pinned staging ring for descriptor uploads
     void *stage[N_STAGE] = {nullptr, nullptr, nullptr, nullptr};
     size_t stage_cap[N_STAGE] = {0, 0, 0, 0};
@@ -531,7 +531,7 @@ void bliss_b200_shutdown(void) {
     DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw4k, &g.t_tw2, &g.t_tw8k, &g.t_filt, &g.t_filt32, &g.blob, &g.mags, &g.cand_mag,
                      &g.cand_pitch, &g.cand_count, &g.cent, &g.roll, &g.flat, &g.flux, &g.thr, &g.loud, &g.eb,
                      &g.zcr, &g.tempo, &g.bpm, &g.bpm_count, &g.tuning, &g.tiles, &g.chroma_dbg, &g.pcm[0],
-                     &g.pcm[1], &g.feats, &g.metric, &g.misc[0], &g.misc[1], &g.misc[2], &g.misc[3],
+                     &g.pcm[1], &g.pcm[2], &g.pcm[3], &g.feats, &g.metric, &g.misc[0], &g.misc[1], &g.misc[2], &g.misc[3],
                      &g.misc[4], &g.misc[5]};
     for (DevBuf *b : all) b->release();
     for (int i = 0; i < N_STAGE; i++) {
@@ -583,10 +583,12 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
     const uint32_t dim = bliss_b200_feature_count(ver);
     CK(g.feats.ensure((size_t)n_songs * dim * 4));
     // The path is PCIe-bound (15.9 MB per 3-min song): chunks of songs are copied on a side stream while
-    // the previous chunk computes (two device PCM buffers).  Chunk size trades pipeline fill (first
-    // copy is exposed) against the per-chunk latency of the sequential kernels (tuning, beat tracker
-    // ~2 ms whatever the chunk size); BLISS_B200_CHUNK_MB overrides the default for experiments.
-    size_t chunk_mb = 128;
+    // earlier chunks compute.  A chunk's kernels have ~3.5 ms of latency whatever its size (tuning, beat
+    // tracker), more than a small chunk's copy time, so the ring holds FOUR device PCM buffers: the
+    // copy engine can run three chunks ahead of the compute stream instead of idling (measured with
+    // BLISS_B200_TRACE: two buffers of 128 MB kept the link at 36 of 55 GB/s).
+    // BLISS_B200_CHUNK_MB overrides the chunk size for experiments.
+    size_t chunk_mb = 256;
     if (const char *e = getenv("BLISS_B200_CHUNK_MB")) chunk_mb = (size_t)std::max(8, atoi(e));
     const size_t chunk_budget = std::min<size_t>(chunk_mb << 20, std::max<size_t>(g.ws_limit / 8, (size_t)64 << 20));
     const bool trace = getenv("BLISS_B200_TRACE") != nullptr;
@@ -597,12 +599,13 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
         CK(cudaEventRecord(tr[2], g.stream));
     }
     size_t done_bytes = 0;
-    cudaEvent_t ev_copy[2], ev_done[2];
-    for (int i = 0; i < 2; i++) {
+    constexpr int NBUF = 4;
+    cudaEvent_t ev_copy[NBUF], ev_done[NBUF];
+    for (int i = 0; i < NBUF; i++) {
         CK(cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
     }
-    bool used[2] = {false, false};
+    bool used[NBUF] = {false, false, false, false};
     std::vector<uint64_t> offs, lens;
     uint32_t first = 0;
     int c = 0, rc = BLISS_B200_OK;
@@ -620,7 +623,7 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
             samples += len;
             count++;
         }
-        const int b = c & 1;
+        const int b = c % NBUF;
         if (used[b]) CK(cudaEventSynchronize(ev_done[b]));  // buffer b free again (also: host may realloc)
         CK(g.pcm[b].ensure(std::max<size_t>(samples, 4) * 4));
         for (uint32_t i = 0; i < count;) {
@@ -671,7 +674,7 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
         cudaStreamSynchronize(g.stream);
         cudaStreamSynchronize(g.copy_stream);
     }
-    for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_copy[i]); cudaEventDestroy(ev_done[i]); }
+    for (int i = 0; i < NBUF; i++) { cudaEventDestroy(ev_copy[i]); cudaEventDestroy(ev_done[i]); }
     return rc;
 }
 

@@ -63,53 +63,49 @@ __device__ __forceinline__ float pair_distance(const float *a, const float *b, i
     return __fsqrt_rn(s);
 }
 
-// All-pairs block: out[i][j] = dist(rows[i], cols[j]); CTA tile 32 x 128, thread = 1 row x 4 cols.
+// All-pairs block: out[i][j] = dist(rows[i], cols[j]).  CTA (128 threads) tile = 32 rows x 256 columns; thread t keeps
+// its two column vectors (t and t + 128) in registers and walks the 32 rows of the tile, whose
+// vectors are broadcast from shared memory; a warp's 32 results of one row are 32 consecutive floats.
 template <int DIM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 distance_matrix_kernel(const float *__restrict__ rows, unsigned int n_rows,
                        const float *__restrict__ cols, unsigned int n_cols, int mode,
                        const float *__restrict__ w_or_m, float *__restrict__ out) {
-    __shared__ float s_a[32][DIM];
-    __shared__ float s_b[128][DIM + 1];
+    constexpr int TR = 32, TC = 256, NT = 128;  // 2 columns per thread
+    __shared__ float s_a[TR][DIM];
     __shared__ float s_w[(DIM <= 32) ? DIM * DIM : 1];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const unsigned int r0 = blockIdx.y * 32u, c0 = blockIdx.x * 128u;
-    for (int e = threadIdx.x; e < 32 * DIM; e += 256) {
+    const unsigned int r0 = blockIdx.y * TR, c0 = blockIdx.x * TC;
+    for (int e = threadIdx.x; e < TR * DIM; e += NT) {
         const unsigned int r = r0 + e / DIM;
         s_a[e / DIM][e % DIM] = r < n_rows ? rows[(size_t)r * DIM + e % DIM] : 0.f;
-    }
-    for (int e = threadIdx.x; e < 128 * DIM; e += 256) {
-        const unsigned int c = c0 + e / DIM;
-        s_b[e / DIM][e % DIM] = c < n_cols ? cols[(size_t)c * DIM + e % DIM] : 0.f;
     }
     const float *wm = nullptr;
     if (w_or_m) {
         const int nw = (mode == 1) ? DIM * DIM : DIM;
         if (DIM <= 32) {
-            for (int e = threadIdx.x; e < nw; e += 256) s_w[e] = w_or_m[e];
+            for (int e = threadIdx.x; e < nw; e += NT) s_w[e] = w_or_m[e];
             wm = s_w;
         } else {
             wm = w_or_m;
         }
     }
+    // this thread's two columns, kept in registers for the whole tile
+    const unsigned int ca = c0 + threadIdx.x, cb = c0 + (unsigned)NT + threadIdx.x;
+    float va[DIM], vb[DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; i++) {
+        va[i] = ca < n_cols ? __ldg(cols + (size_t)ca * DIM + i) : 0.f;
+        vb[i] = cb < n_cols ? __ldg(cols + (size_t)cb * DIM + i) : 0.f;
+    }
     __syncthreads();
-#pragma unroll
-    for (int rr = 0; rr < 4; rr++) {
-        const int lr = ty + 8 * rr;
-        const unsigned int r = r0 + lr;
-        if (r >= n_rows) continue;
-        float res[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) res[q] = pair_distance<DIM>(s_a[lr], s_b[4 * tx + q], DIM, mode, wm);
-        const unsigned int c = c0 + 4u * tx;
-        float *o = out + (size_t)r * n_cols + c;
-        if (c + 3 < n_cols && ((n_cols & 3u) == 0)) {
-            *reinterpret_cast<float4 *>(o) = make_float4(res[0], res[1], res[2], res[3]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (c + q < n_cols) o[q] = res[q];
-        }
+    const unsigned int nr = min((unsigned)TR, n_rows - r0);
+#pragma unroll 1
+    for (unsigned int lr = 0; lr < nr; lr++) {
+        float *o = out + (size_t)(r0 + lr) * n_cols;
+        const float da = pair_distance<DIM>(s_a[lr], va, DIM, mode, wm);
+        const float db = pair_distance<DIM>(s_a[lr], vb, DIM, mode, wm);
+        if (ca < n_cols) o[ca] = da;
+        if (cb < n_cols) o[cb] = db;
     }
 }
 
@@ -196,9 +192,9 @@ nearest_alive_kernel(const float *__restrict__ cur, unsigned int n_cur, const fl
 int launch_distance_matrix(const float *rows, unsigned int n_rows, const float *cols, unsigned int n_cols,
                            int dim, int mode, const float *w_or_m, float *out, cudaStream_t st) {
     if (n_rows == 0 || n_cols == 0) return 0;
-    dim3 grid((n_cols + 127u) / 128u, (n_rows + 31u) / 32u);
-    if (dim == 23) distance_matrix_kernel<23><<<grid, 256, 0, st>>>(rows, n_rows, cols, n_cols, mode, w_or_m, out);
-    else if (dim == 20) distance_matrix_kernel<20><<<grid, 256, 0, st>>>(rows, n_rows, cols, n_cols, mode, w_or_m, out);
+    dim3 grid((n_cols + 255u) / 256u, (n_rows + 31u) / 32u);
+    if (dim == 23) distance_matrix_kernel<23><<<grid, 128, 0, st>>>(rows, n_rows, cols, n_cols, mode, w_or_m, out);
+    else if (dim == 20) distance_matrix_kernel<20><<<grid, 128, 0, st>>>(rows, n_rows, cols, n_cols, mode, w_or_m, out);
     else if (dim <= MAX_DIM) distance_matrix_generic_kernel<<<dim3((n_cols + 255u) / 256u, n_rows), 256, 0, st>>>(rows, n_rows, cols, n_cols, dim, mode, w_or_m, out);
     else return -1;
     return 1;
