@@ -588,8 +588,11 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
     // copy engine can run three chunks ahead of the compute stream instead of idling (measured with
     // BLISS_B200_TRACE: two buffers of 128 MB kept the link at 36 of 55 GB/s).
     // BLISS_B200_CHUNK_MB overrides the chunk size for experiments.
-    size_t chunk_mb = 256;
-    if (const char *e = getenv("BLISS_B200_CHUNK_MB")) chunk_mb = (size_t)std::max(8, atoi(e));
+    // Measured (BLISS_B200_TRACE, 4 GB batch): 128 MB chunks -> 37 GB/s (compute-latency bound: 32 chunks x
+    // 3.5 ms), 256 MB -> 45 GB/s, 512 MB -> 50 GB/s of a 55.6 GB/s link; default = an eighth of the batch.
+    size_t total_mb = 0;
+    for (uint32_t i = 0; i < n_songs; i++) total_mb += (size_t)n_samples[i] * 4 >> 20;
+    size_t chunk_mb = std::min<size_t>(1024, std::max<size_t>(256, total_mb / 8));
     const size_t chunk_budget = std::min<size_t>(chunk_mb << 20, std::max<size_t>(g.ws_limit / 8, (size_t)64 << 20));
     const bool trace = getenv("BLISS_B200_TRACE") != nullptr;
     cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};  // copy begin/end, compute begin/end
