@@ -174,6 +174,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--songs-per-gpu", type=int, default=SONGS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N>1 feature-row exchange: p2p = rows stored into every rank's buffer by the analysis "
+                         "itself + one-warp epoch barrier; nccl = all_gather_into_tensor; auto = p2p, else nccl")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,7 +212,26 @@ def main():
     weights = nat.feature_weights(2)
     stream = torch.cuda.current_stream().cuda_stream
 
-    def step():
+    # N>1: the feature rows of all ranks must meet before the distance row block.  Fused form: the
+    # analysis' last kernel stores each row into every rank's buffer over NVLink (global song order, so
+    # no permutation either) and a one-warp epoch barrier replaces the collective.
+    gather, gather_info = None, None
+    if world > 1 and args.gather in ("auto", "p2p"):
+        ok = torch.ones(1, device=dev)
+        try:
+            gather = M.PeerGather(n_total, dev)
+        except Exception as e:  # no peer access / IPC refused by the container
+            if args.gather == "p2p":
+                raise
+            ok.zero_()
+            print("[bench] peer gather unavailable on rank %d: %s" % (rank, e), file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            gather = None
+    if world > 1:
+        gather_info = {"kind": "p2p-fused" if gather else "nccl"}
+
+    def step_nccl(out):
         nat.analyze_batch_device(pcm.data_ptr(), offs, lens, 2, feats.data_ptr(), stream)
         if world > 1:
             dist.all_gather_into_tensor(all_feats, feats)        # the ONE collective of the path (NCCL)
@@ -218,7 +240,19 @@ def main():
             cols = feats
         rows = cols[row_lo:row_hi]
         nat.distance_matrix_device(rows.data_ptr(), row_hi - row_lo, cols.data_ptr(), n_total, dim,
-                                   dmat.data_ptr(), nat.METRIC_MAHALANOBIS, weights, stream)
+                                   out.data_ptr(), nat.METRIC_MAHALANOBIS, weights, stream)
+        return cols
+
+    def step_p2p(out):
+        gather.scatter(pcm.data_ptr(), offs, lens, 2, rank, world, feats.data_ptr(), stream)
+        cols = gather.commit(n_total, dim, stream)
+        rows = cols[row_lo:row_hi]
+        nat.distance_matrix_device(rows.data_ptr(), row_hi - row_lo, cols.data_ptr(), n_total, dim,
+                                   out.data_ptr(), nat.METRIC_MAHALANOBIS, weights, stream)
+        return cols
+
+    def step():
+        return step_p2p(dmat) if gather else step_nccl(dmat)
 
     def barrier():
         torch.cuda.synchronize()
@@ -255,6 +289,28 @@ def main():
         dist.all_reduce(lz, op=dist.ReduceOp.SUM)
     ms = float(t.item())
     value = world * S * args.steps / (ms / 1e3)
+    if gather:
+        # the fused exchange against the NCCL one: same rows, same distance block, bit for bit
+        gather.check()
+        cols_p2p = step_p2p(dmat).clone()
+        dmat2 = torch.empty_like(dmat)
+        cols_nccl = step_nccl(dmat2).clone()
+        torch.cuda.synchronize()
+        same = torch.tensor([float(torch.equal(cols_p2p, cols_nccl) and torch.equal(dmat, dmat2))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        gather_info["bitwise_equal_to_nccl_path"] = bool(same.item())
+        del dmat2
+        tn0, tn1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        tn0.record()
+        for _ in range(args.steps):
+            step_nccl(dmat)
+        tn1.record()
+        barrier()
+        tn = torch.tensor([tn0.elapsed_time(tn1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        gather_info["nccl_path_ms_per_step"] = float(tn.item()) / args.steps
+        gather_info["fused_path_ms_per_step"] = ms / args.steps
 
     # ---- per-kernel device times (CUDA events on the launching stream) -> roofline -------
     nat.set_profiling(True)
@@ -349,16 +405,19 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: %d synthetic 3-min 22050 Hz f32 mono tracks per GPU, full 23-feature "
-                                   "analysis + all-gather + all-pairs distance row block" % S,
+                                   "analysis + feature-row exchange + all-pairs distance row block" % S,
                        "songs_per_gpu": S, "track_samples": TRACK_SAMPLES, "parallelism": "songs sharded %d-way" % world,
                        "l2": "inputs (%.1f GB PCM per GPU) are far larger than the 126 MB L2; no flush needed"
                              % (S * TRACK_SAMPLES * 4 / 1e9)},
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "per_rank": per_rank,
+            "gather": gather_info,
             "gpu_launches": int(lz.item()),
         }
         _emit(line)
     if world > 1:
         dist.barrier()
+        if gather:
+            gather.destroy()
         dist.destroy_process_group()
 
 

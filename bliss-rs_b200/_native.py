@@ -41,7 +41,11 @@ SYMBOLS = [
     "bliss_b200_song_to_song", "bliss_b200_stft512_mag_device", "bliss_b200_analyze_taps",
     "bliss_b200_set_profiling", "bliss_b200_get_profile", "bliss_b200_kernel_name",
     "bliss_b200_launch_count",
+    "bliss_b200_gather_create", "bliss_b200_gather_connect", "bliss_b200_analyze_batch_device_scatter",
+    "bliss_b200_gather_commit", "bliss_b200_gather_check", "bliss_b200_gather_set_timeout",
+    "bliss_b200_gather_destroy",
 ]
+GATHER_HANDLE_BYTES = 128
 
 
 def load():
@@ -81,6 +85,14 @@ def load():
     L.bliss_b200_kernel_name.argtypes = [C.c_int]
     L.bliss_b200_kernel_name.restype = C.c_char_p
     L.bliss_b200_launch_count.restype = C.c_uint64
+    L.bliss_b200_gather_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, vp, C.POINTER(vp)]
+    L.bliss_b200_gather_connect.argtypes = [vp, vp]
+    L.bliss_b200_analyze_batch_device_scatter.argtypes = [vp, vp, u64p, u64p, C.c_uint32, C.c_uint16, C.c_uint64,
+                                                          C.c_uint64, vp, i32p, vp]
+    L.bliss_b200_gather_commit.argtypes = [vp, vp, C.POINTER(vp)]
+    L.bliss_b200_gather_check.argtypes = [vp]
+    L.bliss_b200_gather_set_timeout.argtypes = [vp, C.c_uint64]
+    L.bliss_b200_gather_destroy.argtypes = [vp]
     _lib = L
     return L
 
@@ -179,6 +191,56 @@ def analyze_batch_device(d_pcm_ptr, offsets, n_samples, version, d_out_ptr, stre
     status = (C.c_int32 * n)()
     check(L.bliss_b200_analyze_batch_device(d_pcm_ptr, off, ln, n, version, d_out_ptr, status, stream_ptr))
     return np.array(status[:], np.int32)
+
+
+class Gather:
+    """bliss_b200_gather: rows finished by this rank's analysis land in every rank's row buffer.
+
+    create -> exchange `handle` (GATHER_HANDLE_BYTES bytes per rank) -> connect(all handles in rank order)
+    -> per step: scatter(...) one or more times, commit() -> device pointer of the complete row buffer.
+    """
+
+    def __init__(self, world, rank, max_rows):
+        L = lib()
+        self.world, self.rank, self.max_rows = int(world), int(rank), int(max_rows)
+        buf = (C.c_ubyte * GATHER_HANDLE_BYTES)()
+        h = C.c_void_p()
+        check(L.bliss_b200_gather_create(self.world, self.rank, self.max_rows, buf, C.byref(h)))
+        self._h = h
+        self.handle = bytes(buf)
+
+    def connect(self, all_handles):
+        blob = b"".join(all_handles)
+        assert len(blob) == self.world * GATHER_HANDLE_BYTES
+        check(lib().bliss_b200_gather_connect(self._h, blob))
+
+    def scatter(self, d_pcm_ptr, offsets, n_samples, version, row_offset, row_stride, d_out_ptr=None,
+                stream_ptr=None):
+        n = len(n_samples)
+        off = (C.c_uint64 * n)(*[int(o) for o in offsets])
+        ln = (C.c_uint64 * n)(*[int(v) for v in n_samples])
+        status = (C.c_int32 * n)()
+        check(lib().bliss_b200_analyze_batch_device_scatter(self._h, d_pcm_ptr, off, ln, n, version,
+                                                            int(row_offset), int(row_stride), d_out_ptr, status,
+                                                            stream_ptr))
+        return np.array(status[:], np.int32)
+
+    def commit(self, stream_ptr=None):
+        """epoch barrier on the stream; returns the device address of this rank's complete row buffer"""
+        p = C.c_void_p()
+        check(lib().bliss_b200_gather_commit(self._h, stream_ptr, C.byref(p)))
+        return p.value
+
+    def check(self):
+        check(lib().bliss_b200_gather_check(self._h))
+
+    def set_timeout_ms(self, ms):
+        check(lib().bliss_b200_gather_set_timeout(self._h, int(ms)))
+
+    def destroy(self):
+        if self._h is not None:
+            lib().bliss_b200_gather_destroy(self._h)
+            self._h = None
 
 
 def stft512_mag_device(d_pcm_ptr, offsets, n_samples, d_mags_ptr, stream_ptr=None):

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -39,7 +40,8 @@ int launch_chroma(const float *, const SongDesc *, const unsigned int *, int, un
                   const int *, double *, double *, cudaStream_t);
 int launch_finalize(const SongDesc *, int, const float *, const float *, const float *, const float *,
                     const unsigned int *, const float *, const double *, int, float *, unsigned int,
-                    cudaStream_t);
+                    const PeerRows &, cudaStream_t);
+int launch_gather_barrier(unsigned int *const *, int, int, unsigned int, unsigned long long, cudaStream_t);
 int launch_distance_matrix(const float *, unsigned int, const float *, unsigned int, int, int, const float *,
                            float *, cudaStream_t);
 int launch_seed_distance(const float *, unsigned int, const float *, unsigned int, int, int, const float *,
@@ -296,7 +298,7 @@ PvocTables pvoc_tables() { return PvocTables{g.t_win512.as<float>(), g.t_twA.as<
 
 // one wave of the full analysis: every kernel of the path, enqueued on `st`
 int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, uint32_t out_base,
-             cudaStream_t st, bool debug) {
+             cudaStream_t st, bool debug, const PeerRows &peers) {
     const int n = (int)w.sd.size();
     if (n == 0) return BLISS_B200_OK;
     CK(g.mags.ensure(std::max<size_t>(w.rows, 2) * CH_STRIDE * sizeof(float)));
@@ -357,7 +359,7 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
     { ProfScope p(K_FINAL, st);
       p.done(launch_finalize(dv.sd, n, g.cent.as<float>(), g.roll.as<float>(), g.flat.as<float>(),
                              g.loud.as<float>(), g.zcr.as<unsigned int>(), g.tempo.as<float>(),
-                             g.tiles.as<double>(), version, d_out, out_base, st)); }
+                             g.tiles.as<double>(), version, d_out, out_base, peers, st)); }
     CK(cudaGetLastError());
     return BLISS_B200_OK;
 }
@@ -365,7 +367,9 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
 // split [0, n_songs) into waves that respect the workspace limit, run them in order
 int analyze_device_locked(const float *d_pcm, const uint64_t *offsets, const uint64_t *n_samples,
                           uint32_t n_songs, int version, float *d_out, int32_t *status, cudaStream_t st,
-                          bool debug) {
+                          bool debug, const PeerRows *peers = nullptr) {
+    PeerRows no_peers;
+    memset(&no_peers, 0, sizeof(no_peers));
     if (((uintptr_t)d_pcm & 15u) != 0) { g_last_error = "d_pcm must be 16-byte aligned"; return BLISS_B200_E_ARG; }
     uint32_t first = 0;
     WavePlan w;
@@ -379,7 +383,7 @@ int analyze_device_locked(const float *d_pcm, const uint64_t *offsets, const uin
             count++;
         }
         plan_wave(offsets, n_samples, first, count, false, w);
-        int rc = run_wave(d_pcm, w, version, d_out, first, st, debug);
+        int rc = run_wave(d_pcm, w, version, d_out, first, st, debug, peers ? *peers : no_peers);
         if (rc) return rc;
         first += count;
     }
@@ -486,6 +490,7 @@ const char *bliss_b200_strerror(int code) {
         case BLISS_B200_E_NOT_INIT: return "bliss_b200_init() not called";
         case BLISS_B200_E_NOMEM: return "workspace limit too small";
         case BLISS_B200_E_NO_DEVICE: return "no CUDA device (no CPU fallback exists)";
+        case BLISS_B200_E_TIMEOUT: return "a peer never reached the gather barrier";
         default: return "unknown";
     }
 }
@@ -575,6 +580,184 @@ int bliss_b200_analyze_batch_device(const float *d_pcm, const uint64_t *offsets,
     if (!d_pcm || !offsets || !n_samples || !d_out) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
     return analyze_device_locked(d_pcm, offsets, n_samples, n_songs, ver, d_out, status,
                                  (cudaStream_t)cuda_stream, false);
+}
+
+// ---- fused feature-row exchange across the GPUs of one box -------------------
+// One allocation per rank: two row buffers (double-buffered by epoch parity) followed by the flag
+// array; exported as a CUDA IPC handle.  Ranks living in the same process (tests) are connected by
+// raw pointer instead.
+struct GatherWire {  // BLISS_B200_GATHER_HANDLE_BYTES bytes on the wire
+    cudaIpcMemHandle_t ipc;
+    uint64_t pid, raw_ptr, max_rows;
+    int32_t device;
+    uint32_t world, rank, magic;
+    unsigned char pad[BLISS_B200_GATHER_HANDLE_BYTES - sizeof(cudaIpcMemHandle_t) - 3 * 8 - 4 * 4];
+};
+static_assert(sizeof(GatherWire) == BLISS_B200_GATHER_HANDLE_BYTES, "wire format");
+constexpr uint32_t GATHER_MAGIC = 0xB2006A74u;
+
+struct bliss_b200_gather {
+    uint32_t world = 0, rank = 0;
+    uint64_t max_rows = 0;
+    size_t buf_floats = 0;  // floats per parity buffer
+    char *local = nullptr;
+    char *peer[MAX_PEERS] = {nullptr};
+    bool opened[MAX_PEERS] = {false};
+    bool connected = false;
+    uint32_t epoch = 1;  // the open epoch; flags start at 0
+    uint32_t dim = 0;    // row width of the open epoch (0 = nothing scattered yet)
+    unsigned long long timeout_ns = 30ull * 1000000000ull;
+    float *rows(int r, uint32_t ep) const { return reinterpret_cast<float *>(peer[r]) + (size_t)(ep & 1u) * buf_floats; }
+    unsigned int *flags(int r) const { return reinterpret_cast<unsigned int *>(peer[r] + 2 * buf_floats * 4); }
+};
+
+int bliss_b200_gather_create(uint32_t world, uint32_t rank, uint64_t max_rows, void *handle_out,
+                             bliss_b200_gather **out) {
+    REQUIRE_INIT();
+    if (!handle_out || !out || world == 0 || world > (uint32_t)MAX_PEERS || rank >= world || max_rows == 0) {
+        g_last_error = "gather_create: need 1 <= world <= 8, rank < world, max_rows > 0";
+        return BLISS_B200_E_ARG;
+    }
+    auto *ga = new bliss_b200_gather();
+    ga->world = world;
+    ga->rank = rank;
+    ga->max_rows = max_rows;
+    ga->buf_floats = align_up((size_t)max_rows * 23, 64);
+    const size_t bytes = 2 * ga->buf_floats * 4 + 256;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { delete ga; g_last_error = std::string("cudaMalloc: ") + cudaGetErrorString(e); return BLISS_B200_E_CUDA; }
+    ga->local = (char *)p;
+    e = cudaMemset(p, 0, bytes);
+    GatherWire w;
+    memset(&w, 0, sizeof(w));
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&w.ipc, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        delete ga;
+        g_last_error = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e);
+        return BLISS_B200_E_CUDA;
+    }
+    w.pid = (uint64_t)getpid();
+    w.raw_ptr = (uint64_t)(uintptr_t)p;
+    w.max_rows = max_rows;
+    w.device = g.device;
+    w.world = world;
+    w.rank = rank;
+    w.magic = GATHER_MAGIC;
+    memcpy(handle_out, &w, sizeof(w));
+    *out = ga;
+    return BLISS_B200_OK;
+}
+
+int bliss_b200_gather_connect(bliss_b200_gather *ga, const void *all_handles) {
+    REQUIRE_INIT();
+    if (!ga || !all_handles) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
+    if (ga->connected) { g_last_error = "gather already connected"; return BLISS_B200_E_ARG; }
+    const GatherWire *w = reinterpret_cast<const GatherWire *>(all_handles);
+    for (uint32_t r = 0; r < ga->world; r++) {
+        GatherWire h;
+        memcpy(&h, &w[r], sizeof(h));
+        if (h.magic != GATHER_MAGIC || h.world != ga->world || h.rank != r || h.max_rows != ga->max_rows) {
+            g_last_error = "gather_connect: handle " + std::to_string(r) + " does not describe rank " +
+                           std::to_string(r) + " of this gather (world / max_rows mismatch?)";
+            return BLISS_B200_E_ARG;
+        }
+        if (r == ga->rank) {
+            ga->peer[r] = ga->local;
+        } else if (h.pid == (uint64_t)getpid()) {
+            // same process (several contexts of one test process): the pointer is directly usable
+            if (h.device != g.device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, g.device, h.device));
+                if (!can) { g_last_error = "gather_connect: no peer access to device " + std::to_string(h.device); return BLISS_B200_E_CUDA; }
+                cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+                (void)cudaGetLastError();
+            }
+            ga->peer[r] = (char *)(uintptr_t)h.raw_ptr;
+        } else {
+            void *p = nullptr;
+            CK(cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess));
+            ga->peer[r] = (char *)p;
+            ga->opened[r] = true;
+        }
+    }
+    ga->connected = true;
+    return BLISS_B200_OK;
+}
+
+int bliss_b200_analyze_batch_device_scatter(bliss_b200_gather *ga, const float *d_pcm, const uint64_t *offsets,
+                                            const uint64_t *n_samples, uint32_t n_songs, uint16_t ver,
+                                            uint64_t row_offset, uint64_t row_stride, float *d_out_local,
+                                            int32_t *status, void *cuda_stream) {
+    REQUIRE_INIT();
+    if (check_version(ver)) return BLISS_B200_E_ARG;
+    if (!ga || !ga->connected) { g_last_error = "gather not connected"; return BLISS_B200_E_ARG; }
+    const uint32_t dim = bliss_b200_feature_count(ver);
+    if (ga->dim != 0 && ga->dim != dim) { g_last_error = "one epoch cannot mix feature versions"; return BLISS_B200_E_ARG; }
+    if (n_songs == 0) return BLISS_B200_OK;
+    if (!d_pcm || !offsets || !n_samples) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
+    if (row_stride == 0 || row_offset + (uint64_t)(n_songs - 1) * row_stride >= ga->max_rows ||
+        row_stride > 0xffffffffull) {
+        g_last_error = "scatter rows fall outside the gather buffer";
+        return BLISS_B200_E_ARG;
+    }
+    PeerRows pr;
+    memset(&pr, 0, sizeof(pr));
+    pr.n_peers = (int)ga->world;
+    for (uint32_t r = 0; r < ga->world; r++) pr.base[r] = ga->rows((int)r, ga->epoch);
+    pr.row_offset = (unsigned int)row_offset;
+    pr.row_stride = (unsigned int)row_stride;
+    ga->dim = dim;
+    return analyze_device_locked(d_pcm, offsets, n_samples, n_songs, ver, d_out_local, status,
+                                 (cudaStream_t)cuda_stream, false, &pr);
+}
+
+int bliss_b200_gather_commit(bliss_b200_gather *ga, void *cuda_stream, const float **d_rows) {
+    REQUIRE_INIT();
+    if (!ga || !ga->connected) { g_last_error = "gather not connected"; return BLISS_B200_E_ARG; }
+    unsigned int *fl[MAX_PEERS] = {nullptr};
+    for (uint32_t r = 0; r < ga->world; r++) fl[r] = ga->flags((int)r);
+    g.launches += (unsigned long long)launch_gather_barrier(fl, (int)ga->world, (int)ga->rank, ga->epoch,
+                                                            ga->timeout_ns, (cudaStream_t)cuda_stream);
+    CK(cudaGetLastError());
+    if (d_rows) *d_rows = ga->rows((int)ga->rank, ga->epoch);
+    ga->epoch++;
+    ga->dim = 0;
+    return BLISS_B200_OK;
+}
+
+int bliss_b200_gather_check(bliss_b200_gather *ga) {
+    REQUIRE_INIT();
+    if (!ga || !ga->local) { g_last_error = "null gather"; return BLISS_B200_E_ARG; }
+    unsigned int st = 0;
+    CK(cudaMemcpy(&st, ga->flags((int)ga->rank) + MAX_PEERS, 4, cudaMemcpyDeviceToHost));  // synchronises
+    if (st != 0) {
+        g_last_error = "gather barrier timed out waiting for rank " + std::to_string(st - 1);
+        return BLISS_B200_E_TIMEOUT;
+    }
+    return BLISS_B200_OK;
+}
+
+int bliss_b200_gather_set_timeout(bliss_b200_gather *ga, uint64_t milliseconds) {
+    if (!ga || milliseconds == 0) return BLISS_B200_E_ARG;
+    ga->timeout_ns = (unsigned long long)milliseconds * 1000000ull;
+    return BLISS_B200_OK;
+}
+
+int bliss_b200_gather_destroy(bliss_b200_gather *ga) {
+    if (!ga) return BLISS_B200_OK;
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (g.inited) {
+        cudaSetDevice(g.device);
+        cudaDeviceSynchronize();
+        for (uint32_t r = 0; r < ga->world; r++)
+            if (ga->opened[r]) cudaIpcCloseMemHandle(ga->peer[r]);
+        if (ga->local) cudaFree(ga->local);
+    }
+    delete ga;
+    return BLISS_B200_OK;
 }
 
 // host buffers: chunks of songs are copied on a side stream while the previous chunk computes

@@ -71,7 +71,15 @@ __device__ __forceinline__ int find_song(const unsigned int *__restrict__ prefix
     return lo;
 }
 
-// ---- kernel launchers (each returns the number of kernels launched) --------
-struct WaveBuffers;
+// ---- fused feature-row exchange (gather.cu, finalize.cu) -------------------------------------
+// Multi-GPU runs shard songs over ranks and every rank needs ALL feature rows before the all-pairs
+// distance.  Instead of a collective after the analysis, finalize_kernel stores
+// each finished row straight into every rank's gather buffer through peer-mapped pointers.
+constexpr int MAX_PEERS = 8;  // one NVSwitch box
+struct PeerRows {
+    float *base[MAX_PEERS];               // rank r's gather buffer of the open epoch (own rank included)
+    int n_peers;                          // 0: no exchange
+    unsigned int row_offset, row_stride;  // global row of local song i = row_offset + i * row_stride
+};
 
 }  // namespace bliss

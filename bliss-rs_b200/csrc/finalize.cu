@@ -44,19 +44,37 @@ __device__ __forceinline__ float normalize(float value, float min_v, float max_v
     return 2.f * (value - min_v) / (max_v - min_v) - 1.f;
 }
 
+// The row leaves the CTA once: to the caller's local output (if any) and, when a gather is open, to
+// the same global row of every rank's gather buffer (plain P2P stores over NVLink; the epoch barrier
+// of gather.cu publishes them).
+__device__ __forceinline__ void store_row(const float *o, int dim, float *__restrict__ out,
+                                          unsigned int out_base, const PeerRows &peers) {
+    const unsigned int local_row = out_base + blockIdx.x;
+    if (out != nullptr && threadIdx.x < dim) out[(size_t)local_row * dim + threadIdx.x] = o[threadIdx.x];
+    if (peers.n_peers > 0) {
+        const size_t g_row = (size_t)peers.row_offset + (size_t)local_row * peers.row_stride;
+        for (int t = threadIdx.x; t < dim * peers.n_peers; t += K9_THREADS) {
+            const int r = t / dim, c = t - r * dim;
+            peers.base[r][g_row * dim + c] = o[c];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(K9_THREADS)
 finalize_kernel(const SongDesc *__restrict__ songs, const float *__restrict__ centroid,
                 const float *__restrict__ rolloff, const float *__restrict__ flatness,
                 const float *__restrict__ loud_ms, const unsigned int *__restrict__ zcr_count,
                 const float *__restrict__ tempo_feature, const double *__restrict__ tile_partials,
-                int version, float *__restrict__ out, unsigned int out_base) {
+                int version, float *__restrict__ out, unsigned int out_base, const PeerRows peers) {
     __shared__ double s_tmp[K9_THREADS / 32];
     __shared__ double s_feat[10];
+    __shared__ float o[24];  // the finished row; stored to `out` and to every peer at the end
     const SongDesc sd = songs[blockIdx.x];
     const int dim = version == 1 ? 20 : 23;
-    float *o = out + ((size_t)out_base + blockIdx.x) * dim;
     if (!sd.valid) {
         if (threadIdx.x < dim) o[threadIdx.x] = 0.f;
+        __syncthreads();
+        store_row(o, dim, out, out_base, peers);
         return;
     }
     float m, s;
@@ -108,15 +126,17 @@ finalize_kernel(const SongDesc *__restrict__ songs, const float *__restrict__ ce
             c[12] = 2.f * ((float)angle - 0.f) / (1.57079637050628662f - 0.f) - 1.f;
         }
     }
+    __syncthreads();
+    store_row(o, dim, out, out_base, peers);
 }
 
 int launch_finalize(const SongDesc *songs, int n_songs, const float *centroid, const float *rolloff,
                     const float *flatness, const float *loud_ms, const unsigned int *zcr_count,
                     const float *tempo_feature, const double *tile_partials, int version, float *out,
-                    unsigned int out_base, cudaStream_t st) {
+                    unsigned int out_base, const PeerRows &peers, cudaStream_t st) {
     if (n_songs == 0) return 0;
     finalize_kernel<<<n_songs, K9_THREADS, 0, st>>>(songs, centroid, rolloff, flatness, loud_ms, zcr_count,
-                                                    tempo_feature, tile_partials, version, out, out_base);
+                                                    tempo_feature, tile_partials, version, out, out_base, peers);
     return 1;
 }
 

@@ -7,6 +7,10 @@ the all-gather of the [n_local x dim] f32 feature rows before the all-pairs dist
 rank r owns the row block `row_block(n, world, r)` of the n x n matrix.
 
 Works on any torch.distributed backend: NCCL on the GPU box, gloo in the CPU tests.
+
+`PeerGather` is the fused form of that exchange on one NVSwitch box: the last kernel of the analysis
+stores each finished row into every rank's row buffer (peer-mapped memory), so the only thing left of
+the collective is a one-warp epoch barrier (include/bliss_b200.h, "fused feature-row exchange").
 """
 from typing import List, Sequence, Tuple
 
@@ -65,3 +69,47 @@ def round_robin_to_global(gathered: torch.Tensor, world: int) -> torch.Tensor:
     (row i*world + r = row i of rank r).  Pure view/permutation, no index tensors."""
     s = gathered.shape[0] // world
     return gathered.view(world, s, -1).transpose(0, 1).reshape(world * s, -1)
+
+
+class _DevArray:
+    """zero-copy torch view of a raw device pointer (via __cuda_array_interface__)"""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerGather:
+    """Fused all-gather of feature rows over peer memory (one process per GPU, one box).
+
+    Construction is collective: every rank creates its buffer, the 128-byte handles travel through
+    `dist.all_gather_object`, every rank maps every peer.  Per step: `scatter(...)` (the analysis;
+    global row of local song i = row_offset + i * row_stride), then `commit()` -> [n_rows, dim] view of
+    this rank's complete row buffer, valid until the commit after next."""
+
+    def __init__(self, max_rows: int, device, group=None):
+        from . import _native as nat
+        self._nat = nat
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = device
+        self.max_rows = int(max_rows)
+        self.g = nat.Gather(self.world, self.rank, self.max_rows)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.g.handle, group=group)
+        self.g.connect(handles)
+
+    def scatter(self, d_pcm_ptr, offsets, n_samples, version, row_offset, row_stride, d_out_ptr=None,
+                stream_ptr=None):
+        return self.g.scatter(d_pcm_ptr, offsets, n_samples, version, row_offset, row_stride, d_out_ptr,
+                              stream_ptr)
+
+    def commit(self, n_rows: int, dim: int, stream_ptr=None) -> torch.Tensor:
+        ptr = self.g.commit(stream_ptr)
+        return torch.as_tensor(_DevArray(ptr, (int(n_rows), int(dim))), device=self.device)
+
+    def check(self):
+        self.g.check()
+
+    def destroy(self):
+        self.g.destroy()

@@ -33,6 +33,7 @@ extern "C" {
 #define BLISS_B200_E_NOT_INIT (-3) /* bliss_b200_init() has not been called */
 #define BLISS_B200_E_NOMEM (-4)    /* one song alone does not fit the workspace limit */
 #define BLISS_B200_E_NO_DEVICE (-5) /* no usable CUDA device: there is NO CPU fallback */
+#define BLISS_B200_E_TIMEOUT (-6)  /* a peer never reached the gather barrier */
 
 /* ---- per-song status (BlissResult<Analysis>) ------------------------------------ */
 #define BLISS_B200_SONG_OK 0
@@ -79,6 +80,40 @@ int bliss_b200_analyze_batch_device(const float *d_pcm, const uint64_t *offsets,
                                     const uint64_t *n_samples, uint32_t n_songs,
                                     uint16_t features_version, float *d_out, int32_t *status,
                                     void *cuda_stream);
+
+/* ---- multi-GPU: fused feature-row exchange ----------------------------------------- *
+ * The reference analyses a library on `cores` threads and then ranks ALL songs against a seed
+ * (src/song/decoder.rs:291-355 -> src/playlist.rs:256-326).  With songs sharded over the GPUs
+ * of one box (one process per GPU) every rank needs all feature rows before its block of the
+ * distance matrix.  Instead of a collective after the analysis, the last kernel of the analysis
+ * stores each finished row straight into EVERY rank's gather buffer (peer-mapped over
+ * NVLink/NVSwitch); what remains of the all-gather is one single-warp epoch barrier.
+ *
+ *   create (each rank)  -> exchange the BLISS_B200_GATHER_HANDLE_BYTES handles by any means
+ *   connect (each rank, all handles in rank order)
+ *   per step: scatter (1..n calls; global row of local song i = row_offset + i * row_stride)
+ *             commit  (barrier on `cuda_stream`; *d_rows = this rank's complete row buffer)
+ *
+ * The row buffer is double-buffered by epoch: work that reads *d_rows must be enqueued on the
+ * same stream before the NEXT commit.  All ranks must issue the same sequence of commits.
+ * Rows no rank wrote keep their previous contents. */
+typedef struct bliss_b200_gather bliss_b200_gather;
+#define BLISS_B200_GATHER_HANDLE_BYTES 128
+int bliss_b200_gather_create(uint32_t world, uint32_t rank, uint64_t max_rows, void *handle_out,
+                             bliss_b200_gather **out);
+int bliss_b200_gather_connect(bliss_b200_gather *g, const void *all_handles);
+/* bliss_b200_analyze_batch_device whose rows also land in every rank's gather buffer;
+ * d_out_local (n_songs x feature_count, device) may be NULL. */
+int bliss_b200_analyze_batch_device_scatter(bliss_b200_gather *g, const float *d_pcm,
+                                            const uint64_t *offsets, const uint64_t *n_samples,
+                                            uint32_t n_songs, uint16_t features_version,
+                                            uint64_t row_offset, uint64_t row_stride,
+                                            float *d_out_local, int32_t *status, void *cuda_stream);
+int bliss_b200_gather_commit(bliss_b200_gather *g, void *cuda_stream, const float **d_rows);
+/* Synchronises the device; E_TIMEOUT if a barrier gave up on a peer (default 30 s). */
+int bliss_b200_gather_check(bliss_b200_gather *g);
+int bliss_b200_gather_set_timeout(bliss_b200_gather *g, uint64_t milliseconds);
+int bliss_b200_gather_destroy(bliss_b200_gather *g);
 
 /* ---- distances, src/playlist.rs ---------------------------------------------------- */
 #define BLISS_B200_METRIC_MAHALANOBIS 0 /* sqrt((a-b)^T M (a-b)), playlist.rs:140-142; M NULL = identity = euclidean_distance :65-71 */
