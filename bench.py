@@ -263,6 +263,7 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    feats_warm = feats.clone()   # every later step must reproduce these bits (no timing-dependent result)
     sampler = ClockSampler(range(world)) if rank == 0 else None  # one node: local GPUs 0..world-1
     if sampler:
         sampler.start()
@@ -275,6 +276,7 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = nat.launch_count() - launches0
+    deterministic = torch.tensor([float(torch.equal(feats, feats_warm))], device=dev)
     clocks = sampler.stop() if sampler else {}
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     lz = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
@@ -287,6 +289,7 @@ def main():
         per_rank = {"ms": [round(v, 2) for v in allr[:, 0].tolist()]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(lz, op=dist.ReduceOp.SUM)
+        dist.all_reduce(deterministic, op=dist.ReduceOp.MIN)
     ms = float(t.item())
     value = world * S * args.steps / (ms / 1e3)
     if gather:
@@ -411,7 +414,7 @@ def main():
                              % (S * TRACK_SAMPLES * 4 / 1e9)},
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "per_rank": per_rank,
             "gather": gather_info,
-            "gpu_launches": int(lz.item()),
+            "gpu_launches": int(lz.item()), "bitwise_reproducible_across_steps": bool(deterministic.item()),
         }
         _emit(line)
     if world > 1:

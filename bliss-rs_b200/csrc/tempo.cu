@@ -205,6 +205,11 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
         __syncthreads();
         const unsigned int timesig0 = sh.timesig;
         const int numelem = timesig0 == 0 ? 4 : (int)timesig0;
+        // gp of the previous cycle.  Read HERE, behind the barrier above: thread 0 rewrites sh.gp in
+        // checkstate below, and when gp <= 0 there is no barrier between that write and a read placed
+        // there -- a late warp would see the new gp, take the other side of a branch that contains
+        // barriers and desynchronise the CTA (seen as run-to-run tempo flips on 2-3 % of 1024 songs).
+        const float gp_in = sh.gp;
         // dfrev = reverse(df * dfwv)
         sh.dfrev[winlen - 1 - tid] = sh.df[tid] * sh.dfwv[tid];
         // vec_autocorr, aubio.rs:819-828
@@ -247,7 +252,6 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
         }
         __syncthreads();
         // ---- checkstate, aubio.rs:1096-1227 ----
-        const float gp_in = sh.gp;
         if (gp_in > 0.f) {  // context-dependent comb (no 1/(2a-1)), Gaussian weighting
             float acc = 0.f;
             if (tid < laglen) {
