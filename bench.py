@@ -262,11 +262,14 @@ def main():
 
     for _ in range(args.warmup):
         step()
-    barrier()
     feats_warm = feats.clone()   # every later step must reproduce these bits (no timing-dependent result)
+    # The sampler is started BEFORE the barrier: forking nvidia-smi from a process this size takes ~75 ms,
+    # which used to delay rank 0's first launch -- every other rank then sat in its first exchange waiting
+    # for rank 0 inside the timed region (seen as 471 vs 396 ms per 5 steps on ranks 1-7 at N=8).
     sampler = ClockSampler(range(world)) if rank == 0 else None  # one node: local GPUs 0..world-1
     if sampler:
         sampler.start()
+    barrier()
     launches0 = nat.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

@@ -1,0 +1,5 @@
+# N-GPU bench only (torchrun, the driver's launch line); fused gather with the NCCL comparator inside
+mkdir -p gpurun_out; cd $GRAFT_REPO_ROOT
+N=${1:-8}
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo BENCH_EXIT $?
+cat gpurun_out/bench_${N}gpu.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k: d[k] for k in ('value','ms_per_step','gather','per_rank','gpu_launches','clocks')}); print(d['e2e'])"; tail -5 gpurun_out/bench_${N}gpu.err
