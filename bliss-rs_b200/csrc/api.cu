@@ -41,6 +41,7 @@ int launch_chroma(const float *, const SongDesc *, const unsigned int *, int, un
 int launch_finalize(const SongDesc *, int, const float *, const float *, const float *, const float *,
                     const unsigned int *, const float *, const double *, int, float *, unsigned int,
                     const PeerRows &, cudaStream_t);
+int launch_wave_setup(const void *, void *, size_t, unsigned int *, unsigned int *, unsigned int, cudaStream_t);
 int launch_gather_barrier(unsigned int *const *, int, int, unsigned int, unsigned long long, cudaStream_t);
 int launch_distance_matrix(const float *, unsigned int, const float *, unsigned int, int, int, const float *,
                            float *, cudaStream_t);
@@ -102,29 +103,54 @@ const char *const kKernelNames[BLISS_B200_N_KERNELS] = {
     "pvoc512_kernel", "timedomain_kernel", "stft8192_kernel", "tuning_kernel", "chroma_kernel",
     "peakpick_kernel", "beattrack_kernel", "finalize_kernel", "distance_kernels", "pvoc512_kernel<mags>"};
 
-constexpr int N_STAGE = 4;
+constexpr int N_STAGE = 2;  // descriptor staging slots per wave set
+constexpr int N_SETS = 3;   // waves in flight
+
+// Everything one wave owns: scratch arrays, its two streams (tempo/timbral chain and chroma chain), the
+// descriptor staging ring.  N_SETS of them exist so that the latency-bound kernels of one wave
+// (tuning, beat tracker: one CTA per song, ~3 ms whatever the wave size) run under the FFT kernels of
+// the next waves instead of leaving the SMs idle.
+struct WaveSet {
+    cudaStream_t main = nullptr, side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_done = nullptr;
+    bool used_in_call = false;
+    DevBuf blob;  // SongDesc + prefix arrays (N_STAGE regions)
+    DevBuf mags, cand_mag, cand_pitch, cand_count, cent, roll, flat, flux, thr, loud, eb, zcr, tempo, bpm,
+        bpm_count, tuning, tiles, chroma_dbg;
+    // pinned staging ring for descriptor uploads
+    void *stage[N_STAGE] = {nullptr, nullptr};
+    size_t stage_cap[N_STAGE] = {0, 0};
+    cudaEvent_t stage_ev[N_STAGE] = {nullptr, nullptr};
+    bool stage_used[N_STAGE] = {false, false};
+    int stage_next = 0;
+    void release() {
+        DevBuf *all[] = {&blob, &mags, &cand_mag, &cand_pitch, &cand_count, &cent, &roll, &flat, &flux, &thr, &loud,
+                         &eb, &zcr, &tempo, &bpm, &bpm_count, &tuning, &tiles, &chroma_dbg};
+        for (DevBuf *b : all) b->release();
+        for (int i = 0; i < N_STAGE; i++) {
+            if (stage[i]) cudaFreeHost(stage[i]);
+            stage[i] = nullptr;
+            stage_cap[i] = 0;
+            if (stage_ev[i]) cudaEventDestroy(stage_ev[i]);
+            stage_ev[i] = nullptr;
+            stage_used[i] = false;
+        }
+    }
+};
 
 struct Ctx {
     std::mutex mu;
     bool inited = false;
     int device = -1;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, side_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_begin = nullptr;
     size_t ws_limit = 0;
     // constant tables
     DevBuf t_win512, t_twA, t_hann8k, t_tw4k, t_tw2, t_tw8k, t_filt, t_filt32;
-    // wave scratch
-    DevBuf blob;  // SongDesc + prefix arrays
-    DevBuf mags, cand_mag, cand_pitch, cand_count, cent, roll, flat, flux, thr, loud, eb, zcr, tempo, bpm,
-        bpm_count, tuning, tiles, chroma_dbg;
+    WaveSet ws[N_SETS];
+    int next_set = 0;
     // host-API staging
     DevBuf pcm[4], feats, metric, misc[6];
-    // pinned staging ring for descriptor uploads
-    void *stage[N_STAGE] = {nullptr, nullptr, nullptr, nullptr};
-    size_t stage_cap[N_STAGE] = {0, 0, 0, 0};
-    cudaEvent_t stage_ev[N_STAGE] = {nullptr, nullptr, nullptr, nullptr};
-    bool stage_used[N_STAGE] = {false, false, false, false};
-    int stage_next = 0;
     // profiling
     bool profiling = false;
     struct EvPair { cudaEvent_t a, b; int kid; };
@@ -257,33 +283,37 @@ struct WaveDev {
     const unsigned int *k1_prefix, *chunk_prefix, *t_prefix, *pair_prefix, *tile_prefix;
 };
 
-int upload_plan(const WavePlan &w, cudaStream_t st, WaveDev &out) {
+int upload_plan(const WavePlan &w, WaveSet &S, cudaStream_t st, WaveDev &out, unsigned int *zcr_count,
+                unsigned int *cand_count) {
     const size_t n = w.sd.size();
     const size_t sd_bytes = align_up(n * sizeof(SongDesc), 256);
     const size_t pf_bytes = align_up((n + 1) * sizeof(uint32_t), 256);
     const size_t total = sd_bytes + 5 * pf_bytes;
-    CK(g.blob.ensure(total * N_STAGE));
-    const int slot = g.stage_next;
-    g.stage_next = (g.stage_next + 1) % N_STAGE;
-    if (g.stage_used[slot]) CK(cudaEventSynchronize(g.stage_ev[slot]));
-    if (g.stage_cap[slot] < total) {
-        if (g.stage[slot]) cudaFreeHost(g.stage[slot]);
-        g.stage[slot] = nullptr;
-        CK(cudaMallocHost(&g.stage[slot], total + total / 4));
-        g.stage_cap[slot] = total + total / 4;
+    CK(S.blob.ensure(total * N_STAGE));
+    const int slot = S.stage_next;
+    S.stage_next = (S.stage_next + 1) % N_STAGE;
+    if (S.stage_used[slot]) CK(cudaEventSynchronize(S.stage_ev[slot]));
+    if (S.stage_cap[slot] < total) {
+        if (S.stage[slot]) cudaFreeHost(S.stage[slot]);
+        S.stage[slot] = nullptr;
+        CK(cudaMallocHost(&S.stage[slot], total + total / 4));
+        S.stage_cap[slot] = total + total / 4;
     }
-    if (!g.stage_ev[slot]) CK(cudaEventCreateWithFlags(&g.stage_ev[slot], cudaEventDisableTiming));
-    char *h = (char *)g.stage[slot];
+    if (!S.stage_ev[slot]) CK(cudaEventCreateWithFlags(&S.stage_ev[slot], cudaEventDisableTiming));
+    char *h = (char *)S.stage[slot];
     memcpy(h, w.sd.data(), n * sizeof(SongDesc));
     const std::vector<uint32_t> *pf[5] = {&w.k1_prefix, &w.chunk_prefix, &w.t_prefix, &w.pair_prefix, &w.tile_prefix};
     for (int i = 0; i < 5; i++) memcpy(h + sd_bytes + i * pf_bytes, pf[i]->data(), (n + 1) * sizeof(uint32_t));
     // each ring slot owns its own region of the device blob, so a wave still executing
     // never sees the next wave's descriptors
-    char *d = g.blob.as<char>() + (size_t)slot * (g.blob.cap / N_STAGE / 256 * 256);
-    if ((size_t)(g.blob.cap / N_STAGE / 256 * 256) < total) { g_last_error = "descriptor blob too small"; return BLISS_B200_E_CUDA; }
-    CK(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(g.stage_ev[slot], st));
-    g.stage_used[slot] = true;
+    char *d = S.blob.as<char>() + (size_t)slot * (S.blob.cap / N_STAGE / 256 * 256);
+    if ((size_t)(S.blob.cap / N_STAGE / 256 * 256) < total) { g_last_error = "descriptor blob too small"; return BLISS_B200_E_CUDA; }
+    // fetched by a kernel (wave_setup.cu), not by the copy engine, which may be busy with PCM for a long time
+    g.launches += (unsigned long long)launch_wave_setup(h, d, total, zcr_count, cand_count,
+                                                        zcr_count ? (unsigned int)n : 0u, st);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(S.stage_ev[slot], st));
+    S.stage_used[slot] = true;
     out.sd = reinterpret_cast<const SongDesc *>(d);
     const unsigned int *p0 = reinterpret_cast<const unsigned int *>(d + sd_bytes);
     out.k1_prefix = p0;
@@ -296,96 +326,149 @@ int upload_plan(const WavePlan &w, cudaStream_t st, WaveDev &out) {
 
 PvocTables pvoc_tables() { return PvocTables{g.t_win512.as<float>(), g.t_twA.as<cpx>()}; }
 
-// one wave of the full analysis: every kernel of the path, enqueued on `st`
-int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, uint32_t out_base,
-             cudaStream_t st, bool debug, const PeerRows &peers) {
+// one wave of the full analysis: every kernel of the path, enqueued on `st` (tempo/timbral chain) and
+// `sb` (chroma chain; may equal st), using the scratch of wave set S
+int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, uint32_t out_base, WaveSet &S,
+             cudaStream_t st, cudaStream_t sb, bool debug, const PeerRows &peers) {
     const int n = (int)w.sd.size();
     if (n == 0) return BLISS_B200_OK;
-    CK(g.mags.ensure(std::max<size_t>(w.rows, 2) * CH_STRIDE * sizeof(float)));
-    CK(g.cand_mag.ensure(std::max<size_t>(w.cands, 1) * sizeof(double)));
-    CK(g.cand_pitch.ensure(std::max<size_t>(w.cands, 1) * sizeof(double)));  // interpolated pitches (f64)
-    CK(g.cand_count.ensure((size_t)n * 4));
-    CK(g.cent.ensure(std::max<size_t>(w.n_s, 1) * 4));
-    CK(g.roll.ensure(std::max<size_t>(w.n_s, 1) * 4));
-    CK(g.flat.ensure(std::max<size_t>(w.n_s, 1) * 4));
-    CK(g.flux.ensure(std::max<size_t>(w.n_t, 1) * 4));
-    CK(g.thr.ensure(std::max<size_t>(w.n_t, 1) * 4));
-    CK(g.loud.ensure(std::max<size_t>(w.n_l, 1) * 4));
-    CK(g.eb.ensure(std::max<size_t>(w.n_eb, 1) * 4));
-    CK(g.zcr.ensure((size_t)n * 4));
-    CK(g.tempo.ensure((size_t)n * 4));
-    CK(g.bpm.ensure(std::max<size_t>(w.bpms, 1) * 4));
-    CK(g.bpm_count.ensure((size_t)n * 4));
-    CK(g.tuning.ensure((size_t)n * 4));
-    CK(g.tiles.ensure(std::max<size_t>(w.tiles, 1) * 10 * sizeof(double)));
-    if (debug) CK(g.chroma_dbg.ensure(std::max<size_t>(w.tiles, 1) * CH_TILE_FRAMES * 12 * sizeof(double)));
+    CK(S.mags.ensure(std::max<size_t>(w.rows, 2) * CH_STRIDE * sizeof(float)));
+    CK(S.cand_mag.ensure(std::max<size_t>(w.cands, 1) * sizeof(double)));
+    CK(S.cand_pitch.ensure(std::max<size_t>(w.cands, 1) * sizeof(double)));  // interpolated pitches (f64)
+    CK(S.cand_count.ensure((size_t)n * 4));
+    CK(S.cent.ensure(std::max<size_t>(w.n_s, 1) * 4));
+    CK(S.roll.ensure(std::max<size_t>(w.n_s, 1) * 4));
+    CK(S.flat.ensure(std::max<size_t>(w.n_s, 1) * 4));
+    CK(S.flux.ensure(std::max<size_t>(w.n_t, 1) * 4));
+    CK(S.thr.ensure(std::max<size_t>(w.n_t, 1) * 4));
+    CK(S.loud.ensure(std::max<size_t>(w.n_l, 1) * 4));
+    CK(S.eb.ensure(std::max<size_t>(w.n_eb, 1) * 4));
+    CK(S.zcr.ensure((size_t)n * 4));
+    CK(S.tempo.ensure((size_t)n * 4));
+    CK(S.bpm.ensure(std::max<size_t>(w.bpms, 1) * 4));
+    CK(S.bpm_count.ensure((size_t)n * 4));
+    CK(S.tuning.ensure((size_t)n * 4));
+    CK(S.tiles.ensure(std::max<size_t>(w.tiles, 1) * 10 * sizeof(double)));
+    if (debug) CK(S.chroma_dbg.ensure(std::max<size_t>(w.tiles, 1) * CH_TILE_FRAMES * 12 * sizeof(double)));
     WaveDev dv;
-    int rc = upload_plan(w, st, dv);
+    int rc = upload_plan(w, S, st, dv, S.zcr.as<unsigned int>(), S.cand_count.as<unsigned int>());  // also zeroes both
     if (rc) return rc;
-    CK(cudaMemsetAsync(g.zcr.p, 0, (size_t)n * 4, st));
-    CK(cudaMemsetAsync(g.cand_count.p, 0, (size_t)n * 4, st));
 
     // Two independent chains per wave: the tempo/timbral chain stays on the caller's stream, the chroma
     // chain runs on a side stream so that its latency-bound kernels (tuning) overlap the other chain's
     // compute-bound ones and vice versa (beat tracker under the chroma STFT).  Joined before finalize.
-    // (while per-kernel profiling is on, both chains are serialised on `st` so that each kernel's
-    // CUDA-event duration is its own and not inflated by the kernel it would overlap with)
-    cudaStream_t sb = g.profiling ? st : g.side_stream;
-    CK(cudaEventRecord(g.ev_fork, st));
-    CK(cudaStreamWaitEvent(sb, g.ev_fork, 0));
+    // (while per-kernel profiling is on, the caller passes sb == st: both chains serialised so that each
+    // kernel's CUDA-event duration is its own and not inflated by the kernel it would overlap with)
+    CK(cudaEventRecord(S.ev_fork, st));
+    CK(cudaStreamWaitEvent(sb, S.ev_fork, 0));
     { ProfScope p(K_STFT8K, sb);
       p.done(launch_stft8192(d_pcm, dv.sd, dv.pair_prefix, n, w.pair_prefix[n], g.t_hann8k.as<float>(),
-                             g.t_tw4k.as<cpx>(), g.t_tw2.as<cpx>(), g.t_tw8k.as<cpx>(), g.mags.as<float>(), g.cand_mag.as<double>(),
-                             g.cand_pitch.as<double>(), g.cand_count.as<unsigned int>(), sb)); }
+                             g.t_tw4k.as<cpx>(), g.t_tw2.as<cpx>(), g.t_tw8k.as<cpx>(), S.mags.as<float>(), S.cand_mag.as<double>(),
+                             S.cand_pitch.as<double>(), S.cand_count.as<unsigned int>(), sb)); }
     { ProfScope p(K_TIME, st);
-      p.done(launch_timedomain(d_pcm, dv.sd, dv.chunk_prefix, n, w.chunk_prefix[n], g.loud.as<float>(),
-                               g.eb.as<float>(), g.zcr.as<unsigned int>(), st)); }
+      p.done(launch_timedomain(d_pcm, dv.sd, dv.chunk_prefix, n, w.chunk_prefix[n], S.loud.as<float>(),
+                               S.eb.as<float>(), S.zcr.as<unsigned int>(), st)); }
     { ProfScope p(K_PVOC, st);
       p.done(launch_pvoc512(d_pcm, dv.sd, dv.k1_prefix, n, w.k1_prefix[n], (int)w.pairs_per_item, pvoc_tables(),
-                            g.cent.as<float>(), g.roll.as<float>(), g.flat.as<float>(), g.flux.as<float>(), st)); }
+                            S.cent.as<float>(), S.roll.as<float>(), S.flat.as<float>(), S.flux.as<float>(), st)); }
     { ProfScope p(K_TUNING, sb);
-      p.done(launch_tuning(g.cand_mag.as<double>(), g.cand_pitch.as<double>(),
-                           g.cand_count.as<unsigned int>(), dv.sd, n, g.tuning.as<int>(), sb)); }
+      p.done(launch_tuning(S.cand_mag.as<double>(), S.cand_pitch.as<double>(),
+                           S.cand_count.as<unsigned int>(), dv.sd, n, S.tuning.as<int>(), sb)); }
     { ProfScope p(K_PEAK, st);
-      p.done(launch_peakpick(g.flux.as<float>(), dv.sd, dv.t_prefix, n, w.t_prefix[n], g.thr.as<float>(), st)); }
+      p.done(launch_peakpick(S.flux.as<float>(), dv.sd, dv.t_prefix, n, w.t_prefix[n], S.thr.as<float>(), st)); }
     { ProfScope p(K_CHROMA, sb);
-      p.done(launch_chroma(g.mags.as<float>(), dv.sd, dv.tile_prefix, n, w.tile_prefix[n], g.t_filt32.as<float>(),
-                           g.tuning.as<int>(), g.tiles.as<double>(), debug ? g.chroma_dbg.as<double>() : nullptr, sb)); }
+      p.done(launch_chroma(S.mags.as<float>(), dv.sd, dv.tile_prefix, n, w.tile_prefix[n], g.t_filt32.as<float>(),
+                           S.tuning.as<int>(), S.tiles.as<double>(), debug ? S.chroma_dbg.as<double>() : nullptr, sb)); }
     { ProfScope p(K_BEAT, st);
-      p.done(launch_beattrack(g.thr.as<float>(), g.eb.as<float>(), dv.sd, n, g.bpm.as<float>(),
-                              g.tempo.as<float>(), g.bpm_count.as<unsigned int>(), st)); }
-    CK(cudaEventRecord(g.ev_join, sb));
-    CK(cudaStreamWaitEvent(st, g.ev_join, 0));
+      p.done(launch_beattrack(S.thr.as<float>(), S.eb.as<float>(), dv.sd, n, S.bpm.as<float>(),
+                              S.tempo.as<float>(), S.bpm_count.as<unsigned int>(), st)); }
+    CK(cudaEventRecord(S.ev_join, sb));
+    CK(cudaStreamWaitEvent(st, S.ev_join, 0));
     { ProfScope p(K_FINAL, st);
-      p.done(launch_finalize(dv.sd, n, g.cent.as<float>(), g.roll.as<float>(), g.flat.as<float>(),
-                             g.loud.as<float>(), g.zcr.as<unsigned int>(), g.tempo.as<float>(),
-                             g.tiles.as<double>(), version, d_out, out_base, peers, st)); }
+      p.done(launch_finalize(dv.sd, n, S.cent.as<float>(), S.roll.as<float>(), S.flat.as<float>(),
+                             S.loud.as<float>(), S.zcr.as<unsigned int>(), S.tempo.as<float>(),
+                             S.tiles.as<double>(), version, d_out, out_base, peers, st)); }
     CK(cudaGetLastError());
     return BLISS_B200_OK;
 }
 
-// split [0, n_songs) into waves that respect the workspace limit, run them in order
+// Split [0, n_songs) into waves and keep up to N_SETS of them in flight.
+//
+// wait_ev: what the waves wait for before touching d_pcm (nullptr: everything enqueued on `st` so far).
+// done_ev: nullptr -> `st` is made to wait for every wave before the call returns (the results are
+//          ordered on `st` like a plain kernel launch); otherwise done_ev[s] is recorded on wave set s's
+//          stream behind this call's last wave there (done_used[s] says whether it was) and `st` is left
+//          alone -- the host path uses this to let the next chunk's waves start while these still run.
 int analyze_device_locked(const float *d_pcm, const uint64_t *offsets, const uint64_t *n_samples,
                           uint32_t n_songs, int version, float *d_out, int32_t *status, cudaStream_t st,
-                          bool debug, const PeerRows *peers = nullptr) {
+                          bool debug, const PeerRows *peers = nullptr, cudaEvent_t wait_ev = nullptr,
+                          cudaEvent_t *done_ev = nullptr, bool *done_used = nullptr) {
     PeerRows no_peers;
     memset(&no_peers, 0, sizeof(no_peers));
     if (((uintptr_t)d_pcm & 15u) != 0) { g_last_error = "d_pcm must be 16-byte aligned"; return BLISS_B200_E_ARG; }
+    // serial mode (per-kernel profiling, debug taps): every wave on set 0, both chains on `st`
+    const bool serial = g.profiling || debug;
+    // Wave size: as many songs as the workspace share of one set holds.  Splitting a resident batch into
+    // more, overlapping waves does NOT pay: measured on 1024 tracks, 1 wave 79.8 ms, 3 waves 80.1, 8 waves
+    // 81.5, 16 waves 81.5 -- the FFT kernels keep every SM busy either way and the one-CTA-per-song
+    // kernels already overlap the other chain.  The sets earn their keep on the host path, where
+    // chunks arrive over PCIe one after the other.  BLISS_B200_WAVE_SONGS caps the wave for experiments.
+    const size_t wave_bytes = serial ? g.ws_limit : g.ws_limit / N_SETS;
+    uint32_t wave_songs = n_songs;
+    if (const char *e = getenv("BLISS_B200_WAVE_SONGS")) wave_songs = std::max(1, atoi(e));
+    for (auto &S : g.ws) S.used_in_call = false;
+    if (!serial && !wait_ev) {
+        CK(cudaEventRecord(g.ev_begin, st));
+        wait_ev = g.ev_begin;
+    }
     uint32_t first = 0;
     WavePlan w;
     while (first < n_songs) {
         size_t bytes = 0;
         uint32_t count = 0;
-        while (first + count < n_songs) {
+        while (first + count < n_songs && count < wave_songs) {
             const size_t b = geom_of(n_samples[first + count]).scratch_bytes + 128;
-            if (count > 0 && bytes + b > g.ws_limit) break;
+            if (count > 0 && bytes + b > wave_bytes) break;
             bytes += b;
             count++;
         }
         plan_wave(offsets, n_samples, first, count, false, w);
-        int rc = run_wave(d_pcm, w, version, d_out, first, st, debug, peers ? *peers : no_peers);
+        int rc;
+        if (serial) {
+            WaveSet &S = g.ws[0];  // set 0 on the caller's stream: order it behind and ahead of set 0's own waves
+            CK(cudaEventRecord(S.ev_done, S.main));
+            CK(cudaStreamWaitEvent(st, S.ev_done, 0));
+            if (wait_ev) CK(cudaStreamWaitEvent(st, wait_ev, 0));
+            rc = run_wave(d_pcm, w, version, d_out, first, S, st, st, debug, peers ? *peers : no_peers);
+            if (rc == 0) {
+                CK(cudaEventRecord(S.ev_done, st));
+                CK(cudaStreamWaitEvent(S.main, S.ev_done, 0));
+            }
+        } else {
+            WaveSet &S = g.ws[g.next_set];
+            g.next_set = (g.next_set + 1) % N_SETS;
+            CK(cudaStreamWaitEvent(S.main, wait_ev, 0));
+            rc = run_wave(d_pcm, w, version, d_out, first, S, S.main, S.side, debug, peers ? *peers : no_peers);
+            S.used_in_call = true;
+        }
         if (rc) return rc;
         first += count;
+    }
+    if (!serial) {
+        for (int i = 0; i < N_SETS; i++) {
+            WaveSet &S = g.ws[i];
+            if (done_used) done_used[i] = S.used_in_call;
+            if (!S.used_in_call) continue;
+            if (done_ev) {
+                CK(cudaEventRecord(done_ev[i], S.main));
+            } else {
+                CK(cudaEventRecord(S.ev_done, S.main));
+                CK(cudaStreamWaitEvent(st, S.ev_done, 0));
+            }
+        }
+    } else if (done_ev) {  // serial mode inside the host path: everything is on `st`
+        if (done_used) for (int i = 0; i < N_SETS; i++) done_used[i] = (i == 0);
+        CK(cudaEventRecord(done_ev[0], st));
     }
     if (status)
         for (uint32_t i = 0; i < n_songs; i++)
@@ -516,9 +599,15 @@ int bliss_b200_init(int device) {
     g.device = device;
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&g.side_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.ev_begin, cudaEventDisableTiming));
+    for (auto &S : g.ws) {
+        CK(cudaStreamCreateWithFlags(&S.main, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&S.side, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));
+    }
+    g.next_set = 0;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     g.ws_limit = (size_t)((double)total_b * 0.40);
@@ -533,19 +622,18 @@ void bliss_b200_shutdown(void) {
     if (!g.inited) return;
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
-    DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw4k, &g.t_tw2, &g.t_tw8k, &g.t_filt, &g.t_filt32, &g.blob, &g.mags, &g.cand_mag,
-                     &g.cand_pitch, &g.cand_count, &g.cent, &g.roll, &g.flat, &g.flux, &g.thr, &g.loud, &g.eb,
-                     &g.zcr, &g.tempo, &g.bpm, &g.bpm_count, &g.tuning, &g.tiles, &g.chroma_dbg, &g.pcm[0],
-                     &g.pcm[1], &g.pcm[2], &g.pcm[3], &g.feats, &g.metric, &g.misc[0], &g.misc[1], &g.misc[2], &g.misc[3],
-                     &g.misc[4], &g.misc[5]};
+    DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw4k, &g.t_tw2, &g.t_tw8k, &g.t_filt, &g.t_filt32,
+                     &g.pcm[0], &g.pcm[1], &g.pcm[2], &g.pcm[3], &g.feats, &g.metric, &g.misc[0], &g.misc[1],
+                     &g.misc[2], &g.misc[3], &g.misc[4], &g.misc[5]};
     for (DevBuf *b : all) b->release();
-    for (int i = 0; i < N_STAGE; i++) {
-        if (g.stage[i]) cudaFreeHost(g.stage[i]);
-        g.stage[i] = nullptr;
-        g.stage_cap[i] = 0;
-        if (g.stage_ev[i]) cudaEventDestroy(g.stage_ev[i]);
-        g.stage_ev[i] = nullptr;
-        g.stage_used[i] = false;
+    for (auto &S : g.ws) {
+        S.release();
+        cudaStreamDestroy(S.main);
+        cudaStreamDestroy(S.side);
+        cudaEventDestroy(S.ev_fork);
+        cudaEventDestroy(S.ev_join);
+        cudaEventDestroy(S.ev_done);
+        S.main = S.side = nullptr;
     }
     for (auto &p : g.ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     g.ev_pending.clear();
@@ -553,9 +641,7 @@ void bliss_b200_shutdown(void) {
     g.ev_pool.clear();
     cudaStreamDestroy(g.stream);
     cudaStreamDestroy(g.copy_stream);
-    cudaStreamDestroy(g.side_stream);
-    cudaEventDestroy(g.ev_fork);
-    cudaEventDestroy(g.ev_join);
+    cudaEventDestroy(g.ev_begin);
     g.inited = false;
 }
 
@@ -760,22 +846,21 @@ int bliss_b200_gather_destroy(bliss_b200_gather *ga) {
     return BLISS_B200_OK;
 }
 
-// host buffers: chunks of songs are copied on a side stream while the previous chunk computes
+// host buffers: chunks of songs are copied on the copy stream while earlier chunks compute
 static int analyze_host_locked(const float *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
                                uint16_t ver, float *out, int32_t *status, bool debug) {
     const uint32_t dim = bliss_b200_feature_count(ver);
     CK(g.feats.ensure((size_t)n_songs * dim * 4));
-    // The path is PCIe-bound (15.9 MB per 3-min song): chunks of songs are copied on a side stream while
-    // earlier chunks compute.  A chunk's kernels have ~3.5 ms of latency whatever its size (tuning, beat
-    // tracker), more than a small chunk's copy time, so the ring holds FOUR device PCM buffers: the
-    // copy engine can run three chunks ahead of the compute stream instead of idling (measured with
-    // BLISS_B200_TRACE: two buffers of 128 MB kept the link at 36 of 55 GB/s).
-    // BLISS_B200_CHUNK_MB overrides the chunk size for experiments.
-    // Measured (BLISS_B200_TRACE, 4 GB batch): 128 MB chunks -> 37 GB/s (compute-latency bound: 32 chunks x
-    // 3.5 ms), 256 MB -> 45 GB/s, 512 MB -> 50 GB/s of a 55.6 GB/s link; default = an eighth of the batch.
-    size_t total_mb = 0;
-    for (uint32_t i = 0; i < n_songs; i++) total_mb += (size_t)n_samples[i] * 4 >> 20;
-    size_t chunk_mb = std::min<size_t>(1024, std::max<size_t>(256, total_mb / 8));
+    // The path is PCIe-bound (15.9 MB per 3-min song).  Songs travel in chunks through a ring of FOUR
+    // device PCM buffers; a chunk's waves wait only for that chunk's copy and run on the wave sets'
+    // own streams, so the copy engine runs up to three chunks ahead and the ~3.5 ms latency floor of a
+    // chunk's kernel chain (tuning, beat tracker) overlaps the next chunks' kernels instead of
+    // serialising (measured with BLISS_B200_TRACE before the wave sets existed: 128 MB chunks 37 GB/s,
+    // 512 MB chunks 50 GB/s of a 55.6 GB/s link, but 9 ms of exposed first copy).
+    // The first chunks are small (64, 128, ... MB) so that compute starts early.
+    // BLISS_B200_CHUNK_MB overrides the steady chunk size for experiments.
+    size_t chunk_mb = 256;
+    if (const char *e = getenv("BLISS_B200_CHUNK_MB")) chunk_mb = std::max(1, atoi(e));
     const size_t chunk_budget = std::min<size_t>(chunk_mb << 20, std::max<size_t>(g.ws_limit / 8, (size_t)64 << 20));
     const bool trace = getenv("BLISS_B200_TRACE") != nullptr;
     cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};  // copy begin/end, compute begin/end
@@ -784,34 +869,47 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
         CK(cudaEventRecord(tr[0], g.copy_stream));
         CK(cudaEventRecord(tr[2], g.stream));
     }
+    std::vector<cudaEvent_t> tr_cb, tr_ce, tr_done;  // per chunk: copy begin / end, compute done (trace only)
+    std::vector<size_t> tr_bytes;
     size_t done_bytes = 0;
     constexpr int NBUF = 4;
-    cudaEvent_t ev_copy[NBUF], ev_done[NBUF];
+    cudaEvent_t ev_copy[NBUF], ev_done[NBUF][N_SETS];
+    bool done_used[NBUF][N_SETS];
     for (int i = 0; i < NBUF; i++) {
         CK(cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+        for (int k = 0; k < N_SETS; k++) {
+            CK(cudaEventCreateWithFlags(&ev_done[i][k], cudaEventDisableTiming));
+            done_used[i][k] = false;
+        }
     }
-    bool used[NBUF] = {false, false, false, false};
     std::vector<uint64_t> offs, lens;
     uint32_t first = 0;
     int c = 0, rc = BLISS_B200_OK;
     while (first < n_songs && rc == BLISS_B200_OK) {
         // chunk = as many songs as fit the PCM budget (at least one)
+        const size_t budget = std::min<size_t>(chunk_budget, c < 8 ? ((size_t)64 << 20) << c : chunk_budget);
         size_t samples = 0;
         uint32_t count = 0;
         offs.clear();
         lens.clear();
         while (first + count < n_songs) {
             const size_t len = align_up((size_t)n_samples[first + count], 4);
-            if (count > 0 && (samples + len) * 4 > chunk_budget) break;
+            if (count > 0 && (samples + len) * 4 > budget) break;
             offs.push_back(samples);
             lens.push_back(n_samples[first + count]);
             samples += len;
             count++;
         }
         const int b = c % NBUF;
-        if (used[b]) CK(cudaEventSynchronize(ev_done[b]));  // buffer b free again (also: host may realloc)
+        for (int k = 0; k < N_SETS; k++)  // buffer b free again (also: the host may reallocate it)
+            if (done_used[b][k]) CK(cudaEventSynchronize(ev_done[b][k]));
         CK(g.pcm[b].ensure(std::max<size_t>(samples, 4) * 4));
+        if (trace) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            CK(cudaEventRecord(e, g.copy_stream));
+            tr_cb.push_back(e);
+        }
         for (uint32_t i = 0; i < count;) {
             if (lens[i] == 0) { i++; continue; }
             if (!pcm[first + i]) { g_last_error = "null pcm pointer"; rc = BLISS_B200_E_ARG; break; }
@@ -829,17 +927,32 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
         }
         if (rc) break;
         CK(cudaEventRecord(ev_copy[b], g.copy_stream));
-        CK(cudaStreamWaitEvent(g.stream, ev_copy[b], 0));
+        if (trace) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            CK(cudaEventRecord(e, g.copy_stream));
+            tr_ce.push_back(e);
+            tr_bytes.push_back(samples * 4);
+        }
         rc = analyze_device_locked(g.pcm[b].as<float>(), offs.data(), lens.data(), count, ver,
                                    g.feats.as<float>() + (size_t)first * dim, status ? status + first : nullptr,
-                                   g.stream, debug);
-        CK(cudaEventRecord(ev_done[b], g.stream));
-        used[b] = true;
+                                   g.stream, debug, nullptr, ev_copy[b], ev_done[b], done_used[b]);
+        if (trace && rc == BLISS_B200_OK) {  // a chunk this small is one wave: its set is the one just used
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            CK(cudaEventRecord(e, g.ws[(g.next_set + N_SETS - 1) % N_SETS].main));
+            tr_done.push_back(e);
+        }
         first += count;
         done_bytes += samples * 4;
         c++;
     }
     if (rc == BLISS_B200_OK) {
+        // the result copy waits for every wave set (and, in serial mode, g.stream ran the waves itself)
+        for (auto &S : g.ws) {
+            CK(cudaEventRecord(S.ev_done, S.main));
+            CK(cudaStreamWaitEvent(g.stream, S.ev_done, 0));
+        }
         if (trace) {
             CK(cudaEventRecord(tr[1], g.copy_stream));
             CK(cudaEventRecord(tr[3], g.stream));
@@ -852,15 +965,33 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
             cudaEventElapsedTime(&ms_comp, tr[2], tr[3]);
             cudaEventElapsedTime(&ms_all, tr[0], tr[3]);
             fprintf(stderr, "[bliss_b200 trace] songs=%u bytes=%.1f MB chunks=%d chunk_mb=%zu copy_stream=%.2f ms (%.1f GB/s) "
-                            "compute_stream=%.2f ms first_copy->last_kernel=%.2f ms\n",
+                            "first_launch->last_kernel=%.2f ms first_copy->last_kernel=%.2f ms\n",
                     n_songs, done_bytes / 1e6, c, chunk_mb, ms_copy, done_bytes / 1e6 / ms_copy, ms_comp, ms_all);
+            // per chunk: when its copy started / ended and when its kernels were done, relative to the first copy
+            double busy = 0.;
+            for (size_t k = 0; k < tr_ce.size() && k < tr_done.size(); k++) {
+                float t_b = 0.f, t_e = 0.f, t_d = 0.f;
+                cudaEventElapsedTime(&t_b, tr[0], tr_cb[k]);
+                cudaEventElapsedTime(&t_e, tr[0], tr_ce[k]);
+                cudaEventElapsedTime(&t_d, tr[0], tr_done[k]);
+                busy += t_e - t_b;
+                if (getenv("BLISS_B200_TRACE_CHUNKS"))
+                    fprintf(stderr, "[bliss_b200 trace]   chunk %2zu %6.1f MB copy %7.2f -> %7.2f ms (%.1f GB/s)  kernels done %7.2f ms (+%.2f)\n",
+                            k, tr_bytes[k] / 1e6, t_b, t_e, tr_bytes[k] / 1e6 / (t_e - t_b), t_d, t_d - t_e);
+            }
+            fprintf(stderr, "[bliss_b200 trace] copy engine busy %.2f ms of %.2f ms (%.1f GB/s while copying)\n", busy, ms_copy,
+                    done_bytes / 1e6 / busy);
             for (auto &e : tr) cudaEventDestroy(e);
         }
     } else {
-        cudaStreamSynchronize(g.stream);
-        cudaStreamSynchronize(g.copy_stream);
+        cudaDeviceSynchronize();
     }
-    for (int i = 0; i < NBUF; i++) { cudaEventDestroy(ev_copy[i]); cudaEventDestroy(ev_done[i]); }
+    for (int i = 0; i < NBUF; i++) {
+        cudaEventDestroy(ev_copy[i]);
+        for (int k = 0; k < N_SETS; k++) cudaEventDestroy(ev_done[i][k]);
+    }
+    for (auto *v : {&tr_cb, &tr_ce, &tr_done})
+        for (auto e : *v) cudaEventDestroy(e);
     return rc;
 }
 
@@ -901,36 +1032,36 @@ int bliss_b200_analyze_taps(const float *pcm, uint64_t n, uint16_t ver, float *o
     auto dl = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
         return dst ? cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) : cudaSuccess;
     };
-    CK(dl(t->centroid, g.cent.p, (size_t)q.n_s * 4));
-    CK(dl(t->rolloff, g.roll.p, (size_t)q.n_s * 4));
-    CK(dl(t->flatness, g.flat.p, (size_t)q.n_s * 4));
-    CK(dl(t->flux, g.flux.p, (size_t)q.n_t * 4));
-    CK(dl(t->thresholded, g.thr.p, (size_t)q.n_t * 4));
+    CK(dl(t->centroid, g.ws[0].cent.p, (size_t)q.n_s * 4));
+    CK(dl(t->rolloff, g.ws[0].roll.p, (size_t)q.n_s * 4));
+    CK(dl(t->flatness, g.ws[0].flat.p, (size_t)q.n_s * 4));
+    CK(dl(t->flux, g.ws[0].flux.p, (size_t)q.n_t * 4));
+    CK(dl(t->thresholded, g.ws[0].thr.p, (size_t)q.n_t * 4));
     uint32_t nb = 0;
-    CK(cudaMemcpy(&nb, g.bpm_count.p, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&nb, g.ws[0].bpm_count.p, 4, cudaMemcpyDeviceToHost));
     if (t->n_bpms) *t->n_bpms = nb;
-    CK(dl(t->bpms, g.bpm.p, (size_t)nb * 4));
-    CK(dl(t->loudness_chunks, g.loud.p, (size_t)q.n_l * 4));
-    CK(dl(t->zero_crossings, g.zcr.p, 4));
+    CK(dl(t->bpms, g.ws[0].bpm.p, (size_t)nb * 4));
+    CK(dl(t->loudness_chunks, g.ws[0].loud.p, (size_t)q.n_l * 4));
+    CK(dl(t->zero_crossings, g.ws[0].zcr.p, 4));
     if (t->stft8192) {
-        CK(cudaMemcpy2D(t->stft8192, (size_t)CH_BINS * 4, g.mags.p, (size_t)CH_STRIDE * 4, (size_t)CH_BINS * 4,
+        CK(cudaMemcpy2D(t->stft8192, (size_t)CH_BINS * 4, g.ws[0].mags.p, (size_t)CH_STRIDE * 4, (size_t)CH_BINS * 4,
                         q.n_c_comp, cudaMemcpyDeviceToHost));
         for (uint32_t f = q.n_c_comp; f < q.n_c; f++) memset(t->stft8192 + (size_t)f * CH_BINS, 0, (size_t)CH_BINS * 4);
     }
     if (t->n_peaks) {
         uint32_t c = 0;
-        CK(cudaMemcpy(&c, g.cand_count.p, 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&c, g.ws[0].cand_count.p, 4, cudaMemcpyDeviceToHost));
         *t->n_peaks = c;
     }
     if (t->tuning) {
         int idx = 0;
-        CK(cudaMemcpy(&idx, g.tuning.p, 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&idx, g.ws[0].tuning.p, 4, cudaMemcpyDeviceToHost));
         *t->tuning = (-50. + (100. * 0.01 * (double)idx)) / 100.;
     }
-    CK(dl(t->chroma, g.chroma_dbg.p, (size_t)q.n_c * 12 * sizeof(double)));
+    CK(dl(t->chroma, g.ws[0].chroma_dbg.p, (size_t)q.n_c * 12 * sizeof(double)));
     if (t->interval_features) {
         std::vector<double> parts((size_t)q.n_tiles * 10);
-        CK(cudaMemcpy(parts.data(), g.tiles.p, parts.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(parts.data(), g.ws[0].tiles.p, parts.size() * sizeof(double), cudaMemcpyDeviceToHost));
         for (int k = 0; k < 10; k++) {
             double acc = 0.;
             for (uint32_t tl = 0; tl < q.n_tiles; tl++) acc += parts[(size_t)tl * 10 + k];
@@ -952,12 +1083,19 @@ int bliss_b200_stft512_mag_device(const float *d_pcm, const uint64_t *offsets, c
         frame_offsets_out[n_songs] = w.n_t;
     }
     WaveDev dv;
-    int rc = upload_plan(w, st, dv);
+    WaveSet &S = g.ws[0];  // borrows set 0's descriptor staging: order `st` behind and ahead of its waves
+    CK(cudaEventRecord(S.ev_done, S.main));
+    CK(cudaStreamWaitEvent(st, S.ev_done, 0));
+    int rc = upload_plan(w, S, st, dv, nullptr, nullptr);
     if (rc) return rc;
-    ProfScope p(K_STFT512, st);
-    p.done(launch_stft512_mags(d_pcm, dv.sd, dv.k1_prefix, (int)n_songs, w.k1_prefix[n_songs],
-                               (int)w.pairs_per_item, pvoc_tables(), d_mags, st));
+    {
+        ProfScope p(K_STFT512, st);
+        p.done(launch_stft512_mags(d_pcm, dv.sd, dv.k1_prefix, (int)n_songs, w.k1_prefix[n_songs],
+                                   (int)w.pairs_per_item, pvoc_tables(), d_mags, st));
+    }
     CK(cudaGetLastError());
+    CK(cudaEventRecord(S.ev_done, st));
+    CK(cudaStreamWaitEvent(S.main, S.ev_done, 0));
     return BLISS_B200_OK;
 }
 
