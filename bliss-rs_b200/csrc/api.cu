@@ -28,16 +28,16 @@ int launch_timedomain(const float *, const SongDesc *, const unsigned int *, int
                       float *, unsigned int *, cudaStream_t);
 int launch_peakpick(const float *, const SongDesc *, const unsigned int *, int, unsigned int, float *,
                     cudaStream_t);
-int launch_beattrack(const float *, const float *, const SongDesc *, int, float *, float *, unsigned int *,
+int launch_beattrack(const float *, const float *, const SongDesc *, int, float *, float *, unsigned int *, int,
                      cudaStream_t);
 int launch_chroma_filter_table(double *, float *, cudaStream_t);
 int launch_stft8192(const float *, const SongDesc *, const unsigned int *, int, unsigned int, const float *,
-                    const cpx *, const cpx *, const cpx *, float *, double *, double *, unsigned int *,
+                    const cpx *, const cpx *, const cpx *, float *, double *, double *, unsigned int *, int,
                     cudaStream_t);
-int launch_tuning(const double *, const double *, const unsigned int *, const SongDesc *, int, int *,
+int launch_tuning(const double *, const double *, const unsigned int *, const SongDesc *, int, int *, int,
                   cudaStream_t);
 int launch_chroma(const float *, const SongDesc *, const unsigned int *, int, unsigned int, const float *,
-                  const int *, double *, double *, cudaStream_t);
+                  const int *, double *, double *, int, cudaStream_t);
 int launch_finalize(const SongDesc *, int, const float *, const float *, const float *, const float *,
                     const unsigned int *, const float *, const double *, int, float *, unsigned int,
                     const PeerRows &, cudaStream_t);
@@ -145,6 +145,7 @@ struct Ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_begin = nullptr;
     size_t ws_limit = 0;
+    int variant = 0;  // BLISS_B200_VARIANT, see common.cuh
     // constant tables
     DevBuf t_win512, t_twA, t_hann8k, t_tw4k, t_tw2, t_tw8k, t_filt, t_filt32;
     WaveSet ws[N_SETS];
@@ -332,7 +333,8 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
              cudaStream_t st, cudaStream_t sb, bool debug, const PeerRows &peers) {
     const int n = (int)w.sd.size();
     if (n == 0) return BLISS_B200_OK;
-    CK(S.mags.ensure(std::max<size_t>(w.rows, 2) * CH_STRIDE * sizeof(float)));
+    // + one tile of rows: chroma_pipe_kernel forms (never dereferences) addresses of a full tile
+    CK(S.mags.ensure((std::max<size_t>(w.rows, 2) + CH_TILE_FRAMES) * CH_STRIDE * sizeof(float)));
     CK(S.cand_mag.ensure(std::max<size_t>(w.cands, 1) * sizeof(double)));
     CK(S.cand_pitch.ensure(std::max<size_t>(w.cands, 1) * sizeof(double)));  // interpolated pitches (f64)
     CK(S.cand_count.ensure((size_t)n * 4));
@@ -364,7 +366,7 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
     { ProfScope p(K_STFT8K, sb);
       p.done(launch_stft8192(d_pcm, dv.sd, dv.pair_prefix, n, w.pair_prefix[n], g.t_hann8k.as<float>(),
                              g.t_tw4k.as<cpx>(), g.t_tw2.as<cpx>(), g.t_tw8k.as<cpx>(), S.mags.as<float>(), S.cand_mag.as<double>(),
-                             S.cand_pitch.as<double>(), S.cand_count.as<unsigned int>(), sb)); }
+                             S.cand_pitch.as<double>(), S.cand_count.as<unsigned int>(), g.variant, sb)); }
     { ProfScope p(K_TIME, st);
       p.done(launch_timedomain(d_pcm, dv.sd, dv.chunk_prefix, n, w.chunk_prefix[n], S.loud.as<float>(),
                                S.eb.as<float>(), S.zcr.as<unsigned int>(), st)); }
@@ -373,15 +375,16 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
                             S.cent.as<float>(), S.roll.as<float>(), S.flat.as<float>(), S.flux.as<float>(), st)); }
     { ProfScope p(K_TUNING, sb);
       p.done(launch_tuning(S.cand_mag.as<double>(), S.cand_pitch.as<double>(),
-                           S.cand_count.as<unsigned int>(), dv.sd, n, S.tuning.as<int>(), sb)); }
+                           S.cand_count.as<unsigned int>(), dv.sd, n, S.tuning.as<int>(), g.variant, sb)); }
     { ProfScope p(K_PEAK, st);
       p.done(launch_peakpick(S.flux.as<float>(), dv.sd, dv.t_prefix, n, w.t_prefix[n], S.thr.as<float>(), st)); }
     { ProfScope p(K_CHROMA, sb);
       p.done(launch_chroma(S.mags.as<float>(), dv.sd, dv.tile_prefix, n, w.tile_prefix[n], g.t_filt32.as<float>(),
-                           S.tuning.as<int>(), S.tiles.as<double>(), debug ? S.chroma_dbg.as<double>() : nullptr, sb)); }
+                           S.tuning.as<int>(), S.tiles.as<double>(), debug ? S.chroma_dbg.as<double>() : nullptr,
+                           g.variant, sb)); }
     { ProfScope p(K_BEAT, st);
       p.done(launch_beattrack(S.thr.as<float>(), S.eb.as<float>(), dv.sd, n, S.bpm.as<float>(),
-                              S.tempo.as<float>(), S.bpm_count.as<unsigned int>(), st)); }
+                              S.tempo.as<float>(), S.bpm_count.as<unsigned int>(), g.variant, st)); }
     CK(cudaEventRecord(S.ev_join, sb));
     CK(cudaStreamWaitEvent(st, S.ev_join, 0));
     { ProfScope p(K_FINAL, st);
@@ -611,6 +614,8 @@ int bliss_b200_init(int device) {
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     g.ws_limit = (size_t)((double)total_b * 0.40);
+    g.variant = 0;
+    if (const char *e = getenv("BLISS_B200_VARIANT")) g.variant = atoi(e);
     int rc = build_tables();
     if (rc) return rc;
     g.inited = true;

@@ -94,6 +94,25 @@ __device__ __forceinline__ void epilogue_bins(const cpx *pk, const cpx *pm, bool
     }
 }
 
+// pair epilogue: bins k = t + 256 M (M = 0..7) from the thread's own registers, their mirrors
+// 4096 - k from the block the mirror thread published (rfft8192.cuh, pass3_regs).  Magnitudes go
+// straight to the spill row; only bins < 1536 (lo[0..5]) are kept for pip_track.
+template <int M>
+__device__ __forceinline__ void epilogue_pairs(const cpx (&v)[16], const cpx *pm, bool t0, const cpx *buf0, cpx wt,
+                                               float *gm_lo, float *gm_hi, float (&lo)[6], float &mx) {
+    if constexpr (M < 8) {
+        const cpx zm = t0 ? buf0[(16 - M) & 15] : pm[-M];
+        float a, b;
+        r8k::untangle_mag_pair(v[bitrev(M, 4)], zm, mul_tw<M, 32>(wt), a, b);
+        gm_lo[256 * M] = a;
+        gm_hi[-256 * M] = b;
+        mx = fmaxf(mx, fmaxf(a, b));
+        if constexpr (M < 6) lo[M] = a;
+        epilogue_pairs<M + 1>(v, pm, t0, buf0, wt, gm_lo, gm_hi, lo, mx);
+    }
+}
+
+template <bool PAIR_EPILOGUE>
 __global__ void __launch_bounds__(K3_THREADS, 4)
 stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
                 const unsigned int *__restrict__ frame_prefix, int n_songs,
@@ -116,6 +135,7 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     const int fbase = (int)(item - frame_prefix[si]) * K3_FRAMES_PER_CTA;
     const float *x = pcm + sd.pcm_off;
     const int n = (int)sd.n;
+    const unsigned int mag_row0 = (unsigned int)sd.mag_off;  // spill rows of a wave stay far below 2^32
 #pragma unroll 1
     for (int f = fbase; f < min(fbase + K3_FRAMES_PER_CTA, (int)sd.n_c_comp); f++) {
     // the frame covers samples s0 .. s0+8191 of the reflect-padded song (utils.rs:11-24, :44-47)
@@ -131,14 +151,14 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
 #pragma unroll
             for (int q = 0; q < 16; q++) {
                 const float2 w = __ldg(ph + 256 * q);
-                v[q] = cpx{__ldg(pa + 512 * q) * w.x, __ldg(pa + 512 * q + 1) * w.y};
+                v[q] = pmul(cpx{__ldg(pa + 512 * q), __ldg(pa + 512 * q + 1)}, cpx{w.x, w.y});
             }
         } else {
 #pragma unroll
             for (int q = 0; q < 16; q++) {
                 const float2 w = __ldg(ph + 256 * q);
                 const long long i0 = (long long)s0 + 2 * (tid + 256 * q);
-                v[q] = cpx{r8k::reflect_sample(x, n, i0) * w.x, r8k::reflect_sample(x, n, i0 + 1) * w.y};
+                v[q] = pmul(cpx{r8k::reflect_sample(x, n, i0), r8k::reflect_sample(x, n, i0 + 1)}, cpx{w.x, w.y});
             }
         }
         r8k::pass1_store(tid, v, tw1, buf);
@@ -146,42 +166,74 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     __syncthreads();
     r8k::pass2(tid, s_tw2, buf);
     __syncthreads();
-    r8k::pass3(tid, buf);
-    __syncthreads();
+    float *sm = reinterpret_cast<float *>(buf);  // magnitudes for pip_track once the FFT data is dead
+    float fmx;                                   // frame maximum
+    if constexpr (!PAIR_EPILOGUE) {
+        r8k::pass3(tid, buf);
+        __syncthreads();
 
-    // natural-order magnitudes: thread owns bins tid + 256 m, m = 0..15; thread 0 also bin 4096
-    float mag[17];
-    mag[16] = 0.f;
-    {
-        const cpx wt = tw8192[tid];
-        const cpx *pk = buf + r8k::zbase(tid);
-        const cpx *pm = buf + r8k::zbase((256 - tid) & 255) + 15;
-        epilogue_bins<0>(pk, pm, tid == 0, buf, wt, mag);
-        if (tid == 0) mag[16] = r8k::untangle_mag(buf[0], buf[0], cpx{-1.f, 0.f});
+        // natural-order magnitudes: thread owns bins tid + 256 m, m = 0..15; thread 0 also bin 4096
+        float mag[17];
+        mag[16] = 0.f;
+        {
+            const cpx wt = tw8192[tid];
+            const cpx *pk = buf + r8k::zbase(tid);
+            const cpx *pm = buf + r8k::zbase((256 - tid) & 255) + 15;
+            epilogue_bins<0>(pk, pm, tid == 0, buf, wt, mag);
+            if (tid == 0) mag[16] = r8k::untangle_mag(buf[0], buf[0], cpx{-1.f, 0.f});
+        }
+        float mx = 0.f;
+#pragma unroll
+        for (int m = 0; m < 17; m++) mx = fmaxf(mx, mag[m]);
+        __syncthreads();  // everyone has read buf; reuse it for the magnitudes
+        float *gm = mags + (size_t)(mag_row0 + (unsigned int)f) * CH_STRIDE;
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            sm[tid + 256 * m] = mag[m];
+            gm[tid + 256 * m] = mag[m];
+        }
+        if (tid == 0) {
+            sm[4096] = mag[16];
+            gm[4096] = mag[16];
+        }
+        // frame maximum (pip_track's ref_value = 0.1 * max over all bins, chroma.rs:289-293)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+        __syncthreads();
+        fmx = s_red[0];
+#pragma unroll
+        for (int w = 1; w < K3_THREADS / 32; w++) fmx = fmaxf(fmx, s_red[w]);
+
+    } else {
+        // pass 3 leaves the thread's own bins t + 256 m in registers; only mirror values travel through smem
+        float lo[6], mx = 0.f;  // lo[M] = |X[t + 256 M]|: the bins pip_track looks at (56..1484)
+        float *gm = mags + (size_t)(mag_row0 + (unsigned int)f) * CH_STRIDE;
+        {
+            cpx v[16];
+            r8k::pass3_regs(tid, v, buf);
+            __syncthreads();
+            const cpx wt = tw8192[tid];
+            const cpx *pm = buf + r8k::zbase((256 - tid) & 255) + 15;
+            epilogue_pairs<0>(v, pm, tid == 0, buf, wt, gm + tid, gm + 4096 - tid, lo, mx);
+            if (tid == 0) {  // the self-mirrored bin 2048: W8192^2048 = -i
+                const float mid = r8k::untangle_mag(v[bitrev(8, 4)], v[bitrev(8, 4)], cpx{0.f, -1.f});
+                gm[2048] = mid;
+                mx = fmaxf(mx, mid);
+            }
+        }
+        __syncthreads();  // every mirror value has been read; reuse buf for the magnitudes pip_track looks at
+#pragma unroll
+        for (int m = 0; m < 6; m++) sm[tid + 256 * m] = lo[m];
+        // frame maximum (pip_track's ref_value = 0.1 * max over all bins, chroma.rs:289-293)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+        __syncthreads();
+        fmx = s_red[0];
+#pragma unroll
+        for (int w = 1; w < K3_THREADS / 32; w++) fmx = fmaxf(fmx, s_red[w]);
     }
-    float mx = 0.f;
-#pragma unroll
-    for (int m = 0; m < 17; m++) mx = fmaxf(mx, mag[m]);
-    __syncthreads();  // everyone has read buf; reuse it for the magnitudes
-    float *sm = reinterpret_cast<float *>(buf);
-    float *gm = mags + (sd.mag_off + (unsigned long long)f) * CH_STRIDE;
-#pragma unroll
-    for (int m = 0; m < 16; m++) {
-        sm[tid + 256 * m] = mag[m];
-        gm[tid + 256 * m] = mag[m];
-    }
-    if (tid == 0) {
-        sm[4096] = mag[16];
-        gm[4096] = mag[16];
-    }
-    // frame maximum (pip_track's ref_value = 0.1 * max over all bins, chroma.rs:289-293)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
-    __syncthreads();
-    float fmx = s_red[0];
-#pragma unroll
-    for (int w = 1; w < K3_THREADS / 32; w++) fmx = fmaxf(fmx, s_red[w]);
 
     // pip_track on centre bins 57..1483 (beginning = 56, end = 1486 for n_fft = 8192).
     // Phase 1 counts this thread's peaks, a block scan reserves the output range, phase 2 emits.
@@ -355,6 +407,206 @@ tuning_kernel(const double *__restrict__ cand_mag, const double *__restrict__ ca
         int best = 0;
         for (int b = 1; b < 100; b++)
             if (hist[b] > hist[best]) best = b;
+        tuning_idx[blockIdx.x] = best;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4 (current): same result as tuning_kernel above, four sweeps over the candidates instead of ten.
+//   sweep 0  min / max key  -> the bits every key shares are skipped
+//   sweep 1+ 12-bit digit histogram below the shared prefix, block scan picks the bucket holding the
+//            wanted rank; repeated only while the bucket holds more keys than fit in shared memory
+//            (heavy duplicates / the 714-peaks-per-frame worst case)
+//   sweep 2  the bucket's keys go to shared memory (+ the smallest key above the bucket)
+//            -> both order statistics by rank counting on <= 2048 keys
+//   sweep 3  residue histogram of the candidates with mag >= threshold, per-warp private bins
+// No warp collectives inside the sweeps, so the loads of consecutive iterations overlap.
+// ---------------------------------------------------------------------------
+constexpr int K4_BINS = 4096;      // 12-bit digits
+constexpr int K4_SURV_CAP = 2048;  // keys of the final bucket kept in shared memory
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+    return (unsigned long long)__shfl_xor_sync(0xffffffffu, (long long)v, m);
+}
+
+__global__ void __launch_bounds__(K4_THREADS)
+tuning_select_kernel(const double *__restrict__ cand_mag, const double *__restrict__ cand_pitch,
+                     const unsigned int *__restrict__ cand_count, const SongDesc *__restrict__ songs,
+                     int *__restrict__ tuning_idx) {
+    __shared__ unsigned int hist[K4_BINS];
+    __shared__ unsigned long long surv[K4_SURV_CAP];
+    __shared__ unsigned long long s_min[K4_THREADS / 32], s_max[K4_THREADS / 32];
+    __shared__ unsigned int s_wsum[K4_THREADS / 32];
+    __shared__ unsigned int s_bucket, s_rank, s_count, s_nsurv;
+    __shared__ unsigned long long s_vlo, s_vhi, s_next;
+    const SongDesc sd = songs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned int n = sd.valid ? cand_count[blockIdx.x] : 0u;
+    if (n == 0) {  // estimate_tuning returns 0 when pip_track finds nothing (chroma.rs:377-379)
+        if (tid == 0) tuning_idx[blockIdx.x] = 50;
+        return;
+    }
+    const unsigned long long *keys = reinterpret_cast<const unsigned long long *>(cand_mag + sd.cand_off);
+    const double *pitches = cand_pitch + sd.cand_off;
+    const unsigned int r_lo = (n - 1) / 2, r_hi = n / 2;  // floor / ceil of (n-1)*0.5 (Midpoint quantile)
+
+    // ---- sweep 0: min / max (all keys are positive doubles: bit order == value order) ----
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+#pragma unroll 4
+    for (unsigned int i = tid; i < n; i += K4_THREADS) {
+        const unsigned long long k = __ldg(keys + i);
+        kmin = k < kmin ? k : kmin;
+        kmax = k > kmax ? k : kmax;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = shfl_xor_u64(kmin, o), b = shfl_xor_u64(kmax, o);
+        kmin = a < kmin ? a : kmin;
+        kmax = b > kmax ? b : kmax;
+    }
+    if (lane == 0) { s_min[wid] = kmin; s_max[wid] = kmax; }
+    if (tid == 0) { s_nsurv = 0; s_next = ~0ull; s_vlo = 0ull; s_vhi = 0ull; }
+    __syncthreads();
+#pragma unroll 1
+    for (int w = 0; w < K4_THREADS / 32; w++) {
+        kmin = s_min[w] < kmin ? s_min[w] : kmin;
+        kmax = s_max[w] > kmax ? s_max[w] : kmax;
+    }
+
+    unsigned long long vlo, vhi;
+    if (kmin == kmax) {
+        vlo = vhi = kmin;
+    } else {
+        // bits [63 : d_prev) are shared by every key still in play and equal `prefix`
+        int d_prev = 64 - __clzll((long long)(kmin ^ kmax));  // 1..63 (the sign bit is always shared)
+        unsigned long long prefix = kmin >> d_prev;
+        unsigned int rank = r_lo, count = n;
+        int lo_bit;
+        while (true) {
+            lo_bit = d_prev > 12 ? d_prev - 12 : 0;
+            const int width = d_prev - lo_bit;
+            const unsigned int dmask = (1u << width) - 1u;
+#pragma unroll
+            for (int j = 0; j < K4_BINS / K4_THREADS; j++) hist[tid + K4_THREADS * j] = 0u;
+            __syncthreads();
+#pragma unroll 4
+            for (unsigned int i = tid; i < n; i += K4_THREADS) {
+                const unsigned long long k = __ldg(keys + i);
+                if ((k >> d_prev) == prefix) atomicAdd(&hist[(unsigned int)(k >> lo_bit) & dmask], 1u);
+            }
+            __syncthreads();
+            // bucket holding `rank`: thread owns bins 4 tid .. 4 tid + 3
+            unsigned int c[K4_BINS / K4_THREADS], mine = 0;
+#pragma unroll
+            for (int j = 0; j < K4_BINS / K4_THREADS; j++) { c[j] = hist[(K4_BINS / K4_THREADS) * tid + j]; mine += c[j]; }
+            unsigned int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_wsum[wid] = incl;
+            __syncthreads();
+            unsigned int before = incl - mine;
+#pragma unroll 1
+            for (int w = 0; w < wid; w++) before += s_wsum[w];
+            if (before <= rank && rank < before + mine) {  // exactly one thread
+                unsigned int e = before;
+#pragma unroll
+                for (int j = 0; j < K4_BINS / K4_THREADS; j++) {
+                    if (rank >= e && rank < e + c[j]) {
+                        s_bucket = (unsigned int)((K4_BINS / K4_THREADS) * tid + j);
+                        s_rank = rank - e;
+                        s_count = c[j];
+                    }
+                    e += c[j];
+                }
+            }
+            __syncthreads();
+            prefix = (prefix << width) | (unsigned long long)s_bucket;
+            rank = s_rank;
+            count = s_count;
+            d_prev = lo_bit;
+            if (count <= (unsigned int)K4_SURV_CAP || lo_bit == 0) break;
+        }
+        // ---- sweep 2: the bucket's keys to shared memory; the smallest key above the bucket ----
+        // (lo_bit == 0 with count > cap: every key of the bucket equals `prefix`, nothing to collect)
+        const bool collect = count <= (unsigned int)K4_SURV_CAP;
+        unsigned long long nxt = ~0ull;
+#pragma unroll 4
+        for (unsigned int i = tid; i < n; i += K4_THREADS) {
+            const unsigned long long k = __ldg(keys + i);
+            const unsigned long long top = k >> lo_bit;
+            if (top == prefix) {
+                if (collect) surv[atomicAdd(&s_nsurv, 1u)] = k;
+            } else if (top > prefix) {
+                nxt = k < nxt ? k : nxt;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long a = shfl_xor_u64(nxt, o);
+            nxt = a < nxt ? a : nxt;
+        }
+        if (lane == 0 && nxt != ~0ull) atomicMin(&s_next, nxt);
+        __syncthreads();
+        if (collect) {
+            // order statistics `rank` and `rank + 1` of the bucket by rank counting (ties by position)
+            for (unsigned int idx = tid; idx < count; idx += K4_THREADS) {
+                const unsigned long long key = surv[idx];
+                unsigned int r = 0;
+                for (unsigned int j = 0; j < count; j++) {
+                    const unsigned long long o = surv[j];
+                    r += (o < key || (o == key && j < idx)) ? 1u : 0u;
+                }
+                if (r == rank) s_vlo = key;
+                if (r == rank + 1u) s_vhi = key;
+            }
+            __syncthreads();
+            vlo = s_vlo;
+            vhi = (rank + 1u < count) ? s_vhi : s_next;
+        } else {
+            vlo = prefix;
+            vhi = (rank + 1u < count) ? prefix : s_next;
+        }
+        if (r_hi == r_lo) vhi = vlo;
+    }
+    const double lower = __longlong_as_double((long long)vlo), higher = __longlong_as_double((long long)vhi);
+    const double thr = lower + (higher - lower) / 2.;  // ndarray-stats Midpoint
+
+    // ---- sweep 3: histogram of residues with mag >= thr (chroma.rs:385-390 -> pitch_tuning :342-356) ----
+    __syncthreads();  // hist / surv are free again
+#pragma unroll
+    for (int j = 0; j < K4_BINS / K4_THREADS; j++) hist[tid + K4_THREADS * j] = 0u;
+    __syncthreads();
+    {
+        unsigned int *my = hist + 128 * wid;  // per-warp private bins
+        const double *mg = cand_mag + sd.cand_off;
+#pragma unroll 2
+        for (unsigned int i = tid; i < n; i += K4_THREADS) {
+            if (__ldg(mg + i) >= thr) {
+                // hz_to_octs with tuning 0, 12 bins per octave, residue in [-0.5, 0.5), 100 bins of 0.01
+                double v = __ldg(pitches + i) / (440.0 / 16.);
+                v = 12.0 * log2(v);
+                v = v - trunc(v);  // == fmod(v, 1.0): the fractional part is exact either way
+                if (v >= 0.5) v -= 1.;
+                const int idx = (int)((v - -0.5) / 0.01);
+                atomicAdd(my + (idx < 0 ? 0 : (idx > 99 ? 99 : idx)), 1u);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < 128) {
+        unsigned int v = 0;
+#pragma unroll 1
+        for (int w = 0; w < K4_THREADS / 32; w++) v += hist[128 * w + tid];
+        hist[tid] = v;  // column `tid` of warp 0's bins: read by this thread only
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int best = 0;
+        for (int b = 1; b < 100; b++)
+            if (hist[b] > hist[best]) best = b;  // argmax = first maximum
         tuning_idx[blockIdx.x] = best;
     }
 }
@@ -539,31 +791,187 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
     }
 }
 
+// ---------------------------------------------------------------------------
+// K5 (current): the same contraction and epilogue as chroma_kernel above -- bit-identical results, the
+// 16-bin f32 chunks and their f64 sums are kept -- but the magnitude tile never passes through
+// registers: cp.async (LDGSTS) copies 64-byte row segments [frame][16 bins] straight into a 3-stage
+// shared-memory ring, one __syncthreads per stage, and the consumer reads its two frames and the
+// broadcast weights with 128-bit loads (row pitch 80 B = 5 x 16 B: conflict-free for quarter warps).
+// Per 16-bin stage and thread: 8 cp.async + 8 LDS.128 (values) + 48 LDS.128 (weights, broadcast)
+// for 384 FMA, against 32 LDG + 32 STS + 32 LDS + 192 LDS before.
+// ---------------------------------------------------------------------------
+constexpr int K5P_STAGES = 3;
+constexpr int K5P_PITCH = K5_KT + 4;  // floats per staged row
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem);
+    // src_bytes < 16: the remainder of the 16 bytes is zero-filled (0: nothing is read)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(K5_THREADS, 3)
+chroma_pipe_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs,
+                   const unsigned int *__restrict__ tile_prefix, int n_songs,
+                   const float *__restrict__ filt_table, const int *__restrict__ tuning_idx,
+                   double *__restrict__ tile_partials /*[tiles][10]*/, double *__restrict__ chroma_dbg) {
+    extern __shared__ __align__(16) unsigned char k5p_smem[];
+    float *s_s = reinterpret_cast<float *>(k5p_smem);                                   // [STAGES][256][PITCH]
+    float *s_w = s_s + K5P_STAGES * CH_TILE_FRAMES * K5P_PITCH;                         // [STAGES][16][12]
+    double *s_red = reinterpret_cast<double *>(s_w + K5P_STAGES * K5_KT * 12);          // [4][10]
+
+    const int tid = threadIdx.x;
+    const unsigned int item = blockIdx.x;
+    const int si = find_song(tile_prefix, n_songs, item);
+    const SongDesc sd = songs[si];
+    const int tile = (int)(item - tile_prefix[si]);
+    const int f0 = tile * CH_TILE_FRAMES;
+    const int nf = min(CH_TILE_FRAMES, (int)sd.n_c - f0);  // frames of this tile
+    // rows that exist in the spill: frames below n_c_comp (the rest are zero rows, utils.rs:27-31)
+    const int nrows = max(0, min(nf, (int)sd.n_c_comp - f0));
+    const float *W = filt_table + (size_t)tuning_idx[si] * CH_BINS * 12;
+    const float *S = mags + (size_t)((unsigned int)sd.mag_off + (unsigned int)f0) * CH_STRIDE;
+
+    // staging map: thread copies 16-byte chunk (tid & 3) of rows (tid >> 2) + 32 i, i = 0..7
+    const int st_c = tid & 3, st_r = tid >> 2;
+    auto issue = [&](int stage, int k0) {
+        float *dst = s_s + (size_t)stage * CH_TILE_FRAMES * K5P_PITCH + st_r * K5P_PITCH + 4 * st_c;
+        const float *src = S + (size_t)st_r * CH_STRIDE + k0 + 4 * st_c;
+#pragma unroll
+        for (int i = 0; i < CH_TILE_FRAMES / 32; i++)  // rows past nrows: nothing is read, zeros are written
+            cp_async16(dst + 32 * i * K5P_PITCH, src + (size_t)32 * i * CH_STRIDE, (st_r + 32 * i) < nrows ? 16 : 0);
+        // (the address of a skipped row still lies inside the spill: api.cu pads it by one tile of rows)
+        if (tid < K5_KT * 12 / 4)  // 48 chunks of weights
+            cp_async16(s_w + stage * K5_KT * 12 + 4 * tid, W + (size_t)k0 * 12 + 4 * tid, 16);
+    };
+
+    double acc0[12], acc1[12];  // frames tid and tid + 128
+#pragma unroll
+    for (int c = 0; c < 12; c++) { acc0[c] = 0.; acc1[c] = 0.; }
+
+    constexpr int N_STAGES_K = (CH_BINS - 1) / K5_KT;  // 256 full stages; bin 4096 is handled after the loop
+    issue(0, 0);
+    cp_async_commit();
+    issue(1, K5_KT);
+    cp_async_commit();
+#pragma unroll 1
+    for (int s = 0; s < N_STAGES_K; s++) {
+        cp_async_wait<K5P_STAGES - 2>();  // this thread's copies of stage s have landed
+        __syncthreads();                  // ... everyone's; and everyone is done with stage s - 1
+        if (s + K5P_STAGES - 1 < N_STAGES_K) issue((s + K5P_STAGES - 1) % K5P_STAGES, (s + K5P_STAGES - 1) * K5_KT);
+        cp_async_commit();  // (possibly empty: keeps the group count uniform)
+        const int buf = s % K5P_STAGES;
+        const float4 *va = reinterpret_cast<const float4 *>(s_s + (size_t)buf * CH_TILE_FRAMES * K5P_PITCH + tid * K5P_PITCH);
+        const float4 *vb = reinterpret_cast<const float4 *>(s_s + (size_t)buf * CH_TILE_FRAMES * K5P_PITCH + (tid + 128) * K5P_PITCH);
+        const float4 *wq = reinterpret_cast<const float4 *>(s_w + buf * K5_KT * 12);
+        float p0[12], p1[12];
+#pragma unroll
+        for (int c = 0; c < 12; c++) { p0[c] = 0.f; p1[c] = 0.f; }
+#pragma unroll
+        for (int g4 = 0; g4 < K5_KT / 4; g4++) {
+            const float4 a4 = va[g4], b4 = vb[g4];
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float a2 = av[j] * av[j], b2 = bv[j] * bv[j];  // spectrum.mapv_inplace(|x| x*x), chroma.rs:400
+                const float4 w0 = wq[(4 * g4 + j) * 3], w1 = wq[(4 * g4 + j) * 3 + 1], w2 = wq[(4 * g4 + j) * 3 + 2];
+                const float wv[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+                for (int c = 0; c < 12; c++) {
+                    p0[c] = fmaf(wv[c], a2, p0[c]);
+                    p1[c] = fmaf(wv[c], b2, p1[c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 12; c++) {
+            acc0[c] += (double)p0[c];
+            acc1[c] += (double)p1[c];
+        }
+    }
+    {   // bin 4096: a chunk of its own (the old tiling staged it with 15 zero bins: same sums)
+        const float a = (tid < nrows) ? __ldg(S + (size_t)tid * CH_STRIDE + (CH_BINS - 1)) : 0.f;
+        const float b = (tid + 128 < nrows) ? __ldg(S + (size_t)(tid + 128) * CH_STRIDE + (CH_BINS - 1)) : 0.f;
+        const float a2 = a * a, b2 = b * b;
+        const float *wl = W + (size_t)(CH_BINS - 1) * 12;
+#pragma unroll
+        for (int c = 0; c < 12; c++) {
+            const float w = __ldg(wl + c);
+            acc0[c] += (double)fmaf(w, a2, 0.f);
+            acc1[c] += (double)fmaf(w, b2, 0.f);
+        }
+    }
+    double feat[10];
+#pragma unroll
+    for (int t = 0; t < 10; t++) feat[t] = 0.;
+    if (tid < nf)
+        frame_interval_features(acc0, feat, chroma_dbg ? chroma_dbg + ((size_t)sd.c_tile_off * CH_TILE_FRAMES + f0 + tid) * 12 : nullptr);
+    if (tid + 128 < nf)
+        frame_interval_features(acc1, feat, chroma_dbg ? chroma_dbg + ((size_t)sd.c_tile_off * CH_TILE_FRAMES + f0 + tid + 128) * 12 : nullptr);
+    // sum the tile's frames (mean_axis over frames finishes in the summary kernel)
+#pragma unroll
+    for (int t = 0; t < 10; t++) {
+        double v = feat[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) s_red[(tid >> 5) * 10 + t] = v;
+    }
+    __syncthreads();
+    if (tid < 10) {
+        double v = 0.;
+#pragma unroll
+        for (int w = 0; w < K5_THREADS / 32; w++) v += s_red[w * 10 + tid];
+        tile_partials[((size_t)sd.c_tile_off + tile) * 10 + tid] = v;
+    }
+}
+constexpr size_t K5P_SMEM = (size_t)K5P_STAGES * CH_TILE_FRAMES * K5P_PITCH * 4 + (size_t)K5P_STAGES * K5_KT * 12 * 4 +
+                            (K5_THREADS / 32) * 10 * 8;
+
 // ---- launchers ---------------------------------------------------------------
 // frame_prefix counts groups of K3_FRAMES_PER_CTA (= 4) frames per song
 int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int *frame_prefix, int n_songs,
                     unsigned int total_frames, const float *hann, const cpx *tw1, const cpx *tw2,
                     const cpx *tw8192, float *mags, double *cand_mag, double *cand_pitch,
-                    unsigned int *cand_count, cudaStream_t st) {
+                    unsigned int *cand_count, int variant, cudaStream_t st) {
     if (total_frames == 0) return 0;
-    stft8192_kernel<<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw1, tw2,
-                                                         tw8192, mags, cand_mag, cand_pitch, cand_count);
+    if (variant & VARIANT_OLD_EPILOGUE)
+        stft8192_kernel<false><<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw1, tw2,
+                                                                    tw8192, mags, cand_mag, cand_pitch, cand_count);
+    else
+        stft8192_kernel<true><<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw1, tw2,
+                                                                   tw8192, mags, cand_mag, cand_pitch, cand_count);
     return 1;
 }
 
 int launch_tuning(const double *cand_mag, const double *cand_pitch, const unsigned int *cand_count,
-                  const SongDesc *songs, int n_songs, int *tuning_idx, cudaStream_t st) {
+                  const SongDesc *songs, int n_songs, int *tuning_idx, int variant, cudaStream_t st) {
     if (n_songs == 0) return 0;
-    tuning_kernel<<<n_songs, K4_THREADS, 0, st>>>(cand_mag, cand_pitch, cand_count, songs, tuning_idx);
+    if (variant & VARIANT_OLD_TUNING)
+        tuning_kernel<<<n_songs, K4_THREADS, 0, st>>>(cand_mag, cand_pitch, cand_count, songs, tuning_idx);
+    else
+        tuning_select_kernel<<<n_songs, K4_THREADS, 0, st>>>(cand_mag, cand_pitch, cand_count, songs, tuning_idx);
     return 1;
 }
 
 int launch_chroma(const float *mags, const SongDesc *songs, const unsigned int *tile_prefix, int n_songs,
                   unsigned int total_tiles, const float *filt_table, const int *tuning_idx,
-                  double *tile_partials, double *chroma_dbg, cudaStream_t st) {
+                  double *tile_partials, double *chroma_dbg, int variant, cudaStream_t st) {
     if (total_tiles == 0) return 0;
-    chroma_kernel<<<total_tiles, K5_THREADS, 0, st>>>(mags, songs, tile_prefix, n_songs, filt_table,
-                                                     tuning_idx, tile_partials, chroma_dbg);
+    if (variant & VARIANT_OLD_CHROMA) {
+        chroma_kernel<<<total_tiles, K5_THREADS, 0, st>>>(mags, songs, tile_prefix, n_songs, filt_table,
+                                                         tuning_idx, tile_partials, chroma_dbg);
+    } else {
+        static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in (per device, once)
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(chroma_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K5P_SMEM) != cudaSuccess)
+                return -1;
+            attr_set = true;
+        }
+        chroma_pipe_kernel<<<total_tiles, K5_THREADS, K5P_SMEM, st>>>(mags, songs, tile_prefix, n_songs, filt_table,
+                                                                     tuning_idx, tile_partials, chroma_dbg);
+    }
     return 1;
 }
 

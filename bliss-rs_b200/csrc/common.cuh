@@ -47,6 +47,15 @@ struct PvocTables {   // device pointers
     const cpx *twA;       // [16][32]  W512^(lane*k1)
 };
 
+// BLISS_B200_VARIANT (environment, read by bliss_b200_init): bit mask that switches a kernel back to its
+// previous implementation, for A/B timing and bisecting on the GPU box.  0 = current kernels.
+enum {
+    VARIANT_OLD_EPILOGUE = 1,  // stft8192_kernel: pass 3 through shared memory + one bin per untangle
+    VARIANT_OLD_TUNING = 2,    // tuning_kernel: 8-pass radix select
+    VARIANT_OLD_CHROMA = 4,    // chroma_kernel: thread-per-frame tiles staged through shared memory
+    VARIANT_OLD_ACF = 8,       // beattrack_kernel: one autocorrelation lag per thread, scalar loads
+};
+
 // Song lookup for flat work lists: largest s with prefix[s] <= item (prefix has n_songs+1
 // entries, prefix[n_songs] = total).  Starts from the proportional guess -- exact for equal-length
 // songs, where it costs one round trip instead of log2(n_songs) dependent loads -- and falls

@@ -28,9 +28,56 @@ __device__ __forceinline__ float approx_sqrtf(float x) {
 }
 #endif
 
-BLISS_HD cpx cadd(cpx a, cpx b) { return cpx{a.x + b.x, a.y + b.y}; }
-BLISS_HD cpx csub(cpx a, cpx b) { return cpx{a.x - b.x, a.y - b.y}; }
-BLISS_HD cpx cmul(cpx a, cpx b) { return cpx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+// ---- packed FP32 (sm_100a: add/sub/mul/fma .f32x2 -> FADD2 / FMUL2 / FFMA2) -----------------------
+// A complex value is a natural f32x2.  One packed instruction does the work of two scalar ones in ONE
+// issue slot, and ptxas folds half swaps, per-half negations and scalar broadcasts of the operands into
+// instruction modifiers (R.F32x2.LO_HI.NP, R.F32), so a radix-16 butterfly costs 81 FP instructions
+// instead of 162.  The FFT kernels are issue-bound (profiles/), not FP-pipe bound, so this is where
+// their time goes.  IEEE results per half are those of the scalar instructions.
+// Host build (tests/cpu_emul) and -DBLISS_NO_PACKED_FP: plain scalar code with the same meaning.
+#if defined(__CUDA_ARCH__) && !defined(BLISS_NO_PACKED_FP)
+#define BLISS_PACKED_FP 1
+__device__ __forceinline__ unsigned long long pk_(cpx a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ cpx up_(unsigned long long v) {
+    cpx r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ cpx padd(cpx a, cpx b) {  // (a.x + b.x, a.y + b.y)
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk_(a)), "l"(pk_(b)));
+    return up_(r);
+}
+__device__ __forceinline__ cpx psub(cpx a, cpx b) {  // (a.x - b.x, a.y - b.y)
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk_(a)), "l"(pk_(b)));
+    return up_(r);
+}
+__device__ __forceinline__ cpx pmul(cpx a, cpx b) {  // (a.x * b.x, a.y * b.y)
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk_(a)), "l"(pk_(b)));
+    return up_(r);
+}
+__device__ __forceinline__ cpx pfma(cpx a, cpx b, cpx c) {  // (a.x * b.x + c.x, a.y * b.y + c.y)
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk_(a)), "l"(pk_(b)), "l"(pk_(c)));
+    return up_(r);
+}
+#else
+BLISS_HD cpx padd(cpx a, cpx b) { return cpx{a.x + b.x, a.y + b.y}; }
+BLISS_HD cpx psub(cpx a, cpx b) { return cpx{a.x - b.x, a.y - b.y}; }
+BLISS_HD cpx pmul(cpx a, cpx b) { return cpx{a.x * b.x, a.y * b.y}; }
+BLISS_HD cpx pfma(cpx a, cpx b, cpx c) { return cpx{a.x * b.x + c.x, a.y * b.y + c.y}; }
+#endif
+
+BLISS_HD cpx cadd(cpx a, cpx b) { return padd(a, b); }
+BLISS_HD cpx csub(cpx a, cpx b) { return psub(a, b); }
+// a * b = b.x (a.x, a.y) + b.y (-a.y, a.x)
+BLISS_HD cpx cmul(cpx a, cpx b) { return pfma(a, cpx{b.x, b.x}, pmul(cpx{-a.y, a.x}, cpx{b.y, b.y})); }
 
 // cos(2*pi*k/32), k = 0..8 (f64-rounded-to-f32 literals)
 __host__ __device__ constexpr float cos32(int k) {
@@ -67,15 +114,15 @@ BLISS_HD cpx mul_tw(cpx v) {
         return cpx{-v.x, -v.y};
     } else if constexpr (k32 == 24) {  // +i
         return cpx{-v.y, v.x};
-    } else if constexpr (k32 == 4) {  // (1 - i)/sqrt2
+    } else if constexpr (k32 == 4) {  // (1 - i)/sqrt2:  h (x + y, y - x)
         constexpr float h = 0.70710678118654752f;
-        return cpx{(v.x + v.y) * h, (v.y - v.x) * h};
-    } else if constexpr (k32 == 12) {  // (-1 - i)/sqrt2
+        return pmul(padd(v, cpx{v.y, -v.x}), cpx{h, h});
+    } else if constexpr (k32 == 12) {  // (-1 - i)/sqrt2:  h (y - x, -x - y)
         constexpr float h = 0.70710678118654752f;
-        return cpx{(v.y - v.x) * h, -(v.x + v.y) * h};
+        return pmul(psub(cpx{v.y, -v.x}, v), cpx{h, h});
     } else {
         constexpr float c = cos32(k32), s = -sin32(k32);  // W = c + i s
-        return cpx{v.x * c - v.y * s, v.x * s + v.y * c};
+        return pfma(v, cpx{c, c}, pmul(cpx{-v.y, v.x}, cpx{s, s}));
     }
 }
 

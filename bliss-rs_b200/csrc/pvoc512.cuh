@@ -60,7 +60,8 @@ BLISS_HD void phase_b_fft(int lane, cpx (&u)[16]) {
 // final radix-2 between lane (0,k1) and lane (1,k1): `other` is the partner's value
 // of the same slot.  Even half keeps F0 + W F1 (k2 = k2'), odd half F0 - W F1 (k2 = k2'+16).
 BLISS_HD cpx phase_b_combine(int lane, cpx own, cpx other) {
-    return (lane >> 4) ? csub(other, own) : cadd(own, other);
+    const float sg = (lane >> 4) ? -1.f : 1.f;  // other + sg * own: exact, one FFMA2
+    return pfma(own, cpx{sg, sg}, other);
 }
 
 // bin index held in slot q of lane after the combine
@@ -76,14 +77,20 @@ BLISS_HD int bin_of(int lane, int q) {
 template <bool SCALE2 = false>
 BLISS_HD void untangle_mag(cpx zk, cpx zm, float &magA, float &magB) {
     const float h = SCALE2 ? 1.0f : 0.5f;
-    const float ar = h * (zk.x + zm.x), ai = h * (zk.y - zm.y);
-    const float br = h * (zk.y + zm.y), bi = h * (zm.x - zk.x);
+    // 2A = (zk.x + zm.x, zk.y - zm.y),  2B = (zk.y + zm.y, zm.x - zk.x)
+    cpx a = padd(zk, cpx{zm.x, -zm.y});
+    cpx b = padd(cpx{zk.y, -zk.x}, cpx{zm.y, zm.x});
+    if (!SCALE2) {
+        a = pmul(a, cpx{h, h});
+        b = pmul(b, cpx{h, h});
+    }
+    const cpx qa = pmul(a, a), qb = pmul(b, b);
 #ifdef __CUDA_ARCH__
-    magA = approx_sqrtf(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
-    magB = approx_sqrtf(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
+    magA = approx_sqrtf(__fadd_rn(qa.x, qa.y));
+    magB = approx_sqrtf(__fadd_rn(qb.x, qb.y));
 #else
-    magA = sqrtf(ar * ar + ai * ai);
-    magB = sqrtf(br * br + bi * bi);
+    magA = sqrtf(qa.x + qa.y);
+    magB = sqrtf(qb.x + qb.y);
 #endif
 }
 

@@ -69,6 +69,23 @@ BLISS_HD void pass3(int b, cpx *buf) {
 // padded position of Z[t + 256 m], t < 256, m < 16:  zbase(t) + m
 BLISS_HD int zbase(int t) { return 273 * (t & 15) + 17 * (t >> 4); }
 
+// pass 3 fused with the untangling: thread t transforms the block that ENDS UP holding its own
+// natural-order bins (block zbase(t) = logical elements 16 b + q with b = 16 (t & 15) + (t >> 4)),
+// so that afterwards v[bitrev(m)] = Z[t + 256 m] is already in its registers.  Only the upper half
+// (m = 8..15) goes back to shared memory: those are the mirror values Z[4096 - k] of the bins
+// k = t' + 256 m', m' < 8, that thread t' = 256 - t untangles (thread 0 mirrors onto itself and also
+// publishes m = 0).  Shared-memory traffic of pass 3 + epilogue: 16 loads + 8 stores + 8 loads per
+// thread instead of 16 + 16 + 32.
+BLISS_HD void pass3_regs(int t, cpx (&v)[16], cpx *buf) {
+    cpx *p = buf + zbase(t);
+#pragma unroll
+    for (int q = 0; q < 16; q++) v[q] = p[q];
+    fft_dif<16>(v);
+#pragma unroll
+    for (int m = 8; m < 16; m++) p[m] = v[bitrev(m, 4)];
+    if (t == 0) p[0] = v[0];
+}
+
 // generic accessor (CPU emulation test)
 BLISS_HD cpx z_value(const cpx *buf, int k) {
     return buf[pad(256 * (k & 15) + 16 * ((k >> 4) & 15) + (k >> 8))];
@@ -76,20 +93,35 @@ BLISS_HD cpx z_value(const cpx *buf, int k) {
 
 // |X[k]| from Z[k], Z[(4096-k)%4096] and w = W8192^k, as `(re*re + im*im).sqrt()` in f32
 // (src/utils.rs:57-60)
+BLISS_HD float sum_sq_sqrt_half(cpx x) {  // 0.5 * sqrt(x.x^2 + x.y^2), squares and sum un-fused
+    const cpx q = pmul(x, x);
+#ifdef __CUDA_ARCH__
+    return 0.5f * approx_sqrtf(__fadd_rn(q.x, q.y));
+#else
+    return 0.5f * sqrtf(q.x + q.y);
+#endif
+}
+
 BLISS_HD float untangle_mag(cpx zk, cpx zm, cpx w) {
     // E = (Zk + conj Zm)/2, O = (Zk - conj Zm)/2;  X = E - i w O
     // (the two factors 1/2 are applied once to the magnitude: exact, power of two)
-    const float er = zk.x + zm.x, ei = zk.y - zm.y;
-    const float orr = zk.x - zm.x, oi = zk.y + zm.y;
-    // w O
-    const float pr = w.x * orr - w.y * oi, pi = w.x * oi + w.y * orr;
+    const cpx e = padd(zk, cpx{zm.x, -zm.y});
+    const cpx o = padd(zk, cpx{-zm.x, zm.y});
+    const cpx p = cmul(o, w);
     // -i (pr + i pi) = pi - i pr
-    const float xr = er + pi, xi = ei - pr;
-#ifdef __CUDA_ARCH__
-    return 0.5f * approx_sqrtf(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi)));
-#else
-    return 0.5f * sqrtf(xr * xr + xi * xi);
-#endif
+    return sum_sq_sqrt_half(padd(e, cpx{p.y, -p.x}));
+}
+
+// Both members of a mirror pair from ONE load pair: |X[k]| and |X[4096 - k]| out of Z[k], Z[4096 - k]
+// and w = W8192^k.  With E, O, P = w O as in untangle_mag:  X[k] = E - i P,
+// X[4096 - k] = conj(E) - i conj(P)  (because W8192^(4096-k) = -conj w, O' = -conj O), whose magnitude
+// is that of E + i P.
+BLISS_HD void untangle_mag_pair(cpx zk, cpx zm, cpx w, float &mag_k, float &mag_m) {
+    const cpx e = padd(zk, cpx{zm.x, -zm.y});
+    const cpx o = padd(zk, cpx{-zm.x, zm.y});
+    const cpx p = cmul(o, w);
+    mag_k = sum_sq_sqrt_half(padd(e, cpx{p.y, -p.x}));  // (er + pi, ei - pr)
+    mag_m = sum_sq_sqrt_half(padd(e, cpx{-p.y, p.x}));  // (er - pi, ei + pr)
 }
 
 // reflect-padded sample (utils.rs:11-24): idx relative to the song, may be < 0 or >= n

@@ -159,7 +159,7 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
         cpx r[16];
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) {
-            r[n1] = cpx{win_a[n1] * s[n1], win_a[n1] * s[n1 + 4]};
+            r[n1] = pmul(cpx{s[n1], s[n1 + 4]}, cpx{win_a[n1], win_a[n1]});
             pka = fmaxf(pka, fabsf(r[n1].x));
             pkb = fmaxf(pkb, fabsf(r[n1].y));
         }

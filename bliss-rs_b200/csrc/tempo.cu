@@ -81,7 +81,7 @@ peakpick_kernel(const float *__restrict__ flux, const SongDesc *__restrict__ son
 // ------------------------------- K8 ----------------------------------------
 constexpr int BT_THREADS = 512;
 
-struct BtShared {
+struct __align__(16) BtShared {
     float df[512], dfrev[512], acf[512], phout[512];
     float dfwv[512];
     float acfout[128], rwv[128], gwv[128], out[128];
@@ -154,10 +154,10 @@ __device__ unsigned int get_timesig(const float *acf, int acflen, int gp) {
     return three > four ? 3u : 4u;
 }
 
-__global__ void __launch_bounds__(BT_THREADS, 4)
+__global__ void __launch_bounds__(BT_THREADS, 3)
 beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_energy,
                  const SongDesc *__restrict__ songs, float *__restrict__ bpm_list,
-                 float *__restrict__ tempo_feature, unsigned int *__restrict__ bpm_count) {
+                 float *__restrict__ tempo_feature, unsigned int *__restrict__ bpm_count, int scalar_acf) {
     __shared__ BtShared sh;
     const SongDesc sd = songs[blockIdx.x];
     const int tid = threadIdx.x;
@@ -212,8 +212,12 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
         const float gp_in = sh.gp;
         // dfrev = reverse(df * dfwv)
         sh.dfrev[winlen - 1 - tid] = sh.df[tid] * sh.dfwv[tid];
-        // vec_autocorr, aubio.rs:819-828
-        {
+        // vec_autocorr, aubio.rs:819-828:  acf[i] = sum_{j < 512-i} df[j] df[j+i] / (512 - i), each lag's sum in
+        // the reference's order (j ascending, un-fused multiply and add).  Thread t < 128 owns the four
+        // consecutive lags 4t..4t+3 and walks j in blocks of four: one broadcast float4 of df[j..j+3] and
+        // one float4 of df[4t+j+4..+7] per 16 multiply-adds (the sliding window df[4t+j..+6] stays in
+        // registers) instead of two scalar shared-memory loads per multiply-add.
+        if (scalar_acf) {  // VARIANT_OLD_ACF: one lag per thread, two scalar loads per multiply-add
             float tmp = 0.f;
             const float *a = sh.df, *b = sh.df + tid;
             const int cnt = winlen - tid;
@@ -227,8 +231,41 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
             }
             for (; j < cnt; j++) tmp += a[j] * b[j];
             sh.acf[tid] = tmp / (float)cnt;
+        } else if (tid < 128) {
+            const int i0 = 4 * tid;
+            const float4 *df4 = reinterpret_cast<const float4 *>(sh.df);
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const int nblk = 128 - tid;  // (512 - i0) / 4 blocks; the last one is partial for lags > i0
+            float4 bc = df4[tid];        // df[i0 + j .. i0 + j + 3], j = 0
+            for (int jq = 0; jq < nblk - 1; jq++) {
+                const float4 a = df4[jq];
+                const float4 bn = df4[tid + jq + 1];
+                const float av[4] = {a.x, a.y, a.z, a.w};
+                const float w[7] = {bc.x, bc.y, bc.z, bc.w, bn.x, bn.y, bn.z};
+                float pr[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int m = 0; m < 4; m++) pr[u][m] = av[u] * w[u + m];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int m = 0; m < 4; m++) acc[m] += pr[u][m];
+                bc = bn;
+            }
+            {   // last block: j = 508 - i0; lag i0 + m still has terms u = 0 .. 3 - m
+                const float4 a = df4[nblk - 1];
+                const float av[4] = {a.x, a.y, a.z, a.w};
+                const float w[4] = {bc.x, bc.y, bc.z, bc.w};
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int m = 0; m < 4; m++)
+                        if (u + m < 4) acc[m] += av[u] * w[u + m];
+            }
+#pragma unroll
+            for (int m = 0; m < 4; m++) sh.acf[i0 + m] = acc[m] / (float)(winlen - i0 - m);
         }
-        __syncthreads();
         // shift-invariant comb filterbank, general model (aubio.rs:992-1003)
         float myv = 0.f;
         if (tid < laglen) {
@@ -441,10 +478,11 @@ int launch_peakpick(const float *flux, const SongDesc *songs, const unsigned int
 }
 
 int launch_beattrack(const float *thr, const float *block_energy, const SongDesc *songs, int n_songs,
-                     float *bpm_list, float *tempo_feature, unsigned int *bpm_count, cudaStream_t st) {
+                     float *bpm_list, float *tempo_feature, unsigned int *bpm_count, int variant,
+                     cudaStream_t st) {
     if (n_songs == 0) return 0;
     beattrack_kernel<<<n_songs, BT_THREADS, 0, st>>>(thr, block_energy, songs, bpm_list, tempo_feature,
-                                                     bpm_count);
+                                                     bpm_count, (variant & VARIANT_OLD_ACF) ? 1 : 0);
     return 1;
 }
 

@@ -132,6 +132,52 @@ int main() {
         }
         printf("rfft8192 (4096 complex): max rel err %.3e\n", err);
         worst = fmax(worst, err);
+        // ---- fused pass 3 + pair epilogue (pass3_regs / untangle_mag_pair), thread by thread ----
+        {
+            std::vector<cpx> buf2(r8k::BUF_CPX);
+            for (int bb = 0; bb < 256; bb++) {
+                cpx v[16];
+                for (int q = 0; q < 16; q++) {
+                    const int nn = bb + 256 * q;
+                    v[q] = cpx{(float)a[2 * nn], (float)a[2 * nn + 1]};
+                }
+                r8k::pass1_store(bb, v, tw.data(), buf2.data());
+            }
+            for (int bb = 0; bb < 256; bb++) r8k::pass2(bb, tw2.data(), buf2.data());
+            static cpx regs[256][16];
+            // poison what pass3_regs does not publish, so that a read of an unpublished slot shows up
+            for (int t = 0; t < 256; t++) r8k::pass3_regs(t, regs[t], buf2.data());
+            for (int t = 0; t < 256; t++)
+                for (int m = (t == 0 ? 1 : 0); m < 8; m++) buf2[r8k::zbase(t) + m] = cpx{NAN, NAN};
+            std::vector<int> hit(4097, 0);
+            double err2 = 0;
+            for (int t = 0; t < 256; t++) {
+                const cpx *pm = buf2.data() + r8k::zbase((256 - t) & 255) + 15;
+                for (int M = 0; M < 8; M++) {
+                    const int k = t + 256 * M;
+                    const cpx zk = regs[t][bitrev(M, 4)];
+                    const cpx zm = (t == 0) ? buf2[(16 - M) & 15] : pm[-M];
+                    const cpx w = cmul(tw8[t], cpx{(float)cos(-2.0 * M_PI * M / 32.0), (float)sin(-2.0 * M_PI * M / 32.0)});
+                    float mk, mm;
+                    r8k::untangle_mag_pair(zk, zm, w, mk, mm);
+                    hit[k]++;
+                    hit[4096 - k]++;
+                    err2 = fmax(err2, fabs(mk - ma[k]) / scale);
+                    err2 = fmax(err2, fabs(mm - ma[4096 - k]) / scale);
+                }
+            }
+            {
+                const cpx z = regs[0][bitrev(8, 4)];
+                const float mg = r8k::untangle_mag(z, z, cpx{0.f, -1.f});
+                hit[2048]++;
+                err2 = fmax(err2, fabs(mg - ma[2048]) / scale);
+            }
+            for (int k = 0; k <= 4096; k++)
+                if (hit[k] != 1) { printf("pair epilogue: bin %d produced %d times\n", k, hit[k]); return 4; }
+            if (!(err2 == err2)) { printf("pair epilogue read an unpublished slot\n"); return 5; }
+            printf("rfft8192 fused pass3 + pair epilogue: max rel err %.3e\n", err2);
+            worst = fmax(worst, err2);
+        }
         std::vector<int> seen(r8k::BUF_CPX, 0);
         for (int i = 0; i < 4096; i++) {
             int p = r8k::pad(i);

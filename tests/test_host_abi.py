@@ -96,3 +96,21 @@ def test_decoder_trait_batches_errors_as_items(monkeypatch):
     assert [p for p, _ in got] == ["bad", "a", "b", "c"]
     assert isinstance(got[0][1], B.DecodingError) and isinstance(got[1][1], B.Song)
     assert calls == [2, 1]
+
+
+def test_fft_index_logic_on_host(tmp_path):
+    """tests/cpu_emul/emul_fft.cu runs the warp / CTA FFT passes of pvoc512.cuh and rfft8192.cuh (incl. the
+    fused pass 3 + mirror-pair epilogue) thread by thread on the host and compares with an f64 DFT."""
+    exe = str(tmp_path / "emul_fft")
+    src = os.path.join(ROOT, "tests", "cpu_emul", "emul_fft.cu")
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-w", "-o", exe, src])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "OK" in out.stdout
+
+
+def test_variant_mask_names_match_header():
+    """BLISS_B200_VARIANT bits (A/B switch back to a kernel's previous implementation) stay documented."""
+    txt = open(os.path.join(ROOT, "bliss-rs_b200", "csrc", "common.cuh")).read()
+    for name in ("VARIANT_OLD_EPILOGUE = 1", "VARIANT_OLD_TUNING = 2", "VARIANT_OLD_CHROMA = 4", "VARIANT_OLD_ACF = 8"):
+        assert name in txt
