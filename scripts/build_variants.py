@@ -8,13 +8,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "bliss-rs_b200", "csrc")
 OUT = os.path.join(ROOT, "bliss-rs_b200", "variants")
-SOURCES = ["spectral.cu", "tempo.cu", "chroma.cu", "finalize.cu", "distance.cu", "api.cu"]
+SOURCES = ["spectral.cu", "tempo.cu", "chroma.cu", "finalize.cu", "distance.cu", "gather.cu", "wave_setup.cu", "api.cu"]
 BASE = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
         "-Wno-deprecated-gpu-targets"]
 
 VARIANTS = {
-    "k1mb3": ["-DK1_MINBLOCKS=3"],
-    "k1mb4": ["-DK1_MINBLOCKS=4"],
+    "nopacked": ["-DBLISS_NO_PACKED_FP"],  # scalar FADD/FMUL/FFMA butterflies instead of the f32x2 forms
 }
 
 
