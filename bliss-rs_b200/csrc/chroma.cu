@@ -136,11 +136,18 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     const float *x = pcm + sd.pcm_off;
     const int n = (int)sd.n;
     const unsigned int mag_row0 = (unsigned int)sd.mag_off;  // spill rows of a wave stay far below 2^32
+    const int fend = min(fbase + K3_FRAMES_PER_CTA, (int)sd.n_c_comp);
 #pragma unroll 1
-    for (int f = fbase; f < min(fbase + K3_FRAMES_PER_CTA, (int)sd.n_c_comp); f++) {
+    for (int f = fbase; f < fend; f++) {
     // the frame covers samples s0 .. s0+8191 of the reflect-padded song (utils.rs:11-24, :44-47)
     const int s0 = CH_HOP * f - 4096;
     const bool interior = (s0 >= 0) && (s0 + 8191 < n);
+    // The next frame shares 5987 of its 8192 samples with this one; the 2205 new ones (70 lines of 128 B)
+    // are requested into L2 now, a whole frame time before its loads need them.
+    if (tid < 70 && f + 1 < fend) {
+        const int nx = s0 + 8192 + 32 * tid;
+        if (nx < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + nx));
+    }
 
     // pass 1 straight from global memory: z[nn] = w[2nn] x[2nn] + i w[2nn+1] x[2nn+1], nn = tid + 256 q
     {

@@ -53,7 +53,8 @@ enum {
     VARIANT_OLD_EPILOGUE = 1,  // stft8192_kernel: pass 3 through shared memory + one bin per untangle
     VARIANT_OLD_TUNING = 2,    // tuning_kernel: 8-pass radix select
     VARIANT_OLD_CHROMA = 4,    // chroma_kernel: thread-per-frame tiles staged through shared memory
-    VARIANT_OLD_ACF = 8,       // beattrack_kernel: one autocorrelation lag per thread, scalar loads
+    VARIANT_OLD_ACF = 8,       // beattrack_kernel: one autocorrelation lag at a time, scalar loads
+    VARIANT_BT512 = 16,        // beattrack_kernel: 512 threads per song (3 songs per SM) instead of 128 (8 per SM)
 };
 
 // Song lookup for flat work lists: largest s with prefix[s] <= item (prefix has n_songs+1

@@ -135,21 +135,12 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
     {
         const int base = 256 * jstart - 384 + lane;
 #pragma unroll
-        for (int m = 0; m < 12; m++) {
-            const int idx = base + 32 * m;
-            s[m + 8] = (idx >= 0 && idx < n) ? __ldg(x + idx) : 0.f;
+        for (int m = 0; m < 20; m++) {
+            const int idx = base + 32 * m;  // rows 12..19 are >= 0 and < n for every valid pair
+            s[m] = (idx >= 0 && idx < n) ? __ldg(x + idx) : 0.f;
         }
     }
     for (int j = jstart; j < j1; j++) {
-        // slide the window by 256 samples and fetch the 8 new rows
-#pragma unroll
-        for (int m = 0; m < 12; m++) s[m] = s[m + 8];
-        {
-            const int base = 256 * j - 384 + lane + 32 * 12;  // >= 0 for every j; < n for valid pairs except j < 1
-            const float *px = x + base;  // 256 j + lane + 32 m <= 256 j + 255 < n for every pair j < n_t
-#pragma unroll
-            for (int m = 0; m < 8; m++) s[12 + m] = __ldg(px + 32 * m);
-        }
         // Two real frames ride one complex FFT (A in re, B in im); untangling leaks
         // eps*max(|A|,|B|) of rounding noise into the weaker frame.  B is therefore pre-scaled by a
         // power of two (exact) to A's level and scaled back afterwards, and a frame whose windowed
@@ -162,6 +153,16 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
             r[n1] = pmul(cpx{s[n1], s[n1 + 4]}, cpx{win_a[n1], win_a[n1]});
             pka = fmaxf(pka, fabsf(r[n1].x));
             pkb = fmaxf(pkb, fabsf(r[n1].y));
+        }
+        // slide the window by 256 samples and fetch the 8 new rows of the NEXT pair now: the loads are in
+        // flight during this pair's FFT instead of stalling the window multiply at the top of the loop
+        // (ncu: 10 % of the kernel's stall samples sat on that first multiply)
+#pragma unroll
+        for (int m = 0; m < 12; m++) s[m] = s[m + 8];
+        if (j + 1 < j1) {
+            const float *px = x + 256 * (j + 1) - 384 + lane + 32 * 12;  // 256 (j+1) + lane + 32 m < n for j + 1 < n_t
+#pragma unroll
+            for (int m = 0; m < 8; m++) s[12 + m] = __ldg(px + 32 * m);
         }
         const unsigned int ua = __reduce_max_sync(0xffffffffu, __float_as_uint(pka));
         const unsigned int ub = __reduce_max_sync(0xffffffffu, __float_as_uint(pkb));

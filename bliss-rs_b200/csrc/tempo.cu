@@ -10,8 +10,7 @@
 //
 // K8 is one CTA per song: the state machine is sequential over ~n_t/128 cycles,
 // every cycle's autocorrelation / comb filterbank / phase histogram is spread over
-// the CTA with one thread per output element, keeping each element's f32
-// accumulation order identical to the reference's loops.
+// the CTA, keeping each element's f32 accumulation order identical to the reference's loops.
 #include "common.cuh"
 
 namespace bliss {
@@ -79,8 +78,12 @@ peakpick_kernel(const float *__restrict__ flux, const SongDesc *__restrict__ son
 }
 
 // ------------------------------- K8 ----------------------------------------
-constexpr int BT_THREADS = 512;
-
+// BT threads per song.  Every phase is written as a loop over its 512 / 256 / 128 elements with stride BT,
+// so the same code runs with one element per thread (BT = 512, the previous layout, kept as
+// VARIANT_BT512) or with 128 threads and up to four elements each (current): the kernel is a chain of
+// ~17 barrier-separated, latency-bound phases per cycle, most of them 128 wide or single-threaded, so what
+// counts is how many songs are resident per SM (8 CTAs of 128 threads instead of 3 of 512) and how
+// cheap a barrier is, not how wide one song runs.
 struct __align__(16) BtShared {
     float df[512], dfrev[512], acf[512], phout[512];
     float dfwv[512];
@@ -101,7 +104,9 @@ struct __align__(16) BtShared {
 };
 
 // aubio.rs:787-799 vec_max_elem: last index of the maximum, 0.0 is the floor
-// (returns 0 when every element is negative).  All threads must call.
+// (returns 0 when every element is negative).  Each thread brings the best (value, index) of its own
+// elements (ties: larger index); all threads must call.
+template <int BT>
 __device__ int block_max_elem(BtShared &sh, float v, int idx, bool active) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float bv = active ? v : -INFINITY;
@@ -117,7 +122,7 @@ __device__ int block_max_elem(BtShared &sh, float v, int idx, bool active) {
     if (threadIdx.x == 0) {
         float mv = sh.red_v[0];
         int mi = sh.red_i[0];
-        for (int w = 1; w < BT_THREADS / 32; w++) {
+        for (int w = 1; w < BT / 32; w++) {
             if (sh.red_v[w] > mv || (sh.red_v[w] == mv && sh.red_i[w] > mi)) { mv = sh.red_v[w]; mi = sh.red_i[w]; }
         }
         sh.maxidx = (mv >= 0.f && mi >= 0) ? mi : 0;
@@ -154,10 +159,12 @@ __device__ unsigned int get_timesig(const float *acf, int acflen, int gp) {
     return three > four ? 3u : 4u;
 }
 
-__global__ void __launch_bounds__(BT_THREADS, 3)
+template <int BT>
+__global__ void __launch_bounds__(BT, BT == 512 ? 3 : 8)
 beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_energy,
                  const SongDesc *__restrict__ songs, float *__restrict__ bpm_list,
                  float *__restrict__ tempo_feature, unsigned int *__restrict__ bpm_count, int scalar_acf) {
+    static_assert(BT >= 128 && BT <= 512 && BT % 32 == 0, "128-wide phases run as `if (tid < 128)`");
     __shared__ BtShared sh;
     const SongDesc sd = songs[blockIdx.x];
     const int tid = threadIdx.x;
@@ -177,7 +184,7 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
     const unsigned int rayparam_u = (unsigned int)rayparam_f;
     {
         const float dfwvnorm = expf((logf(2.0f) / rayparam_f) * (float)(winlen + 2));
-        sh.dfwv[tid] = expf((logf(2.0f) / rayparam_f) * (float)(tid + 1)) / dfwvnorm;
+        for (int e = tid; e < winlen; e += BT) sh.dfwv[e] = expf((logf(2.0f) / rayparam_f) * (float)(e + 1)) / dfwvnorm;
         if (tid < laglen) {
             const float i_f = (float)(tid + 1);
             const float r2 = rayparam_f * rayparam_f;
@@ -185,7 +192,7 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
             sh.gwv[tid] = 0.f;
             sh.out[tid] = 0.f;
         }
-        if (tid < 2 * laglen) sh.phwv[tid] = 1.0f;
+        for (int e = tid; e < 2 * laglen; e += BT) sh.phwv[e] = 1.0f;
         if (tid == 0) {
             sh.timesig = 0; sh.lastbeat = 0.f; sh.counter = 0; sh.flagstep = 0;
             sh.gp = 0.f; sh.bp = 0.f; sh.rp = 1.0f; sh.rp1 = 0.f; sh.rp2 = 0.f;
@@ -198,9 +205,9 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
     for (int c = 1; c <= cycles; c++) {
         // dfframe[j] = DD[128c - 512 + j], DD[u] = thr[u-1] (u >= 1), 0 otherwise:
         // the very first thresholded value lands in dfframe[385] (blockpos pre-increment)
-        {
-            const int u = 128 * c - 512 + tid;
-            sh.df[tid] = (u >= 1) ? D[u - 1] : 0.f;
+        for (int e = tid; e < winlen; e += BT) {
+            const int u = 128 * c - 512 + e;
+            sh.df[e] = (u >= 1) ? D[u - 1] : 0.f;
         }
         __syncthreads();
         const unsigned int timesig0 = sh.timesig;
@@ -211,61 +218,66 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
         // barriers and desynchronise the CTA (seen as run-to-run tempo flips on 2-3 % of 1024 songs).
         const float gp_in = sh.gp;
         // dfrev = reverse(df * dfwv)
-        sh.dfrev[winlen - 1 - tid] = sh.df[tid] * sh.dfwv[tid];
+        for (int e = tid; e < winlen; e += BT) sh.dfrev[winlen - 1 - e] = sh.df[e] * sh.dfwv[e];
         // vec_autocorr, aubio.rs:819-828:  acf[i] = sum_{j < 512-i} df[j] df[j+i] / (512 - i), each lag's sum in
-        // the reference's order (j ascending, un-fused multiply and add).  Thread t < 128 owns the four
-        // consecutive lags 4t..4t+3 and walks j in blocks of four: one broadcast float4 of df[j..j+3] and
-        // one float4 of df[4t+j+4..+7] per 16 multiply-adds (the sliding window df[4t+j..+6] stays in
-        // registers) instead of two scalar shared-memory loads per multiply-add.
-        if (scalar_acf) {  // VARIANT_OLD_ACF: one lag per thread, two scalar loads per multiply-add
-            float tmp = 0.f;
-            const float *a = sh.df, *b = sh.df + tid;
-            const int cnt = winlen - tid;
-            int j = 0;
-            for (; j + 8 <= cnt; j += 8) {  // products first (independent), then the ordered adds
-                float pr[8];
+        // the reference's order (j ascending, un-fused multiply and add).
+        if (scalar_acf) {  // VARIANT_OLD_ACF: one lag at a time, two scalar loads per multiply-add
+            for (int lag = tid; lag < winlen; lag += BT) {
+                float tmp = 0.f;
+                const float *a = sh.df, *b = sh.df + lag;
+                const int cnt = winlen - lag;
+                int j = 0;
+                for (; j + 8 <= cnt; j += 8) {  // products first (independent), then the ordered adds
+                    float pr[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) pr[u] = a[j + u] * b[j + u];
+                    for (int u = 0; u < 8; u++) pr[u] = a[j + u] * b[j + u];
 #pragma unroll
-                for (int u = 0; u < 8; u++) tmp += pr[u];
+                    for (int u = 0; u < 8; u++) tmp += pr[u];
+                }
+                for (; j < cnt; j++) tmp += a[j] * b[j];
+                sh.acf[lag] = tmp / (float)cnt;
             }
-            for (; j < cnt; j++) tmp += a[j] * b[j];
-            sh.acf[tid] = tmp / (float)cnt;
-        } else if (tid < 128) {
-            const int i0 = 4 * tid;
-            const float4 *df4 = reinterpret_cast<const float4 *>(sh.df);
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            const int nblk = 128 - tid;  // (512 - i0) / 4 blocks; the last one is partial for lags > i0
-            float4 bc = df4[tid];        // df[i0 + j .. i0 + j + 3], j = 0
-            for (int jq = 0; jq < nblk - 1; jq++) {
-                const float4 a = df4[jq];
-                const float4 bn = df4[tid + jq + 1];
-                const float av[4] = {a.x, a.y, a.z, a.w};
-                const float w[7] = {bc.x, bc.y, bc.z, bc.w, bn.x, bn.y, bn.z};
-                float pr[4][4];
+        } else {
+            // Thread t < 128 owns the four consecutive lags 4t..4t+3 and walks j in blocks of four: one
+            // broadcast float4 of df[j..j+3] and one float4 of df[4t+j+4..+7] per 16 multiply-adds (the
+            // sliding window df[4t+j..+6] stays in registers) instead of two scalar loads per multiply-add.
+            for (int t = tid; t < 128; t += BT) {
+                const int i0 = 4 * t;
+                const float4 *df4 = reinterpret_cast<const float4 *>(sh.df);
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const int nblk = 128 - t;  // (512 - i0) / 4 blocks; the last one is partial for lags > i0
+                float4 bc = df4[t];        // df[i0 + j .. i0 + j + 3], j = 0
+                for (int jq = 0; jq < nblk - 1; jq++) {
+                    const float4 a = df4[jq];
+                    const float4 bn = df4[t + jq + 1];
+                    const float av[4] = {a.x, a.y, a.z, a.w};
+                    const float w[7] = {bc.x, bc.y, bc.z, bc.w, bn.x, bn.y, bn.z};
+                    float pr[4][4];
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+                    for (int u = 0; u < 4; u++)
 #pragma unroll
-                    for (int m = 0; m < 4; m++) pr[u][m] = av[u] * w[u + m];
+                        for (int m = 0; m < 4; m++) pr[u][m] = av[u] * w[u + m];
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+                    for (int u = 0; u < 4; u++)
 #pragma unroll
-                    for (int m = 0; m < 4; m++) acc[m] += pr[u][m];
-                bc = bn;
+                        for (int m = 0; m < 4; m++) acc[m] += pr[u][m];
+                    bc = bn;
+                }
+                {   // last block: j = 508 - i0; lag i0 + m still has terms u = 0 .. 3 - m
+                    const float4 a = df4[nblk - 1];
+                    const float av[4] = {a.x, a.y, a.z, a.w};
+                    const float w[4] = {bc.x, bc.y, bc.z, bc.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+#pragma unroll
+                        for (int m = 0; m < 4; m++)
+                            if (u + m < 4) acc[m] += av[u] * w[u + m];
+                }
+#pragma unroll
+                for (int m = 0; m < 4; m++) sh.acf[i0 + m] = acc[m] / (float)(winlen - i0 - m);
             }
-            {   // last block: j = 508 - i0; lag i0 + m still has terms u = 0 .. 3 - m
-                const float4 a = df4[nblk - 1];
-                const float av[4] = {a.x, a.y, a.z, a.w};
-                const float w[4] = {bc.x, bc.y, bc.z, bc.w};
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-#pragma unroll
-                    for (int m = 0; m < 4; m++)
-                        if (u + m < 4) acc[m] += av[u] * w[u + m];
-            }
-#pragma unroll
-            for (int m = 0; m < 4; m++) sh.acf[i0 + m] = acc[m] / (float)(winlen - i0 - m);
         }
+        __syncthreads();  // acf complete before the comb filterbank reads arbitrary lags
         // shift-invariant comb filterbank, general model (aubio.rs:992-1003)
         float myv = 0.f;
         if (tid < laglen) {
@@ -282,7 +294,7 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
             myv = acc;
         }
         __syncthreads();
-        int maxindex = block_max_elem(sh, myv, tid, tid < laglen);
+        int maxindex = block_max_elem<BT>(sh, myv, tid, tid < laglen);
         if (tid == 0) {
             if (maxindex > 0 && maxindex < laglen - 1) sh.rp = quadratic_peak_pos(sh.acfout, laglen, maxindex);
             else sh.rp = (float)rayparam_u;
@@ -304,7 +316,7 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
             __syncthreads();
             if (tid < laglen) sh.acfout[tid] = acc;
             __syncthreads();
-            maxindex = block_max_elem(sh, acc, tid, tid < laglen);
+            maxindex = block_max_elem<BT>(sh, acc, tid, tid < laglen);
         }
         if (tid == 0) {
             int counter = sh.counter;
@@ -357,12 +369,13 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
                 const float diff = (float)(tid + 1) - gp;
                 sh.gwv[tid] = expf(-0.5f * diff * diff / (g_var * g_var));
             }
-            if (tid < 2 * laglen) {
-                if (mode == 1 && sh.phase_gauss) {
-                    const float diff = 1.0f + (float)tid - (float)step + lastbeat;
-                    sh.phwv[tid] = expf(-0.5f * diff * diff / (bp_pre / 8.0f));
+            const bool gauss = (mode == 1 && sh.phase_gauss);
+            for (int e = tid; e < 2 * laglen; e += BT) {
+                if (gauss) {
+                    const float diff = 1.0f + (float)e - (float)step + lastbeat;
+                    sh.phwv[e] = expf(-0.5f * diff * diff / (bp_pre / 8.0f));
                 } else {
-                    sh.phwv[tid] = 1.0f;
+                    sh.phwv[e] = 1.0f;
                 }
             }
         }
@@ -380,17 +393,22 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
         } else {
             // beat phase, aubio.rs:1026-1057
             const int kmax = (int)floorf((float)winlen / bp);
-            float ph = 0.f;
-            if ((float)tid < bp) {
-                for (int k = 0; k < kmax; k++) {
-                    const int idx = tid + (int)floorf(bp * (float)k + 0.5f);
-                    if (idx < winlen) ph += sh.dfrev[idx];
+            float best_v = -INFINITY;
+            int best_i = -1;
+            for (int e = tid; e < winlen; e += BT) {
+                float ph = 0.f;
+                if ((float)e < bp) {
+                    for (int k = 0; k < kmax; k++) {
+                        const int idx = e + (int)floorf(bp * (float)k + 0.5f);
+                        if (idx < winlen) ph += sh.dfrev[idx];
+                    }
                 }
+                if (e < 2 * laglen) ph *= sh.phwv[e];
+                sh.phout[e] = ph;
+                if (ph >= best_v) { best_v = ph; best_i = e; }  // e ascends: ties keep the larger index
             }
-            if (tid < 2 * laglen) ph *= sh.phwv[tid];
-            sh.phout[tid] = ph;
             __syncthreads();
-            maxindex = block_max_elem(sh, ph, tid, true);
+            maxindex = block_max_elem<BT>(sh, best_v, best_i, true);
             if (tid < step) sh.out[tid] = 0.f;
             __syncthreads();
             if (tid == 0) {
@@ -451,7 +469,7 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
     const int r_lo = (nb - 1) / 2, r_hi = nb / 2;  // floor/ceil((nb-1)/2)
     if (tid == 0) { sh.red_v[0] = 0.f; sh.red_v[1] = 0.f; }
     __syncthreads();
-    for (int i = tid; i < nb; i += BT_THREADS) {
+    for (int i = tid; i < nb; i += BT) {
         const float v = bpms[i];
         int rank = 0;
         for (int k = 0; k < nb; k++) {
@@ -481,8 +499,13 @@ int launch_beattrack(const float *thr, const float *block_energy, const SongDesc
                      float *bpm_list, float *tempo_feature, unsigned int *bpm_count, int variant,
                      cudaStream_t st) {
     if (n_songs == 0) return 0;
-    beattrack_kernel<<<n_songs, BT_THREADS, 0, st>>>(thr, block_energy, songs, bpm_list, tempo_feature,
-                                                     bpm_count, (variant & VARIANT_OLD_ACF) ? 1 : 0);
+    const int scalar_acf = (variant & VARIANT_OLD_ACF) ? 1 : 0;
+    if (variant & VARIANT_BT512)
+        beattrack_kernel<512><<<n_songs, 512, 0, st>>>(thr, block_energy, songs, bpm_list, tempo_feature, bpm_count,
+                                                       scalar_acf);
+    else
+        beattrack_kernel<128><<<n_songs, 128, 0, st>>>(thr, block_energy, songs, bpm_list, tempo_feature, bpm_count,
+                                                       scalar_acf);
     return 1;
 }
 

@@ -186,6 +186,7 @@ class Song:
     duration: float = 0.0
     analysis: Optional[Analysis] = None
     features_version: FeaturesVersion = FeaturesVersion.Version2
+    cue_info: Optional[object] = None  # library.CueInfo when the song was cut out of a CUE sheet (src/song/mod.rs:71-76)
 
     @staticmethod
     def analyze(sample_array) -> Analysis:

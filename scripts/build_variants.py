@@ -14,6 +14,7 @@ BASE = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17
 
 VARIANTS = {
     "nopacked": ["-DBLISS_NO_PACKED_FP"],  # scalar FADD/FMUL/FFMA butterflies instead of the f32x2 forms
+    "k1mb3": ["-DK1_MINBLOCKS=3"],          # pvoc512_kernel at 3 CTAs/SM (80 registers, ~100 B of spills)
 }
 
 
