@@ -807,7 +807,10 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
 // Per 16-bin stage and thread: 8 cp.async + 8 LDS.128 (values) + 48 LDS.128 (weights, broadcast)
 // for 384 FMA, against 32 LDG + 32 STS + 32 LDS + 192 LDS before.
 // ---------------------------------------------------------------------------
-constexpr int K5P_STAGES = 3;
+#ifndef K5P_STAGES_N
+#define K5P_STAGES_N 3
+#endif
+constexpr int K5P_STAGES = K5P_STAGES_N;
 constexpr int K5P_PITCH = K5_KT + 4;  // floats per staged row
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
@@ -819,7 +822,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(K5_THREADS, 3)
+__global__ void __launch_bounds__(K5_THREADS, K5P_STAGES_N == 3 ? 3 : 2)
 chroma_pipe_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs,
                    const unsigned int *__restrict__ tile_prefix, int n_songs,
                    const float *__restrict__ filt_table, const int *__restrict__ tuning_idx,
@@ -845,10 +848,17 @@ chroma_pipe_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ 
     const int st_c = tid & 3, st_r = tid >> 2;
     auto issue = [&](int stage, int k0) {
         float *dst = s_s + (size_t)stage * CH_TILE_FRAMES * K5P_PITCH + st_r * K5P_PITCH + 4 * st_c;
+#ifdef K5P_FAKE_CONTIG  // timing experiment only (wrong results): what if a stage were one contiguous 16 KB block?
+        const float *src = S + (size_t)k0 * CH_TILE_FRAMES + st_r * K5_KT + 4 * st_c;
+#pragma unroll
+        for (int i = 0; i < CH_TILE_FRAMES / 32; i++)
+            cp_async16(dst + 32 * i * K5P_PITCH, src + (size_t)32 * i * K5_KT, (st_r + 32 * i) < nrows ? 16 : 0);
+#else
         const float *src = S + (size_t)st_r * CH_STRIDE + k0 + 4 * st_c;
 #pragma unroll
         for (int i = 0; i < CH_TILE_FRAMES / 32; i++)  // rows past nrows: nothing is read, zeros are written
             cp_async16(dst + 32 * i * K5P_PITCH, src + (size_t)32 * i * CH_STRIDE, (st_r + 32 * i) < nrows ? 16 : 0);
+#endif
         // (the address of a skipped row still lies inside the spill: api.cu pads it by one tile of rows)
         if (tid < K5_KT * 12 / 4)  // 48 chunks of weights
             cp_async16(s_w + stage * K5_KT * 12 + 4 * tid, W + (size_t)k0 * 12 + 4 * tid, 16);
@@ -859,10 +869,11 @@ chroma_pipe_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ 
     for (int c = 0; c < 12; c++) { acc0[c] = 0.; acc1[c] = 0.; }
 
     constexpr int N_STAGES_K = (CH_BINS - 1) / K5_KT;  // 256 full stages; bin 4096 is handled after the loop
-    issue(0, 0);
-    cp_async_commit();
-    issue(1, K5_KT);
-    cp_async_commit();
+#pragma unroll
+    for (int p = 0; p < K5P_STAGES - 1; p++) {
+        issue(p, p * K5_KT);
+        cp_async_commit();
+    }
 #pragma unroll 1
     for (int s = 0; s < N_STAGES_K; s++) {
         cp_async_wait<K5P_STAGES - 2>();  // this thread's copies of stage s have landed
@@ -873,29 +884,28 @@ chroma_pipe_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ 
         const float4 *va = reinterpret_cast<const float4 *>(s_s + (size_t)buf * CH_TILE_FRAMES * K5P_PITCH + tid * K5P_PITCH);
         const float4 *vb = reinterpret_cast<const float4 *>(s_s + (size_t)buf * CH_TILE_FRAMES * K5P_PITCH + (tid + 128) * K5P_PITCH);
         const float4 *wq = reinterpret_cast<const float4 *>(s_w + buf * K5_KT * 12);
-        float p0[12], p1[12];
+        // (frame a, frame b) ride one FFMA2 per chroma row: .x = frame tid, .y = frame tid + 128; each half is
+        // exactly the scalar fmaf(w, s^2, p) of the previous kernel
+        cpx p[12];
 #pragma unroll
-        for (int c = 0; c < 12; c++) { p0[c] = 0.f; p1[c] = 0.f; }
+        for (int c = 0; c < 12; c++) p[c] = cpx{0.f, 0.f};
 #pragma unroll
         for (int g4 = 0; g4 < K5_KT / 4; g4++) {
             const float4 a4 = va[g4], b4 = vb[g4];
             const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float a2 = av[j] * av[j], b2 = bv[j] * bv[j];  // spectrum.mapv_inplace(|x| x*x), chroma.rs:400
+                const cpx sq{av[j] * av[j], bv[j] * bv[j]};  // spectrum.mapv_inplace(|x| x*x), chroma.rs:400
                 const float4 w0 = wq[(4 * g4 + j) * 3], w1 = wq[(4 * g4 + j) * 3 + 1], w2 = wq[(4 * g4 + j) * 3 + 2];
                 const float wv[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
-                for (int c = 0; c < 12; c++) {
-                    p0[c] = fmaf(wv[c], a2, p0[c]);
-                    p1[c] = fmaf(wv[c], b2, p1[c]);
-                }
+                for (int c = 0; c < 12; c++) p[c] = pfma(cpx{wv[c], wv[c]}, sq, p[c]);
             }
         }
 #pragma unroll
         for (int c = 0; c < 12; c++) {
-            acc0[c] += (double)p0[c];
-            acc1[c] += (double)p1[c];
+            acc0[c] += (double)p[c].x;
+            acc1[c] += (double)p[c].y;
         }
     }
     {   // bin 4096: a chunk of its own (the old tiling staged it with 15 zero bins: same sums)
