@@ -848,17 +848,10 @@ chroma_pipe_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ 
     const int st_c = tid & 3, st_r = tid >> 2;
     auto issue = [&](int stage, int k0) {
         float *dst = s_s + (size_t)stage * CH_TILE_FRAMES * K5P_PITCH + st_r * K5P_PITCH + 4 * st_c;
-#ifdef K5P_FAKE_CONTIG  // timing experiment only (wrong results): what if a stage were one contiguous 16 KB block?
-        const float *src = S + (size_t)k0 * CH_TILE_FRAMES + st_r * K5_KT + 4 * st_c;
-#pragma unroll
-        for (int i = 0; i < CH_TILE_FRAMES / 32; i++)
-            cp_async16(dst + 32 * i * K5P_PITCH, src + (size_t)32 * i * K5_KT, (st_r + 32 * i) < nrows ? 16 : 0);
-#else
         const float *src = S + (size_t)st_r * CH_STRIDE + k0 + 4 * st_c;
 #pragma unroll
         for (int i = 0; i < CH_TILE_FRAMES / 32; i++)  // rows past nrows: nothing is read, zeros are written
             cp_async16(dst + 32 * i * K5P_PITCH, src + (size_t)32 * i * CH_STRIDE, (st_r + 32 * i) < nrows ? 16 : 0);
-#endif
         // (the address of a skipped row still lies inside the spill: api.cu pads it by one tile of rows)
         if (tid < K5_KT * 12 / 4)  // 48 chunks of weights
             cp_async16(s_w + stage * K5_KT * 12 + 4 * tid, W + (size_t)k0 * 12 + 4 * tid, 16);

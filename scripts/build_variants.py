@@ -15,7 +15,6 @@ BASE = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17
 VARIANTS = {
     "nopacked": ["-DBLISS_NO_PACKED_FP"],  # scalar FADD/FMUL/FFMA butterflies instead of the f32x2 forms
     "k5s4": ["-DK5P_STAGES_N=4"],           # chroma_pipe_kernel: 4-stage ring, 2 CTAs/SM
-    "k5contig": ["-DK5P_FAKE_CONTIG"],      # timing experiment: chroma stages read as contiguous 16 KB blocks (wrong results)
 }
 
 
