@@ -120,7 +120,7 @@ def algorithmic_bytes_per_song():
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU algorithm (oracle port; the Rust crate cannot be built
-    here) on all host threads.  One step = `cores` songs, one per worker thread, scheduled
+    here) on all host threads.  One step = 4 x `cores` songs, contiguous chunks per worker thread, scheduled
     like Decoder::analyze_paths_with_options (src/song/decoder.rs:278-332)."""
     if rank != 0:
         return
@@ -128,7 +128,7 @@ def run_reference(args, rank, world):
     from bliss_rs_b200 import synth
     from oracle import oracle as O
     cores = os.cpu_count() or 1
-    n_songs = cores
+    n_songs = 4 * cores  # four songs per worker thread and step: ~2 s of wall per step on any box
     distinct = min(n_songs, 16)
     base = [synth.gen_track(BASE_SEED, i, TRACK_SAMPLES).numpy() for i in range(distinct)]
     songs = [base[i % distinct] for i in range(n_songs)]
@@ -144,7 +144,7 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: synthetic 3-min 22050 Hz f32 mono tracks, full 23-feature analysis "
-                               "(CPU arm: %d songs per step, one per host thread)" % n_songs,
+                               "(CPU arm: %d songs per step, four per host thread)" % n_songs,
                    "track_samples": TRACK_SAMPLES},
         "cpu_baseline": {"value": val, "unit": "songs/s", "cores": cores, "kind": "port",
                          "sample": "%d x 3-min synthetic tracks per step, %d steps, %d threads (C oracle, "
@@ -391,7 +391,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         cores = os.cpu_count() or 1
-        n_cpu = min(max(cores, 8), 64)
+        n_cpu = min(max(4 * cores, 64), 256)  # a few seconds of wall on all cores (tens of core-seconds)
         songs = [pcm[offs[i]:offs[i] + TRACK_SAMPLES].cpu().numpy() for i in range(min(n_cpu, S))]
         t0 = time.perf_counter()
         ost, ofe = O.analyze_batch(songs, 2, n_threads=cores)

@@ -3,7 +3,10 @@
 profiles/: one markdown table per capture with duration, DRAM traffic, pipe utilisation, occupancy
 and the PC-sampling stall mix of every kernel of this repo.
 
-  python scripts/summarize_ncu.py gpurun_out/prof_r01.ncu-rep profiles/ncu_r01_full.md [songs]
+  python scripts/summarize_ncu.py gpurun_out/prof_r01.ncu-rep profiles/ncu_r01_full.md [songs [traffic.json]]
+
+With `traffic.json` it also writes the per-kernel DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per
+launch and per song that bench.py reports as `roofline.traffic`, keyed by the kernel names of the bench JSON.
 """
 import csv
 import io
@@ -50,6 +53,23 @@ def main():
                  "cold-cache, compare shares, not absolutes (the timed numbers are in the bench JSON).")
     open(out, "w").write("\n".join(lines) + "\n")
     print("wrote", out)
+    if len(sys.argv) > 4 and songs:
+        import json
+        import re
+        # bench.py's kernel ids (api.cu kKernelNames) for the current kernels
+        alias = {"chroma_pipe_kernel": "chroma_kernel", "tuning_select_kernel": "tuning_kernel"}
+        tr = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full (%s), one launch = %d "
+                          "synthetic 3-min songs; bench.py scales bytes_per_song by the songs per launch" % (out, songs),
+              "songs_per_launch": songs}
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        units = rows[1]
+        for r in data:
+            name = re.sub(r"<.*", "", g(r, "Kernel Name").split("(")[0].replace("void ", "").replace("bliss::", ""))
+            name = alias.get(name, name)
+            b = sum(float(g(r, k, "0") or 0) * unit.get(units[col[k]], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            tr[name] = {"bytes_per_launch": b, "bytes_per_song": b / songs}
+        json.dump(tr, open(sys.argv[4], "w"), indent=1)
+        print("wrote", sys.argv[4])
 
 
 if __name__ == "__main__":
