@@ -386,6 +386,29 @@ def main():
            "bitwise_equal_to_device_path": e2e_match,
            "note": "bliss_b200_analyze_batch on pinned host buffers; PCIe-bound (15.9 MB per song)"}
 
+    # ---- e2e for 16-bit sources: bliss_b200_analyze_batch_s16 (s16 -> f32 on the device, half the PCIe bytes).
+    # Reported next to `e2e`, never instead of it: BASELINE.json's metric is quoted on f32 PCM.
+    e2e_s16 = None
+    if world == 1:
+        host16 = torch.empty(ES * TRACK_SAMPLES, dtype=torch.int16, pin_memory=True)
+        host16.copy_((host * 32767.0).round().to(torch.int16))
+        ptrs16 = (ctypes.c_void_p * ES)(*[host16.data_ptr() + 2 * i * TRACK_SAMPLES for i in range(ES)])
+        s16_out = np.zeros((ES, dim), np.float32)
+        nat.analyze_batch_s16_ptrs(ptrs16, hlens, 2, s16_out, e2e_status)  # warm-up (allocations)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            nat.analyze_batch_s16_ptrs(ptrs16, hlens, 2, s16_out, e2e_status)
+        torch.cuda.synchronize()
+        dt16 = time.perf_counter() - t0
+        # same samples converted on the host and sent as f32: must give the same bits
+        host.copy_(host16.to(torch.float32) / 32768.0)
+        nat.analyze_batch_ptrs(ptrs, hlens, 2, e2e_out, e2e_status)
+        e2e_s16 = {"value": ES * e2e_steps / dt16, "unit": "songs/s", "h2d_bytes_per_step": ES * TRACK_SAMPLES * 2,
+                   "d2h_bytes_per_step": ES * dim * 4, "songs_per_step": ES, "steps": e2e_steps,
+                   "bitwise_equal_to_f32_path": bool(np.array_equal(s16_out, e2e_out)),
+                   "note": "bliss_b200_analyze_batch_s16: signed 16-bit mono 22 050 Hz samples, x/32768 on the device"}
+        del host16
+
     # ---- CPU baseline (oracle = port of the reference algorithm) on rank 0, bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -415,7 +438,7 @@ def main():
                        "songs_per_gpu": S, "track_samples": TRACK_SAMPLES, "parallelism": "songs sharded %d-way" % world,
                        "l2": "inputs (%.1f GB PCM per GPU) are far larger than the 126 MB L2; no flush needed"
                              % (S * TRACK_SAMPLES * 4 / 1e9)},
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "per_rank": per_rank,
+            "e2e": e2e, "e2e_s16": e2e_s16, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "per_rank": per_rank,
             "gather": gather_info,
             "gpu_launches": int(lz.item()), "bitwise_reproducible_across_steps": bool(deterministic.item()),
         }

@@ -36,6 +36,7 @@ _inited_device = None
 SYMBOLS = [
     "bliss_b200_init", "bliss_b200_shutdown", "bliss_b200_set_workspace_limit", "bliss_b200_strerror",
     "bliss_b200_last_error", "bliss_b200_feature_count", "bliss_b200_analyze", "bliss_b200_analyze_batch",
+    "bliss_b200_analyze_batch_s16",
     "bliss_b200_analyze_batch_device", "bliss_b200_feature_weights", "bliss_b200_distance",
     "bliss_b200_distance_matrix", "bliss_b200_distance_matrix_device", "bliss_b200_closest_to_songs",
     "bliss_b200_song_to_song", "bliss_b200_stft512_mag_device", "bliss_b200_analyze_taps",
@@ -70,6 +71,7 @@ def load():
     L.bliss_b200_feature_count.restype = C.c_uint32
     L.bliss_b200_analyze.argtypes = [vp, C.c_uint64, C.c_uint16, vp]
     L.bliss_b200_analyze_batch.argtypes = [vp, u64p, C.c_uint32, C.c_uint16, vp, i32p]
+    L.bliss_b200_analyze_batch_s16.argtypes = [vp, u64p, C.c_uint32, C.c_uint16, vp, i32p]
     L.bliss_b200_analyze_batch_device.argtypes = [vp, u64p, u64p, C.c_uint32, C.c_uint16, vp, i32p, vp]
     L.bliss_b200_feature_weights.argtypes = [C.c_uint16, vp]
     L.bliss_b200_distance.argtypes = [vp, vp, C.c_uint32, C.c_int, vp, f32p]
@@ -172,6 +174,27 @@ def analyze_batch_ptrs(ptrs, lens, version, out, status):
     L = lib()
     check(L.bliss_b200_analyze_batch(ptrs, lens, len(lens), version, out.ctypes.data,
                                      status.ctypes.data_as(C.POINTER(C.c_int32))))
+
+
+def analyze_batch_s16(pcms, version=2):
+    """host int16 buffers (mono, 22 050 Hz): converted to f32 on the device (x / 32768)"""
+    L = lib()
+    pcms = [np.ascontiguousarray(p, dtype=np.int16).reshape(-1) for p in pcms]
+    n = len(pcms)
+    ptrs = (C.c_void_p * n)(*[p.ctypes.data if p.size else None for p in pcms])
+    lens = (C.c_uint64 * n)(*[p.size for p in pcms])
+    out = np.zeros((n, feature_count(version)), np.float32)
+    status = np.zeros(n, np.int32)
+    check(L.bliss_b200_analyze_batch_s16(ptrs, lens, n, version, out.ctypes.data,
+                                         status.ctypes.data_as(C.POINTER(C.c_int32))))
+    return status, out
+
+
+def analyze_batch_s16_ptrs(ptrs, lens, version, out, status):
+    """raw form used by bench.py: ptrs/lens are ctypes arrays over pinned host int16 buffers"""
+    L = lib()
+    check(L.bliss_b200_analyze_batch_s16(ptrs, lens, len(lens), version, out.ctypes.data,
+                                         status.ctypes.data_as(C.POINTER(C.c_int32))))
 
 
 def analyze(pcm, version=2):

@@ -42,6 +42,7 @@ int launch_finalize(const SongDesc *, int, const float *, const float *, const f
                     const unsigned int *, const float *, const double *, int, float *, unsigned int,
                     const PeerRows &, cudaStream_t);
 int launch_wave_setup(const void *, void *, size_t, unsigned int *, unsigned int *, unsigned int, cudaStream_t);
+int launch_s16_to_f32(const short *, float *, size_t, cudaStream_t);
 int launch_gather_barrier(unsigned int *const *, int, int, unsigned int, unsigned long long, cudaStream_t);
 int launch_distance_matrix(const float *, unsigned int, const float *, unsigned int, int, int, const float *,
                            float *, cudaStream_t);
@@ -151,7 +152,7 @@ struct Ctx {
     WaveSet ws[N_SETS];
     int next_set = 0;
     // host-API staging
-    DevBuf pcm[4], feats, metric, misc[6];
+    DevBuf pcm[4], raw16[4], feats, metric, misc[6];
     // profiling
     bool profiling = false;
     struct EvPair { cudaEvent_t a, b; int kid; };
@@ -628,7 +629,7 @@ void bliss_b200_shutdown(void) {
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
     DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw4k, &g.t_tw2, &g.t_tw8k, &g.t_filt, &g.t_filt32,
-                     &g.pcm[0], &g.pcm[1], &g.pcm[2], &g.pcm[3], &g.feats, &g.metric, &g.misc[0], &g.misc[1],
+                     &g.pcm[0], &g.pcm[1], &g.pcm[2], &g.pcm[3], &g.raw16[0], &g.raw16[1], &g.raw16[2], &g.raw16[3], &g.feats, &g.metric, &g.misc[0], &g.misc[1],
                      &g.misc[2], &g.misc[3], &g.misc[4], &g.misc[5]};
     for (DevBuf *b : all) b->release();
     for (auto &S : g.ws) {
@@ -851,9 +852,16 @@ int bliss_b200_gather_destroy(bliss_b200_gather *ga) {
     return BLISS_B200_OK;
 }
 
+}  // extern "C" (the host path below is a template)
+
 // host buffers: chunks of songs are copied on the copy stream while earlier chunks compute
-static int analyze_host_locked(const float *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
+// T = float: the decoder's output as the reference hands it to Song::analyze; T = int16_t: signed 16-bit mono
+// 22 050 Hz samples, converted on the device (x / 32768, what swresample's s16 -> flt conversion does) so that
+// only half the bytes cross PCIe.
+template <typename T>
+static int analyze_host_locked(const T *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
                                uint16_t ver, float *out, int32_t *status, bool debug) {
+    constexpr bool kS16 = sizeof(T) == 2;
     const uint32_t dim = bliss_b200_feature_count(ver);
     CK(g.feats.ensure((size_t)n_songs * dim * 4));
     // The path is PCIe-bound (15.9 MB per 3-min song).  Songs travel in chunks through a ring of FOUR
@@ -909,6 +917,7 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
         for (int k = 0; k < N_SETS; k++)  // buffer b free again (also: the host may reallocate it)
             if (done_used[b][k]) CK(cudaEventSynchronize(ev_done[b][k]));
         CK(g.pcm[b].ensure(std::max<size_t>(samples, 4) * 4));
+        if (kS16) CK(g.raw16[b].ensure(std::max<size_t>(samples, 4) * 2));
         if (trace) {
             cudaEvent_t e;
             CK(cudaEventCreate(&e));
@@ -926,11 +935,16 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
                 j++;
                 run += (size_t)lens[j];
             }
-            CK(cudaMemcpyAsync(g.pcm[b].as<float>() + offs[i], pcm[first + i], run * 4, cudaMemcpyHostToDevice,
-                               g.copy_stream));
+            void *dst = kS16 ? (void *)(g.raw16[b].as<short>() + offs[i]) : (void *)(g.pcm[b].as<float>() + offs[i]);
+            CK(cudaMemcpyAsync(dst, pcm[first + i], run * sizeof(T), cudaMemcpyHostToDevice, g.copy_stream));
             i = j + 1;
         }
         if (rc) break;
+        if (kS16) {  // same offsets in both buffers; runs behind the copies on the copy stream
+            g.launches += (unsigned long long)launch_s16_to_f32(g.raw16[b].as<short>(), g.pcm[b].as<float>(), samples,
+                                                               g.copy_stream);
+            CK(cudaGetLastError());
+        }
         CK(cudaEventRecord(ev_copy[b], g.copy_stream));
         if (trace) {
             cudaEvent_t e;
@@ -1000,8 +1014,19 @@ static int analyze_host_locked(const float *const *pcm, const uint64_t *n_sample
     return rc;
 }
 
+extern "C" {
+
 int bliss_b200_analyze_batch(const float *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
                              uint16_t ver, float *out, int32_t *status) {
+    REQUIRE_INIT();
+    if (check_version(ver)) return BLISS_B200_E_ARG;
+    if (n_songs == 0) return BLISS_B200_OK;
+    if (!pcm || !n_samples || !out) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
+    return analyze_host_locked(pcm, n_samples, n_songs, ver, out, status, false);
+}
+
+int bliss_b200_analyze_batch_s16(const int16_t *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
+                                 uint16_t ver, float *out, int32_t *status) {
     REQUIRE_INIT();
     if (check_version(ver)) return BLISS_B200_E_ARG;
     if (n_songs == 0) return BLISS_B200_OK;

@@ -33,4 +33,36 @@ int launch_wave_setup(const void *src_host, void *dst, size_t bytes, unsigned in
     return 1;
 }
 
+// ---- s16 -> f32 (bliss_b200_analyze_batch_s16) ----------------------------------------------------------
+// What the reference's decoder does to signed 16-bit mono 22 050 Hz material before Song::analyze sees it:
+// swresample's s16 -> flt conversion, x * (1 / 32768) (src/song/decoder/ffmpeg.rs:36-109; pinned by the decoder
+// test of data/s16_mono_22_5kHz.flac, :455-462, which the golden fixture reproduces bit for bit).
+// n is a multiple of 4 (chunk layout of api.cu); 8 samples per thread: one 16-byte load, two 16-byte stores.
+__global__ void __launch_bounds__(256)
+s16_to_f32_kernel(const short *__restrict__ in, float *__restrict__ out, size_t n) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const float k = 1.0f / 32768.0f;
+    if (i + 8 <= n) {
+        const int4 v = *reinterpret_cast<const int4 *>(in + i);
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            f[2 * j] = (float)(short)(w[j] & 0xffff) * k;
+            f[2 * j + 1] = (float)(short)(w[j] >> 16) * k;
+        }
+        *reinterpret_cast<float4 *>(out + i) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4 *>(out + i + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    } else {
+        for (size_t j = i; j < n; j++) out[j] = (float)in[j] * k;
+    }
+}
+
+int launch_s16_to_f32(const short *in, float *out, size_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    const size_t threads = (n + 7) / 8;
+    s16_to_f32_kernel<<<(unsigned int)((threads + 255) / 256), 256, 0, st>>>(in, out, n);
+    return 1;
+}
+
 }  // namespace bliss

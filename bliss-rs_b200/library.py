@@ -118,7 +118,7 @@ class Library:
             self.conn.execute(
                 "insert into song (path, artist, title, album, album_artist, duration, track_number, disc_number, "
                 "genre, analyzed, version, extra_info, cue_path, audio_file_path) "
-                "values (?1, ?2, ?3, ?4, ?5, ?6, ?7, ?8, ?9, ?10, ?11, ?12, ?13, ?14) "
+                "values (?, ?, ?, ?, ?, ?, ?, ?, ?, ?, ?, ?, ?, ?) "
                 "on conflict(path) do update set artist=excluded.artist, title=excluded.title, album=excluded.album, "
                 "track_number=excluded.track_number, disc_number=excluded.disc_number, "
                 "album_artist=excluded.album_artist, duration=excluded.duration, genre=excluded.genre, "
@@ -128,22 +128,22 @@ class Library:
                  song.track_number, song.disc_number, song.genre, True, int(song.features_version),
                  json.dumps(library_song.extra_info), cue.cue_path if cue else None,
                  cue.audio_file_path if cue else None))
-            self.conn.execute("delete from feature where song_id in (select id from song where path = ?1)", (song.path,))
+            self.conn.execute("delete from feature where song_id in (select id from song where path = ?)", (song.path,))
             self.conn.executemany(
-                "insert into feature (song_id, feature, feature_index) values ((select id from song where path = ?1), ?2, ?3) "
+                "insert into feature (song_id, feature, feature_index) values ((select id from song where path = ?), ?, ?) "
                 "on conflict(song_id, feature_index) do update set feature=excluded.feature",
                 [(song.path, float(v), i) for i, v in enumerate(song.analysis.internal_analysis)])
 
     def store_failed_song(self, song_path: str, error: BlissError, features_version: FeaturesVersion):
         """src/library.rs:1639-1670: `insert or replace` with the error text, analyzed stays false."""
         with self.conn:
-            self.conn.execute("insert or replace into song (path, error, version) values (?1, ?2, ?3)",
+            self.conn.execute("insert or replace into song (path, error, version) values (?, ?, ?)",
                               (song_path, str(error), int(features_version)))
 
     def delete_path(self, song_path: str) -> int:
         """src/library.rs delete_path: features go with the song (on delete cascade)."""
         with self.conn:
-            cur = self.conn.execute("delete from song where path = ?1", (song_path,))
+            cur = self.conn.execute("delete from song where path = ?", (song_path,))
         if cur.rowcount == 0:
             raise ProviderError("tried to delete song %s, not existing in the database." % song_path)
         return cur.rowcount

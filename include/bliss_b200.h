@@ -71,6 +71,14 @@ int bliss_b200_analyze(const float *pcm, uint64_t n_samples, uint16_t features_v
 int bliss_b200_analyze_batch(const float *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
                              uint16_t features_version, float *out, int32_t *status);
 
+/* Decode-side feed for 16-bit sources: the same call with the decoder's signed 16-bit mono 22 050 Hz samples
+ * as they are BEFORE the reference's resampler turns them into f32 (swresample s16 -> flt: x / 32768,
+ * src/song/decoder/ffmpeg.rs:36-109; the decoder test :455-462 pins that conversion bit for bit).  The
+ * conversion runs on the device, so half the bytes cross PCIe.  Results are bit-identical to
+ * bliss_b200_analyze_batch on the converted samples. */
+int bliss_b200_analyze_batch_s16(const int16_t *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
+                                 uint16_t features_version, float *out, int32_t *status);
+
 /* Same, PCM already resident in device memory: song i is d_pcm[offsets[i] .. offsets[i]+n_samples[i]).
  * d_pcm must be 16-byte aligned; offsets/n_samples/status are HOST arrays; d_out is a DEVICE
  * buffer (n_songs x feature_count).  Work is enqueued on `cuda_stream` (a cudaStream_t, may be

@@ -154,6 +154,27 @@ inline std::vector<AnalysisResult> analyze_batch(const std::vector<const float *
     return res;
 }
 
+// Same for 16-bit sources (signed 16-bit mono 22 050 Hz as decoded, before the resampler's s16 -> flt step):
+// converted on the device, half the PCIe bytes, results bit-identical to analyze_batch on x / 32768.
+inline std::vector<AnalysisResult> analyze_batch_s16(const std::vector<const int16_t *> &pcm,
+                                                     const std::vector<uint64_t> &n, const AnalysisOptions &o = {}) {
+    detail::ensure_init();
+    const size_t dim = feature_count(o.features_version);
+    std::vector<float> out(dim * pcm.size());
+    std::vector<int32_t> status(pcm.size());
+    detail::check_call(bliss_b200_analyze_batch_s16(pcm.data(), n.data(), static_cast<uint32_t>(pcm.size()),
+                                                    static_cast<uint16_t>(o.features_version), out.data(), status.data()));
+    std::vector<AnalysisResult> res;
+    res.reserve(pcm.size());
+    for (size_t i = 0; i < pcm.size(); i++) {
+        if (status[i] == BLISS_B200_SONG_OK)
+            res.emplace_back(Analysis(std::vector<float>(out.begin() + i * dim, out.begin() + (i + 1) * dim), o.features_version));
+        else
+            res.emplace_back(detail::status_error(status[i]));
+    }
+    return res;
+}
+
 // src/song/decoder.rs:34-67
 struct PreAnalyzedSong {
     std::string path;

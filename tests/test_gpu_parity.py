@@ -320,6 +320,19 @@ def test_device_api_matches_host_api(pcm_song, pcm_piano):
     assert np.array_equal(got[[0, 1, 3]], hfe[[0, 1, 3]]) and (got[2] == 0).all()
 
 
+def test_s16_ingest_is_the_f32_path_on_converted_samples(golden, pcm_song, pcm_piano):
+    """bliss_b200_analyze_batch_s16: the decoder's 16-bit samples, converted on the device exactly as ffmpeg's
+    s16 -> flt step does (x / 32768; the fixture reproduces the reference's decoder test bit for bit)."""
+    s16 = [golden["pcm_s16_mono"], golden["pcm_piano"], golden["pcm_s16_mono"][:5000], golden["pcm_piano"][:60001]]
+    st16, f16 = B.native.analyze_batch_s16(s16, 2)
+    st32, f32 = B.native.analyze_batch([x.astype(np.float32) / np.float32(32768.0) for x in s16], 2)
+    assert list(st16) == [0, 0, 1, 0] and np.array_equal(st16, st32)
+    assert np.array_equal(f16[st16 == 0], f32[st32 == 0])
+    assert np.abs(f16[0] - golden["expected_analysis_v2"]).max() < 1e-5  # src/song/mod.rs:553-591
+    st1, f1 = B.native.analyze_batch_s16(s16[:2], 1)
+    assert np.abs(f1[0] - golden["expected_analysis_v1"]).max() < 1e-5
+
+
 def test_cue_style_subslices_of_one_buffer(pcm_song):
     """BlissCueFile::get_songs (src/cue.rs:208-243) analyses sub-slices of ONE decoded buffer cut at
     (start_s * 22050) as usize -- arbitrary, unaligned sample offsets; they may even overlap."""
