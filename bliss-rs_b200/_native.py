@@ -34,7 +34,8 @@ _inited_device = None
 
 # every symbol include/bliss_b200.h declares
 SYMBOLS = [
-    "bliss_b200_init", "bliss_b200_shutdown", "bliss_b200_set_workspace_limit", "bliss_b200_strerror",
+    "bliss_b200_init", "bliss_b200_shutdown", "bliss_b200_set_workspace_limit", "bliss_b200_set_variant",
+    "bliss_b200_strerror",
     "bliss_b200_last_error", "bliss_b200_feature_count", "bliss_b200_analyze", "bliss_b200_analyze_batch",
     "bliss_b200_analyze_batch_s16",
     "bliss_b200_analyze_batch_device", "bliss_b200_feature_weights", "bliss_b200_distance",
@@ -174,6 +175,13 @@ def analyze_batch_ptrs(ptrs, lens, version, out, status):
     L = lib()
     check(L.bliss_b200_analyze_batch(ptrs, lens, len(lens), version, out.ctypes.data,
                                      status.ctypes.data_as(C.POINTER(C.c_int32))))
+
+
+def set_variant(mask: int) -> int:
+    """diagnostic: kernel implementation mask (include/bliss_b200.h); returns the previous mask"""
+    L = lib()
+    L.bliss_b200_set_variant.argtypes = [C.c_int]
+    return int(L.bliss_b200_set_variant(int(mask)))
 
 
 def analyze_batch_s16(pcms, version=2):

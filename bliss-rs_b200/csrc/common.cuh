@@ -55,6 +55,7 @@ enum {
     VARIANT_OLD_CHROMA = 4,    // chroma_kernel: thread-per-frame tiles staged through shared memory
     VARIANT_OLD_ACF = 8,       // beattrack_kernel: one autocorrelation lag at a time, scalar loads
     VARIANT_BT512 = 16,        // beattrack_kernel: 512 threads per song (3 songs per SM) instead of 128 (8 per SM)
+    VARIANT_R64 = 32,          // stft8192: 4096 = 64 x 64, two radix-64 passes by 64 threads per frame (experimental)
 };
 
 // Song lookup for flat work lists: largest s with prefix[s] <= item (prefix has n_songs+1

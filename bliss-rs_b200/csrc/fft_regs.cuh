@@ -153,6 +153,87 @@ BLISS_HD void fft_dif(cpx (&v)[N]) {
     DifStage<N, 0, N>::run(v);
 }
 
+// ---- radix up to 64: twiddles on the 256-point circle ---------------------------------------------------
+// cos(2*pi*k/256), k = 0..64 (f64-rounded-to-f32 literals)
+__host__ __device__ constexpr float cos256_tab(int k) {
+    constexpr float t[65] = {
+        1.f, 0.99969881869620425f, 0.99879545620517241f, 0.99729045667869021f,
+        0.99518472667219693f, 0.99247953459870997f, 0.98917650996478101f, 0.98527764238894122f,
+        0.98078528040323043f, 0.97570213003852857f, 0.97003125319454397f, 0.96377606579543984f,
+        0.95694033573220882f, 0.94952818059303667f, 0.94154406518302081f, 0.93299279883473896f,
+        0.92387953251128674f, 0.91420975570353069f, 0.90398929312344334f, 0.89322430119551532f,
+        0.88192126434835505f, 0.87008699110871146f, 0.85772861000027212f, 0.84485356524970712f,
+        0.83146961230254524f, 0.81758481315158371f, 0.80320753148064494f, 0.78834642762660634f,
+        0.77301045336273699f, 0.75720884650648457f, 0.74095112535495911f, 0.724247082951467f,
+        0.70710678118654757f, 0.68954054473706694f, 0.67155895484701833f, 0.65317284295377676f,
+        0.63439328416364549f, 0.61523159058062682f, 0.59569930449243347f, 0.57580819141784534f,
+        0.55557023301960229f, 0.53499761988709726f, 0.51410274419322166f, 0.49289819222978409f,
+        0.47139673682599781f, 0.4496113296546066f, 0.4275550934302822f, 0.40524131400498986f,
+        0.38268343236508984f, 0.35989503653498828f, 0.33688985339222005f, 0.31368174039889157f,
+        0.29028467725446233f, 0.26671275747489842f, 0.24298017990326398f, 0.21910124015686977f,
+        0.19509032201612833f, 0.17096188876030136f, 0.14673047445536175f, 0.12241067519921628f,
+        0.09801714032956077f, 0.073564563599667454f, 0.049067674327418126f, 0.024541228522912264f,
+        0.f};
+    return t[k];
+}
+__host__ __device__ constexpr float cos256(int k) {
+    k = ((k % 256) + 256) % 256;
+    if (k > 128) k = 256 - k;
+    bool neg = false;
+    if (k > 64) { k = 128 - k; neg = true; }
+    const float v = cos256_tab(k);
+    return neg ? -v : v;
+}
+__host__ __device__ constexpr float sin256(int k) { return cos256(k - 64); }
+
+// multiply by W_256^K = exp(-2*pi*i*K/256), K compile-time
+template <int K>
+BLISS_HD cpx mul_tw256(cpx v) {
+    constexpr int k = ((K % 256) + 256) % 256;
+    if constexpr (k == 0) {
+        return v;
+    } else if constexpr (k == 64) {  // -i
+        return cpx{v.y, -v.x};
+    } else if constexpr (k == 128) {  // -1
+        return cpx{-v.x, -v.y};
+    } else if constexpr (k == 192) {  // +i
+        return cpx{-v.y, v.x};
+    } else if constexpr (k == 32) {  // (1 - i)/sqrt2
+        constexpr float h = 0.70710678118654752f;
+        return pmul(padd(v, cpx{v.y, -v.x}), cpx{h, h});
+    } else if constexpr (k == 96) {  // (-1 - i)/sqrt2
+        constexpr float h = 0.70710678118654752f;
+        return pmul(psub(cpx{v.y, -v.x}, v), cpx{h, h});
+    } else {
+        constexpr float c = cos256(k), s = -sin256(k);  // W = c + i s
+        return pfma(v, cpx{c, c}, pmul(cpx{-v.y, v.x}, cpx{s, s}));
+    }
+}
+
+// Decimation-in-frequency radix-2 recursion for N | 256 (same structure as DifStage)
+template <int N, int OFF, int TOTAL>
+struct DifStageG {
+    template <int K>
+    static BLISS_HD void bfly(cpx (&v)[TOTAL]) {
+        if constexpr (K < N / 2) {
+            cpx a = v[OFF + K], b = v[OFF + K + N / 2];
+            v[OFF + K] = cadd(a, b);
+            v[OFF + K + N / 2] = mul_tw256<K * (256 / N)>(csub(a, b));
+            bfly<K + 1>(v);
+        }
+    }
+    static BLISS_HD void run(cpx (&v)[TOTAL]) {
+        if constexpr (N >= 2) {
+            bfly<0>(v);
+            DifStageG<N / 2, OFF, TOTAL>::run(v);
+            DifStageG<N / 2, OFF + N / 2, TOTAL>::run(v);
+        }
+    }
+};
+
+// 64-point FFT in registers; on return position p holds X[bitrev_6(p)]
+BLISS_HD void fft_dif64(cpx (&v)[64]) { DifStageG<64, 0, 64>::run(v); }
+
 __host__ __device__ constexpr int bitrev(int x, int bits) {
     int r = 0;
     for (int b = 0; b < bits; b++)

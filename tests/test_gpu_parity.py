@@ -333,6 +333,30 @@ def test_s16_ingest_is_the_f32_path_on_converted_samples(golden, pcm_song, pcm_p
     assert np.abs(f1[0] - golden["expected_analysis_v1"]).max() < 1e-5
 
 
+def test_kernel_implementations_agree(pcm_song, pcm_piano):
+    """bliss_b200_set_variant: the previous implementation of every reworked kernel is still in the library.
+    Tuning select, chroma contraction, autocorrelation and beat-tracker CTA width must reproduce the current
+    kernels BIT FOR BIT; the two other cuts of the 8192-point FFT (previous epilogue, 64 x 64) round
+    differently in the last place and must agree to 1e-5 with identical tuning / tempo decisions."""
+    songs = [pcm_song, pcm_piano] + [synth.gen_track(77, i, 22050 * 40 + 101 * i, device="cuda").cpu().numpy() for i in range(6)]
+    try:
+        B.native.set_variant(0)
+        st0, f0 = B.native.analyze_batch(songs, 2)
+        assert (st0 == 0).all()
+        for mask in (2, 4, 8, 16, 2 | 4 | 8 | 16):
+            B.native.set_variant(mask)
+            st, f = B.native.analyze_batch(songs, 2)
+            assert np.array_equal(f, f0), "variant %d differs in columns %s" % (mask, np.nonzero((f != f0).any(0))[0])
+        for mask in (1, 32, 63):
+            B.native.set_variant(mask)
+            st, f = B.native.analyze_batch(songs, 2)
+            assert (st == 0).all()
+            assert np.abs(f - f0).max() < 1e-5, (mask, np.abs(f - f0).max(0))
+            assert np.array_equal(f[:, 0], f0[:, 0])  # tempo does not depend on the chroma STFT at all
+    finally:
+        B.native.set_variant(0)
+
+
 def test_cue_style_subslices_of_one_buffer(pcm_song):
     """BlissCueFile::get_songs (src/cue.rs:208-243) analyses sub-slices of ONE decoded buffer cut at
     (start_s * 22050) as usize -- arbitrary, unaligned sample offsets; they may even overlap."""
