@@ -14,7 +14,6 @@ BASE = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17
 
 VARIANTS = {
     "nopacked": ["-DBLISS_NO_PACKED_FP"],  # scalar FADD/FMUL/FFMA butterflies instead of the f32x2 forms
-    "k5s4": ["-DK5P_STAGES_N=4"],           # chroma_pipe_kernel: 4-stage ring, 2 CTAs/SM
 }
 
 
