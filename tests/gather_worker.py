@@ -1,4 +1,4 @@
-"""Launched by test_gpu_gather.py / scripts/gpu_multi.sh under torch.distributed.run: every rank analyses
+"""Launched by test_gpu_gather.py / scripts/gpu_multi2.sh under torch.distributed.run: every rank analyses
 its round-robin shard, rows travel (a) by the fused peer stores + epoch barrier and (b) by the NCCL
 all-gather; both must give every rank the rows of a whole-corpus analysis, bit for bit."""
 import os
