@@ -349,6 +349,10 @@ def main():
             traffic = {"gb_per_launch": ent["bytes_per_song"] * S / 1e9,
                        "algorithmic_gb_per_launch": alg.get(dom["kernel"], 0) * S / 1e9,
                        "source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum)"}
+            # what the same ncu capture says the kernel is actually bound by (percent of peak)
+            for k in ("l1tex_data_pipe_pct", "issue_active_pct", "dram_pct", "lts_pct"):
+                if k in ent:
+                    traffic[k] = ent[k]
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["algorithmic_gbs"], "peak": peak,

@@ -67,7 +67,14 @@ def main():
             name = re.sub(r"<.*", "", g(r, "Kernel Name").split("(")[0].replace("void ", "").replace("bliss::", ""))
             name = alias.get(name, name)
             b = sum(float(g(r, k, "0") or 0) * unit.get(units[col[k]], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-            tr[name] = {"bytes_per_launch": b, "bytes_per_song": b / songs}
+            pct = lambda k: round(float(g(r, k, "0") or 0), 1)
+            tr[name] = {"bytes_per_launch": b, "bytes_per_song": b / songs,
+                        # where the kernel actually sits (same capture): the unified L1 / shared-memory data pipe,
+                        # issue slots, DRAM, L2
+                        "l1tex_data_pipe_pct": pct("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                        "issue_active_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                        "dram_pct": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                        "lts_pct": pct("lts__throughput.avg.pct_of_peak_sustained_elapsed")}
         json.dump(tr, open(sys.argv[4], "w"), indent=1)
         print("wrote", sys.argv[4])
 
