@@ -380,9 +380,14 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
     { ProfScope p(K_PEAK, st);
       p.done(launch_peakpick(S.flux.as<float>(), dv.sd, dv.t_prefix, n, w.t_prefix[n], S.thr.as<float>(), st)); }
     { ProfScope p(K_CHROMA, sb);
-      p.done(launch_chroma(S.mags.as<float>(), dv.sd, dv.tile_prefix, n, w.tile_prefix[n], g.t_filt32.as<float>(),
-                           S.tuning.as<int>(), S.tiles.as<double>(), debug ? S.chroma_dbg.as<double>() : nullptr,
-                           g.variant, sb)); }
+      const int nl = launch_chroma(S.mags.as<float>(), dv.sd, dv.tile_prefix, n, w.tile_prefix[n], g.t_filt32.as<float>(),
+                                   S.tuning.as<int>(), S.tiles.as<double>(), debug ? S.chroma_dbg.as<double>() : nullptr,
+                                   g.variant, sb);
+      p.done(nl);
+      if (nl < 0) {  // the opt-in to > 48 KB of dynamic shared memory was refused
+          g_last_error = "cudaFuncSetAttribute(chroma_pipe_kernel, MaxDynamicSharedMemorySize) failed";
+          return BLISS_B200_E_CUDA;
+      } }
     { ProfScope p(K_BEAT, st);
       p.done(launch_beattrack(S.thr.as<float>(), S.eb.as<float>(), dv.sd, n, S.bpm.as<float>(),
                               S.tempo.as<float>(), S.bpm_count.as<unsigned int>(), g.variant, st)); }
