@@ -22,4 +22,4 @@ for r in outs[1:]:
     d = (r != outs[0])
     print("differ:", int(d.sum()), "columns", d.any(0).nonzero().flatten().tolist(), "rows", d.any(1).nonzero().flatten().tolist()[:20])
 print("tempo run0:", [round(float(v), 5) for v in outs[0][:8, 0]])
-print("tempo run1:", [round(float(v), 5) for v in outs[1][:8, 0]])
+print("tempo run1:", [round(float(v), 5) for v in outs[-1][:8, 0]])
