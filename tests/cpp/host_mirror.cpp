@@ -1,0 +1,90 @@
+// Exercises include/bliss_b200.hpp (the C++17 host mirror of the reference API) against libbliss_b200.so.
+// Built and run by tests/test_host_abi.py: without a GPU it must fail loudly ("NO_DEVICE": there is no CPU
+// fallback); with one it analyses a synthetic clip through Song::analyze, the batched Decoder seam and the
+// 16-bit entry point and prints "OK".
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "bliss_b200.hpp"
+
+using namespace bliss;
+
+struct ToneDecoder : Decoder {  // a Decoder whose "files" are synthetic tones; "bad" fails to decode
+    PreAnalyzedSong decode(const std::string &path) override {
+        if (path == "bad") throw BlissError(BlissError::DecodingError, "while opening format for file 'bad'");
+        PreAnalyzedSong p;
+        p.path = path;
+        p.title = path;
+        const size_t n = path == "short" ? 4000 : 22050 * 12;
+        p.sample_array.resize(n);
+        const double f = 220.0 * (1 + (int)path.size());
+        for (size_t i = 0; i < n; i++)
+            p.sample_array[i] = (float)(0.3 * std::sin(2 * M_PI * f * i / SAMPLE_RATE) + 0.2 * ((i / 5512) % 2 ? 1 : 0) * std::sin(2 * M_PI * 80.0 * i / SAMPLE_RATE));
+        p.duration_s = (double)n / SAMPLE_RATE;
+        return p;
+    }
+};
+
+int main() {
+    // things that need no device
+    if (feature_count(FeaturesVersion::Version2) != 23 || feature_count(FeaturesVersion::Version1) != 20) return 2;
+    const auto w = feature_weights(LATEST);
+    if (w.size() != 23 * 23 || w[0] != 0.25f || w[24] != 1.0f) return 3;
+    try {
+        Analysis wrong(std::vector<float>(5, 0.f), LATEST);  // Analysis::new length check, src/song/mod.rs:326-339
+        return 4;
+    } catch (const BlissError &e) {
+        if (e.kind != BlissError::ProviderError) return 5;
+    }
+    ToneDecoder dec;
+    try {
+        const Song s = dec.song_from_path("a");
+        if (s.analysis->as_vec().size() != 23) return 6;
+        const Song t = dec.song_from_path("bbb");
+        const float d = s.distance(t), d0 = s.distance(s);
+        if (!(d > 0.f) || d0 != 0.f) return 7;
+        // the batching seam: errors are items, the batch survives them (src/song/decoder.rs:319-325)
+        auto res = dec.analyze_paths({"a", "bad", "short", "bbb"}, {}, 2);
+        if (res.size() != 4) return 8;
+        int ok = 0, err = 0;
+        for (auto &r : res) {
+            if (auto *song = std::get_if<Song>(&r.second)) {
+                ok++;
+                const Song &ref = r.first == "a" ? s : t;
+                if (std::memcmp(song->analysis->as_vec().data(), ref.analysis->as_vec().data(), 23 * sizeof(float)) != 0) return 9;
+            } else {
+                err++;
+                const auto &e = std::get<BlissError>(r.second);
+                if (r.first == "short" && std::string(e.what()).find("empty or too short song.") == std::string::npos) return 10;
+                if (r.first == "bad" && e.kind != BlissError::DecodingError) return 11;
+            }
+        }
+        if (ok != 2 || err != 2) return 12;
+        // 16-bit entry point == f32 entry point on x / 32768
+        PreAnalyzedSong p = dec.decode("a");
+        std::vector<int16_t> q(p.sample_array.size());
+        std::vector<float> back(q.size());
+        for (size_t i = 0; i < q.size(); i++) {
+            q[i] = (int16_t)std::lrint(p.sample_array[i] * 32767.0);
+            back[i] = (float)q[i] / 32768.0f;
+        }
+        auto r16 = analyze_batch_s16({q.data()}, {q.size()});
+        auto r32 = analyze_batch({back.data()}, {back.size()});
+        if (std::get<Analysis>(r16[0]).as_vec() != std::get<Analysis>(r32[0]).as_vec()) return 13;
+        // playlist: closest_to_songs keeps the seed first
+        std::vector<float> cands;
+        for (const Song *x : {&t, &s}) cands.insert(cands.end(), x->analysis->as_vec().begin(), x->analysis->as_vec().end());
+        const auto order = playlist::closest_to_songs(s.analysis->as_vec(), cands, 23, playlist::mahalanobis_distance_builder(w));
+        if (order.size() != 2 || order[0] != 1) return 14;
+        std::puts("OK");
+        return 0;
+    } catch (const BlissError &e) {
+        if (std::string(e.what()).find("no CPU fallback") != std::string::npos) {
+            std::puts("NO_DEVICE");
+            return 0;
+        }
+        std::fprintf(stderr, "unexpected BlissError: %s\n", e.what());
+        return 20;
+    }
+}

@@ -115,3 +115,30 @@ def test_variant_mask_names_match_header():
     for name in ("VARIANT_OLD_EPILOGUE = 1", "VARIANT_OLD_TUNING = 2", "VARIANT_OLD_CHROMA = 4", "VARIANT_OLD_ACF = 8",
                  "VARIANT_BT512 = 16", "VARIANT_R64 = 32"):
         assert name in txt
+
+
+def _build_cpp_mirror(tmp_path):
+    exe = str(tmp_path / "host_mirror")
+    libdir = os.path.dirname(B.native.SO_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+                           os.path.join(ROOT, "tests", "cpp", "host_mirror.cpp"), "-o", exe, "-L" + libdir,
+                           "-lbliss_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_cpp_host_mirror_builds_and_refuses_to_run_without_gpu(tmp_path):
+    """include/bliss_b200.hpp (C++17 mirror of Song / Analysis / Decoder / playlist) compiles and links against the
+    C ABI; the device-free parts work and the first analysis fails loudly: there is no CPU fallback."""
+    out = subprocess.run([_build_cpp_mirror(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert out.stdout.strip() == "NO_DEVICE"
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_on_gpu(tmp_path):
+    """the same program on a GPU box: Song::analyze, the Decoder batching seam (errors as items), the 16-bit
+    entry point and closest_to_songs through the C++ mirror"""
+    out = subprocess.run([_build_cpp_mirror(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert out.stdout.strip() == "OK"
