@@ -6,14 +6,18 @@
 
 A "step" = one pass of the hot path over one batch: every rank analyses its shard of
 synthetic 3-min 22 050 Hz f32 mono tracks (BASELINE.json configs[1]: 1024 tracks per GPU, full
-descriptor set, PCM resident in HBM), the 23-float rows are all-gathered across ranks (NCCL) and
-each rank computes its row block of the all-pairs distance matrix (configs[3] shape).  Weak
-scaling: per-GPU work is fixed, value = all songs of all ranks / max-over-ranks device time.
+descriptor set, PCM resident in HBM), the 23-float rows reach every rank (stored straight into the
+peers' buffers by the analysis' last kernel + a one-warp epoch barrier; --gather nccl = the
+all_gather comparator) and each rank computes its row block of the all-pairs distance matrix
+(configs[3] shape).  Weak scaling: per-GPU work is fixed, value = all songs of all ranks /
+max-over-ranks device time.
 
 Prints ONE JSON line on rank 0 (see the task contract): value, e2e (same metric through the
-C-ABI call with pinned HOST buffers, H2D + D2H inside the timed region), roofline of the
-dominant kernel (CUDA-event timed inside this run), cpu_baseline (oracle on the host cores),
-clocks, gpu_launches.
+C-ABI call with pinned HOST f32 buffers, H2D + D2H inside the timed region), e2e_s16 (the same
+through bliss_b200_analyze_batch_s16: 16-bit host buffers converted on the device; an extra, the
+metric itself is quoted on f32 PCM), roofline of the dominant kernel (CUDA-event timed inside this
+run; roofline.traffic = its ncu DRAM bytes and the percentages of the resources that bind it, from
+profiles/ncu_traffic.json), cpu_baseline (oracle on the host cores), clocks, gpu_launches.
 """
 import argparse
 import ctypes
