@@ -35,6 +35,67 @@ def mahalanobis_distance_builder(m) -> _Metric:
     return _Metric(native.METRIC_MAHALANOBIS, np.ascontiguousarray(m, np.float32), "mahalanobis_distance")
 
 
+def variance_based_weight_matrix(seeds: Sequence) -> np.ndarray:
+    """src/playlist.rs:173-221: diagonal Mahalanobis matrix that weights the dimensions the seeds agree on
+    (inverse variance, normalised so that the weights sum to the dimension).  A few f32 operations on
+    n_seeds x dim values in the reference's order; feed the result to `mahalanobis_distance_builder`."""
+    from .song import ProviderError
+    seeds = [np.asarray(getattr(getattr(s, "analysis", s), "internal_analysis", getattr(s, "analysis", s)), np.float32).reshape(-1)
+             for s in seeds]
+    if len(seeds) < 2:
+        raise ProviderError("seeds must contain more than one element")
+    n = seeds[0].size
+    if n == 0:
+        raise ProviderError("seed feature vectors must not be empty")
+    if any(s.size != n for s in seeds):
+        raise ProviderError("all seed feature vectors must have the same length")
+    n_seeds = np.float32(len(seeds))
+    mean = np.zeros(n, np.float32)
+    for s in seeds:
+        mean = mean + s
+    mean = mean / n_seeds
+    variance = np.zeros(n, np.float32)
+    for s in seeds:
+        diff = s - mean
+        variance = variance + diff * diff
+    variance = variance / n_seeds
+    weights = np.float32(1.0) / (variance + np.float32(1e-6))
+    total = np.float32(0.0)
+    for w in weights:  # Array1::sum on a contiguous f32 array: pairwise-unrolled in ndarray, sequential here;
+        total = np.float32(total + w)  # the reference's own tests hold the result to 1e-4
+    weights = weights * (np.float32(n) / total)
+    return np.diag(weights).astype(np.float32)
+
+
+def closest_album_to_group(group: Sequence, pool: Sequence) -> List:
+    """src/playlist.rs:424-485: an "album playlist": `group` first, then the albums of `pool` ordered by the
+    euclidean distance of their mean analysis to the group's mean analysis, each album by (disc, track); songs
+    of the group and songs without an album tag leave the pool.  Distances run on the device."""
+    from .song import ProviderError
+    group, pool = list(group), list(pool)
+    if not group:
+        raise ProviderError("Mean of empty slice")
+    song = lambda s: s.as_ref() if hasattr(s, "as_ref") else s
+    pool = [s for s in pool if not any(song(g) == song(s) for g in group)]
+    albums = {}
+    for s in pool:
+        album = song(s).album
+        if album is not None:
+            albums.setdefault(album, []).append(np.asarray(song(s).analysis.internal_analysis, np.float32))
+    first = _vectors([song(g) for g in group]).mean(axis=0, dtype=np.float32)
+    names = list(albums)
+    playlist = list(group)
+    if names:
+        means = np.stack([np.stack(albums[a]).mean(axis=0, dtype=np.float32) for a in names])
+        d = native.distance_matrix(first[None, :], means, native.METRIC_MAHALANOBIS, None)[0]
+        for i in np.argsort(d, kind="stable"):
+            al = [s for s in pool if song(s).album == names[i]]
+            opt = lambda v: (v is not None, v if v is not None else 0)  # Option ordering: None < Some(_)
+            al.sort(key=lambda s: (opt(song(s).disc_number), opt(song(s).track_number)))
+            playlist.extend(al)
+    return playlist
+
+
 def _vectors(songs) -> np.ndarray:
     rows = []
     for s in songs:
