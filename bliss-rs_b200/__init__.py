@@ -10,7 +10,8 @@ from .song import (AnalysisIndex, AnalysisIndexv1, Analysis, AnalysisOptions, Bl
                    DecodingError, ProviderError, Decoder, FeaturesVersion, PreAnalyzedSong, Song,
                    NUMBER_FEATURES, SAMPLE_RATE, CHANNELS, analyze_batch)
 from . import playlist
+from . import library
 
-__all__ = ["native", "playlist", "AnalysisIndex", "AnalysisIndexv1", "Analysis", "AnalysisOptions", "BlissError",
+__all__ = ["native", "playlist", "library", "AnalysisIndex", "AnalysisIndexv1", "Analysis", "AnalysisOptions", "BlissError",
            "AnalysisError", "DecodingError", "ProviderError", "Decoder", "FeaturesVersion", "PreAnalyzedSong",
            "Song", "NUMBER_FEATURES", "SAMPLE_RATE", "CHANNELS", "analyze_batch"]
