@@ -266,6 +266,21 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    if gather and args.gather == "auto":
+        # a peer mapping that opened but does not carry the stores shows up as a barrier time-out in the
+        # warm-up: every rank then drops to the NCCL exchange together instead of failing the run
+        ok = torch.ones(1, device=dev)
+        try:
+            gather.check()
+        except Exception as e:
+            ok.zero_()
+            print("[bench] peer gather failed its warm-up on rank %d: %s" % (rank, e), file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            gather = None
+            gather_info = {"kind": "nccl", "note": "fused peer-store exchange failed its warm-up check"}
+            for _ in range(args.warmup):
+                step()
     feats_warm = feats.clone()   # every later step must reproduce these bits (no timing-dependent result)
     # The sampler is started BEFORE the barrier: forking nvidia-smi from a process this size takes ~75 ms,
     # which used to delay rank 0's first launch -- every other rank then sat in its first exchange waiting

@@ -8,10 +8,10 @@ docstring.  No CPU implementation exists in this package.
 from . import _native as native
 from .song import (AnalysisIndex, AnalysisIndexv1, Analysis, AnalysisOptions, BlissError, AnalysisError,
                    DecodingError, ProviderError, Decoder, FeaturesVersion, PreAnalyzedSong, Song,
-                   NUMBER_FEATURES, SAMPLE_RATE, CHANNELS, analyze_batch)
+                   NUMBER_FEATURES, SAMPLE_RATE, CHANNELS, analyze_batch, analyze_batch_pcm, pcm_to_mono)
 from . import playlist
 from . import library
 
 __all__ = ["native", "playlist", "library", "AnalysisIndex", "AnalysisIndexv1", "Analysis", "AnalysisOptions", "BlissError",
            "AnalysisError", "DecodingError", "ProviderError", "Decoder", "FeaturesVersion", "PreAnalyzedSong",
-           "Song", "NUMBER_FEATURES", "SAMPLE_RATE", "CHANNELS", "analyze_batch"]
+           "Song", "NUMBER_FEATURES", "SAMPLE_RATE", "CHANNELS", "analyze_batch", "analyze_batch_pcm", "pcm_to_mono"]

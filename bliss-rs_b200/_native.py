@@ -37,7 +37,7 @@ SYMBOLS = [
     "bliss_b200_init", "bliss_b200_shutdown", "bliss_b200_set_workspace_limit", "bliss_b200_set_variant",
     "bliss_b200_strerror",
     "bliss_b200_last_error", "bliss_b200_feature_count", "bliss_b200_analyze", "bliss_b200_analyze_batch",
-    "bliss_b200_analyze_batch_s16",
+    "bliss_b200_analyze_batch_s16", "bliss_b200_analyze_batch_pcm", "bliss_b200_pcm_to_mono",
     "bliss_b200_analyze_batch_device", "bliss_b200_feature_weights", "bliss_b200_distance",
     "bliss_b200_distance_matrix", "bliss_b200_distance_matrix_device", "bliss_b200_closest_to_songs",
     "bliss_b200_song_to_song", "bliss_b200_stft512_mag_device", "bliss_b200_analyze_taps",
@@ -73,6 +73,8 @@ def load():
     L.bliss_b200_analyze.argtypes = [vp, C.c_uint64, C.c_uint16, vp]
     L.bliss_b200_analyze_batch.argtypes = [vp, u64p, C.c_uint32, C.c_uint16, vp, i32p]
     L.bliss_b200_analyze_batch_s16.argtypes = [vp, u64p, C.c_uint32, C.c_uint16, vp, i32p]
+    L.bliss_b200_analyze_batch_pcm.argtypes = [vp, u64p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint16, vp, i32p]
+    L.bliss_b200_pcm_to_mono.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint32, vp]
     L.bliss_b200_analyze_batch_device.argtypes = [vp, u64p, u64p, C.c_uint32, C.c_uint16, vp, i32p, vp]
     L.bliss_b200_feature_weights.argtypes = [C.c_uint16, vp]
     L.bliss_b200_distance.argtypes = [vp, vp, C.c_uint32, C.c_int, vp, f32p]
@@ -203,6 +205,51 @@ def analyze_batch_s16_ptrs(ptrs, lens, version, out, status):
     L = lib()
     check(L.bliss_b200_analyze_batch_s16(ptrs, lens, len(lens), version, out.ctypes.data,
                                          status.ctypes.data_as(C.POINTER(C.c_int32))))
+
+
+PCM_S16, PCM_S32, PCM_F32 = 1, 2, 3
+_PCM_FORMATS = {np.dtype(np.int16): PCM_S16, np.dtype(np.int32): PCM_S32, np.dtype(np.float32): PCM_F32}
+
+
+def _frames(a):
+    """[n_frames] or [n_frames, channels] int16 / int32 / float32 -> (contiguous 2-D array, format code)"""
+    a = np.ascontiguousarray(a)
+    if a.dtype not in _PCM_FORMATS:
+        raise TypeError("PCM frames must be int16, int32 or float32, not %s" % a.dtype)
+    if a.ndim == 1:
+        a = a[:, None]
+    if a.ndim != 2:
+        raise ValueError("PCM frames must be [n_frames] or [n_frames, channels]")
+    return a, _PCM_FORMATS[a.dtype]
+
+
+def analyze_batch_pcm(frames, sample_rate=22050, version=2):
+    """interleaved frames as the codec delivers them ([n_frames, channels] int16 / int32 / float32 arrays of ONE
+    format and channel count, 22 050 Hz): sample-format conversion and down-mix run on the device"""
+    L = lib()
+    arrs = [_frames(f) for f in frames]
+    n = len(arrs)
+    out = np.zeros((n, feature_count(version)), np.float32)
+    status = np.zeros(n, np.int32)
+    if n == 0:
+        return status, out
+    fmt, ch = arrs[0][1], arrs[0][0].shape[1]
+    if any(f != fmt or a.shape[1] != ch for a, f in arrs):
+        raise ValueError("one call takes one sample format and one channel count")
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data if a.size else None for a, _ in arrs])
+    lens = (C.c_uint64 * n)(*[a.shape[0] for a, _ in arrs])
+    check(L.bliss_b200_analyze_batch_pcm(ptrs, lens, n, fmt, ch, int(sample_rate), version, out.ctypes.data,
+                                         status.ctypes.data_as(C.POINTER(C.c_int32))))
+    return status, out
+
+
+def pcm_to_mono(frames):
+    """the conversion alone: what PreAnalyzedSong.sample_array holds for such a source"""
+    L = lib()
+    a, fmt = _frames(frames)
+    out = np.zeros(a.shape[0], np.float32)
+    check(L.bliss_b200_pcm_to_mono(a.ctypes.data if a.size else None, a.shape[0], fmt, a.shape[1], out.ctypes.data))
+    return out
 
 
 def analyze(pcm, version=2):

@@ -43,6 +43,7 @@ int launch_finalize(const SongDesc *, int, const float *, const float *, const f
                     const PeerRows &, cudaStream_t);
 int launch_wave_setup(const void *, void *, size_t, unsigned int *, unsigned int *, unsigned int, cudaStream_t);
 int launch_s16_to_f32(const short *, float *, size_t, cudaStream_t);
+int launch_pcm_to_mono(const void *, float *, size_t, int, unsigned int, cudaStream_t);
 int launch_gather_barrier(unsigned int *const *, int, int, unsigned int, unsigned long long, cudaStream_t);
 int launch_distance_matrix(const float *, unsigned int, const float *, unsigned int, int, int, const float *,
                            float *, cudaStream_t);
@@ -592,6 +593,7 @@ const char *bliss_b200_strerror(int code) {
         case BLISS_B200_E_NOMEM: return "workspace limit too small";
         case BLISS_B200_E_NO_DEVICE: return "no CUDA device (no CPU fallback exists)";
         case BLISS_B200_E_TIMEOUT: return "a peer never reached the gather barrier";
+        case BLISS_B200_E_UNSUPPORTED: return "unsupported input (sample rate other than 22050 Hz)";
         default: return "unknown";
     }
 }
@@ -878,13 +880,23 @@ int bliss_b200_gather_destroy(bliss_b200_gather *ga) {
 }  // extern "C" (the host path below is a template)
 
 // host buffers: chunks of songs are copied on the copy stream while earlier chunks compute
-// T = float: the decoder's output as the reference hands it to Song::analyze; T = int16_t: signed 16-bit mono
-// 22 050 Hz samples, converted on the device (x / 32768, what swresample's s16 -> flt conversion does) so that
-// only half the bytes cross PCIe.
-template <typename T>
-static int analyze_host_locked(const T *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
-                               uint16_t ver, float *out, int32_t *status, bool debug) {
-    constexpr bool kS16 = sizeof(T) == 2;
+// HostPcm describes what the host pointers hold.  {F32, 1}: the decoder's output as the reference hands it to
+// Song::analyze, copied straight into the PCM buffer.  Anything else (interleaved s16 / s32 / f32 frames of
+// `channels` channels at 22 050 Hz) lands in a raw staging buffer and is converted / down-mixed on the device
+// behind its copy (wave_setup.cu), so that e.g. 16-bit mono material sends half the bytes over PCIe.
+struct HostPcm {
+    int fmt;            // BLISS_B200_PCM_*
+    uint32_t channels;
+    size_t frame_bytes() const { return (size_t)(fmt == BLISS_B200_PCM_S16 ? 2 : 4) * channels; }
+    bool direct() const { return fmt == BLISS_B200_PCM_F32 && channels == 1; }
+};
+
+static int analyze_host_locked(const void *const *pcm_v, const uint64_t *n_samples, uint32_t n_songs,
+                               uint16_t ver, float *out, int32_t *status, bool debug,
+                               HostPcm hp = HostPcm{BLISS_B200_PCM_F32, 1}) {
+    const char *const *pcm = reinterpret_cast<const char *const *>(pcm_v);
+    const bool kRaw = !hp.direct();
+    const size_t fb = hp.frame_bytes();
     const uint32_t dim = bliss_b200_feature_count(ver);
     CK(g.feats.ensure((size_t)n_songs * dim * 4));
     // The path is PCIe-bound (15.9 MB per 3-min song).  Songs travel in chunks through a ring of FOUR
@@ -930,7 +942,7 @@ static int analyze_host_locked(const T *const *pcm, const uint64_t *n_samples, u
         lens.clear();
         while (first + count < n_songs) {
             const size_t len = align_up((size_t)n_samples[first + count], 4);
-            if (count > 0 && (samples + len) * 4 > budget) break;
+            if (count > 0 && (samples + len) * std::max<size_t>(4, fb) > budget) break;  // the larger of the two buffers
             offs.push_back(samples);
             lens.push_back(n_samples[first + count]);
             samples += len;
@@ -940,7 +952,7 @@ static int analyze_host_locked(const T *const *pcm, const uint64_t *n_samples, u
         for (int k = 0; k < N_SETS; k++)  // buffer b free again (also: the host may reallocate it)
             if (done_used[b][k]) CK(cudaEventSynchronize(ev_done[b][k]));
         CK(g.pcm[b].ensure(std::max<size_t>(samples, 4) * 4));
-        if (kS16) CK(g.raw16[b].ensure(std::max<size_t>(samples, 4) * 2));
+        if (kRaw) CK(g.raw16[b].ensure(std::max<size_t>(samples, 4) * fb));
         if (trace) {
             cudaEvent_t e;
             CK(cudaEventCreate(&e));
@@ -954,18 +966,22 @@ static int analyze_host_locked(const T *const *pcm, const uint64_t *n_samples, u
             uint32_t j = i;
             size_t run = (size_t)lens[i];
             while (j + 1 < count && lens[j + 1] > 0 && (lens[j] & 3u) == 0 &&
-                   pcm[first + j + 1] == pcm[first + j] + lens[j]) {
+                   pcm[first + j + 1] == pcm[first + j] + (size_t)lens[j] * fb) {
                 j++;
                 run += (size_t)lens[j];
             }
-            void *dst = kS16 ? (void *)(g.raw16[b].as<short>() + offs[i]) : (void *)(g.pcm[b].as<float>() + offs[i]);
-            CK(cudaMemcpyAsync(dst, pcm[first + i], run * sizeof(T), cudaMemcpyHostToDevice, g.copy_stream));
+            void *dst = kRaw ? (void *)(g.raw16[b].as<char>() + (size_t)offs[i] * fb) : (void *)(g.pcm[b].as<float>() + offs[i]);
+            CK(cudaMemcpyAsync(dst, pcm[first + i], run * fb, cudaMemcpyHostToDevice, g.copy_stream));
             i = j + 1;
         }
         if (rc) break;
-        if (kS16) {  // same offsets in both buffers; runs behind the copies on the copy stream
-            g.launches += (unsigned long long)launch_s16_to_f32(g.raw16[b].as<short>(), g.pcm[b].as<float>(), samples,
-                                                               g.copy_stream);
+        if (kRaw) {  // same frame offsets in both buffers; runs behind the copies on the copy stream
+            if (hp.fmt == BLISS_B200_PCM_S16 && hp.channels == 1)
+                g.launches += (unsigned long long)launch_s16_to_f32(g.raw16[b].as<short>(), g.pcm[b].as<float>(), samples,
+                                                                   g.copy_stream);
+            else
+                g.launches += (unsigned long long)launch_pcm_to_mono(g.raw16[b].p, g.pcm[b].as<float>(), samples, hp.fmt,
+                                                                    hp.channels, g.copy_stream);
             CK(cudaGetLastError());
         }
         CK(cudaEventRecord(ev_copy[b], g.copy_stream));
@@ -1045,7 +1061,7 @@ int bliss_b200_analyze_batch(const float *const *pcm, const uint64_t *n_samples,
     if (check_version(ver)) return BLISS_B200_E_ARG;
     if (n_songs == 0) return BLISS_B200_OK;
     if (!pcm || !n_samples || !out) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
-    return analyze_host_locked(pcm, n_samples, n_songs, ver, out, status, false);
+    return analyze_host_locked(reinterpret_cast<const void *const *>(pcm), n_samples, n_songs, ver, out, status, false);
 }
 
 int bliss_b200_analyze_batch_s16(const int16_t *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
@@ -1054,7 +1070,52 @@ int bliss_b200_analyze_batch_s16(const int16_t *const *pcm, const uint64_t *n_sa
     if (check_version(ver)) return BLISS_B200_E_ARG;
     if (n_songs == 0) return BLISS_B200_OK;
     if (!pcm || !n_samples || !out) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
-    return analyze_host_locked(pcm, n_samples, n_songs, ver, out, status, false);
+    return analyze_host_locked(reinterpret_cast<const void *const *>(pcm), n_samples, n_songs, ver, out, status, false,
+                               HostPcm{BLISS_B200_PCM_S16, 1});
+}
+
+static int check_pcm_format(int fmt, uint32_t channels, uint32_t sample_rate) {
+    if (fmt != BLISS_B200_PCM_S16 && fmt != BLISS_B200_PCM_S32 && fmt != BLISS_B200_PCM_F32) {
+        g_last_error = "unknown sample format " + std::to_string(fmt) + " (BLISS_B200_PCM_S16 / _S32 / _F32)";
+        return BLISS_B200_E_ARG;
+    }
+    if (channels == 0 || channels > BLISS_B200_PCM_MAX_CHANNELS) {
+        g_last_error = "channel count " + std::to_string(channels) + " outside 1.." + std::to_string(BLISS_B200_PCM_MAX_CHANNELS);
+        return BLISS_B200_E_ARG;
+    }
+    if (sample_rate != (uint32_t)SAMPLE_RATE) {
+        g_last_error = "sample rate " + std::to_string(sample_rate) + " Hz: this library holds no resampler, the decoder "
+                       "must deliver 22050 Hz (src/lib.rs:143)";
+        return BLISS_B200_E_UNSUPPORTED;
+    }
+    return 0;
+}
+
+int bliss_b200_analyze_batch_pcm(const void *const *pcm, const uint64_t *n_frames, uint32_t n_songs, int sample_format,
+                                 uint32_t channels, uint32_t sample_rate, uint16_t ver, float *out, int32_t *status) {
+    REQUIRE_INIT();
+    if (check_version(ver)) return BLISS_B200_E_ARG;
+    if (int rc = check_pcm_format(sample_format, channels, sample_rate)) return rc;
+    if (n_songs == 0) return BLISS_B200_OK;
+    if (!pcm || !n_frames || !out) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
+    return analyze_host_locked(pcm, n_frames, n_songs, ver, out, status, false, HostPcm{sample_format, channels});
+}
+
+int bliss_b200_pcm_to_mono(const void *pcm, uint64_t n_frames, int sample_format, uint32_t channels, float *out) {
+    REQUIRE_INIT();
+    if (int rc = check_pcm_format(sample_format, channels, (uint32_t)SAMPLE_RATE)) return rc;
+    if (n_frames == 0) return BLISS_B200_OK;
+    if (!pcm || !out) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
+    const HostPcm hp{sample_format, channels};
+    const size_t padded = align_up((size_t)n_frames, 4);
+    CK(g.raw16[0].ensure(padded * hp.frame_bytes()));
+    CK(g.pcm[0].ensure(padded * 4));
+    CK(cudaMemcpyAsync(g.raw16[0].p, pcm, (size_t)n_frames * hp.frame_bytes(), cudaMemcpyHostToDevice, g.stream));
+    g.launches += (unsigned long long)launch_pcm_to_mono(g.raw16[0].p, g.pcm[0].as<float>(), padded, hp.fmt, hp.channels, g.stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, g.pcm[0].p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return BLISS_B200_OK;
 }
 
 int bliss_b200_analyze(const float *pcm, uint64_t n, uint16_t ver, float *out) {
@@ -1065,7 +1126,7 @@ int bliss_b200_analyze(const float *pcm, uint64_t n, uint16_t ver, float *out) {
         REQUIRE_INIT();
         if (check_version(ver)) return BLISS_B200_E_ARG;
         if (!out || (!pcm && n > 0)) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
-        int rc = analyze_host_locked(p, len, 1, ver, out, &status, false);
+        int rc = analyze_host_locked(reinterpret_cast<const void *const *>(p), len, 1, ver, out, &status, false);
         if (rc) return rc;
     }
     return status;
@@ -1078,7 +1139,7 @@ int bliss_b200_analyze_taps(const float *pcm, uint64_t n, uint16_t ver, float *o
     int32_t status = 0;
     const float *p[1] = {pcm};
     uint64_t len[1] = {n};
-    int rc = analyze_host_locked(p, len, 1, ver, out, &status, true);
+    int rc = analyze_host_locked(reinterpret_cast<const void *const *>(p), len, 1, ver, out, &status, true);
     if (rc) return rc;
     if (status != 0 || !t) return status;
     const SongGeom q = geom_of(n);

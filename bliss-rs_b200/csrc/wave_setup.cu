@@ -65,4 +65,57 @@ int launch_s16_to_f32(const short *in, float *out, size_t n, cudaStream_t st) {
     return 1;
 }
 
+// ---- interleaved PCM -> mono f32 (bliss_b200_analyze_batch_pcm, bliss_b200_pcm_to_mono) ------------------
+// The sample-format and down-mix steps of the reference's decoders for sources that already run at
+// 22 050 Hz (a resampler is not part of this library):
+//   s16 -> flt   x * 2^-15, s32 -> flt   x * 2^-31      swresample's conversions behind
+//                                                       src/song/decoder/ffmpeg.rs:36-109 (symphonia's
+//                                                       `sample as f32 / 32768.0` rounds identically)
+//   stereo       c L + c R, c = (float)sqrt(1/2), products and sum rounded separately: swresample's
+//                default FL+FR -> FC matrix for float output, "averaging the channels and multiplying by
+//                the square root of 2" in the words of src/song/decoder/symphonia.rs:260-262; pinned by
+//                the decoder test of data/s16_stereo_22_5kHz.flac, src/song/decoder/ffmpeg.rs:447-452
+//   > 2 channels mean of the channels, summed in channel order: src/song/decoder/symphonia.rs:289-299
+// FMT: 1 = s16, 2 = s32, 3 = f32 (include/bliss_b200.h).  Flat over the chunk's frames (the padding frames
+// between songs are converted too and never read); n_frames is a multiple of 4: four frames per thread,
+// one 16-byte store.
+template <int FMT>
+__device__ __forceinline__ float pcm_sample(const void *in, size_t i) {
+    if (FMT == 1) return __fmul_rn((float)static_cast<const short *>(in)[i], 1.0f / 32768.0f);
+    if (FMT == 2) return __fmul_rn((float)static_cast<const int *>(in)[i], 1.0f / 2147483648.0f);
+    return static_cast<const float *>(in)[i];
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256)
+pcm_to_mono_kernel(const void *__restrict__ in, float *__restrict__ out, size_t n_frames, unsigned int channels) {
+    const size_t f0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (f0 >= n_frames) return;
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const size_t base = (f0 + k) * channels;
+        if (channels == 1) {
+            r[k] = pcm_sample<FMT>(in, base);
+        } else if (channels == 2) {
+            const float c = 0.70710678118654752440f;
+            r[k] = __fadd_rn(__fmul_rn(pcm_sample<FMT>(in, base), c), __fmul_rn(pcm_sample<FMT>(in, base + 1), c));
+        } else {
+            float s = 0.f;
+            for (unsigned int ch = 0; ch < channels; ch++) s = __fadd_rn(s, pcm_sample<FMT>(in, base + ch));
+            r[k] = __fdiv_rn(s, (float)channels);
+        }
+    }
+    *reinterpret_cast<float4 *>(out + f0) = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+int launch_pcm_to_mono(const void *in, float *out, size_t n_frames, int fmt, unsigned int channels, cudaStream_t st) {
+    if (n_frames == 0) return 0;
+    const unsigned int grid = (unsigned int)(((n_frames + 3) / 4 + 255) / 256);
+    if (fmt == 1) pcm_to_mono_kernel<1><<<grid, 256, 0, st>>>(in, out, n_frames, channels);
+    else if (fmt == 2) pcm_to_mono_kernel<2><<<grid, 256, 0, st>>>(in, out, n_frames, channels);
+    else pcm_to_mono_kernel<3><<<grid, 256, 0, st>>>(in, out, n_frames, channels);
+    return 1;
+}
+
 }  // namespace bliss

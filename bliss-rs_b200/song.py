@@ -234,6 +234,30 @@ def analyze_batch(sample_arrays: Sequence, analysis_options: AnalysisOptions = N
     return out
 
 
+def analyze_batch_pcm(frames: Sequence, sample_rate: int = SAMPLE_RATE, analysis_options: AnalysisOptions = None) -> List:
+    """analyze_batch for sources the codec delivers as interleaved [n_frames, channels] int16 / int32 / float32
+    frames at 22 050 Hz: the decoders' sample-format conversion and down-mix (src/song/decoder/ffmpeg.rs:36-109,
+    symphonia.rs:260-300) run on the device.  One format and channel count per call; any other sample rate raises
+    (resampling stays with the decoder)."""
+    analysis_options = analysis_options or AnalysisOptions()
+    ver = FeaturesVersion(analysis_options.features_version)
+    status, feats = native.analyze_batch_pcm(frames, sample_rate, int(ver))
+    return [_result_item(st, row, ver) for st, row in zip(status, feats)]
+
+
+def pcm_to_mono(frames) -> np.ndarray:
+    """PreAnalyzedSong.sample_array of such a source (src/song/decoder.rs:64)"""
+    return native.pcm_to_mono(frames)
+
+
+def _result_item(st, row, ver):
+    if st == 0:
+        return Analysis(row, ver)
+    if st == 1:
+        return AnalysisError("empty or too short song.")
+    return AnalysisError("internal error in the B200 analysis backend (status %d)" % st)
+
+
 @dataclass
 class PreAnalyzedSong:
     """src/song/decoder.rs:34-67"""

@@ -34,6 +34,7 @@ extern "C" {
 #define BLISS_B200_E_NOMEM (-4)    /* one song alone does not fit the workspace limit */
 #define BLISS_B200_E_NO_DEVICE (-5) /* no usable CUDA device: there is NO CPU fallback */
 #define BLISS_B200_E_TIMEOUT (-6)  /* a peer never reached the gather barrier */
+#define BLISS_B200_E_UNSUPPORTED (-7) /* input this library does not take (a sample rate other than 22 050 Hz) */
 
 /* ---- per-song status (BlissResult<Analysis>) ------------------------------------ */
 #define BLISS_B200_SONG_OK 0
@@ -85,6 +86,29 @@ int bliss_b200_analyze_batch(const float *const *pcm, const uint64_t *n_samples,
  * bliss_b200_analyze_batch on the converted samples. */
 int bliss_b200_analyze_batch_s16(const int16_t *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
                                  uint16_t features_version, float *out, int32_t *status);
+
+/* Decode-side feed, general form: interleaved frames as the container's codec delivers them, for sources that
+ * already run at 22 050 Hz -- the sample-format conversion and the down-mix to mono of the reference's decoders
+ * run on the device behind each chunk's copy:
+ *   s16 / s32 -> f32   x * 2^-15 / x * 2^-31 (swresample's conversions, src/song/decoder/ffmpeg.rs:36-109;
+ *                      symphonia's `as f32 / 32768.0` rounds identically)
+ *   2 channels         c L + c R with c = (float)sqrt(1/2) (swresample's stereo -> mono matrix for float output,
+ *                      src/song/decoder/symphonia.rs:260-262; pinned by the decoder test of
+ *                      data/s16_stereo_22_5kHz.flac, src/song/decoder/ffmpeg.rs:447-452)
+ *   > 2 channels       mean of the channels in channel order (src/song/decoder/symphonia.rs:289-299)
+ * pcm[i]: n_frames[i] frames of `channels` samples; one format per call.  sample_rate must be 22050: there is no
+ * resampler here (E_UNSUPPORTED otherwise; swresample / rubato stay on the decoder's side of the boundary).
+ * Results are bit-identical to bliss_b200_analyze_batch on the output of bliss_b200_pcm_to_mono. */
+#define BLISS_B200_PCM_S16 1
+#define BLISS_B200_PCM_S32 2
+#define BLISS_B200_PCM_F32 3
+#define BLISS_B200_PCM_MAX_CHANNELS 8
+int bliss_b200_analyze_batch_pcm(const void *const *pcm, const uint64_t *n_frames, uint32_t n_songs,
+                                 int sample_format, uint32_t channels, uint32_t sample_rate,
+                                 uint16_t features_version, float *out, int32_t *status);
+/* The conversion alone (host in, host out): what PreAnalyzedSong::sample_array (src/song/decoder.rs:64) holds
+ * for such a source.  out: n_frames floats. */
+int bliss_b200_pcm_to_mono(const void *pcm, uint64_t n_frames, int sample_format, uint32_t channels, float *out);
 
 /* Same, PCM already resident in device memory: song i is d_pcm[offsets[i] .. offsets[i]+n_samples[i]).
  * d_pcm must be 16-byte aligned; offsets/n_samples/status are HOST arrays; d_out is a DEVICE

@@ -175,6 +175,39 @@ inline std::vector<AnalysisResult> analyze_batch_s16(const std::vector<const int
     return res;
 }
 
+// Decode-side feed, general form (bliss_b200_analyze_batch_pcm): interleaved frames of one sample format and
+// channel count at 22 050 Hz; the decoders' sample-format conversion and down-mix (src/song/decoder/ffmpeg.rs:36-109,
+// symphonia.rs:260-300) run on the device.  A sample rate other than 22 050 Hz throws: resampling stays on the
+// decoder's side of the boundary.
+enum class PcmFormat : int { S16 = BLISS_B200_PCM_S16, S32 = BLISS_B200_PCM_S32, F32 = BLISS_B200_PCM_F32 };
+inline std::vector<AnalysisResult> analyze_batch_pcm(const std::vector<const void *> &frames, const std::vector<uint64_t> &n_frames,
+                                                     PcmFormat format, uint32_t channels, uint32_t sample_rate = BLISS_B200_SAMPLE_RATE,
+                                                     const AnalysisOptions &o = {}) {
+    detail::ensure_init();
+    const size_t dim = feature_count(o.features_version);
+    std::vector<float> out(dim * frames.size());
+    std::vector<int32_t> status(frames.size());
+    detail::check_call(bliss_b200_analyze_batch_pcm(frames.data(), n_frames.data(), static_cast<uint32_t>(frames.size()),
+                                                    static_cast<int>(format), channels, sample_rate,
+                                                    static_cast<uint16_t>(o.features_version), out.data(), status.data()));
+    std::vector<AnalysisResult> res;
+    res.reserve(frames.size());
+    for (size_t i = 0; i < frames.size(); i++) {
+        if (status[i] == BLISS_B200_SONG_OK)
+            res.emplace_back(Analysis(std::vector<float>(out.begin() + i * dim, out.begin() + (i + 1) * dim), o.features_version));
+        else
+            res.emplace_back(detail::status_error(status[i]));
+    }
+    return res;
+}
+// the conversion alone: PreAnalyzedSong::sample_array of such a source
+inline std::vector<float> pcm_to_mono(const void *frames, uint64_t n_frames, PcmFormat format, uint32_t channels) {
+    detail::ensure_init();
+    std::vector<float> out(n_frames);
+    detail::check_call(bliss_b200_pcm_to_mono(frames, n_frames, static_cast<int>(format), channels, out.data()));
+    return out;
+}
+
 // src/song/decoder.rs:34-67
 struct PreAnalyzedSong {
     std::string path;

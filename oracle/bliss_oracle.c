@@ -1247,3 +1247,43 @@ void bo_song_to_song(const float *seeds, uint32_t n_seeds, const float *cands, u
     }
     free(pool);
 }
+
+/* ---- decode-side feed: sample format + down-mix for sources already at 22 050 Hz ----------
+ * What the reference's decoders do between the codec's output and PreAnalyzedSong::sample_array
+ * (src/song/decoder.rs:64) when no rate change is needed:
+ *   s16 / s32 -> f32: swresample's x * (1.0f / (1 << 15)) and x * (1.0f / (1U << 31)) behind
+ *     src/song/decoder/ffmpeg.rs:36-109 (symphonia's sample conversion divides by the same powers
+ *     of two and rounds identically);
+ *   stereo: swresample's FL+FR -> FC matrix for float output, c*L + c*R with c = (float)M_SQRT1_2 --
+ *     "averaging the channels and multiplying by the square root of 2 ... recovers the exact
+ *     behavior of ffmpeg", src/song/decoder/symphonia.rs:260-262, :280-287;
+ *   more than two channels: `chunk.iter().sum::<f32>() / num_channels as f32`, :289-299.
+ * Pinned by the adler32 the reference asserts for data/s16_stereo_22_5kHz.flac
+ * (src/song/decoder/ffmpeg.rs:447-452); both channels of that file are identical, so the hash
+ * pins the two constants but not the rounding order of the two products.
+ * fmt: 1 = s16, 2 = s32, 3 = f32. */
+static inline float bo_pcm_sample(const void *in, int fmt, size_t i) {
+    if (fmt == 1) return (float)((const int16_t *)in)[i] * (1.0f / 32768.0f);
+    if (fmt == 2) return (float)((const int32_t *)in)[i] * (1.0f / 2147483648.0f);
+    return ((const float *)in)[i];
+}
+
+int bo_pcm_to_mono(const void *pcm, uint64_t n_frames, int fmt, uint32_t channels, float *out) {
+    if (fmt < 1 || fmt > 3 || channels == 0) return -1;
+    const float c = (float)0.70710678118654752440; /* M_SQRT1_2 */
+    for (uint64_t f = 0; f < n_frames; f++) {
+        const size_t base = (size_t)f * channels;
+        if (channels == 1) {
+            out[f] = bo_pcm_sample(pcm, fmt, base);
+        } else if (channels == 2) {
+            const float l = bo_pcm_sample(pcm, fmt, base) * c;
+            const float r = bo_pcm_sample(pcm, fmt, base + 1) * c;
+            out[f] = l + r;
+        } else {
+            float s = 0.f;
+            for (uint32_t ch = 0; ch < channels; ch++) s += bo_pcm_sample(pcm, fmt, base + ch);
+            out[f] = s / (float)channels;
+        }
+    }
+    return 0;
+}

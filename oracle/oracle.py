@@ -78,6 +78,8 @@ def lib():
         L.bo_mahalanobis_distance.restype = C.c_float
         L.bo_default_distance.argtypes = [f32p, f32p, C.c_int]
         L.bo_default_distance.restype = C.c_float
+        L.bo_pcm_to_mono.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, f32p]
+        L.bo_pcm_to_mono.restype = C.c_int
         L.bo_feature_weights.argtypes = [C.c_int, f32p]
         L.bo_closest_to_songs.argtypes = [f32p, C.c_uint32, f32p, C.c_uint32, C.c_uint32,
                                           C.c_void_p, u32p, C.c_void_p]
@@ -328,3 +330,18 @@ def fft(z):
     v = z.view(np.float32)
     lib().bo_fft(v, z.size)
     return z
+
+
+PCM_FORMATS = {np.dtype(np.int16): 1, np.dtype(np.int32): 2, np.dtype(np.float32): 3}
+
+
+def pcm_to_mono(frames):
+    """interleaved [n_frames, channels] (or [n_frames]) s16 / s32 / f32 at 22 050 Hz -> mono f32, as the
+    reference's decoders do it (src/song/decoder/ffmpeg.rs:36-109, symphonia.rs:260-300)"""
+    a = np.ascontiguousarray(frames)
+    if a.ndim == 1:
+        a = a[:, None]
+    out = np.zeros(a.shape[0], np.float32)
+    rc = lib().bo_pcm_to_mono(a.ctypes.data, a.shape[0], PCM_FORMATS[a.dtype], a.shape[1], out)
+    assert rc == 0
+    return out

@@ -72,6 +72,26 @@ int main() {
         auto r16 = analyze_batch_s16({q.data()}, {q.size()});
         auto r32 = analyze_batch({back.data()}, {back.size()});
         if (std::get<Analysis>(r16[0]).as_vec() != std::get<Analysis>(r32[0]).as_vec()) return 13;
+        // interleaved stereo 16-bit frames == f32 entry point on the down-mixed samples (c L + c R, c = sqrt(1/2))
+        std::vector<int16_t> st(2 * q.size());
+        for (size_t i = 0; i < q.size(); i++) {
+            st[2 * i] = q[i];
+            st[2 * i + 1] = (int16_t)(q[i] / 2);
+        }
+        const std::vector<float> mono = pcm_to_mono(st.data(), q.size(), PcmFormat::S16, 2);
+        const float c = 0.70710678118654752440f;
+        for (size_t i = 0; i < q.size(); i += 997) {
+            const volatile float l = ((float)st[2 * i] / 32768.0f) * c, r = ((float)st[2 * i + 1] / 32768.0f) * c;
+            if (mono[i] != l + r) return 15;
+        }
+        auto rst = analyze_batch_pcm({st.data()}, {q.size()}, PcmFormat::S16, 2);
+        auto rmo = analyze_batch({mono.data()}, {mono.size()});
+        if (std::get<Analysis>(rst[0]).as_vec() != std::get<Analysis>(rmo[0]).as_vec()) return 16;
+        try {
+            analyze_batch_pcm({st.data()}, {q.size()}, PcmFormat::S16, 2, 44100);
+            return 17;  // no resampler: must refuse
+        } catch (const BlissError &) {
+        }
         // playlist: closest_to_songs keeps the seed first
         std::vector<float> cands;
         for (const Song *x : {&t, &s}) cands.insert(cands.end(), x->analysis->as_vec().begin(), x->analysis->as_vec().end());

@@ -133,7 +133,8 @@ def _subframe(br: BitReader, blocksize: int, bps: int):
     return s
 
 
-def decode_flac_mono16(path: str) -> np.ndarray:
+def decode_flac(path: str, expect):
+    """-> int64 array [channels, n_frames]; `expect` = (rate, channels, bits per sample) of the stream"""
     data = open(path, "rb").read()
     assert data[:4] == b"fLaC"
     pos = 4
@@ -148,14 +149,14 @@ def decode_flac_mono16(path: str) -> np.ndarray:
             ch = ((v >> 41) & 7) + 1
             bps = ((v >> 36) & 31) + 1
             total = v & ((1 << 36) - 1)
-            assert (rate, ch, bps) == (22050, 1, 16), (rate, ch, bps)
+            assert (rate, ch, bps) == tuple(expect), (rate, ch, bps)
         pos += 4 + ln
         if hdr & 0x80:
             break
-    out = []
+    out = [[] for _ in range(ch)]
     br = BitReader(data, pos)
     bs_table = {1: 192, 2: 576, 3: 1152, 4: 2304, 5: 4608}
-    while len(out) < total:
+    while len(out[0]) < total:
         assert br.read(14) == 0x3FFE, "lost frame sync"
         br.read(1)
         br.read(1)
@@ -164,7 +165,7 @@ def decode_flac_mono16(path: str) -> np.ndarray:
         ch_code = br.read(4)
         br.read(3)
         br.read(1)
-        assert ch_code == 0
+        assert ch_code <= 10
         br.read_utf8()
         if bs_code == 6:
             blocksize = br.read(8) + 1
@@ -179,10 +180,34 @@ def decode_flac_mono16(path: str) -> np.ndarray:
         elif sr_code in (13, 14):
             br.read(16)
         br.read(8)  # crc8
-        out.extend(_subframe(br, blocksize, 16))
+        if ch_code < 8:      # independent channels
+            subs = [_subframe(br, blocksize, bps) for _ in range(ch_code + 1)]
+        elif ch_code == 8:   # left + side
+            left = _subframe(br, blocksize, bps)
+            side = _subframe(br, blocksize, bps + 1)
+            subs = [left, [a - b for a, b in zip(left, side)]]
+        elif ch_code == 9:   # side + right
+            side = _subframe(br, blocksize, bps + 1)
+            right = _subframe(br, blocksize, bps)
+            subs = [[a + b for a, b in zip(side, right)], right]
+        else:                # mid + side
+            mid = _subframe(br, blocksize, bps)
+            side = _subframe(br, blocksize, bps + 1)
+            subs = [[], []]
+            for m, d in zip(mid, side):
+                m = (m << 1) | (d & 1)
+                subs[0].append((m + d) >> 1)
+                subs[1].append((m - d) >> 1)
+        assert len(subs) == ch
+        for dst, sub in zip(out, subs):
+            dst.extend(sub)
         br.align()
         br.read(16)  # crc16
-    pcm = np.array(out[:total], dtype=np.int64)
+    return np.array([c[:total] for c in out], dtype=np.int64)
+
+
+def decode_flac_mono16(path: str) -> np.ndarray:
+    pcm = decode_flac(path, (22050, 1, 16))[0]
     assert pcm.min() >= -32768 and pcm.max() <= 32767
     return pcm.astype(np.int16)
 
@@ -207,6 +232,20 @@ def main():
     dec = np.load(os.path.join(DATA, "librosa-decoded.npy"))
     assert np.array_equal(dec, piano.astype(np.float32) / np.float32(32768.0))
     g["pcm_piano"] = piano
+
+    # data/s16_stereo_22_5kHz.flac: the decoder test src/song/decoder/ffmpeg.rs:447-452 asserts the adler32 of
+    # ffmpeg's mono f32le output, i.e. of swresample's s16 -> flt conversion followed by its stereo -> mono
+    # matrix c*L + c*R, c = (float)sqrt(1/2) (no rate change: the file runs at 22 050 Hz).  Both channels of
+    # this file are identical, so the hash pins the two constants, not the rounding order of the products.
+    st = decode_flac(os.path.join(DATA, "s16_stereo_22_5kHz.flac"), (22050, 2, 16))
+    assert st.min() >= -32768 and st.max() <= 32767
+    st = np.ascontiguousarray(st.T.astype(np.int16))  # interleaved frames [n, 2]
+    k, c = np.float32(1.0 / 32768.0), np.float32(np.sqrt(0.5))
+    mono = (st[:, 0].astype(np.float32) * k) * c + (st[:, 1].astype(np.float32) * k) * c
+    a = zlib.adler32(mono.astype("<f4").tobytes()) & 0xFFFFFFFF
+    assert a == 0x1D7B2D6D, hex(a)  # src/song/decoder/ffmpeg.rs:447-452
+    g["pcm_s16_stereo"] = st
+    g["adler32_stereo_downmix"] = np.uint32(a)
 
     for name in ["chroma-filter", "chroma-interval", "chroma", "interval-feature-matrix",
                  "librosa-stft", "pitch-tuning", "spectrum-chroma-mags",

@@ -278,3 +278,44 @@ def test_fft_matches_numpy():
         ref = np.fft.fft(z.astype(np.complex128))
         err = np.abs(O.fft(z) - ref).max() / np.abs(ref).max()
         assert err < 2e-6
+
+
+# ---- song/decoder/*.rs: sample format + down-mix of sources already at 22 050 Hz ----------
+
+def _adler32_f32(x):
+    import zlib
+    return zlib.adler32(np.asarray(x, "<f4").tobytes()) & 0xFFFFFFFF
+
+
+def test_pcm_to_mono_decoder_hashes(golden):
+    # src/song/decoder/ffmpeg.rs:454-462 test_decode_mono, :447-452 test_resample_stereo, :523-527 test_decode_wav:
+    # the adler32 of the decoder's f32le output
+    assert _adler32_f32(O.pcm_to_mono(golden["pcm_s16_mono"])) == 0x5E01930B
+    assert _adler32_f32(O.pcm_to_mono(golden["pcm_piano"])) == 0xDE831E82
+    st = golden["pcm_s16_stereo"]
+    assert st.shape[1] == 2
+    mono = O.pcm_to_mono(st)
+    assert _adler32_f32(mono) == 0x1D7B2D6D == int(golden["adler32_stereo_downmix"])
+    # "averaging the channels and multiplying by the square root of 2" (src/song/decoder/symphonia.rs:260-287) agrees
+    # with it within the f32::EPSILON mean difference of compare_ffmpeg_to_symphonia_for_all_test_songs (:703-709)
+    f = st.astype(np.float32) / np.float32(32768.0)
+    sym = (f[:, 0] + f[:, 1]) * np.float32(np.sqrt(2.0)) / np.float32(2.0)
+    assert np.abs(sym - mono).mean() < np.finfo(np.float32).eps
+
+
+def test_pcm_to_mono_formats():
+    rng = np.random.default_rng(5)
+    k15, k31 = np.float32(2.0 ** -15), np.float32(2.0 ** -31)
+    c = np.float32(np.sqrt(0.5))
+    s16 = rng.integers(-32768, 32768, (1000, 2), dtype=np.int16)
+    want = (s16[:, 0].astype(np.float32) * k15) * c + (s16[:, 1].astype(np.float32) * k15) * c
+    assert np.array_equal(O.pcm_to_mono(s16), want)
+    s32 = rng.integers(-2 ** 31, 2 ** 31, (1000, 1), dtype=np.int64).astype(np.int32)
+    assert np.array_equal(O.pcm_to_mono(s32), s32[:, 0].astype(np.float32) * k31)
+    # more than two channels: chunk.iter().sum::<f32>() / n (src/song/decoder/symphonia.rs:289-299)
+    f6 = rng.standard_normal((777, 6)).astype(np.float32)
+    acc = np.zeros(777, np.float32)
+    for ch in range(6):
+        acc = acc + f6[:, ch]
+    assert np.array_equal(O.pcm_to_mono(f6), acc / np.float32(6))
+    assert np.array_equal(O.pcm_to_mono(f6[:, 0].copy()), f6[:, 0])
