@@ -505,8 +505,17 @@ int build_tables() {
             twA[k1 * 32 + l] = cpx{(float)cos(a), (float)sin(a)};
         }
     // periodic Hann of utils::stft (utils.rs:36-38)
-    std::vector<float> hann(8192);
+    std::vector<float> hann(8192 + 4 * 256);
     for (int i = 0; i < 8192; i++) hann[i] = 0.5f - 0.5f * cosf(2.f * (float)i * PI_F / 8192.f);
+    // behind the window: per-thread phase (cos e, cos o, sin e, sin o) of samples 2 tid, 2 tid + 1 for the
+    // synthesised-window variant of stft8192_kernel (VARIANT_WINSYN, rfft8192.cuh hann_pair)
+    for (int t = 0; t < 256; t++) {
+        const double te = 2.0 * M_PI * (double)(2 * t) / 8192.0, to = 2.0 * M_PI * (double)(2 * t + 1) / 8192.0;
+        hann[8192 + 4 * t + 0] = (float)cos(te);
+        hann[8192 + 4 * t + 1] = (float)cos(to);
+        hann[8192 + 4 * t + 2] = (float)sin(te);
+        hann[8192 + 4 * t + 3] = (float)sin(to);
+    }
     // pass-1 twiddles [k1][b] = W4096^(b k1), pass-2 twiddles [k2][j] = W256^(j k2), and W8192^t, t < 256
     // (real-FFT untangling): rfft8192.cuh
     std::vector<cpx> tw4(4096), tw2(256), tw(256);

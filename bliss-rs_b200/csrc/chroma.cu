@@ -113,7 +113,19 @@ __device__ __forceinline__ void epilogue_pairs(const cpx (&v)[16], const cpx *pm
     }
 }
 
-template <bool PAIR_EPILOGUE>
+// VAR (experimental cuts of pass 1, behind bliss_b200_set_variant; 0 = the measured kernel):
+constexpr int K3V_TWPROD = 1;  // pass-1 twiddles: 4 loads + 11 products instead of 15 loads (rfft8192.cuh)
+constexpr int K3V_WINSYN = 2;  // Hann pairs from the thread's phase instead of 16 window loads
+
+template <int Q>
+__device__ __forceinline__ void window_synth(cpx (&v)[16], cpx cw, cpx sw) {
+    if constexpr (Q < 16) {
+        v[Q] = pmul(v[Q], r8k::hann_pair<Q>(cw, sw));
+        window_synth<Q + 1>(v, cw, sw);
+    }
+}
+
+template <bool PAIR_EPILOGUE, int VAR = 0>
 __global__ void __launch_bounds__(K3_THREADS, 4)
 stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
                 const unsigned int *__restrict__ frame_prefix, int n_songs,
@@ -154,7 +166,31 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     {
         cpx v[16];
         const float2 *ph = reinterpret_cast<const float2 *>(hann) + tid;
-        if (interior) {
+        if constexpr ((VAR & K3V_WINSYN) != 0) {
+            // samples only; the window comes from the thread's phase entry behind the 8192 window values
+            const float4 pw = __ldg(reinterpret_cast<const float4 *>(hann + CH_WIN) + tid);
+            if (interior) {
+                const float *pa = x + s0 + 2 * tid;
+                if ((reinterpret_cast<size_t>(pa) & 7) == 0) {
+                    const float2 *pa2 = reinterpret_cast<const float2 *>(pa);
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        const float2 xx = __ldg(pa2 + 256 * q);
+                        v[q] = cpx{xx.x, xx.y};
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) v[q] = cpx{__ldg(pa + 512 * q), __ldg(pa + 512 * q + 1)};
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const long long i0 = (long long)s0 + 2 * (tid + 256 * q);
+                    v[q] = cpx{r8k::reflect_sample(x, n, i0), r8k::reflect_sample(x, n, i0 + 1)};
+                }
+            }
+            window_synth<0>(v, cpx{pw.x, pw.y}, cpx{pw.z, pw.w});
+        } else if (interior) {
             const float *pa = x + s0 + 2 * tid;
             if ((reinterpret_cast<size_t>(pa) & 7) == 0) {  // even frames of an 8-byte aligned song: one 64-bit load per pair
                 const float2 *pa2 = reinterpret_cast<const float2 *>(pa);  // (half the L1 wavefronts of two 32-bit loads)
@@ -179,7 +215,8 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
                 v[q] = pmul(cpx{r8k::reflect_sample(x, n, i0), r8k::reflect_sample(x, n, i0 + 1)}, cpx{w.x, w.y});
             }
         }
-        r8k::pass1_store(tid, v, tw1, buf);
+        if constexpr ((VAR & K3V_TWPROD) != 0) r8k::pass1_store_prod(tid, v, tw1, buf);
+        else r8k::pass1_store(tid, v, tw1, buf);
     }
     __syncthreads();
     r8k::pass2(tid, s_tw2, buf);
@@ -1119,6 +1156,15 @@ int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int 
     else if (variant & VARIANT_OLD_EPILOGUE)
         stft8192_kernel<false><<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw1, tw2,
                                                                     tw8192, mags, cand_mag, cand_pitch, cand_count);
+    else if ((variant & VARIANT_TWPROD) && (variant & VARIANT_WINSYN))
+        stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN><<<total_frames, K3_THREADS, 0, st>>>(
+            pcm, songs, frame_prefix, n_songs, hann, tw1, tw2, tw8192, mags, cand_mag, cand_pitch, cand_count);
+    else if (variant & VARIANT_TWPROD)
+        stft8192_kernel<true, K3V_TWPROD><<<total_frames, K3_THREADS, 0, st>>>(
+            pcm, songs, frame_prefix, n_songs, hann, tw1, tw2, tw8192, mags, cand_mag, cand_pitch, cand_count);
+    else if (variant & VARIANT_WINSYN)
+        stft8192_kernel<true, K3V_WINSYN><<<total_frames, K3_THREADS, 0, st>>>(
+            pcm, songs, frame_prefix, n_songs, hann, tw1, tw2, tw8192, mags, cand_mag, cand_pitch, cand_count);
     else
         stft8192_kernel<true><<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw1, tw2,
                                                                    tw8192, mags, cand_mag, cand_pitch, cand_count);

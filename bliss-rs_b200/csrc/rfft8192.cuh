@@ -36,6 +36,52 @@ BLISS_HD void pass1_store(int b, cpx (&v)[16], const cpx *tw1 /*[16][256]*/, cpx
     }
 }
 
+// pass 1 with 4 twiddle loads instead of 15 (VARIANT_TWPROD): W^b, W^2b, W^4b, W^8b come from the table, the
+// other eleven are products of at most three of them (<= 3 extra roundings, ~2e-7 relative).  The kernel is bound
+// by the L1 / shared-memory data pipe (profiles/): 11 fewer 64-bit loads per thread are 176 fewer wavefronts per
+// frame for 22 more packed FP instructions per thread.  Products are formed right before their use so that only
+// the four loaded values stay live.
+BLISS_HD void pass1_store_prod(int b, cpx (&v)[16], const cpx *tw1 /*[16][256]*/, cpx *buf) {
+    fft_dif<16>(v);
+    cpx *o = buf + b + (b >> 4);
+    const cpx *t = tw1 + b;
+    const cpx t1 = t[256 * 1], t2 = t[256 * 2], t4 = t[256 * 4], t8 = t[256 * 8];
+#define BLISS_P1(k1, w) o[273 * (k1)] = cmul(v[bitrev((k1), 4)], (w))
+    o[0] = v[0];
+    BLISS_P1(8, t8);
+    BLISS_P1(4, t4);
+    BLISS_P1(12, cmul(t4, t8));
+    BLISS_P1(2, t2);
+    BLISS_P1(10, cmul(t2, t8));
+    const cpx t6 = cmul(t2, t4);
+    BLISS_P1(6, t6);
+    BLISS_P1(14, cmul(t6, t8));
+    BLISS_P1(1, t1);
+    BLISS_P1(9, cmul(t1, t8));
+    const cpx t5 = cmul(t1, t4);
+    BLISS_P1(5, t5);
+    BLISS_P1(13, cmul(t5, t8));
+    const cpx t3 = cmul(t1, t2);
+    BLISS_P1(3, t3);
+    BLISS_P1(11, cmul(t3, t8));
+    const cpx t7 = cmul(t3, t4);
+    BLISS_P1(7, t7);
+    BLISS_P1(15, cmul(t7, t8));
+#undef BLISS_P1
+}
+
+// Periodic Hann pair (w[n], w[n + 1]) for n = 2 (tid + 256 Q) from the thread's own phase (VARIANT_WINSYN):
+//   w[n] = 0.5 - 0.5 cos(theta + 2 pi Q / 16),  theta = 2 pi (2 tid [+ 1]) / 8192
+//        = 0.5 - 0.5 (cos theta C_Q - sin theta S_Q)
+// cw = (cos theta_even, cos theta_odd), sw = (sin theta_even, sin theta_odd) (f64-generated table, one 16-byte load
+// per frame); C_Q, S_Q are compile-time constants: two packed FMAs per sample pair instead of one 64-bit load.
+// Differs from the f32 `0.5 - 0.5 cosf(...)` table of the reference by ~1e-7 absolute per coefficient.
+template <int Q>
+BLISS_HD cpx hann_pair(cpx cw, cpx sw) {
+    constexpr float a = -0.5f * cos32(2 * Q), b = 0.5f * sin32(2 * Q);
+    return pfma(cw, cpx{a, a}, pfma(sw, cpx{b, b}, cpx{0.5f, 0.5f}));
+}
+
 // pass 2: butterfly b in [0,256): blk = b>>4 (k1), j = b&15; radix 16 at stride 16 inside the
 // 256-block;  pad(256 blk + j + 16 q) = 273 blk + j + 17 q;  twiddle tw2[k2][j] = W256^(j k2)
 // (a 2 KB table the kernel keeps in shared memory)

@@ -259,6 +259,49 @@ int main() {
             printf("rfft8192 as 64 x 64 (two radix-64 passes): max rel err %.3e\n", err3);
             worst = fmax(worst, err3);
         }
+        // ---- VARIANT_TWPROD: pass-1 twiddles from 4 loads + 11 products store (nearly) what 15 loads store ----
+        {
+            std::vector<cpx> bufA(r8k::BUF_CPX), bufB(r8k::BUF_CPX);
+            for (int bb = 0; bb < 256; bb++) {
+                cpx v[16], u[16];
+                for (int q = 0; q < 16; q++) {
+                    const int nn = bb + 256 * q;
+                    v[q] = u[q] = cpx{(float)a[2 * nn], (float)a[2 * nn + 1]};
+                }
+                r8k::pass1_store(bb, v, tw.data(), bufA.data());
+                r8k::pass1_store_prod(bb, u, tw.data(), bufB.data());
+            }
+            double dmax = 0, vmax = 0;
+            for (int i = 0; i < 4096; i++) {
+                const cpx p = bufA[r8k::pad(i)], q = bufB[r8k::pad(i)];
+                dmax = fmax(dmax, fmax(fabs(p.x - q.x), fabs(p.y - q.y)));
+                vmax = fmax(vmax, fmax(fabs(p.x), fabs(p.y)));
+            }
+            printf("pass-1 product twiddles: max diff %.3e of %.3e\n", dmax, vmax);
+            if (!(dmax <= 1e-6 * vmax)) { printf("product twiddles disagree\n"); return 9; }
+        }
+        // ---- VARIANT_WINSYN: Hann pairs from the thread's phase against the reference's f32 window ----
+        {
+            const float PI_F = 3.14159274101257324f;
+            double wmax = 0;
+            cpx w[256][16];
+            for (int t = 0; t < 256; t++) {
+                const double te = 2.0 * M_PI * (double)(2 * t) / 8192.0, to = 2.0 * M_PI * (double)(2 * t + 1) / 8192.0;
+                const cpx cw{(float)cos(te), (float)cos(to)}, sw{(float)sin(te), (float)sin(to)};
+#define BLISS_W(Q) w[t][Q] = r8k::hann_pair<Q>(cw, sw);
+                BLISS_W(0) BLISS_W(1) BLISS_W(2) BLISS_W(3) BLISS_W(4) BLISS_W(5) BLISS_W(6) BLISS_W(7)
+                BLISS_W(8) BLISS_W(9) BLISS_W(10) BLISS_W(11) BLISS_W(12) BLISS_W(13) BLISS_W(14) BLISS_W(15)
+#undef BLISS_W
+                for (int q = 0; q < 16; q++) {
+                    const int n0 = 2 * (t + 256 * q);
+                    const float r0 = 0.5f - 0.5f * cosf(2.f * (float)n0 * PI_F / 8192.f);        // utils.rs:36-38
+                    const float r1 = 0.5f - 0.5f * cosf(2.f * (float)(n0 + 1) * PI_F / 8192.f);
+                    wmax = fmax(wmax, fmax(fabs(w[t][q].x - r0), fabs(w[t][q].y - r1)));
+                }
+            }
+            printf("synthesised Hann window: max abs diff to the f32 table %.3e\n", wmax);
+            if (!(wmax <= 4e-7)) { printf("synthesised window disagrees\n"); return 10; }
+        }
         std::vector<int> seen(r8k::BUF_CPX, 0);
         for (int i = 0; i < 4096; i++) {
             int p = r8k::pad(i);

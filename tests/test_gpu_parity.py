@@ -333,50 +333,6 @@ def test_s16_ingest_is_the_f32_path_on_converted_samples(golden, pcm_song, pcm_p
     assert np.abs(f1[0] - golden["expected_analysis_v1"]).max() < 1e-5
 
 
-def test_pcm_feed_matches_the_decoders_conversion(golden):
-    """bliss_b200_pcm_to_mono / bliss_b200_analyze_batch_pcm: interleaved s16 / s32 / f32 frames at 22 050 Hz,
-    converted and down-mixed on the device like the reference's decoders do (src/song/decoder/ffmpeg.rs:36-109,
-    symphonia.rs:260-300).  Bit-exact against the oracle and against the adler32 values the reference's decoder
-    tests assert for ffmpeg's output (ffmpeg.rs:447-462)."""
-    import zlib
-
-    def adler(x):
-        return zlib.adler32(np.asarray(x, "<f4").tobytes()) & 0xFFFFFFFF
-
-    st = golden["pcm_s16_stereo"]
-    mono = B.native.pcm_to_mono(st)
-    assert adler(mono) == 0x1D7B2D6D                                   # ffmpeg.rs:447-452 test_resample_stereo
-    assert adler(B.native.pcm_to_mono(golden["pcm_s16_mono"])) == 0x5E01930B  # :454-462 test_decode_mono
-    rng = np.random.default_rng(11)
-    cases = [rng.integers(-32768, 32768, (50001, ch), dtype=np.int16) for ch in (1, 2, 3, 6, 8)]
-    cases += [rng.integers(-2 ** 31, 2 ** 31, (40003, ch), dtype=np.int64).astype(np.int32) for ch in (1, 2, 5)]
-    cases += [rng.standard_normal((30002, ch)).astype(np.float32) for ch in (1, 2, 4)]
-    cases += [st[:1], st[:0]]
-    for a in cases:
-        got, want = B.native.pcm_to_mono(a), O.pcm_to_mono(a)
-        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (a.dtype, a.shape)
-    # the analysis of such sources = the f32 path on the converted samples, bit for bit
-    songs = [st, st[:100000], st[:5000], np.repeat(golden["pcm_piano"][:, None], 2, axis=1)]
-    st_p, f_p = B.native.analyze_batch_pcm(songs, 22050, 2)
-    st_f, f_f = B.native.analyze_batch([O.pcm_to_mono(x) for x in songs], 2)
-    assert list(st_p) == [0, 0, 1, 0] and np.array_equal(st_p, st_f)
-    assert np.array_equal(f_p[st_p == 0], f_f[st_f == 0])
-    rc, want = O.analyze(O.pcm_to_mono(st), 2)
-    assert rc == 0 and _close(f_p[0], want).all()
-    s32 = [(x.astype(np.int32) << 16) for x in songs[:2]]          # the same samples as 32-bit material
-    st_q, f_q = B.native.analyze_batch_pcm(s32, 22050, 1)
-    st_g, f_g = B.native.analyze_batch([O.pcm_to_mono(x) for x in songs[:2]], 1)
-    assert np.array_equal(f_q, f_g)
-    six = [np.ascontiguousarray(np.repeat(golden["pcm_s16_mono"][:, None], 6, axis=1))]
-    st_6, f_6 = B.native.analyze_batch_pcm(six, 22050, 2)
-    st_m, f_m = B.native.analyze_batch([O.pcm_to_mono(six[0])], 2)
-    assert np.array_equal(f_6, f_m)
-    with pytest.raises(B.native.NativeError, match="22050"):          # no resampler on this side of the boundary
-        B.native.analyze_batch_pcm(songs[:1], 44100, 2)
-    with pytest.raises(B.native.NativeError):
-        B.native.analyze_batch_pcm([np.zeros((9000, 9), np.int16)], 22050, 2)
-
-
 def test_kernel_implementations_agree(pcm_song, pcm_piano):
     """bliss_b200_set_variant: the previous implementation of every reworked kernel is still in the library.
     Tuning select, chroma contraction, autocorrelation and beat-tracker CTA width must reproduce the current
@@ -505,3 +461,67 @@ def test_dedup_playlist():
     pl = [song(0.0), song(0.001), song(0.5, "t", "a"), song(0.9, "t", "a"), song(0.9), song(0.0)]
     kept = list(B.playlist.dedup_playlist(pl))
     assert [round(float(s.analysis.as_arr1()[0]), 6) for s in kept] == [0.0, 0.5, 0.9, 0.0]
+
+
+def test_pcm_feed_matches_the_decoders_conversion(golden):
+    """bliss_b200_pcm_to_mono / bliss_b200_analyze_batch_pcm: interleaved s16 / s32 / f32 frames at 22 050 Hz,
+    converted and down-mixed on the device like the reference's decoders do (src/song/decoder/ffmpeg.rs:36-109,
+    symphonia.rs:260-300).  Bit-exact against the oracle and against the adler32 values the reference's decoder
+    tests assert for ffmpeg's output (ffmpeg.rs:447-462)."""
+    import zlib
+
+    def adler(x):
+        return zlib.adler32(np.asarray(x, "<f4").tobytes()) & 0xFFFFFFFF
+
+    st = golden["pcm_s16_stereo"]
+    mono = B.native.pcm_to_mono(st)
+    assert adler(mono) == 0x1D7B2D6D                                   # ffmpeg.rs:447-452 test_resample_stereo
+    assert adler(B.native.pcm_to_mono(golden["pcm_s16_mono"])) == 0x5E01930B  # :454-462 test_decode_mono
+    rng = np.random.default_rng(11)
+    cases = [rng.integers(-32768, 32768, (50001, ch), dtype=np.int16) for ch in (1, 2, 3, 6, 8)]
+    cases += [rng.integers(-2 ** 31, 2 ** 31, (40003, ch), dtype=np.int64).astype(np.int32) for ch in (1, 2, 5)]
+    cases += [rng.standard_normal((30002, ch)).astype(np.float32) for ch in (1, 2, 4)]
+    cases += [st[:1], st[:0]]
+    for a in cases:
+        got, want = B.native.pcm_to_mono(a), O.pcm_to_mono(a)
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (a.dtype, a.shape)
+    # the analysis of such sources = the f32 path on the converted samples, bit for bit
+    songs = [st, st[:100000], st[:5000], np.repeat(golden["pcm_piano"][:, None], 2, axis=1)]
+    st_p, f_p = B.native.analyze_batch_pcm(songs, 22050, 2)
+    st_f, f_f = B.native.analyze_batch([O.pcm_to_mono(x) for x in songs], 2)
+    assert list(st_p) == [0, 0, 1, 0] and np.array_equal(st_p, st_f)
+    assert np.array_equal(f_p[st_p == 0], f_f[st_f == 0])
+    rc, want = O.analyze(O.pcm_to_mono(st), 2)
+    assert rc == 0 and _close(f_p[0], want).all()
+    s32 = [(x.astype(np.int32) << 16) for x in songs[:2]]          # the same samples as 32-bit material
+    st_q, f_q = B.native.analyze_batch_pcm(s32, 22050, 1)
+    st_g, f_g = B.native.analyze_batch([O.pcm_to_mono(x) for x in songs[:2]], 1)
+    assert np.array_equal(f_q, f_g)
+    six = [np.ascontiguousarray(np.repeat(golden["pcm_s16_mono"][:, None], 6, axis=1))]
+    st_6, f_6 = B.native.analyze_batch_pcm(six, 22050, 2)
+    st_m, f_m = B.native.analyze_batch([O.pcm_to_mono(six[0])], 2)
+    assert np.array_equal(f_6, f_m)
+    with pytest.raises(B.native.NativeError, match="22050"):          # no resampler on this side of the boundary
+        B.native.analyze_batch_pcm(songs[:1], 44100, 2)
+    with pytest.raises(B.native.NativeError):
+        B.native.analyze_batch_pcm([np.zeros((9000, 9), np.int16)], 22050, 2)
+
+
+def test_experimental_pass1_variants_agree(pcm_song, pcm_piano):
+    """BLISS_B200_VARIANT bits 64 / 128: pass 1 of stft8192_kernel with product twiddles (4 table loads instead
+    of 15) and with the Hann window synthesised from the thread's phase (no window loads).  Candidates for the
+    data-pipe-bound kernel, not the default: they round differently in the last place (window coefficients differ
+    from the reference's f32 table by <= 2.4e-7) and must agree with the measured kernel to 1e-5."""
+    songs = [pcm_song, pcm_piano] + [synth.gen_track(78, i, 22050 * 35 + 211 * i, device="cuda").cpu().numpy() for i in range(6)]
+    try:
+        B.native.set_variant(0)
+        st0, f0 = B.native.analyze_batch(songs, 2)
+        assert (st0 == 0).all()
+        for mask in (64, 128, 64 | 128):
+            B.native.set_variant(mask)
+            st, f = B.native.analyze_batch(songs, 2)
+            assert (st == 0).all()
+            assert np.abs(f - f0).max() < 1e-5, (mask, np.abs(f - f0).max(0))
+            assert np.array_equal(f[:, :10], f0[:, :10])  # only the chroma features depend on the chroma STFT
+    finally:
+        B.native.set_variant(0)
