@@ -23,7 +23,7 @@ namespace bliss {
 int launch_pvoc512(const float *, const SongDesc *, const unsigned int *, int, unsigned int, int, PvocTables,
                    float *, float *, float *, float *, cudaStream_t);
 int launch_stft512_mags(const float *, const SongDesc *, const unsigned int *, int, unsigned int, int,
-                        PvocTables, float *, cudaStream_t);
+                        PvocTables, float *, int, cudaStream_t);
 int launch_timedomain(const float *, const SongDesc *, const unsigned int *, int, unsigned int, float *,
                       float *, unsigned int *, cudaStream_t);
 int launch_peakpick(const float *, const SongDesc *, const unsigned int *, int, unsigned int, float *,
@@ -1214,7 +1214,7 @@ int bliss_b200_stft512_mag_device(const float *d_pcm, const uint64_t *offsets, c
     {
         ProfScope p(K_STFT512, st);
         p.done(launch_stft512_mags(d_pcm, dv.sd, dv.k1_prefix, (int)n_songs, w.k1_prefix[n_songs],
-                                   (int)w.pairs_per_item, pvoc_tables(), d_mags, st));
+                                   (int)w.pairs_per_item, pvoc_tables(), d_mags, g.variant, st));
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(S.ev_done, st));

@@ -266,6 +266,139 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
 }
 
 // ---------------------------------------------------------------------------
+// STFT micro-benchmark kernel for the hop-256 framing (BASELINE.json config 3 = PVocTempo::do_,
+// src/aubio.rs:338-425), experimental (VARIANT_STFT_PAIRS): tempo frames j and j+1 ride ONE complex
+// 512-point FFT and BOTH are wanted, whereas pvoc512_kernel<false, true> transforms the hop-128 pair
+// (timbral frames 2j, 2j+1) and throws the even one away -- half the transforms per track.  Each lane
+// untangles bins lane + 32 i (the natural-order tile in shared memory allows any assignment), so a frame's
+// 257 magnitudes leave as eight 128-byte warp stores instead of eight stores at a 32-byte lane stride.
+//   frame j  = x[256 j - 256 .. 256 j + 256),  frame j+1 = x[256 j .. 256 j + 512)   (zeros before the song)
+//   window rows s[r] = x[256 j - 256 + lane + 32 r], r = 0..23: A row n1 = s[n1], B row n1 = s[n1 + 8];
+//   the next pair starts 16 rows further on.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+stft512_pairs_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
+                     const unsigned int *__restrict__ item_prefix, int n_songs, unsigned int total_items,
+                     int frames_per_item, PvocTables tab, float *__restrict__ mags_out) {
+    __shared__ float s_win[512];
+    __shared__ cpx s_twA[16 * 32];
+    __shared__ cpx s_ex[8][pv::EXCH_CPX];
+
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        s_win[i] = tab.win[i];
+        s_twA[i] = tab.twA[i];
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int item = blockIdx.x * 8u + (unsigned)warp;
+    if (item >= total_items) return;
+    const int si = find_song(item_prefix, n_songs, item);
+    const SongDesc sd = songs[si];
+    const int j0 = (int)(item - item_prefix[si]) * frames_per_item;
+    const int j1 = min(j0 + frames_per_item, (int)sd.n_t);
+    const float *x = pcm + sd.pcm_off;
+    const int n = (int)sd.n;
+    cpx *S = s_ex[warp];
+
+    float win_a[16];  // w[lane + 32*n1]
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) win_a[n1] = s_win[lane + 32 * n1];
+
+    float s[24];
+    {
+        const int base = 256 * j0 - 256 + lane;
+#pragma unroll
+        for (int m = 0; m < 24; m++) {
+            const int idx = base + 32 * m;
+            s[m] = (idx >= 0 && idx < n) ? __ldg(x + idx) : 0.f;
+        }
+    }
+    for (int j = j0; j < j1; j += 2) {
+        // same frame packing as pvoc512_kernel: B pre-scaled by an exact power of two to A's level, an
+        // all-zero windowed frame forced to exact zeros (see there)
+        float pka = 0.f, pkb = 0.f;
+        cpx r[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            r[n1] = pmul(cpx{s[n1], s[n1 + 8]}, cpx{win_a[n1], win_a[n1]});
+            pka = fmaxf(pka, fabsf(r[n1].x));
+            pkb = fmaxf(pkb, fabsf(r[n1].y));
+        }
+        // slide by 512 samples; the 16 new rows of the next pair are requested before this pair's FFT
+#pragma unroll
+        for (int m = 0; m < 8; m++) s[m] = s[m + 16];
+        if (j + 2 < j1) {
+            const int base = 256 * (j + 2) - 256 + lane + 32 * 8;  // >= 0; frame j+2 is valid: rows 8..15 are inside the song
+            const float *px = x + base;
+#pragma unroll
+            for (int m = 0; m < 8; m++) s[8 + m] = __ldg(px + 32 * m);
+            if (j + 3 < (int)sd.n_t) {  // frame j+3 exists: its last 8 rows are inside the song too
+#pragma unroll
+                for (int m = 8; m < 16; m++) s[8 + m] = __ldg(px + 32 * m);
+            } else {
+#pragma unroll
+                for (int m = 8; m < 16; m++) {
+                    const int idx = base + 32 * m;
+                    s[8 + m] = (idx < n) ? __ldg(x + idx) : 0.f;
+                }
+            }
+        }
+        const unsigned int ua = __reduce_max_sync(0xffffffffu, __float_as_uint(pka));
+        const unsigned int ub = __reduce_max_sync(0xffffffffu, __float_as_uint(pkb));
+        int sh = (int)(ua >> 23) - (int)(ub >> 23);
+        sh = (ua == 0u || ub == 0u) ? 0 : max(-60, min(60, sh));
+        const float gscale = __uint_as_float((unsigned)(127 + sh) << 23);
+        const float ginv = __uint_as_float((unsigned)(127 - sh) << 23);
+        if (sh != 0) {
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) r[n1].y *= gscale;
+        }
+        pv::phase_a(lane, r, s_twA, S);
+        __syncwarp();
+        pv::phase_b_load(lane, r, S);
+        __syncwarp();
+        pv::phase_b_fft(lane, r);
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const cpx o = shfl_xor_cpx(r[q], 16);
+            const cpx z = pv::phase_b_combine(lane, r[q], o);
+            S[pv::zpos(pv::bin_of(lane, q))] = z;
+        }
+        __syncwarp();
+        // lane owns bins lane + 32 i of both frames
+        float ma[8], mb[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int k = lane + 32 * i;
+            const cpx zk = S[pv::zpos(k)];
+            const cpx zm = S[pv::zpos((512 - k) & 511)];
+            pv::untangle_mag<true>(zk, zm, ma[i], mb[i]);  // 2|A|, 2|B|
+        }
+        const cpx zn = S[pv::zpos(256)];  // Nyquist: A = |Re|, B = |Im| (aubio.rs:403-405)
+        float nyq_a = 2.f * fabsf(zn.x), nyq_b = 2.f * fabsf(zn.y);
+        if (lane == 0) {  // DC: abs(re), aubio.rs:403
+            const cpx z0 = S[0];
+            ma[0] = 2.f * fabsf(z0.x);
+            mb[0] = 2.f * fabsf(z0.y);
+        }
+        __syncwarp();  // S is rewritten by the next pair's phase A
+        const float ka = (ua == 0u) ? 0.f : 0.5f;
+        const float kb = (ub == 0u) ? 0.f : 0.5f * ginv;
+        float *oa = mags_out + ((size_t)sd.t_off + (size_t)j) * 257u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) oa[lane + 32 * i] = ma[i] * ka;
+        if (lane == 0) oa[256] = nyq_a * ka;
+        if (j + 1 < j1) {
+            float *ob = oa + 257;
+#pragma unroll
+            for (int i = 0; i < 8; i++) ob[lane + 32 * i] = mb[i] * kb;
+            if (lane == 0) ob[256] = nyq_b * kb;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K2: one warp per 1024-sample loudness chunk.
 //   number_crossings        src/utils.rs:81-95      (one call over the whole song, song/mod.rs:470-474)
 //   level_lin per chunk     src/misc.rs:12-18       (chunks(1024) incl. short tail, song/mod.rs:478)
@@ -363,9 +496,13 @@ int launch_pvoc512(const float *pcm, const SongDesc *songs, const unsigned int *
 
 int launch_stft512_mags(const float *pcm, const SongDesc *songs, const unsigned int *item_prefix,
                         int n_songs, unsigned int total_items, int pairs_per_item, PvocTables tab,
-                        float *mags, cudaStream_t st) {
+                        float *mags, int variant, cudaStream_t st) {
     if (total_items == 0) return 0;
     const unsigned int grid = (total_items + 7u) / 8u;
+    if (variant & VARIANT_STFT_PAIRS) {  // an item's `pairs_per_item` hop-128 pairs are as many hop-256 frames
+        stft512_pairs_kernel<<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items, pairs_per_item, tab, mags);
+        return 1;
+    }
     pvoc512_kernel<false, true><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
                                                       pairs_per_item, tab, nullptr, nullptr, nullptr,
                                                       nullptr, mags);

@@ -525,3 +525,35 @@ def test_experimental_pass1_variants_agree(pcm_song, pcm_piano):
             assert np.array_equal(f[:, :10], f0[:, :10])  # only the chroma features depend on the chroma STFT
     finally:
         B.native.set_variant(0)
+
+
+
+def test_experimental_stft_pair_kernel(pcm_song, pcm_piano):
+    """BLISS_B200_VARIANT bit 256: the STFT micro-benchmark with hop-256 frames j, j+1 sharing one FFT
+    (stft512_pairs_kernel) against the oracle's PVocTempo norms and against the default kernel, on several
+    songs of ragged lengths in one call (odd frame counts, item boundaries)."""
+    songs = [pcm_song[:60000], pcm_piano[:8192 + 256 * 7 + 13], pcm_song[1000:1000 + 256 * 300 + 511], pcm_piano]
+    flat = np.concatenate([np.pad(x, (0, (-len(x)) % 4)) for x in songs]).astype(np.float32)
+    offs = np.cumsum([0] + [len(x) + (-len(x)) % 4 for x in songs[:-1]]).tolist()
+    lens = [len(x) for x in songs]
+    n_t = [(n - 512) // 256 + 1 for n in lens]
+    d = torch.from_numpy(flat).cuda()
+    try:
+        outs = {}
+        for mask in (0, 256):
+            B.native.set_variant(mask)
+            mags = torch.full((sum(n_t), 257), -1.0, dtype=torch.float32, device="cuda")
+            fo = B.native.stft512_mag_device(d.data_ptr(), offs, lens, mags.data_ptr(), None)
+            torch.cuda.synchronize()
+            assert list(fo) == np.cumsum([0] + n_t).tolist()
+            outs[mask] = mags.cpu().numpy()
+        for i, x in enumerate(songs):
+            want = O.tempo_norms(x)
+            lo = int(np.sum(n_t[:i]))
+            for mask in (0, 256):
+                got = outs[mask][lo:lo + n_t[i]]
+                assert (got >= 0).all(), "variant %d left magnitudes of song %d unwritten" % (mask, i)
+                err = np.abs(got - want).max() / want.max()
+                assert err < 1e-6, (mask, i, err)
+    finally:
+        B.native.set_variant(0)

@@ -109,11 +109,22 @@ def test_fft_index_logic_on_host(tmp_path):
     assert "OK" in out.stdout
 
 
+def test_stft_pair_kernel_design_on_host(tmp_path):
+    """tests/cpu_emul/emul_stft_pairs.cu: the hop-256 pairing of stft512_pairs_kernel (window rows, slide,
+    load bounds, silence, magnitudes against an f64 DFT) transcribed onto the host."""
+    exe = str(tmp_path / "emul_stft_pairs")
+    src = os.path.join(ROOT, "tests", "cpu_emul", "emul_stft_pairs.cu")
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-w", "-o", exe, src])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "OK" in out.stdout
+
+
 def test_variant_mask_names_match_header():
     """BLISS_B200_VARIANT bits (A/B switch back to a kernel's previous implementation) stay documented."""
     txt = open(os.path.join(ROOT, "bliss-rs_b200", "csrc", "common.cuh")).read()
     for name in ("VARIANT_OLD_EPILOGUE = 1", "VARIANT_OLD_TUNING = 2", "VARIANT_OLD_CHROMA = 4", "VARIANT_OLD_ACF = 8",
-                 "VARIANT_BT512 = 16", "VARIANT_R64 = 32", "VARIANT_TWPROD = 64", "VARIANT_WINSYN = 128"):
+                 "VARIANT_BT512 = 16", "VARIANT_R64 = 32", "VARIANT_TWPROD = 64", "VARIANT_WINSYN = 128", "VARIANT_STFT_PAIRS = 256"):
         assert name in txt
 
 
