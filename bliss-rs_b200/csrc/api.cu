@@ -21,7 +21,7 @@
 namespace bliss {
 // launchers implemented in the other translation units
 int launch_pvoc512(const float *, const SongDesc *, const unsigned int *, int, unsigned int, int, PvocTables,
-                   float *, float *, float *, float *, cudaStream_t);
+                   float *, float *, float *, float *, int, cudaStream_t);
 int launch_stft512_mags(const float *, const SongDesc *, const unsigned int *, int, unsigned int, int,
                         PvocTables, float *, int, cudaStream_t);
 int launch_timedomain(const float *, const SongDesc *, const unsigned int *, int, unsigned int, float *,
@@ -374,7 +374,7 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
                                S.eb.as<float>(), S.zcr.as<unsigned int>(), st)); }
     { ProfScope p(K_PVOC, st);
       p.done(launch_pvoc512(d_pcm, dv.sd, dv.k1_prefix, n, w.k1_prefix[n], (int)w.pairs_per_item, pvoc_tables(),
-                            S.cent.as<float>(), S.roll.as<float>(), S.flat.as<float>(), S.flux.as<float>(), st)); }
+                            S.cent.as<float>(), S.roll.as<float>(), S.flat.as<float>(), S.flux.as<float>(), g.variant, st)); }
     { ProfScope p(K_TUNING, sb);
       p.done(launch_tuning(S.cand_mag.as<double>(), S.cand_pitch.as<double>(),
                            S.cand_count.as<unsigned int>(), dv.sd, n, S.tuning.as<int>(), g.variant, sb)); }

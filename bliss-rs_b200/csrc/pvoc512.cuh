@@ -36,6 +36,36 @@ BLISS_HD void phase_a(int lane, cpx (&r)[16], const cpx *twA, cpx *S) {
     }
 }
 
+// Phase A with the lane's twiddles W512^(lane k1) formed from four of them (k1 = 1, 2, 4, 8: loop-invariant
+// per lane, kept in registers for the whole run) instead of 15 shared-memory loads per frame pair
+// (experimental, VARIANT_PV_TWPROD): <= 3 extra roundings per twiddle (~2e-7 relative).
+BLISS_HD void phase_a_prod(int lane, cpx (&r)[16], cpx t1, cpx t2, cpx t4, cpx t8, cpx *S) {
+    fft_dif<16>(r);
+    cpx *o = S + lane;
+#define BLISS_PA(k1, w) o[(k1) * ROW] = cmul(r[bitrev((k1), 4)], (w))
+    o[0] = r[0];
+    BLISS_PA(8, t8);
+    BLISS_PA(4, t4);
+    BLISS_PA(12, cmul(t4, t8));
+    BLISS_PA(2, t2);
+    BLISS_PA(10, cmul(t2, t8));
+    const cpx t6 = cmul(t2, t4);
+    BLISS_PA(6, t6);
+    BLISS_PA(14, cmul(t6, t8));
+    BLISS_PA(1, t1);
+    BLISS_PA(9, cmul(t1, t8));
+    const cpx t5 = cmul(t1, t4);
+    BLISS_PA(5, t5);
+    BLISS_PA(13, cmul(t5, t8));
+    const cpx t3 = cmul(t1, t2);
+    BLISS_PA(3, t3);
+    BLISS_PA(11, cmul(t3, t8));
+    const cpx t7 = cmul(t3, t4);
+    BLISS_PA(7, t7);
+    BLISS_PA(15, cmul(t7, t8));
+#undef BLISS_PA
+}
+
 // Phase B, lane = p*16 + k1: gather the parity-p half of row k1.
 BLISS_HD void phase_b_load(int lane, cpx (&u)[16], const cpx *S) {
     const int k1 = lane & 15, p = lane >> 4;

@@ -93,7 +93,7 @@ __device__ __forceinline__ void frame_descriptors(const float (&v)[8], int lane,
 #ifndef K1_MINBLOCKS
 #define K1_MINBLOCKS 2
 #endif
-template <bool WITH_DESC, bool WITH_MAGS>
+template <bool WITH_DESC, bool WITH_MAGS, bool TWPROD = false>
 __global__ void __launch_bounds__(256, K1_MINBLOCKS)
 pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
                const unsigned int *__restrict__ item_prefix, int n_songs, unsigned int total_items,
@@ -124,6 +124,13 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
     float win_a[16];  // w[lane + 32*n1]
 #pragma unroll
     for (int n1 = 0; n1 < 16; n1++) win_a[n1] = s_win[lane + 32 * n1];
+    cpx tw1 = cpx{1.f, 0.f}, tw2 = tw1, tw4 = tw1, tw8 = tw1;  // W512^(lane k1), k1 = 1, 2, 4, 8 (TWPROD)
+    if constexpr (TWPROD) {
+        tw1 = s_twA[1 * 32 + lane];
+        tw2 = s_twA[2 * 32 + lane];
+        tw4 = s_twA[4 * 32 + lane];
+        tw8 = s_twA[8 * 32 + lane];
+    }
 
     float old[8];  // previous tempo frame's magnitudes of this lane's bins
 #pragma unroll
@@ -174,7 +181,8 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
 #pragma unroll
             for (int n1 = 0; n1 < 16; n1++) r[n1].y *= gscale;
         }
-        pv::phase_a(lane, r, s_twA, S);
+        if constexpr (TWPROD) pv::phase_a_prod(lane, r, tw1, tw2, tw4, tw8, S);
+        else pv::phase_a(lane, r, s_twA, S);
         __syncwarp();
         pv::phase_b_load(lane, r, S);
         __syncwarp();
@@ -485,12 +493,17 @@ timedomain_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
 // ---- launchers ---------------------------------------------------------------
 int launch_pvoc512(const float *pcm, const SongDesc *songs, const unsigned int *item_prefix, int n_songs,
                    unsigned int total_items, int pairs_per_item, PvocTables tab, float *centroid,
-                   float *rolloff, float *flatness, float *flux, cudaStream_t st) {
+                   float *rolloff, float *flatness, float *flux, int variant, cudaStream_t st) {
     if (total_items == 0) return 0;
     const unsigned int grid = (total_items + 7u) / 8u;
-    pvoc512_kernel<true, false><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
-                                                      pairs_per_item, tab, centroid, rolloff, flatness,
-                                                      flux, nullptr);
+    if (variant & VARIANT_PV_TWPROD)
+        pvoc512_kernel<true, false, true><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
+                                                                pairs_per_item, tab, centroid, rolloff, flatness,
+                                                                flux, nullptr);
+    else
+        pvoc512_kernel<true, false><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
+                                                          pairs_per_item, tab, centroid, rolloff, flatness,
+                                                          flux, nullptr);
     return 1;
 }
 

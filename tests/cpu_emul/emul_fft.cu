@@ -72,6 +72,25 @@ int main() {
         }
         printf("fft512 pair: max rel err %.3e\n", err);
         worst = fmax(worst, err);
+        // VARIANT_PV_TWPROD: phase A with product twiddles stores (nearly) what the table form stores
+        {
+            std::vector<cpx> S2(pv::EXCH_CPX);
+            for (int lane = 0; lane < 32; lane++) {
+                cpx r[16], u[16];
+                for (int n1 = 0; n1 < 16; n1++) r[n1] = u[n1] = cpx{(float)a[lane + 32 * n1], (float)b[lane + 32 * n1]};
+                pv::phase_a(lane, r, twA.data(), S.data());
+                pv::phase_a_prod(lane, u, twA[1 * 32 + lane], twA[2 * 32 + lane], twA[4 * 32 + lane], twA[8 * 32 + lane], S2.data());
+            }
+            double dmax = 0, vmax = 0;
+            for (int k1 = 0; k1 < 16; k1++)
+                for (int lane = 0; lane < 32; lane++) {
+                    const cpx p = S[k1 * pv::ROW + lane], q = S2[k1 * pv::ROW + lane];
+                    dmax = fmax(dmax, fmax(fabs(p.x - q.x), fabs(p.y - q.y)));
+                    vmax = fmax(vmax, fmax(fabs(p.x), fabs(p.y)));
+                }
+            printf("fft512 phase-A product twiddles: max diff %.3e of %.3e\n", dmax, vmax);
+            if (!(dmax <= 1e-6 * vmax)) { printf("phase-A product twiddles disagree\n"); return 11; }
+        }
     }
     // ---------------- 8192-point real FFT as 4096 complex, one frame per CTA ----------------
     {

@@ -557,3 +557,25 @@ def test_experimental_stft_pair_kernel(pcm_song, pcm_piano):
                 assert err < 1e-6, (mask, i, err)
     finally:
         B.native.set_variant(0)
+
+
+def test_experimental_pvoc_twiddle_variant(pcm_song, pcm_piano):
+    """BLISS_B200_VARIANT bit 512: pvoc512_kernel with the phase-A twiddles formed from four per-lane registers
+    (no twiddle loads in the frame loop).  Rounds differently in the last place: timbral descriptors within 1e-5
+    of the measured kernel, parity with the oracle within the usual bar, everything behind the chroma STFT
+    untouched."""
+    songs = [pcm_song, pcm_piano] + [synth.gen_track(79, i, 22050 * 30 + 173 * i, device="cuda").cpu().numpy() for i in range(6)]
+    try:
+        B.native.set_variant(0)
+        st0, f0 = B.native.analyze_batch(songs, 2)
+        B.native.set_variant(512)
+        st, f = B.native.analyze_batch(songs, 2)
+        assert (st0 == 0).all() and (st == 0).all()
+        assert np.abs(f[:, 1:10] - f0[:, 1:10]).max() < 1e-5, np.abs(f - f0).max(0)
+        assert np.array_equal(f[:, 10:], f0[:, 10:])
+        assert (np.abs(f[:, 0] - f0[:, 0]) < 1e-5).sum() >= len(songs) - 1  # a tempo decision may sit on an edge
+        for i in (0, 1):
+            rc, want = O.analyze(songs[i], 2)
+            assert rc == 0 and _close(f[i], want).all(), (i, np.abs(f[i] - want).max())
+    finally:
+        B.native.set_variant(0)

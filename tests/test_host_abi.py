@@ -124,7 +124,7 @@ def test_variant_mask_names_match_header():
     """BLISS_B200_VARIANT bits (A/B switch back to a kernel's previous implementation) stay documented."""
     txt = open(os.path.join(ROOT, "bliss-rs_b200", "csrc", "common.cuh")).read()
     for name in ("VARIANT_OLD_EPILOGUE = 1", "VARIANT_OLD_TUNING = 2", "VARIANT_OLD_CHROMA = 4", "VARIANT_OLD_ACF = 8",
-                 "VARIANT_BT512 = 16", "VARIANT_R64 = 32", "VARIANT_TWPROD = 64", "VARIANT_WINSYN = 128", "VARIANT_STFT_PAIRS = 256"):
+                 "VARIANT_BT512 = 16", "VARIANT_R64 = 32", "VARIANT_TWPROD = 64", "VARIANT_WINSYN = 128", "VARIANT_STFT_PAIRS = 256", "VARIANT_PV_TWPROD = 512"):
         assert name in txt
 
 
