@@ -104,7 +104,7 @@ BLISS_HD int bin_of(int lane, int q) {
 //   A[k] = (Z[k] + conj Z[N-k]) / 2,   B[k] = (Z[k] - conj Z[N-k]) / (2i)
 // and return their magnitudes as `(re*re + im*im).sqrt()` (aubio.rs:248-252).
 // SCALE2 = true returns 2|A|, 2|B| (the exact factor 1/2 is folded into a later power-of-two scale).
-template <bool SCALE2 = false>
+template <bool SCALE2 = false, bool FTZ = false>
 BLISS_HD void untangle_mag(cpx zk, cpx zm, float &magA, float &magB) {
     const float h = SCALE2 ? 1.0f : 0.5f;
     // 2A = (zk.x + zm.x, zk.y - zm.y),  2B = (zk.y + zm.y, zm.x - zk.x)
@@ -116,8 +116,13 @@ BLISS_HD void untangle_mag(cpx zk, cpx zm, float &magA, float &magB) {
     }
     const cpx qa = pmul(a, a), qb = pmul(b, b);
 #ifdef __CUDA_ARCH__
-    magA = approx_sqrtf(__fadd_rn(qa.x, qa.y));
-    magB = approx_sqrtf(__fadd_rn(qb.x, qb.y));
+    if (FTZ) {
+        magA = approx_sqrtf_ftz(__fadd_rn(qa.x, qa.y));
+        magB = approx_sqrtf_ftz(__fadd_rn(qb.x, qb.y));
+    } else {
+        magA = approx_sqrtf(__fadd_rn(qa.x, qa.y));
+        magB = approx_sqrtf(__fadd_rn(qb.x, qb.y));
+    }
 #else
     magA = sqrtf(qa.x + qa.y);
     magB = sqrtf(qb.x + qb.y);

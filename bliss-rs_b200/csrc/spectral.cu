@@ -87,13 +87,115 @@ __device__ __forceinline__ void frame_descriptors(const float (&v)[8], int lane,
     }
 }
 
+// ---- both frames of a pair at once (experimental, VARIANT_PV_PAIRDESC) --------------------------------------
+// Transposed reductions: the first butterfly step sends each half-warp the OTHER frame's partial, so lanes 0..15
+// finish frame A's total and lanes 16..31 frame B's with one shuffle per step instead of two.  The tree is the
+// one warp_sum / warp_prod walk (a_l + a_(l^16) first, then offsets 8, 4, 2, 1 inside the half), so the totals
+// are bit-identical to theirs.
+__device__ __forceinline__ float pair_sum(float a, float b, int lane) {
+    const bool hi = (lane & 16) != 0;
+    float mine = hi ? b : a;
+    mine += __shfl_xor_sync(0xffffffffu, hi ? a : b, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    return mine;
+}
+__device__ __forceinline__ double pair_prod(double a, double b, int lane) {
+    const bool hi = (lane & 16) != 0;
+    double mine = hi ? b : a;
+    mine *= __shfl_xor_sync(0xffffffffu, hi ? a : b, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) mine *= __shfl_xor_sync(0xffffffffu, mine, o);
+    return mine;
+}
+
+// per-lane part of frame_descriptors for one frame
+struct LanePart {
+    float s1, sw, run, c[8];
+    double mant;
+    int ex;
+    bool is_zero;
+};
+__device__ __forceinline__ LanePart lane_part(const float (&v)[8], int lane) {
+    LanePart p;
+    p.s1 = 0.f;
+    p.sw = 0.f;
+    p.run = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        p.s1 += v[i];
+        p.sw += (float)(8 * lane + i) * v[i];
+        p.run += v[i] * v[i];
+        p.c[i] = p.run;
+    }
+    double m = ((double)v[0] * (double)v[1]) * ((double)v[2] * (double)v[3]);
+    m *= 3.273390607896142e150;
+    m *= ((double)v[4] * (double)v[5]) * ((double)v[6] * (double)v[7]);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+    p.is_zero = (m == 0.0);
+    p.ex = (int)(bits >> 52);
+    p.mant = __longlong_as_double((long long)((bits & 0xFFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
+    return p;
+}
+// roll-off count of one frame (aubio.rs:36-58): warp scan of the per-lane energy, as frame_descriptors
+__device__ __forceinline__ void rolloff_count(const LanePart &p, int lane, float &total, int &cnt) {
+    float incl = p.run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    const float excl = incl - p.run;
+    const float thr = total * 0.95f;
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) c += ((excl + p.c[i]) < thr) ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, c);
+}
+// Descriptors of frames A (returned in lanes 0..15) and B (lanes 16..31): same arithmetic as two calls of
+// frame_descriptors, with the reductions transposed and the scalar finish (two IEEE divisions, log2f, exp2f:
+// 78 instructions per frame) executed once per pair.
+__device__ __forceinline__ void pair_descriptors(const float (&va)[8], const float (&vb)[8], int lane,
+                                                 float &centroid, float &rolloff, float &flatness) {
+    const LanePart a = lane_part(va, lane), b = lane_part(vb, lane);
+    const bool hi = (lane & 16) != 0;
+    const int zero_a = __any_sync(0xffffffffu, a.is_zero), zero_b = __any_sync(0xffffffffu, b.is_zero);
+    const int ex_a = __reduce_add_sync(0xffffffffu, a.ex), ex_b = __reduce_add_sync(0xffffffffu, b.ex);
+    const double mant = pair_prod(a.mant, b.mant, lane);
+    const float s1 = pair_sum(a.s1, b.s1, lane);
+    const float sw = pair_sum(a.sw, b.sw, lane);
+    float total_a, total_b;
+    int cnt_a, cnt_b;
+    rolloff_count(a, lane, total_a, cnt_a);
+    rolloff_count(b, lane, total_b, cnt_b);
+    const float total = hi ? total_b : total_a;
+    const int cnt = hi ? cnt_b : cnt_a;
+    const int zero = hi ? zero_b : zero_a;
+    const int ex = hi ? ex_b : ex_a;
+    const float freq = (float)SAMPLE_RATE / 512.f;
+    float bin = (total == 0.f) ? 0.f : (float)min(cnt + 1, 256);
+    rolloff = freq * bin;
+    centroid = (s1 == 0.f) ? 0.f : freq * fmaxf(sw / s1, 0.f);
+    if (zero) {
+        flatness = 0.f;
+    } else {
+        const float gm = exp2f((log2f((float)mant) + (float)ex) / 256.f - (1023.f + 500.f) / 8.f);
+        flatness = gm / (s1 / 256.f);
+    }
+}
+
 // WITH_DESC: timbral descriptors + flux (the analysis path).
 // WITH_MAGS: materialise the 257 tempo-frame magnitudes (STFT micro-benchmark,
 //            BASELINE.json config 3 = PVocTempo framing: 512 / hop 256).
 #ifndef K1_MINBLOCKS
 #define K1_MINBLOCKS 2
 #endif
-template <bool WITH_DESC, bool WITH_MAGS, bool TWPROD = false>
+// TWPROD (VARIANT_PV_TWPROD) and PAIRDESC (VARIANT_PV_PAIRDESC) are experimental cuts, off by default.
+// PAIRDESC: pair_descriptors + the data kept 2^30 above its level so that the magnitudes need MUFU.SQRT only
+// (approx_sqrtf_ftz): every result is bit-identical to the default kernel's unless an intermediate of the
+// default kernel is denormal.
+template <bool WITH_DESC, bool WITH_MAGS, bool TWPROD = false, bool PAIRDESC = false>
 __global__ void __launch_bounds__(256, K1_MINBLOCKS)
 pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
                const unsigned int *__restrict__ item_prefix, int n_songs, unsigned int total_items,
@@ -123,7 +225,7 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
 
     float win_a[16];  // w[lane + 32*n1]
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) win_a[n1] = s_win[lane + 32 * n1];
+    for (int n1 = 0; n1 < 16; n1++) win_a[n1] = s_win[lane + 32 * n1] * (PAIRDESC ? 1073741824.f : 1.f);  // 2^30: exact
     cpx tw1 = cpx{1.f, 0.f}, tw2 = tw1, tw4 = tw1, tw8 = tw1;  // W512^(lane k1), k1 = 1, 2, 4, 8 (TWPROD)
     if constexpr (TWPROD) {
         tw1 = s_twA[1 * 32 + lane];
@@ -201,7 +303,7 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
             const int k = 8 * lane + i;
             const cpx zk = S[pv::zpos(k)];
             const cpx zm = S[pv::zpos((512 - k) & 511)];
-            pv::untangle_mag<true>(zk, zm, ma[i], mb[i]);  // 2|A|, 2|B|: halved by ka / kb below
+            pv::untangle_mag<true, PAIRDESC>(zk, zm, ma[i], mb[i]);  // 2|A|, 2|B|: halved by ka / kb below
         }
         const cpx zn = S[pv::zpos(256)];  // Nyquist: A = |Re|, B = |Im|
         float nyq_a = 2.f * fabsf(zn.x), nyq_b = 2.f * fabsf(zn.y);
@@ -211,8 +313,9 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
             mb[0] = 2.f * fabsf(z0.y);
         }
         __syncwarp();  // S is rewritten by the next pair's phase A
-        const float ka = (ua == 0u) ? 0.f : 0.5f;  // powers of two: exact
-        const float kb = (ub == 0u) ? 0.f : 0.5f * ginv;
+        constexpr float kHalf = PAIRDESC ? 0.5f / 1073741824.f : 0.5f;  // takes the window's 2^30 out again
+        const float ka = (ua == 0u) ? 0.f : kHalf;  // powers of two: exact
+        const float kb = (ub == 0u) ? 0.f : kHalf * ginv;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             ma[i] *= ka;
@@ -250,6 +353,15 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
                 }
                 float c, ro, fa;
                 const int fa_idx = 2 * j, fb_idx = 2 * j + 1;
+                if constexpr (PAIRDESC) {
+                    pair_descriptors(ma, mb, lane, c, ro, fa);
+                    const int fidx = 2 * j + (lane >> 4);  // lanes 0..15 hold frame 2j's values, 16..31 frame 2j+1's
+                    if ((lane & 15) == 0 && fidx < (int)sd.n_s) {
+                        centroid[sd.s_off + fidx] = c;
+                        rolloff[sd.s_off + fidx] = ro;
+                        flatness[sd.s_off + fidx] = fa;
+                    }
+                } else {
                 if (fa_idx < (int)sd.n_s) {
                     frame_descriptors(ma, lane, c, ro, fa);
                     if (lane == 0) {
@@ -265,6 +377,7 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
                         rolloff[sd.s_off + fb_idx] = ro;
                         flatness[sd.s_off + fb_idx] = fa;
                     }
+                }
                 }
             }
         } else if (WITH_MAGS) {
@@ -496,7 +609,15 @@ int launch_pvoc512(const float *pcm, const SongDesc *songs, const unsigned int *
                    float *rolloff, float *flatness, float *flux, int variant, cudaStream_t st) {
     if (total_items == 0) return 0;
     const unsigned int grid = (total_items + 7u) / 8u;
-    if (variant & VARIANT_PV_TWPROD)
+    if ((variant & VARIANT_PV_TWPROD) && (variant & VARIANT_PV_PAIRDESC))
+        pvoc512_kernel<true, false, true, true><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
+                                                                      pairs_per_item, tab, centroid, rolloff,
+                                                                      flatness, flux, nullptr);
+    else if (variant & VARIANT_PV_PAIRDESC)
+        pvoc512_kernel<true, false, false, true><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
+                                                                       pairs_per_item, tab, centroid, rolloff,
+                                                                       flatness, flux, nullptr);
+    else if (variant & VARIANT_PV_TWPROD)
         pvoc512_kernel<true, false, true><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
                                                                 pairs_per_item, tab, centroid, rolloff, flatness,
                                                                 flux, nullptr);

@@ -120,11 +120,44 @@ def test_stft_pair_kernel_design_on_host(tmp_path):
     assert "OK" in out.stdout
 
 
+def test_transposed_pair_reduction_tree_is_the_butterfly():
+    """pair_sum / pair_prod of spectral.cu (VARIANT_PV_PAIRDESC) reduce frame A's partials into lanes 0..15 and
+    frame B's into lanes 16..31 with one shuffle per step.  Their tree must be the xor-butterfly of warp_sum /
+    warp_prod, value for value -- modelled here lane by lane in f32 / f64 -- so that the variant's descriptors are
+    bit-identical to the default kernel's."""
+    lane = np.arange(32)
+    hi = (lane & 16) != 0
+
+    def butterfly(v, op):
+        v = v.copy()
+        for o in (16, 8, 4, 2, 1):
+            v = op(v, v[lane ^ o])
+        return v
+
+    def transposed(a, b, op):
+        mine, send = np.where(hi, b, a), np.where(hi, a, b)
+        mine = op(mine, send[lane ^ 16])
+        for o in (8, 4, 2, 1):
+            mine = op(mine, mine[lane ^ o])
+        return mine
+
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        a = (rng.standard_normal(32) * 10 ** rng.uniform(-3, 3)).astype(np.float32)
+        b = rng.standard_normal(32).astype(np.float32)
+        p = transposed(a, b, np.add)
+        assert np.array_equal(p[:16].view(np.uint32), butterfly(a, np.add)[:16].view(np.uint32))
+        assert np.array_equal(p[16:].view(np.uint32), butterfly(b, np.add)[16:].view(np.uint32))
+        da, db = rng.uniform(1, 2, 32), rng.uniform(1, 2, 32)
+        q = transposed(da, db, np.multiply)
+        assert np.array_equal(q[:16], butterfly(da, np.multiply)[:16]) and np.array_equal(q[16:], butterfly(db, np.multiply)[16:])
+
+
 def test_variant_mask_names_match_header():
     """BLISS_B200_VARIANT bits (A/B switch back to a kernel's previous implementation) stay documented."""
     txt = open(os.path.join(ROOT, "bliss-rs_b200", "csrc", "common.cuh")).read()
     for name in ("VARIANT_OLD_EPILOGUE = 1", "VARIANT_OLD_TUNING = 2", "VARIANT_OLD_CHROMA = 4", "VARIANT_OLD_ACF = 8",
-                 "VARIANT_BT512 = 16", "VARIANT_R64 = 32", "VARIANT_TWPROD = 64", "VARIANT_WINSYN = 128", "VARIANT_STFT_PAIRS = 256", "VARIANT_PV_TWPROD = 512"):
+                 "VARIANT_BT512 = 16", "VARIANT_R64 = 32", "VARIANT_TWPROD = 64", "VARIANT_WINSYN = 128", "VARIANT_STFT_PAIRS = 256", "VARIANT_PV_TWPROD = 512", "VARIANT_PV_PAIRDESC = 1024"):
         assert name in txt
 
 
