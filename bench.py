@@ -458,7 +458,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: %d synthetic 3-min 22050 Hz f32 mono tracks per GPU, full 23-feature "
                                    "analysis + feature-row exchange + all-pairs distance row block" % S,
-                       "songs_per_gpu": S, "track_samples": TRACK_SAMPLES, "parallelism": "songs sharded %d-way" % world,
+                       "songs_per_gpu": S, "track_samples": TRACK_SAMPLES,
+                       "kernel_variant_mask": int(os.environ.get("BLISS_B200_VARIANT", "0") or 0), "parallelism": "songs sharded %d-way" % world,
                        "l2": "inputs (%.1f GB PCM per GPU) are far larger than the 126 MB L2; no flush needed"
                              % (S * TRACK_SAMPLES * 4 / 1e9)},
             "e2e": e2e, "e2e_s16": e2e_s16, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "per_rank": per_rank,

@@ -60,7 +60,7 @@ def main():
     rd = tracks * TRACK * 4 / 1e9 / (ms / 1e3)
     wr = tracks * n_t * 257 * 4 / 1e9 / (ms / 1e3)
     print(json.dumps({
-        "bench": "stft512_hop256_mag", "tracks": tracks, "resident_tracks": R, "passes": passes,
+        "bench": "stft512_hop256_mag", "kernel_variant_mask": int(os.environ.get("BLISS_B200_VARIANT", "0") or 0), "tracks": tracks, "resident_tracks": R, "passes": passes,
         "ms_total": ms, "tracks_per_s": tracks / (ms / 1e3), "read_gbs_algorithmic": rd, "write_gbs": wr,
         "hbm_peak_gbs": peak, "peak_source": src, "frac_read_of_peak": rd / peak,
         "frac_read_plus_write_of_peak": (rd + wr) / peak,

@@ -1,0 +1,26 @@
+# round-2 opener (1 GPU): GPU tests (incl. the experimental kernel cuts written blind at the end of round 1),
+# then the same bench line once per BLISS_B200_VARIANT mask so that every cut is A/B-timed on one box, then the
+# STFT micro-benchmark with and without the hop-256 pair kernel.  Everything lands in gpurun_out/.
+#   gpurun --timeout 1500 -- 'bash scripts/gpu_r02_ab.sh'
+# masks: 64 stft8192 product twiddles | 128 stft8192 synthesised window | 512 pvoc512 product twiddles |
+#        1024 pvoc512 pair descriptors + MUFU-only magnitudes | 256 STFT micro-benchmark pair kernel
+mkdir -p gpurun_out; cd $GRAFT_REPO_ROOT
+nvidia-smi -L; nproc
+timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -s > gpurun_out/ab_tests.log 2>&1; echo TEST_EXIT $?; tail -6 gpurun_out/ab_tests.log | cut -c1-300
+grep -h "bit-identical" gpurun_out/ab_tests.log | head -3
+summ() { python - "$1" <<'PY'
+import json,sys
+try:
+    d=json.load(open(sys.argv[1]))
+    print(sys.argv[1], 'value %.0f' % d['value'], 'ms/step %.2f' % d['ms_per_step'], 'repro', d.get('bitwise_reproducible_across_steps'), 'par', (d.get('cpu_baseline') or {}).get('parity_max_abs_err'), ' '.join('%s=%.2f' % (k['kernel'][:8], k['avg_ms']) for k in d['roofline']['kernels'][:7]))
+except Exception as e:
+    print(sys.argv[1], 'unreadable', e)
+PY
+}
+for v in 0 64 128 192 512 1024 1536 1728; do
+  extra="--no-cpu-baseline"; [ $v = 0 ] && extra=""; [ $v = 1728 ] && extra=""   # parity against the oracle for the default and for everything on
+  BLISS_B200_VARIANT=$v timeout 400 python bench.py --steps 5 --warmup 3 $extra > gpurun_out/ab_v$v.json 2> gpurun_out/ab_v$v.err; echo "VARIANT $v exit $?"; summ gpurun_out/ab_v$v.json
+done
+for v in 0 256; do
+  BLISS_B200_VARIANT=$v timeout 200 python bench_stft.py --tracks 4000 --resident 1000 > gpurun_out/ab_stft_v$v.json 2> gpurun_out/ab_stft_v$v.err; echo "STFT VARIANT $v exit $?"; cut -c1-400 gpurun_out/ab_stft_v$v.json
+done
