@@ -114,7 +114,7 @@ __device__ __forceinline__ void epilogue_pairs(const cpx (&v)[16], const cpx *pm
 }
 
 // VAR (experimental cuts of pass 1, behind bliss_b200_set_variant; 0 = the measured kernel):
-constexpr int K3V_TWPROD = 1;  // pass-1 twiddles: 4 loads + 11 products instead of 15 loads (rfft8192.cuh)
+constexpr int K3V_TWPROD = 1;  // pass-1 and pass-2 twiddles: 4 loads + 11 products instead of 15 loads each (rfft8192.cuh)
 constexpr int K3V_WINSYN = 2;  // Hann pairs from the thread's phase instead of 16 window loads
 
 template <int Q>
@@ -219,7 +219,8 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
         else r8k::pass1_store(tid, v, tw1, buf);
     }
     __syncthreads();
-    r8k::pass2(tid, s_tw2, buf);
+    if constexpr ((VAR & K3V_TWPROD) != 0) r8k::pass2_prod(tid, s_tw2, buf);
+    else r8k::pass2(tid, s_tw2, buf);
     __syncthreads();
     float *sm = reinterpret_cast<float *>(buf);  // magnitudes for pip_track once the FFT data is dead
     float fmx;                                   // frame maximum

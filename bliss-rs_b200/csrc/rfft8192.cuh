@@ -101,6 +101,40 @@ BLISS_HD void pass2(int b, const cpx *tw2 /*[16][16]*/, cpx *buf) {
     }
 }
 
+// pass 2 with 4 twiddle loads instead of 15 (VARIANT_TWPROD, like pass1_store_prod): W256^j, ^2j, ^4j, ^8j from
+// the shared-memory table, the other eleven by products formed right before their use.
+BLISS_HD void pass2_prod(int b, const cpx *tw2 /*[16][16]*/, cpx *buf) {
+    const int blk = b >> 4, j = b & 15;
+    cpx *p = buf + 273 * blk + j;
+    cpx v[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) v[q] = p[17 * q];
+    fft_dif<16>(v);
+    const cpx t1 = tw2[16 * 1 + j], t2 = tw2[16 * 2 + j], t4 = tw2[16 * 4 + j], t8 = tw2[16 * 8 + j];
+#define BLISS_P2(k2, w) p[17 * (k2)] = cmul(v[bitrev((k2), 4)], (w))
+    p[0] = v[0];
+    BLISS_P2(8, t8);
+    BLISS_P2(4, t4);
+    BLISS_P2(12, cmul(t4, t8));
+    BLISS_P2(2, t2);
+    BLISS_P2(10, cmul(t2, t8));
+    const cpx t6 = cmul(t2, t4);
+    BLISS_P2(6, t6);
+    BLISS_P2(14, cmul(t6, t8));
+    BLISS_P2(1, t1);
+    BLISS_P2(9, cmul(t1, t8));
+    const cpx t5 = cmul(t1, t4);
+    BLISS_P2(5, t5);
+    BLISS_P2(13, cmul(t5, t8));
+    const cpx t3 = cmul(t1, t2);
+    BLISS_P2(3, t3);
+    BLISS_P2(11, cmul(t3, t8));
+    const cpx t7 = cmul(t3, t4);
+    BLISS_P2(7, t7);
+    BLISS_P2(15, cmul(t7, t8));
+#undef BLISS_P2
+}
+
 // pass 3: butterfly b in [0,256): 16 consecutive logical elements;  pad(16 b + q) = 17 b + (b>>4) + q
 BLISS_HD void pass3(int b, cpx *buf) {
     cpx *p = buf + 17 * b + (b >> 4);

@@ -298,6 +298,19 @@ int main() {
             }
             printf("pass-1 product twiddles: max diff %.3e of %.3e\n", dmax, vmax);
             if (!(dmax <= 1e-6 * vmax)) { printf("product twiddles disagree\n"); return 9; }
+            bufB = bufA;  // same input to both forms of pass 2
+            for (int bb = 0; bb < 256; bb++) {
+                r8k::pass2(bb, tw2.data(), bufA.data());
+                r8k::pass2_prod(bb, tw2.data(), bufB.data());
+            }
+            dmax = vmax = 0;
+            for (int i = 0; i < 4096; i++) {
+                const cpx p = bufA[r8k::pad(i)], q = bufB[r8k::pad(i)];
+                dmax = fmax(dmax, fmax(fabs(p.x - q.x), fabs(p.y - q.y)));
+                vmax = fmax(vmax, fmax(fabs(p.x), fabs(p.y)));
+            }
+            printf("pass-2 product twiddles: max diff %.3e of %.3e\n", dmax, vmax);
+            if (!(dmax <= 1e-6 * vmax)) { printf("pass-2 product twiddles disagree\n"); return 12; }
         }
         // ---- VARIANT_WINSYN: Hann pairs from the thread's phase against the reference's f32 window ----
         {
