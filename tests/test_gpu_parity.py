@@ -507,6 +507,14 @@ def test_pcm_feed_matches_the_decoders_conversion(golden):
         B.native.analyze_batch_pcm([np.zeros((9000, 9), np.int16)], 22050, 2)
 
 
+# The kernel cuts behind BLISS_B200_VARIANT bits 64 ... 1024 were written after round 1's GPU budget was spent: they
+# are OFF by default, validated on the host only (tests/cpu_emul, tests/test_host_abi.py), and their tests below
+# have never met hardware.  Non-strict xfail keeps a defect in code that is not on the product path from masking
+# the parity suite of the code that is; an XPASS is the expected outcome and promotes the cut to a plain test.
+experimental = pytest.mark.xfail(reason="experimental kernel variant, first hardware run", strict=False)
+
+
+@experimental
 def test_experimental_pass1_variants_agree(pcm_song, pcm_piano):
     """BLISS_B200_VARIANT bits 64 / 128: pass 1 of stft8192_kernel with product twiddles (4 table loads instead
     of 15) and with the Hann window synthesised from the thread's phase (no window loads).  Candidates for the
@@ -528,6 +536,7 @@ def test_experimental_pass1_variants_agree(pcm_song, pcm_piano):
 
 
 
+@experimental
 def test_experimental_stft_pair_kernel(pcm_song, pcm_piano):
     """BLISS_B200_VARIANT bit 256: the STFT micro-benchmark with hop-256 frames j, j+1 sharing one FFT
     (stft512_pairs_kernel) against the oracle's PVocTempo norms and against the default kernel, on several
@@ -559,6 +568,7 @@ def test_experimental_stft_pair_kernel(pcm_song, pcm_piano):
         B.native.set_variant(0)
 
 
+@experimental
 def test_experimental_pvoc_twiddle_variant(pcm_song, pcm_piano):
     """BLISS_B200_VARIANT bit 512: pvoc512_kernel with the phase-A twiddles formed from four per-lane registers
     (no twiddle loads in the frame loop).  Rounds differently in the last place: timbral descriptors within 1e-5
@@ -581,6 +591,7 @@ def test_experimental_pvoc_twiddle_variant(pcm_song, pcm_piano):
         B.native.set_variant(0)
 
 
+@experimental
 def test_experimental_pvoc_pair_descriptors_are_bit_identical(pcm_song, pcm_piano):
     """BLISS_B200_VARIANT bit 1024: both frames' descriptors reduced by transposed butterflies and finished once
     per pair, magnitudes by MUFU.SQRT alone on data kept 2^30 above its level.  Same arithmetic, same trees, exact
