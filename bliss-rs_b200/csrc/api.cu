@@ -886,7 +886,7 @@ int bliss_b200_gather_destroy(bliss_b200_gather *ga) {
     return BLISS_B200_OK;
 }
 
-}  // extern "C" (the host path below is a template)
+}  // extern "C" (the host path below is internal)
 
 // host buffers: chunks of songs are copied on the copy stream while earlier chunks compute
 // HostPcm describes what the host pointers hold.  {F32, 1}: the decoder's output as the reference hands it to
