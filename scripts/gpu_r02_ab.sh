@@ -22,5 +22,5 @@ for v in 0 64 128 192 512 1024 1536 1728; do
   BLISS_B200_VARIANT=$v timeout 400 python bench.py --steps 5 --warmup 3 $extra > gpurun_out/ab_v$v.json 2> gpurun_out/ab_v$v.err; echo "VARIANT $v exit $?"; summ gpurun_out/ab_v$v.json
 done
 for v in 0 256; do
-  BLISS_B200_VARIANT=$v timeout 200 python bench_stft.py --tracks 4000 --resident 1000 > gpurun_out/ab_stft_v$v.json 2> gpurun_out/ab_stft_v$v.err; echo "STFT VARIANT $v exit $?"; cut -c1-400 gpurun_out/ab_stft_v$v.json
+  BLISS_B200_VARIANT=$v timeout 300 python bench_stft.py --tracks 4000 --resident 1000 --cufft > gpurun_out/ab_stft_v$v.json 2> gpurun_out/ab_stft_v$v.err; echo "STFT VARIANT $v exit $?"; cut -c1-400 gpurun_out/ab_stft_v$v.json
 done
