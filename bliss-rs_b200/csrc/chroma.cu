@@ -116,6 +116,7 @@ __device__ __forceinline__ void epilogue_pairs(const cpx (&v)[16], const cpx *pm
 // VAR (experimental cuts of pass 1, behind bliss_b200_set_variant; 0 = the measured kernel):
 constexpr int K3V_TWPROD = 1;  // pass-1 and pass-2 twiddles: 4 loads + 11 products instead of 15 loads each (rfft8192.cuh)
 constexpr int K3V_WINSYN = 2;  // Hann pairs from the thread's phase instead of 16 window loads
+constexpr int K3V_LAY16 = 4;   // column-group pitch 16 instead of 17 in the FFT buffer: conflict-free mirror loads (rfft8192.cuh)
 
 template <int Q>
 __device__ __forceinline__ void window_synth(cpx (&v)[16], cpx cw, cpx sw) {
@@ -140,6 +141,7 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     __shared__ unsigned int s_scan[K3_THREADS / 32];
     __shared__ unsigned int s_base;
 
+    constexpr int LB = (PAIR_EPILOGUE && (VAR & K3V_LAY16) != 0) ? 16 : 17;  // the old epilogue gathers by bin: keeps pad()
     const int tid = threadIdx.x;
     s_tw2[tid] = tw2g[tid];  // visible after the barrier that follows pass 1
     const unsigned int item = blockIdx.x;
@@ -215,12 +217,12 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
                 v[q] = pmul(cpx{r8k::reflect_sample(x, n, i0), r8k::reflect_sample(x, n, i0 + 1)}, cpx{w.x, w.y});
             }
         }
-        if constexpr ((VAR & K3V_TWPROD) != 0) r8k::pass1_store_prod(tid, v, tw1, buf);
-        else r8k::pass1_store(tid, v, tw1, buf);
+        if constexpr ((VAR & K3V_TWPROD) != 0) r8k::pass1_store_prod<LB>(tid, v, tw1, buf);
+        else r8k::pass1_store<LB>(tid, v, tw1, buf);
     }
     __syncthreads();
-    if constexpr ((VAR & K3V_TWPROD) != 0) r8k::pass2_prod(tid, s_tw2, buf);
-    else r8k::pass2(tid, s_tw2, buf);
+    if constexpr ((VAR & K3V_TWPROD) != 0) r8k::pass2_prod<LB>(tid, s_tw2, buf);
+    else r8k::pass2<LB>(tid, s_tw2, buf);
     __syncthreads();
     float *sm = reinterpret_cast<float *>(buf);  // magnitudes for pip_track once the FFT data is dead
     float fmx;                                   // frame maximum
@@ -267,10 +269,10 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
         float *gm = mags + (size_t)(mag_row0 + (unsigned int)f) * CH_STRIDE;
         {
             cpx v[16];
-            r8k::pass3_regs(tid, v, buf);
+            r8k::pass3_regs<LB>(tid, v, buf);
             __syncthreads();
             const cpx wt = tw8192[tid];
-            const cpx *pm = buf + r8k::zbase((256 - tid) & 255) + 15;
+            const cpx *pm = buf + r8k::zbase<LB>((256 - tid) & 255) + 15;
             epilogue_pairs<0>(v, pm, tid == 0, buf, wt, gm + tid, gm + 4096 - tid, lo, mx);
             if (tid == 0) {  // the self-mirrored bin 2048: W8192^2048 = -i
                 const float mid = r8k::untangle_mag(v[bitrev(8, 4)], v[bitrev(8, 4)], cpx{0.f, -1.f});
@@ -1157,18 +1159,24 @@ int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int 
     else if (variant & VARIANT_OLD_EPILOGUE)
         stft8192_kernel<false><<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw1, tw2,
                                                                     tw8192, mags, cand_mag, cand_pitch, cand_count);
-    else if ((variant & VARIANT_TWPROD) && (variant & VARIANT_WINSYN))
-        stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN><<<total_frames, K3_THREADS, 0, st>>>(
-            pcm, songs, frame_prefix, n_songs, hann, tw1, tw2, tw8192, mags, cand_mag, cand_pitch, cand_count);
-    else if (variant & VARIANT_TWPROD)
-        stft8192_kernel<true, K3V_TWPROD><<<total_frames, K3_THREADS, 0, st>>>(
-            pcm, songs, frame_prefix, n_songs, hann, tw1, tw2, tw8192, mags, cand_mag, cand_pitch, cand_count);
-    else if (variant & VARIANT_WINSYN)
-        stft8192_kernel<true, K3V_WINSYN><<<total_frames, K3_THREADS, 0, st>>>(
-            pcm, songs, frame_prefix, n_songs, hann, tw1, tw2, tw8192, mags, cand_mag, cand_pitch, cand_count);
-    else
-        stft8192_kernel<true><<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw1, tw2,
-                                                                   tw8192, mags, cand_mag, cand_pitch, cand_count);
+    else {
+        auto go = [&](auto kern) {
+            kern<<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw1, tw2, tw8192, mags,
+                                                      cand_mag, cand_pitch, cand_count);
+        };
+        const int var = ((variant & VARIANT_TWPROD) ? K3V_TWPROD : 0) | ((variant & VARIANT_WINSYN) ? K3V_WINSYN : 0) |
+                        ((variant & VARIANT_LAY16) ? K3V_LAY16 : 0);
+        switch (var) {
+            case 1: go(stft8192_kernel<true, 1>); break;
+            case 2: go(stft8192_kernel<true, 2>); break;
+            case 3: go(stft8192_kernel<true, 3>); break;
+            case 4: go(stft8192_kernel<true, 4>); break;
+            case 5: go(stft8192_kernel<true, 5>); break;
+            case 6: go(stft8192_kernel<true, 6>); break;
+            case 7: go(stft8192_kernel<true, 7>); break;
+            default: go(stft8192_kernel<true>); break;
+        }
+    }
     return 1;
 }
 

@@ -60,6 +60,8 @@ enum {
     VARIANT_STFT_PAIRS = 256,  // STFT micro-benchmark: hop-256 frames j, j+1 share one FFT, 128-byte magnitude stores (experimental)
     VARIANT_PV_TWPROD = 512,   // pvoc512: phase-A twiddles from 4 per-lane registers + 11 products instead of 15 smem loads per pair (experimental)
     VARIANT_PV_PAIRDESC = 1024, // pvoc512: both frames' descriptors reduced / finished together, MUFU-only magnitudes on 2^30-scaled data (experimental; bit-identical results)
+    VARIANT_PV_ZPOS4 = 2048,   // pvoc512: natural-order tile padded k + (k >> 4): conflict-free stores as well as loads (experimental; bit-identical results)
+    VARIANT_LAY16 = 4096,      // stft8192: FFT buffer without the per-16 padding: conflict-free mirror loads in the pair epilogue (experimental; bit-identical results)
     VARIANT_WINSYN = 128,      // stft8192: Hann window from the thread's phase (2 FFMA2 per pair) instead of 16 loads (experimental)
 };
 

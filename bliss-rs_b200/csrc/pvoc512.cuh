@@ -22,6 +22,13 @@ namespace pv {
 constexpr int ROW = 33;                       // padded row (float2 units) of the 16x32 exchange tile
 constexpr int EXCH_CPX = 584;                 // >= max(16*33, zpos(511)+1 = 575)
 BLISS_HD int zpos(int k) { return k + (k >> 3); }   // padded natural-order position of bin k
+// The same tile with another padding (experimental): SHIFT = 4 keeps the 8-bins-per-lane loads of pvoc512_kernel
+// conflict-free and also frees its natural-order STORE (lanes k1 = 0..15 write consecutive slots; with SHIFT = 3
+// slots k1 = 0 and k1 = 15 of every store share a bank: 64 instead of 32 wavefronts per frame pair -- the 35
+// conflict wavefronts per pair of the ncu capture).  SHIFT = 0: no padding, the conflict-free choice when lanes own
+// bins lane + 32 i (stft512_pairs_kernel).  Wavefront model: tests/test_host_abi.py.
+template <int SHIFT>
+BLISS_HD int zpos_s(int k) { return SHIFT > 0 ? k + (k >> SHIFT) : k; }
 
 // Phase A (lane = n2): r[n1] = z[lane + 32*n1]; radix-16 over n1, twiddle
 // W512^(lane*k1), scatter to S[k1][lane].

@@ -23,9 +23,15 @@ BLISS_HD int pad(int i) { return i + (i >> 4) + (i >> 8); }
 
 // pass 1: butterfly b in [0,256): v[q] = z[b + 256 q];  pad(b + 256 k1) = b + (b>>4) + 273 k1.
 // tw1 is laid out [k1][b] = W4096^(b k1) so that the 32 lanes of a warp read 256 contiguous bytes.
+// LB: pitch of a 16-element column group inside a 256-element row (position = 273 r + LB c + m for the logical
+// element 256 r + 16 c + m).  17 = pad() above, the measured layout.  16 (experimental, VARIANT_LAY16) drops the
+// per-group padding: passes 1-3 stay conflict-free and the mirror loads of the pair epilogue lose their 2-way
+// conflict (thread t reads the block of thread 256 - t: with LB = 17 lanes 0 and 15 of every half-warp meet in one
+// bank, 256 instead of 136 wavefronts per frame -- the model is tests/test_host_abi.py).
+template <int LB = 17>
 BLISS_HD void pass1_store(int b, cpx (&v)[16], const cpx *tw1 /*[16][256]*/, cpx *buf) {
     fft_dif<16>(v);
-    cpx *o = buf + b + (b >> 4);
+    cpx *o = LB == 17 ? buf + b + (b >> 4) : buf + (b & 15) + LB * (b >> 4);
     const cpx *t = tw1 + b;
 #pragma unroll
     for (int s = 0; s < 16; s++) {
@@ -41,9 +47,10 @@ BLISS_HD void pass1_store(int b, cpx (&v)[16], const cpx *tw1 /*[16][256]*/, cpx
 // by the L1 / shared-memory data pipe (profiles/): 11 fewer 64-bit loads per thread are 176 fewer wavefronts per
 // frame for 22 more packed FP instructions per thread.  Products are formed right before their use so that only
 // the four loaded values stay live.
+template <int LB = 17>
 BLISS_HD void pass1_store_prod(int b, cpx (&v)[16], const cpx *tw1 /*[16][256]*/, cpx *buf) {
     fft_dif<16>(v);
-    cpx *o = buf + b + (b >> 4);
+    cpx *o = LB == 17 ? buf + b + (b >> 4) : buf + (b & 15) + LB * (b >> 4);
     const cpx *t = tw1 + b;
     const cpx t1 = t[256 * 1], t2 = t[256 * 2], t4 = t[256 * 4], t8 = t[256 * 8];
 #define BLISS_P1(k1, w) o[273 * (k1)] = cmul(v[bitrev((k1), 4)], (w))
@@ -85,33 +92,35 @@ BLISS_HD cpx hann_pair(cpx cw, cpx sw) {
 // pass 2: butterfly b in [0,256): blk = b>>4 (k1), j = b&15; radix 16 at stride 16 inside the
 // 256-block;  pad(256 blk + j + 16 q) = 273 blk + j + 17 q;  twiddle tw2[k2][j] = W256^(j k2)
 // (a 2 KB table the kernel keeps in shared memory)
+template <int LB = 17>
 BLISS_HD void pass2(int b, const cpx *tw2 /*[16][16]*/, cpx *buf) {
     const int blk = b >> 4, j = b & 15;
     cpx *p = buf + 273 * blk + j;
     cpx v[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) v[q] = p[17 * q];
+    for (int q = 0; q < 16; q++) v[q] = p[LB * q];
     fft_dif<16>(v);
 #pragma unroll
     for (int s = 0; s < 16; s++) {
         const int k2 = bitrev(s, 4);
         cpx o = v[s];
         if (k2 != 0) o = cmul(o, tw2[16 * k2 + j]);
-        p[17 * k2] = o;
+        p[LB * k2] = o;
     }
 }
 
 // pass 2 with 4 twiddle loads instead of 15 (VARIANT_TWPROD, like pass1_store_prod): W256^j, ^2j, ^4j, ^8j from
 // the shared-memory table, the other eleven by products formed right before their use.
+template <int LB = 17>
 BLISS_HD void pass2_prod(int b, const cpx *tw2 /*[16][16]*/, cpx *buf) {
     const int blk = b >> 4, j = b & 15;
     cpx *p = buf + 273 * blk + j;
     cpx v[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) v[q] = p[17 * q];
+    for (int q = 0; q < 16; q++) v[q] = p[LB * q];
     fft_dif<16>(v);
     const cpx t1 = tw2[16 * 1 + j], t2 = tw2[16 * 2 + j], t4 = tw2[16 * 4 + j], t8 = tw2[16 * 8 + j];
-#define BLISS_P2(k2, w) p[17 * (k2)] = cmul(v[bitrev((k2), 4)], (w))
+#define BLISS_P2(k2, w) p[LB * (k2)] = cmul(v[bitrev((k2), 4)], (w))
     p[0] = v[0];
     BLISS_P2(8, t8);
     BLISS_P2(4, t4);
@@ -147,7 +156,8 @@ BLISS_HD void pass3(int b, cpx *buf) {
 }
 
 // padded position of Z[t + 256 m], t < 256, m < 16:  zbase(t) + m
-BLISS_HD int zbase(int t) { return 273 * (t & 15) + 17 * (t >> 4); }
+template <int LB = 17>
+BLISS_HD int zbase(int t) { return 273 * (t & 15) + LB * (t >> 4); }
 
 // pass 3 fused with the untangling: thread t transforms the block that ENDS UP holding its own
 // natural-order bins (block zbase(t) = logical elements 16 b + q with b = 16 (t & 15) + (t >> 4)),
@@ -156,8 +166,9 @@ BLISS_HD int zbase(int t) { return 273 * (t & 15) + 17 * (t >> 4); }
 // k = t' + 256 m', m' < 8, that thread t' = 256 - t untangles (thread 0 mirrors onto itself and also
 // publishes m = 0).  Shared-memory traffic of pass 3 + epilogue: 16 loads + 8 stores + 8 loads per
 // thread instead of 16 + 16 + 32.
+template <int LB = 17>
 BLISS_HD void pass3_regs(int t, cpx (&v)[16], cpx *buf) {
-    cpx *p = buf + zbase(t);
+    cpx *p = buf + zbase<LB>(t);
 #pragma unroll
     for (int q = 0; q < 16; q++) v[q] = p[q];
     fft_dif<16>(v);

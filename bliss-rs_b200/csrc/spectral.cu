@@ -195,7 +195,8 @@ __device__ __forceinline__ void pair_descriptors(const float (&va)[8], const flo
 // PAIRDESC: pair_descriptors + the data kept 2^30 above its level so that the magnitudes need MUFU.SQRT only
 // (approx_sqrtf_ftz): every result is bit-identical to the default kernel's unless an intermediate of the
 // default kernel is denormal.
-template <bool WITH_DESC, bool WITH_MAGS, bool TWPROD = false, bool PAIRDESC = false>
+// ZS: padding shift of the natural-order tile (pvoc512.cuh zpos_s; 3 = the measured layout, 4 = VARIANT_PV_ZPOS4).
+template <bool WITH_DESC, bool WITH_MAGS, bool TWPROD = false, bool PAIRDESC = false, int ZS = 3>
 __global__ void __launch_bounds__(256, K1_MINBLOCKS)
 pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
                const unsigned int *__restrict__ item_prefix, int n_songs, unsigned int total_items,
@@ -293,7 +294,7 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
         for (int q = 0; q < 16; q++) {
             const cpx o = shfl_xor_cpx(r[q], 16);
             const cpx z = pv::phase_b_combine(lane, r[q], o);
-            S[pv::zpos(pv::bin_of(lane, q))] = z;
+            S[pv::zpos_s<ZS>(pv::bin_of(lane, q))] = z;
         }
         __syncwarp();
         // natural-order epilogue: lane owns bins 8*lane .. 8*lane+7 of both frames
@@ -301,11 +302,11 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int k = 8 * lane + i;
-            const cpx zk = S[pv::zpos(k)];
-            const cpx zm = S[pv::zpos((512 - k) & 511)];
+            const cpx zk = S[pv::zpos_s<ZS>(k)];
+            const cpx zm = S[pv::zpos_s<ZS>((512 - k) & 511)];
             pv::untangle_mag<true, PAIRDESC>(zk, zm, ma[i], mb[i]);  // 2|A|, 2|B|: halved by ka / kb below
         }
-        const cpx zn = S[pv::zpos(256)];  // Nyquist: A = |Re|, B = |Im|
+        const cpx zn = S[pv::zpos_s<ZS>(256)];  // Nyquist: A = |Re|, B = |Im|
         float nyq_a = 2.f * fabsf(zn.x), nyq_b = 2.f * fabsf(zn.y);
         if (lane == 0) {  // DC: abs(re), aubio.rs:240 / :403
             const cpx z0 = S[0];
@@ -484,7 +485,7 @@ stft512_pairs_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__
         for (int q = 0; q < 16; q++) {
             const cpx o = shfl_xor_cpx(r[q], 16);
             const cpx z = pv::phase_b_combine(lane, r[q], o);
-            S[pv::zpos(pv::bin_of(lane, q))] = z;
+            S[pv::zpos_s<0>(pv::bin_of(lane, q))] = z;  // unpadded: conflict-free for bins lane + 32 i
         }
         __syncwarp();
         // lane owns bins lane + 32 i of both frames
@@ -492,11 +493,11 @@ stft512_pairs_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int k = lane + 32 * i;
-            const cpx zk = S[pv::zpos(k)];
-            const cpx zm = S[pv::zpos((512 - k) & 511)];
+            const cpx zk = S[pv::zpos_s<0>(k)];
+            const cpx zm = S[pv::zpos_s<0>((512 - k) & 511)];
             pv::untangle_mag<true>(zk, zm, ma[i], mb[i]);  // 2|A|, 2|B|
         }
-        const cpx zn = S[pv::zpos(256)];  // Nyquist: A = |Re|, B = |Im| (aubio.rs:403-405)
+        const cpx zn = S[pv::zpos_s<0>(256)];  // Nyquist: A = |Re|, B = |Im| (aubio.rs:403-405)
         float nyq_a = 2.f * fabsf(zn.x), nyq_b = 2.f * fabsf(zn.y);
         if (lane == 0) {  // DC: abs(re), aubio.rs:403
             const cpx z0 = S[0];
@@ -609,22 +610,23 @@ int launch_pvoc512(const float *pcm, const SongDesc *songs, const unsigned int *
                    float *rolloff, float *flatness, float *flux, int variant, cudaStream_t st) {
     if (total_items == 0) return 0;
     const unsigned int grid = (total_items + 7u) / 8u;
-    if ((variant & VARIANT_PV_TWPROD) && (variant & VARIANT_PV_PAIRDESC))
-        pvoc512_kernel<true, false, true, true><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
-                                                                      pairs_per_item, tab, centroid, rolloff,
-                                                                      flatness, flux, nullptr);
-    else if (variant & VARIANT_PV_PAIRDESC)
-        pvoc512_kernel<true, false, false, true><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
-                                                                       pairs_per_item, tab, centroid, rolloff,
-                                                                       flatness, flux, nullptr);
-    else if (variant & VARIANT_PV_TWPROD)
-        pvoc512_kernel<true, false, true><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
-                                                                pairs_per_item, tab, centroid, rolloff, flatness,
-                                                                flux, nullptr);
-    else
-        pvoc512_kernel<true, false><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
-                                                          pairs_per_item, tab, centroid, rolloff, flatness,
-                                                          flux, nullptr);
+    auto go = [&](auto kern) {
+        kern<<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items, pairs_per_item, tab, centroid, rolloff,
+                                   flatness, flux, nullptr);
+    };
+    const bool tw = (variant & VARIANT_PV_TWPROD) != 0, pd = (variant & VARIANT_PV_PAIRDESC) != 0,
+               z4 = (variant & VARIANT_PV_ZPOS4) != 0;
+    if (z4) {
+        if (tw && pd) go(pvoc512_kernel<true, false, true, true, 4>);
+        else if (pd) go(pvoc512_kernel<true, false, false, true, 4>);
+        else if (tw) go(pvoc512_kernel<true, false, true, false, 4>);
+        else go(pvoc512_kernel<true, false, false, false, 4>);
+    } else {
+        if (tw && pd) go(pvoc512_kernel<true, false, true, true>);
+        else if (pd) go(pvoc512_kernel<true, false, false, true>);
+        else if (tw) go(pvoc512_kernel<true, false, true>);
+        else go(pvoc512_kernel<true, false>);
+    }
     return 1;
 }
 

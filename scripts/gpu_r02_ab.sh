@@ -3,7 +3,9 @@
 # STFT micro-benchmark with and without the hop-256 pair kernel.  Everything lands in gpurun_out/.
 #   gpurun --timeout 1500 -- 'bash scripts/gpu_r02_ab.sh'
 # masks: 64 stft8192 product twiddles | 128 stft8192 synthesised window | 512 pvoc512 product twiddles |
-#        1024 pvoc512 pair descriptors + MUFU-only magnitudes | 256 STFT micro-benchmark pair kernel
+#        1024 pvoc512 pair descriptors + MUFU-only magnitudes | 2048 pvoc512 conflict-free tile padding |
+#        4096 stft8192 conflict-free buffer layout | 256 STFT micro-benchmark pair kernel
+#        (4288 = all stft8192 cuts, 3584 = all pvoc512 cuts, 7872 = everything)
 mkdir -p gpurun_out; cd $GRAFT_REPO_ROOT
 nvidia-smi -L; nproc
 timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -s > gpurun_out/ab_tests.log 2>&1; echo TEST_EXIT $?; tail -6 gpurun_out/ab_tests.log | cut -c1-300
@@ -17,8 +19,8 @@ except Exception as e:
     print(sys.argv[1], 'unreadable', e)
 PY
 }
-for v in 0 64 128 192 512 1024 1536 1728; do
-  extra="--no-cpu-baseline"; [ $v = 0 ] && extra=""; [ $v = 1728 ] && extra=""   # parity against the oracle for the default and for everything on
+for v in 0 64 128 4096 4288 512 1024 2048 3584 7872; do
+  extra="--no-cpu-baseline"; [ $v = 0 ] && extra=""; [ $v = 7872 ] && extra=""   # parity against the oracle for the default and for everything on
   BLISS_B200_VARIANT=$v timeout 400 python bench.py --steps 5 --warmup 3 $extra > gpurun_out/ab_v$v.json 2> gpurun_out/ab_v$v.err; echo "VARIANT $v exit $?"; summ gpurun_out/ab_v$v.json
 done
 for v in 0 256; do

@@ -72,6 +72,23 @@ int main() {
         }
         printf("fft512 pair: max rel err %.3e\n", err);
         worst = fmax(worst, err);
+        // the other paddings of the natural-order tile (zpos_s<4>: VARIANT_PV_ZPOS4, zpos_s<0>: stft512_pairs_kernel)
+        // are injective, fit the tile, and carry the same untangling
+        {
+            std::vector<int> seen4(pv::EXCH_CPX, 0), seen0(pv::EXCH_CPX, 0);
+            for (int k = 0; k < 512; k++) {
+                const int p4 = pv::zpos_s<4>(k), p0 = pv::zpos_s<0>(k);
+                if (p4 >= pv::EXCH_CPX || p0 >= pv::EXCH_CPX || seen4[p4]++ || seen0[p0]++) { printf("zpos_s collision at %d\n", k); return 13; }
+            }
+            std::vector<cpx> Z4(pv::EXCH_CPX);
+            for (int k = 0; k < 512; k++) Z4[pv::zpos_s<4>(k)] = Z[pv::zpos(k)];
+            for (int k = 0; k <= 256; k++) {
+                float fa, fb, ga, gb;
+                pv::untangle_mag(Z[pv::zpos(k)], Z[pv::zpos((512 - k) & 511)], fa, fb);
+                pv::untangle_mag(Z4[pv::zpos_s<4>(k)], Z4[pv::zpos_s<4>((512 - k) & 511)], ga, gb);
+                if (fa != ga || fb != gb) { printf("zpos_s<4> changes bin %d\n", k); return 14; }
+            }
+        }
         // VARIANT_PV_TWPROD: phase A with product twiddles stores (nearly) what the table form stores
         {
             std::vector<cpx> S2(pv::EXCH_CPX);
@@ -197,6 +214,50 @@ int main() {
             if (!(err2 == err2)) { printf("pair epilogue read an unpublished slot\n"); return 5; }
             printf("rfft8192 fused pass3 + pair epilogue: max rel err %.3e\n", err2);
             worst = fmax(worst, err2);
+        }
+        // ---- VARIANT_LAY16: the same three passes + pair epilogue on the buffer without the per-16 padding ----
+        {
+            std::vector<cpx> buf16(r8k::BUF_CPX, cpx{NAN, NAN});
+            for (int bb = 0; bb < 256; bb++) {
+                cpx v[16];
+                for (int q = 0; q < 16; q++) {
+                    const int nn = bb + 256 * q;
+                    v[q] = cpx{(float)a[2 * nn], (float)a[2 * nn + 1]};
+                }
+                r8k::pass1_store<16>(bb, v, tw.data(), buf16.data());
+            }
+            for (int bb = 0; bb < 256; bb++) r8k::pass2<16>(bb, tw2.data(), buf16.data());
+            static cpx regs16[256][16];
+            for (int t = 0; t < 256; t++) r8k::pass3_regs<16>(t, regs16[t], buf16.data());
+            for (int t = 0; t < 256; t++)
+                for (int m = (t == 0 ? 1 : 0); m < 8; m++) buf16[r8k::zbase<16>(t) + m] = cpx{NAN, NAN};
+            std::vector<int> hit(4097, 0);
+            double err16 = 0;
+            bool same = true;
+            for (int t = 0; t < 256; t++) {
+                const cpx *pm = buf16.data() + r8k::zbase<16>((256 - t) & 255) + 15;
+                for (int M = 0; M < 8; M++) {
+                    const int k = t + 256 * M;
+                    const cpx zk = regs16[t][bitrev(M, 4)];
+                    const cpx zm = (t == 0) ? buf16[(16 - M) & 15] : pm[-M];
+                    const cpx chk = r8k::z_value(buf.data(), (4096 - k) & 4095);  // the padded layout's value of the same bin
+                    if (zm.x != chk.x || zm.y != chk.y) same = false;
+                    const cpx w = cmul(tw8[t], cpx{(float)cos(-2.0 * M_PI * M / 32.0), (float)sin(-2.0 * M_PI * M / 32.0)});
+                    float mk, mm;
+                    r8k::untangle_mag_pair(zk, zm, w, mk, mm);
+                    hit[k]++;
+                    hit[4096 - k]++;
+                    err16 = fmax(err16, fabs(mk - ma[k]) / scale);
+                    err16 = fmax(err16, fabs(mm - ma[4096 - k]) / scale);
+                }
+            }
+            hit[2048]++;
+            for (int k = 0; k <= 4096; k++)
+                if (hit[k] != 1) { printf("LAY16 epilogue: bin %d produced %d times\n", k, hit[k]); return 15; }
+            if (!same) { printf("LAY16 mirror values differ from the padded layout's\n"); return 16; }
+            if (!(err16 == err16)) { printf("LAY16 epilogue read an unpublished slot\n"); return 17; }
+            printf("rfft8192 without the per-16 padding (LAY16): max rel err %.3e, mirror values identical\n", err16);
+            worst = fmax(worst, err16);
         }
         // ---- 4096 = 64 x 64: two radix-64 passes, 64 "threads" (rfft8192_r64.cuh) ----
         {

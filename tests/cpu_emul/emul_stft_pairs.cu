@@ -67,12 +67,12 @@ int main() {
                 for (int lane = 0; lane < 32; lane++) { pv::phase_b_load(lane, r[lane], S.data()); pv::phase_b_fft(lane, r[lane]); }
                 std::vector<cpx> Z(pv::EXCH_CPX);
                 for (int lane = 0; lane < 32; lane++)
-                    for (int q = 0; q < 16; q++) Z[pv::zpos(pv::bin_of(lane, q))] = pv::phase_b_combine(lane, r[lane][q], r[lane ^ 16][q]);
+                    for (int q = 0; q < 16; q++) Z[pv::zpos_s<0>(pv::bin_of(lane, q))] = pv::phase_b_combine(lane, r[lane][q], r[lane ^ 16][q]);
                 const float ka = (ua == 0u) ? 0.f : 0.5f, kb = (ub == 0u) ? 0.f : 0.5f * ginv;
                 for (int lane = 0; lane < 32; lane++) {
                     float ma[8], mb[8];
-                    for (int i = 0; i < 8; i++) { const int k = lane + 32 * i; pv::untangle_mag<true>(Z[pv::zpos(k)], Z[pv::zpos((512 - k) & 511)], ma[i], mb[i]); }
-                    const cpx zn = Z[pv::zpos(256)];
+                    for (int i = 0; i < 8; i++) { const int k = lane + 32 * i; pv::untangle_mag<true>(Z[pv::zpos_s<0>(k)], Z[pv::zpos_s<0>((512 - k) & 511)], ma[i], mb[i]); }
+                    const cpx zn = Z[pv::zpos_s<0>(256)];
                     float nyq_a = 2.f * fabsf(zn.x), nyq_b = 2.f * fabsf(zn.y);
                     if (lane == 0) { ma[0] = 2.f * fabsf(Z[0].x); mb[0] = 2.f * fabsf(Z[0].y); }
                     float *oa = out.data() + (size_t)j * 257;

@@ -624,3 +624,38 @@ def test_experimental_pvoc_pair_descriptors_are_bit_identical(pcm_song, pcm_pian
         assert np.abs(f[:, 1:10] - f0[:, 1:10]).max() < 1e-5 and np.array_equal(f[:, 10:], f0[:, 10:])
     finally:
         B.native.set_variant(0)
+
+
+@experimental
+def test_experimental_pvoc_tile_padding_is_bit_identical(pcm_song, pcm_piano):
+    """BLISS_B200_VARIANT bit 2048: the natural-order tile of pvoc512_kernel padded k + (k >> 4) instead of
+    k + (k >> 3) (conflict-free stores).  Only shared-memory addresses change: every feature bit for bit."""
+    songs = [pcm_song, pcm_piano] + [synth.gen_track(81, i, 22050 * 20 + 59 * i, device="cuda").cpu().numpy() for i in range(4)]
+    try:
+        B.native.set_variant(0)
+        st0, f0 = B.native.analyze_batch(songs, 2)
+        B.native.set_variant(2048)
+        st, f = B.native.analyze_batch(songs, 2)
+        assert (st0 == 0).all() and (st == 0).all()
+        assert np.array_equal(f, f0), np.abs(f - f0).max(0)
+    finally:
+        B.native.set_variant(0)
+
+
+@experimental
+def test_experimental_fft8192_buffer_layout_is_bit_identical(pcm_song, pcm_piano):
+    """BLISS_B200_VARIANT bit 4096: stft8192_kernel's FFT buffer without the per-16 padding (conflict-free mirror
+    loads in the pair epilogue).  Only shared-memory addresses change: every feature and every magnitude bit for bit."""
+    songs = [pcm_song, pcm_piano] + [synth.gen_track(82, i, 22050 * 20 + 61 * i, device="cuda").cpu().numpy() for i in range(4)]
+    try:
+        B.native.set_variant(0)
+        st0, f0 = B.native.analyze_batch(songs, 2)
+        _, _, taps0 = B.native.analyze_taps(pcm_piano, 2)
+        B.native.set_variant(4096)
+        st, f = B.native.analyze_batch(songs, 2)
+        _, _, taps = B.native.analyze_taps(pcm_piano, 2)
+        assert (st0 == 0).all() and (st == 0).all()
+        assert np.array_equal(f, f0), np.abs(f - f0).max(0)
+        assert np.array_equal(taps["stft8192"], taps0["stft8192"])
+    finally:
+        B.native.set_variant(0)

@@ -153,11 +153,83 @@ def test_transposed_pair_reduction_tree_is_the_butterfly():
         assert np.array_equal(q[:16], butterfly(da, np.multiply)[:16]) and np.array_equal(q[16:], butterfly(db, np.multiply)[16:])
 
 
+def test_natural_order_tile_padding_wavefront_model():
+    """Why VARIANT_PV_ZPOS4 and the unpadded tile of stft512_pairs_kernel exist: shared-memory wavefronts of the
+    512-point kernels' natural-order tile under the usual bank model (a 64-bit warp access = two half-warp
+    wavefronts, more when two lanes of a half-warp hit different 8-byte words of one bank pair).  The measured
+    kernel's padding k + (k >> 3) serves its loads (bins 8 lane + i) without conflicts but gives every one of its 16
+    stores a 2-way conflict -- 32 extra wavefronts per frame pair, the 35 conflict wavefronts per pair ncu reports
+    (profiles/ncu_r01b_full_128songs.md: 69.8 M conflicts over 1.98 M pairs)."""
+    def bitrev4(x):
+        return int("{:04b}".format(x)[::-1], 2)
+
+    def wavefronts(idx):
+        tot = 0
+        for h in (0, 1):
+            words = {}
+            for lane in range(16 * h, 16 * h + 16):
+                words.setdefault(idx[lane] % 16, set()).add(idx[lane])
+            tot += max(len(v) for v in words.values())
+        return tot
+
+    def bin_of(lane, q):
+        return (lane & 15) + 16 * (bitrev4(q) + 16 * (lane >> 4))
+
+    def cost(z, own):
+        st = sum(wavefronts([z(bin_of(l, q)) for l in range(32)]) for q in range(16))
+        ld = sum(wavefronts([z(own(l, i)) for l in range(32)]) for i in range(8))
+        mi = sum(wavefronts([z((512 - own(l, i)) & 511) for l in range(32)]) for i in range(8))
+        return st, ld, mi
+
+    eight_per_lane = lambda l, i: 8 * l + i     # pvoc512_kernel
+    strided = lambda l, i: l + 32 * i           # stft512_pairs_kernel
+    assert cost(lambda k: k + (k >> 3), eight_per_lane) == (64, 16, 16)   # measured layout: stores 2x the ideal 32
+    assert cost(lambda k: k + (k >> 4), eight_per_lane) == (32, 16, 18)   # VARIANT_PV_ZPOS4: -30 wavefronts per pair
+    assert cost(lambda k: k + (k >> 3), strided) == (64, 32, 32)
+    assert cost(lambda k: k, strided) == (32, 16, 16)                     # stft512_pairs_kernel: the ideal 64
+
+
+def test_fft8192_buffer_layout_wavefront_model():
+    """Why VARIANT_LAY16 exists: shared-memory wavefronts per frame of stft8192_kernel's FFT buffer (8-byte elements;
+    logical element 256 r + 16 c + m at 273 r + LB c + m) under the same bank model.  With the measured LB = 17 the
+    three passes are conflict-free but every mirror load of the pair epilogue (thread t reads the block thread 256 - t
+    published) puts lanes 0 and 15 of a half-warp into one bank: 256 instead of 136 wavefronts per frame, most of
+    the 202 conflict wavefronts per frame of the ncu capture (46.5 M over 230 400 frames)."""
+    def wavefronts(idx):
+        tot = 0
+        for h in range(0, len(idx), 16):
+            words = {}
+            for i in idx[h:h + 16]:
+                words.setdefault(i % 16, set()).add(i)
+            tot += max(len(v) for v in words.values())
+        return tot
+
+    def model(lb):
+        pos = lambda r, c, m: 273 * r + lb * c + m
+        t256 = range(256)
+        out = {"pass1 st": sum(wavefronts([pos(k1, b >> 4, b & 15) for b in t256]) for k1 in range(16)),
+               "pass2 ld": sum(wavefronts([pos(b >> 4, q, b & 15) for b in t256]) for q in range(16)),
+               "pass3 ld": sum(wavefronts([pos(t & 15, t >> 4, q) for t in t256]) for q in range(16)),
+               "pass3 st": sum(wavefronts([pos(t & 15, t >> 4, m) for t in t256]) for m in range(8, 16))}
+
+        def mirror(t, M):
+            if t == 0:
+                return pos(0, 0, (16 - M) & 15)
+            tp = (256 - t) & 255
+            return pos(tp & 15, tp >> 4, 15 - M)
+        out["mirror ld"] = sum(wavefronts([mirror(t, M) for t in t256]) for M in range(8))
+        assert len({pos(r, c, m) for r in range(16) for c in range(16) for m in range(16)}) == 4096  # injective
+        return out
+
+    assert model(17) == {"pass1 st": 256, "pass2 ld": 256, "pass3 ld": 256, "pass3 st": 128, "mirror ld": 256}
+    assert model(16) == {"pass1 st": 256, "pass2 ld": 256, "pass3 ld": 256, "pass3 st": 128, "mirror ld": 136}
+
+
 def test_variant_mask_names_match_header():
     """BLISS_B200_VARIANT bits (A/B switch back to a kernel's previous implementation) stay documented."""
     txt = open(os.path.join(ROOT, "bliss-rs_b200", "csrc", "common.cuh")).read()
     for name in ("VARIANT_OLD_EPILOGUE = 1", "VARIANT_OLD_TUNING = 2", "VARIANT_OLD_CHROMA = 4", "VARIANT_OLD_ACF = 8",
-                 "VARIANT_BT512 = 16", "VARIANT_R64 = 32", "VARIANT_TWPROD = 64", "VARIANT_WINSYN = 128", "VARIANT_STFT_PAIRS = 256", "VARIANT_PV_TWPROD = 512", "VARIANT_PV_PAIRDESC = 1024"):
+                 "VARIANT_BT512 = 16", "VARIANT_R64 = 32", "VARIANT_TWPROD = 64", "VARIANT_WINSYN = 128", "VARIANT_STFT_PAIRS = 256", "VARIANT_PV_TWPROD = 512", "VARIANT_PV_PAIRDESC = 1024", "VARIANT_PV_ZPOS4 = 2048", "VARIANT_LAY16 = 4096"):
         assert name in txt
 
 
