@@ -225,6 +225,20 @@ def test_fft8192_buffer_layout_wavefront_model():
     assert model(16) == {"pass1 st": 256, "pass2 ld": 256, "pass3 ld": 256, "pass3 st": 128, "mirror ld": 136}
 
 
+def test_rust_shim_files_match_integration_md():
+    """integration/rust/*.rs are INTEGRATION.md's ```rust blocks (scripts/extract_rust_shim.py), and every C-ABI
+    function the Rust side declares exists in the header with that name."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("extract_rust_shim", os.path.join(ROOT, "scripts", "extract_rust_shim.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    hdr = open(os.path.join(ROOT, "include", "bliss_b200.h")).read()
+    for name, text in mod.render().items():
+        assert open(os.path.join(ROOT, "integration", "rust", name)).read() == text, name
+        for fn in re.findall(r"\bfn (bliss_b200_[a-z0-9_]+)\(", text):
+            assert re.search(r"\b%s\s*\(" % fn, hdr), fn
+
+
 def test_variant_mask_names_match_header():
     """BLISS_B200_VARIANT bits (A/B switch back to a kernel's previous implementation) stay documented."""
     txt = open(os.path.join(ROOT, "bliss-rs_b200", "csrc", "common.cuh")).read()
