@@ -61,6 +61,7 @@ __global__ void f64_to_f32_kernel(const double *__restrict__ in, float *__restri
 }
 
 // builds the f64 table (chroma.rs:197-267 as written) and the f32 copy chroma_kernel multiplies with
+#ifndef BLISS_HOST_EMUL  // tests/cpu_emul/emul_kernels.cpp compiles this file's STFT kernels with g++ (no <<< >>>, no PTX)
 int launch_chroma_filter_table(double *table, float *table32, cudaStream_t st) {
     dim3 grid((CH_BINS + 127) / 128, 100);
     chroma_filter_table_kernel<<<grid, 128, 0, st>>>(table);
@@ -68,6 +69,7 @@ int launch_chroma_filter_table(double *table, float *table32, cudaStream_t st) {
     f64_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(table, table32, n);
     return 2;
 }
+#endif
 
 // ---------------------------------------------------------------------------
 // K3: one CTA (256 threads) per chroma frame: 8192-point real FFT as a 4096-point complex FFT
@@ -161,7 +163,9 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     // are requested into L2 now, a whole frame time before its loads need them.
     if (tid < 70 && f + 1 < fend) {
         const int nx = s0 + 8192 + 32 * tid;
+#ifdef __CUDA_ARCH__
         if (nx < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + nx));
+#endif
     }
 
     // pass 1 straight from global memory: z[nn] = w[2nn] x[2nn] + i w[2nn+1] x[2nn+1], nn = tid + 256 q
@@ -495,6 +499,7 @@ stft8192_r64_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ 
     }
 }
 
+#ifndef BLISS_HOST_EMUL  // everything below (tuning, contraction, launchers) is outside the host emulation
 // ---------------------------------------------------------------------------
 // K4: one CTA per song.  threshold = Midpoint median of the candidate magnitudes
 // (exact radix select on the f64 bit patterns: all values are positive), then the
@@ -1209,5 +1214,6 @@ int launch_chroma(const float *mags, const SongDesc *songs, const unsigned int *
     }
     return 1;
 }
+#endif  // BLISS_HOST_EMUL
 
 }  // namespace bliss

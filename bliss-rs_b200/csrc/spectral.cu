@@ -605,6 +605,7 @@ timedomain_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
 }
 
 // ---- launchers ---------------------------------------------------------------
+#ifndef BLISS_HOST_EMUL  // tests/cpu_emul/emul_kernels.cpp compiles the kernels above with g++ and runs them on the host
 int launch_pvoc512(const float *pcm, const SongDesc *songs, const unsigned int *item_prefix, int n_songs,
                    unsigned int total_items, int pairs_per_item, PvocTables tab, float *centroid,
                    float *rolloff, float *flatness, float *flux, int variant, cudaStream_t st) {
@@ -655,5 +656,6 @@ int launch_timedomain(const float *pcm, const SongDesc *songs, const unsigned in
                                             block_energy, zcr_count);
     return 1;
 }
+#endif  // BLISS_HOST_EMUL
 
 }  // namespace bliss

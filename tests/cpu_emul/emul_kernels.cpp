@@ -1,0 +1,210 @@
+// emul_kernels.cpp -- runs the SOURCE of this repository's CUDA kernels on the host (cuda_on_cpu/cuda_runtime.h:
+// every CUDA thread a fiber, warp collectives and __syncthreads() real rendezvous points) on one short song and
+// writes what they produce as raw little-endian arrays; tests/test_host_abi.py compares those with the oracle and
+// the experimental kernel cuts (BLISS_B200_VARIANT bits) with the measured kernels.
+//
+//   g++ -std=c++17 -O1 -ffp-contract=off -DBLISS_HOST_EMUL -I tests/cpu_emul/cuda_on_cpu emul_kernels.cpp
+//   ./emul_kernels song.f32 out_dir
+//
+// TEST INFRASTRUCTURE.  The kernels are compiled unmodified: the .cu files are #included, their launchers
+// (<<< >>>) and the kernels outside this emulation are compiled out by BLISS_HOST_EMUL, inline PTX has host
+// fall-backs behind #ifdef __CUDA_ARCH__.
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../bliss-rs_b200/csrc/spectral.cu"
+#include "../../bliss-rs_b200/csrc/wave_setup.cu"
+#include "../../bliss-rs_b200/csrc/chroma.cu"
+
+using namespace bliss;
+
+static std::string g_out;
+
+template <class T>
+static void dump(const char *name, const std::vector<T> &v) {
+    const std::string p = g_out + "/" + name;
+    FILE *f = fopen(p.c_str(), "wb");
+    if (!f) { perror(p.c_str()); exit(2); }
+    fwrite(v.data(), sizeof(T), v.size(), f);
+    fclose(f);
+}
+
+int main(int argc, char **argv) {
+    if (argc < 3) { fprintf(stderr, "usage: %s song.f32 out_dir\n", argv[0]); return 2; }
+    g_out = argv[2];
+    std::vector<float> x;
+    {
+        FILE *f = fopen(argv[1], "rb");
+        if (!f) { perror(argv[1]); return 2; }
+        fseek(f, 0, SEEK_END);
+        const long bytes = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        x.resize(bytes / 4);
+        if (fread(x.data(), 4, x.size(), f) != x.size()) return 2;
+        fclose(f);
+    }
+    const unsigned n = (unsigned)x.size();
+    x.resize(n + 8, 0.f);  // the kernels never read past n; the slack only keeps a violation from crashing first
+    // geometry of one song (api.cu geom_of): src/song/mod.rs:435-478, src/utils.rs:30
+    SongDesc sd;
+    memset(&sd, 0, sizeof(sd));
+    sd.n = n;
+    sd.n_s = (n - 512) / 128 + 1;
+    sd.n_t = (n - 512) / 256 + 1;
+    sd.n_c = (unsigned)ceilf((float)n / 2205.f);
+    sd.n_c_comp = std::min(sd.n_c, n / 2205 + 1);  // windows(8192).step_by(2205) over the n + 8192 padded samples
+    sd.n_l = (n + 1023) / 1024;
+    sd.valid = 1;
+    const std::vector<SongDesc> songs(1, sd);
+
+    // ---- tables (api.cu build_tables) --------------------------------------------------------------------
+    const float PI_F = 3.14159274101257324f;
+    std::vector<float> win(512);
+    for (int i = 0; i < 512; i++) win[i] = 0.5f * (1.0f - cosf(2.0f * PI_F * (float)i / 512.f));
+    std::vector<cpx> twA(16 * 32);
+    for (int k1 = 0; k1 < 16; k1++)
+        for (int l = 0; l < 32; l++) {
+            const double a = -2.0 * M_PI * (double)(k1 * l) / 512.0;
+            twA[k1 * 32 + l] = cpx{(float)cos(a), (float)sin(a)};
+        }
+    PvocTables tab{win.data(), twA.data()};
+    std::vector<float> hann(8192 + 4 * 256);
+    for (int i = 0; i < 8192; i++) hann[i] = 0.5f - 0.5f * cosf(2.f * (float)i * PI_F / 8192.f);
+    for (int t = 0; t < 256; t++) {
+        const double te = 2.0 * M_PI * (double)(2 * t) / 8192.0, to = 2.0 * M_PI * (double)(2 * t + 1) / 8192.0;
+        hann[8192 + 4 * t + 0] = (float)cos(te);
+        hann[8192 + 4 * t + 1] = (float)cos(to);
+        hann[8192 + 4 * t + 2] = (float)sin(te);
+        hann[8192 + 4 * t + 3] = (float)sin(to);
+    }
+    std::vector<cpx> tw4(4096), tw2(256), tw8(256);
+    for (int k1 = 0; k1 < 16; k1++)
+        for (int b = 0; b < 256; b++) {
+            const double a = -2.0 * M_PI * (double)(b * k1) / 4096.0;
+            tw4[k1 * 256 + b] = cpx{(float)cos(a), (float)sin(a)};
+        }
+    for (int k2 = 0; k2 < 16; k2++)
+        for (int j = 0; j < 16; j++) {
+            const double a = -2.0 * M_PI * (double)(j * k2) / 256.0;
+            tw2[k2 * 16 + j] = cpx{(float)cos(a), (float)sin(a)};
+        }
+    for (int m = 0; m < 256; m++) {
+        const double a = -2.0 * M_PI * (double)m / 8192.0;
+        tw8[m] = cpx{(float)cos(a), (float)sin(a)};
+    }
+
+    // ---- pvoc512_kernel: the measured build and the experimental cuts --------------------------------------
+    const int ppi = 8;  // pairs per work item: several items, so that halo pairs and item boundaries are exercised
+    const unsigned items = (sd.n_t + ppi - 1) / ppi;
+    const std::vector<unsigned> item_prefix = {0u, items};
+    auto run_pvoc = [&](const char *tag, auto kern) {
+        std::vector<float> cen(sd.n_s, -7.f), rol(sd.n_s, -7.f), fla(sd.n_s, -7.f), flux(sd.n_t, -7.f);
+        emu::launch((items + 7) / 8, 256, [&] {
+            kern(x.data(), songs.data(), item_prefix.data(), 1, items, ppi, tab, cen.data(), rol.data(), fla.data(),
+                 flux.data(), nullptr);
+        });
+        dump((std::string("centroid_") + tag).c_str(), cen);
+        dump((std::string("rolloff_") + tag).c_str(), rol);
+        dump((std::string("flatness_") + tag).c_str(), fla);
+        dump((std::string("flux_") + tag).c_str(), flux);
+    };
+    run_pvoc("default", pvoc512_kernel<true, false>);
+    run_pvoc("v512", pvoc512_kernel<true, false, true>);
+    run_pvoc("v1024", pvoc512_kernel<true, false, false, true>);
+    run_pvoc("v2048", pvoc512_kernel<true, false, false, false, 4>);
+    run_pvoc("v3584", pvoc512_kernel<true, false, true, true, 4>);
+
+    // ---- STFT micro-benchmark kernels ----------------------------------------------------------------------
+    {
+        std::vector<float> mags((size_t)sd.n_t * 257, -7.f);
+        emu::launch((items + 7) / 8, 256, [&] {
+            pvoc512_kernel<false, true>(x.data(), songs.data(), item_prefix.data(), 1, items, ppi, tab, nullptr, nullptr,
+                                        nullptr, nullptr, mags.data());
+        });
+        dump("stft512_default", mags);
+        const int fpi = 13;  // an odd item length: pairs straddle nothing, single frames end items
+        const unsigned items2 = (sd.n_t + fpi - 1) / fpi;
+        const std::vector<unsigned> prefix2 = {0u, items2};
+        std::fill(mags.begin(), mags.end(), -7.f);
+        emu::launch((items2 + 7) / 8, 256, [&] {
+            stft512_pairs_kernel(x.data(), songs.data(), prefix2.data(), 1, items2, fpi, tab, mags.data());
+        });
+        dump("stft512_v256", mags);
+    }
+
+    // ---- timedomain_kernel ---------------------------------------------------------------------------------
+    {
+        const unsigned groups = (sd.n_l + 7) / 8;
+        const std::vector<unsigned> gp = {0u, groups};
+        std::vector<float> loud(sd.n_l, -7.f), eb(n / 256 + 1, -7.f);
+        std::vector<unsigned> zcr(1, 0u);
+        emu::launch((groups + 7) / 8, 256, [&] {
+            timedomain_kernel(x.data(), songs.data(), gp.data(), 1, groups, loud.data(), eb.data(), zcr.data());
+        });
+        dump("loudness_chunks", loud);
+        dump("zcr_count", zcr);
+    }
+
+    // ---- pcm_to_mono_kernel: the song as 16-bit stereo (L = x, R = x / 2), 32-bit mono, 3-channel float -----
+    {
+        const size_t frames = (n + 3) / 4 * 4;
+        std::vector<short> st(2 * frames, 0);
+        std::vector<int> s32(frames, 0);
+        std::vector<float> f3(3 * frames, 0.f);
+        for (unsigned i = 0; i < n; i++) {
+            const short s = (short)lrintf(x[i] * 32767.f);
+            st[2 * i] = s;
+            st[2 * i + 1] = (short)(s / 2);
+            s32[i] = (int)s * 65536 + (int)(i % 251);
+            f3[3 * i] = x[i];
+            f3[3 * i + 1] = -0.5f * x[i];
+            f3[3 * i + 2] = 0.25f;
+        }
+        std::vector<float> out(frames, -7.f);
+        const unsigned grid = (unsigned)((frames / 4 + 255) / 256);
+        emu::launch(grid, 256, [&] { pcm_to_mono_kernel<1>(st.data(), out.data(), frames, 2u); });
+        dump("mono_from_s16_stereo", out);
+        dump("in_s16_stereo", st);
+        emu::launch(grid, 256, [&] { pcm_to_mono_kernel<2>(s32.data(), out.data(), frames, 1u); });
+        dump("mono_from_s32", out);
+        dump("in_s32", s32);
+        emu::launch(grid, 256, [&] { pcm_to_mono_kernel<3>(f3.data(), out.data(), frames, 3u); });
+        dump("mono_from_f32x3", out);
+        dump("in_f32x3", f3);
+    }
+
+    // ---- stft8192_kernel: the measured build and the experimental cuts ---------------------------------------
+    {
+        const unsigned ctas = (sd.n_c_comp + K3_FRAMES_PER_CTA - 1) / K3_FRAMES_PER_CTA;
+        const std::vector<unsigned> fp = {0u, ctas};
+        auto run_stft = [&](const char *tag, auto kern) {
+            std::vector<float> mags((size_t)sd.n_c_comp * CH_STRIDE, -7.f);
+            std::vector<double> cm((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.), cp((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.);
+            std::vector<unsigned> cc(1, 0u);
+            emu::launch(ctas, K3_THREADS, [&] {
+                kern(x.data(), songs.data(), fp.data(), 1, hann.data(), tw4.data(), tw2.data(), tw8.data(), mags.data(),
+                     cm.data(), cp.data(), cc.data());
+            });
+            std::vector<float> dense((size_t)sd.n_c_comp * CH_BINS);
+            for (unsigned f = 0; f < sd.n_c_comp; f++)
+                memcpy(&dense[(size_t)f * CH_BINS], &mags[(size_t)f * CH_STRIDE], CH_BINS * 4);
+            dump((std::string("stft8192_") + tag).c_str(), dense);
+            dump((std::string("peaks_") + tag).c_str(), cc);
+            cm.resize(cc[0]);
+            cp.resize(cc[0]);
+            std::sort(cm.begin(), cm.end());
+            std::sort(cp.begin(), cp.end());
+            dump((std::string("peak_mags_") + tag).c_str(), cm);
+            dump((std::string("peak_pitches_") + tag).c_str(), cp);
+        };
+        run_stft("default", stft8192_kernel<true>);
+        run_stft("v64", stft8192_kernel<true, K3V_TWPROD>);
+        run_stft("v128", stft8192_kernel<true, K3V_WINSYN>);
+        run_stft("v4096", stft8192_kernel<true, K3V_LAY16>);
+        run_stft("v4288", stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN | K3V_LAY16>);
+        run_stft("old_epilogue", stft8192_kernel<false>);
+    }
+    printf("n %u n_s %u n_t %u n_c %u n_c_comp %u n_l %u\nOK\n", n, sd.n_s, sd.n_t, sd.n_c, sd.n_c_comp, sd.n_l);
+    return 0;
+}

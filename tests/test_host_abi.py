@@ -109,6 +109,72 @@ def test_fft_index_logic_on_host(tmp_path):
     assert "OK" in out.stdout
 
 
+def test_kernel_sources_run_on_the_host(tmp_path, golden):
+    """tests/cpu_emul/emul_kernels.cpp: the SOURCE of pvoc512_kernel, stft512_pairs_kernel, timedomain_kernel,
+    pcm_to_mono_kernel and stft8192_kernel -- the measured builds and every experimental BLISS_B200_VARIANT cut --
+    compiled with g++ against cuda_on_cpu/cuda_runtime.h (each CUDA thread a fiber; shuffles, reductions and
+    __syncthreads() real rendezvous points) and run on a 40 000-sample clip with a stretch of digital silence.
+    Outputs against the oracle with the bars of the GPU stage tests; address-only and same-tree variants must be
+    bit-identical to the measured kernels (the host has no FMA contraction and an IEEE sqrt, so this says the
+    variants compute the same thing, not what the device rounds to)."""
+    from oracle import oracle as O
+    exe = str(tmp_path / "emul_kernels")
+    here = os.path.join(ROOT, "tests", "cpu_emul")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DBLISS_HOST_EMUL", "-I",
+                           os.path.join(here, "cuda_on_cpu"), "-o", exe, os.path.join(here, "emul_kernels.cpp")])
+    x = (golden["pcm_s16_mono"][20000:60000].astype(np.float32) / np.float32(32768.0)).copy()
+    x[15000:16500] = 0.0
+    song = str(tmp_path / "song.f32")
+    x.tofile(song)
+    out = subprocess.run([exe, song, str(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+    def ld(name, t=np.float32):
+        return np.fromfile(str(tmp_path / name), t)
+
+    def same_bits(a, b):
+        return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+    # ---- pvoc512_kernel and its cuts: per-frame descriptors + spectral flux
+    c, r, f = O.timbral_frames(x)
+    _, flux, _, _ = O.tempo(x, taps=True)
+    for tag in ("default", "v512", "v1024", "v2048", "v3584"):
+        ce, ro, fl, fx = (ld("%s_%s" % (k, tag)) for k in ("centroid", "rolloff", "flatness", "flux"))
+        assert ce.shape == c.shape and fx.shape == flux.shape
+        assert (np.abs(ce - c) / np.maximum(1.0, np.abs(c))).max() < 1e-4, tag
+        assert np.mean(ro != r) < 2e-3 and np.abs(ro - r).max() <= 2 * 22050 / 512 + 1e-3, tag
+        assert (np.abs(fl - f) / (2e-4 * np.abs(f) + 1e-5)).max() < 1.0, tag
+        assert np.abs(fx - flux).max() / np.abs(flux).max() < 1e-5, tag
+    for tag in ("v1024", "v2048"):   # transposed reductions / tile padding: the same arithmetic, the same trees
+        for k in ("centroid", "rolloff", "flatness", "flux"):
+            assert same_bits(ld("%s_%s" % (k, tag)), ld(k + "_default")), (tag, k)
+    # ---- STFT micro-benchmark kernels
+    want = O.tempo_norms(x)
+    for tag in ("default", "v256"):
+        m = ld("stft512_" + tag).reshape(-1, 257)
+        assert m.shape == want.shape and (m >= 0).all(), tag
+        assert np.abs(m - want).max() / want.max() < 1e-6, tag
+    # ---- timedomain_kernel
+    assert int(ld("zcr_count", np.uint32)[0]) == O.number_crossings(x)
+    chunks = ld("loudness_chunks")
+    ms = np.array([np.mean(x[i:i + 1024].astype(np.float64) ** 2) for i in range(0, x.size, 1024)])
+    assert chunks.shape == ms.shape and np.abs(chunks - ms).max() <= 1e-6 * ms.max()
+    # ---- pcm_to_mono_kernel: bit-exact against the oracle
+    assert same_bits(ld("mono_from_s16_stereo"), O.pcm_to_mono(ld("in_s16_stereo", np.int16).reshape(-1, 2)))
+    assert same_bits(ld("mono_from_s32"), O.pcm_to_mono(ld("in_s32", np.int32)))
+    assert same_bits(ld("mono_from_f32x3"), O.pcm_to_mono(ld("in_f32x3").reshape(-1, 3)))
+    # ---- stft8192_kernel and its cuts: magnitudes + pip-track candidates
+    S = O.stft(x, 8192, 2205)
+    p, _ = O.pip_track(S, 8192)
+    for tag in ("default", "v64", "v128", "v4096", "v4288", "old_epilogue"):
+        g = ld("stft8192_" + tag).reshape(-1, 4097)
+        assert g.T.shape == S.shape and (g >= 0).all(), tag
+        assert np.abs(g.T - S).max() / S.max() < 2e-6, tag
+        assert int(ld("peaks_" + tag, np.uint32)[0]) == p.size, tag
+        assert np.abs(ld("peak_pitches_" + tag, np.float64) - np.sort(p)).max() < 1e-3, tag
+    assert same_bits(ld("stft8192_v4096"), ld("stft8192_default"))       # addresses only
+
+
 def test_stft_pair_kernel_design_on_host(tmp_path):
     """tests/cpu_emul/emul_stft_pairs.cu: the hop-256 pairing of stft512_pairs_kernel (window rows, slide,
     load bounds, silence, magnitudes against an f64 DFT) transcribed onto the host."""
