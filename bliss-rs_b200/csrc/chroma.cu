@@ -499,7 +499,6 @@ stft8192_r64_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ 
     }
 }
 
-#ifndef BLISS_HOST_EMUL  // everything below (tuning, contraction, launchers) is outside the host emulation
 // ---------------------------------------------------------------------------
 // K4: one CTA per song.  threshold = Midpoint median of the candidate magnitudes
 // (exact radix select on the f64 bit patterns: all values are positive), then the
@@ -508,6 +507,7 @@ stft8192_r64_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ 
 // ---------------------------------------------------------------------------
 constexpr int K4_THREADS = 1024;
 
+#ifndef BLISS_HOST_EMUL  // the previous tuning kernel (partial-mask __match_any_sync) is not part of the host emulation
 __device__ __forceinline__ void hist_add(unsigned int *hist, unsigned int bucket, bool active) {
     // warp-aggregated shared-memory histogram update
     const unsigned int act = __ballot_sync(0xffffffffu, active);
@@ -630,6 +630,7 @@ tuning_kernel(const double *__restrict__ cand_mag, const double *__restrict__ ca
     }
 }
 
+#endif  // BLISS_HOST_EMUL
 // ---------------------------------------------------------------------------
 // K4 (current): same result as tuning_kernel above, four sweeps over the candidates instead of ten.
 //   sweep 0  min / max key  -> the bits every key shares are skipped
@@ -1025,6 +1026,15 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
 constexpr int K5P_STAGES = K5P_STAGES_N;
 constexpr int K5P_PITCH = K5_KT + 4;  // floats per staged row
 
+#ifdef BLISS_HOST_EMUL  // host emulation: the copy happens on the spot (a legal completion time for cp.async)
+inline void cp_async16(void *smem, const void *gmem, int src_bytes) {
+    memset(smem, 0, 16);
+    if (src_bytes > 0) memcpy(smem, gmem, (size_t)src_bytes);
+}
+inline void cp_async_commit() {}
+template <int N>
+inline void cp_async_wait() {}
+#else
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
     const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem);
     // src_bytes < 16: the remainder of the 16 bytes is zero-filled (0: nothing is read)
@@ -1033,13 +1043,18 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+#endif
 
 __global__ void __launch_bounds__(K5_THREADS, K5P_STAGES_N == 3 ? 3 : 2)
 chroma_pipe_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs,
                    const unsigned int *__restrict__ tile_prefix, int n_songs,
                    const float *__restrict__ filt_table, const int *__restrict__ tuning_idx,
                    double *__restrict__ tile_partials /*[tiles][10]*/, double *__restrict__ chroma_dbg) {
+#ifdef BLISS_HOST_EMUL
+    unsigned char *k5p_smem = emu::dynamic_smem();
+#else
     extern __shared__ __align__(16) unsigned char k5p_smem[];
+#endif
     float *s_s = reinterpret_cast<float *>(k5p_smem);                                   // [STAGES][256][PITCH]
     float *s_w = s_s + K5P_STAGES * CH_TILE_FRAMES * K5P_PITCH;                         // [STAGES][16][12]
     double *s_red = reinterpret_cast<double *>(s_w + K5P_STAGES * K5_KT * 12);          // [4][10]
@@ -1152,6 +1167,7 @@ constexpr size_t K5P_SMEM = (size_t)K5P_STAGES * CH_TILE_FRAMES * K5P_PITCH * 4 
                             (K5_THREADS / 32) * 10 * 8;
 
 // ---- launchers ---------------------------------------------------------------
+#ifndef BLISS_HOST_EMUL
 // frame_prefix counts groups of K3_FRAMES_PER_CTA (= 4) frames per song
 int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int *frame_prefix, int n_songs,
                     unsigned int total_frames, const float *hann, const cpx *tw1, const cpx *tw2,

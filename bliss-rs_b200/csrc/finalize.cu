@@ -130,6 +130,7 @@ finalize_kernel(const SongDesc *__restrict__ songs, const float *__restrict__ ce
     store_row(o, dim, out, out_base, peers);
 }
 
+#ifndef BLISS_HOST_EMUL  // tests/cpu_emul/emul_kernels.cpp runs the kernels above on the host
 int launch_finalize(const SongDesc *songs, int n_songs, const float *centroid, const float *rolloff,
                     const float *flatness, const float *loud_ms, const unsigned int *zcr_count,
                     const float *tempo_feature, const double *tile_partials, int version, float *out,
@@ -140,4 +141,5 @@ int launch_finalize(const SongDesc *songs, int n_songs, const float *centroid, c
     return 1;
 }
 
+#endif  // BLISS_HOST_EMUL
 }  // namespace bliss

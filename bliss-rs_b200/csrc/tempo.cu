@@ -488,6 +488,7 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
     }
 }
 
+#ifndef BLISS_HOST_EMUL  // tests/cpu_emul/emul_kernels.cpp runs the kernels above on the host
 int launch_peakpick(const float *flux, const SongDesc *songs, const unsigned int *t_prefix, int n_songs,
                     unsigned int total, float *thr, cudaStream_t st) {
     if (total == 0) return 0;
@@ -509,4 +510,5 @@ int launch_beattrack(const float *thr, const float *block_energy, const SongDesc
     return 1;
 }
 
+#endif  // BLISS_HOST_EMUL
 }  // namespace bliss

@@ -42,9 +42,12 @@ typedef void *cudaStream_t;
 namespace emu {
 struct Fiber {
     ucontext_t ctx;
-    std::vector<char> stack;
     bool done = false;
 };
+constexpr size_t STACK_BYTES = 128 * 1024;  // per CUDA thread; the kernels keep their big arrays in __shared__
+inline std::vector<char> &stack_pool() { static std::vector<char> p; return p; }
+inline std::vector<unsigned char> &dyn_smem_buf() { static std::vector<unsigned char> b; return b; }
+inline unsigned char *dynamic_smem() { return dyn_smem_buf().data(); }  // extern __shared__ of the running CTA
 struct Cta {
     unsigned n = 0;
     std::vector<Fiber> f;
@@ -111,11 +114,14 @@ inline void trampoline() {
     }
     swapcontext(&c->f[me].ctx, &c->sched);
 }
-// kernel<<<grid, block>>>(args...)  ==  emu::launch(grid, block, [&] { kernel(args...); });
-inline void launch(unsigned grid, unsigned block, std::function<void()> body) {
-    gdim().x = grid;
+// kernel<<<grid, block, dyn_smem>>>(args...)  ==  emu::launch(grid, block, [&] { kernel(args...); }, dyn_smem);
+inline void launch(dim3 grid, unsigned block, std::function<void()> body, size_t dyn_smem = 0) {
+    gdim() = grid;
     bdim().x = block;
-    for (unsigned b = 0; b < grid; b++) {
+    if (stack_pool().size() < (size_t)block * STACK_BYTES) stack_pool().resize((size_t)block * STACK_BYTES);
+    if (dyn_smem_buf().size() < dyn_smem + 16) dyn_smem_buf().resize(dyn_smem + 16);
+    for (unsigned by = 0; by < grid.y; by++)
+    for (unsigned b = 0; b < grid.x; b++) {
         Cta c;
         c.n = block;
         c.f.resize(block);
@@ -129,12 +135,12 @@ inline void launch(unsigned grid, unsigned block, std::function<void()> body) {
         c.body = body;
         cta() = &c;
         bid().x = b;
+        bid().y = by;
         for (unsigned t = 0; t < block; t++) {
             Fiber &f = c.f[t];
-            f.stack.resize(256 * 1024);
             getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = f.stack.data();
-            f.ctx.uc_stack.ss_size = f.stack.size();
+            f.ctx.uc_stack.ss_sp = stack_pool().data() + (size_t)t * STACK_BYTES;
+            f.ctx.uc_stack.ss_size = STACK_BYTES;
             f.ctx.uc_link = &c.sched;
             makecontext(&f.ctx, (void (*)())trampoline, 0);
         }
@@ -153,6 +159,11 @@ inline void launch(unsigned grid, unsigned block, std::function<void()> body) {
         }
         cta() = nullptr;
     }
+}
+inline void launch(unsigned grid, unsigned block, std::function<void()> body, size_t dyn_smem = 0) {
+    dim3 g;
+    g.x = grid;
+    launch(g, block, std::move(body), dyn_smem);
 }
 
 template <class T>
@@ -247,11 +258,20 @@ inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+inline void __threadfence_block() {}
 inline void __threadfence() {}
 inline void __threadfence_system() {}
 inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }  // one OS thread
 inline int atomicAdd(int *p, int v) { const int o = *p; *p = o + v; return o; }
 inline unsigned atomicExch(unsigned *p, unsigned v) { const unsigned o = *p; *p = v; return o; }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+inline float atomicAdd(float *p, float v) { const float o = *p; *p = o + v; return o; }
+inline unsigned atomicMin(unsigned *p, unsigned v) { const unsigned o = *p; if (v < o) *p = v; return o; }
+inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (v < o) *p = v; return o; }
+inline unsigned atomicMax(unsigned *p, unsigned v) { const unsigned o = *p; if (v > o) *p = v; return o; }
+inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
 // CUDA's global min / max overloads
 template <class T> inline T min(T a, T b) { return b < a ? b : a; }
 template <class T> inline T max(T a, T b) { return a < b ? b : a; }

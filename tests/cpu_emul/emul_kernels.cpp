@@ -4,7 +4,7 @@
 // the experimental kernel cuts (BLISS_B200_VARIANT bits) with the measured kernels.
 //
 //   g++ -std=c++17 -O1 -ffp-contract=off -DBLISS_HOST_EMUL -I tests/cpu_emul/cuda_on_cpu emul_kernels.cpp
-//   ./emul_kernels song.f32 out_dir
+//   ./emul_kernels song.f32 out_dir [full]
 //
 // TEST INFRASTRUCTURE.  The kernels are compiled unmodified: the .cu files are #included, their launchers
 // (<<< >>>) and the kernels outside this emulation are compiled out by BLISS_HOST_EMUL, inline PTX has host
@@ -16,6 +16,8 @@
 #include "../../bliss-rs_b200/csrc/spectral.cu"
 #include "../../bliss-rs_b200/csrc/wave_setup.cu"
 #include "../../bliss-rs_b200/csrc/chroma.cu"
+#include "../../bliss-rs_b200/csrc/tempo.cu"
+#include "../../bliss-rs_b200/csrc/finalize.cu"
 
 using namespace bliss;
 
@@ -31,8 +33,9 @@ static void dump(const char *name, const std::vector<T> &v) {
 }
 
 int main(int argc, char **argv) {
-    if (argc < 3) { fprintf(stderr, "usage: %s song.f32 out_dir\n", argv[0]); return 2; }
+    if (argc < 3) { fprintf(stderr, "usage: %s song.f32 out_dir [full]\n", argv[0]); return 2; }
     g_out = argv[2];
+    const bool stages = !(argc > 3 && std::string(argv[3]) == "full");  // "full": only the whole-path runs at the end
     std::vector<float> x;
     {
         FILE *f = fopen(argv[1], "rb");
@@ -99,6 +102,7 @@ int main(int argc, char **argv) {
     const unsigned items = (sd.n_t + ppi - 1) / ppi;
     const std::vector<unsigned> item_prefix = {0u, items};
     auto run_pvoc = [&](const char *tag, auto kern) {
+        if (!stages) return;
         std::vector<float> cen(sd.n_s, -7.f), rol(sd.n_s, -7.f), fla(sd.n_s, -7.f), flux(sd.n_t, -7.f);
         emu::launch((items + 7) / 8, 256, [&] {
             kern(x.data(), songs.data(), item_prefix.data(), 1, items, ppi, tab, cen.data(), rol.data(), fla.data(),
@@ -116,7 +120,7 @@ int main(int argc, char **argv) {
     run_pvoc("v3584", pvoc512_kernel<true, false, true, true, 4>);
 
     // ---- STFT micro-benchmark kernels ----------------------------------------------------------------------
-    {
+    if (stages) {
         std::vector<float> mags((size_t)sd.n_t * 257, -7.f);
         emu::launch((items + 7) / 8, 256, [&] {
             pvoc512_kernel<false, true>(x.data(), songs.data(), item_prefix.data(), 1, items, ppi, tab, nullptr, nullptr,
@@ -134,7 +138,7 @@ int main(int argc, char **argv) {
     }
 
     // ---- timedomain_kernel ---------------------------------------------------------------------------------
-    {
+    if (stages) {
         const unsigned groups = (sd.n_l + 7) / 8;
         const std::vector<unsigned> gp = {0u, groups};
         std::vector<float> loud(sd.n_l, -7.f), eb(n / 256 + 1, -7.f);
@@ -147,7 +151,7 @@ int main(int argc, char **argv) {
     }
 
     // ---- pcm_to_mono_kernel: the song as 16-bit stereo (L = x, R = x / 2), 32-bit mono, 3-channel float -----
-    {
+    if (stages) {
         const size_t frames = (n + 3) / 4 * 4;
         std::vector<short> st(2 * frames, 0);
         std::vector<int> s32(frames, 0);
@@ -175,7 +179,7 @@ int main(int argc, char **argv) {
     }
 
     // ---- stft8192_kernel: the measured build and the experimental cuts ---------------------------------------
-    {
+    if (stages) {
         const unsigned ctas = (sd.n_c_comp + K3_FRAMES_PER_CTA - 1) / K3_FRAMES_PER_CTA;
         const std::vector<unsigned> fp = {0u, ctas};
         auto run_stft = [&](const char *tag, auto kern) {
@@ -204,6 +208,78 @@ int main(int argc, char **argv) {
         run_stft("v4096", stft8192_kernel<true, K3V_LAY16>);
         run_stft("v4288", stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN | K3V_LAY16>);
         run_stft("old_epilogue", stft8192_kernel<false>);
+    }
+    // ---- the whole path, kernel after kernel as run_wave (api.cu) enqueues them: 23 features ------------------
+    {
+        std::vector<double> table((size_t)100 * CH_BINS * 12, 0.);  // only the row of the estimated tuning is filled
+        std::vector<float> table32(table.size(), 0.f);
+        auto full = [&](const char *tag, auto pvoc_kern, auto stft_kern) {
+            // tempo / timbral chain
+            const unsigned groups = (sd.n_l + 7) / 8;
+            const std::vector<unsigned> gp = {0u, groups}, tp = {0u, sd.n_t};
+            std::vector<float> loud(sd.n_l, 0.f), eb(n / 256 + 1, 0.f), cen(sd.n_s), rol(sd.n_s), fla(sd.n_s), flux(sd.n_t),
+                thr(sd.n_t), bpm(sd.n_t / 16 + 16, 0.f), tempo(1, 0.f);
+            std::vector<unsigned> zcr(1, 0u), nbpm(1, 0u);
+            emu::launch((groups + 7) / 8, 256, [&] {
+                timedomain_kernel(x.data(), songs.data(), gp.data(), 1, groups, loud.data(), eb.data(), zcr.data());
+            });
+            emu::launch((items + 7) / 8, 256, [&] {
+                pvoc_kern(x.data(), songs.data(), item_prefix.data(), 1, items, ppi, tab, cen.data(), rol.data(), fla.data(),
+                          flux.data(), nullptr);
+            });
+            emu::launch((sd.n_t + 255) / 256, 256, [&] { peakpick_kernel(flux.data(), songs.data(), tp.data(), 1, sd.n_t, thr.data()); });
+            emu::launch(1, 128, [&] {
+                beattrack_kernel<128>(thr.data(), eb.data(), songs.data(), bpm.data(), tempo.data(), nbpm.data(), 0);
+            });
+            // chroma chain
+            const unsigned ctas = (sd.n_c_comp + K3_FRAMES_PER_CTA - 1) / K3_FRAMES_PER_CTA;
+            const std::vector<unsigned> fp = {0u, ctas};
+            std::vector<float> mags(((size_t)sd.n_c_comp + CH_TILE_FRAMES) * CH_STRIDE, 0.f);
+            std::vector<double> cm((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.), cp((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.);
+            std::vector<unsigned> cc(1, 0u);
+            emu::launch(ctas, K3_THREADS, [&] {
+                stft_kern(x.data(), songs.data(), fp.data(), 1, hann.data(), tw4.data(), tw2.data(), tw8.data(), mags.data(),
+                          cm.data(), cp.data(), cc.data());
+            });
+            std::vector<int> tuning(1, -1);
+            emu::launch(1, K4_THREADS, [&] { tuning_select_kernel(cm.data(), cp.data(), cc.data(), songs.data(), tuning.data()); });
+            if (tuning[0] < 0 || tuning[0] > 99) { printf("tuning index %d\n", tuning[0]); exit(3); }
+            {   // the filterbank of that tuning (chroma_filter_table_kernel computes row blockIdx.y of the table)
+                dim3 grid;
+                grid.x = (CH_BINS + 127) / 128;
+                emu::bid().y = 0;
+                for (unsigned bx = 0; bx < grid.x; bx++) {  // one row only: blockIdx.y is set by hand
+                    emu::launch(1, 128, [&] {
+                        emu::bid().x = bx;
+                        emu::bid().y = (unsigned)tuning[0];
+                        chroma_filter_table_kernel(table.data());
+                    });
+                }
+                emu::bid().y = 0;
+                const size_t lo = (size_t)tuning[0] * CH_BINS * 12;
+                for (size_t i = lo; i < lo + (size_t)CH_BINS * 12; i++) table32[i] = (float)table[i];  // f64_to_f32_kernel
+            }
+            const unsigned tiles = (sd.n_c + CH_TILE_FRAMES - 1) / CH_TILE_FRAMES;
+            const std::vector<unsigned> tlp = {0u, tiles};
+            std::vector<double> partials((size_t)tiles * 10, 0.);
+            emu::launch(tiles, K5_THREADS, [&] {
+                chroma_pipe_kernel(mags.data(), songs.data(), tlp.data(), 1, table32.data(), tuning.data(), partials.data(), nullptr);
+            }, K5P_SMEM);
+            // summary
+            PeerRows peers;
+            memset(&peers, 0, sizeof(peers));
+            std::vector<float> out(24, 0.f);
+            emu::launch(1, K9_THREADS, [&] {
+                finalize_kernel(songs.data(), cen.data(), rol.data(), fla.data(), loud.data(), zcr.data(), tempo.data(),
+                                partials.data(), 2, out.data(), 0u, peers);
+            });
+            out.resize(23);
+            dump((std::string("features_") + tag).c_str(), out);
+            std::vector<float> misc = {(float)tuning[0], (float)nbpm[0], tempo[0]};
+            dump((std::string("misc_") + tag).c_str(), misc);
+        };
+        full("default", pvoc512_kernel<true, false>, stft8192_kernel<true>);
+        full("all_cuts", pvoc512_kernel<true, false, true, true, 4>, stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN | K3V_LAY16>);
     }
     printf("n %u n_s %u n_t %u n_c %u n_c_comp %u n_l %u\nOK\n", n, sd.n_s, sd.n_t, sd.n_c, sd.n_c_comp, sd.n_l);
     return 0;

@@ -109,6 +109,37 @@ def test_fft_index_logic_on_host(tmp_path):
     assert "OK" in out.stdout
 
 
+def _build_kernel_emulation(tmp_path):
+    exe = str(tmp_path / "emul_kernels")
+    here = os.path.join(ROOT, "tests", "cpu_emul")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DBLISS_HOST_EMUL", "-I",
+                           os.path.join(here, "cuda_on_cpu"), "-o", exe, os.path.join(here, "emul_kernels.cpp")])
+    return exe
+
+
+def test_kernel_sources_reproduce_the_reference_golden_vector(tmp_path, golden):
+    """The whole path -- timedomain, pvoc512, peakpick, beattrack, stft8192, tuning_select, chroma_filter_table,
+    chroma_pipe, finalize: the kernels' own source, launched in run_wave's order by tests/cpu_emul/emul_kernels.cpp on
+    the host (cuda_on_cpu) -- on the reference's golden clip: its 23 expected values (src/song/mod.rs:553-580) within
+    the reference's own 1e-5, once with the measured kernels and once with every experimental cut switched on."""
+    from oracle import oracle as O
+    exe = _build_kernel_emulation(tmp_path)
+    x = golden["pcm_s16_mono"].astype(np.float32) / np.float32(32768.0)
+    song = str(tmp_path / "song.f32")
+    x.tofile(song)
+    out = subprocess.run([exe, song, str(tmp_path), "full"], capture_output=True, text=True)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+    rc, want = O.analyze(x, 2)
+    assert rc == 0
+    for tag in ("default", "all_cuts"):
+        f = np.fromfile(str(tmp_path / ("features_" + tag)), np.float32)
+        tuning_idx, n_bpm, tempo = np.fromfile(str(tmp_path / ("misc_" + tag)), np.float32)
+        assert f.shape == (23,)
+        assert np.abs(f - golden["expected_analysis_v2"]).max() < 1e-5, (tag, f)
+        assert np.abs(f - want).max() < 1e-5, (tag, np.abs(f - want).max())
+        assert int(tuning_idx) == 45 and n_bpm > 0 and abs(tempo - want[0]) < 1e-6  # tuning -0.05 (src/chroma.rs:657-665)
+
+
 def test_kernel_sources_run_on_the_host(tmp_path, golden):
     """tests/cpu_emul/emul_kernels.cpp: the SOURCE of pvoc512_kernel, stft512_pairs_kernel, timedomain_kernel,
     pcm_to_mono_kernel and stft8192_kernel -- the measured builds and every experimental BLISS_B200_VARIANT cut --
@@ -118,10 +149,7 @@ def test_kernel_sources_run_on_the_host(tmp_path, golden):
     bit-identical to the measured kernels (the host has no FMA contraction and an IEEE sqrt, so this says the
     variants compute the same thing, not what the device rounds to)."""
     from oracle import oracle as O
-    exe = str(tmp_path / "emul_kernels")
-    here = os.path.join(ROOT, "tests", "cpu_emul")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DBLISS_HOST_EMUL", "-I",
-                           os.path.join(here, "cuda_on_cpu"), "-o", exe, os.path.join(here, "emul_kernels.cpp")])
+    exe = _build_kernel_emulation(tmp_path)
     x = (golden["pcm_s16_mono"][20000:60000].astype(np.float32) / np.float32(32768.0)).copy()
     x[15000:16500] = 0.0
     song = str(tmp_path / "song.f32")
@@ -173,6 +201,11 @@ def test_kernel_sources_run_on_the_host(tmp_path, golden):
         assert int(ld("peaks_" + tag, np.uint32)[0]) == p.size, tag
         assert np.abs(ld("peak_pitches_" + tag, np.float64) - np.sort(p)).max() < 1e-3, tag
     assert same_bits(ld("stft8192_v4096"), ld("stft8192_default"))       # addresses only
+    # ---- and the whole path on this clip (too short for a beat: tempo = -1, src/temporal.rs:66-77)
+    rc, feats = O.analyze(x, 2)
+    for tag in ("default", "all_cuts"):
+        got = ld("features_" + tag)
+        assert rc == 0 and got.shape == (23,) and np.abs(got - feats).max() < 1e-5, tag
 
 
 def test_stft_pair_kernel_design_on_host(tmp_path):
