@@ -629,9 +629,22 @@ int bliss_b200_init(int device) {
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&g.ev_begin, cudaEventDisableTiming));
+    // BLISS_B200_STREAM_PRIORITY (experiment, unmeasured; default 0 = both chains at the same priority):
+    //   1 = the tempo / timbral chain's stream is preferred by the block scheduler: pvoc512 finishes first and the
+    //       latency-bound beat tracker runs under the rest of the chroma STFT instead of at the end of the step
+    //   2 = the chroma chain's stream is preferred: stft8192 finishes first, tuning and the HBM-bound contraction
+    //       run under the issue-bound pvoc512
+    int prio_main = 0, prio_side = 0;
+    if (const char *e = getenv("BLISS_B200_STREAM_PRIORITY")) {
+        int lo = 0, hi = 0;  // numerically lower = higher priority
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const int mode = atoi(e);
+        if (mode == 1) { prio_main = hi; prio_side = lo; }
+        if (mode == 2) { prio_main = lo; prio_side = hi; }
+    }
     for (auto &S : g.ws) {
-        CK(cudaStreamCreateWithFlags(&S.main, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&S.side, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithPriority(&S.main, cudaStreamNonBlocking, prio_main));
+        CK(cudaStreamCreateWithPriority(&S.side, cudaStreamNonBlocking, prio_side));
         CK(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));

@@ -23,6 +23,11 @@ for v in 0 64 128 4096 4288 512 1024 2048 3584 7872; do
   extra="--no-cpu-baseline"; [ $v = 0 ] && extra=""; [ $v = 7872 ] && extra=""   # parity against the oracle for the default and for everything on
   BLISS_B200_VARIANT=$v timeout 400 python bench.py --steps 5 --warmup 3 $extra > gpurun_out/ab_v$v.json 2> gpurun_out/ab_v$v.err; echo "VARIANT $v exit $?"; summ gpurun_out/ab_v$v.json
 done
+# stream priorities between the two chains of a wave (api.cu, BLISS_B200_STREAM_PRIORITY): 1 = tempo / timbral chain
+# first, 2 = chroma chain first
+for pr in 1 2; do
+  BLISS_B200_STREAM_PRIORITY=$pr timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ab_prio$pr.json 2> gpurun_out/ab_prio$pr.err; echo "PRIORITY $pr exit $?"; summ gpurun_out/ab_prio$pr.json
+done
 for v in 0 256; do
   BLISS_B200_VARIANT=$v timeout 300 python bench_stft.py --tracks 4000 --resident 1000 --cufft > gpurun_out/ab_stft_v$v.json 2> gpurun_out/ab_stft_v$v.err; echo "STFT VARIANT $v exit $?"; cut -c1-400 gpurun_out/ab_stft_v$v.json
 done
