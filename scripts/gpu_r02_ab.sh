@@ -28,6 +28,11 @@ done
 for pr in 1 2; do
   BLISS_B200_STREAM_PRIORITY=$pr timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ab_prio$pr.json 2> gpurun_out/ab_prio$pr.err; echo "PRIORITY $pr exit $?"; summ gpurun_out/ab_prio$pr.json
 done
+# sub-waves of a resident batch (BLISS_B200_WAVE_SONGS): the HBM-bound contraction of one sub-wave under the SM-bound
+# FFT kernels of the next (measured flat with the first-half kernels; the contraction has changed since)
+for ws in 512 256; do
+  BLISS_B200_WAVE_SONGS=$ws timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ab_wave$ws.json 2> gpurun_out/ab_wave$ws.err; echo "WAVE_SONGS $ws exit $?"; summ gpurun_out/ab_wave$ws.json
+done
 for v in 0 256; do
   BLISS_B200_VARIANT=$v timeout 300 python bench_stft.py --tracks 4000 --resident 1000 --cufft > gpurun_out/ab_stft_v$v.json 2> gpurun_out/ab_stft_v$v.err; echo "STFT VARIANT $v exit $?"; cut -c1-400 gpurun_out/ab_stft_v$v.json
 done
