@@ -8,7 +8,9 @@
 // playlist.rs:1009-1108) hold bit for bit.  The direct (a-b)^2 form is kept on
 // purpose: the GEMM form |a|^2+|b|^2-2ab cancels for the near-duplicates that
 // dedup_playlist thresholds at 0.05 (playlist.rs:381-382).
+#ifndef BLISS_HOST_EMUL  // tests/cpu_emul/emul_distance.cpp runs the kernels below on the host (no CUB, no <<< >>>)
 #include <cub/device/device_radix_sort.cuh>
+#endif
 
 #include "common.cuh"
 
@@ -189,6 +191,7 @@ nearest_alive_kernel(const float *__restrict__ cur, unsigned int n_cur, const fl
 }
 
 // ---- launchers ---------------------------------------------------------------
+#ifndef BLISS_HOST_EMUL
 int launch_distance_matrix(const float *rows, unsigned int n_rows, const float *cols, unsigned int n_cols,
                            int dim, int mode, const float *w_or_m, float *out, cudaStream_t st) {
     if (n_rows == 0 || n_cols == 0) return 0;
@@ -234,4 +237,5 @@ int launch_nearest_alive(const float *cur, unsigned int n_cur, const float *cand
     return 1;
 }
 
+#endif  // BLISS_HOST_EMUL
 }  // namespace bliss

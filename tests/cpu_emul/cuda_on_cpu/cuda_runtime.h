@@ -255,6 +255,8 @@ inline double __longlong_as_double(long long l) { return emu::unbits<double>(emu
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fsqrt_rn(float a) { return sqrtf(a); }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }

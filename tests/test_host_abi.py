@@ -140,6 +140,53 @@ def test_kernel_sources_reproduce_the_reference_golden_vector(tmp_path, golden):
         assert int(tuning_idx) == 45 and n_bpm > 0 and abs(tempo - want[0]) < 1e-6  # tuning -0.05 (src/chroma.rs:657-665)
 
 
+def test_distance_kernel_sources_are_bit_exact_on_the_host(tmp_path):
+    """tests/cpu_emul/emul_distance.cpp: distance_matrix_kernel<23|20>, the generic kernel, seed_distance_kernel +
+    key packing and nearest_alive_kernel of distance.cu run on the host (cuda_on_cpu).  These kernels spell their
+    f32 order out (__fmul_rn / __fadd_rn, ndarray's unrolled_dot), so every distance and both playlist orders --
+    ties between exact duplicates included -- must equal the oracle BIT FOR BIT (src/playlist.rs:65-142, 256-326)."""
+    from oracle import oracle as O
+    exe = str(tmp_path / "emul_distance")
+    here = os.path.join(ROOT, "tests", "cpu_emul")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DBLISS_HOST_EMUL", "-I",
+                           os.path.join(here, "cuda_on_cpu"), "-o", exe, os.path.join(here, "emul_distance.cpp")])
+    rng = np.random.default_rng(3)
+    for dim in (23, 20, 7):
+        n, n_seeds = 70, 2
+        rows = (rng.random((n, dim), dtype=np.float32) * 2 - 1).astype(np.float32)
+        rows[5], rows[11] = rows[9], rows[0]            # exact duplicates: ties in both orderings
+        d = tmp_path / ("dim%d" % dim)
+        d.mkdir()
+        rows.tofile(str(d / "rows.f32"))
+        out = subprocess.run([exe, str(d / "rows.f32"), str(n), str(dim), str(n_seeds), str(d)], capture_output=True, text=True)
+        assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+        def ld(name, t=np.float32):
+            return np.fromfile(str(d / name), t)
+
+        w = np.ones(dim, np.float32)
+        if dim == 23:
+            w[0], w[10:] = 0.25, np.float32(3.0) / np.float32(13.0)  # VERSION2_WEIGHTS, src/lib.rs:209-234
+        M, full = np.diag(w).astype(np.float32), ld("full_matrix").reshape(dim, dim)
+        mw, me, mf, mc = (ld("matrix_" + k).reshape(n, n) for k in ("weights", "euclidean", "full", "cosine"))
+        for i in range(0, n, 7):
+            for j in range(n):
+                a, b = rows[i], rows[j]
+                assert np.float32(O.mahalanobis_distance(a, b, M)) == mw[i, j]
+                assert np.float32(O.euclidean_distance(a, b)) == me[i, j]
+                assert np.float32(O.mahalanobis_distance(a, b, full)) == mf[i, j]
+                c = np.float32(O.cosine_distance(a, b))
+                assert c == mc[i, j] or (np.isnan(c) and np.isnan(mc[i, j]))
+        if dim in (20, 23):  # FeaturesVersion::distance_metric, src/lib.rs:176-178
+            got = mw if dim == 23 else me
+            for i in range(0, n, 9):
+                for j in range(0, n, 3):
+                    assert np.float32(O.default_distance(rows[i], rows[j], 2 if dim == 23 else 1)) == got[i, j]
+        order, keys = O.closest_to_songs(rows[:n_seeds], rows, M)
+        assert np.array_equal(order, ld("closest_order", np.uint32)) and np.array_equal(keys, ld("closest_keys"))
+        assert np.array_equal(O.song_to_song(rows[:n_seeds], rows, M), ld("chain_order", np.uint32))
+
+
 def test_kernel_sources_run_on_the_host(tmp_path, golden):
     """tests/cpu_emul/emul_kernels.cpp: the SOURCE of pvoc512_kernel, stft512_pairs_kernel, timedomain_kernel,
     pcm_to_mono_kernel and stft8192_kernel -- the measured builds and every experimental BLISS_B200_VARIANT cut --
