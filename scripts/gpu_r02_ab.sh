@@ -36,3 +36,8 @@ done
 for v in 0 256; do
   BLISS_B200_VARIANT=$v timeout 300 python bench_stft.py --tracks 4000 --resident 1000 --cufft > gpurun_out/ab_stft_v$v.json 2> gpurun_out/ab_stft_v$v.err; echo "STFT VARIANT $v exit $?"; cut -c1-400 gpurun_out/ab_stft_v$v.json
 done
+# one full ncu capture of the two FFT kernels with every cut on (compare with profiles/ncu_r01b_full_128songs.md:
+# data-pipe wavefronts, bank conflicts, issue slots) and of the STFT pair kernel
+BLISS_B200_VARIANT=7872 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"pvoc512_kernel|stft8192_kernel" -c 2 -o gpurun_out/ab_prof_v7872 python bench.py --steps 1 --warmup 0 --songs-per-gpu 128 --no-cpu-baseline > gpurun_out/ab_ncu_v7872.log 2>&1; echo NCU_EXIT $?
+BLISS_B200_VARIANT=256 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"stft512_pairs_kernel" -c 1 -o gpurun_out/ab_prof_stft_v256 python bench_stft.py --tracks 128 --resident 128 --warmup 0 > gpurun_out/ab_ncu_stft_v256.log 2>&1; echo NCU_STFT_EXIT $?
+ls -la gpurun_out | grep " ab_"
