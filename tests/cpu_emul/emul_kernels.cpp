@@ -4,7 +4,7 @@
 // the experimental kernel cuts (BLISS_B200_VARIANT bits) with the measured kernels.
 //
 //   g++ -std=c++17 -O1 -ffp-contract=off -DBLISS_HOST_EMUL -I tests/cpu_emul/cuda_on_cpu emul_kernels.cpp
-//   ./emul_kernels song.f32 out_dir [full]
+//   ./emul_kernels song.f32 out_dir [full | batch n1 n2 ...]
 //
 // TEST INFRASTRUCTURE.  The kernels are compiled unmodified: the .cu files are #included, their launchers
 // (<<< >>>) and the kernels outside this emulation are compiled out by BLISS_HOST_EMUL, inline PTX has host
@@ -35,7 +35,8 @@ static void dump(const char *name, const std::vector<T> &v) {
 int main(int argc, char **argv) {
     if (argc < 3) { fprintf(stderr, "usage: %s song.f32 out_dir [full]\n", argv[0]); return 2; }
     g_out = argv[2];
-    const bool stages = !(argc > 3 && std::string(argv[3]) == "full");  // "full": only the whole-path runs at the end
+    const bool batch_mode = argc > 3 && std::string(argv[3]) == "batch";
+    const bool stages = !(argc > 3 && (std::string(argv[3]) == "full" || batch_mode));  // "full": only the whole-path runs
     std::vector<float> x;
     {
         FILE *f = fopen(argv[1], "rb");
@@ -278,8 +279,97 @@ int main(int argc, char **argv) {
             std::vector<float> misc = {(float)tuning[0], (float)nbpm[0], tempo[0]};
             dump((std::string("misc_") + tag).c_str(), misc);
         };
-        full("default", pvoc512_kernel<true, false>, stft8192_kernel<true>);
-        full("all_cuts", pvoc512_kernel<true, false, true, true, 4>, stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN | K3V_LAY16>);
+        if (!batch_mode) full("default", pvoc512_kernel<true, false>, stft8192_kernel<true>);
+        if (!batch_mode) full("all_cuts", pvoc512_kernel<true, false, true, true, 4>, stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN | K3V_LAY16>);
+    }
+    // ---- a ragged batch: "batch n1 n2 ..." cuts the file into consecutive songs (4-sample aligned starts, a too short
+    //      one allowed) and runs the whole path over all of them at once, descriptors and prefix arrays laid out as
+    //      plan_wave (api.cu) lays them out: song lookup, item boundaries and per-song offsets of every kernel ----------
+    if (argc > 4 && std::string(argv[3]) == "batch") {
+        std::vector<SongDesc> bs;
+        std::vector<unsigned> k1p(1, 0u), chp(1, 0u), tpp(1, 0u), prp(1, 0u), tlp(1, 0u);
+        size_t off = 0, rows = 0, cands = 0, ns = 0, nt = 0, nl = 0, neb = 0, tiles = 0, bpms = 0;
+        const int bppi = 16;
+        for (int a = 4; a < argc; a++) {
+            const unsigned len = (unsigned)atoi(argv[a]);
+            SongDesc d;
+            memset(&d, 0, sizeof(d));
+            d.pcm_off = off;
+            d.n = len;
+            d.valid = len >= (unsigned)MIN_SAMPLES ? 1u : 0u;
+            unsigned q_ns = 0, q_nt = 0, q_nc = 0, q_ncc = 0, q_nl = 0, q_tiles = 0;
+            if (d.valid) {
+                q_ns = (len - 512) / 128 + 1;
+                q_nt = (len - 512) / 256 + 1;
+                q_nc = (unsigned)ceilf((float)len / 2205.f);
+                q_ncc = std::min(q_nc, len / 2205 + 1);
+                q_nl = (len + 1023) / 1024;
+                q_tiles = (q_nc + CH_TILE_FRAMES - 1) / CH_TILE_FRAMES;
+                d.n_s = q_ns; d.n_t = q_nt; d.n_c = q_nc; d.n_c_comp = q_ncc; d.n_l = q_nl;
+            }
+            d.mag_off = rows; d.cand_off = cands;
+            d.s_off = (unsigned)ns; d.t_off = (unsigned)nt; d.l_off = (unsigned)nl; d.e_off = (unsigned)neb;
+            d.c_tile_off = (unsigned)tiles; d.bpm_off = (unsigned)bpms;
+            k1p.push_back(k1p.back() + (d.valid ? (q_nt + bppi - 1) / bppi : 0));
+            chp.push_back(chp.back() + (d.valid ? (q_nl + 7) / 8 : 0));
+            tpp.push_back(tpp.back() + q_nt);
+            prp.push_back(prp.back() + (d.valid ? (q_ncc + 3) / 4 : 0));
+            tlp.push_back(tlp.back() + q_tiles);
+            if (d.valid) {
+                rows += q_ncc; cands += (size_t)q_ncc * CH_MAX_PEAKS; ns += q_ns; nt += q_nt; nl += q_nl; neb += len / 256;
+                tiles += q_tiles; bpms += q_nt / 16 + 16;
+            }
+            bs.push_back(d);
+            off += (len + 3) / 4 * 4;
+        }
+        if (off > n + 8) { fprintf(stderr, "batch longer than the file\n"); return 2; }
+        const int k = (int)bs.size();
+        std::vector<double> table((size_t)100 * CH_BINS * 12, 0.);
+        std::vector<float> table32(table.size(), 0.f);
+        auto batch = [&](const char *tag, auto pvoc_kern, auto stft_kern) {
+            std::vector<float> loud(nl + 1, 0.f), eb(neb + 1, 0.f), cen(ns + 1), rol(ns + 1), fla(ns + 1), flux(nt + 1), thr(nt + 1),
+                bpm(bpms + 1, 0.f), tempo(k, 0.f), mags((rows + CH_TILE_FRAMES) * CH_STRIDE, 0.f), out((size_t)k * 23, 0.f);
+            std::vector<unsigned> zcr(k, 0u), nbpm(k, 0u), cc(k, 0u);
+            std::vector<double> cm(cands + 1, 0.), cp(cands + 1, 0.), partials(tiles * 10 + 10, 0.);
+            std::vector<int> tuning(k, 0);
+            emu::launch((chp[k] + 7) / 8, 256, [&] { timedomain_kernel(x.data(), bs.data(), chp.data(), k, chp[k], loud.data(), eb.data(), zcr.data()); });
+            emu::launch((k1p[k] + 7) / 8, 256, [&] {
+                pvoc_kern(x.data(), bs.data(), k1p.data(), k, k1p[k], bppi, tab, cen.data(), rol.data(), fla.data(), flux.data(), nullptr);
+            });
+            emu::launch((tpp[k] + 255) / 256, 256, [&] { peakpick_kernel(flux.data(), bs.data(), tpp.data(), k, tpp[k], thr.data()); });
+            emu::launch((unsigned)k, 128, [&] { beattrack_kernel<128>(thr.data(), eb.data(), bs.data(), bpm.data(), tempo.data(), nbpm.data(), 0); });
+            emu::launch(prp[k], K3_THREADS, [&] {
+                stft_kern(x.data(), bs.data(), prp.data(), k, hann.data(), tw4.data(), tw2.data(), tw8.data(), mags.data(), cm.data(),
+                          cp.data(), cc.data());
+            });
+            emu::launch((unsigned)k, K4_THREADS, [&] { tuning_select_kernel(cm.data(), cp.data(), cc.data(), bs.data(), tuning.data()); });
+            for (int i = 0; i < k; i++) {
+                if (!bs[i].valid) continue;
+                for (unsigned bx = 0; bx < (CH_BINS + 127) / 128; bx++)
+                    emu::launch(1, 128, [&] {
+                        emu::bid().x = bx;
+                        emu::bid().y = (unsigned)tuning[i];
+                        chroma_filter_table_kernel(table.data());
+                    });
+                emu::bid().y = 0;
+                const size_t lo = (size_t)tuning[i] * CH_BINS * 12;
+                for (size_t e = lo; e < lo + (size_t)CH_BINS * 12; e++) table32[e] = (float)table[e];
+            }
+            emu::launch(tlp[k], K5_THREADS, [&] {
+                chroma_pipe_kernel(mags.data(), bs.data(), tlp.data(), k, table32.data(), tuning.data(), partials.data(), nullptr);
+            }, K5P_SMEM);
+            PeerRows peers;
+            memset(&peers, 0, sizeof(peers));
+            emu::launch((unsigned)k, K9_THREADS, [&] {
+                finalize_kernel(bs.data(), cen.data(), rol.data(), fla.data(), loud.data(), zcr.data(), tempo.data(), partials.data(), 2,
+                                out.data(), 0u, peers);
+            });
+            dump((std::string("batch_features_") + tag).c_str(), out);
+        };
+        batch("default", pvoc512_kernel<true, false>, stft8192_kernel<true>);
+        batch("all_cuts", pvoc512_kernel<true, false, true, true, 4>, stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN | K3V_LAY16>);
+        printf("batch of %d songs\nOK\n", k);
+        return 0;
     }
     printf("n %u n_s %u n_t %u n_c %u n_c_comp %u n_l %u\nOK\n", n, sd.n_s, sd.n_t, sd.n_c, sd.n_c_comp, sd.n_l);
     return 0;

@@ -187,6 +187,31 @@ def test_distance_kernel_sources_are_bit_exact_on_the_host(tmp_path):
         assert np.array_equal(O.song_to_song(rows[:n_seeds], rows, M), ld("chain_order", np.uint32))
 
 
+def test_kernel_sources_on_a_ragged_batch(tmp_path, golden):
+    """The whole path over five songs at once -- ragged lengths, one too short (status 1, src/song/mod.rs:417-430),
+    one of exactly 8192 samples -- with descriptors and prefix arrays laid out as plan_wave (api.cu) lays them out:
+    song lookup, item boundaries and the per-song offsets of every kernel, on the host, against the oracle; measured
+    kernels and all experimental cuts."""
+    from oracle import oracle as O
+    exe = _build_kernel_emulation(tmp_path)
+    a = golden["pcm_s16_mono"].astype(np.float32) / np.float32(32768.0)
+    b = golden["pcm_piano"].astype(np.float32) / np.float32(32768.0)
+    songs = [a[:90001], b[:5000], b[:70003], a[100000:100000 + 8192], a[50000:50000 + 33333]]
+    flat = np.concatenate([np.pad(x, (0, (-len(x)) % 4)) for x in songs]).astype(np.float32)
+    path = str(tmp_path / "batch.f32")
+    flat.tofile(path)
+    out = subprocess.run([exe, path, str(tmp_path), "batch"] + [str(len(x)) for x in songs], capture_output=True, text=True)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+    for tag in ("default", "all_cuts"):
+        f = np.fromfile(str(tmp_path / ("batch_features_" + tag)), np.float32).reshape(len(songs), 23)
+        for i, x in enumerate(songs):
+            rc, want = O.analyze(x, 2)
+            if rc == 0:
+                assert np.abs(f[i] - want).max() < 1e-5, (tag, i, np.abs(f[i] - want).max())
+            else:
+                assert rc == 1 and (f[i] == 0).all()  # the row of a rejected song is left alone
+
+
 def test_kernel_sources_run_on_the_host(tmp_path, golden):
     """tests/cpu_emul/emul_kernels.cpp: the SOURCE of pvoc512_kernel, stft512_pairs_kernel, timedomain_kernel,
     pcm_to_mono_kernel and stft8192_kernel -- the measured builds and every experimental BLISS_B200_VARIANT cut --
