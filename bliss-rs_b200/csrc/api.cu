@@ -505,7 +505,7 @@ int build_tables() {
             twA[k1 * 32 + l] = cpx{(float)cos(a), (float)sin(a)};
         }
     // periodic Hann of utils::stft (utils.rs:36-38)
-    std::vector<float> hann(8192 + 4 * 256);
+    std::vector<float> hann(2 * (8192 + 4 * 256));
     for (int i = 0; i < 8192; i++) hann[i] = 0.5f - 0.5f * cosf(2.f * (float)i * PI_F / 8192.f);
     // behind the window: per-thread phase (cos e, cos o, sin e, sin o) of samples 2 tid, 2 tid + 1 for the
     // synthesised-window variant of stft8192_kernel (VARIANT_WINSYN, rfft8192.cuh hann_pair)
@@ -515,6 +515,16 @@ int build_tables() {
         hann[8192 + 4 * t + 1] = (float)cos(to);
         hann[8192 + 4 * t + 2] = (float)sin(te);
         hann[8192 + 4 * t + 3] = (float)sin(to);
+    }
+    // ... and both once more for the frame rotated by one sample (VARIANT_ODDSHIFT, chroma.cu): the window read as
+    // hann[(m + 8191) % 8192], the phase of samples 2 tid - 1 and 2 tid
+    for (int m = 0; m < 8192; m++) hann[9216 + m] = hann[(m + 8191) % 8192];
+    for (int t = 0; t < 256; t++) {
+        const double ta = 2.0 * M_PI * (double)(2 * t - 1) / 8192.0, tb = 2.0 * M_PI * (double)(2 * t) / 8192.0;
+        hann[17408 + 4 * t + 0] = (float)cos(ta);
+        hann[17408 + 4 * t + 1] = (float)cos(tb);
+        hann[17408 + 4 * t + 2] = (float)sin(ta);
+        hann[17408 + 4 * t + 3] = (float)sin(tb);
     }
     // pass-1 twiddles [k1][b] = W4096^(b k1), pass-2 twiddles [k2][j] = W256^(j k2), and W8192^t, t < 256
     // (real-FFT untangling): rfft8192.cuh

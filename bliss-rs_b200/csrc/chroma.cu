@@ -119,6 +119,14 @@ __device__ __forceinline__ void epilogue_pairs(const cpx (&v)[16], const cpx *pm
 constexpr int K3V_TWPROD = 1;  // pass-1 and pass-2 twiddles: 4 loads + 11 products instead of 15 loads each (rfft8192.cuh)
 constexpr int K3V_WINSYN = 2;  // Hann pairs from the thread's phase instead of 16 window loads
 constexpr int K3V_LAY16 = 4;   // column-group pitch 16 instead of 17 in the FFT buffer: conflict-free mirror loads (rfft8192.cuh)
+// Frames that start on an odd sample (hop 2205 is odd: every second one) cannot load (x[2n], x[2n+1]) as one aligned
+// 64-bit pair.  K3V_ODDSHIFT transforms the frame rotated by one sample instead, y'[m] = y[(m - 1) mod 8192]: its
+// pairs (y[2n-1], y[2n]) ARE aligned, |DFT(y')| = |DFT(y)| (a circular shift is a phase factor), and the only
+// element that wraps is the first (y'[0] = y[8191], thread 0).  The window is read from a copy rotated the same way.
+constexpr int K3V_ODDSHIFT = 8;
+constexpr int K3_HANN_PHASE = CH_WIN;                 // float4[256] behind the window (api.cu build_tables)
+constexpr int K3_HANN_SHIFT = CH_WIN + 1024;          // hann[(m + 8191) % 8192]
+constexpr int K3_HANN_SHIFT_PHASE = 2 * CH_WIN + 1024;  // float4[256]: phase of samples 2 tid - 1, 2 tid
 
 template <int Q>
 __device__ __forceinline__ void window_synth(cpx (&v)[16], cpx cw, cpx sw) {
@@ -174,7 +182,7 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
         const float2 *ph = reinterpret_cast<const float2 *>(hann) + tid;
         if constexpr ((VAR & K3V_WINSYN) != 0) {
             // samples only; the window comes from the thread's phase entry behind the 8192 window values
-            const float4 pw = __ldg(reinterpret_cast<const float4 *>(hann + CH_WIN) + tid);
+            float4 pw = __ldg(reinterpret_cast<const float4 *>(hann + K3_HANN_PHASE) + tid);
             if (interior) {
                 const float *pa = x + s0 + 2 * tid;
                 if ((reinterpret_cast<size_t>(pa) & 7) == 0) {
@@ -184,6 +192,15 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
                         const float2 xx = __ldg(pa2 + 256 * q);
                         v[q] = cpx{xx.x, xx.y};
                     }
+                } else if constexpr ((VAR & K3V_ODDSHIFT) != 0) {
+                    const float2 *pa2 = reinterpret_cast<const float2 *>(pa - 1);  // pa is 4 mod 8: pa - 1 is aligned
+                    pw = __ldg(reinterpret_cast<const float4 *>(hann + K3_HANN_SHIFT_PHASE) + tid);
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        const float2 xx = __ldg(pa2 + 256 * q);
+                        v[q] = cpx{xx.x, xx.y};
+                    }
+                    if (tid == 0) v[0].x = __ldg(x + s0 + 8191);  // y'[0] = y[8191]
                 } else {
 #pragma unroll
                     for (int q = 0; q < 16; q++) v[q] = cpx{__ldg(pa + 512 * q), __ldg(pa + 512 * q + 1)};
@@ -204,6 +221,16 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
                 for (int q = 0; q < 16; q++) {
                     const float2 w = __ldg(ph + 256 * q);
                     const float2 xx = __ldg(pa2 + 256 * q);
+                    v[q] = pmul(cpx{xx.x, xx.y}, cpx{w.x, w.y});
+                }
+            } else if constexpr ((VAR & K3V_ODDSHIFT) != 0) {
+                const float2 *pa2 = reinterpret_cast<const float2 *>(pa - 1);  // pa is 4 mod 8: pa - 1 is aligned
+                const float2 *phs = reinterpret_cast<const float2 *>(hann + K3_HANN_SHIFT) + tid;
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const float2 w = __ldg(phs + 256 * q);
+                    float2 xx = __ldg(pa2 + 256 * q);
+                    if (q == 0 && tid == 0) xx.x = __ldg(x + s0 + 8191);  // y'[0] = y[8191]
                     v[q] = pmul(cpx{xx.x, xx.y}, cpx{w.x, w.y});
                 }
             } else {
@@ -1186,7 +1213,7 @@ int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int 
                                                       cand_mag, cand_pitch, cand_count);
         };
         const int var = ((variant & VARIANT_TWPROD) ? K3V_TWPROD : 0) | ((variant & VARIANT_WINSYN) ? K3V_WINSYN : 0) |
-                        ((variant & VARIANT_LAY16) ? K3V_LAY16 : 0);
+                        ((variant & VARIANT_LAY16) ? K3V_LAY16 : 0) | ((variant & VARIANT_ODDSHIFT) ? K3V_ODDSHIFT : 0);
         switch (var) {
             case 1: go(stft8192_kernel<true, 1>); break;
             case 2: go(stft8192_kernel<true, 2>); break;
@@ -1195,7 +1222,14 @@ int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int 
             case 5: go(stft8192_kernel<true, 5>); break;
             case 6: go(stft8192_kernel<true, 6>); break;
             case 7: go(stft8192_kernel<true, 7>); break;
-            default: go(stft8192_kernel<true>); break;
+            case 8: go(stft8192_kernel<true, 8>); break;
+            case 12: go(stft8192_kernel<true, 12>); break;
+            case 15: go(stft8192_kernel<true, 15>); break;
+            default:
+                if (var == 0) go(stft8192_kernel<true>);
+                else if (var & K3V_ODDSHIFT) go(stft8192_kernel<true, 15>);  // other mixes with bit 8192: everything on
+                else go(stft8192_kernel<true, 7>);
+                break;
         }
     }
     return 1;

@@ -61,7 +61,8 @@ int bliss_b200_set_workspace_limit(uint64_t bytes);
  * the default yet: 64 product twiddles, 128 synthesised Hann window in pass 1 of the 8192-point FFT, 256 hop-256
  * frame pairs in the STFT micro-benchmark, 512 product twiddles in the 512-point FFT, 1024 pair-wise descriptor
  * reductions + MUFU-only magnitudes and 2048 a conflict-free tile padding in the same kernel,
- * 4096 a conflict-free FFT-buffer layout in the 8192-point kernel (bliss-rs_b200/csrc/common.cuh).  0 = the current kernels.  Returns the previous mask; BLISS_B200_VARIANT in the environment sets the
+ * 4096 a conflict-free FFT-buffer layout and 8192 aligned loads for odd-start frames in the 8192-point kernel
+ * (bliss-rs_b200/csrc/common.cuh).  0 = the current kernels.  Returns the previous mask; BLISS_B200_VARIANT in the environment sets the
  * initial one.  Used by the A/B timings in profiles/ and by the test that all implementations agree. */
 int bliss_b200_set_variant(int mask);
 

@@ -5,7 +5,8 @@
 # masks: 64 stft8192 product twiddles | 128 stft8192 synthesised window | 512 pvoc512 product twiddles |
 #        1024 pvoc512 pair descriptors + MUFU-only magnitudes | 2048 pvoc512 conflict-free tile padding |
 #        4096 stft8192 conflict-free buffer layout | 256 STFT micro-benchmark pair kernel
-#        (4288 = all stft8192 cuts, 3584 = all pvoc512 cuts, 7872 = everything)
+#        8192 stft8192 aligned loads for odd-start frames
+#        (12480 = all stft8192 cuts, 3584 = all pvoc512 cuts, 16064 = everything)
 mkdir -p gpurun_out; cd $GRAFT_REPO_ROOT
 nvidia-smi -L; nproc
 timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -s > gpurun_out/ab_tests.log 2>&1; echo TEST_EXIT $?; tail -6 gpurun_out/ab_tests.log | cut -c1-300
@@ -19,8 +20,8 @@ except Exception as e:
     print(sys.argv[1], 'unreadable', e)
 PY
 }
-for v in 0 64 128 4096 4288 512 1024 2048 3584 7872; do
-  extra="--no-cpu-baseline"; [ $v = 0 ] && extra=""; [ $v = 7872 ] && extra=""   # parity against the oracle for the default and for everything on
+for v in 0 64 128 4096 8192 12480 512 1024 2048 3584 16064; do
+  extra="--no-cpu-baseline"; [ $v = 0 ] && extra=""; [ $v = 16064 ] && extra=""   # parity against the oracle for the default and for everything on
   BLISS_B200_VARIANT=$v timeout 400 python bench.py --steps 5 --warmup 3 $extra > gpurun_out/ab_v$v.json 2> gpurun_out/ab_v$v.err; echo "VARIANT $v exit $?"; summ gpurun_out/ab_v$v.json
 done
 # stream priorities between the two chains of a wave (api.cu, BLISS_B200_STREAM_PRIORITY): 1 = tempo / timbral chain
@@ -38,6 +39,6 @@ for v in 0 256; do
 done
 # one full ncu capture of the two FFT kernels with every cut on (compare with profiles/ncu_r01b_full_128songs.md:
 # data-pipe wavefronts, bank conflicts, issue slots) and of the STFT pair kernel
-BLISS_B200_VARIANT=7872 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"pvoc512_kernel|stft8192_kernel" -c 2 -o gpurun_out/ab_prof_v7872 python bench.py --steps 1 --warmup 0 --songs-per-gpu 128 --no-cpu-baseline > gpurun_out/ab_ncu_v7872.log 2>&1; echo NCU_EXIT $?
+BLISS_B200_VARIANT=16064 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"pvoc512_kernel|stft8192_kernel" -c 2 -o gpurun_out/ab_prof_v16064 python bench.py --steps 1 --warmup 0 --songs-per-gpu 128 --no-cpu-baseline > gpurun_out/ab_ncu_v16064.log 2>&1; echo NCU_EXIT $?
 BLISS_B200_VARIANT=256 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"stft512_pairs_kernel" -c 1 -o gpurun_out/ab_prof_stft_v256 python bench_stft.py --tracks 128 --resident 128 --warmup 0 > gpurun_out/ab_ncu_stft_v256.log 2>&1; echo NCU_STFT_EXIT $?
 ls -la gpurun_out | grep " ab_"

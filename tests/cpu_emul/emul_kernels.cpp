@@ -73,7 +73,7 @@ int main(int argc, char **argv) {
             twA[k1 * 32 + l] = cpx{(float)cos(a), (float)sin(a)};
         }
     PvocTables tab{win.data(), twA.data()};
-    std::vector<float> hann(8192 + 4 * 256);
+    std::vector<float> hann(2 * (8192 + 4 * 256));
     for (int i = 0; i < 8192; i++) hann[i] = 0.5f - 0.5f * cosf(2.f * (float)i * PI_F / 8192.f);
     for (int t = 0; t < 256; t++) {
         const double te = 2.0 * M_PI * (double)(2 * t) / 8192.0, to = 2.0 * M_PI * (double)(2 * t + 1) / 8192.0;
@@ -81,6 +81,14 @@ int main(int argc, char **argv) {
         hann[8192 + 4 * t + 1] = (float)cos(to);
         hann[8192 + 4 * t + 2] = (float)sin(te);
         hann[8192 + 4 * t + 3] = (float)sin(to);
+    }
+    for (int m = 0; m < 8192; m++) hann[9216 + m] = hann[(m + 8191) % 8192];
+    for (int t = 0; t < 256; t++) {
+        const double ta = 2.0 * M_PI * (double)(2 * t - 1) / 8192.0, tb = 2.0 * M_PI * (double)(2 * t) / 8192.0;
+        hann[17408 + 4 * t + 0] = (float)cos(ta);
+        hann[17408 + 4 * t + 1] = (float)cos(tb);
+        hann[17408 + 4 * t + 2] = (float)sin(ta);
+        hann[17408 + 4 * t + 3] = (float)sin(tb);
     }
     std::vector<cpx> tw4(4096), tw2(256), tw8(256);
     for (int k1 = 0; k1 < 16; k1++)
@@ -208,6 +216,8 @@ int main(int argc, char **argv) {
         run_stft("v128", stft8192_kernel<true, K3V_WINSYN>);
         run_stft("v4096", stft8192_kernel<true, K3V_LAY16>);
         run_stft("v4288", stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN | K3V_LAY16>);
+        run_stft("v8192", stft8192_kernel<true, K3V_ODDSHIFT>);
+        run_stft("v12480", stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN | K3V_LAY16 | K3V_ODDSHIFT>);
         run_stft("old_epilogue", stft8192_kernel<false>);
     }
     // ---- the whole path, kernel after kernel as run_wave (api.cu) enqueues them: 23 features ------------------
@@ -280,7 +290,7 @@ int main(int argc, char **argv) {
             dump((std::string("misc_") + tag).c_str(), misc);
         };
         if (!batch_mode) full("default", pvoc512_kernel<true, false>, stft8192_kernel<true>);
-        if (!batch_mode) full("all_cuts", pvoc512_kernel<true, false, true, true, 4>, stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN | K3V_LAY16>);
+        if (!batch_mode) full("all_cuts", pvoc512_kernel<true, false, true, true, 4>, stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN | K3V_LAY16 | K3V_ODDSHIFT>);
     }
     // ---- a ragged batch: "batch n1 n2 ..." cuts the file into consecutive songs (4-sample aligned starts, a too short
     //      one allowed) and runs the whole path over all of them at once, descriptors and prefix arrays laid out as
@@ -367,7 +377,7 @@ int main(int argc, char **argv) {
             dump((std::string("batch_features_") + tag).c_str(), out);
         };
         batch("default", pvoc512_kernel<true, false>, stft8192_kernel<true>);
-        batch("all_cuts", pvoc512_kernel<true, false, true, true, 4>, stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN | K3V_LAY16>);
+        batch("all_cuts", pvoc512_kernel<true, false, true, true, 4>, stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN | K3V_LAY16 | K3V_ODDSHIFT>);
         printf("batch of %d songs\nOK\n", k);
         return 0;
     }

@@ -659,3 +659,26 @@ def test_experimental_fft8192_buffer_layout_is_bit_identical(pcm_song, pcm_piano
         assert np.array_equal(taps["stft8192"], taps0["stft8192"])
     finally:
         B.native.set_variant(0)
+
+
+@experimental
+def test_experimental_odd_frame_rotation(pcm_song, pcm_piano):
+    """BLISS_B200_VARIANT bit 8192: chroma frames that start on an odd sample (every second one: the hop is 2205) are
+    transformed rotated by one sample, which makes their sample pairs aligned 64-bit loads; |DFT| is unchanged by a
+    circular shift, so only rounding moves: magnitudes within 2e-6 of the oracle, features within 1e-5 of the
+    measured kernel, nothing outside the chroma features touched."""
+    songs = [pcm_song, pcm_piano] + [synth.gen_track(83, i, 22050 * 20 + 67 * i, device="cuda").cpu().numpy() for i in range(4)]
+    try:
+        B.native.set_variant(0)
+        st0, f0 = B.native.analyze_batch(songs, 2)
+        for mask in (8192, 8192 | 4096 | 128 | 64):
+            B.native.set_variant(mask)
+            st, f = B.native.analyze_batch(songs, 2)
+            assert (st == 0).all() and np.abs(f - f0).max() < 1e-5, (mask, np.abs(f - f0).max(0))
+            assert np.array_equal(f[:, :10], f0[:, :10])
+        B.native.set_variant(8192)
+        _, _, taps = B.native.analyze_taps(pcm_piano, 2)
+        S = O.stft(pcm_piano, 8192, 2205)
+        assert np.abs(taps["stft8192"].T - S).max() / S.max() < 2e-6
+    finally:
+        B.native.set_variant(0)

@@ -266,13 +266,16 @@ def test_kernel_sources_run_on_the_host(tmp_path, golden):
     # ---- stft8192_kernel and its cuts: magnitudes + pip-track candidates
     S = O.stft(x, 8192, 2205)
     p, _ = O.pip_track(S, 8192)
-    for tag in ("default", "v64", "v128", "v4096", "v4288", "old_epilogue"):
+    for tag in ("default", "v64", "v128", "v4096", "v4288", "v8192", "v12480", "old_epilogue"):
         g = ld("stft8192_" + tag).reshape(-1, 4097)
         assert g.T.shape == S.shape and (g >= 0).all(), tag
         assert np.abs(g.T - S).max() / S.max() < 2e-6, tag
         assert int(ld("peaks_" + tag, np.uint32)[0]) == p.size, tag
         assert np.abs(ld("peak_pitches_" + tag, np.float64) - np.sort(p)).max() < 1e-3, tag
     assert same_bits(ld("stft8192_v4096"), ld("stft8192_default"))       # addresses only
+    g0, g8 = ld("stft8192_default").reshape(-1, 4097), ld("stft8192_v8192").reshape(-1, 4097)
+    changed = np.nonzero((g0 != g8).any(1))[0]  # the rotated transform touches interior frames that start on an odd sample only
+    assert len(changed) > 0 and all((2205 * int(f) - 4096) % 2 == 1 and 2205 * int(f) - 4096 >= 0 for f in changed)
     # ---- and the whole path on this clip (too short for a beat: tempo = -1, src/temporal.rs:66-77)
     rc, feats = O.analyze(x, 2)
     for tag in ("default", "all_cuts"):
@@ -414,7 +417,7 @@ def test_variant_mask_names_match_header():
     """BLISS_B200_VARIANT bits (A/B switch back to a kernel's previous implementation) stay documented."""
     txt = open(os.path.join(ROOT, "bliss-rs_b200", "csrc", "common.cuh")).read()
     for name in ("VARIANT_OLD_EPILOGUE = 1", "VARIANT_OLD_TUNING = 2", "VARIANT_OLD_CHROMA = 4", "VARIANT_OLD_ACF = 8",
-                 "VARIANT_BT512 = 16", "VARIANT_R64 = 32", "VARIANT_TWPROD = 64", "VARIANT_WINSYN = 128", "VARIANT_STFT_PAIRS = 256", "VARIANT_PV_TWPROD = 512", "VARIANT_PV_PAIRDESC = 1024", "VARIANT_PV_ZPOS4 = 2048", "VARIANT_LAY16 = 4096"):
+                 "VARIANT_BT512 = 16", "VARIANT_R64 = 32", "VARIANT_TWPROD = 64", "VARIANT_WINSYN = 128", "VARIANT_STFT_PAIRS = 256", "VARIANT_PV_TWPROD = 512", "VARIANT_PV_PAIRDESC = 1024", "VARIANT_PV_ZPOS4 = 2048", "VARIANT_LAY16 = 4096", "VARIANT_ODDSHIFT = 8192"):
         assert name in txt
 
 
