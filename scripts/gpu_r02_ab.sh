@@ -1,7 +1,7 @@
 # round-2 opener (1 GPU): GPU tests (incl. the experimental kernel cuts written blind at the end of round 1),
 # then the same bench line once per BLISS_B200_VARIANT mask so that every cut is A/B-timed on one box, then the
 # STFT micro-benchmark with and without the hop-256 pair kernel.  Everything lands in gpurun_out/.
-#   gpurun --timeout 1500 -- 'bash scripts/gpu_r02_ab.sh'
+#   gpurun --timeout 2400 -- 'bash scripts/gpu_r02_ab.sh'      (15 bench lines of about a minute each + tests + two ncu captures)
 # masks: 64 stft8192 product twiddles | 128 stft8192 synthesised window | 512 pvoc512 product twiddles |
 #        1024 pvoc512 pair descriptors + MUFU-only magnitudes | 2048 pvoc512 conflict-free tile padding |
 #        4096 stft8192 conflict-free buffer layout | 256 STFT micro-benchmark pair kernel
