@@ -14,7 +14,11 @@ constexpr int PV_HOP_TEMPO = 256;         // temporal.rs:41
 constexpr int CH_WIN = 8192;              // chroma.rs:39
 constexpr int CH_HOP = 2205;              // chroma.rs:74
 constexpr int CH_BINS = 4097;
-constexpr int CH_STRIDE = 4104;           // padded row of the magnitude spill (16 B aligned rows)
+#ifndef BLISS_CH_STRIDE
+#define BLISS_CH_STRIDE 4104  // -DBLISS_CH_STRIDE=4128 (scripts/build_variants.py): rows aligned to 128-byte lines
+#endif
+constexpr int CH_STRIDE = BLISS_CH_STRIDE;  // padded row of the magnitude spill (16 B aligned rows)
+static_assert(CH_STRIDE >= 4100 && CH_STRIDE % 4 == 0, "a row holds 4097 magnitudes, 16-byte aligned");
 constexpr int CH_TILE_FRAMES = 256;      // chroma frames per CTA of chroma_kernel (2 per thread)
 constexpr int CH_MAX_PEAKS = 714;         // max local maxima among centre bins 57..1483
 constexpr int LOUD_WIN = 1024;            // misc.rs:44

@@ -14,6 +14,9 @@ BASE = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17
 
 VARIANTS = {
     "nopacked": ["-DBLISS_NO_PACKED_FP"],  # scalar FADD/FMUL/FFMA butterflies instead of the f32x2 forms
+    # magnitude-spill rows on 128-byte lines (each low-half row store of stft8192_kernel spans
+    # two lines with the 4104-float pitch); unmeasured
+    "stride4128": ["-DBLISS_CH_STRIDE=4128"],
 }
 
 

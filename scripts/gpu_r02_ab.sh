@@ -34,6 +34,10 @@ done
 for ws in 512 256; do
   BLISS_B200_WAVE_SONGS=$ws timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ab_wave$ws.json 2> gpurun_out/ab_wave$ws.err; echo "WAVE_SONGS $ws exit $?"; summ gpurun_out/ab_wave$ws.json
 done
+# magnitude-spill rows on 128-byte lines: a separate build (python scripts/build_variants.py BEFORE the gpurun call)
+if [ -f bliss-rs_b200/variants/libbliss_b200_stride4128.so ]; then
+  BLISS_B200_SO=$PWD/bliss-rs_b200/variants/libbliss_b200_stride4128.so timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ab_stride4128.json 2> gpurun_out/ab_stride4128.err; echo "STRIDE 4128 exit $?"; summ gpurun_out/ab_stride4128.json
+fi
 for v in 0 256; do
   BLISS_B200_VARIANT=$v timeout 300 python bench_stft.py --tracks 4000 --resident 1000 --cufft > gpurun_out/ab_stft_v$v.json 2> gpurun_out/ab_stft_v$v.err; echo "STFT VARIANT $v exit $?"; cut -c1-400 gpurun_out/ab_stft_v$v.json
 done
