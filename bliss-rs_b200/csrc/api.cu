@@ -665,6 +665,10 @@ int bliss_b200_init(int device) {
     g.ws_limit = (size_t)((double)total_b * 0.40);
     g.variant = 0;
     if (const char *e = getenv("BLISS_B200_VARIANT")) g.variant = atoi(e);
+#ifdef BLISS_HOST_EMUL
+    fprintf(stderr, "[bliss_b200] HOST-EMULATED TEST BUILD (tests/cpu_emul): kernels run on the CPU, thread by thread. "
+                    "Not a product path -- the product library is built by nvcc and needs a B200.\n");
+#endif
     int rc = build_tables();
     if (rc) return rc;
     g.inited = true;

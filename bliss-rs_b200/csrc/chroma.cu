@@ -61,15 +61,13 @@ __global__ void f64_to_f32_kernel(const double *__restrict__ in, float *__restri
 }
 
 // builds the f64 table (chroma.rs:197-267 as written) and the f32 copy chroma_kernel multiplies with
-#ifndef BLISS_HOST_EMUL  // tests/cpu_emul/emul_kernels.cpp compiles this file's STFT kernels with g++ (no <<< >>>, no PTX)
 int launch_chroma_filter_table(double *table, float *table32, cudaStream_t st) {
     dim3 grid((CH_BINS + 127) / 128, 100);
-    chroma_filter_table_kernel<<<grid, 128, 0, st>>>(table);
+    BLISS_LAUNCH(chroma_filter_table_kernel, grid, 128, 0, st, table);
     const size_t n = (size_t)100 * CH_BINS * 12;
-    f64_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(table, table32, n);
+    BLISS_LAUNCH(f64_to_f32_kernel, (unsigned)((n + 255) / 256), 256, 0, st, table, table32, n);
     return 2;
 }
-#endif
 
 // ---------------------------------------------------------------------------
 // K3: one CTA (256 threads) per chroma frame: 8192-point real FFT as a 4096-point complex FFT
@@ -1194,7 +1192,6 @@ constexpr size_t K5P_SMEM = (size_t)K5P_STAGES * CH_TILE_FRAMES * K5P_PITCH * 4 
                             (K5_THREADS / 32) * 10 * 8;
 
 // ---- launchers ---------------------------------------------------------------
-#ifndef BLISS_HOST_EMUL
 // frame_prefix counts groups of K3_FRAMES_PER_CTA (= 4) frames per song
 int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int *frame_prefix, int n_songs,
                     unsigned int total_frames, const float *hann, const cpx *tw1, const cpx *tw2,
@@ -1202,14 +1199,14 @@ int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int 
                     unsigned int *cand_count, int variant, cudaStream_t st) {
     if (total_frames == 0) return 0;
     if (variant & VARIANT_R64)
-        stft8192_r64_kernel<<<total_frames, K3R_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw64, tw8192,
+        BLISS_LAUNCH(stft8192_r64_kernel, total_frames, K3R_THREADS, 0, st, pcm, songs, frame_prefix, n_songs, hann, tw64, tw8192,
                                                                  mags, cand_mag, cand_pitch, cand_count);
     else if (variant & VARIANT_OLD_EPILOGUE)
-        stft8192_kernel<false><<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw1, tw2,
+        BLISS_LAUNCH(stft8192_kernel<false>, total_frames, K3_THREADS, 0, st, pcm, songs, frame_prefix, n_songs, hann, tw1, tw2,
                                                                     tw8192, mags, cand_mag, cand_pitch, cand_count);
     else {
         auto go = [&](auto kern) {
-            kern<<<total_frames, K3_THREADS, 0, st>>>(pcm, songs, frame_prefix, n_songs, hann, tw1, tw2, tw8192, mags,
+            BLISS_LAUNCH(kern, total_frames, K3_THREADS, 0, st, pcm, songs, frame_prefix, n_songs, hann, tw1, tw2, tw8192, mags,
                                                       cand_mag, cand_pitch, cand_count);
         };
         const int var = ((variant & VARIANT_TWPROD) ? K3V_TWPROD : 0) | ((variant & VARIANT_WINSYN) ? K3V_WINSYN : 0) |
@@ -1238,10 +1235,12 @@ int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int 
 int launch_tuning(const double *cand_mag, const double *cand_pitch, const unsigned int *cand_count,
                   const SongDesc *songs, int n_songs, int *tuning_idx, int variant, cudaStream_t st) {
     if (n_songs == 0) return 0;
+#ifndef BLISS_HOST_EMUL  // (the previous kernel's partial-mask __match_any_sync is not modelled by the host emulation)
     if (variant & VARIANT_OLD_TUNING)
-        tuning_kernel<<<n_songs, K4_THREADS, 0, st>>>(cand_mag, cand_pitch, cand_count, songs, tuning_idx);
+        BLISS_LAUNCH(tuning_kernel, n_songs, K4_THREADS, 0, st, cand_mag, cand_pitch, cand_count, songs, tuning_idx);
     else
-        tuning_select_kernel<<<n_songs, K4_THREADS, 0, st>>>(cand_mag, cand_pitch, cand_count, songs, tuning_idx);
+#endif
+        BLISS_LAUNCH(tuning_select_kernel, n_songs, K4_THREADS, 0, st, cand_mag, cand_pitch, cand_count, songs, tuning_idx);
     return 1;
 }
 
@@ -1250,7 +1249,7 @@ int launch_chroma(const float *mags, const SongDesc *songs, const unsigned int *
                   double *tile_partials, double *chroma_dbg, int variant, cudaStream_t st) {
     if (total_tiles == 0) return 0;
     if (variant & VARIANT_OLD_CHROMA) {
-        chroma_kernel<<<total_tiles, K5_THREADS, 0, st>>>(mags, songs, tile_prefix, n_songs, filt_table,
+        BLISS_LAUNCH(chroma_kernel, total_tiles, K5_THREADS, 0, st, mags, songs, tile_prefix, n_songs, filt_table,
                                                          tuning_idx, tile_partials, chroma_dbg);
     } else {
         static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in (per device, once)
@@ -1259,11 +1258,10 @@ int launch_chroma(const float *mags, const SongDesc *songs, const unsigned int *
                 return -1;
             attr_set = true;
         }
-        chroma_pipe_kernel<<<total_tiles, K5_THREADS, K5P_SMEM, st>>>(mags, songs, tile_prefix, n_songs, filt_table,
+        BLISS_LAUNCH(chroma_pipe_kernel, total_tiles, K5_THREADS, K5P_SMEM, st, mags, songs, tile_prefix, n_songs, filt_table,
                                                                      tuning_idx, tile_partials, chroma_dbg);
     }
     return 1;
 }
-#endif  // BLISS_HOST_EMUL
 
 }  // namespace bliss

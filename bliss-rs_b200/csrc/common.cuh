@@ -5,6 +5,17 @@
 
 #include "fft_regs.cuh"
 
+// Kernel launches go through one macro.  In the product build (nvcc) it IS the launch statement.  Under
+// BLISS_HOST_EMUL -- defined only by the CPU test-suite's host emulation (tests/cpu_emul: g++ against a stub
+// cuda_runtime.h), never by bliss-rs_b200/_build.py -- it runs the kernel's source on the host, thread by thread,
+// at the point of the call.  There is no CPU path in the product: bliss_b200_init fails without a device.
+#ifdef BLISS_HOST_EMUL
+#define BLISS_LAUNCH(kern, grid, block, smem, stream, ...) \
+    emu::launch(emu::as_dim3(grid), (unsigned)(block), [=] { kern(__VA_ARGS__); }, (size_t)(smem))
+#else
+#define BLISS_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 namespace bliss {
 
 constexpr int SAMPLE_RATE = 22050;        // src/lib.rs:143

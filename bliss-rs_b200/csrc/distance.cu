@@ -191,14 +191,13 @@ nearest_alive_kernel(const float *__restrict__ cur, unsigned int n_cur, const fl
 }
 
 // ---- launchers ---------------------------------------------------------------
-#ifndef BLISS_HOST_EMUL
 int launch_distance_matrix(const float *rows, unsigned int n_rows, const float *cols, unsigned int n_cols,
                            int dim, int mode, const float *w_or_m, float *out, cudaStream_t st) {
     if (n_rows == 0 || n_cols == 0) return 0;
     dim3 grid((n_cols + 255u) / 256u, (n_rows + 31u) / 32u);
-    if (dim == 23) distance_matrix_kernel<23><<<grid, 128, 0, st>>>(rows, n_rows, cols, n_cols, mode, w_or_m, out);
-    else if (dim == 20) distance_matrix_kernel<20><<<grid, 128, 0, st>>>(rows, n_rows, cols, n_cols, mode, w_or_m, out);
-    else if (dim <= MAX_DIM) distance_matrix_generic_kernel<<<dim3((n_cols + 255u) / 256u, n_rows), 256, 0, st>>>(rows, n_rows, cols, n_cols, dim, mode, w_or_m, out);
+    if (dim == 23) BLISS_LAUNCH(distance_matrix_kernel<23>, grid, 128, 0, st, rows, n_rows, cols, n_cols, mode, w_or_m, out);
+    else if (dim == 20) BLISS_LAUNCH(distance_matrix_kernel<20>, grid, 128, 0, st, rows, n_rows, cols, n_cols, mode, w_or_m, out);
+    else if (dim <= MAX_DIM) BLISS_LAUNCH(distance_matrix_generic_kernel, dim3((n_cols + 255u) / 256u, n_rows), 256, 0, st, rows, n_rows, cols, n_cols, dim, mode, w_or_m, out);
     else return -1;
     return 1;
 }
@@ -206,7 +205,7 @@ int launch_distance_matrix(const float *rows, unsigned int n_rows, const float *
 int launch_seed_distance(const float *seeds, unsigned int n_seeds, const float *cands, unsigned int n_cands,
                          int dim, int mode, const float *w_or_m, float *keys, cudaStream_t st) {
     if (n_cands == 0) return 0;
-    seed_distance_kernel<<<(n_cands + 255u) / 256u, 256, 0, st>>>(seeds, n_seeds, cands, n_cands, dim, mode,
+    BLISS_LAUNCH(seed_distance_kernel, (n_cands + 255u) / 256u, 256, 0, st, seeds, n_seeds, cands, n_cands, dim, mode,
                                                                   w_or_m, keys);
     return 1;
 }
@@ -214,8 +213,12 @@ int launch_seed_distance(const float *seeds, unsigned int n_seeds, const float *
 // stable ascending order of keys -> order[]; tmp buffers supplied by the caller
 size_t sort_temp_bytes(unsigned int n) {
     size_t bytes = 0;
+#ifdef BLISS_HOST_EMUL
+    bytes = 16 + (size_t)n;  // host emulation: std::sort stands in for the device radix sort, no scratch needed
+#else
     cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const unsigned long long *)nullptr,
                                    (unsigned long long *)nullptr, (int)n);
+#endif
     return bytes;
 }
 
@@ -223,19 +226,24 @@ int launch_stable_argsort(const float *keys, unsigned int n, unsigned long long 
                           unsigned long long *k_out, void *tmp, size_t tmp_bytes, unsigned int *order,
                           cudaStream_t st) {
     if (n == 0) return 0;
-    make_sort_keys_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(keys, n, k_in);
+    BLISS_LAUNCH(make_sort_keys_kernel, (n + 255u) / 256u, 256, 0, st, keys, n, k_in);
+#ifdef BLISS_HOST_EMUL
+    (void)tmp; (void)tmp_bytes;
+    std::copy(k_in, k_in + n, k_out);
+    std::sort(k_out, k_out + n);  // the keys carry the index in their low half: any correct sort gives the stable order
+#else
     cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, k_in, k_out, (int)n, 0, 64, st);
-    unpack_order_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(k_out, n, order);
+#endif
+    BLISS_LAUNCH(unpack_order_kernel, (n + 255u) / 256u, 256, 0, st, k_out, n, order);
     return 3;
 }
 
 int launch_nearest_alive(const float *cur, unsigned int n_cur, const float *cands, unsigned int n_cands,
                          int dim, int mode, const float *w_or_m, unsigned char *alive, unsigned int *order,
                          unsigned int step, float *next_cur, cudaStream_t st) {
-    nearest_alive_kernel<<<1, 1024, 0, st>>>(cur, n_cur, cands, n_cands, dim, mode, w_or_m, alive, order, step,
+    BLISS_LAUNCH(nearest_alive_kernel, 1, 1024, 0, st, cur, n_cur, cands, n_cands, dim, mode, w_or_m, alive, order, step,
                                              next_cur);
     return 1;
 }
 
-#endif  // BLISS_HOST_EMUL
 }  // namespace bliss

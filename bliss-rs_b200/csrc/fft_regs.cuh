@@ -79,7 +79,8 @@ __device__ __forceinline__ cpx pfma(cpx a, cpx b, cpx c) {  // (a.x * b.x + c.x,
 BLISS_HD cpx padd(cpx a, cpx b) { return cpx{a.x + b.x, a.y + b.y}; }
 BLISS_HD cpx psub(cpx a, cpx b) { return cpx{a.x - b.x, a.y - b.y}; }
 BLISS_HD cpx pmul(cpx a, cpx b) { return cpx{a.x * b.x, a.y * b.y}; }
-BLISS_HD cpx pfma(cpx a, cpx b, cpx c) { return cpx{a.x * b.x + c.x, a.y * b.y + c.y}; }
+// fused, like the FFMA2 it stands in for (host emulation: tests/cpu_emul; nvcc contracts a * b + c into FFMA anyway)
+BLISS_HD cpx pfma(cpx a, cpx b, cpx c) { return cpx{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
 #endif
 
 BLISS_HD cpx cadd(cpx a, cpx b) { return padd(a, b); }

@@ -130,16 +130,14 @@ finalize_kernel(const SongDesc *__restrict__ songs, const float *__restrict__ ce
     store_row(o, dim, out, out_base, peers);
 }
 
-#ifndef BLISS_HOST_EMUL  // tests/cpu_emul/emul_kernels.cpp runs the kernels above on the host
 int launch_finalize(const SongDesc *songs, int n_songs, const float *centroid, const float *rolloff,
                     const float *flatness, const float *loud_ms, const unsigned int *zcr_count,
                     const float *tempo_feature, const double *tile_partials, int version, float *out,
                     unsigned int out_base, const PeerRows &peers, cudaStream_t st) {
     if (n_songs == 0) return 0;
-    finalize_kernel<<<n_songs, K9_THREADS, 0, st>>>(songs, centroid, rolloff, flatness, loud_ms, zcr_count,
+    BLISS_LAUNCH(finalize_kernel, n_songs, K9_THREADS, 0, st, songs, centroid, rolloff, flatness, loud_ms, zcr_count,
                                                     tempo_feature, tile_partials, version, out, out_base, peers);
     return 1;
 }
 
-#endif  // BLISS_HOST_EMUL
 }  // namespace bliss

@@ -605,14 +605,13 @@ timedomain_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
 }
 
 // ---- launchers ---------------------------------------------------------------
-#ifndef BLISS_HOST_EMUL  // tests/cpu_emul/emul_kernels.cpp compiles the kernels above with g++ and runs them on the host
 int launch_pvoc512(const float *pcm, const SongDesc *songs, const unsigned int *item_prefix, int n_songs,
                    unsigned int total_items, int pairs_per_item, PvocTables tab, float *centroid,
                    float *rolloff, float *flatness, float *flux, int variant, cudaStream_t st) {
     if (total_items == 0) return 0;
     const unsigned int grid = (total_items + 7u) / 8u;
     auto go = [&](auto kern) {
-        kern<<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items, pairs_per_item, tab, centroid, rolloff,
+        BLISS_LAUNCH(kern, grid, 256, 0, st, pcm, songs, item_prefix, n_songs, total_items, pairs_per_item, tab, centroid, rolloff,
                                    flatness, flux, nullptr);
     };
     const bool tw = (variant & VARIANT_PV_TWPROD) != 0, pd = (variant & VARIANT_PV_PAIRDESC) != 0,
@@ -637,12 +636,13 @@ int launch_stft512_mags(const float *pcm, const SongDesc *songs, const unsigned 
     if (total_items == 0) return 0;
     const unsigned int grid = (total_items + 7u) / 8u;
     if (variant & VARIANT_STFT_PAIRS) {  // an item's `pairs_per_item` hop-128 pairs are as many hop-256 frames
-        stft512_pairs_kernel<<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items, pairs_per_item, tab, mags);
+        BLISS_LAUNCH(stft512_pairs_kernel, grid, 256, 0, st, pcm, songs, item_prefix, n_songs, total_items, pairs_per_item, tab, mags);
         return 1;
     }
-    pvoc512_kernel<false, true><<<grid, 256, 0, st>>>(pcm, songs, item_prefix, n_songs, total_items,
-                                                      pairs_per_item, tab, nullptr, nullptr, nullptr,
-                                                      nullptr, mags);
+    const auto mags_kernel = pvoc512_kernel<false, true>;  // (a template-id with a comma cannot be a macro argument)
+    float *const none = nullptr;
+    BLISS_LAUNCH(mags_kernel, grid, 256, 0, st, pcm, songs, item_prefix, n_songs, total_items, pairs_per_item, tab, none, none,
+                 none, none, mags);
     return 1;
 }
 
@@ -652,10 +652,9 @@ int launch_timedomain(const float *pcm, const SongDesc *songs, const unsigned in
                       unsigned int *zcr_count, cudaStream_t st) {
     if (total_groups == 0) return 0;
     const unsigned int grid = (total_groups + 7u) / 8u;
-    timedomain_kernel<<<grid, 256, 0, st>>>(pcm, songs, group_prefix, n_songs, total_groups, loud_ms,
+    BLISS_LAUNCH(timedomain_kernel, grid, 256, 0, st, pcm, songs, group_prefix, n_songs, total_groups, loud_ms,
                                             block_energy, zcr_count);
     return 1;
 }
-#endif  // BLISS_HOST_EMUL
 
 }  // namespace bliss

@@ -488,11 +488,10 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
     }
 }
 
-#ifndef BLISS_HOST_EMUL  // tests/cpu_emul/emul_kernels.cpp runs the kernels above on the host
 int launch_peakpick(const float *flux, const SongDesc *songs, const unsigned int *t_prefix, int n_songs,
                     unsigned int total, float *thr, cudaStream_t st) {
     if (total == 0) return 0;
-    peakpick_kernel<<<(total + 255u) / 256u, 256, 0, st>>>(flux, songs, t_prefix, n_songs, total, thr);
+    BLISS_LAUNCH(peakpick_kernel, (total + 255u) / 256u, 256, 0, st, flux, songs, t_prefix, n_songs, total, thr);
     return 1;
 }
 
@@ -502,13 +501,12 @@ int launch_beattrack(const float *thr, const float *block_energy, const SongDesc
     if (n_songs == 0) return 0;
     const int scalar_acf = (variant & VARIANT_OLD_ACF) ? 1 : 0;
     if (variant & VARIANT_BT512)
-        beattrack_kernel<512><<<n_songs, 512, 0, st>>>(thr, block_energy, songs, bpm_list, tempo_feature, bpm_count,
+        BLISS_LAUNCH(beattrack_kernel<512>, n_songs, 512, 0, st, thr, block_energy, songs, bpm_list, tempo_feature, bpm_count,
                                                        scalar_acf);
     else
-        beattrack_kernel<128><<<n_songs, 128, 0, st>>>(thr, block_energy, songs, bpm_list, tempo_feature, bpm_count,
+        BLISS_LAUNCH(beattrack_kernel<128>, n_songs, 128, 0, st, thr, block_energy, songs, bpm_list, tempo_feature, bpm_count,
                                                        scalar_acf);
     return 1;
 }
 
-#endif  // BLISS_HOST_EMUL
 }  // namespace bliss

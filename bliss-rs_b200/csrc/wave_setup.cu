@@ -22,18 +22,16 @@ __global__ void wave_setup_kernel(const uint4 *__restrict__ src_host, uint4 *__r
     }
 }
 
-#ifndef BLISS_HOST_EMUL
 int launch_wave_setup(const void *src_host, void *dst, size_t bytes, unsigned int *zcr_count,
                       unsigned int *cand_count, unsigned int n_songs, cudaStream_t st) {
     const unsigned int n16 = (unsigned int)((bytes + 15) / 16);
     const unsigned int n = n16 > n_songs ? n16 : n_songs;
     if (n == 0) return 0;
-    wave_setup_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(reinterpret_cast<const uint4 *>(src_host),
+    BLISS_LAUNCH(wave_setup_kernel, (n + 255u) / 256u, 256, 0, st, reinterpret_cast<const uint4 *>(src_host),
                                                          reinterpret_cast<uint4 *>(dst), n16, zcr_count, cand_count,
                                                          n_songs);
     return 1;
 }
-#endif
 
 // ---- s16 -> f32 (bliss_b200_analyze_batch_s16) ----------------------------------------------------------
 // What the reference's decoder does to signed 16-bit mono 22 050 Hz material before Song::analyze sees it:
@@ -60,14 +58,12 @@ s16_to_f32_kernel(const short *__restrict__ in, float *__restrict__ out, size_t 
     }
 }
 
-#ifndef BLISS_HOST_EMUL
 int launch_s16_to_f32(const short *in, float *out, size_t n, cudaStream_t st) {
     if (n == 0) return 0;
     const size_t threads = (n + 7) / 8;
-    s16_to_f32_kernel<<<(unsigned int)((threads + 255) / 256), 256, 0, st>>>(in, out, n);
+    BLISS_LAUNCH(s16_to_f32_kernel, (unsigned int)((threads + 255) / 256), 256, 0, st, in, out, n);
     return 1;
 }
-#endif
 
 // ---- interleaved PCM -> mono f32 (bliss_b200_analyze_batch_pcm, bliss_b200_pcm_to_mono) ------------------
 // The sample-format and down-mix steps of the reference's decoders for sources that already run at
@@ -113,15 +109,13 @@ pcm_to_mono_kernel(const void *__restrict__ in, float *__restrict__ out, size_t 
     *reinterpret_cast<float4 *>(out + f0) = make_float4(r[0], r[1], r[2], r[3]);
 }
 
-#ifndef BLISS_HOST_EMUL
 int launch_pcm_to_mono(const void *in, float *out, size_t n_frames, int fmt, unsigned int channels, cudaStream_t st) {
     if (n_frames == 0) return 0;
     const unsigned int grid = (unsigned int)(((n_frames + 3) / 4 + 255) / 256);
-    if (fmt == 1) pcm_to_mono_kernel<1><<<grid, 256, 0, st>>>(in, out, n_frames, channels);
-    else if (fmt == 2) pcm_to_mono_kernel<2><<<grid, 256, 0, st>>>(in, out, n_frames, channels);
-    else pcm_to_mono_kernel<3><<<grid, 256, 0, st>>>(in, out, n_frames, channels);
+    if (fmt == 1) BLISS_LAUNCH(pcm_to_mono_kernel<1>, grid, 256, 0, st, in, out, n_frames, channels);
+    else if (fmt == 2) BLISS_LAUNCH(pcm_to_mono_kernel<2>, grid, 256, 0, st, in, out, n_frames, channels);
+    else BLISS_LAUNCH(pcm_to_mono_kernel<3>, grid, 256, 0, st, in, out, n_frames, channels);
     return 1;
 }
-#endif
 
 }  // namespace bliss

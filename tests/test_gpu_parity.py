@@ -18,6 +18,29 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-4
 
+# This suite runs on a B200.  The CPU suite also runs a slice of it WITHOUT a GPU against the host-emulated TEST
+# build of the library (tests/test_host_abi.py::test_c_abi_on_the_host_emulated_library: the same sources compiled
+# with g++ against tests/cpu_emul/cuda_on_cpu, BLISS_B200_SO pointing at it): "device" buffers are host tensors then
+# and the synthetic extras shrink, because every CUDA thread is a fiber there.
+DEV = "cuda" if torch.cuda.is_available() else "cpu"
+EMULATED = DEV == "cpu"
+
+
+def _sync():
+    if DEV == "cuda":
+        torch.cuda.synchronize()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream if DEV == "cuda" else None
+
+
+def _extra_tracks(seed, count, seconds, step):
+    """synthetic tracks that widen a test's batch (one short one under the host emulation)"""
+    if EMULATED:
+        count, seconds = 1, 3
+    return [synth.gen_track(seed, i, 22050 * seconds + step * i, device=DEV).cpu().numpy() for i in range(count)]
+
 
 def _close(got, want, tol=TOL):
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
@@ -252,7 +275,7 @@ def test_large_batch_is_bitwise_reproducible():
     for _ in range(3):
         out = torch.zeros((n, 23), device=dev)
         st = B.native.analyze_batch_device(pcm.data_ptr(), offs, lens, 2, out.data_ptr())
-        torch.cuda.synchronize()
+        _sync()
         assert (st == 0).all()
         runs.append(out)
     for r in runs[1:]:
@@ -262,7 +285,7 @@ def test_large_batch_is_bitwise_reproducible():
     # and the batch agrees with the same songs analysed in small groups
     small = torch.zeros((16, 23), device=dev)
     B.native.analyze_batch_device(pcm.data_ptr(), offs[500:516], lens[500:516], 2, small.data_ptr())
-    torch.cuda.synchronize()
+    _sync()
     assert torch.equal(small, runs[0][500:516])
     rc, o = O.analyze(pcm[offs[1000]:offs[1000] + lens[1000]].cpu().numpy(), 2)
     assert _close(runs[0][1000].cpu().numpy(), o).all()
@@ -272,7 +295,7 @@ def test_mixed_duration_corpus_and_playlist_order():
     """30 s .. 10 min tracks (Zipf-like), one call; then playlist-from-seed = closest_to_songs
     ([seed], all, v2 metric) must come out in the oracle's order (stable on ties)."""
     secs = [30, 30, 45, 600, 60, 30, 210, 120, 30, 75, 30, 300]
-    songs = [synth.gen_track(23, i, 22050 * s_ + 37 * i, device="cuda").cpu().numpy() for i, s_ in enumerate(secs)]
+    songs = [synth.gen_track(23, i, 22050 * s_ + 37 * i, device=DEV).cpu().numpy() for i, s_ in enumerate(secs)]
     st, feats = B.native.analyze_batch(songs, 2)
     ost, ofe = O.analyze_batch(songs, 2, n_threads=12)
     assert (st == 0).all() and (ost == 0).all()
@@ -293,7 +316,7 @@ def test_song_longer_than_2_pow_24_samples():
     """utils.rs:30 computes the chroma frame count in f32 ((len as f32 / 2205.).ceil()), exact only below
     2^24 samples (~12.7 min).  A 13.2-minute track exercises the same f32 formula on both sides."""
     n = (1 << 24) + 700001
-    x = synth.gen_track(29, 5, n, device="cuda").cpu().numpy()
+    x = synth.gen_track(29, 5, n, device=DEV).cpu().numpy()
     a = B.Song.analyze(x).as_arr1()
     rc, o = O.analyze(x, 2)
     _report("13-min track", a, o)
@@ -307,13 +330,13 @@ def test_device_api_matches_host_api(pcm_song, pcm_piano):
     for s in songs:
         offs.append(total)
         total += (len(s) + 3) // 4 * 4
-    flat = torch.zeros(total, dtype=torch.float32, device="cuda")
+    flat = torch.zeros(total, dtype=torch.float32, device=DEV)
     for o, s in zip(offs, songs):
-        flat[o:o + len(s)] = torch.from_numpy(s).cuda()
-    out = torch.full((len(songs), 23), 7.0, dtype=torch.float32, device="cuda")
+        flat[o:o + len(s)] = torch.from_numpy(s).to(DEV)
+    out = torch.full((len(songs), 23), 7.0, dtype=torch.float32, device=DEV)
     st = B.native.analyze_batch_device(flat.data_ptr(), offs, [len(s) for s in songs], 2, out.data_ptr(),
-                                       torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
+                                       _stream())
+    _sync()
     hst, hfe = B.native.analyze_batch(songs, 2)
     assert list(st) == list(hst) == [0, 0, 1, 0]
     got = out.cpu().numpy()
@@ -338,7 +361,7 @@ def test_kernel_implementations_agree(pcm_song, pcm_piano):
     Tuning select, chroma contraction, autocorrelation and beat-tracker CTA width must reproduce the current
     kernels BIT FOR BIT; the two other cuts of the 8192-point FFT (previous epilogue, 64 x 64) round
     differently in the last place and must agree to 1e-5 with identical tuning / tempo decisions."""
-    songs = [pcm_song, pcm_piano] + [synth.gen_track(77, i, 22050 * 40 + 101 * i, device="cuda").cpu().numpy() for i in range(6)]
+    songs = [pcm_song, pcm_piano] + _extra_tracks(77, 6, 40, 101)
     try:
         B.native.set_variant(0)
         st0, f0 = B.native.analyze_batch(songs, 2)
@@ -360,13 +383,13 @@ def test_kernel_implementations_agree(pcm_song, pcm_piano):
 def test_cue_style_subslices_of_one_buffer(pcm_song):
     """BlissCueFile::get_songs (src/cue.rs:208-243) analyses sub-slices of ONE decoded buffer cut at
     (start_s * 22050) as usize -- arbitrary, unaligned sample offsets; they may even overlap."""
-    d = torch.from_numpy(np.ascontiguousarray(pcm_song)).cuda()
+    d = torch.from_numpy(np.ascontiguousarray(pcm_song)).to(DEV)
     cuts = [(0, 88201), (88201, 176403), (100003, 230001), (176403, len(pcm_song))]
     offs = [a for a, b in cuts]
     lens = [b - a for a, b in cuts]
-    out = torch.zeros((len(cuts), 23), dtype=torch.float32, device="cuda")
+    out = torch.zeros((len(cuts), 23), dtype=torch.float32, device=DEV)
     st = B.native.analyze_batch_device(d.data_ptr(), offs, lens, 2, out.data_ptr(), None)
-    torch.cuda.synchronize()
+    _sync()
     assert (st == 0).all()
     got = out.cpu().numpy()
     for i, (a, b) in enumerate(cuts):
@@ -377,10 +400,10 @@ def test_cue_style_subslices_of_one_buffer(pcm_song):
 def test_stft512_magnitudes(pcm_song):
     x = pcm_song[:60000]
     n_t = (len(x) - 512) // 256 + 1
-    d = torch.from_numpy(np.ascontiguousarray(x)).cuda()
-    mags = torch.zeros((n_t, 257), dtype=torch.float32, device="cuda")
+    d = torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+    mags = torch.zeros((n_t, 257), dtype=torch.float32, device=DEV)
     fo = B.native.stft512_mag_device(d.data_ptr(), [0], [len(x)], mags.data_ptr(), None)
-    torch.cuda.synchronize()
+    _sync()
     assert list(fo) == [0, n_t]
     want = O.tempo_norms(x)
     err = np.abs(mags.cpu().numpy() - want).max() / want.max()
@@ -520,7 +543,7 @@ def test_experimental_pass1_variants_agree(pcm_song, pcm_piano):
     of 15) and with the Hann window synthesised from the thread's phase (no window loads).  Candidates for the
     data-pipe-bound kernel, not the default: they round differently in the last place (window coefficients differ
     from the reference's f32 table by <= 2.4e-7) and must agree with the measured kernel to 1e-5."""
-    songs = [pcm_song, pcm_piano] + [synth.gen_track(78, i, 22050 * 35 + 211 * i, device="cuda").cpu().numpy() for i in range(6)]
+    songs = [pcm_song, pcm_piano] + _extra_tracks(78, 6, 35, 211)
     try:
         B.native.set_variant(0)
         st0, f0 = B.native.analyze_batch(songs, 2)
@@ -546,14 +569,14 @@ def test_experimental_stft_pair_kernel(pcm_song, pcm_piano):
     offs = np.cumsum([0] + [len(x) + (-len(x)) % 4 for x in songs[:-1]]).tolist()
     lens = [len(x) for x in songs]
     n_t = [(n - 512) // 256 + 1 for n in lens]
-    d = torch.from_numpy(flat).cuda()
+    d = torch.from_numpy(flat).to(DEV)
     try:
         outs = {}
         for mask in (0, 256):
             B.native.set_variant(mask)
-            mags = torch.full((sum(n_t), 257), -1.0, dtype=torch.float32, device="cuda")
+            mags = torch.full((sum(n_t), 257), -1.0, dtype=torch.float32, device=DEV)
             fo = B.native.stft512_mag_device(d.data_ptr(), offs, lens, mags.data_ptr(), None)
-            torch.cuda.synchronize()
+            _sync()
             assert list(fo) == np.cumsum([0] + n_t).tolist()
             outs[mask] = mags.cpu().numpy()
         for i, x in enumerate(songs):
@@ -574,7 +597,7 @@ def test_experimental_pvoc_twiddle_variant(pcm_song, pcm_piano):
     (no twiddle loads in the frame loop).  Rounds differently in the last place: timbral descriptors within 1e-5
     of the measured kernel, parity with the oracle within the usual bar, everything behind the chroma STFT
     untouched."""
-    songs = [pcm_song, pcm_piano] + [synth.gen_track(79, i, 22050 * 30 + 173 * i, device="cuda").cpu().numpy() for i in range(6)]
+    songs = [pcm_song, pcm_piano] + _extra_tracks(79, 6, 30, 173)
     try:
         B.native.set_variant(0)
         st0, f0 = B.native.analyze_batch(songs, 2)
@@ -598,7 +621,7 @@ def test_experimental_pvoc_pair_descriptors_are_bit_identical(pcm_song, pcm_pian
     power-of-two scalings: every feature is expected to equal the measured kernel's bit for bit (reported; held
     to 1e-6); together with bit 512 (product twiddles) within 1e-5."""
     songs = [pcm_song, pcm_piano, np.concatenate([np.zeros(30000, np.float32), pcm_piano[:40000], np.zeros(5000, np.float32)])]
-    songs += [synth.gen_track(80, i, 22050 * 25 + 97 * i, device="cuda").cpu().numpy() for i in range(5)]
+    songs += _extra_tracks(80, 5, 25, 97)
     try:
         B.native.set_variant(0)
         st0, f0 = B.native.analyze_batch(songs, 2)
@@ -630,7 +653,7 @@ def test_experimental_pvoc_pair_descriptors_are_bit_identical(pcm_song, pcm_pian
 def test_experimental_pvoc_tile_padding_is_bit_identical(pcm_song, pcm_piano):
     """BLISS_B200_VARIANT bit 2048: the natural-order tile of pvoc512_kernel padded k + (k >> 4) instead of
     k + (k >> 3) (conflict-free stores).  Only shared-memory addresses change: every feature bit for bit."""
-    songs = [pcm_song, pcm_piano] + [synth.gen_track(81, i, 22050 * 20 + 59 * i, device="cuda").cpu().numpy() for i in range(4)]
+    songs = [pcm_song, pcm_piano] + _extra_tracks(81, 4, 20, 59)
     try:
         B.native.set_variant(0)
         st0, f0 = B.native.analyze_batch(songs, 2)
@@ -646,7 +669,7 @@ def test_experimental_pvoc_tile_padding_is_bit_identical(pcm_song, pcm_piano):
 def test_experimental_fft8192_buffer_layout_is_bit_identical(pcm_song, pcm_piano):
     """BLISS_B200_VARIANT bit 4096: stft8192_kernel's FFT buffer without the per-16 padding (conflict-free mirror
     loads in the pair epilogue).  Only shared-memory addresses change: every feature and every magnitude bit for bit."""
-    songs = [pcm_song, pcm_piano] + [synth.gen_track(82, i, 22050 * 20 + 61 * i, device="cuda").cpu().numpy() for i in range(4)]
+    songs = [pcm_song, pcm_piano] + _extra_tracks(82, 4, 20, 61)
     try:
         B.native.set_variant(0)
         st0, f0 = B.native.analyze_batch(songs, 2)
@@ -667,7 +690,7 @@ def test_experimental_odd_frame_rotation(pcm_song, pcm_piano):
     transformed rotated by one sample, which makes their sample pairs aligned 64-bit loads; |DFT| is unchanged by a
     circular shift, so only rounding moves: magnitudes within 2e-6 of the oracle, features within 1e-5 of the
     measured kernel, nothing outside the chroma features touched."""
-    songs = [pcm_song, pcm_piano] + [synth.gen_track(83, i, 22050 * 20 + 67 * i, device="cuda").cpu().numpy() for i in range(4)]
+    songs = [pcm_song, pcm_piano] + _extra_tracks(83, 4, 20, 67)
     try:
         B.native.set_variant(0)
         st0, f0 = B.native.analyze_batch(songs, 2)

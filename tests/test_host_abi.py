@@ -4,6 +4,7 @@ behaviour, and nothing silently falls back to the CPU when no GPU is present."""
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -115,6 +116,42 @@ def _build_kernel_emulation(tmp_path):
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DBLISS_HOST_EMUL", "-I",
                            os.path.join(here, "cuda_on_cpu"), "-o", exe, os.path.join(here, "emul_kernels.cpp")])
     return exe
+
+
+def _build_host_emulated_library(tmp_path):
+    """The library's own sources (api.cu included) compiled with g++ against tests/cpu_emul/cuda_on_cpu: a TEST build
+    in a temporary directory, never installed, never looked for by the package."""
+    here = os.path.join(ROOT, "tests", "cpu_emul")
+    csrc = os.path.join(ROOT, "bliss-rs_b200", "csrc")
+    names = ["spectral", "tempo", "chroma", "finalize", "distance", "gather", "wave_setup", "api"]
+    procs = [subprocess.Popen(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-x", "c++", "-DBLISS_HOST_EMUL",
+                               "-I", os.path.join(here, "cuda_on_cpu"), "-I", os.path.join(ROOT, "include"), "-c",
+                               os.path.join(csrc, n + ".cu"), "-o", str(tmp_path / (n + ".o"))]) for n in names]
+    assert all(p.wait() == 0 for p in procs)
+    so = str(tmp_path / "libbliss_b200_hostemu_TEST.so")
+    subprocess.check_call(["g++", "-shared", "-o", so] + [str(tmp_path / (n + ".o")) for n in names] + ["-lpthread"])
+    return so
+
+
+def test_c_abi_on_the_host_emulated_library(tmp_path):
+    """The whole library -- host logic of api.cu (chunked host path, waves, descriptors, raw-PCM staging, taps,
+    playlist calls) AND every kernel -- as a TEST build for the host: the same sources compiled with g++ against
+    tests/cpu_emul/cuda_on_cpu (kernel launches run the kernel's source thread by thread at the point of the call,
+    the runtime API is a synchronous stub).  A slice of the GPU suite then runs against it through the real C ABI
+    and the Python binding (BLISS_B200_SO), without a GPU: golden vector, too-short songs, 16-bit and
+    interleaved-PCM ingest, CUE-style sub-slices through the device API, both STFT micro-benchmark kernels,
+    distances and playlist orders.  This is how host-side changes made without a GPU are checked; it is not a
+    product path (the product library is built by nvcc, and bliss_b200_init fails without a device)."""
+    so = _build_host_emulated_library(tmp_path)
+    env = dict(os.environ, BLISS_B200_SO=so, CUDA_VISIBLE_DEVICES="")
+    pick = ("golden_clip_v2 or too_short or s16_ingest or pcm_feed or distance_known or distance_matrix_bit or "
+            "closest_to_songs or dedup or stft512_magnitudes or experimental_stft_pair or cue_style")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
+                          "-p", "no:cacheprovider", "--tb=short", "-k", pick], capture_output=True, text=True, env=env, cwd=ROOT)
+    tail = out.stdout[-1500:] + out.stderr[-500:]
+    assert out.returncode == 0, tail
+    m = re.search(r"(\d+) passed", out.stdout)
+    assert m and int(m.group(1)) >= 10 and "failed" not in out.stdout, tail
 
 
 def test_kernel_sources_reproduce_the_reference_golden_vector(tmp_path, golden):
