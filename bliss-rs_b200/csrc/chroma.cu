@@ -392,6 +392,18 @@ __device__ __forceinline__ void r64_epilogue_pairs(const cpx (&u)[64], const cpx
     }
 }
 
+template <int Q>
+__device__ __forceinline__ void window_synth64(cpx (&v)[64], cpx cw, cpx sw) {
+    if constexpr (Q < 64) {
+        v[Q] = pmul(v[Q], r8k::hann_pair64<Q>(cw, sw));
+        window_synth64<Q + 1>(v, cw, sw);
+    }
+}
+
+// VAR: K3V_WINSYN / K3V_ODDSHIFT as in stft8192_kernel (experimental; 0 = the measured radix-64 kernel).  The kernel
+// stalled on the 128 sample + 64 window loads at the head of each frame: with both cuts a thread issues 64 aligned
+// 64-bit sample loads and one 16-byte phase load instead.
+template <int VAR = 0>
 __global__ void __launch_bounds__(K3R_THREADS, 5)
 stft8192_r64_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
                     const unsigned int *__restrict__ frame_prefix, int n_songs,
@@ -427,7 +439,34 @@ stft8192_r64_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ 
         {   // pass 1: z[nn] = w[2nn] x[2nn] + i w[2nn+1] x[2nn+1], nn = tid + 64 q
             cpx v[64];
             const float2 *ph = reinterpret_cast<const float2 *>(hann) + tid;
-            if (interior) {
+            if constexpr ((VAR & K3V_WINSYN) != 0) {
+                float4 pw = __ldg(reinterpret_cast<const float4 *>(hann + K3_HANN_PHASE) + tid);
+                if (interior) {
+                    const float *pa = x + s0 + 2 * tid;
+                    const bool aligned = (reinterpret_cast<size_t>(pa) & 7) == 0;
+                    if (aligned || (VAR & K3V_ODDSHIFT) != 0) {
+                        // odd-start frames are transformed rotated by one sample (see K3V_ODDSHIFT): aligned pairs
+                        const float2 *pa2 = reinterpret_cast<const float2 *>(aligned ? pa : pa - 1);
+                        if (!aligned) pw = __ldg(reinterpret_cast<const float4 *>(hann + K3_HANN_SHIFT_PHASE) + tid);
+#pragma unroll
+                        for (int q = 0; q < 64; q++) {
+                            const float2 xx = __ldg(pa2 + 64 * q);
+                            v[q] = cpx{xx.x, xx.y};
+                        }
+                        if (!aligned && tid == 0) v[0].x = __ldg(x + s0 + 8191);  // y'[0] = y[8191]
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 64; q++) v[q] = cpx{__ldg(pa + 128 * q), __ldg(pa + 128 * q + 1)};
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 64; q++) {
+                        const long long i0 = (long long)s0 + 2 * (tid + 64 * q);
+                        v[q] = cpx{r8k::reflect_sample(x, n, i0), r8k::reflect_sample(x, n, i0 + 1)};
+                    }
+                }
+                window_synth64<0>(v, cpx{pw.x, pw.y}, cpx{pw.z, pw.w});
+            } else if (interior) {
                 const float *pa = x + s0 + 2 * tid;
                 if ((reinterpret_cast<size_t>(pa) & 7) == 0) {
                     const float2 *pa2 = reinterpret_cast<const float2 *>(pa);
@@ -435,6 +474,16 @@ stft8192_r64_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ 
                     for (int q = 0; q < 64; q++) {
                         const float2 w = __ldg(ph + 64 * q);
                         const float2 xx = __ldg(pa2 + 64 * q);
+                        v[q] = pmul(cpx{xx.x, xx.y}, cpx{w.x, w.y});
+                    }
+                } else if constexpr ((VAR & K3V_ODDSHIFT) != 0) {
+                    const float2 *pa2 = reinterpret_cast<const float2 *>(pa - 1);
+                    const float2 *phs = reinterpret_cast<const float2 *>(hann + K3_HANN_SHIFT) + tid;
+#pragma unroll
+                    for (int q = 0; q < 64; q++) {
+                        const float2 w = __ldg(phs + 64 * q);
+                        float2 xx = __ldg(pa2 + 64 * q);
+                        if (q == 0 && tid == 0) xx.x = __ldg(x + s0 + 8191);  // y'[0] = y[8191]
                         v[q] = pmul(cpx{xx.x, xx.y}, cpx{w.x, w.y});
                     }
                 } else {
@@ -1198,9 +1247,17 @@ int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int 
                     const cpx *tw8192, const cpx *tw64, float *mags, double *cand_mag, double *cand_pitch,
                     unsigned int *cand_count, int variant, cudaStream_t st) {
     if (total_frames == 0) return 0;
-    if (variant & VARIANT_R64)
-        BLISS_LAUNCH(stft8192_r64_kernel, total_frames, K3R_THREADS, 0, st, pcm, songs, frame_prefix, n_songs, hann, tw64, tw8192,
-                                                                 mags, cand_mag, cand_pitch, cand_count);
+    if (variant & VARIANT_R64) {
+        auto go64 = [&](auto kern) {
+            BLISS_LAUNCH(kern, total_frames, K3R_THREADS, 0, st, pcm, songs, frame_prefix, n_songs, hann, tw64, tw8192, mags,
+                         cand_mag, cand_pitch, cand_count);
+        };
+        const bool ws = (variant & VARIANT_WINSYN) != 0, os = (variant & VARIANT_ODDSHIFT) != 0;
+        if (ws && os) go64(stft8192_r64_kernel<K3V_WINSYN | K3V_ODDSHIFT>);
+        else if (ws) go64(stft8192_r64_kernel<K3V_WINSYN>);
+        else if (os) go64(stft8192_r64_kernel<K3V_ODDSHIFT>);
+        else go64(stft8192_r64_kernel<0>);
+    }
     else if (variant & VARIANT_OLD_EPILOGUE)
         BLISS_LAUNCH(stft8192_kernel<false>, total_frames, K3_THREADS, 0, st, pcm, songs, frame_prefix, n_songs, hann, tw1, tw2,
                                                                     tw8192, mags, cand_mag, cand_pitch, cand_count);

@@ -77,8 +77,8 @@ enum {
     VARIANT_PV_PAIRDESC = 1024, // pvoc512: both frames' descriptors reduced / finished together, MUFU-only magnitudes on 2^30-scaled data (experimental; bit-identical results)
     VARIANT_PV_ZPOS4 = 2048,   // pvoc512: natural-order tile padded k + (k >> 4): conflict-free stores as well as loads (experimental; bit-identical results)
     VARIANT_LAY16 = 4096,      // stft8192: FFT buffer without the per-16 padding: conflict-free mirror loads in the pair epilogue (experimental; bit-identical results)
-    VARIANT_ODDSHIFT = 8192,   // stft8192: frames starting on an odd sample are transformed rotated by one sample, so that their pairs load as aligned 64-bit words (experimental)
-    VARIANT_WINSYN = 128,      // stft8192: Hann window from the thread's phase (2 FFMA2 per pair) instead of 16 loads (experimental)
+    VARIANT_ODDSHIFT = 8192,   // stft8192 (both cuts, also with bit 32): frames starting on an odd sample are transformed rotated by one sample, so that their pairs load as aligned 64-bit words (experimental)
+    VARIANT_WINSYN = 128,      // stft8192 (both cuts, also with bit 32): Hann window from the thread's phase (2 FFMA2 per pair) instead of 16 (radix-64: 64) loads (experimental)
 };
 
 // Song lookup for flat work lists: largest s with prefix[s] <= item (prefix has n_songs+1

@@ -1,11 +1,12 @@
 # round-2 opener (1 GPU): GPU tests (incl. the experimental kernel cuts written blind at the end of round 1),
 # then the same bench line once per BLISS_B200_VARIANT mask so that every cut is A/B-timed on one box, then the
 # STFT micro-benchmark with and without the hop-256 pair kernel.  Everything lands in gpurun_out/.
-#   gpurun --timeout 2400 -- 'bash scripts/gpu_r02_ab.sh'      (15 bench lines of about a minute each + tests + two ncu captures)
+#   gpurun --timeout 2400 -- 'bash scripts/gpu_r02_ab.sh'      (19 bench lines of about a minute each + tests + two ncu captures)
 # masks: 64 stft8192 product twiddles | 128 stft8192 synthesised window | 512 pvoc512 product twiddles |
 #        1024 pvoc512 pair descriptors + MUFU-only magnitudes | 2048 pvoc512 conflict-free tile padding |
 #        4096 stft8192 conflict-free buffer layout | 256 STFT micro-benchmark pair kernel
 #        8192 stft8192 aligned loads for odd-start frames
+#        32 the radix-64 stft8192 kernel (measured in round 1), 160 / 8224 / 8352 = it with the window / odd-start / both load cuts
 #        (12480 = all stft8192 cuts, 3584 = all pvoc512 cuts, 16064 = everything)
 mkdir -p gpurun_out; cd $GRAFT_REPO_ROOT
 nvidia-smi -L; nproc
@@ -20,7 +21,7 @@ except Exception as e:
     print(sys.argv[1], 'unreadable', e)
 PY
 }
-for v in 0 64 128 4096 8192 12480 512 1024 2048 3584 16064; do
+for v in 0 64 128 4096 8192 12480 32 160 8224 8352 512 1024 2048 3584 16064; do
   extra="--no-cpu-baseline"; [ $v = 0 ] && extra=""; [ $v = 16064 ] && extra=""   # parity against the oracle for the default and for everything on
   BLISS_B200_VARIANT=$v timeout 400 python bench.py --steps 5 --warmup 3 $extra > gpurun_out/ab_v$v.json 2> gpurun_out/ab_v$v.err; echo "VARIANT $v exit $?"; summ gpurun_out/ab_v$v.json
 done

@@ -309,7 +309,8 @@ def test_kernel_sources_run_on_the_host(tmp_path, golden):
     # ---- stft8192_kernel and its cuts: magnitudes + pip-track candidates
     S = O.stft(x, 8192, 2205)
     p, _ = O.pip_track(S, 8192)
-    for tag in ("default", "v64", "v128", "v4096", "v4288", "v8192", "v12480", "old_epilogue"):
+    for tag in ("default", "v64", "v128", "v4096", "v4288", "v8192", "v12480", "old_epilogue",
+                "r64", "r64_v128", "r64_v8192", "r64_v8320"):
         g = ld("stft8192_" + tag).reshape(-1, 4097)
         assert g.T.shape == S.shape and (g >= 0).all(), tag
         assert np.abs(g.T - S).max() / S.max() < 2e-6, tag
@@ -318,6 +319,9 @@ def test_kernel_sources_run_on_the_host(tmp_path, golden):
     assert same_bits(ld("stft8192_v4096"), ld("stft8192_default"))       # addresses only
     g0, g8 = ld("stft8192_default").reshape(-1, 4097), ld("stft8192_v8192").reshape(-1, 4097)
     changed = np.nonzero((g0 != g8).any(1))[0]  # the rotated transform touches interior frames that start on an odd sample only
+    assert len(changed) > 0 and all((2205 * int(f) - 4096) % 2 == 1 and 2205 * int(f) - 4096 >= 0 for f in changed)
+    r0, r8 = ld("stft8192_r64").reshape(-1, 4097), ld("stft8192_r64_v8192").reshape(-1, 4097)
+    changed = np.nonzero((r0 != r8).any(1))[0]  # the same cut on the radix-64 kernel
     assert len(changed) > 0 and all((2205 * int(f) - 4096) % 2 == 1 and 2205 * int(f) - 4096 >= 0 for f in changed)
     # ---- and the whole path on this clip (too short for a beat: tempo = -1, src/temporal.rs:66-77)
     rc, feats = O.analyze(x, 2)

@@ -182,6 +182,15 @@ def test_chroma_desc(pcm_song):
     assert abs(-0.04999999999999999 - tuning) < 1e-6
 
 
+def test_chroma_end_result_on_silence():
+    # src/chroma.rs:816-866 test_end_result_edge_cases, the digital-silence row (data/silence.ogg decodes to zeros):
+    # every chroma column sums to 0 -> E = exp(0) L1-normalised = 1/12 -> all interval classes equal within their
+    # group -> 2/sqrt(6) - 1 six times, 2/sqrt(4) - 1 = 0 four times; tol 1e-7 as in the reference
+    v2, tuning = O.chroma(np.zeros(22050 * 3, np.float32), 2)
+    exp = np.array([-0.18350339] * 6 + [0.0] * 4, np.float32)
+    assert np.abs(v2[:10] - exp).max() < 1e-7 and tuning == 0.0
+
+
 def test_chroma_stft_decode(pcm_song, golden):
     # src/chroma.rs:623-639, tol 1e-7
     S = O.stft(pcm_song, 8192, 2205)
