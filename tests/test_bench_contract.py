@@ -1,0 +1,52 @@
+"""bench.py's output contract, checked without a GPU: the reference arm (CPU, the oracle port) is run live on a tiny
+sample, and the measured lines committed under profiles/ are checked for the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+        "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches")
+
+
+def _baseline():
+    return json.load(open(os.path.join(ROOT, "BASELINE.json")))
+
+
+def test_reference_arm_prints_one_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""), timeout=900)
+    assert out.returncode == 0, out.stderr[-800:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    for k in BASE + ("impl", "cpu_baseline"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 1 and d["higher_is_better"] is True
+    assert d["unit"] == "songs/s" and d["value"] > 0 and d["vs_baseline"] is None and d["gpu_launches"] == 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"]
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["metric"] == _baseline()["metric"]
+
+
+def test_committed_bench_lines_keep_the_contract():
+    metric = _baseline()["metric"]
+    for name, n in (("bench_r01_1gpu.json", 1), ("bench_r01_2gpu.json", 2), ("bench_r01_8gpu.json", 8)):
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        for k in BASE + ("roofline", "cpu_baseline", "clocks"):
+            assert k in d, (name, k)
+        assert d["metric"] == metric and d["n_gpus"] == n and d["warmup"] >= 3 and d["gpu_launches"] > 0
+        assert d["scaling"] == "weak" and d["dtype"] == "f32" and d["data"] == "synthetic" and d["vs_baseline"] is None
+        assert abs(d["value"] - n * d["config"]["songs_per_gpu"] / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+        r = d["roofline"]
+        assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        e = d["e2e"]
+        assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
+        c = d["clocks"]
+        assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        assert c["sm_mhz"] >= 0.9 * c["sm_max_mhz"]
+    cb = json.load(open(os.path.join(ROOT, "profiles", "bench_r01_1gpu.json")))["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and cb["parity_within_1e-4"] is True
