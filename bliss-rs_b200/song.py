@@ -1,6 +1,8 @@
 """Mirror of src/song/mod.rs, src/song/decoder.rs and the types of src/lib.rs."""
 import enum
 import os
+import queue
+import threading
 from dataclasses import dataclass, field
 from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
 
@@ -312,24 +314,91 @@ class Decoder:
     @classmethod
     def analyze_paths_with_options(cls, paths: Iterable[str],
                                    analysis_options: AnalysisOptions) -> Iterator[Tuple[str, object]]:
-        """Yields (path, Song | BlissError) like the reference's mpsc iterator
-        (src/song/decoder.rs:278-332); order of arrival is unspecified there, batch
-        order here."""
-        batch: List[Tuple[str, PreAnalyzedSong]] = []
+        """Yields (path, Song | BlissError) like the reference's mpsc iterator (src/song/decoder.rs:278-332; order
+        of arrival is unspecified there as here).  Same thread layout up to the analysis: min(available cores,
+        number_cores) workers, each on a contiguous chunk of the paths (:283-304), run `decode`; decoding errors
+        are items (:319-325).  Instead of analysing its own song, a worker hands the decoded buffer to ONE
+        batcher thread through a bounded queue (2 x BATCH_SONGS songs: decoders stall rather than pile PCM up), and
+        the batcher sends <= BATCH_SONGS buffers per bliss_b200_analyze_batch call while the workers keep decoding
+        (the call releases the GIL).  INTEGRATION.md section 3 is the same body in Rust."""
+        paths = list(paths)
+        results: "queue.Queue" = queue.Queue()  # the channel the reference returns
+        if not paths:
+            return iter(())
+        cores = max(1, min(os.cpu_count() or 1, int(analysis_options.number_cores)))
+        chunk_length = max(len(paths) // cores, 1)
+        chunks = [paths[i:i + chunk_length] for i in range(0, len(paths), chunk_length)]
+        decoded: "queue.Queue" = queue.Queue(maxsize=2 * cls.BATCH_SONGS)
+        stop = threading.Event()  # the consumer went away, or a thread failed
+        worker_done, end = object(), object()
 
-        def flush():
-            results = analyze_batch([p.sample_array for _, p in batch], analysis_options)
-            for (path, pre), res in zip(batch, results):
-                yield (path, res if isinstance(res, BlissError) else pre._song(res, analysis_options))
-            batch.clear()
+        def hand_over(item):
+            while not stop.is_set():
+                try:
+                    decoded.put(item, timeout=0.1)
+                    return
+                except queue.Full:
+                    pass
 
-        for path in paths:
+        def worker(chunk):
             try:
-                batch.append((path, cls.decode(path)))
-            except BlissError as e:  # decoding errors are items too
-                yield (path, e)
-                continue
-            if len(batch) >= cls.BATCH_SONGS:
-                yield from flush()
-        if batch:
-            yield from flush()
+                for path in chunk:
+                    if stop.is_set():
+                        break
+                    try:
+                        hand_over((path, cls.decode(path)))
+                    except BlissError as e:  # decoding errors are items too
+                        results.put((path, e))
+            except BaseException as e:  # a bug in decode(): surfaces in the consumer, not in a dead thread
+                results.put((end, e))  # before the batcher can see `stop` and send its own end marker
+                stop.set()
+            finally:
+                hand_over(worker_done)
+
+        def batcher():
+            batch: List[Tuple[str, PreAnalyzedSong]] = []
+
+            def flush():
+                analyses = analyze_batch([p.sample_array for _, p in batch], analysis_options)
+                for (path, pre), res in zip(batch, analyses):
+                    results.put((path, res if isinstance(res, BlissError) else pre._song(res, analysis_options)))
+                batch.clear()
+
+            try:
+                left = len(chunks)
+                while left and not stop.is_set():
+                    try:
+                        item = decoded.get(timeout=0.1)
+                    except queue.Empty:
+                        continue
+                    if item is worker_done:
+                        left -= 1
+                        continue
+                    batch.append(item)
+                    if len(batch) >= cls.BATCH_SONGS:
+                        flush()
+                if batch and not stop.is_set():
+                    flush()
+                results.put((end, None))
+            except BaseException as e:  # e.g. a CUDA failure of the whole call
+                stop.set()
+                results.put((end, e))
+
+        threads = [threading.Thread(target=worker, args=(c,), daemon=True) for c in chunks]
+        threads.append(threading.Thread(target=batcher, daemon=True))
+        for t in threads:
+            t.start()
+
+        def drain():
+            try:
+                while True:
+                    path, item = results.get()
+                    if path is end:
+                        if item is not None:
+                            raise item
+                        return
+                    yield (path, item)
+            finally:
+                stop.set()
+
+        return drain()

@@ -9,7 +9,12 @@
 //   PreAnalyzedSong, Decoder               src/song/decoder.rs:34-333
 //   distances, closest_to_songs, ...       src/playlist.rs:65-326
 #pragma once
+#include <algorithm>
+#include <condition_variable>
 #include <cstdint>
+#include <deque>
+#include <exception>
+#include <mutex>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -230,27 +235,87 @@ class Decoder {
     }
 
     using PathResult = std::pair<std::string, std::variant<Song, BlissError>>;
+    // Decoder::analyze_paths_with_options, src/song/decoder.rs:278-332, with the thread layout of the reference up to
+    // the analysis: min(available cores, number_cores) threads, each on a contiguous chunk of the paths (:283-304),
+    // call decode() -- which therefore has to be safe to call concurrently, like the reference's associated
+    // function -- and decoding errors are items (:319-325).  Instead of analysing its own song a worker hands the
+    // decoded buffer over (bounded: 2 x batch_songs songs, decoders stall rather than pile PCM up); the calling
+    // thread is the batcher: <= batch_songs buffers per bliss_b200_analyze_batch call while the workers keep
+    // decoding.  The order of the results is the order of arrival (unspecified in the reference as well).
+    // INTEGRATION.md section 3 is the same body in Rust.
     std::vector<PathResult> analyze_paths(const std::vector<std::string> &paths, const AnalysisOptions &o = {},
                                           size_t batch_songs = 64) {
         std::vector<PathResult> out;
-        std::vector<PreAnalyzedSong> batch;
-        auto flush = [&]() {
-            std::vector<const float *> ptrs;
-            std::vector<uint64_t> lens;
-            for (auto &p : batch) { ptrs.push_back(p.sample_array.data()); lens.push_back(p.sample_array.size()); }
-            auto res = analyze_batch(ptrs, lens, o);
-            for (size_t i = 0; i < batch.size(); i++) {
-                if (auto *a = std::get_if<Analysis>(&res[i])) out.emplace_back(batch[i].path, to_song(batch[i], *a, o));
-                else out.emplace_back(batch[i].path, std::get<BlissError>(res[i]));
+        if (paths.empty()) return out;
+        batch_songs = std::max<size_t>(batch_songs, 1);
+        const size_t cores = std::max<size_t>(1, std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), o.number_cores));
+        const size_t chunk_length = std::max<size_t>(paths.size() / cores, 1);
+        std::mutex mu;  // guards everything below and `out`
+        std::condition_variable not_empty, not_full;
+        std::deque<PreAnalyzedSong> decoded;
+        size_t workers_left = (paths.size() + chunk_length - 1) / chunk_length;
+        std::exception_ptr failure;
+        auto worker = [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; i++) {
+                try {
+                    PreAnalyzedSong p = decode(paths[i]);
+                    std::unique_lock<std::mutex> lk(mu);
+                    not_full.wait(lk, [&] { return decoded.size() < 2 * batch_songs || failure; });
+                    if (failure) break;
+                    decoded.push_back(std::move(p));
+                    not_empty.notify_one();
+                } catch (const BlissError &e) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    out.emplace_back(paths[i], e);
+                } catch (...) {  // a bug in decode(): rethrown on the calling thread
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (!failure) failure = std::current_exception();
+                    break;
+                }
             }
-            batch.clear();
+            std::lock_guard<std::mutex> lk(mu);
+            workers_left--;
+            not_empty.notify_one();
         };
-        for (const auto &path : paths) {
-            try { batch.push_back(decode(path)); }
-            catch (const BlissError &e) { out.emplace_back(path, e); continue; }
-            if (batch.size() >= batch_songs) flush();
+        std::vector<std::thread> threads;
+        for (size_t lo = 0; lo < paths.size(); lo += chunk_length)
+            threads.emplace_back(worker, lo, std::min(paths.size(), lo + chunk_length));
+        std::vector<PreAnalyzedSong> batch;
+        try {
+            for (;;) {
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    not_empty.wait(lk, [&] { return !decoded.empty() || workers_left == 0 || failure; });
+                    if (failure) break;
+                    while (!decoded.empty() && batch.size() < batch_songs) {
+                        batch.push_back(std::move(decoded.front()));
+                        decoded.pop_front();
+                    }
+                    not_full.notify_all();
+                    if (batch.size() < batch_songs && (workers_left > 0 || !decoded.empty())) continue;  // keep filling
+                    if (batch.empty()) break;  // every worker is done and everything decoded has been analysed
+                }
+                std::vector<const float *> ptrs;
+                std::vector<uint64_t> lens;
+                for (auto &p : batch) { ptrs.push_back(p.sample_array.data()); lens.push_back(p.sample_array.size()); }
+                auto res = analyze_batch(ptrs, lens, o);  // outside the lock: the workers keep decoding
+                std::lock_guard<std::mutex> lk(mu);
+                for (size_t i = 0; i < batch.size(); i++) {
+                    if (auto *a = std::get_if<Analysis>(&res[i])) out.emplace_back(batch[i].path, to_song(batch[i], *a, o));
+                    else out.emplace_back(batch[i].path, std::get<BlissError>(res[i]));
+                }
+                batch.clear();
+            }
+        } catch (...) {  // e.g. a CUDA failure of the whole call: stop the workers before unwinding past their captures
+            std::lock_guard<std::mutex> lk(mu);
+            if (!failure) failure = std::current_exception();
         }
-        if (!batch.empty()) flush();
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            not_full.notify_all();
+        }
+        for (auto &t : threads) t.join();
+        if (failure) std::rethrow_exception(failure);
         return out;
     }
 

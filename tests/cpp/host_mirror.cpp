@@ -2,21 +2,38 @@
 // Built and run by tests/test_host_abi.py: without a GPU it must fail loudly ("NO_DEVICE": there is no CPU
 // fallback); with one it analyses a synthetic clip through Song::analyze, the batched Decoder seam and the
 // 16-bit entry point and prints "OK".
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <set>
 
 #include "bliss_b200.hpp"
 
 using namespace bliss;
 
 struct ToneDecoder : Decoder {  // a Decoder whose "files" are synthetic tones; "bad" fails to decode
-    PreAnalyzedSong decode(const std::string &path) override {
+    std::atomic<int> now{0}, peak{0}, calls{0};
+    PreAnalyzedSong decode(const std::string &path) override {  // called from analyze_paths' worker threads
+        struct Busy {
+            ToneDecoder &d;
+            explicit Busy(ToneDecoder &dd) : d(dd) {
+                d.calls++;
+                const int n = ++d.now;
+                int p = d.peak.load();
+                while (n > p && !d.peak.compare_exchange_weak(p, n)) {}
+            }
+            ~Busy() { d.now--; }
+        } busy(*this);
+        const bool is_short = path.rfind("short", 0) == 0;
+        if (is_short) std::this_thread::sleep_for(std::chrono::milliseconds(5));
         if (path == "bad") throw BlissError(BlissError::DecodingError, "while opening format for file 'bad'");
+        if (path == "bug") throw std::logic_error("decode() is broken");
         PreAnalyzedSong p;
         p.path = path;
         p.title = path;
-        const size_t n = path == "short" ? 4000 : 22050 * 12;
+        const size_t n = is_short ? 4000 : 22050 * 12;
         p.sample_array.resize(n);
         const double f = 220.0 * (1 + (int)path.size());
         for (size_t i = 0; i < n; i++)
@@ -61,6 +78,39 @@ int main() {
             }
         }
         if (ok != 2 || err != 2) return 12;
+        // the same seam with decoding threads: 3 cores over 14 paths -> chunks of 4 -> 4 worker threads (the reference's
+        // paths.chunks(len / cores), src/song/decoder.rs:300-304), every path answered exactly once, rows stay with
+        // their songs, the calling thread batches <= 3 songs per GPU call while the workers decode
+        {
+            std::vector<std::string> paths = {"short0", "short1", "a", "short2", "short3", "bad", "short4", "short5",
+                                              "short6", "bbb", "short7", "short8", "short9", "shortA"};
+            AnalysisOptions o3;
+            o3.number_cores = 3;
+            dec.peak = 0;
+            dec.calls = 0;
+            auto many = dec.analyze_paths(paths, o3, 3);
+            if (many.size() != paths.size() || dec.calls != (int)paths.size()) return 21;
+            std::multiset<std::string> want(paths.begin(), paths.end()), got;
+            for (auto &r : many) {
+                got.insert(r.first);
+                if (auto *song = std::get_if<Song>(&r.second)) {
+                    if (r.first != "a" && r.first != "bbb") return 22;
+                    const Song &ref = r.first == "a" ? s : t;
+                    if (song->path != r.first || std::memcmp(song->analysis->as_vec().data(), ref.analysis->as_vec().data(), 23 * sizeof(float)) != 0) return 23;
+                } else if ((r.first == "bad") != (std::get<BlissError>(r.second).kind == BlissError::DecodingError)) {
+                    return 24;
+                }
+            }
+            if (got != want) return 25;
+            if (std::thread::hardware_concurrency() >= 2 && dec.peak < 2) return 26;  // decoders did run side by side
+            try {  // a failure of decode() that is not a BlissError reaches the caller, after the workers have stopped
+                dec.analyze_paths({"short0", "bug", "short1", "short2"}, o3, 2);
+                return 27;
+            } catch (const std::logic_error &) {
+            }
+            if (dec.now != 0) return 28;
+            if (!dec.analyze_paths({}, o3).empty()) return 29;
+        }
         // 16-bit entry point == f32 entry point on x / 32768
         PreAnalyzedSong p = dec.decode("a");
         std::vector<int16_t> q(p.sample_array.size());

@@ -93,10 +93,75 @@ def test_decoder_trait_batches_errors_as_items(monkeypatch):
         return [B.Analysis(np.zeros(23)) for _ in arrays]
 
     monkeypatch.setattr(B.song, "analyze_batch", fake_batch)
-    got = list(Dec.analyze_paths(["a", "bad", "b", "c"]))
+    one_core = B.AnalysisOptions(number_cores=1)  # one decoding thread: the order of arrival is determined
+    got = list(Dec.analyze_paths_with_options(["a", "bad", "b", "c"], one_core))
     assert [p for p, _ in got] == ["bad", "a", "b", "c"]
     assert isinstance(got[0][1], B.DecodingError) and isinstance(got[1][1], B.Song)
     assert calls == [2, 1]
+    assert list(Dec.analyze_paths([])) == []
+
+
+def test_decoder_trait_decodes_on_number_cores_threads_while_the_batcher_runs(monkeypatch):
+    """Decoder::analyze_paths_with_options (src/song/decoder.rs:278-332): min(cores, number_cores) decoding threads
+    on contiguous chunks, ONE batcher making the GPU calls while they keep decoding, a bounded hand-over queue,
+    every path answered exactly once, failures of decode() that are not BlissErrors re-raised to the consumer."""
+    import threading
+    import time
+    lock, state = threading.Lock(), {"now": 0, "peak": 0, "threads": set(), "batch_threads": set(), "overlap": False}
+
+    class Dec(B.Decoder):
+        BATCH_SONGS = 4
+
+        @classmethod
+        def decode(cls, path):
+            with lock:
+                state["now"] += 1
+                state["peak"] = max(state["peak"], state["now"])
+                state["threads"].add(threading.get_ident())
+            time.sleep(0.01)
+            with lock:
+                state["now"] -= 1
+            if path.startswith("bad"):
+                raise B.DecodingError(path)
+            if path == "bug":
+                raise ZeroDivisionError("decode() is broken")
+            return B.PreAnalyzedSong(path=path, sample_array=np.full(9000, float(path), np.float32))
+
+    def fake_batch(arrays, opts=None):
+        with lock:
+            state["batch_threads"].add(threading.get_ident())
+            state["overlap"] = state["overlap"] or state["now"] > 0
+        assert 1 <= len(arrays) <= Dec.BATCH_SONGS
+        time.sleep(0.005)
+        return [B.AnalysisError("empty or too short song.") if a[0] == 7 else B.Analysis(np.full(23, a[0])) for a in arrays]
+
+    monkeypatch.setattr(B.song, "analyze_batch", fake_batch)
+    monkeypatch.setattr(B.song.os, "cpu_count", lambda: 8)
+    paths = [str(i) for i in range(40)] + ["bad1", "bad2"]
+    got = list(Dec.analyze_paths_with_options(paths, B.AnalysisOptions(number_cores=4)))
+    assert sorted(p for p, _ in got) == sorted(paths)                     # every path exactly once
+    for p, r in got:
+        if p.startswith("bad"):
+            assert isinstance(r, B.DecodingError)
+        elif p == "7":
+            assert isinstance(r, B.AnalysisError)                        # a rejected song is an item of its batch
+        else:
+            assert isinstance(r, B.Song) and r.path == p and r.analysis.as_arr1()[0] == float(p)   # rows stay with their songs
+    # 42 paths / 4 cores -> chunks of 10 -> 5 chunk threads, like the reference's paths.chunks(len / cores)
+    assert len(state["threads"]) == 5 and 2 <= state["peak"] <= 5
+    assert len(state["batch_threads"]) == 1 and not state["batch_threads"] & state["threads"]
+    assert state["overlap"]                                               # GPU calls ran while decoders were busy
+    with pytest.raises(ZeroDivisionError):
+        list(Dec.analyze_paths_with_options(["1", "2", "bug", "3"], B.AnalysisOptions(number_cores=2)))
+    # a consumer that walks away does not leave the producers blocked on the bounded queue for ever
+    before = threading.active_count()
+    it = Dec.analyze_paths_with_options([str(i) for i in range(200)], B.AnalysisOptions(number_cores=4))
+    next(it)
+    it.close()
+    deadline = time.time() + 10
+    while threading.active_count() > before and time.time() < deadline:
+        time.sleep(0.05)
+    assert threading.active_count() <= before
 
 
 def test_fft_index_logic_on_host(tmp_path):
