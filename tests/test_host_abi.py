@@ -219,7 +219,7 @@ def test_c_abi_on_the_host_emulated_library(tmp_path):
     assert m and int(m.group(1)) >= 10 and "failed" not in out.stdout, tail
     # ... and the C++17 host mirror (include/bliss_b200.hpp: Song, Decoder, analyze_batch[_s16|_pcm], playlist) end to end
     exe = str(tmp_path / "host_mirror_emu")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
                            os.path.join(ROOT, "tests", "cpp", "host_mirror.cpp"), "-o", exe, so, "-Wl,-rpath," + str(tmp_path)])
     run = subprocess.run([exe], capture_output=True, text=True)
     assert run.returncode == 0 and run.stdout.strip().endswith("OK"), run.stdout + run.stderr
@@ -536,7 +536,7 @@ def test_variant_mask_names_match_header():
 def _build_cpp_mirror(tmp_path):
     exe = str(tmp_path / "host_mirror")
     libdir = os.path.dirname(B.native.SO_PATH)
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
                            os.path.join(ROOT, "tests", "cpp", "host_mirror.cpp"), "-o", exe, "-L" + libdir,
                            "-lbliss_b200", "-Wl,-rpath," + libdir])
     return exe
