@@ -9,9 +9,12 @@ from . import _native as native
 from .song import (AnalysisIndex, AnalysisIndexv1, Analysis, AnalysisOptions, BlissError, AnalysisError,
                    DecodingError, ProviderError, Decoder, FeaturesVersion, PreAnalyzedSong, Song,
                    NUMBER_FEATURES, SAMPLE_RATE, CHANNELS, analyze_batch, analyze_batch_pcm, pcm_to_mono)
+from .song import analyze_decoded
+from .decoder import WavDecoder
 from . import playlist
 from . import library
 
 __all__ = ["native", "playlist", "library", "AnalysisIndex", "AnalysisIndexv1", "Analysis", "AnalysisOptions", "BlissError",
            "AnalysisError", "DecodingError", "ProviderError", "Decoder", "FeaturesVersion", "PreAnalyzedSong",
-           "Song", "NUMBER_FEATURES", "SAMPLE_RATE", "CHANNELS", "analyze_batch", "analyze_batch_pcm", "pcm_to_mono"]
+           "Song", "NUMBER_FEATURES", "SAMPLE_RATE", "CHANNELS", "analyze_batch", "analyze_batch_pcm", "pcm_to_mono", "analyze_decoded",
+           "WavDecoder"]

@@ -1,0 +1,55 @@
+"""A concrete `Decoder` for the one family of sources this backend can take without the crate's decoders: RIFF/WAVE
+PCM files that already run at 22 050 Hz (src/lib.rs:143).
+
+The reference's decoders (src/song/decoder/ffmpeg.rs, symphonia.rs) do three things to such a file: unpack the
+codec's frames, convert the sample format to f32 and down-mix to mono; nothing is resampled.  `WavDecoder.decode`
+does the first on the host (Python's `wave`) and leaves the packed frames in `PreAnalyzedSong.pcm_frames`; the other
+two run on the device behind the copy (`bliss_b200_analyze_batch_pcm`: x * 2^-15 / x * 2^-31, c L + c R with
+c = (float)sqrt(1/2), mean in channel order for more channels), so `Decoder.analyze_paths` sends the file's own bytes
+over PCIe.  Any other sample rate is a DecodingError: there is no resampler on this side of the boundary (DESIGN.md
+section 7) -- such files stay with the crate's decoders.
+
+Sample widths, as ffmpeg's pcm decoders deliver them (libavcodec/pcm.c behind ffmpeg.rs:190-360):
+  8 bit unsigned  -> (x - 128) * 2^-7   (carried as s16: (x - 128) << 8)
+  16 bit signed   -> x * 2^-15
+  24 bit signed   -> x * 2^-23          (carried as s32: x << 8, what pcm_s24le decodes to)
+  32 bit signed   -> x * 2^-31
+"""
+import wave
+
+import numpy as np
+
+from .song import SAMPLE_RATE, Decoder, DecodingError, PreAnalyzedSong
+
+MAX_CHANNELS = 8  # BLISS_B200_PCM_MAX_CHANNELS, include/bliss_b200.h
+
+
+class WavDecoder(Decoder):
+    @classmethod
+    def decode(cls, path: str) -> PreAnalyzedSong:
+        try:
+            with wave.open(str(path), "rb") as w:
+                channels, width, rate, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+                raw = w.readframes(n)
+        except (wave.Error, OSError, EOFError) as e:
+            raise DecodingError("while opening format for file '%s': %s." % (path, e))
+        if rate != SAMPLE_RATE:
+            raise DecodingError("file '%s' runs at %d Hz: this backend holds no resampler, only %d Hz sources are taken."
+                                % (path, rate, SAMPLE_RATE))
+        if not 1 <= channels <= MAX_CHANNELS:
+            raise DecodingError("file '%s' has %d channels (1..%d are taken)." % (path, channels, MAX_CHANNELS))
+        n = len(raw) // (width * channels)  # a truncated file: the whole frames that are there
+        raw = raw[:n * width * channels]
+        if width == 1:
+            frames = (np.frombuffer(raw, np.uint8).astype(np.int16) - 128) << 8
+        elif width == 2:
+            frames = np.frombuffer(raw, "<i2").astype(np.int16, copy=False)
+        elif width == 3:
+            b = np.frombuffer(raw, np.uint8).reshape(-1, 3).astype(np.uint32)
+            frames = ((b[:, 0] << 8) | (b[:, 1] << 16) | (b[:, 2] << 24)).view(np.int32)
+        elif width == 4:
+            frames = np.frombuffer(raw, "<i4").astype(np.int32, copy=False)
+        else:
+            raise DecodingError("file '%s': %d-byte samples." % (path, width))
+        frames = np.ascontiguousarray(frames.reshape(n, channels))
+        return PreAnalyzedSong(path=str(path), duration=n / float(rate), pcm_frames=frames)

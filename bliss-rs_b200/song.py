@@ -247,6 +247,26 @@ def analyze_batch_pcm(frames: Sequence, sample_rate: int = SAMPLE_RATE, analysis
     return [_result_item(st, row, ver) for st, row in zip(status, feats)]
 
 
+def analyze_decoded(songs: Sequence["PreAnalyzedSong"], analysis_options: AnalysisOptions = None) -> List:
+    """One batch of decoded songs -> one entry per song (Analysis | BlissError).  Songs that carry sample_array go
+    through analyze_batch; songs that carry packed frames are grouped by (sample format, channel count) -- one
+    bliss_b200_analyze_batch_pcm call takes one of each -- and converted on the device."""
+    out: List = [None] * len(songs)
+    groups = {}
+    for i, p in enumerate(songs):
+        f = p.pcm_frames
+        key = None if f is None else (np.asarray(f).dtype.str, 1 if np.asarray(f).ndim == 1 else np.asarray(f).shape[1])
+        groups.setdefault(key, []).append(i)
+    for key, idx in groups.items():
+        if key is None:
+            res = analyze_batch([songs[i].sample_array for i in idx], analysis_options)
+        else:
+            res = analyze_batch_pcm([songs[i].pcm_frames for i in idx], SAMPLE_RATE, analysis_options)
+        for i, r in zip(idx, res):
+            out[i] = r
+    return out
+
+
 def pcm_to_mono(frames) -> np.ndarray:
     """PreAnalyzedSong.sample_array of such a source (src/song/decoder.rs:64)"""
     return native.pcm_to_mono(frames)
@@ -273,11 +293,22 @@ class PreAnalyzedSong:
     genre: Optional[str] = None
     duration: float = 0.0
     sample_array: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
+    #: Not in the reference.  A decoder whose source already runs at 22 050 Hz may leave the codec's packed frames
+    #: here ([n_frames, channels] int16 / int32 / float32) instead of filling sample_array: sample-format conversion
+    #: and down-mix then run on the device behind the copy (bliss_b200_analyze_batch_pcm),
+    #: and e.g. 16-bit mono material sends half the bytes over PCIe.
+    pcm_frames: Optional[np.ndarray] = None
+
+    def mono(self) -> np.ndarray:
+        """sample_array as the reference's decoders would have filled it (src/song/decoder.rs:64)"""
+        return self.sample_array if self.pcm_frames is None else pcm_to_mono(self.pcm_frames)
 
     def to_song_with_options(self, analysis_options: AnalysisOptions) -> Song:
         """src/song/decoder.rs:85-100"""
-        analysis = Song.analyze_with_options(self.sample_array, analysis_options)
-        return self._song(analysis, analysis_options)
+        res = analyze_decoded([self], analysis_options)[0]
+        if isinstance(res, BlissError):
+            raise res
+        return self._song(res, analysis_options)
 
     def _song(self, analysis, analysis_options):
         return Song(path=self.path, artist=self.artist, album_artist=self.album_artist, title=self.title,
@@ -359,7 +390,7 @@ class Decoder:
             batch: List[Tuple[str, PreAnalyzedSong]] = []
 
             def flush():
-                analyses = analyze_batch([p.sample_array for _, p in batch], analysis_options)
+                analyses = analyze_decoded([p for _, p in batch], analysis_options)
                 for (path, pre), res in zip(batch, analyses):
                     results.put((path, res if isinstance(res, BlissError) else pre._song(res, analysis_options)))
                 batch.clear()

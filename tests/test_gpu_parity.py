@@ -532,6 +532,40 @@ def test_pcm_feed_matches_the_decoders_conversion(golden):
         B.native.analyze_batch_pcm([np.zeros((9000, 9), np.int16)], 22050, 2)
 
 
+def test_wav_files_through_the_decoder_pipeline(tmp_path, golden, pcm_piano):
+    """File -> features: 22 050 Hz WAV files through WavDecoder.analyze_paths (decoding threads, one batcher, packed
+    frames converted and down-mixed on the device).  The 16-bit mono file is data/piano.wav's content, so its row
+    must be Song::analyze of the decoder's f32 samples (ffmpeg.rs:523-527 pins those) bit for bit; the stereo and
+    24-bit files must equal the analysis of the oracle's conversion of the same frames; a 44.1 kHz file and a short
+    one are error items of the same call."""
+    import wave
+
+    def write(name, frames, width, rate=22050):
+        frames = np.asarray(frames)
+        with wave.open(str(tmp_path / name), "wb") as w:
+            w.setnchannels(1 if frames.ndim == 1 else frames.shape[1])
+            w.setsampwidth(width)
+            w.setframerate(rate)
+            if width == 3:
+                w.writeframes(np.ascontiguousarray(frames.astype("<i4").reshape(-1).view(np.uint8).reshape(-1, 4)[:, :3]).tobytes())
+            else:
+                w.writeframes(frames.astype("<i2").tobytes())
+        return str(tmp_path / name)
+
+    s16 = golden["pcm_piano"]
+    st = np.stack([s16, np.roll(s16, 7) // 2], 1).astype(np.int16)
+    s24 = s16.astype(np.int32) * 256 + 37
+    paths = [write("piano.wav", s16, 2), write("stereo.wav", st, 2), write("piano24.wav", s24, 3),
+             write("cd.wav", s16, 2, rate=44100), write("short.wav", s16[:4000], 2)]
+    got = dict(B.WavDecoder.analyze_paths_with_options(paths, B.AnalysisOptions(number_cores=2)))
+    assert len(got) == 5
+    assert np.array_equal(got[paths[0]].analysis.as_arr1(), B.Song.analyze(pcm_piano).as_arr1())
+    assert np.array_equal(got[paths[1]].analysis.as_arr1(), B.Song.analyze(O.pcm_to_mono(st)).as_arr1())
+    assert np.array_equal(got[paths[2]].analysis.as_arr1(), B.Song.analyze(O.pcm_to_mono(s24 * 256)).as_arr1())
+    assert isinstance(got[paths[3]], B.DecodingError) and isinstance(got[paths[4]], B.AnalysisError)
+    assert abs(got[paths[0]].duration - s16.size / 22050.0) < 1e-9
+
+
 # The kernel cuts behind BLISS_B200_VARIANT bits 64 ... 1024 were written after round 1's GPU budget was spent: they
 # are OFF by default, validated on the host only (tests/cpu_emul, tests/test_host_abi.py), and their tests below
 # have never met hardware.  Non-strict xfail keeps a defect in code that is not on the product path from masking

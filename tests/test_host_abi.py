@@ -164,6 +164,75 @@ def test_decoder_trait_decodes_on_number_cores_threads_while_the_batcher_runs(mo
     assert threading.active_count() <= before
 
 
+def _write_wav(path, frames, width, rate=22050):
+    import wave
+    frames = np.asarray(frames)
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(1 if frames.ndim == 1 else frames.shape[1])
+        w.setsampwidth(width)
+        w.setframerate(rate)
+        if width == 3:
+            b = frames.astype("<i4").reshape(-1).view(np.uint8).reshape(-1, 4)[:, :3]
+            w.writeframes(np.ascontiguousarray(b).tobytes())
+        else:
+            w.writeframes(frames.astype({1: "u1", 2: "<i2", 4: "<i4"}[width]).tobytes())
+
+
+def test_wav_decoder_keeps_the_codecs_frames(tmp_path, golden, monkeypatch):
+    """bliss-rs_b200/decoder.py: a 22 050 Hz RIFF/WAVE PCM file is unpacked on the host and nothing else -- the frames
+    reach bliss_b200_analyze_batch_pcm as the file holds them; other rates and unreadable files are DecodingErrors
+    (items of analyze_paths); a batch that mixes formats is split into one call per (format, channel count)."""
+    s16 = golden["pcm_piano"][:30000]                       # data/piano.wav is such a file (ffmpeg.rs:523-527)
+    rng = np.random.default_rng(1)
+    st = np.stack([s16, (s16 // 3).astype(np.int16)], 1)
+    s24 = rng.integers(-(1 << 23), 1 << 23, 5000)
+    u8 = rng.integers(0, 256, 5000)
+    _write_wav(tmp_path / "mono16.wav", s16, 2)
+    _write_wav(tmp_path / "stereo16.wav", st, 2)
+    _write_wav(tmp_path / "mono24.wav", s24, 3)
+    _write_wav(tmp_path / "mono8.wav", u8, 1)
+    _write_wav(tmp_path / "mono32.wav", s24 * 256, 4)
+    _write_wav(tmp_path / "cd.wav", s16, 2, rate=44100)
+    (tmp_path / "junk.wav").write_bytes(b"not a wave file")
+    d = B.WavDecoder.decode(str(tmp_path / "mono16.wav"))
+    assert d.pcm_frames.dtype == np.int16 and np.array_equal(d.pcm_frames[:, 0], s16) and d.sample_array.size == 0
+    assert abs(d.duration - 30000 / 22050) < 1e-9 and d.path.endswith("mono16.wav")
+    assert np.array_equal(B.WavDecoder.decode(str(tmp_path / "stereo16.wav")).pcm_frames, st)
+    d24 = B.WavDecoder.decode(str(tmp_path / "mono24.wav")).pcm_frames
+    assert d24.dtype == np.int32 and np.array_equal(d24[:, 0], s24 * 256)   # pcm_s24le -> s32: x << 8
+    assert np.array_equal(B.WavDecoder.decode(str(tmp_path / "mono32.wav")).pcm_frames[:, 0], s24 * 256)
+    d8 = B.WavDecoder.decode(str(tmp_path / "mono8.wav")).pcm_frames
+    assert d8.dtype == np.int16 and np.array_equal(d8[:, 0], (u8 - 128) * 256)   # pcm_u8: (x - 128) * 2^-7
+    for bad in ("cd.wav", "junk.wav", "missing.wav"):
+        with pytest.raises(B.DecodingError):
+            B.WavDecoder.decode(str(tmp_path / bad))
+    calls = []
+
+    def fake_pcm(frames, sample_rate=22050, opts=None):
+        calls.append(("pcm", frames[0].dtype.str, frames[0].shape[1], len(frames)))
+        return [B.Analysis(np.full(23, f.shape[1] + f.dtype.itemsize / 10)) for f in frames]
+
+    def fake_f32(arrays, opts=None):
+        calls.append(("f32", len(arrays)))
+        return [B.Analysis(np.zeros(23)) for _ in arrays]
+
+    monkeypatch.setattr(B.song, "analyze_batch_pcm", fake_pcm)
+    monkeypatch.setattr(B.song, "analyze_batch", fake_f32)
+    names = ["mono16.wav", "stereo16.wav", "cd.wav", "mono24.wav", "mono8.wav", "junk.wav", "mono32.wav"]
+    got = dict(B.WavDecoder.analyze_paths_with_options([str(tmp_path / n) for n in names], B.AnalysisOptions(number_cores=1)))
+    assert len(got) == len(names)
+    tag = {n: (got[str(tmp_path / n)].analysis.as_arr1()[0] if isinstance(got[str(tmp_path / n)], B.Song) else None) for n in names}
+    assert tag["cd.wav"] is None and tag["junk.wav"] is None
+    assert [round(float(tag[n]), 1) for n in ("mono16.wav", "stereo16.wav", "mono24.wav", "mono8.wav", "mono32.wav")] == \
+        [1.2, 2.2, 1.4, 1.2, 1.4]                                       # every row back with its own song
+    assert sorted(calls) == [("pcm", "<i2", 1, 2), ("pcm", "<i2", 2, 1), ("pcm", "<i4", 1, 2)]
+    # songs that carry sample_array keep going through analyze_batch, in the same batch
+    calls.clear()
+    mixed = [B.PreAnalyzedSong(path="a", sample_array=np.zeros(9000, np.float32)), B.WavDecoder.decode(str(tmp_path / "mono16.wav"))]
+    res = B.analyze_decoded(mixed)
+    assert sorted(calls) == [("f32", 1), ("pcm", "<i2", 1, 1)] and res[0].as_arr1()[0] == 0.0 and res[1].as_arr1()[0] > 1.0
+
+
 def test_fft_index_logic_on_host(tmp_path):
     """tests/cpu_emul/emul_fft.cu runs the warp / CTA FFT passes of pvoc512.cuh and rfft8192.cuh (incl. the
     fused pass 3 + mirror-pair epilogue) thread by thread on the host and compares with an f64 DFT."""
@@ -204,13 +273,13 @@ def test_c_abi_on_the_host_emulated_library(tmp_path):
     tests/cpu_emul/cuda_on_cpu (kernel launches run the kernel's source thread by thread at the point of the call,
     the runtime API is a synchronous stub).  A slice of the GPU suite then runs against it through the real C ABI
     and the Python binding (BLISS_B200_SO), without a GPU: golden vector, too-short songs, 16-bit and
-    interleaved-PCM ingest, CUE-style sub-slices through the device API, both STFT micro-benchmark kernels,
+    interleaved-PCM ingest, WAV files through the decoder pipeline, CUE-style sub-slices through the device API, both STFT micro-benchmark kernels,
     distances and playlist orders.  This is how host-side changes made without a GPU are checked; it is not a
     product path (the product library is built by nvcc, and bliss_b200_init fails without a device)."""
     so = _build_host_emulated_library(tmp_path)
     env = dict(os.environ, BLISS_B200_SO=so, CUDA_VISIBLE_DEVICES="")
     pick = ("golden_clip_v2 or too_short or s16_ingest or pcm_feed or distance_known or distance_matrix_bit or "
-            "closest_to_songs or dedup or stft512_magnitudes or experimental_stft_pair or cue_style")
+            "closest_to_songs or dedup or stft512_magnitudes or experimental_stft_pair or cue_style or wav_files")
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
                           "-p", "no:cacheprovider", "--tb=short", "-k", pick], capture_output=True, text=True, env=env, cwd=ROOT)
     tail = out.stdout[-1500:] + out.stderr[-500:]
