@@ -564,6 +564,16 @@ def test_wav_files_through_the_decoder_pipeline(tmp_path, golden, pcm_piano):
     assert np.array_equal(got[paths[2]].analysis.as_arr1(), B.Song.analyze(O.pcm_to_mono(s24 * 256)).as_arr1())
     assert isinstance(got[paths[3]], B.DecodingError) and isinstance(got[paths[4]], B.AnalysisError)
     assert abs(got[paths[0]].duration - s16.size / 22050.0) < 1e-9
+    # ... and on into the reference's on-disk format (src/library.rs:500-529, 1544-1670): files -> decoder threads ->
+    # GPU batches -> SQLite rows; the two refused files are rows of the failed-song kind, a second run is a no-op
+    lib = B.library.Library(str(tmp_path / "songs.db"), decoder=B.WavDecoder)
+    assert lib.update_library(paths) == (3, 2)
+    stored = {s.bliss_song.path: s.bliss_song.analysis.as_arr1() for s in lib.songs_from_library()}
+    assert sorted(stored) == sorted(paths[:3])
+    for p in paths[:3]:
+        assert np.array_equal(stored[p], got[p].analysis.as_arr1())
+    assert sorted(f.song_path for f in lib.get_failed_songs()) == sorted(paths[3:])
+    lib.close()
 
 
 # The kernel cuts behind BLISS_B200_VARIANT bits 64 ... 1024 were written after round 1's GPU budget was spent: they
