@@ -366,5 +366,69 @@ inline std::vector<uint32_t> song_to_song(const std::vector<float> &seeds, const
                                                static_cast<uint32_t>(order.size()), dim, mt.metric, mt.mp(), order.data()));
     return order;
 }
+// all pairs on the device: out[i * n_cols + j] = d(rows[i], cols[j])
+inline std::vector<float> distance_matrix(const std::vector<float> &rows, const std::vector<float> &cols, uint32_t dim,
+                                          const Metric &mt = {}) {
+    detail::ensure_init();
+    const uint32_t nr = static_cast<uint32_t>(rows.size() / dim), nc = static_cast<uint32_t>(cols.size() / dim);
+    std::vector<float> out(static_cast<size_t>(nr) * nc);
+    if (!out.empty()) detail::check_call(bliss_b200_distance_matrix(rows.data(), nr, cols.data(), nc, dim, mt.metric, mt.mp(), out.data()));
+    return out;
+}
+// variance_based_weight_matrix, :173-221: the diagonal Mahalanobis matrix (dim x dim, row-major) that weights the
+// dimensions the seeds agree on -- inverse variance, normalised so that the weights sum to dim.  A few f32 operations
+// on n_seeds x dim values, host side as in the reference; feed the result to mahalanobis_distance_builder.
+inline std::vector<float> variance_based_weight_matrix(const std::vector<std::vector<float>> &seeds) {
+    if (seeds.size() < 2) throw BlissError(BlissError::ProviderError, "seeds must contain more than one element");
+    const size_t n = seeds[0].size();
+    if (n == 0) throw BlissError(BlissError::ProviderError, "seed feature vectors must not be empty");
+    for (const auto &sd : seeds)
+        if (sd.size() != n) throw BlissError(BlissError::ProviderError, "all seed feature vectors must have the same length");
+    const float n_seeds = static_cast<float>(seeds.size());
+    std::vector<float> mean(n, 0.f), variance(n, 0.f), m(n * n, 0.f);
+    for (const auto &sd : seeds)
+        for (size_t i = 0; i < n; i++) mean[i] += sd[i];
+    for (size_t i = 0; i < n; i++) mean[i] /= n_seeds;
+    for (const auto &sd : seeds)
+        for (size_t i = 0; i < n; i++) {
+            const float diff = sd[i] - mean[i];
+            variance[i] = variance[i] + diff * diff;
+        }
+    float sum = 0.f;
+    for (size_t i = 0; i < n; i++) {
+        variance[i] = 1.0f / (variance[i] / n_seeds + 1e-6f);
+        sum += variance[i];
+    }
+    for (size_t i = 0; i < n; i++) m[i * n + i] = variance[i] * (static_cast<float>(n) / sum);
+    return m;
+}
+// dedup_playlist_custom_distance, :367-402 (dedup_playlist, :343-349, is the euclidean case): a song goes when it is
+// closer than the threshold (default 0.05) to the last song kept, or carries the same title and artist tags as it.
+// The distances come from one device call.  Returns the indices of the songs that stay.
+inline std::vector<size_t> dedup_playlist_custom_distance(const std::vector<Song> &songs, std::optional<float> distance_threshold = {},
+                                                          const Metric &mt = {}) {
+    std::vector<size_t> keep;
+    if (songs.empty()) return keep;
+    const float thr = distance_threshold.value_or(0.05f);
+    const uint32_t dim = static_cast<uint32_t>(songs[0].analysis->as_vec().size());
+    std::vector<float> rows;
+    for (const Song &sg : songs) rows.insert(rows.end(), sg.analysis->as_vec().begin(), sg.analysis->as_vec().end());
+    const std::vector<float> d = songs.size() > 1 ? distance_matrix(rows, rows, dim, mt) : std::vector<float>();
+    const size_t n = songs.size();
+    for (size_t i = 0; i < n;) {
+        size_t j = i + 1;
+        for (; j < n; j++) {
+            const Song &a = songs[i], &b = songs[j];
+            const bool same_tags = a.title && b.title && a.artist && b.artist && *a.title == *b.title && *a.artist == *b.artist;
+            if (!(d[i * n + j] < thr || same_tags)) break;
+        }
+        keep.push_back(i);
+        i = j;
+    }
+    return keep;
+}
+inline std::vector<size_t> dedup_playlist(const std::vector<Song> &songs, std::optional<float> distance_threshold = {}) {
+    return dedup_playlist_custom_distance(songs, distance_threshold, euclidean_distance());
+}
 }  // namespace playlist
 }  // namespace bliss

@@ -54,6 +54,29 @@ int main() {
     } catch (const BlissError &e) {
         if (e.kind != BlissError::ProviderError) return 5;
     }
+    // variance_based_weight_matrix: the reference's own tests, src/playlist.rs:1664-1760 (host side, no device)
+    {
+        using playlist::variance_based_weight_matrix;
+        const auto m = variance_based_weight_matrix({{1.f, 0.f, 1.f}, {1.f, 100.f, 1.f}, {1.f, 200.f, 1.f}});
+        if (m.size() != 9 || !(m[0] > m[4]) || !(m[8] > m[4])) return 30;
+        if (m[1] != 0.f || m[2] != 0.f || m[3] != 0.f || m[5] != 0.f || m[6] != 0.f || m[7] != 0.f) return 31;
+        if (std::fabs(m[0] + m[4] + m[8] - 3.f) >= 1e-4f) return 32;
+        const auto id = variance_based_weight_matrix({{1.f, 2.f, 3.f}, {1.f, 2.f, 3.f}, {1.f, 2.f, 3.f}});
+        if (std::fabs(id[0] - 1.f) >= 1e-4f || std::fabs(id[4] - 1.f) >= 1e-4f || std::fabs(id[8] - 1.f) >= 1e-4f) return 33;
+        const auto two = variance_based_weight_matrix({{0.f, 50.f}, {0.f, 150.f}});
+        if (two.size() != 4 || !(two[0] > two[3])) return 34;
+        int refused = 0;
+        for (const std::vector<std::vector<float>> &bad :
+             {std::vector<std::vector<float>>{{1.f, 2.f}}, std::vector<std::vector<float>>{{1.f, 2.f}, {1.f}},
+              std::vector<std::vector<float>>{{}, {}}}) {
+            try {
+                variance_based_weight_matrix(bad);
+            } catch (const BlissError &e) {
+                refused += e.kind == BlissError::ProviderError;
+            }
+        }
+        if (refused != 3) return 35;
+    }
     ToneDecoder dec;
     try {
         const Song s = dec.song_from_path("a");
@@ -147,6 +170,32 @@ int main() {
         for (const Song *x : {&t, &s}) cands.insert(cands.end(), x->analysis->as_vec().begin(), x->analysis->as_vec().end());
         const auto order = playlist::closest_to_songs(s.analysis->as_vec(), cands, 23, playlist::mahalanobis_distance_builder(w));
         if (order.size() != 2 || order[0] != 1) return 14;
+        // dedup_playlist[_custom_distance]: the reference's own test, src/playlist.rs:507-640
+        {
+            auto mk = [](const char *path, float filler, float v16, const char *title, const char *artist) {
+                Song x;
+                x.path = path;
+                std::vector<float> a(23, 1.f);
+                for (int i = 0; i < 16; i++) a[i] = filler;
+                if (filler != 1.f) a[16] = v16;
+                x.analysis = Analysis(a, LATEST);
+                if (title) x.title = title;
+                if (artist) x.artist = artist;
+                return x;
+            };
+            const std::vector<Song> pl = {mk("path-to-first", 1.f, 1.f, nullptr, nullptr), mk("path-to-dupe", 1.f, 1.f, nullptr, nullptr),
+                                          mk("path-to-second", 2.f, 1.9f, "dupe-title", "dupe-artist"),
+                                          mk("path-to-third", 2.f, 2.5f, "dupe-title", "dupe-artist"),
+                                          mk("path-to-fourth", 2.f, 0.f, "dupe-title", "no-dupe-artist"),
+                                          mk("path-to-fourth", 2.f, 0.001f, nullptr, nullptr)};
+            const std::vector<size_t> kept = {0, 2, 4}, first_only = {0};
+            if (playlist::dedup_playlist_custom_distance(pl, {}, playlist::euclidean_distance()) != kept) return 40;
+            if (playlist::dedup_playlist_custom_distance(pl, 20.f, playlist::euclidean_distance()) != first_only) return 41;
+            if (playlist::dedup_playlist(pl, 20.f) != first_only || playlist::dedup_playlist(pl) != kept) return 42;
+            if (!playlist::dedup_playlist({}).empty()) return 43;
+            const auto dm = playlist::distance_matrix(pl[0].analysis->as_vec(), pl[2].analysis->as_vec(), 23);
+            if (dm.size() != 1 || dm[0] != playlist::distance(pl[0].analysis->as_vec(), pl[2].analysis->as_vec())) return 44;
+        }
         std::puts("OK");
         return 0;
     } catch (const BlissError &e) {
