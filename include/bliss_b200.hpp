@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdio>
+#include <cstring>
 #include <deque>
 #include <exception>
 #include <mutex>
@@ -220,7 +222,50 @@ struct PreAnalyzedSong {
     std::optional<int> track_number, disc_number;
     double duration_s = 0.;
     std::vector<float> sample_array;  // mono f32le 22 050 Hz
+    // Not in the reference.  A decoder whose source already runs at 22 050 Hz may leave the codec's packed
+    // interleaved frames here instead of filling sample_array (pcm_channels > 0 says so): sample-format conversion
+    // and down-mix then run on the device behind the copy (analyze_batch_pcm), and e.g. 16-bit mono material sends
+    // half the bytes over PCIe.
+    std::vector<unsigned char> pcm_frames;
+    PcmFormat pcm_format = PcmFormat::F32;
+    uint32_t pcm_channels = 0;
+    uint64_t n_frames() const { return pcm_channels ? pcm_frames.size() / ((pcm_format == PcmFormat::S16 ? 2 : 4) * pcm_channels) : sample_array.size(); }
+    std::vector<float> mono() const {  // sample_array as the reference's decoders would have filled it
+        return pcm_channels ? pcm_to_mono(pcm_frames.data(), n_frames(), pcm_format, pcm_channels) : sample_array;
+    }
 };
+
+// One batch of decoded songs -> one entry per song.  Songs that carry sample_array go through analyze_batch; songs
+// that carry packed frames are grouped by (sample format, channel count) -- one bliss_b200_analyze_batch_pcm call
+// takes one of each.
+inline std::vector<AnalysisResult> analyze_decoded(const std::vector<PreAnalyzedSong> &songs, const AnalysisOptions &o = {}) {
+    std::vector<AnalysisResult> out(songs.size(), AnalysisResult(BlissError(BlissError::AnalysisError, "not analysed")));
+    std::vector<char> done(songs.size(), 0);
+    for (size_t first = 0; first < songs.size(); first++) {
+        if (done[first]) continue;
+        const PreAnalyzedSong &lead = songs[first];
+        std::vector<size_t> idx;
+        for (size_t i = first; i < songs.size(); i++)
+            if (!done[i] && songs[i].pcm_channels == lead.pcm_channels && (lead.pcm_channels == 0 || songs[i].pcm_format == lead.pcm_format)) {
+                idx.push_back(i);
+                done[i] = 1;
+            }
+        std::vector<uint64_t> lens;
+        for (size_t i : idx) lens.push_back(songs[i].n_frames());
+        std::vector<AnalysisResult> res;
+        if (lead.pcm_channels == 0) {
+            std::vector<const float *> ptrs;
+            for (size_t i : idx) ptrs.push_back(songs[i].sample_array.data());
+            res = analyze_batch(ptrs, lens, o);
+        } else {
+            std::vector<const void *> ptrs;
+            for (size_t i : idx) ptrs.push_back(songs[i].pcm_frames.data());
+            res = analyze_batch_pcm(ptrs, lens, lead.pcm_format, lead.pcm_channels, BLISS_B200_SAMPLE_RATE, o);
+        }
+        for (size_t k = 0; k < idx.size(); k++) out[idx[k]] = std::move(res[k]);
+    }
+    return out;
+}
 
 // trait Decoder, src/song/decoder.rs:115-333: implement decode(); the provided functions keep the
 // reference's meaning, with analysis batched onto the GPU.
@@ -231,7 +276,12 @@ class Decoder {
 
     Song song_from_path(const std::string &path, const AnalysisOptions &o = {}) {
         PreAnalyzedSong p = decode(path);
-        return to_song(p, Song::analyze_with_options(p.sample_array.data(), p.sample_array.size(), o), o);
+        if (p.pcm_channels == 0) return to_song(p, Song::analyze_with_options(p.sample_array.data(), p.sample_array.size(), o), o);
+        std::vector<PreAnalyzedSong> one;
+        one.push_back(std::move(p));
+        AnalysisResult r = std::move(analyze_decoded(one, o)[0]);
+        if (auto *e = std::get_if<BlissError>(&r)) throw *e;
+        return to_song(one[0], std::get<Analysis>(std::move(r)), o);
     }
 
     using PathResult = std::pair<std::string, std::variant<Song, BlissError>>;
@@ -295,10 +345,7 @@ class Decoder {
                     if (batch.size() < batch_songs && (workers_left > 0 || !decoded.empty())) continue;  // keep filling
                     if (batch.empty()) break;  // every worker is done and everything decoded has been analysed
                 }
-                std::vector<const float *> ptrs;
-                std::vector<uint64_t> lens;
-                for (auto &p : batch) { ptrs.push_back(p.sample_array.data()); lens.push_back(p.sample_array.size()); }
-                auto res = analyze_batch(ptrs, lens, o);  // outside the lock: the workers keep decoding
+                auto res = analyze_decoded(batch, o);  // outside the lock: the workers keep decoding
                 std::lock_guard<std::mutex> lk(mu);
                 for (size_t i = 0; i < batch.size(); i++) {
                     if (auto *a = std::get_if<Analysis>(&res[i])) out.emplace_back(batch[i].path, to_song(batch[i], *a, o));
@@ -327,6 +374,69 @@ class Decoder {
         s.analysis = std::move(a);
         s.features_version = o.features_version;
         return s;
+    }
+};
+
+// A concrete Decoder for the one family of sources this backend takes without the crate's decoders: RIFF/WAVE files
+// that already run at 22 050 Hz (src/lib.rs:143).  The reference's decoders unpack such a file, convert the sample
+// format to f32 and down-mix; nothing is resampled.  decode() does the first on the host and leaves the packed frames
+// in PreAnalyzedSong::pcm_frames, the rest runs on the device.  Widths as ffmpeg's pcm decoders deliver them:
+// u8 -> (x - 128) 2^-7 (carried as s16), s16 -> x 2^-15, s24 -> x 2^-23 (carried as s32: x << 8), s32 -> x 2^-31,
+// IEEE f32 as it is.  Any other rate or encoding throws DecodingError: no resampler lives on this side of the boundary.
+class WavDecoder : public Decoder {
+  public:
+    PreAnalyzedSong decode(const std::string &path) override {
+        auto fail = [&](const std::string &why) { return BlissError(BlissError::DecodingError, "while opening format for file '" + path + "': " + why + "."); };
+        std::FILE *f = std::fopen(path.c_str(), "rb");
+        if (!f) throw fail("cannot open");
+        std::vector<unsigned char> raw;
+        unsigned char buf[1 << 16];
+        for (size_t got; (got = std::fread(buf, 1, sizeof buf, f)) > 0;) raw.insert(raw.end(), buf, buf + got);
+        std::fclose(f);
+        auto u16 = [&](size_t o) { return static_cast<uint32_t>(raw[o] | (raw[o + 1] << 8)); };
+        auto u32 = [&](size_t o) { return static_cast<uint32_t>(raw[o]) | (static_cast<uint32_t>(raw[o + 1]) << 8) | (static_cast<uint32_t>(raw[o + 2]) << 16) | (static_cast<uint32_t>(raw[o + 3]) << 24); };
+        if (raw.size() < 12 || std::memcmp(raw.data(), "RIFF", 4) != 0 || std::memcmp(raw.data() + 8, "WAVE", 4) != 0) throw fail("not a RIFF/WAVE file");
+        uint32_t tag = 0, channels = 0, rate = 0, bits = 0;
+        size_t data_off = 0, data_len = 0;
+        for (size_t o = 12; o + 8 <= raw.size();) {
+            const size_t len = u32(o + 4), body = o + 8;
+            if (std::memcmp(raw.data() + o, "fmt ", 4) == 0 && len >= 16 && body + len <= raw.size()) {
+                tag = u16(body); channels = u16(body + 2); rate = u32(body + 4); bits = u16(body + 14);
+                if (tag == 0xFFFE && len >= 26) tag = u16(body + 24);  // WAVE_FORMAT_EXTENSIBLE: the sub-format's first two bytes
+            } else if (std::memcmp(raw.data() + o, "data", 4) == 0) {
+                data_off = body;
+                data_len = std::min(len, raw.size() - body);  // a truncated file: what is there
+                break;
+            }
+            o = body + len + (len & 1);
+        }
+        if (!channels || !data_off) throw fail("no fmt / data chunk");
+        if (rate != SAMPLE_RATE) throw fail("runs at " + std::to_string(rate) + " Hz: this backend holds no resampler, only 22050 Hz sources are taken");
+        if (channels > BLISS_B200_PCM_MAX_CHANNELS) throw fail(std::to_string(channels) + " channels");
+        const bool pcm = tag == 1 && (bits == 8 || bits == 16 || bits == 24 || bits == 32), flt = tag == 3 && bits == 32;
+        if (!pcm && !flt) throw fail("encoding " + std::to_string(tag) + " with " + std::to_string(bits) + " bits per sample");
+        const size_t width = bits / 8, n = data_len / (width * channels), count = n * channels;
+        const unsigned char *d = raw.data() + data_off;
+        PreAnalyzedSong p;
+        p.path = path;
+        p.duration_s = static_cast<double>(n) / rate;
+        p.pcm_channels = channels;
+        p.pcm_format = flt ? PcmFormat::F32 : (bits <= 16 ? PcmFormat::S16 : PcmFormat::S32);
+        p.pcm_frames.resize(count * (bits <= 16 ? 2 : 4));
+        if (bits == 16 || bits == 32) {
+            std::memcpy(p.pcm_frames.data(), d, p.pcm_frames.size());  // little-endian hosts only, like the rest of the library
+        } else if (bits == 8) {
+            for (size_t i = 0; i < count; i++) {
+                const int16_t v = static_cast<int16_t>((static_cast<int>(d[i]) - 128) * 256);
+                std::memcpy(p.pcm_frames.data() + 2 * i, &v, 2);
+            }
+        } else {  // 24
+            for (size_t i = 0; i < count; i++) {
+                const uint32_t v = (static_cast<uint32_t>(d[3 * i]) << 8) | (static_cast<uint32_t>(d[3 * i + 1]) << 16) | (static_cast<uint32_t>(d[3 * i + 2]) << 24);
+                std::memcpy(p.pcm_frames.data() + 4 * i, &v, 4);
+            }
+        }
+        return p;
     }
 };
 

@@ -7,7 +7,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <set>
+#include <unistd.h>
 
 #include "bliss_b200.hpp"
 
@@ -33,7 +35,7 @@ struct ToneDecoder : Decoder {  // a Decoder whose "files" are synthetic tones; 
         PreAnalyzedSong p;
         p.path = path;
         p.title = path;
-        const size_t n = is_short ? 4000 : 22050 * 12;
+        const size_t n = is_short ? 4000 : 22050 * 6;
         p.sample_array.resize(n);
         const double f = 220.0 * (1 + (int)path.size());
         for (size_t i = 0; i < n; i++)
@@ -164,6 +166,59 @@ int main() {
             analyze_batch_pcm({st.data()}, {q.size()}, PcmFormat::S16, 2, 44100);
             return 17;  // no resampler: must refuse
         } catch (const BlissError &) {
+        }
+        // WavDecoder: 22 050 Hz WAV files through the decoder pipeline, the file's own frames converted on the device
+        {
+            const char *tmp = std::getenv("TMPDIR");
+            const std::string dir = std::string(tmp ? tmp : "/tmp") + "/bliss_b200_host_mirror_" + std::to_string((long)::getpid());
+            auto write_wav = [&](const std::string &name, uint32_t tag, uint32_t channels, uint32_t rate, uint32_t bits, const void *data, size_t bytes) {
+                const std::string path = dir + "_" + name;
+                std::FILE *f = std::fopen(path.c_str(), "wb");
+                auto w32 = [&](uint32_t v) { std::fwrite(&v, 4, 1, f); };
+                auto w16 = [&](uint16_t v) { std::fwrite(&v, 2, 1, f); };
+                std::fwrite("RIFF", 1, 4, f); w32((uint32_t)(36 + bytes)); std::fwrite("WAVEfmt ", 1, 8, f); w32(16);
+                w16((uint16_t)tag); w16((uint16_t)channels); w32(rate); w32(rate * channels * bits / 8); w16((uint16_t)(channels * bits / 8)); w16((uint16_t)bits);
+                std::fwrite("data", 1, 4, f); w32((uint32_t)bytes);
+                std::fwrite(data, 1, bytes, f);
+                std::fclose(f);
+                return path;
+            };
+            std::vector<unsigned char> s24(3 * q.size());
+            std::vector<int32_t> s24_as_s32(q.size());
+            for (size_t i = 0; i < q.size(); i++) {
+                const int32_t v = (int32_t)q[i] * 256 + 5;  // a 24-bit value
+                s24[3 * i] = (unsigned char)(v & 255); s24[3 * i + 1] = (unsigned char)((v >> 8) & 255); s24[3 * i + 2] = (unsigned char)((v >> 16) & 255);
+                s24_as_s32[i] = (int32_t)((uint32_t)v << 8);
+            }
+            const std::vector<std::string> wavs = {
+                write_wav("mono16.wav", 1, 1, 22050, 16, q.data(), 2 * q.size()), write_wav("stereo16.wav", 1, 2, 22050, 16, st.data(), 2 * st.size()),
+                write_wav("mono24.wav", 1, 1, 22050, 24, s24.data(), s24.size()), write_wav("float.wav", 3, 1, 22050, 32, back.data(), 4 * back.size()),
+                write_wav("cd.wav", 1, 1, 44100, 16, q.data(), 2 * q.size()), dir + "_missing.wav"};
+            WavDecoder wd;
+            AnalysisOptions o2;
+            o2.number_cores = 2;
+            auto got = wd.analyze_paths(wavs, o2, 3);
+            auto r24 = analyze_batch_pcm({s24_as_s32.data()}, {s24_as_s32.size()}, PcmFormat::S32, 1);
+            if (got.size() != wavs.size()) return 50;
+            int songs_ok = 0, refused = 0;
+            for (auto &r : got) {
+                const std::string name = r.first.substr(dir.size() + 1);
+                if (auto *song = std::get_if<Song>(&r.second)) {
+                    songs_ok++;
+                    const std::vector<float> &v = song->analysis->as_vec();
+                    if (name == "mono16.wav" && v != std::get<Analysis>(r16[0]).as_vec()) return 51;
+                    if (name == "stereo16.wav" && v != std::get<Analysis>(rst[0]).as_vec()) return 52;
+                    if (name == "mono24.wav" && v != std::get<Analysis>(r24[0]).as_vec()) return 53;
+                    if (name == "float.wav" && v != std::get<Analysis>(r32[0]).as_vec()) return 54;
+                    if (std::fabs(song->duration_s - 6.0) > 1e-9) return 55;
+                } else {
+                    refused += std::get<BlissError>(r.second).kind == BlissError::DecodingError && (name == "cd.wav" || name == "missing.wav");
+                }
+            }
+            if (songs_ok != 4 || refused != 2) return 56;
+            if (wd.song_from_path(wavs[1]).analysis->as_vec() != std::get<Analysis>(rst[0]).as_vec()) return 57;
+            if (wd.decode(wavs[1]).mono() != mono) return 58;
+            for (const auto &w : wavs) std::remove(w.c_str());
         }
         // playlist: closest_to_songs keeps the seed first
         std::vector<float> cands;
