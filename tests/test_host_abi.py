@@ -194,6 +194,13 @@ def test_wav_decoder_keeps_the_codecs_frames(tmp_path, golden, monkeypatch):
     _write_wav(tmp_path / "mono32.wav", s24 * 256, 4)
     _write_wav(tmp_path / "cd.wav", s16, 2, rate=44100)
     (tmp_path / "junk.wav").write_bytes(b"not a wave file")
+    f32 = (s16[:7001] / np.float32(32768.0)).astype("<f4")   # IEEE float (format tag 3), odd data size + a trailing chunk
+    (tmp_path / "float.wav").write_bytes(b"RIFF" + (36 + f32.nbytes + 12).to_bytes(4, "little") + b"WAVEfmt " + (16).to_bytes(4, "little")
+                                         + np.array([3, 1], "<u2").tobytes() + np.array([22050, 88200], "<u4").tobytes()
+                                         + np.array([4, 32], "<u2").tobytes() + b"data" + f32.nbytes.to_bytes(4, "little")
+                                         + f32.tobytes() + b"LIST" + (4).to_bytes(4, "little") + b"INFO")
+    df = B.WavDecoder.decode(str(tmp_path / "float.wav")).pcm_frames
+    assert df.dtype == np.float32 and df.shape == (7001, 1) and np.array_equal(df[:, 0], f32)
     d = B.WavDecoder.decode(str(tmp_path / "mono16.wav"))
     assert d.pcm_frames.dtype == np.int16 and np.array_equal(d.pcm_frames[:, 0], s16) and d.sample_array.size == 0
     assert abs(d.duration - 30000 / 22050) < 1e-9 and d.path.endswith("mono16.wav")
