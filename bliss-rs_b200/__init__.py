@@ -11,10 +11,12 @@ from .song import (AnalysisIndex, AnalysisIndexv1, Analysis, AnalysisOptions, Bl
                    NUMBER_FEATURES, SAMPLE_RATE, CHANNELS, analyze_batch, analyze_batch_pcm, pcm_to_mono)
 from .song import analyze_decoded
 from .decoder import WavDecoder
+from .cue import BlissCue
+from . import cue
 from . import playlist
 from . import library
 
 __all__ = ["native", "playlist", "library", "AnalysisIndex", "AnalysisIndexv1", "Analysis", "AnalysisOptions", "BlissError",
            "AnalysisError", "DecodingError", "ProviderError", "Decoder", "FeaturesVersion", "PreAnalyzedSong",
            "Song", "NUMBER_FEATURES", "SAMPLE_RATE", "CHANNELS", "analyze_batch", "analyze_batch_pcm", "pcm_to_mono", "analyze_decoded",
-           "WavDecoder"]
+           "WavDecoder", "BlissCue", "cue"]

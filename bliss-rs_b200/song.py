@@ -376,6 +376,14 @@ class Decoder:
                 for path in chunk:
                     if stop.is_set():
                         break
+                    if os.path.splitext(str(path))[1].lower() == ".cue":  # :305-318: every track of the sheet is an item
+                        from .cue import BlissCue
+                        try:
+                            for song in BlissCue(cls).songs_from_path_with_options(path, analysis_options):
+                                results.put((path, song))
+                        except BlissError as e:
+                            results.put((path, e))
+                        continue
                     try:
                         hand_over((path, cls.decode(path)))
                     except BlissError as e:  # decoding errors are items too

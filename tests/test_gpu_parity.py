@@ -564,6 +564,16 @@ def test_wav_files_through_the_decoder_pipeline(tmp_path, golden, pcm_piano):
     assert np.array_equal(got[paths[2]].analysis.as_arr1(), B.Song.analyze(O.pcm_to_mono(s24 * 256)).as_arr1())
     assert isinstance(got[paths[3]], B.DecodingError) and isinstance(got[paths[4]], B.AnalysisError)
     assert abs(got[paths[0]].duration - s16.size / 22050.0) < 1e-9
+    # a CUE sheet over one of the files (src/cue.rs:208-243): both tracks are slices of ONE decoded buffer analysed in one
+    # call; each must be Song::analyze of that slice of the decoder's samples, bit for bit
+    (tmp_path / "stereo.cue").write_text('PERFORMER "P"\nTITLE "T"\nFILE "stereo.wav" WAVE\n  TRACK 01 AUDIO\n    TITLE "one"\n'
+                                         '    INDEX 01 0:00:00\n  TRACK 02 AUDIO\n    TITLE "two"\n    INDEX 01 0:02:37\n')
+    cut = int(np.float32(np.float32(2) + np.float32(37 * 1_000_000_000 // 75) / np.float32(1e9)) * np.float32(22050))
+    tracks = B.BlissCue(B.WavDecoder).songs_from_path(str(tmp_path / "stereo.cue"))
+    mono = O.pcm_to_mono(st)
+    assert [t.title for t in tracks] == ["one", "two"] and 54000 < cut < 55000
+    assert np.array_equal(tracks[0].analysis.as_arr1(), B.Song.analyze(mono[:cut]).as_arr1())
+    assert np.array_equal(tracks[1].analysis.as_arr1(), B.Song.analyze(mono[cut:]).as_arr1())
     # ... and on into the reference's on-disk format (src/library.rs:500-529, 1544-1670): files -> decoder threads ->
     # GPU batches -> SQLite rows; the two refused files are rows of the failed-song kind, a second run is a no-op
     lib = B.library.Library(str(tmp_path / "songs.db"), decoder=B.WavDecoder)

@@ -240,6 +240,81 @@ def test_wav_decoder_keeps_the_codecs_frames(tmp_path, golden, monkeypatch):
     assert sorted(calls) == [("f32", 1), ("pcm", "<i2", 1, 1)] and res[0].as_arr1()[0] == 0.0 and res[1].as_arr1()[0] > 1.0
 
 
+CUE_SHEET = """REM GENRE Random
+REM DATE 2022
+REM DISCNUMBER 1
+PERFORMER "Polochon_street"
+TITLE "Album for CUE test"
+FILE "%s" WAVE
+  TRACK 01 AUDIO
+    TITLE "Renaissance"
+    PERFORMER "David TMX"
+    INDEX 01 0:00:00
+  TRACK 02 AUDIO
+    TITLE "Piano"
+    PERFORMER "Polochon_street"
+    INDEX 01 0:11:05
+  TRACK 03 AUDIO
+    TITLE "Tone"
+    PERFORMER "Polochon_street"
+    INDEX 01 0:16:69
+
+FILE "not-existing.wav" WAVE
+  TRACK 01 AUDIO
+    TITLE "Nope"
+    PERFORMER "Charlie"
+    INDEX 01 0:00:00
+  TRACK 02 AUDIO
+    TITLE "Nope"
+    PERFORMER "Charlie"
+    INDEX 01 0:10:00
+"""  # data/testcue.cue of the reference, the audio file's name left open
+
+
+def test_cue_sheet_tracks_are_slices_of_one_decoded_buffer(tmp_path, monkeypatch):
+    """bliss-rs_b200/cue.py against src/cue.rs and its test (:262-420): track boundaries in f32 exactly as the
+    reference computes them -- the three durations its test asserts for data/testcue.cue pin 0:11:05 -> sample 244 020
+    and 0:16:69 -> 373 086 on the 496 272-sample file --, tags and paths of the songs, a missing audio file as an
+    error item, every slice of the sheet in ONE analysis call, .cue paths inside Decoder::analyze_paths."""
+    total = 496272
+    rng = np.random.default_rng(0)
+    s16 = rng.integers(-3000, 3000, total).astype(np.int16)
+    _write_wav(tmp_path / "album.wav", s16, 2)
+    sheet = tmp_path / "album.cue"
+    sheet.write_text(CUE_SHEET % "album.wav")
+    calls = []
+
+    def fake(songs, opts=None):
+        calls.append([np.asarray(p.pcm_frames)[:, 0].copy() for p in songs])
+        return [B.Analysis(np.full(23, float(len(p.pcm_frames)))) for p in songs]
+
+    monkeypatch.setattr(B.cue, "analyze_decoded", fake)
+    got = B.BlissCue(B.WavDecoder).songs_from_path(str(sheet))
+    assert len(got) == 4 and len(calls) == 1 and len(calls[0]) == 3
+    for piece, (a, b) in zip(calls[0], ((0, 244020), (244020, 373086), (373086, total))):
+        assert np.array_equal(piece, s16[a:b])
+    durations = [np.float32(11.066666603), np.float32(5.853333473), np.float32(5.586666584)]   # src/cue.rs:311, 356, 402
+    for i, (song, title, artist) in enumerate(zip(got, ("Renaissance", "Piano", "Tone"), ("David TMX", "Polochon_street", "Polochon_street"))):
+        assert isinstance(song, B.Song) and song.path == "%s/CUE_TRACK%03d" % (sheet, i + 1)
+        assert (song.title, song.artist, song.album, song.album_artist) == (title, artist, "Album for CUE test", "Polochon_street")
+        assert (song.track_number, song.disc_number, song.genre) == (i + 1, 1, "Random")
+        assert np.float32(song.duration) == durations[i]
+        assert song.cue_info.cue_path == str(sheet) and song.cue_info.audio_file_path == str(tmp_path / "album.wav")
+        assert song.analysis.as_arr1()[0] == float(len(calls[0][i]))            # rows stay with their tracks
+    assert isinstance(got[3], B.DecodingError)                                   # not-existing.wav: one error for the file
+    with pytest.raises(B.DecodingError):
+        B.BlissCue(B.WavDecoder).songs_from_path(str(tmp_path / "nope.cue"))
+    # a track that starts behind the end of the audio: an error item here (the reference's slice would panic)
+    (tmp_path / "late.cue").write_text('FILE "album.wav" WAVE\n TRACK 01 AUDIO\n  INDEX 01 0:00:00\n TRACK 02 AUDIO\n  INDEX 01 9:00:00\n')
+    late = B.BlissCue(B.WavDecoder).songs_from_path(str(tmp_path / "late.cue"))
+    assert len(late) == 2 and all(isinstance(x, B.DecodingError) for x in late)
+    # Decoder::analyze_paths: every track of a .cue path is an item under the sheet's path (src/song/decoder.rs:305-318)
+    monkeypatch.setattr(B.song, "analyze_decoded", fake)
+    items = list(B.WavDecoder.analyze_paths_with_options([str(tmp_path / "album.wav"), str(sheet)], B.AnalysisOptions(number_cores=2)))
+    assert sorted(p for p, _ in items) == sorted([str(tmp_path / "album.wav")] + [str(sheet)] * 4)
+    assert sum(isinstance(r, B.Song) for _, r in items) == 4
+
+
 def test_fft_index_logic_on_host(tmp_path):
     """tests/cpu_emul/emul_fft.cu runs the warp / CTA FFT passes of pvoc512.cuh and rfft8192.cuh (incl. the
     fused pass 3 + mirror-pair epilogue) thread by thread on the host and compares with an f64 DFT."""
