@@ -362,18 +362,22 @@ def test_c_abi_on_the_host_emulated_library(tmp_path):
     env = dict(os.environ, BLISS_B200_SO=so, CUDA_VISIBLE_DEVICES="")
     pick = ("golden_clip_v2 or too_short or s16_ingest or pcm_feed or distance_known or distance_matrix_bit or "
             "closest_to_songs or dedup or stft512_magnitudes or experimental_stft_pair or cue_style or wav_files")
-    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
-                          "-p", "no:cacheprovider", "--tb=short", "-k", pick], capture_output=True, text=True, env=env, cwd=ROOT)
-    tail = out.stdout[-1500:] + out.stderr[-500:]
-    assert out.returncode == 0, tail
-    m = re.search(r"(\d+) passed", out.stdout)
-    assert m and int(m.group(1)) >= 10 and "failed" not in out.stdout, tail
-    # ... and the C++17 host mirror (include/bliss_b200.hpp: Song, Decoder, analyze_batch[_s16|_pcm], playlist) end to end
+    # the C++17 host mirror (include/bliss_b200.hpp: Song, Decoder, WavDecoder, analyze_batch[_s16|_pcm], playlist) end to
+    # end, started first and left running beside the Python slice
     exe = str(tmp_path / "host_mirror_emu")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
                            os.path.join(ROOT, "tests", "cpp", "host_mirror.cpp"), "-o", exe, so, "-Wl,-rpath," + str(tmp_path)])
-    run = subprocess.run([exe], capture_output=True, text=True)
-    assert run.returncode == 0 and run.stdout.strip().endswith("OK"), run.stdout + run.stderr
+    mirror = subprocess.Popen([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=dict(env, TMPDIR=str(tmp_path)))
+    workers = str(max(1, min(4, (os.cpu_count() or 2) - 1)))  # the slice's tests are independent processes' worth of work
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
+                          "-p", "no:cacheprovider", "--tb=short", "-n", workers, "-k", pick],
+                         capture_output=True, text=True, env=env, cwd=ROOT)
+    tail = out.stdout[-1500:] + out.stderr[-500:]
+    mirror_out, mirror_err = mirror.communicate(timeout=1200)
+    assert out.returncode == 0, tail
+    m = re.search(r"(\d+) passed", out.stdout)
+    assert m and int(m.group(1)) >= 10 and "failed" not in out.stdout, tail
+    assert mirror.returncode == 0 and mirror_out.strip().endswith("OK"), mirror_out + mirror_err
 
 
 def test_kernel_sources_reproduce_the_reference_golden_vector(tmp_path, golden):
