@@ -313,6 +313,17 @@ def test_cue_sheet_tracks_are_slices_of_one_decoded_buffer(tmp_path, monkeypatch
     items = list(B.WavDecoder.analyze_paths_with_options([str(tmp_path / "album.wav"), str(sheet)], B.AnalysisOptions(number_cores=2)))
     assert sorted(p for p, _ in items) == sorted([str(tmp_path / "album.wav")] + [str(sheet)] * 4)
     assert sum(isinstance(r, B.Song) for _, r in items) == 4
+    # ... and in the Library: "passing vec![file.cue] will add individual tracks with the cue_info field set in the
+    # database" (src/library.rs:891-892); the sheet's missing second FILE is a failed-song row under the sheet's path
+    lib = B.library.Library(str(tmp_path / "songs.db"), decoder=B.WavDecoder)
+    assert lib.update_library([str(sheet)]) == (3, 1)
+    stored = sorted(lib.songs_from_library(), key=lambda x: x.bliss_song.path)
+    assert [x.bliss_song.path for x in stored] == ["%s/CUE_TRACK%03d" % (sheet, i) for i in (1, 2, 3)]
+    assert all(x.bliss_song.cue_info.cue_path == str(sheet) and x.bliss_song.cue_info.audio_file_path == str(tmp_path / "album.wav")
+               for x in stored)
+    assert [x.bliss_song.title for x in stored] == ["Renaissance", "Piano", "Tone"]
+    assert [f.song_path for f in lib.get_failed_songs()] == [str(sheet)]
+    lib.close()
 
 
 def test_fft_index_logic_on_host(tmp_path):
