@@ -16,8 +16,8 @@ Prints ONE JSON line on rank 0 (see the task contract): value, e2e (same metric 
 C-ABI call with pinned HOST f32 buffers, H2D + D2H inside the timed region), e2e_s16 (the same
 through bliss_b200_analyze_batch_s16: 16-bit host buffers converted on the device; an extra, the
 metric itself is quoted on f32 PCM), roofline of the dominant kernel (CUDA-event timed inside this
-run; roofline.traffic = its ncu DRAM bytes and the percentages of the resources that bind it, from
-profiles/ncu_traffic.json), cpu_baseline (oracle on the host cores), clocks, gpu_launches.
+run; roofline.traffic = its ncu DRAM bytes per launch, roofline.traffic_detail = the same in GB beside the
+algorithmic bytes and the percentages of the resources that bind it, from profiles/ncu_traffic.json), cpu_baseline (oracle on the host cores), clocks, gpu_launches.
 """
 import argparse
 import ctypes
@@ -359,23 +359,26 @@ def main():
                         "algorithmic_gbs": (b / 1e9) / (avg_ms / 1e3) if avg_ms > 0 else None})
     kernels.sort(key=lambda k: -k["share"])
     dom = kernels[0]
-    traffic = None
+    traffic = traffic_detail = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         try:
             ent = json.load(open(tp)).get(dom["kernel"])
-            # measured DRAM bytes per song (ncu --set full, profiles/) x songs per launch, in GB like `achieved`
-            traffic = {"gb_per_launch": ent["bytes_per_song"] * S / 1e9,
-                       "algorithmic_gb_per_launch": alg.get(dom["kernel"], 0) * S / 1e9,
-                       "source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum)"}
+            # measured DRAM bytes per song (ncu --set full, profiles/) x songs per launch: bytes per launch, a plain
+            # number like the algorithmic bytes behind `achieved`
+            traffic = float(ent["bytes_per_song"]) * S
+            traffic_detail = {"unit": "bytes per launch", "gb_per_launch": traffic / 1e9,
+                              "algorithmic_gb_per_launch": alg.get(dom["kernel"], 0) * S / 1e9,
+                              "source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum)"}
             # what the same ncu capture says the kernel is actually bound by (percent of peak)
             for k in ("l1tex_data_pipe_pct", "issue_active_pct", "dram_pct", "lts_pct"):
                 if k in ent:
-                    traffic[k] = ent[k]
+                    traffic_detail[k] = ent[k]
         except Exception:
-            traffic = None
+            traffic = traffic_detail = None
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["algorithmic_gbs"], "peak": peak,
-                "unit": "GB/s", "frac": dom["algorithmic_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": dom["algorithmic_gbs"] / peak, "traffic": traffic,
+                "traffic_detail": traffic_detail, "peak_source": peak_src,
                 "avg_launch_ms": dom["avg_ms"], "share_of_step": dom["share"],
                 "note": "FFT work: the kernel is FP32-pipe / shared-memory bound at algorithmic-minimum traffic "
                         "(DESIGN.md); the HBM roofline is reported because BASELINE.json fixes it",
