@@ -10,9 +10,11 @@
 //   distances, closest_to_songs, ...       src/playlist.rs:65-326
 #pragma once
 #include <algorithm>
+#include <cctype>
 #include <condition_variable>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <exception>
@@ -125,6 +127,8 @@ struct Song {
     double duration_s = 0.;
     std::optional<Analysis> analysis;
     FeaturesVersion features_version = LATEST;
+    struct CueInfo { std::string cue_path, audio_file_path; };  // src/cue.rs: CueInfo
+    std::optional<CueInfo> cue_info;                            // set when the song was cut out of a CUE sheet
 
     // Song::analyze / analyze_with_options, src/song/mod.rs:403-508
     static Analysis analyze(const float *samples, size_t n) { return analyze_with_options(samples, n, AnalysisOptions{}); }
@@ -308,6 +312,13 @@ class Decoder {
         auto worker = [&](size_t lo, size_t hi) {
             for (size_t i = lo; i < hi; i++) {
                 try {
+                    const std::string &pth = paths[i];
+                    if (pth.size() >= 4 && cue_extension(pth.substr(pth.size() - 4))) {  // :305-318: every track of the sheet is an item
+                        auto items = songs_from_cue(pth, o);
+                        std::lock_guard<std::mutex> lk(mu);
+                        for (auto &it : items) out.emplace_back(pth, std::move(it));
+                        continue;
+                    }
                     PreAnalyzedSong p = decode(paths[i]);
                     std::unique_lock<std::mutex> lk(mu);
                     not_full.wait(lk, [&] { return decoded.size() < 2 * batch_songs || failure; });
@@ -367,6 +378,11 @@ class Decoder {
     }
 
   private:
+    static bool cue_extension(std::string e) {
+        for (char &c : e) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
+        return e == ".cue";
+    }
+    inline std::vector<std::variant<Song, BlissError>> songs_from_cue(const std::string &path, const AnalysisOptions &o);  // BlissCue, below
     static Song to_song(const PreAnalyzedSong &p, Analysis a, const AnalysisOptions &o) {  // decoder.rs:85-100
         Song s;
         s.path = p.path; s.artist = p.artist; s.album_artist = p.album_artist; s.title = p.title; s.album = p.album;
@@ -439,6 +455,193 @@ class WavDecoder : public Decoder {
         return p;
     }
 };
+
+// ---- src/cue.rs -----------------------------------------------------------------------------------
+// BlissCue<D>: the songs of a CUE sheet, cut out of ONE decoded buffer per FILE of the sheet (:208-243); here the
+// slices of all tracks of all files go to the device in one batched call.  Sheet parsing is the rcue crate's job in
+// the reference (0.1.3, not vendored): restated for the commands src/cue.rs reads -- REM comments, PERFORMER, TITLE,
+// FILE, TRACK, INDEX mm:ss:ff at 75 frames per second -- in non-strict mode.  Track boundaries as the reference
+// computes them: (index.as_secs_f32() * SAMPLE_RATE as f32) as usize, in f32 (:212-213, :231).
+namespace cue {
+struct Track {
+    std::string no;
+    std::optional<std::string> title, performer;
+    std::vector<std::pair<std::string, std::pair<uint64_t, uint32_t>>> indices;  // (index number, (seconds, nanoseconds))
+};
+struct CueFile { std::string file; std::vector<Track> tracks; };
+struct Cue {
+    std::optional<std::string> performer, title;
+    std::vector<std::pair<std::string, std::string>> comments;
+    std::vector<CueFile> files;
+};
+namespace detail {
+inline std::string trim(const std::string &x) {
+    const size_t a = x.find_first_not_of(" \t\r\n"), b = x.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? std::string() : x.substr(a, b - a + 1);
+}
+inline std::string unquote(const std::string &x) {
+    const std::string t = trim(x);
+    return t.size() >= 2 && t.front() == '"' && t.back() == '"' ? t.substr(1, t.size() - 2) : t;
+}
+inline std::string upper(std::string x) {
+    for (char &c : x) c = static_cast<char>(std::toupper(static_cast<unsigned char>(c)));
+    return x;
+}
+}  // namespace detail
+inline Cue parse(const std::string &text) {
+    Cue cue;
+    bool in_file = false, in_track = false;
+    size_t pos = 0;
+    while (pos <= text.size()) {
+        const size_t nl = text.find('\n', pos);
+        std::string line = detail::trim(text.substr(pos, nl == std::string::npos ? std::string::npos : nl - pos));
+        pos = nl == std::string::npos ? text.size() + 1 : nl + 1;
+        if (line.compare(0, 3, "\xEF\xBB\xBF") == 0) line = line.substr(3);
+        if (line.empty()) continue;
+        const size_t sp = line.find(' ');
+        const std::string cmd = detail::upper(line.substr(0, sp)), rest = sp == std::string::npos ? std::string() : detail::trim(line.substr(sp + 1));
+        if (cmd == "REM") {
+            const size_t k = rest.find(' ');
+            cue.comments.emplace_back(rest.substr(0, k), k == std::string::npos ? std::string() : detail::unquote(rest.substr(k + 1)));
+        } else if (cmd == "PERFORMER" || cmd == "TITLE") {
+            std::optional<std::string> *dst = nullptr;
+            if (in_track) dst = cmd == "TITLE" ? &cue.files.back().tracks.back().title : &cue.files.back().tracks.back().performer;
+            else if (!in_file) dst = cmd == "TITLE" ? &cue.title : &cue.performer;
+            if (dst) *dst = detail::unquote(rest);
+        } else if (cmd == "FILE" && !rest.empty()) {
+            std::string name;
+            if (rest[0] == '"') {
+                const size_t q = rest.find('"', 1);
+                if (q == std::string::npos) continue;
+                name = rest.substr(1, q - 1);
+            } else {
+                name = rest.substr(0, rest.find(' '));
+            }
+            cue.files.push_back(CueFile{name, {}});
+            in_file = true;
+            in_track = false;
+        } else if (cmd == "TRACK" && in_file && !rest.empty()) {
+            Track t;
+            t.no = rest.substr(0, rest.find(' '));
+            cue.files.back().tracks.push_back(t);
+            in_track = true;
+        } else if (cmd == "INDEX" && in_track) {
+            unsigned long long mm = 0, ss = 0, ff = 0;
+            char no[16] = {0};
+            if (std::sscanf(rest.c_str(), "%15s %llu:%llu:%llu", no, &mm, &ss, &ff) == 4)
+                cue.files.back().tracks.back().indices.emplace_back(no, std::make_pair(static_cast<uint64_t>(mm * 60 + ss), static_cast<uint32_t>(ff * 1000000000ull / 75)));
+        }
+    }
+    return cue;
+}
+inline size_t sample_index(const std::pair<uint64_t, uint32_t> &ts) {  // Duration::as_secs_f32() * SAMPLE_RATE as f32, as usize
+    volatile float secs = static_cast<float>(ts.first) + static_cast<float>(ts.second) / 1000000000.0f;
+    volatile float idx = secs * static_cast<float>(SAMPLE_RATE);
+    return static_cast<size_t>(idx);
+}
+}  // namespace cue
+
+class BlissCue {
+  public:
+    explicit BlissCue(Decoder &d) : decoder_(d) {}
+    using Item = std::variant<Song, BlissError>;
+    // songs_from_path_with_options, :85-106: one entry per track -- a Song with cue_info, or the BlissError the
+    // reference would have pushed; a sheet that cannot be read throws DecodingError (:110-116).
+    std::vector<Item> songs_from_path(const std::string &path, const AnalysisOptions &o = {}) {
+        std::FILE *f = std::fopen(path.c_str(), "rb");
+        if (!f) throw BlissError(BlissError::DecodingError, "when opening CUE file '" + path + "'");
+        std::string text;
+        char buf[4096];
+        for (size_t got; (got = std::fread(buf, 1, sizeof buf, f)) > 0;) text.append(buf, got);
+        std::fclose(f);
+        const cue::Cue sheet = cue::parse(text);
+        std::optional<std::string> genre;
+        std::optional<int> disc_number;
+        for (const auto &c : sheet.comments) {
+            const std::string k = cue::detail::upper(c.first);
+            if (k == "GENRE" && !genre) genre = c.second;
+            if ((k == "DISCNUMBER" || k == "DISC") && !disc_number) {
+                char *end = nullptr;
+                const long v = std::strtol(c.second.c_str(), &end, 10);
+                if (end != c.second.c_str() && *end == 0) disc_number = static_cast<int>(v);
+                else break;
+            }
+        }
+        const size_t slash = path.find_last_of('/');
+        const std::string parent = slash == std::string::npos ? std::string() : path.substr(0, slash + 1);
+        std::vector<Item> out;
+        std::vector<PreAnalyzedSong> pieces;  // what goes to the device, in the order of `slots`
+        std::vector<size_t> slots;
+        for (const cue::CueFile &cf : sheet.files) {
+            const std::string audio = parent + cf.file;
+            PreAnalyzedSong decoded;
+            try {
+                decoded = decoder_.decode(audio);
+            } catch (const BlissError &e) {
+                out.emplace_back(e);
+                continue;
+            }
+            const size_t total = decoded.n_frames();
+            if (total == 0) {
+                out.emplace_back(BlissError(BlissError::DecodingError, "empty audio file associated to CUE sheet"));
+                continue;
+            }
+            const size_t frame_bytes = decoded.pcm_channels ? (decoded.pcm_format == PcmFormat::S16 ? 2 : 4) * decoded.pcm_channels : 0;
+            const size_t n_tracks = cf.tracks.size();
+            for (size_t i = 0; i < n_tracks; i++) {
+                const cue::Track &t = cf.tracks[i];
+                if (t.indices.empty()) continue;
+                size_t end = total;  // the last track runs to the end of the file (:229-241)
+                if (i + 1 < n_tracks) {
+                    if (cf.tracks[i + 1].indices.empty()) continue;
+                    end = cue::sample_index(cf.tracks[i + 1].indices.front().second);
+                }
+                const size_t start = cue::sample_index(t.indices.front().second);
+                if (!(start <= end && end <= total)) {  // the reference's slice would panic here
+                    out.emplace_back(BlissError(BlissError::DecodingError, "CUE track " + t.no + " of '" + path + "' lies outside its audio file"));
+                    continue;
+                }
+                Song sg;
+                char name[32];
+                std::snprintf(name, sizeof name, "/CUE_TRACK%03zu", i + 1);
+                sg.path = path + name;
+                sg.album = sheet.title; sg.artist = t.performer; sg.album_artist = sheet.performer; sg.title = t.title;
+                sg.genre = genre; sg.disc_number = disc_number; sg.features_version = o.features_version;
+                char *endp = nullptr;
+                const long no = std::strtol(t.no.c_str(), &endp, 10);
+                if (endp != t.no.c_str() && *endp == 0) sg.track_number = static_cast<int>(no);
+                sg.duration_s = static_cast<double>(static_cast<float>(end - start) / static_cast<float>(SAMPLE_RATE));
+                sg.cue_info = Song::CueInfo{path, audio};
+                PreAnalyzedSong piece;
+                if (decoded.pcm_channels) {
+                    piece.pcm_channels = decoded.pcm_channels;
+                    piece.pcm_format = decoded.pcm_format;
+                    piece.pcm_frames.assign(decoded.pcm_frames.begin() + start * frame_bytes, decoded.pcm_frames.begin() + end * frame_bytes);
+                } else {
+                    piece.sample_array.assign(decoded.sample_array.begin() + start, decoded.sample_array.begin() + end);
+                }
+                pieces.push_back(std::move(piece));
+                slots.push_back(out.size());
+                out.emplace_back(std::move(sg));
+            }
+        }
+        if (!pieces.empty()) {
+            std::vector<AnalysisResult> res = analyze_decoded(pieces, o);
+            for (size_t k = 0; k < res.size(); k++) {
+                if (auto *a = std::get_if<Analysis>(&res[k])) std::get<Song>(out[slots[k]]).analysis = std::move(*a);
+                else out[slots[k]] = std::get<BlissError>(res[k]);
+            }
+        }
+        return out;
+    }
+
+  private:
+    Decoder &decoder_;
+};
+
+inline std::vector<std::variant<Song, BlissError>> Decoder::songs_from_cue(const std::string &path, const AnalysisOptions &o) {
+    return BlissCue(*this).songs_from_path(path, o);
+}
 
 // ---- src/playlist.rs ----------------------------------------------------------------------------
 namespace playlist {

@@ -79,6 +79,23 @@ int main() {
         }
         if (refused != 3) return 35;
     }
+    // src/cue.rs: the reference's test sheet (data/testcue.cue), parsed; 0:11:05 -> sample 244 020 and 0:16:69 -> 373 086,
+    // the boundaries behind the durations its test asserts (:311, :356, :402)
+    const std::string sheet_text =
+        "REM GENRE Random\nREM DATE 2022\nREM DISCNUMBER 1\nPERFORMER \"Polochon_street\"\nTITLE \"Album for CUE test\"\n"
+        "FILE \"%s\" WAVE\n  TRACK 01 AUDIO\n    TITLE \"Renaissance\"\n    PERFORMER \"David TMX\"\n    INDEX 01 0:00:00\n"
+        "  TRACK 02 AUDIO\n    TITLE \"Piano\"\n    PERFORMER \"Polochon_street\"\n    INDEX 01 0:11:05\n"
+        "  TRACK 03 AUDIO\n    TITLE \"Tone\"\n    PERFORMER \"Polochon_street\"\n    INDEX 01 0:16:69\n\n"
+        "FILE \"not-existing.wav\" WAVE\n  TRACK 01 AUDIO\n    TITLE \"Nope\"\n    PERFORMER \"Charlie\"\n    INDEX 01 0:00:00\n";
+    {
+        const cue::Cue c = cue::parse(sheet_text);
+        if (c.files.size() != 2 || c.files[0].tracks.size() != 3 || c.files[0].file != "%s" || c.files[1].file != "not-existing.wav") return 60;
+        if (*c.performer != "Polochon_street" || *c.title != "Album for CUE test" || c.comments.size() != 3 || c.comments[2].second != "1") return 61;
+        const cue::Track &t2 = c.files[0].tracks[1];
+        if (t2.no != "02" || *t2.title != "Piano" || *t2.performer != "Polochon_street" || t2.indices.size() != 1) return 62;
+        if (cue::sample_index(t2.indices[0].second) != 244020 || cue::sample_index(c.files[0].tracks[2].indices[0].second) != 373086) return 63;
+        if ((float)244020 / 22050.f != 11.066666603f || (float)(373086 - 244020) / 22050.f != 5.853333473f) return 64;
+    }
     ToneDecoder dec;
     try {
         const Song s = dec.song_from_path("a");
@@ -218,6 +235,34 @@ int main() {
             if (songs_ok != 4 || refused != 2) return 56;
             if (wd.song_from_path(wavs[1]).analysis->as_vec() != std::get<Analysis>(rst[0]).as_vec()) return 57;
             if (wd.decode(wavs[1]).mono() != mono) return 58;
+            // a CUE sheet over the stereo file: both tracks are slices of one decoded buffer, analysed in one call, and
+            // equal the analysis of the same slices of the down-mixed samples; .cue paths inside analyze_paths
+            {
+                std::string text = sheet_text.substr(0, sheet_text.find("  TRACK 03"));
+                const std::string wav_name = wavs[1].substr(wavs[1].find_last_of('/') + 1);
+                text.replace(text.find("%s"), 2, wav_name);
+                text.replace(text.find("0:11:05"), 7, "0:02:37");
+                const std::string cue_path = dir + "_album.cue";
+                std::FILE *cf = std::fopen(cue_path.c_str(), "wb");
+                std::fwrite(text.data(), 1, text.size(), cf);
+                std::fclose(cf);
+                const size_t cut = cue::sample_index({2, 37ull * 1000000000ull / 75});
+                auto tracks = BlissCue(wd).songs_from_path(cue_path);
+                auto direct = analyze_batch({mono.data(), mono.data() + cut}, {cut, mono.size() - cut});
+                if (tracks.size() != 2 || cut < 54000 || cut > 55000) return 70;
+                for (int k = 0; k < 2; k++) {
+                    const Song *sg = std::get_if<Song>(&tracks[k]);
+                    if (!sg || sg->analysis->as_vec() != std::get<Analysis>(direct[k]).as_vec()) return 71;
+                    if (sg->path != cue_path + (k ? "/CUE_TRACK002" : "/CUE_TRACK001") || *sg->title != (k ? "Piano" : "Renaissance")) return 72;
+                    if (*sg->album != "Album for CUE test" || *sg->album_artist != "Polochon_street" || *sg->genre != "Random" || *sg->disc_number != 1 || *sg->track_number != k + 1) return 73;
+                    if (sg->cue_info->cue_path != cue_path || sg->cue_info->audio_file_path != wavs[1]) return 74;
+                }
+                auto items = wd.analyze_paths({wavs[0], cue_path}, o2, 3);
+                int under_sheet = 0;
+                for (auto &r : items) under_sheet += r.first == cue_path && std::holds_alternative<Song>(r.second);
+                if (items.size() != 3 || under_sheet != 2) return 75;
+                std::remove(cue_path.c_str());
+            }
             for (const auto &w : wavs) std::remove(w.c_str());
         }
         // playlist: closest_to_songs keeps the seed first
