@@ -590,7 +590,31 @@ def test_wav_files_through_the_decoder_pipeline(tmp_path, golden, pcm_piano):
 # are OFF by default, validated on the host only (tests/cpu_emul, tests/test_host_abi.py), and their tests below
 # have never met hardware.  Non-strict xfail keeps a defect in code that is not on the product path from masking
 # the parity suite of the code that is; an XPASS is the expected outcome and promotes the cut to a plain test.
-experimental = pytest.mark.xfail(reason="experimental kernel variant, first hardware run", strict=False)
+_xfail_experimental = pytest.mark.xfail(reason="experimental kernel variant, first hardware run", strict=False)
+
+
+def experimental(fn):
+    """... and each of them runs in a CHILD pytest process with a time limit: a kernel that has never met hardware may
+    fault (a sticky CUDA error would fail every later test of this process) or hang (and take the whole GPU run
+    with it); the child is killed at the limit and the test reports xfail.  The child runs the body for real
+    (--runxfail), its output is passed on."""
+    import functools
+    import os
+    import subprocess
+    import sys
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        if os.environ.get("BLISS_B200_EXPERIMENTAL_CHILD") == "1":
+            return fn(*args, **kwargs)
+        out = subprocess.run([sys.executable, "-m", "pytest", "%s::%s" % (os.path.abspath(__file__), fn.__name__), "-q", "-s", "-m", "gpu",
+                              "-p", "no:cacheprovider", "--runxfail", "--tb=short"],
+                             env=dict(os.environ, BLISS_B200_EXPERIMENTAL_CHILD="1"), capture_output=True, text=True, timeout=900,
+                             cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        print(out.stdout[-3000:])
+        assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-1000:]
+
+    return _xfail_experimental(wrapper)
 
 
 @experimental
