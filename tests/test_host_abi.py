@@ -721,6 +721,7 @@ def test_cpp_host_mirror_builds_and_refuses_to_run_without_gpu(tmp_path):
 def test_cpp_host_mirror_on_gpu(tmp_path):
     """the same program on a GPU box: Song::analyze, the Decoder batching seam (errors as items), the 16-bit
     entry point and closest_to_songs through the C++ mirror"""
-    out = subprocess.run([_build_cpp_mirror(tmp_path)], capture_output=True, text=True)
+    out = subprocess.run([_build_cpp_mirror(tmp_path)], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, TMPDIR=str(tmp_path)))
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert out.stdout.strip() == "OK"
