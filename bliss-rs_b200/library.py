@@ -66,6 +66,10 @@ class LibrarySong:
     bliss_song: Song
     extra_info: Any = None
 
+    def as_ref(self) -> Song:
+        """impl AsRef<Song> for LibrarySong<T>"""
+        return self.bliss_song
+
 
 @dataclass
 class ProcessingError:
@@ -190,6 +194,67 @@ class Library:
             "order by feature_index", (song_path,))]
         ls.bliss_song.analysis = self._analysis(values, ls.bliss_song.features_version)
         return ls
+
+    def songs_from_album(self, album_title: str) -> List[LibrarySong]:
+        """src/library.rs:1379-1412: the analysed songs of one album, by (disc, track)"""
+        ver = int(self.analysis_options.features_version)
+        rows = self.conn.execute(self._SONG_SELECT + "where album = ? and analyzed = true and version = ? "
+                                 "order by disc_number, track_number", (album_title, ver)).fetchall()
+        if not rows:
+            raise ProviderError("target album was not found in the database.")
+        out = []
+        for row in rows:
+            ls = self._song_from_row(row)
+            values = [r[0] for r in self.conn.execute("select feature from feature where song_id = ? order by feature_index", (row[13],))]
+            ls.bliss_song.analysis = self._analysis(values, ls.bliss_song.features_version)
+            out.append(ls)
+        return out
+
+    def delete_paths(self, paths: Iterable[str]) -> int:
+        """src/library.rs:1725-1748: how many rows went"""
+        paths = [str(p) for p in paths]
+        if not paths:
+            return 0
+        with self.conn:
+            cur = self.conn.execute("delete from song where path in (%s)" % ",".join("?" * len(paths)), paths)
+        return cur.rowcount
+
+    # ---- playlists: the distance kernels' consumers (src/library.rs:762-893) ---------------------
+    def playlist_from(self, song_paths: Sequence[str]) -> List[LibrarySong]:
+        """:762-767: euclidean distance, closest_to_songs, de-duplicated"""
+        from . import playlist
+        return self.playlist_from_custom(song_paths, playlist.euclidean_distance, playlist.closest_to_songs, True)
+
+    def playlist_from_custom(self, initial_song_paths: Sequence[str], distance, sort_by, deduplicate: bool) -> List[LibrarySong]:
+        """:805-848: the initial songs, then the rest of the library as `sort_by(initial, rest, distance)` orders it
+        (closest_to_songs / song_to_song: one device call each), optionally through dedup_playlist_custom_distance."""
+        from . import playlist
+        initial = []
+        for p in initial_song_paths:
+            try:
+                initial.append(self.song_from_path(p))
+            except ProviderError:
+                raise ProviderError("song '%s' has not been analyzed" % p)
+        rest = [s for s in self.songs_from_library() if s.bliss_song.path not in set(initial_song_paths)]
+        ordered = initial + list(sort_by(initial, rest, distance))
+        if deduplicate:
+            ordered = list(playlist.dedup_playlist_custom_distance(ordered, None, distance))
+        return ordered
+
+    def album_playlist_from(self, album_title: str, number_albums: int) -> List[LibrarySong]:
+        """:850-876: the album, then the `number_albums` closest albums (closest_album_to_group)"""
+        from . import playlist
+        album = self.songs_from_album(album_title)
+        ordered = playlist.closest_album_to_group(album, self.songs_from_library())
+        album_count, index, current = 0, 0, album_title
+        for s in ordered:
+            if s.bliss_song.album != current:
+                album_count += 1
+                if album_count > number_albums:
+                    break
+                current = s.bliss_song.album
+            index += 1
+        return ordered[:index]
 
     @staticmethod
     def _analysis(values: Sequence[float], version: FeaturesVersion) -> Analysis:

@@ -96,9 +96,15 @@ def closest_album_to_group(group: Sequence, pool: Sequence) -> List:
     return playlist
 
 
+def _song(s):
+    """impl AsRef<Song>: a Song, or anything that wraps one (library.LibrarySong), src/playlist.rs:256-262"""
+    return s.as_ref() if hasattr(s, "as_ref") else s
+
+
 def _vectors(songs) -> np.ndarray:
     rows = []
     for s in songs:
+        s = _song(s)
         a = getattr(s, "analysis", s)
         rows.append(np.asarray(getattr(a, "internal_analysis", a), np.float32))
     return np.stack(rows) if rows else np.zeros((0, 0), np.float32)
@@ -161,7 +167,7 @@ def dedup_playlist_custom_distance(playlist: Iterable, distance_threshold: Optio
         while i < n:
             j = i + 1
             while j < n:
-                s1, s2 = songs[i], songs[j]
+                s1, s2 = _song(songs[i]), _song(songs[j])
                 same_tags = (getattr(s1, "title", None) is not None and getattr(s2, "title", None) is not None
                              and getattr(s1, "artist", None) is not None and getattr(s2, "artist", None) is not None
                              and s1.title == s2.title and s1.artist == s2.artist)

@@ -532,6 +532,53 @@ def test_pcm_feed_matches_the_decoders_conversion(golden):
         B.native.analyze_batch_pcm([np.zeros((9000, 9), np.int16)], 22050, 2)
 
 
+def test_library_playlists_run_on_the_distance_kernels(tmp_path):
+    """Library::playlist_from / playlist_from_custom / album_playlist_from (src/library.rs:762-876): the stored songs
+    come back from SQLite, the orderings come from the device (closest_to_songs, song_to_song, closest_album_to_group,
+    dedup) and must be the orderings the oracle's f32 distances give."""
+    L = B.library
+    rng = np.random.default_rng(9)
+    lib = L.Library(str(tmp_path / "songs.db"))
+    rows = (rng.random((40, 23), dtype=np.float32) * 2 - 1).astype(np.float32)
+    rows[7] = rows[3] + np.float32(1e-3)      # a near-duplicate of song 3: closer than the 0.05 de-duplication threshold
+    for i, r in enumerate(rows):
+        song = B.Song(path="/music/%02d" % i, title="t%d" % i, artist="a%d" % (i % 5), album="album%d" % (i // 4),
+                      track_number=i % 4 + 1, disc_number=1, analysis=B.Analysis(r), duration=1.0)
+        lib.store_song(L.LibrarySong(song, {"n": i}))
+    seeds = ["/music/03", "/music/11"]
+    others = [i for i in range(40) if i not in (3, 11)]
+    order, _ = O.closest_to_songs(rows[[3, 11]], rows[others], np.eye(23, dtype=np.float32))
+    want = [3, 11] + [others[i] for i in order]
+    got = lib.playlist_from_custom(seeds, B.playlist.euclidean_distance, B.playlist.closest_to_songs, False)
+    assert [s.bliss_song.path for s in got] == ["/music/%02d" % i for i in want] and got[5].extra_info == {"n": want[5]}
+    dedup = [s.bliss_song.path for s in lib.playlist_from(["/music/03"])]   # one seed: its near-duplicate comes right behind it
+    rest = [i for i in range(40) if i != 3]
+    order1, _ = O.closest_to_songs(rows[[3]], rows[rest], np.eye(23, dtype=np.float32))
+    kept, last = [], None
+    for i in [3] + [rest[k] for k in order1]:   # dedup_playlist_custom_distance, src/playlist.rs:367-402, on the oracle's distances
+        if last is not None and np.float32(O.euclidean_distance(rows[last], rows[i])) < np.float32(0.05):
+            continue
+        kept.append(i)
+        last = i
+    assert dedup == ["/music/%02d" % i for i in kept] and len(kept) == 39 and "/music/07" not in dedup
+    chain = lib.playlist_from_custom(seeds, B.playlist.euclidean_distance, B.playlist.song_to_song, False)
+    want_chain = [3, 11] + [others[i] for i in O.song_to_song(rows[[3, 11]], rows[others], np.eye(23, dtype=np.float32))]
+    assert [s.bliss_song.path for s in chain] == ["/music/%02d" % i for i in want_chain]
+    with pytest.raises(B.ProviderError, match="has not been analyzed"):
+        lib.playlist_from(["/music/nope"])
+    # album playlist: the album itself by (disc, track), then the closest albums by the distance of the mean analyses
+    albums = lib.album_playlist_from("album2", 2)
+    means = np.stack([rows[4 * a:4 * a + 4].mean(axis=0, dtype=np.float32) for a in range(10)])
+    d = [np.float32(O.euclidean_distance(means[2], means[a])) for a in range(10)]
+    nearest = sorted((a for a in range(10) if a != 2), key=lambda a: d[a])[:2]
+    assert [s.bliss_song.album for s in albums] == ["album2"] * 4 + ["album%d" % nearest[0]] * 4 + ["album%d" % nearest[1]] * 4
+    assert [s.bliss_song.track_number for s in albums] == [1, 2, 3, 4] * 3
+    with pytest.raises(B.ProviderError, match="target album was not found"):
+        lib.album_playlist_from("nope", 1)
+    assert lib.delete_paths(["/music/00", "/music/01", "/music/zz"]) == 2 and lib.delete_paths([]) == 0
+    lib.close()
+
+
 def test_wav_files_through_the_decoder_pipeline(tmp_path, golden, pcm_piano):
     """File -> features: 22 050 Hz WAV files through WavDecoder.analyze_paths (decoding threads, one batcher, packed
     frames converted and down-mixed on the device).  The 16-bit mono file is data/piano.wav's content, so its row
