@@ -743,5 +743,58 @@ inline std::vector<size_t> dedup_playlist_custom_distance(const std::vector<Song
 inline std::vector<size_t> dedup_playlist(const std::vector<Song> &songs, std::optional<float> distance_threshold = {}) {
     return dedup_playlist_custom_distance(songs, distance_threshold, euclidean_distance());
 }
+// closest_album_to_group, :424-485: an "album playlist" -- `group` first, then the albums of `pool` ordered by the
+// euclidean distance of their mean analysis to the group's mean analysis (one device call), each album by
+// (disc, track) with None < Some(_); songs of the group and songs without an album tag leave the pool.
+inline std::vector<Song> closest_album_to_group(const std::vector<Song> &group, const std::vector<Song> &pool_in) {
+    if (group.empty()) throw BlissError(BlissError::ProviderError, "Mean of empty slice");
+    auto same = [](const Song &a, const Song &b) {  // #[derive(PartialEq)] on Song
+        return a.path == b.path && a.artist == b.artist && a.album_artist == b.album_artist && a.title == b.title && a.album == b.album &&
+               a.genre == b.genre && a.track_number == b.track_number && a.disc_number == b.disc_number && a.duration_s == b.duration_s &&
+               a.features_version == b.features_version && a.analysis.has_value() == b.analysis.has_value() &&
+               (!a.analysis || a.analysis->as_vec() == b.analysis->as_vec());
+    };
+    std::vector<const Song *> pool;
+    for (const Song &sg : pool_in) {
+        bool in_group = false;
+        for (const Song &g : group) in_group = in_group || same(g, sg);
+        if (!in_group) pool.push_back(&sg);
+    }
+    const size_t dim = group[0].analysis->as_vec().size();
+    auto mean_of = [&](const std::vector<const Song *> &v) {  // mean_axis(Axis(0)): rows summed in order, then / n, in f32
+        std::vector<float> m(dim, 0.f);
+        for (const Song *sg : v)
+            for (size_t i = 0; i < dim; i++) m[i] += sg->analysis->as_vec()[i];
+        for (float &x : m) x /= static_cast<float>(v.size());
+        return m;
+    };
+    std::vector<std::string> names;
+    std::vector<std::vector<const Song *>> members;
+    for (const Song *sg : pool) {
+        if (!sg->album) continue;
+        size_t k = 0;
+        while (k < names.size() && names[k] != *sg->album) k++;
+        if (k == names.size()) { names.push_back(*sg->album); members.emplace_back(); }
+        members[k].push_back(sg);
+    }
+    std::vector<const Song *> group_ptrs;
+    for (const Song &g : group) group_ptrs.push_back(&g);
+    std::vector<Song> out(group);
+    if (names.empty()) return out;
+    std::vector<float> means;
+    for (const auto &m : members) { const auto v = mean_of(m); means.insert(means.end(), v.begin(), v.end()); }
+    const std::vector<float> d = distance_matrix(mean_of(group_ptrs), means, static_cast<uint32_t>(dim));
+    std::vector<size_t> order(names.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return d[a] < d[b]; });
+    for (size_t k : order) {
+        std::vector<const Song *> al = members[k];
+        std::stable_sort(al.begin(), al.end(), [](const Song *a, const Song *b) {
+            return std::make_pair(a->disc_number, a->track_number) < std::make_pair(b->disc_number, b->track_number);  // nullopt < any value
+        });
+        for (const Song *sg : al) out.push_back(*sg);
+    }
+    return out;
+}
 }  // namespace playlist
 }  // namespace bliss

@@ -296,6 +296,44 @@ int main() {
             const auto dm = playlist::distance_matrix(pl[0].analysis->as_vec(), pl[2].analysis->as_vec(), 23);
             if (dm.size() != 1 || dm[0] != playlist::distance(pl[0].analysis->as_vec(), pl[2].analysis->as_vec())) return 44;
         }
+        // closest_album_to_group: the reference's own test, src/playlist.rs:1113-1262
+        {
+            auto mk = [](const char *path, float val, const char *album, const char *artist, int track, int disc) {
+                Song x;
+                x.path = path;
+                x.analysis = Analysis(std::vector<float>(23, val), LATEST);
+                if (album) x.album = album;
+                if (artist) x.artist = artist;
+                if (track) x.track_number = track;
+                if (disc) x.disc_number = disc;
+                return x;
+            };
+            const Song first = mk("path-to-first", 0.f, "Album", "Artist", 1, 1), second = mk("path-to-third", 10.f, "Album", "Another Artist", 2, 1);
+            const Song o11 = mk("path-to-second-2", 0.15f, "Another Album", "Artist", 1, 1), o12 = mk("path-to-second", 0.1f, "Another Album", "Artist", 2, 1);
+            const Song o21 = mk("path-to-fourth", 20.f, "Another Album", "Another Artist", 1, 2), o24 = mk("path-to-fourth", 20.f, "Another Album", "Another Artist", 4, 2);
+            const Song none = mk("path-to-fifth", 40.f, nullptr, "Third Artist", 0, 0);
+            const auto got = playlist::closest_album_to_group({first, second}, {first, o12, o24, second, o21, o11, none});
+            const std::vector<std::pair<std::string, int>> want = {{"path-to-first", 1}, {"path-to-third", 2}, {"path-to-second-2", 1},
+                                                                   {"path-to-second", 2}, {"path-to-fourth", 1}, {"path-to-fourth", 4}};
+            if (got.size() != want.size()) return 80;
+            for (size_t i = 0; i < want.size(); i++)
+                if (got[i].path != want[i].first || *got[i].track_number != want[i].second) return 81;
+            std::vector<Song> pool2;
+            for (int i : {2, 1}) pool2.push_back(mk(("far-" + std::to_string(i)).c_str(), 30.f + i, "Far", nullptr, i, 0));
+            for (int i : {2, 1}) pool2.push_back(mk(("near-" + std::to_string(i)).c_str(), 6.f + i, "Near", nullptr, i, 0));
+            pool2.push_back(first);
+            const auto two = playlist::closest_album_to_group({first, second}, pool2);
+            const std::vector<std::string> names = {"path-to-first", "path-to-third", "near-1", "near-2", "far-1", "far-2"};
+            if (two.size() != names.size()) return 82;
+            for (size_t i = 0; i < names.size(); i++)
+                if (two[i].path != names[i]) return 83;
+            try {
+                playlist::closest_album_to_group({}, pool2);
+                return 84;
+            } catch (const BlissError &e) {
+                if (e.kind != BlissError::ProviderError) return 85;
+            }
+        }
         std::puts("OK");
         return 0;
     } catch (const BlissError &e) {
