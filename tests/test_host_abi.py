@@ -717,6 +717,19 @@ def test_cpp_host_mirror_builds_and_refuses_to_run_without_gpu(tmp_path):
     assert out.stdout.strip() == "NO_DEVICE"
 
 
+def test_header_is_c99_and_the_library_links_from_c(tmp_path):
+    """include/bliss_b200.h under gcc -std=c99 -pedantic -Werror; tests/c/abi_c99.c links against the library, uses the
+    device-free entry points and sees bliss_b200_init refuse a box without a GPU (on a GPU box: one too-short song)."""
+    exe = str(tmp_path / "abi_c99")
+    libdir = os.path.dirname(B.native.SO_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_c99.c"), "-o", exe, "-L" + libdir, "-lbliss_b200",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert out.stdout.startswith("DEVICE_OK" if torch.cuda.is_available() else "NO_DEVICE")
+
+
 @pytest.mark.gpu
 def test_cpp_host_mirror_on_gpu(tmp_path):
     """the same program on a GPU box: Song::analyze, the Decoder batching seam (errors as items), the 16-bit
