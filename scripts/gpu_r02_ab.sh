@@ -47,3 +47,4 @@ done
 BLISS_B200_VARIANT=16064 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"pvoc512_kernel|stft8192_kernel" -c 2 -o gpurun_out/ab_prof_v16064 python bench.py --steps 1 --warmup 0 --songs-per-gpu 128 --no-cpu-baseline > gpurun_out/ab_ncu_v16064.log 2>&1; echo NCU_EXIT $?
 BLISS_B200_VARIANT=256 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"stft512_pairs_kernel" -c 1 -o gpurun_out/ab_prof_stft_v256 python bench_stft.py --tracks 128 --resident 128 --warmup 0 > gpurun_out/ab_ncu_stft_v256.log 2>&1; echo NCU_STFT_EXIT $?
 ls -la gpurun_out | grep " ab_"
+python scripts/ab_report.py gpurun_out
