@@ -821,15 +821,20 @@ uint64_t bo_pip_track(const double *S, uint32_t frames, uint32_t n_fft, double *
     return cnt;
 }
 
-/* chroma.rs:334-359 (+ utils.rs:119-129 hz_to_octs_inplace with tuning 0, 12 bins) */
+/* utils.rs:119-129 hz_to_octs_inplace */
+void bo_hz_to_octs(double *f, uint64_t n, double tuning, uint32_t bins_per_octave) {
+    const double a440 = 440.0 * pow(2.0, tuning / (double)bins_per_octave);
+    for (uint64_t i = 0; i < n; i++) f[i] = log2(f[i] / (a440 / 16.));
+}
+
+/* chroma.rs:334-359 (hz_to_octs_inplace with tuning 0, 12 bins) */
 double bo_pitch_tuning(double *f, uint64_t n, double resolution) {
     if (n == 0) return 0.0;
-    const double a440 = 440.0 * pow(2.0, 0.0 / 12.0);
     uint32_t nb = (uint32_t)((0.5 - -0.5) / resolution);
     uint64_t *counts = (uint64_t *)calloc(nb, sizeof(uint64_t));
+    bo_hz_to_octs(f, n, 0.0, 12);
     for (uint64_t i = 0; i < n; i++) {
-        double v = f[i] / (a440 / 16.);
-        v = log2(v);
+        double v = f[i];
         v = fmod(12.0 * v, 1.0);
         if (v >= 0.5) v -= 1.;
         f[i] = v;

@@ -58,6 +58,8 @@ def lib():
         L.bo_tempo_norms.argtypes = [f32p, C.c_uint64, C.c_uint32, f32p]
         L.bo_pip_track.argtypes = [f64p, C.c_uint32, C.c_uint32, f64p, f64p]
         L.bo_pip_track.restype = C.c_uint64
+        L.bo_hz_to_octs.argtypes = [f64p, C.c_uint64, C.c_double, C.c_uint32]
+        L.bo_hz_to_octs.restype = None
         L.bo_pitch_tuning.argtypes = [f64p, C.c_uint64, C.c_double]
         L.bo_pitch_tuning.restype = C.c_double
         L.bo_estimate_tuning.argtypes = [f64p, C.c_uint32, C.c_uint32]
@@ -214,6 +216,13 @@ def pip_track(S, n_fft):
     m = np.zeros(cap, np.float64)
     cnt = lib().bo_pip_track(Sf, Sf.shape[0], n_fft, p, m)
     return p[:cnt].copy(), m[:cnt].copy()
+
+
+def hz_to_octs(freqs, tuning=0.0, bins_per_octave=12):
+    """utils.rs:119-129"""
+    f = np.ascontiguousarray(freqs, np.float64).copy()
+    lib().bo_hz_to_octs(f, f.size, float(tuning), int(bins_per_octave))
+    return f
 
 
 def pitch_tuning(freqs, resolution):

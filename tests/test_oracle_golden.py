@@ -206,6 +206,12 @@ def test_estimate_tuning(golden):
     assert O.estimate_tuning(np.zeros((8192, 1)), 8192) == 0.0
 
 
+def test_hz_to_octs_inplace():
+    # src/utils.rs:517-525
+    got = O.hz_to_octs([32.0, 64.0, 128.0, 256.0], 0.5, 10)
+    assert np.abs(got - np.array([0.16864029, 1.16864029, 2.16864029, 3.16864029])).max() < 1e-4
+
+
 def test_pitch_tuning(golden):
     # src/chroma.rs:668-679
     assert O.pitch_tuning(golden["pitch_tuning"], 0.05) == -0.1
