@@ -168,10 +168,25 @@ class Analysis:
                 and np.array_equal(self.internal_analysis, other.internal_analysis))
 
     def __repr__(self):
-        """impl Debug, src/song/mod.rs:294-318"""
+        """impl Debug, src/song/mod.rs:294-318: the named fields, then the vector as a comment; floats as Rust's
+        `{:?}` prints an f32 (shortest digits that round-trip, at least one decimal, exponent form outside
+        [1e-4, 1e16))"""
         names = AnalysisIndex if self.features_version == FeaturesVersion.Version2 else AnalysisIndexv1
-        body = ", ".join("%s: %s" % (n.name, repr(float(v))) for n, v in zip(names, self.internal_analysis))
-        return "Analysis (Version %d) { %s }" % (int(self.features_version), body)
+        vals = [_f32_debug(v) for v in self.internal_analysis]
+        body = ", ".join("%s: %s" % (n.name, v) for n, v in zip(names, vals))
+        return "Analysis (Version %d) { %s } /* [%s] */" % (int(self.features_version), body, ", ".join(vals))
+
+
+def _f32_debug(v) -> str:
+    v = np.float32(v)
+    if np.isnan(v):
+        return "NaN"
+    if np.isinf(v):
+        return "inf" if v > 0 else "-inf"
+    a = np.float32(abs(v))
+    if a == 0 or np.float32(1e-4) <= a < np.float32(1e16):
+        return np.format_float_positional(v, unique=True, trim="0")
+    return np.format_float_scientific(v, unique=True, trim="-", exp_digits=1).replace("e+", "e")
 
 
 @dataclass

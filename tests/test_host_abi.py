@@ -62,6 +62,25 @@ def test_analysis_type_behaviour():
         a.distance(v1)
     assert a.as_vec()[1] == pytest.approx(0.1) and a.as_arr1().dtype == np.float32
     assert "Analysis (Version 2)" in repr(a) and "Tempo" in repr(a)
+    # impl Debug for Analysis: the exact strings of the reference's tests (src/song/mod.rs:712-735), values taken from them
+    v2 = [0.3846389, -0.849141, -0.7548105, -0.8790748, -0.63258266, -0.7258959, -0.775738, -0.8146726, 0.2716726, 0.25779057,
+          -0.34292513, -0.62803423, -0.28095096, 0.08686459, 0.24446082, -0.5723257, 0.23292065, 0.19981146, -0.58594406,
+          -0.06784296, -0.06000763, -0.58485717, -0.07880378]
+    assert repr(B.Analysis(v2)) == (
+        "Analysis (Version 2) { Tempo: 0.3846389, Zcr: -0.849141, MeanSpectralCentroid: -0.7548105, StdDeviationSpectralCentroid: "
+        "-0.8790748, MeanSpectralRolloff: -0.63258266, StdDeviationSpectralRolloff: -0.7258959, MeanSpectralFlatness: -0.775738, "
+        "StdDeviationSpectralFlatness: -0.8146726, MeanLoudness: 0.2716726, StdDeviationLoudness: 0.25779057, Chroma1: -0.34292513, "
+        "Chroma2: -0.62803423, Chroma3: -0.28095096, Chroma4: 0.08686459, Chroma5: 0.24446082, Chroma6: -0.5723257, Chroma7: "
+        "0.23292065, Chroma8: 0.19981146, Chroma9: -0.58594406, Chroma10: -0.06784296, Chroma11: -0.06000763, Chroma12: -0.58485717, "
+        "Chroma13: -0.07880378 } /* [0.3846389, -0.849141, -0.7548105, -0.8790748, -0.63258266, -0.7258959, -0.775738, -0.8146726, "
+        "0.2716726, 0.25779057, -0.34292513, -0.62803423, -0.28095096, 0.08686459, 0.24446082, -0.5723257, 0.23292065, 0.19981146, "
+        "-0.58594406, -0.06784296, -0.06000763, -0.58485717, -0.07880378] */")
+    v1 = v2[:10] + [-0.35661936, -0.63578653, -0.29593682, 0.06421304, 0.21852458, -0.581239, -0.9466835, -0.9481153, -0.9820945, -0.95968974]
+    r1 = repr(B.Analysis(v1, B.FeaturesVersion.Version1))
+    assert r1.startswith("Analysis (Version 1) { Tempo: 0.3846389, ") and "Chroma10: -0.95968974 } /* [0.3846389, " in r1
+    assert r1.endswith("-0.9820945, -0.95968974] */") and "Chroma11" not in r1
+    from bliss_rs_b200.song import _f32_debug
+    assert [_f32_debug(x) for x in (1, -0.0, 1.5e-5, 1e-7, 3e20, 0.0001, 123456.7)] == ["1.0", "-0.0", "1.5e-5", "1e-7", "3e20", "0.0001", "123456.7"]
     # FeaturesVersion::try_from, src/lib.rs:195-207
     assert B.FeaturesVersion.try_from(1) == B.FeaturesVersion.Version1
     with pytest.raises(B.ProviderError):
