@@ -263,7 +263,7 @@ int main() {
                 if (items.size() != 3 || under_sheet != 2) return 75;
                 std::remove(cue_path.c_str());
             }
-            for (const auto &w : wavs) std::remove(w.c_str());
+            for (const auto &wav : wavs) std::remove(wav.c_str());
         }
         // playlist: closest_to_songs keeps the seed first
         std::vector<float> cands;
