@@ -736,6 +736,22 @@ def test_cpp_host_mirror_builds_and_refuses_to_run_without_gpu(tmp_path):
     assert out.stdout.strip() == "NO_DEVICE"
 
 
+def test_cpp_decoder_pipeline_under_thread_sanitizer(tmp_path):
+    """tests/cpp/pipeline_tsan.cpp: Decoder::analyze_paths of the C++ mirror -- decoding threads, bounded hand-over, one
+    batcher, the two failure paths -- built with -fsanitize=thread over a C ABI stubbed inside the test program: 27 000
+    songs through 1 / 3 / 8 decoding threads and batch sizes 1 / 7 / 64, every path answered once, rows with their
+    songs, GPU calls never overlapping, no data race reported."""
+    exe = str(tmp_path / "pipeline_tsan")
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-pthread", "-Wall", "-Wextra", "-Werror",
+                            "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+                            os.path.join(ROOT, "tests", "cpp", "pipeline_tsan.cpp"), "-o", exe], capture_output=True, text=True)
+    if build.returncode != 0 and "tsan" in build.stderr.lower():
+        pytest.skip("no ThreadSanitizer runtime in this image")
+    assert build.returncode == 0, build.stderr[-2000:]
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.startswith("OK") and "ThreadSanitizer" not in out.stderr, out.stdout + out.stderr[-3000:]
+
+
 def test_header_is_c99_and_the_library_links_from_c(tmp_path):
     """include/bliss_b200.h under gcc -std=c99 -pedantic -Werror; tests/c/abi_c99.c links against the library, uses the
     device-free entry points and sees bliss_b200_init refuse a box without a GPU (on a GPU box: one too-short song)."""
