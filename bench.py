@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--songs-per-gpu", type=int, default=SONGS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels-only", action="store_true",
+                    help="A/B runs: device-timed value + per-kernel times only (no e2e legs, no CPU baseline)")
     ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N>1 feature-row exchange: p2p = rows stored into every rank's buffer by the analysis "
                          "itself + one-warp epoch barrier; nccl = all_gather_into_tensor; auto = p2p, else nccl")
@@ -385,6 +387,20 @@ def main():
                 "kernels": kernels}
 
     # ---- e2e: the C-ABI call with pinned HOST buffers (H2D + D2H inside the timed region) --
+    if args.kernels_only:
+        if rank == 0:
+            _emit({"metric": METRIC, "value": value, "unit": "songs/s", "n_gpus": world, "steps": args.steps,
+                   "warmup": args.warmup, "ms_per_step": ms / args.steps, "kernels_only": True,
+                   "config": {"kernel_variant_mask": int(os.environ.get("BLISS_B200_VARIANT", "0") or 0),
+                              "songs_per_gpu": S},
+                   "roofline": roofline, "clocks": clocks, "gpu_launches": int(lz.item()),
+                   "bitwise_reproducible_across_steps": bool(deterministic.item())})
+        if world > 1:
+            dist.barrier()
+            if gather:
+                gather.destroy()
+            dist.destroy_process_group()
+        return
     ES = min(E2E_SONGS, S)
     host = torch.empty(ES * TRACK_SAMPLES, dtype=torch.float32, pin_memory=True)
     for i in range(ES):

@@ -663,8 +663,8 @@ int bliss_b200_init(int device) {
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     g.ws_limit = (size_t)((double)total_b * 0.40);
-    g.variant = 0;
-    if (const char *e = getenv("BLISS_B200_VARIANT")) g.variant = atoi(e);
+    g.variant = VARIANT_PROMOTED;  // user mask 0
+    if (const char *e = getenv("BLISS_B200_VARIANT")) g.variant = atoi(e) ^ VARIANT_PROMOTED;
 #ifdef BLISS_HOST_EMUL
     fprintf(stderr, "[bliss_b200] HOST-EMULATED TEST BUILD (tests/cpu_emul): kernels run on the CPU, thread by thread. "
                     "Not a product path -- the product library is built by nvcc and needs a B200.\n");
@@ -707,8 +707,10 @@ void bliss_b200_shutdown(void) {
 // previous mask.  The environment variable BLISS_B200_VARIANT sets the initial value.
 int bliss_b200_set_variant(int mask) {
     std::lock_guard<std::mutex> lk(g.mu);
-    const int prev = g.variant;
-    g.variant = mask;
+    // The cuts promoted in round 2 (profiles/ab_r02.md) are ON for mask 0: the user's bit switches a kernel BACK to
+    // its previous implementation, like bits 1..32; internally the promoted bits are stored inverted.
+    const int prev = g.variant ^ VARIANT_PROMOTED;
+    g.variant = mask ^ VARIANT_PROMOTED;
     return prev;
 }
 

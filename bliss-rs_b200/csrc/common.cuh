@@ -26,7 +26,7 @@ constexpr int CH_WIN = 8192;              // chroma.rs:39
 constexpr int CH_HOP = 2205;              // chroma.rs:74
 constexpr int CH_BINS = 4097;
 #ifndef BLISS_CH_STRIDE
-#define BLISS_CH_STRIDE 4104  // -DBLISS_CH_STRIDE=4128 (scripts/build_variants.py): rows aligned to 128-byte lines
+#define BLISS_CH_STRIDE 4128  // rows on 128-byte lines (A/B of round 2: chroma contraction 7.51 -> 6.86 ms, stft8192 -0.3 ms against 4104)
 #endif
 constexpr int CH_STRIDE = BLISS_CH_STRIDE;  // padded row of the magnitude spill (16 B aligned rows)
 static_assert(CH_STRIDE >= 4100 && CH_STRIDE % 4 == 0, "a row holds 4097 magnitudes, 16-byte aligned");
@@ -79,6 +79,12 @@ enum {
     VARIANT_LAY16 = 4096,      // stft8192: FFT buffer without the per-16 padding: conflict-free mirror loads in the pair epilogue (experimental; bit-identical results)
     VARIANT_ODDSHIFT = 8192,   // stft8192 (both cuts, also with bit 32): frames starting on an odd sample are transformed rotated by one sample, so that their pairs load as aligned 64-bit words (experimental)
     VARIANT_WINSYN = 128,      // stft8192 (both cuts, also with bit 32): Hann window from the thread's phase (2 FFMA2 per pair) instead of 16 (radix-64: 64) loads (experimental)
+    // Bits 64 ... 8192 were written blind at the end of round 1 and A/B-timed on one B200 at the start of round 2
+    // (profiles/ab_r02.md: all on = 59.7 ms per 1024-track step against 67.4 ms, every bit bit-reproducible): they
+    // are now what the library runs.  Internally the bit still means "cut on"; the PUBLIC mask (BLISS_B200_VARIANT,
+    // bliss_b200_set_variant) is XORed with VARIANT_PROMOTED, so that 0 = the promoted kernels and a set bit goes
+    // back to the kernel measured in round 1, like bits 1..32.
+    VARIANT_PROMOTED = 64 | 128 | 256 | 512 | 1024 | 2048 | 4096 | 8192,
 };
 
 // Song lookup for flat work lists: largest s with prefix[s] <= item (prefix has n_songs+1

@@ -633,11 +633,11 @@ def test_wav_files_through_the_decoder_pipeline(tmp_path, golden, pcm_piano):
     lib.close()
 
 
-# The kernel cuts behind BLISS_B200_VARIANT bits 64 ... 1024 were written after round 1's GPU budget was spent: they
-# are OFF by default, validated on the host only (tests/cpu_emul, tests/test_host_abi.py), and their tests below
-# have never met hardware.  Non-strict xfail keeps a defect in code that is not on the product path from masking
-# the parity suite of the code that is; an XPASS is the expected outcome and promotes the cut to a plain test.
-_xfail_experimental = pytest.mark.xfail(reason="experimental kernel variant, first hardware run", strict=False)
+# The kernel cuts behind BLISS_B200_VARIANT bits 64 ... 8192 were written after round 1's GPU budget was spent, passed
+# on the driver's B200 at the end of round 1 and won the A/B of round 2 (profiles/ab_r02.md): they are the default
+# now (mask 0) and a set bit switches BACK to the kernel measured in round 1.  The tests below compare the two
+# implementations of each cut whichever way round the bit reads; they are plain tests (no xfail) run in a child
+# process with a time limit.
 
 
 def experimental(fn):
@@ -661,7 +661,7 @@ def experimental(fn):
         print(out.stdout[-3000:])
         assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-1000:]
 
-    return _xfail_experimental(wrapper)
+    return wrapper
 
 
 @experimental
