@@ -373,8 +373,13 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
       p.done(launch_timedomain(d_pcm, dv.sd, dv.chunk_prefix, n, w.chunk_prefix[n], S.loud.as<float>(),
                                S.eb.as<float>(), S.zcr.as<unsigned int>(), st)); }
     { ProfScope p(K_PVOC, st);
-      p.done(launch_pvoc512(d_pcm, dv.sd, dv.k1_prefix, n, w.k1_prefix[n], (int)w.pairs_per_item, pvoc_tables(),
-                            S.cent.as<float>(), S.roll.as<float>(), S.flat.as<float>(), S.flux.as<float>(), g.variant, st)); }
+      const int nl = launch_pvoc512(d_pcm, dv.sd, dv.k1_prefix, n, w.k1_prefix[n], (int)w.pairs_per_item, pvoc_tables(),
+                                    S.cent.as<float>(), S.roll.as<float>(), S.flat.as<float>(), S.flux.as<float>(), g.variant, st);
+      p.done(nl);
+      if (nl < 0) {
+          g_last_error = "cudaFuncSetAttribute(pvoc512v2_kernel, MaxDynamicSharedMemorySize) failed";
+          return BLISS_B200_E_CUDA;
+      } }
     { ProfScope p(K_TUNING, sb);
       p.done(launch_tuning(S.cand_mag.as<double>(), S.cand_pitch.as<double>(),
                            S.cand_count.as<unsigned int>(), dv.sd, n, S.tuning.as<int>(), g.variant, sb)); }

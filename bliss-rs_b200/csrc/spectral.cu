@@ -388,6 +388,291 @@ pvoc512_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs
 }
 
 // ---------------------------------------------------------------------------
+// pvoc512v2_kernel (round 2): the same work as pvoc512_kernel -- one warp walks a run of frame pairs, timbral
+// frames 2j / 2j+1 ride one complex 512-point FFT, each sample is fetched once through the 20-row sliding register
+// window -- re-cut around what the round-1 captures showed the kernel to be bound by (issue slots 70 %, L1 /
+// shared-memory data pipe 67 %: 1 111 instructions and ~260 wavefronts per pair with every round-1 cut on):
+//   * phase B is a decimation-in-FREQUENCY split of the 32-point DFT over n2: lane (p, k1) forms
+//     u[n2] = y[n2] + (-1)^p y[n2 + 16], rotates by W32^(n2 p) and runs ONE radix-16, which leaves it the bins
+//     k = k1 + 16 (2 q + p), q = 0..15 -- no radix-2 shuffle stage (32 SHFL + 16 FFMA2 per pair gone);
+//   * the mirror bins Z[512 - k] of a lane's eight LOW bins (q < 8) are the eight HIGH bins of ONE other lane
+//     (1 - p, 16 - k1), same slot order: 16 SHFL replace the natural-order round trip through shared memory
+//     (16 STS.64 + 18 LDS.64, 2-way conflicts), and every lane untangles exactly eight bins of both frames;
+//     the bins a lane ends up with are lane + 32 i: a row of magnitudes is written as 128-byte warp stores;
+//   * the per-frame descriptors leave the FFT loop: magnitudes of four pairs (eight frames) go to a per-warp tile
+//     in shared memory and are reduced FOUR LANES PER FRAME, 64 consecutive bins per lane, serially in registers:
+//     2 shuffle steps per quantity instead of 5, one scalar finish (two IEEE divisions, log2f, exp2f) per eight
+//     frames instead of per pair; geometric_mean's per-8-bin f64 products (utils.rs:104-111) keep their order.
+// Shared memory: 4.1 KB exchange tile + 8.5 KB magnitude tile per warp (101 KB per CTA, two CTAs per SM).
+// ---------------------------------------------------------------------------
+namespace pv2 {
+constexpr int ROW = 33;                      // padded row (cpx) of the 16 x 32 exchange tile: S[k1][n2]
+constexpr int EXCH_CPX = 16 * ROW;           // 528 cpx = 4224 B
+constexpr int TILE_PAIRS = 4;                // pairs (x 2 frames) per descriptor tile
+constexpr int TILE_ROW = 272;                // floats per frame row: bin k at k + 4 (k >> 6), Nyquist at NYQ_POS
+constexpr int NYQ_POS = 268;
+constexpr int WARP_SMEM_BYTES = EXCH_CPX * 8 + 2 * TILE_PAIRS * TILE_ROW * 4;  // 12 928
+static_assert(WARP_SMEM_BYTES % 16 == 0 && (EXCH_CPX * 8) % 16 == 0, "128-bit tile loads");
+
+template <int N2>
+BLISS_HD void tw32_nat(cpx (&u)[16]) {  // u[n2] *= W32^n2, natural order
+    if constexpr (N2 < 16) {
+        u[N2] = mul_tw<N2, 32>(u[N2]);
+        tw32_nat<N2 + 1>(u);
+    }
+}
+
+// Descriptors of the frames of one tile (rows 0 .. 2 n_pairs - 1), four lanes per frame: lane = 4 f + g reduces
+// bins 64 g .. 64 g + 63 of row f.  spectral_centroid / spectral_rolloff (aubio.rs:16-58, clamp timbral.rs:184-187),
+// flatness = geometric_mean / mean (utils.rs:101-117, timbral.rs:196-208); the 256-bin cvec carries the Nyquist
+// magnitude in slot 255 (aubio.rs:255-261).
+__device__ __forceinline__ void tile_descriptors(const float *T, int n_pairs, int lane, int frame0, int n_s,
+                                                 float *__restrict__ centroid, float *__restrict__ rolloff,
+                                                 float *__restrict__ flatness) {
+    const int f = lane >> 2, g = lane & 3;
+    const float *row = T + f * TILE_ROW;
+    const float4 *q = reinterpret_cast<const float4 *>(row + 68 * g);  // tpos(64 g) = 64 g + 4 g
+    const float nyq = row[NYQ_POS];
+    float s1 = 0.f, sw = 0.f, run = 0.f, c8[8];
+    double mant = 1.0;
+    int ex = 0;
+    bool zero = false;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const float4 a = q[2 * t], b = q[2 * t + 1];
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (t == 7 && g == 3) v[7] = nyq;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            s1 += v[i];
+            sw = fmaf((float)(8 * t + i), v[i], sw);
+            run = fmaf(v[i], v[i], run);
+        }
+        c8[t] = run;
+        // geometric_mean's per-group product, utils.rs:104-111 (order kept)
+        double m = ((double)v[0] * (double)v[1]) * ((double)v[2] * (double)v[3]);
+        m *= 3.273390607896142e150;
+        m *= ((double)v[4] * (double)v[5]) * ((double)v[6] * (double)v[7]);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+        zero = zero || (m == 0.0);
+        ex += (int)(bits >> 52);
+        mant *= __longlong_as_double((long long)((bits & 0xFFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
+    }
+    sw = fmaf((float)(64 * g), s1, sw);  // sum (64 g + i) v
+    const unsigned int full = 0xffffffffu;
+    s1 += __shfl_xor_sync(full, s1, 1);
+    s1 += __shfl_xor_sync(full, s1, 2);
+    sw += __shfl_xor_sync(full, sw, 1);
+    sw += __shfl_xor_sync(full, sw, 2);
+    ex += __shfl_xor_sync(full, ex, 1);
+    ex += __shfl_xor_sync(full, ex, 2);
+    mant *= __shfl_xor_sync(full, mant, 1);
+    mant *= __shfl_xor_sync(full, mant, 2);
+    const unsigned int zb = __ballot_sync(full, zero);
+    const bool any_zero = ((zb >> (lane & ~3)) & 0xFu) != 0u;
+    // roll-off: number of bins whose inclusive energy prefix stays below 0.95 of the total (aubio.rs:36-58);
+    // the prefix is non-decreasing, so each lane counts inside its own 64 bins and the counts add up
+    float incl = run;
+    {
+        float t1 = __shfl_up_sync(full, incl, 1);
+        if (g >= 1) incl += t1;
+        t1 = __shfl_up_sync(full, incl, 2);
+        if (g >= 2) incl += t1;
+    }
+    const float total = __shfl_sync(full, incl, lane | 3);
+    float excl = __shfl_up_sync(full, incl, 1);
+    if (g == 0) excl = 0.f;
+    const float thr = total * 0.95f;
+    int gb = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) gb += ((excl + c8[t]) < thr) ? 1 : 0;
+    const int tg = min(gb, 7);  // the group that holds the crossing (re-scanned with the arithmetic of the first pass)
+    float r2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 7; t++)
+        if (tg > t) r2 = c8[t];
+    int within = 0;
+    {
+        const float4 a = q[2 * tg], b = q[2 * tg + 1];
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (tg == 7 && g == 3) v[7] = nyq;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            r2 = fmaf(v[i], v[i], r2);
+            within += ((excl + r2) < thr) ? 1 : 0;
+        }
+    }
+    int cnt = (gb == 8) ? 64 : 8 * gb + within;
+    cnt += __shfl_xor_sync(full, cnt, 1);
+    cnt += __shfl_xor_sync(full, cnt, 2);
+    const float freq = (float)SAMPLE_RATE / 512.f;  // bin_to_freq, aubio.rs:68-71
+    const float bin = (total == 0.f) ? 0.f : (float)min(cnt + 1, 256);
+    const float ro = freq * bin;
+    const float ce = (s1 == 0.f) ? 0.f : freq * fmaxf(sw / s1, 0.f);
+    float fl = 0.f;
+    if (!any_zero) {
+        const float gm = exp2f((log2f((float)mant) + (float)ex) / 256.f - (1023.f + 500.f) / 8.f);
+        fl = gm / (s1 / 256.f);
+    }
+    const int fidx = frame0 + f;
+    if (g == 0 && f < 2 * n_pairs && fidx < n_s) {
+        centroid[fidx] = ce;
+        rolloff[fidx] = ro;
+        flatness[fidx] = fl;
+    }
+}
+}  // namespace pv2
+
+__global__ void __launch_bounds__(256, 2)
+pvoc512v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
+                 const unsigned int *__restrict__ item_prefix, int n_songs, unsigned int total_items,
+                 int pairs_per_item, PvocTables tab, float *__restrict__ centroid, float *__restrict__ rolloff,
+                 float *__restrict__ flatness, float *__restrict__ flux, float *__restrict__ /*mags_out: unused*/) {
+#ifdef BLISS_HOST_EMUL
+    unsigned char *pv2_smem = emu::dynamic_smem();
+#else
+    extern __shared__ __align__(16) unsigned char pv2_smem[];
+#endif
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int item = blockIdx.x * 8u + (unsigned)warp;
+    if (item >= total_items) return;
+    const int si = find_song(item_prefix, n_songs, item);
+    const SongDesc sd = songs[si];
+    const int j0 = (int)(item - item_prefix[si]) * pairs_per_item;
+    const int j1 = min(j0 + pairs_per_item, (int)sd.n_t);
+    const float *x = pcm + sd.pcm_off;
+    const int n = (int)sd.n;
+    cpx *S = reinterpret_cast<cpx *>(pv2_smem + (size_t)warp * pv2::WARP_SMEM_BYTES);
+    float *T = reinterpret_cast<float *>(S + pv2::EXCH_CPX);
+
+    float win_a[16];  // 2^30 w[lane + 32 n1]: the magnitudes then need MUFU.SQRT only (exact power of two, taken out below)
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) win_a[n1] = __ldg(tab.win + lane + 32 * n1) * 1073741824.f;
+    const float2 *twg = reinterpret_cast<const float2 *>(tab.twA);  // W512^(lane k1), k1 = 1, 2, 4, 8
+    const float2 g1 = __ldg(twg + 1 * 32 + lane), g2 = __ldg(twg + 2 * 32 + lane), g4 = __ldg(twg + 4 * 32 + lane),
+                 g8 = __ldg(twg + 8 * 32 + lane);
+    const cpx tw1 = cpx{g1.x, g1.y}, tw2 = cpx{g2.x, g2.y}, tw4 = cpx{g4.x, g4.y}, tw8 = cpx{g8.x, g8.y};
+    const int k1 = lane & 15, p = lane >> 4;
+    const float sgn = p ? -1.f : 1.f;
+    const int mirror_lane = (k1 != 0) ? 16 * (1 - p) + 16 - k1 : lane;  // holds Z[512 - k] of this lane's low bins
+
+    float old[8];  // previous tempo frame's magnitudes of bins lane + 32 i
+#pragma unroll
+    for (int i = 0; i < 8; i++) old[i] = 0.f;
+    float old256 = 0.f;
+
+    float s[20];  // s[m] = x[256*j - 384 + lane + 32*m]
+    const int jstart = (j0 > 0) ? j0 - 1 : j0;  // halo pair: only to seed `old`
+    {
+        const int base = 256 * jstart - 384 + lane;
+#pragma unroll
+        for (int m = 0; m < 20; m++) {
+            const int idx = base + 32 * m;  // rows 12..19 are >= 0 and < n for every valid pair
+            s[m] = (idx >= 0 && idx < n) ? __ldg(x + idx) : 0.f;
+        }
+    }
+    int trow = 0, jt0 = j0;  // pairs in the open tile, its first pair
+    for (int j = jstart; j < j1; j++) {
+        // frame packing, power-of-two pre-scaling of B and exact zeros for digital silence: as pvoc512_kernel
+        float pka = 0.f, pkb = 0.f;
+        cpx r[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            r[n1] = pmul(cpx{s[n1], s[n1 + 4]}, cpx{win_a[n1], win_a[n1]});
+            pka = fmaxf(pka, fabsf(r[n1].x));
+            pkb = fmaxf(pkb, fabsf(r[n1].y));
+        }
+#pragma unroll
+        for (int m = 0; m < 12; m++) s[m] = s[m + 8];
+        if (j + 1 < j1) {
+            const float *px = x + 256 * (j + 1) - 384 + lane + 32 * 12;  // 256 (j+1) + lane + 32 m < n for j + 1 < n_t
+#pragma unroll
+            for (int m = 0; m < 8; m++) s[12 + m] = __ldg(px + 32 * m);
+        }
+        const unsigned int ua = __reduce_max_sync(0xffffffffu, __float_as_uint(pka));
+        const unsigned int ub = __reduce_max_sync(0xffffffffu, __float_as_uint(pkb));
+        int sh = (int)(ua >> 23) - (int)(ub >> 23);  // exponent difference of the two peaks
+        sh = (ua == 0u || ub == 0u) ? 0 : max(-60, min(60, sh));
+        const float gscale = __uint_as_float((unsigned)(127 + sh) << 23);
+        const float ginv = __uint_as_float((unsigned)(127 - sh) << 23);
+        if (sh != 0) {  // warp-uniform; the common case (similar levels) skips the rescale
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) r[n1].y *= gscale;
+        }
+        pv::phase_a_prod(lane, r, tw1, tw2, tw4, tw8, S);  // S[k1][n2] = W512^(n2 k1) sum_n1 z[n2 + 32 n1] W16^(n1 k1)  (ROW = 33)
+        __syncwarp();
+        // phase B: X[k1 + 16 (2 q + p)] = sum_{n2 < 16} (y[n2] + (-1)^p y[n2 + 16]) W32^(n2 p) W16^(n2 q)
+        {
+            const cpx *yrow = S + k1 * pv2::ROW;
+#pragma unroll
+            for (int n2 = 0; n2 < 16; n2++) r[n2] = pfma(yrow[n2 + 16], cpx{sgn, sgn}, yrow[n2]);
+        }
+        __syncwarp();  // S is rewritten by the next pair's phase A
+        if (p) pv2::tw32_nat<1>(r);
+        fft_dif<16>(r);  // r[slot] = X[k1 + 16 (2 bitrev(slot) + p)]
+        // the eight low bins k = lane + 32 i (q = i < 8) and their mirrors 512 - k = slot q = 15 - i of mirror_lane
+        float ma[8], mb[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const cpx hi = r[bitrev(15 - i, 4)];
+            cpx zm = cpx{__shfl_sync(0xffffffffu, hi.x, mirror_lane), __shfl_sync(0xffffffffu, hi.y, mirror_lane)};
+            if (i > 0 && lane == 0) zm = r[bitrev(16 - i, 4)];  // k = 32 i: 512 - k = 16 * 2 (16 - i), this lane's own slot
+            pv::untangle_mag<true, true>(r[bitrev(i, 4)], zm, ma[i], mb[i]);  // 2|A|, 2|B|: halved by ka / kb below
+        }
+        const cpx zn = r[bitrev(8, 4)];  // lane 0: Z[256], the Nyquist bin: A = |Re|, B = |Im| (aubio.rs:255-261, :403-405)
+        float nyq_a = 2.f * fabsf(zn.x), nyq_b = 2.f * fabsf(zn.y);
+        if (lane == 0) {  // DC: abs(re), aubio.rs:240 / :403
+            ma[0] = 2.f * fabsf(r[0].x);
+            mb[0] = 2.f * fabsf(r[0].y);
+        }
+        constexpr float kHalf = 0.5f / 1073741824.f;  // takes the window's 2^30 out again
+        const float ka = (ua == 0u) ? 0.f : kHalf;    // powers of two: exact
+        const float kb = (ub == 0u) ? 0.f : kHalf * ginv;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            ma[i] *= ka;
+            mb[i] *= kb;
+        }
+        nyq_a *= ka;
+        nyq_b *= kb;
+        // SpecFlux over the 257 correct bins of the tempo frame (aubio.rs:455-467)
+        float fl = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            fl += (mb[i] > old[i]) ? (mb[i] - old[i]) : 0.f;
+            old[i] = mb[i];
+        }
+        if (lane == 0) {
+            fl += (nyq_b > old256) ? (nyq_b - old256) : 0.f;
+            old256 = nyq_b;
+        }
+        fl = warp_sum(fl);
+        if (j >= j0) {  // not the halo pair
+            if (lane == 0) flux[sd.t_off + j] = fl;
+            float *Ta = T + (2 * trow) * pv2::TILE_ROW + lane, *Tb = Ta + pv2::TILE_ROW;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                Ta[32 * i + 4 * (i >> 1)] = ma[i];  // bin lane + 32 i at tpos = k + 4 (k >> 6)
+                Tb[32 * i + 4 * (i >> 1)] = mb[i];
+            }
+            if (lane == 0) {
+                Ta[pv2::NYQ_POS] = nyq_a;
+                Tb[pv2::NYQ_POS] = nyq_b;
+            }
+            trow++;
+            if (trow == pv2::TILE_PAIRS || j + 1 == j1) {
+                __syncwarp();
+                pv2::tile_descriptors(T, trow, lane, 2 * jt0, (int)sd.n_s, centroid + sd.s_off, rolloff + sd.s_off,
+                                      flatness + sd.s_off);
+                __syncwarp();
+                jt0 += trow;
+                trow = 0;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // STFT micro-benchmark kernel for the hop-256 framing (BASELINE.json config 3 = PVocTempo::do_,
 // src/aubio.rs:338-425), experimental (VARIANT_STFT_PAIRS): tempo frames j and j+1 ride ONE complex
 // 512-point FFT and BOTH are wanted, whereas pvoc512_kernel<false, true> transforms the hop-128 pair
@@ -614,6 +899,20 @@ int launch_pvoc512(const float *pcm, const SongDesc *songs, const unsigned int *
         BLISS_LAUNCH(kern, grid, 256, 0, st, pcm, songs, item_prefix, n_songs, total_items, pairs_per_item, tab, centroid, rolloff,
                                    flatness, flux, nullptr);
     };
+    if ((variant & VARIANT_PVOC_V1) == 0) {  // the round-2 kernel
+        constexpr int smem = 8 * pv2::WARP_SMEM_BYTES;
+#ifndef BLISS_HOST_EMUL
+        static bool opted = false;  // > 48 KB of dynamic shared memory is an opt-in
+        if (!opted) {
+            if (cudaFuncSetAttribute(pvoc512v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+            opted = true;
+        }
+#endif
+        float *const none = nullptr;
+        BLISS_LAUNCH(pvoc512v2_kernel, grid, 256, smem, st, pcm, songs, item_prefix, n_songs, total_items, pairs_per_item, tab,
+                     centroid, rolloff, flatness, flux, none);
+        return 1;
+    }
     const bool tw = (variant & VARIANT_PV_TWPROD) != 0, pd = (variant & VARIANT_PV_PAIRDESC) != 0,
                z4 = (variant & VARIANT_PV_ZPOS4) != 0;
     if (z4) {

@@ -116,7 +116,7 @@ int main(int argc, char **argv) {
         emu::launch((items + 7) / 8, 256, [&] {
             kern(x.data(), songs.data(), item_prefix.data(), 1, items, ppi, tab, cen.data(), rol.data(), fla.data(),
                  flux.data(), nullptr);
-        });
+        }, 8 * pv2::WARP_SMEM_BYTES);
         dump((std::string("centroid_") + tag).c_str(), cen);
         dump((std::string("rolloff_") + tag).c_str(), rol);
         dump((std::string("flatness_") + tag).c_str(), fla);
@@ -127,6 +127,7 @@ int main(int argc, char **argv) {
     run_pvoc("v1024", pvoc512_kernel<true, false, false, true>);
     run_pvoc("v2048", pvoc512_kernel<true, false, false, false, 4>);
     run_pvoc("v3584", pvoc512_kernel<true, false, true, true, 4>);
+    run_pvoc("v2", pvoc512v2_kernel);
 
     // ---- STFT micro-benchmark kernels ----------------------------------------------------------------------
     if (stages) {
@@ -265,7 +266,7 @@ int main(int argc, char **argv) {
             emu::launch((items + 7) / 8, 256, [&] {
                 pvoc_kern(x.data(), songs.data(), item_prefix.data(), 1, items, ppi, tab, cen.data(), rol.data(), fla.data(),
                           flux.data(), nullptr);
-            });
+            }, 8 * pv2::WARP_SMEM_BYTES);
             emu::launch((sd.n_t + 255) / 256, 256, [&] { peakpick_kernel(flux.data(), songs.data(), tp.data(), 1, sd.n_t, thr.data()); });
             emu::launch(1, 128, [&] {
                 beattrack_kernel<128>(thr.data(), eb.data(), songs.data(), bpm.data(), tempo.data(), nbpm.data(), 0);
@@ -373,7 +374,7 @@ int main(int argc, char **argv) {
             emu::launch((chp[k] + 7) / 8, 256, [&] { timedomain_kernel(x.data(), bs.data(), chp.data(), k, chp[k], loud.data(), eb.data(), zcr.data()); });
             emu::launch((k1p[k] + 7) / 8, 256, [&] {
                 pvoc_kern(x.data(), bs.data(), k1p.data(), k, k1p[k], bppi, tab, cen.data(), rol.data(), fla.data(), flux.data(), nullptr);
-            });
+            }, 8 * pv2::WARP_SMEM_BYTES);
             emu::launch((tpp[k] + 255) / 256, 256, [&] { peakpick_kernel(flux.data(), bs.data(), tpp.data(), k, tpp[k], thr.data()); });
             emu::launch((unsigned)k, 128, [&] { beattrack_kernel<128>(thr.data(), eb.data(), bs.data(), bpm.data(), tempo.data(), nbpm.data(), 0); });
             emu::launch(prp[k], K3_THREADS, [&] {

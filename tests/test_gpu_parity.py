@@ -640,6 +640,9 @@ def test_wav_files_through_the_decoder_pipeline(tmp_path, golden, pcm_piano):
 # process with a time limit.
 
 
+PVOC_V1 = 16384  # BLISS_B200_VARIANT bit: the round-1 pvoc512_kernel (its cuts are bits 512 / 1024 / 2048) instead of pvoc512v2_kernel
+
+
 def experimental(fn):
     """... and each of them runs in a CHILD pytest process with a time limit: a kernel that has never met hardware may
     fault (a sticky CUDA error would fail every later test of this process) or hang (and take the whole GPU run
@@ -726,9 +729,9 @@ def test_experimental_pvoc_twiddle_variant(pcm_song, pcm_piano):
     untouched."""
     songs = [pcm_song, pcm_piano] + _extra_tracks(79, 6, 30, 173)
     try:
-        B.native.set_variant(0)
+        B.native.set_variant(PVOC_V1)
         st0, f0 = B.native.analyze_batch(songs, 2)
-        B.native.set_variant(512)
+        B.native.set_variant(PVOC_V1 | 512)
         st, f = B.native.analyze_batch(songs, 2)
         assert (st0 == 0).all() and (st == 0).all()
         assert np.abs(f[:, 1:10] - f0[:, 1:10]).max() < 1e-5, np.abs(f - f0).max(0)
@@ -750,10 +753,10 @@ def test_experimental_pvoc_pair_descriptors_are_bit_identical(pcm_song, pcm_pian
     songs = [pcm_song, pcm_piano, np.concatenate([np.zeros(30000, np.float32), pcm_piano[:40000], np.zeros(5000, np.float32)])]
     songs += _extra_tracks(80, 5, 25, 97)
     try:
-        B.native.set_variant(0)
+        B.native.set_variant(PVOC_V1)
         st0, f0 = B.native.analyze_batch(songs, 2)
         _, _, taps0 = B.native.analyze_taps(pcm_song, 2)
-        B.native.set_variant(1024)
+        B.native.set_variant(PVOC_V1 | 1024)
         st, f = B.native.analyze_batch(songs, 2)
         _, _, taps = B.native.analyze_taps(pcm_song, 2)
         assert (st0 == 0).all() and (st == 0).all()
@@ -769,7 +772,7 @@ def test_experimental_pvoc_pair_descriptors_are_bit_identical(pcm_song, pcm_pian
         for k in ("centroid", "flatness", "flux"):
             assert np.allclose(taps[k], taps0[k], rtol=2e-6, atol=1e-9), k
         assert (taps["rolloff"] != taps0["rolloff"]).sum() <= 2  # a discrete bin: an ulp may move a frame by one bin
-        B.native.set_variant(1024 | 512)
+        B.native.set_variant(PVOC_V1 | 1024 | 512)
         st, f = B.native.analyze_batch(songs, 2)
         assert np.abs(f[:, 1:10] - f0[:, 1:10]).max() < 1e-5 and np.array_equal(f[:, 10:], f0[:, 10:])
     finally:
@@ -782,9 +785,9 @@ def test_experimental_pvoc_tile_padding_is_bit_identical(pcm_song, pcm_piano):
     k + (k >> 3) (conflict-free stores).  Only shared-memory addresses change: every feature bit for bit."""
     songs = [pcm_song, pcm_piano] + _extra_tracks(81, 4, 20, 59)
     try:
-        B.native.set_variant(0)
+        B.native.set_variant(PVOC_V1)
         st0, f0 = B.native.analyze_batch(songs, 2)
-        B.native.set_variant(2048)
+        B.native.set_variant(PVOC_V1 | 2048)
         st, f = B.native.analyze_batch(songs, 2)
         assert (st0 == 0).all() and (st == 0).all()
         assert np.array_equal(f, f0), np.abs(f - f0).max(0)
@@ -831,5 +834,35 @@ def test_experimental_odd_frame_rotation(pcm_song, pcm_piano):
         _, _, taps = B.native.analyze_taps(pcm_piano, 2)
         S = O.stft(pcm_piano, 8192, 2205)
         assert np.abs(taps["stft8192"].T - S).max() / S.max() < 2e-6
+    finally:
+        B.native.set_variant(0)
+
+
+@experimental
+def test_pvoc512v2_against_the_round1_kernel(pcm_song, pcm_piano):
+    """pvoc512v2_kernel (mask 0) against pvoc512_kernel (bit 16384): the same FFT pair packing, another split of the
+    32-point stage, register mirrors instead of the natural-order tile, descriptors reduced four lanes per frame.
+    Per-frame taps within the bars of the stage tests, features within 1e-5, everything behind the chroma STFT
+    untouched; parity with the oracle through the usual bar."""
+    silence = np.concatenate([np.zeros(30000, np.float32), pcm_piano[:40000], np.zeros(5000, np.float32)])
+    songs = [pcm_song, pcm_piano, silence] + _extra_tracks(83, 6, 30, 173)
+    try:
+        B.native.set_variant(PVOC_V1)
+        st0, f0 = B.native.analyze_batch(songs, 2)
+        _, _, taps0 = B.native.analyze_taps(pcm_song, 2)
+        B.native.set_variant(0)
+        st, f = B.native.analyze_batch(songs, 2)
+        _, _, taps = B.native.analyze_taps(pcm_song, 2)
+        assert (st0 == 0).all() and (st == 0).all()
+        assert np.abs(f[:, 1:10] - f0[:, 1:10]).max() < 1e-5, np.abs(f - f0).max(0)
+        assert np.array_equal(f[:, 10:], f0[:, 10:])
+        assert (np.abs(f[:, 0] - f0[:, 0]) < 1e-5).sum() >= len(songs) - 1  # a tempo decision may sit on an edge
+        assert np.allclose(taps["centroid"], taps0["centroid"], rtol=1e-5, atol=1e-3)
+        assert np.allclose(taps["flatness"], taps0["flatness"], rtol=2e-4, atol=1e-5)
+        assert np.abs(taps["flux"] - taps0["flux"]).max() <= 1e-5 * np.abs(taps0["flux"]).max()
+        assert np.mean(taps["rolloff"] != taps0["rolloff"]) < 2e-3
+        for i in (0, 1, 2):
+            rc, want = O.analyze(songs[i], 2)
+            assert rc == 0 and _close(f[i], want).all(), (i, np.abs(f[i] - want).max())
     finally:
         B.native.set_variant(0)
