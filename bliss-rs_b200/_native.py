@@ -26,7 +26,7 @@ class Taps(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "centroid", "rolloff", "flatness", "flux", "thresholded", "bpms", "n_bpms",
         "loudness_chunks", "zero_crossings", "stft8192", "n_peaks", "tuning", "chroma",
-        "interval_features")]
+        "interval_features", "peak_pitches", "peak_mags")]
 
 
 _lib = None
@@ -34,13 +34,13 @@ _inited_device = None
 
 # every symbol include/bliss_b200.h declares
 SYMBOLS = [
-    "bliss_b200_init", "bliss_b200_shutdown", "bliss_b200_set_workspace_limit", "bliss_b200_set_variant",
+    "bliss_b200_init", "bliss_b200_init_devices", "bliss_b200_device_count", "bliss_b200_shutdown", "bliss_b200_set_workspace_limit", "bliss_b200_set_variant",
     "bliss_b200_strerror",
     "bliss_b200_last_error", "bliss_b200_feature_count", "bliss_b200_analyze", "bliss_b200_analyze_batch",
     "bliss_b200_analyze_batch_s16", "bliss_b200_analyze_batch_pcm", "bliss_b200_pcm_to_mono",
     "bliss_b200_analyze_batch_device", "bliss_b200_feature_weights", "bliss_b200_distance",
     "bliss_b200_distance_matrix", "bliss_b200_distance_matrix_device", "bliss_b200_closest_to_songs",
-    "bliss_b200_song_to_song", "bliss_b200_stft512_mag_device", "bliss_b200_analyze_taps",
+    "bliss_b200_song_to_song", "bliss_b200_stft512_mag_device", "bliss_b200_analyze_taps", "bliss_b200_chroma_filter",
     "bliss_b200_set_profiling", "bliss_b200_get_profile", "bliss_b200_kernel_name",
     "bliss_b200_launch_count",
     "bliss_b200_gather_create", "bliss_b200_gather_connect", "bliss_b200_analyze_batch_device_scatter",
@@ -120,6 +120,22 @@ def init(device=None):
     check(L.bliss_b200_init(int(device)))
     _inited_device = device
     return L
+
+
+def init_devices(n_devices=0):
+    """bliss_b200_init_devices: contexts on devices 0 .. n-1 (0 = all visible); the host-buffer calls then shard one
+    call's songs over every device from this one process.  Returns the number of devices in use."""
+    global _inited_device
+    L = load()
+    n = L.bliss_b200_init_devices(int(n_devices))
+    if n <= 0:
+        check(n)
+    _inited_device = 0
+    return int(n)
+
+
+def device_count():
+    return int(load().bliss_b200_device_count())
 
 
 def lib():
@@ -350,11 +366,21 @@ def analyze_taps(pcm, version=2):
         "zero_crossings": np.zeros(1, np.uint32), "stft8192": np.zeros((n_c, 4097), np.float32),
         "n_peaks": np.zeros(1, np.uint64), "tuning": np.zeros(1, np.float64),
         "chroma": np.zeros((n_c, 12), np.float64), "interval_features": np.zeros(10, np.float64),
+        "peak_pitches": np.zeros(n_c * 714, np.float64), "peak_mags": np.zeros(n_c * 714, np.float64),
     }
     t = Taps(**{k: v.ctypes.data for k, v in a.items()})
     rc = check(L.bliss_b200_analyze_taps(pcm.ctypes.data, n, version, out.ctypes.data, C.byref(t)))
     a["bpms"] = a["bpms"][:int(a["n_bpms"][0])]
+    a["peak_pitches"] = a["peak_pitches"][:int(a["n_peaks"][0])]
+    a["peak_mags"] = a["peak_mags"][:int(a["n_peaks"][0])]
     return rc, out, a
+
+
+def chroma_filter(tuning_index):
+    """The device's chroma filterbank for tuning (-50 + tuning_index) / 100: f64 [12, 4097] (src/chroma.rs:197-267)."""
+    out = np.zeros((12, 4097), np.float64)
+    check(lib().bliss_b200_chroma_filter(int(tuning_index), out.ctypes.data))
+    return out
 
 
 def feature_weights(version=2):

@@ -13,6 +13,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bliss_b200.h"
@@ -164,7 +165,17 @@ struct Ctx {
     std::atomic<unsigned long long> launches{0};
 };
 
-Ctx g;
+// One context per device.  Slot 0 is the primary context (bliss_b200_init); bliss_b200_init_devices fills slots
+// 0 .. n-1 with devices 0 .. n-1, and the host-buffer entry points then shard one call's songs over all of them from
+// ONE process (the reference is one process: src/song/decoder.rs:282-331), one worker thread per device.  Every
+// function below reaches "its" context through `g`: the calling thread's current context (thread-local; the primary
+// one unless a multi-device dispatcher set another).
+constexpr int MAX_DEVICES = 16;
+Ctx g_ctx[MAX_DEVICES];
+std::atomic<int> g_n_ctx{0};          // initialised contexts (slots 0 .. n-1)
+std::mutex g_init_mu;                 // serialises init / shutdown of the context table
+thread_local Ctx *g_cur = &g_ctx[0];
+#define g (*g_cur)
 
 struct ProfScope {
     Ctx::EvPair pr{nullptr, nullptr, -1};
@@ -366,9 +377,14 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
     CK(cudaEventRecord(S.ev_fork, st));
     CK(cudaStreamWaitEvent(sb, S.ev_fork, 0));
     { ProfScope p(K_STFT8K, sb);
-      p.done(launch_stft8192(d_pcm, dv.sd, dv.pair_prefix, n, w.pair_prefix[n], g.t_hann8k.as<float>(),
-                             g.t_tw4k.as<cpx>(), g.t_tw2.as<cpx>(), g.t_tw8k.as<cpx>(), g.t_tw64.as<cpx>(), S.mags.as<float>(), S.cand_mag.as<double>(),
-                             S.cand_pitch.as<double>(), S.cand_count.as<unsigned int>(), g.variant, sb)); }
+      const int nl = launch_stft8192(d_pcm, dv.sd, dv.pair_prefix, n, w.pair_prefix[n], g.t_hann8k.as<float>(),
+                                     g.t_tw4k.as<cpx>(), g.t_tw2.as<cpx>(), g.t_tw8k.as<cpx>(), g.t_tw64.as<cpx>(), S.mags.as<float>(), S.cand_mag.as<double>(),
+                                     S.cand_pitch.as<double>(), S.cand_count.as<unsigned int>(), g.variant, sb);
+      p.done(nl);
+      if (nl < 0) {
+          g_last_error = "cudaFuncSetAttribute(stft8192v2_kernel, MaxDynamicSharedMemorySize) failed";
+          return BLISS_B200_E_CUDA;
+      } }
     { ProfScope p(K_TIME, st);
       p.done(launch_timedomain(d_pcm, dv.sd, dv.chunk_prefix, n, w.chunk_prefix[n], S.loud.as<float>(),
                                S.eb.as<float>(), S.zcr.as<unsigned int>(), st)); }
@@ -531,6 +547,16 @@ int build_tables() {
         hann[17408 + 4 * t + 2] = (float)sin(ta);
         hann[17408 + 4 * t + 3] = (float)sin(tb);
     }
+    // stft8192v2_kernel (stft8192_v2.cuh): the Hann phase of a frame rotated by r = 0..3 samples, [r][thread < 128]
+    // {cos phi_0..3, sin phi_0..3}, phi_j = 2 pi (4 thread + j - r) / 8192
+    hann.resize(2 * (8192 + 4 * 256) + 4 * 128 * 8);
+    for (int r = 0; r < 4; r++)
+        for (int t = 0; t < 128; t++)
+            for (int j = 0; j < 4; j++) {
+                const double ph = 2.0 * M_PI * (double)(4 * t + j - r) / 8192.0;
+                hann[2 * (8192 + 4 * 256) + (size_t)(r * 128 + t) * 8 + j] = (float)cos(ph);
+                hann[2 * (8192 + 4 * 256) + (size_t)(r * 128 + t) * 8 + 4 + j] = (float)sin(ph);
+            }
     // pass-1 twiddles [k1][b] = W4096^(b k1), pass-2 twiddles [k2][j] = W256^(j k2), and W8192^t, t < 256
     // (real-FFT untangling): rfft8192.cuh
     std::vector<cpx> tw4(4096), tw2(256), tw(256);
@@ -626,8 +652,8 @@ const char *bliss_b200_last_error(void) { return g_last_error.c_str(); }
 
 uint32_t bliss_b200_feature_count(uint16_t v) { return v == 2 ? 23u : v == 1 ? 20u : 0u; }
 
-int bliss_b200_init(int device) {
-    std::lock_guard<std::mutex> lk(g.mu);
+// initialise the calling thread's current context `g` on `device` (caller holds g.mu)
+static int init_ctx_locked(int device) {
     if (g.inited) {
         if (g.device == device) return BLISS_B200_OK;
         g_last_error = "already initialised on another device";
@@ -644,11 +670,8 @@ int bliss_b200_init(int device) {
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&g.ev_begin, cudaEventDisableTiming));
-    // BLISS_B200_STREAM_PRIORITY (experiment, unmeasured; default 0 = both chains at the same priority):
-    //   1 = the tempo / timbral chain's stream is preferred by the block scheduler: pvoc512 finishes first and the
-    //       latency-bound beat tracker runs under the rest of the chroma STFT instead of at the end of the step
-    //   2 = the chroma chain's stream is preferred: stft8192 finishes first, tuning and the HBM-bound contraction
-    //       run under the issue-bound pvoc512
+    // BLISS_B200_STREAM_PRIORITY (experiment; measured flat in round 2, profiles/ab_r02.md; default 0 = both chains at
+    // the same priority): 1 = the tempo / timbral chain's stream is preferred by the block scheduler, 2 = the chroma chain's
     int prio_main = 0, prio_side = 0;
     if (const char *e = getenv("BLISS_B200_STREAM_PRIORITY")) {
         int lo = 0, hi = 0;  // numerically lower = higher priority
@@ -680,7 +703,49 @@ int bliss_b200_init(int device) {
     return BLISS_B200_OK;
 }
 
-void bliss_b200_shutdown(void) {
+int bliss_b200_init(int device) {
+    std::lock_guard<std::mutex> lk0(g_init_mu);
+    g_cur = &g_ctx[0];
+    std::lock_guard<std::mutex> lk(g.mu);
+    const int rc = init_ctx_locked(device);
+    if (rc == BLISS_B200_OK && g_n_ctx.load() < 1) g_n_ctx = 1;
+    return rc;
+}
+
+// Multi-device form: contexts on devices 0 .. n_devices-1 (n_devices <= 0: every visible device).
+// Afterwards ONE call of bliss_b200_analyze_batch / _s16 / _pcm shards its songs over all of them (longest first onto
+// the least loaded device), one host thread and one copy stream per device, and bliss_b200_distance_matrix splits its
+// rows the same way.  The device-pointer entry points keep using the primary context (device 0).  Returns the number
+// of devices in use (> 0) or a negative error.
+int bliss_b200_init_devices(int n_devices) {
+    std::lock_guard<std::mutex> lk0(g_init_mu);
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        g_last_error = "no CUDA device visible";
+        return BLISS_B200_E_NO_DEVICE;
+    }
+    if (n_devices <= 0 || n_devices > count) n_devices = count;
+    n_devices = std::min(n_devices, MAX_DEVICES);
+    if (g_ctx[0].inited && g_ctx[0].device != 0) {
+        g_last_error = "the primary context is bound to a device other than 0: shut down first";
+        return BLISS_B200_E_ARG;
+    }
+    int rc = BLISS_B200_OK;
+    for (int d = 0; d < n_devices && rc == BLISS_B200_OK; d++) {
+        g_cur = &g_ctx[d];
+        std::lock_guard<std::mutex> lk(g.mu);
+        rc = init_ctx_locked(d);
+    }
+    g_cur = &g_ctx[0];
+    cudaSetDevice(0);
+    if (rc != BLISS_B200_OK) return rc;
+    if (g_n_ctx.load() < n_devices) g_n_ctx = n_devices;
+    return g_n_ctx.load();
+}
+
+int bliss_b200_device_count(void) { return g_n_ctx.load(); }
+
+static void shutdown_ctx() {  // the calling thread's current context
     std::lock_guard<std::mutex> lk(g.mu);
     if (!g.inited) return;
     cudaSetDevice(g.device);
@@ -708,21 +773,38 @@ void bliss_b200_shutdown(void) {
     g.inited = false;
 }
 
+void bliss_b200_shutdown(void) {
+    std::lock_guard<std::mutex> lk0(g_init_mu);
+    for (int d = MAX_DEVICES - 1; d >= 0; d--) {
+        g_cur = &g_ctx[d];
+        shutdown_ctx();
+    }
+    g_cur = &g_ctx[0];
+    g_n_ctx = 0;
+}
+
 // Diagnostic: which kernel implementations run (bit mask of common.cuh VARIANT_*; 0 = current).  Returns the
 // previous mask.  The environment variable BLISS_B200_VARIANT sets the initial value.
 int bliss_b200_set_variant(int mask) {
-    std::lock_guard<std::mutex> lk(g.mu);
     // The cuts promoted in round 2 (profiles/ab_r02.md) are ON for mask 0: the user's bit switches a kernel BACK to
     // its previous implementation, like bits 1..32; internally the promoted bits are stored inverted.
-    const int prev = g.variant ^ VARIANT_PROMOTED;
-    g.variant = mask ^ VARIANT_PROMOTED;
+    int prev = 0;
+    for (int d = std::max(1, g_n_ctx.load()) - 1; d >= 0; d--) {  // every context; the primary one's mask is returned
+        Ctx &c = g_ctx[d];
+        std::lock_guard<std::mutex> lk(c.mu);
+        prev = c.variant ^ VARIANT_PROMOTED;
+        c.variant = mask ^ VARIANT_PROMOTED;
+    }
     return prev;
 }
 
 int bliss_b200_set_workspace_limit(uint64_t bytes) {
-    std::lock_guard<std::mutex> lk(g.mu);
-    if (!g.inited) return BLISS_B200_E_NOT_INIT;
-    g.ws_limit = (size_t)bytes;
+    if (!g_ctx[0].inited) return BLISS_B200_E_NOT_INIT;
+    for (int d = 0; d < std::max(1, g_n_ctx.load()); d++) {
+        Ctx &c = g_ctx[d];
+        std::lock_guard<std::mutex> lk(c.mu);
+        c.ws_limit = (size_t)bytes;
+    }
     return BLISS_B200_OK;
 }
 
@@ -1096,10 +1178,79 @@ static int analyze_host_locked(const void *const *pcm_v, const uint64_t *n_sampl
     return rc;
 }
 
+// ---- one call, every device (bliss_b200_init_devices) --------------------------------------------------------
+// Songs are independent (Song::analyze is a pure function): the call's songs are dealt longest
+// first onto the least loaded device (LPT; equal lengths end up round-robin) and each device's share runs
+// analyze_host_locked on its own context from its own host thread -- its own copy stream, wave sets and PCM ring,
+// so the H2D copies of all devices are in flight together.  Per-song results do not depend on the device or on the
+// batch they travel in: the rows are bit-identical to a single-device call (tests/test_gpu_multidevice.py).
+static std::vector<std::vector<uint32_t>> shard_lpt(const uint64_t *n_samples, uint32_t n_songs, int nd) {
+    std::vector<uint32_t> order(n_songs);
+    for (uint32_t i = 0; i < n_songs; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return n_samples[a] > n_samples[b]; });
+    std::vector<std::vector<uint32_t>> mine((size_t)nd);
+    std::vector<uint64_t> load((size_t)nd, 0);
+    for (uint32_t i : order) {
+        int best = 0;
+        for (int d = 1; d < nd; d++)
+            if (load[d] < load[best]) best = d;
+        mine[best].push_back(i);
+        load[best] += n_samples[i] + 4096;  // a per-song constant keeps very short songs spread out as well
+    }
+    for (auto &v : mine) std::sort(v.begin(), v.end());  // original order inside a device: consecutive host buffers stay one copy
+    return mine;
+}
+
+static int analyze_host_multi(const void *const *pcm, const uint64_t *n_samples, uint32_t n_songs, uint16_t ver,
+                              float *out, int32_t *status, HostPcm hp) {
+    const int nd = g_n_ctx.load();
+    const uint32_t dim = bliss_b200_feature_count(ver);
+    const auto mine = shard_lpt(n_samples, n_songs, nd);
+    std::vector<int> rcs((size_t)nd, BLISS_B200_OK);
+    std::vector<std::string> errs((size_t)nd);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < nd; d++) {
+        if (mine[d].empty()) continue;
+        workers.emplace_back([&, d] {
+            g_cur = &g_ctx[d];
+            std::lock_guard<std::mutex> lk(g.mu);
+            const std::vector<uint32_t> &ids = mine[d];
+            const uint32_t m = (uint32_t)ids.size();
+            auto fail = [&](int rc) { rcs[d] = rc; errs[d] = g_last_error; };
+            if (!g.inited) { g_last_error = "device context not initialised"; return fail(BLISS_B200_E_NOT_INIT); }
+            if (cudaSetDevice(g.device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return fail(BLISS_B200_E_CUDA); }
+            std::vector<const void *> ptrs(m);
+            std::vector<uint64_t> lens(m);
+            for (uint32_t k = 0; k < m; k++) { ptrs[k] = pcm[ids[k]]; lens[k] = n_samples[ids[k]]; }
+            std::vector<float> lout((size_t)m * dim, 0.f);
+            std::vector<int32_t> lst(m, 0);
+            const int rc = analyze_host_locked(ptrs.data(), lens.data(), m, ver, lout.data(), lst.data(), false, hp);
+            if (rc) return fail(rc);
+            for (uint32_t k = 0; k < m; k++) {
+                if (lst[k] == 0) memcpy(out + (size_t)ids[k] * dim, lout.data() + (size_t)k * dim, (size_t)dim * 4);  // a rejected song's row is left alone
+                if (status) status[ids[k]] = lst[k];
+            }
+        });
+    }
+    for (auto &t : workers) t.join();
+    for (int d = 0; d < nd; d++)
+        if (rcs[d]) { g_last_error = "device " + std::to_string(d) + ": " + errs[d]; return rcs[d]; }
+    return BLISS_B200_OK;
+}
+
+// `true` when this call is to be sharded over several devices
+static bool use_all_devices(uint32_t n_songs) { return g_n_ctx.load() > 1 && n_songs > 1 && g_cur == &g_ctx[0]; }
+
 extern "C" {
 
 int bliss_b200_analyze_batch(const float *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
                              uint16_t ver, float *out, int32_t *status) {
+    if (use_all_devices(n_songs)) {
+        if (check_version(ver)) return BLISS_B200_E_ARG;
+        if (!pcm || !n_samples || !out) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
+        return analyze_host_multi(reinterpret_cast<const void *const *>(pcm), n_samples, n_songs, ver, out, status,
+                                  HostPcm{BLISS_B200_PCM_F32, 1});
+    }
     REQUIRE_INIT();
     if (check_version(ver)) return BLISS_B200_E_ARG;
     if (n_songs == 0) return BLISS_B200_OK;
@@ -1109,6 +1260,12 @@ int bliss_b200_analyze_batch(const float *const *pcm, const uint64_t *n_samples,
 
 int bliss_b200_analyze_batch_s16(const int16_t *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
                                  uint16_t ver, float *out, int32_t *status) {
+    if (use_all_devices(n_songs)) {
+        if (check_version(ver)) return BLISS_B200_E_ARG;
+        if (!pcm || !n_samples || !out) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
+        return analyze_host_multi(reinterpret_cast<const void *const *>(pcm), n_samples, n_songs, ver, out, status,
+                                  HostPcm{BLISS_B200_PCM_S16, 1});
+    }
     REQUIRE_INIT();
     if (check_version(ver)) return BLISS_B200_E_ARG;
     if (n_songs == 0) return BLISS_B200_OK;
@@ -1136,6 +1293,12 @@ static int check_pcm_format(int fmt, uint32_t channels, uint32_t sample_rate) {
 
 int bliss_b200_analyze_batch_pcm(const void *const *pcm, const uint64_t *n_frames, uint32_t n_songs, int sample_format,
                                  uint32_t channels, uint32_t sample_rate, uint16_t ver, float *out, int32_t *status) {
+    if (use_all_devices(n_songs)) {
+        if (check_version(ver)) return BLISS_B200_E_ARG;
+        if (int rc = check_pcm_format(sample_format, channels, sample_rate)) return rc;
+        if (!pcm || !n_frames || !out) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
+        return analyze_host_multi(pcm, n_frames, n_songs, ver, out, status, HostPcm{sample_format, channels});
+    }
     REQUIRE_INIT();
     if (check_version(ver)) return BLISS_B200_E_ARG;
     if (int rc = check_pcm_format(sample_format, channels, sample_rate)) return rc;
@@ -1209,6 +1372,12 @@ int bliss_b200_analyze_taps(const float *pcm, uint64_t n, uint16_t ver, float *o
         uint32_t c = 0;
         CK(cudaMemcpy(&c, g.ws[0].cand_count.p, 4, cudaMemcpyDeviceToHost));
         *t->n_peaks = c;
+    }
+    if (t->peak_pitches || t->peak_mags) {
+        unsigned int c = 0;
+        CK(cudaMemcpy(&c, g.ws[0].cand_count.p, 4, cudaMemcpyDeviceToHost));
+        CK(dl(t->peak_pitches, g.ws[0].cand_pitch.p, (size_t)c * sizeof(double)));
+        CK(dl(t->peak_mags, g.ws[0].cand_mag.p, (size_t)c * sizeof(double)));
     }
     if (t->tuning) {
         int idx = 0;
@@ -1310,9 +1479,33 @@ static int distance_matrix_host_locked(const float *rows, uint32_t n_rows, const
 
 int bliss_b200_distance_matrix(const float *rows, uint32_t n_rows, const float *cols, uint32_t n_cols,
                                uint32_t dim, int metric, const float *m, float *out) {
-    REQUIRE_INIT();
     if (!rows || !cols || !out || dim == 0 || dim > 64) { g_last_error = "bad argument"; return BLISS_B200_E_ARG; }
     if (n_rows == 0 || n_cols == 0) return BLISS_B200_OK;
+    const int nd = g_n_ctx.load();
+    if (nd > 1 && g_cur == &g_ctx[0] && (uint64_t)n_rows * n_cols >= (1ull << 22)) {
+        // row blocks over the devices: every entry is computed by the same kernel whatever the
+        // split, so the matrix is bit-identical to the single-device one
+        std::vector<int> rcs((size_t)nd, BLISS_B200_OK);
+        std::vector<std::string> errs((size_t)nd);
+        std::vector<std::thread> workers;
+        for (int d = 0; d < nd; d++) {
+            const uint32_t r0 = (uint32_t)((uint64_t)n_rows * d / nd), r1 = (uint32_t)((uint64_t)n_rows * (d + 1) / nd);
+            if (r1 == r0) continue;
+            workers.emplace_back([&, d, r0, r1] {
+                g_cur = &g_ctx[d];
+                std::lock_guard<std::mutex> lk(g.mu);
+                if (!g.inited || cudaSetDevice(g.device) != cudaSuccess) { rcs[d] = BLISS_B200_E_CUDA; errs[d] = "device context unavailable"; return; }
+                rcs[d] = distance_matrix_host_locked(rows + (size_t)r0 * dim, r1 - r0, cols, n_cols, dim, metric, m,
+                                                     out + (size_t)r0 * n_cols);
+                if (rcs[d]) errs[d] = g_last_error;
+            });
+        }
+        for (auto &t : workers) t.join();
+        for (int d = 0; d < nd; d++)
+            if (rcs[d]) { g_last_error = "device " + std::to_string(d) + ": " + errs[d]; return rcs[d]; }
+        return BLISS_B200_OK;
+    }
+    REQUIRE_INIT();
     return distance_matrix_host_locked(rows, n_rows, cols, n_cols, dim, metric, m, out);
 }
 
@@ -1417,6 +1610,22 @@ int bliss_b200_get_profile(double *ms, uint64_t *launches) {
 
 const char *bliss_b200_kernel_name(int k) { return (k >= 0 && k < BLISS_B200_N_KERNELS) ? kKernelNames[k] : ""; }
 
-uint64_t bliss_b200_launch_count(void) { return (uint64_t)g.launches.load(); }
+int bliss_b200_chroma_filter(int tuning_index, double *out) {
+    REQUIRE_INIT();
+    if (!out || tuning_index < 0 || tuning_index > 99) { g_last_error = "tuning_index must be 0..99"; return BLISS_B200_E_ARG; }
+    // device layout [idx][bin][12] (chroma.cu) -> [12][4097] as chroma_filter returns it
+    std::vector<double> t((size_t)CH_BINS * 12);
+    CK(cudaMemcpy(t.data(), g.t_filt.as<double>() + (size_t)tuning_index * CH_BINS * 12, t.size() * sizeof(double),
+                  cudaMemcpyDeviceToHost));
+    for (int b = 0; b < CH_BINS; b++)
+        for (int c = 0; c < 12; c++) out[(size_t)c * CH_BINS + b] = t[(size_t)b * 12 + c];
+    return BLISS_B200_OK;
+}
+
+uint64_t bliss_b200_launch_count(void) {
+    uint64_t n = 0;
+    for (int d = 0; d < std::max(1, g_n_ctx.load()); d++) n += (uint64_t)g_ctx[d].launches.load();
+    return n;
+}
 
 }  // extern "C"

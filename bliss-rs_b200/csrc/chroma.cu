@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "rfft8192.cuh"
 #include "rfft8192_r64.cuh"
+#include "stft8192_v2.cuh"
 
 namespace bliss {
 
@@ -1247,6 +1248,18 @@ int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int 
                     const cpx *tw8192, const cpx *tw64, float *mags, double *cand_mag, double *cand_pitch,
                     unsigned int *cand_count, int variant, cudaStream_t st) {
     if (total_frames == 0) return 0;
+    if ((variant & (VARIANT_STFT_V1 | VARIANT_R64 | VARIANT_OLD_EPILOGUE)) == 0) {  // the round-2 kernel (stft8192_v2.cuh)
+#ifndef BLISS_HOST_EMUL
+        // > 48 KB of dynamic shared memory is an opt-in, per device: set on every launch
+        if (cudaFuncSetAttribute(stft8192v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2::SMEM_BYTES) != cudaSuccess)
+            return -1;
+#endif
+        const unsigned int grid = (total_frames + s2::ITEMS_PER_CTA - 1) / s2::ITEMS_PER_CTA;
+        const int fpi = K3_FRAMES_PER_CTA;
+        BLISS_LAUNCH(stft8192v2_kernel, grid, s2::THREADS, s2::SMEM_BYTES, st, pcm, songs, frame_prefix, n_songs, total_frames, fpi, hann,
+                     tw1, tw2, tw8192, mags, cand_mag, cand_pitch, cand_count);
+        return 1;
+    }
     if (variant & VARIANT_R64) {
         auto go64 = [&](auto kern) {
             BLISS_LAUNCH(kern, total_frames, K3R_THREADS, 0, st, pcm, songs, frame_prefix, n_songs, hann, tw64, tw8192, mags,
@@ -1309,12 +1322,9 @@ int launch_chroma(const float *mags, const SongDesc *songs, const unsigned int *
         BLISS_LAUNCH(chroma_kernel, total_tiles, K5_THREADS, 0, st, mags, songs, tile_prefix, n_songs, filt_table,
                                                          tuning_idx, tile_partials, chroma_dbg);
     } else {
-        static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in (per device, once)
-        if (!attr_set) {
-            if (cudaFuncSetAttribute(chroma_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K5P_SMEM) != cudaSuccess)
-                return -1;
-            attr_set = true;
-        }
+        // > 48 KB of dynamic shared memory needs the opt-in, per device: set on every launch
+        if (cudaFuncSetAttribute(chroma_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K5P_SMEM) != cudaSuccess)
+            return -1;
         BLISS_LAUNCH(chroma_pipe_kernel, total_tiles, K5_THREADS, K5P_SMEM, st, mags, songs, tile_prefix, n_songs, filt_table,
                                                                      tuning_idx, tile_partials, chroma_dbg);
     }

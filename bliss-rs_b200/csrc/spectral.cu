@@ -902,11 +902,9 @@ int launch_pvoc512(const float *pcm, const SongDesc *songs, const unsigned int *
     if ((variant & VARIANT_PVOC_V1) == 0) {  // the round-2 kernel
         constexpr int smem = 8 * pv2::WARP_SMEM_BYTES;
 #ifndef BLISS_HOST_EMUL
-        static bool opted = false;  // > 48 KB of dynamic shared memory is an opt-in
-        if (!opted) {
-            if (cudaFuncSetAttribute(pvoc512v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-            opted = true;
-        }
+        // > 48 KB of dynamic shared memory is an opt-in, per device: set on every launch (cheap, and correct for any
+        // number of devices and host threads)
+        if (cudaFuncSetAttribute(pvoc512v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
 #endif
         float *const none = nullptr;
         BLISS_LAUNCH(pvoc512v2_kernel, grid, 256, smem, st, pcm, songs, item_prefix, n_songs, total_items, pairs_per_item, tab,

@@ -51,6 +51,15 @@ extern "C" {
  * (windows, twiddles, the 100 chroma filterbanks of src/chroma.rs:197-267).
  * Idempotent for the same device.  Fails with E_NO_DEVICE when no GPU is present. */
 int bliss_b200_init(int device);
+/* Every B200 of the box behind ONE process (the reference is one process: worker threads + a channel,
+ * src/song/decoder.rs:282-331): contexts on devices 0 .. n_devices-1 (n_devices <= 0: all visible devices).
+ * Afterwards one call of bliss_b200_analyze_batch / _s16 / _pcm deals its songs longest-first over all devices (one
+ * host thread, copy stream and PCM ring per device) and bliss_b200_distance_matrix splits its rows; results are
+ * bit-identical to a single-device call.  The device-pointer entry points keep using device 0.
+ * Returns the number of devices in use (> 0) or a negative error code. */
+int bliss_b200_init_devices(int n_devices);
+/* Number of devices the host-buffer calls use (0 before init). */
+int bliss_b200_device_count(void);
 void bliss_b200_shutdown(void);
 /* Upper bound on device scratch memory a call may hold (default: 40% of the device). */
 int bliss_b200_set_workspace_limit(uint64_t bytes);
@@ -212,9 +221,15 @@ typedef struct {
     double *tuning;
     double *chroma;
     double *interval_features;
+    double *peak_pitches;   /* pip_track (src/chroma.rs:269-331): interpolated pitches [Hz] and magnitudes of the */
+    double *peak_mags;      /* n_peaks candidates, in no particular order; capacity n_c x 714 each */
 } bliss_b200_taps;
 int bliss_b200_analyze_taps(const float *pcm, uint64_t n_samples, uint16_t features_version, float *out,
                             const bliss_b200_taps *taps);
+/* One of the 100 chroma filterbanks the contraction multiplies with (chroma_filter, src/chroma.rs:197-267, for
+ * tuning = (-50 + tuning_index) / 100, tuning_index 0..99): out[12][4097] f64, rows = chroma bins as the reference
+ * returns them (pinned by data/chroma-filter.npy at 1e-9, src/chroma.rs:705-714). */
+int bliss_b200_chroma_filter(int tuning_index, double *out);
 
 /* Per-kernel device time (CUDA events on the launching stream) accumulated while profiling is
  * on.  Kernel ids: 0 pvoc512, 1 timedomain, 2 stft8192, 3 tuning, 4 chroma, 5 peakpick,

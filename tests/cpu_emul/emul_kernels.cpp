@@ -90,6 +90,14 @@ int main(int argc, char **argv) {
         hann[17408 + 4 * t + 2] = (float)sin(ta);
         hann[17408 + 4 * t + 3] = (float)sin(tb);
     }
+    hann.resize(2 * (8192 + 4 * 256) + 4 * 128 * 8);  // stft8192v2_kernel's rotated phases (api.cu build_tables)
+    for (int r = 0; r < 4; r++)
+        for (int t = 0; t < 128; t++)
+            for (int j = 0; j < 4; j++) {
+                const double ph = 2.0 * M_PI * (double)(4 * t + j - r) / 8192.0;
+                hann[2 * (8192 + 4 * 256) + (size_t)(r * 128 + t) * 8 + j] = (float)cos(ph);
+                hann[2 * (8192 + 4 * 256) + (size_t)(r * 128 + t) * 8 + 4 + j] = (float)sin(ph);
+            }
     std::vector<cpx> tw4(4096), tw2(256), tw8(256);
     for (int k1 = 0; k1 < 16; k1++)
         for (int b = 0; b < 256; b++) {
@@ -212,6 +220,26 @@ int main(int argc, char **argv) {
             dump((std::string("peak_mags_") + tag).c_str(), cm);
             dump((std::string("peak_pitches_") + tag).c_str(), cp);
         };
+        {   // stft8192v2_kernel (round 2): 128 threads, bulk-copy staging, four work items per CTA
+            std::vector<float> mags((size_t)sd.n_c_comp * CH_STRIDE, -7.f);
+            std::vector<double> cm((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.), cp((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.);
+            std::vector<unsigned> cc(1, 0u);
+            emu::launch((ctas + s2::ITEMS_PER_CTA - 1) / s2::ITEMS_PER_CTA, s2::THREADS, [&] {
+                stft8192v2_kernel(x.data(), songs.data(), fp.data(), 1, ctas, K3_FRAMES_PER_CTA, hann.data(), tw4.data(), tw2.data(),
+                                  tw8.data(), mags.data(), cm.data(), cp.data(), cc.data());
+            }, s2::SMEM_BYTES);
+            std::vector<float> dense((size_t)sd.n_c_comp * CH_BINS);
+            for (unsigned f = 0; f < sd.n_c_comp; f++)
+                memcpy(&dense[(size_t)f * CH_BINS], &mags[(size_t)f * CH_STRIDE], CH_BINS * 4);
+            dump("stft8192_v2", dense);
+            dump("peaks_v2", cc);
+            cm.resize(cc[0]);
+            cp.resize(cc[0]);
+            std::sort(cm.begin(), cm.end());
+            std::sort(cp.begin(), cp.end());
+            dump("peak_mags_v2", cm);
+            dump("peak_pitches_v2", cp);
+        }
         run_stft("default", stft8192_kernel<true>);
         run_stft("v64", stft8192_kernel<true, K3V_TWPROD>);
         run_stft("v128", stft8192_kernel<true, K3V_WINSYN>);

@@ -122,6 +122,18 @@ def _stage_checks(pcm, label):
     assert abs(t["tuning"][0] - otuning) < 1e-9, (t["tuning"][0], otuning)
     p, m = O.pip_track(S, 8192)
     assert abs(int(t["n_peaks"][0]) - p.size) <= max(2, p.size // 2000)
+    # pip_track's own arithmetic (src/chroma.rs:269-331; the reference pins pitches and magnitudes at 1e-8 sorted,
+    # :682-702): the oracle run on the DEVICE's magnitudes must give the device's candidates
+    pd, md = O.pip_track(t["stft8192"].T.astype(np.float64), 8192)
+    assert pd.size == int(t["n_peaks"][0]) == t["peak_pitches"].size
+    if pd.size:
+        pe = np.abs(np.sort(t["peak_pitches"]) - np.sort(pd)).max()
+        me = np.abs(np.sort(t["peak_mags"]) - np.sort(md)).max() / max(1e-30, np.abs(md).max())
+        print(label, "pip_track on the device's magnitudes: pitch err %.2e Hz, mag err (rel. to max) %.2e" % (pe, me))
+        assert pe < 1e-8 and me < 1e-12
+    # loudness chunks (level_lin per chunk, tail chunk kept: src/misc.rs:12-18, src/song/mod.rs:478)
+    ms = np.array([np.mean(pcm[i:i + 1024].astype(np.float64) ** 2) for i in range(0, pcm.size, 1024)])
+    assert t["loudness_chunks"].shape == ms.shape and np.abs(t["loudness_chunks"] - ms).max() <= 1e-6 * max(ms.max(), 1e-30)
     ch = np.abs(t["chroma"].T - ocm).max()
     print(label, "chroma max abs err %.2e" % ch)
     assert ch < 2e-5
@@ -640,6 +652,7 @@ def test_wav_files_through_the_decoder_pipeline(tmp_path, golden, pcm_piano):
 # process with a time limit.
 
 
+STFT_V1 = 32768  # BLISS_B200_VARIANT bit: the round-1 stft8192_kernel (its cuts are bits 64 / 128 / 4096 / 8192) instead of stftv2
 PVOC_V1 = 16384  # BLISS_B200_VARIANT bit: the round-1 pvoc512_kernel (its cuts are bits 512 / 1024 / 2048) instead of pvoc512v2_kernel
 
 
@@ -675,11 +688,11 @@ def test_experimental_pass1_variants_agree(pcm_song, pcm_piano):
     from the reference's f32 table by <= 2.4e-7) and must agree with the measured kernel to 1e-5."""
     songs = [pcm_song, pcm_piano] + _extra_tracks(78, 6, 35, 211)
     try:
-        B.native.set_variant(0)
+        B.native.set_variant(STFT_V1)
         st0, f0 = B.native.analyze_batch(songs, 2)
         assert (st0 == 0).all()
         for mask in (64, 128, 64 | 128):
-            B.native.set_variant(mask)
+            B.native.set_variant(STFT_V1 | mask)
             st, f = B.native.analyze_batch(songs, 2)
             assert (st == 0).all()
             assert np.abs(f - f0).max() < 1e-5, (mask, np.abs(f - f0).max(0))
@@ -801,10 +814,10 @@ def test_experimental_fft8192_buffer_layout_is_bit_identical(pcm_song, pcm_piano
     loads in the pair epilogue).  Only shared-memory addresses change: every feature and every magnitude bit for bit."""
     songs = [pcm_song, pcm_piano] + _extra_tracks(82, 4, 20, 61)
     try:
-        B.native.set_variant(0)
+        B.native.set_variant(STFT_V1)
         st0, f0 = B.native.analyze_batch(songs, 2)
         _, _, taps0 = B.native.analyze_taps(pcm_piano, 2)
-        B.native.set_variant(4096)
+        B.native.set_variant(STFT_V1 | 4096)
         st, f = B.native.analyze_batch(songs, 2)
         _, _, taps = B.native.analyze_taps(pcm_piano, 2)
         assert (st0 == 0).all() and (st == 0).all()
@@ -822,15 +835,15 @@ def test_experimental_odd_frame_rotation(pcm_song, pcm_piano):
     measured kernel, nothing outside the chroma features touched."""
     songs = [pcm_song, pcm_piano] + _extra_tracks(83, 4, 20, 67)
     try:
-        B.native.set_variant(0)
+        B.native.set_variant(STFT_V1)
         st0, f0 = B.native.analyze_batch(songs, 2)
         # ... and the same two load cuts on the radix-64 kernel (bit 32)
         for mask in (8192, 8192 | 4096 | 128 | 64, 32 | 128, 32 | 8192, 32 | 8192 | 128):
-            B.native.set_variant(mask)
+            B.native.set_variant(STFT_V1 | mask)
             st, f = B.native.analyze_batch(songs, 2)
             assert (st == 0).all() and np.abs(f - f0).max() < 1e-5, (mask, np.abs(f - f0).max(0))
             assert np.array_equal(f[:, :10], f0[:, :10])
-        B.native.set_variant(8192)
+        B.native.set_variant(STFT_V1 | 8192)
         _, _, taps = B.native.analyze_taps(pcm_piano, 2)
         S = O.stft(pcm_piano, 8192, 2205)
         assert np.abs(taps["stft8192"].T - S).max() / S.max() < 2e-6
@@ -866,3 +879,55 @@ def test_pvoc512v2_against_the_round1_kernel(pcm_song, pcm_piano):
             assert rc == 0 and _close(f[i], want).all(), (i, np.abs(f[i] - want).max())
     finally:
         B.native.set_variant(0)
+
+
+@experimental
+def test_stft8192v2_against_the_round1_kernel(pcm_song, pcm_piano):
+    """stft8192v2_kernel (mask 0: bulk-copy staging, frames rotated to a 16-byte boundary, mirror pairs in registers,
+    bulk-stored magnitude rows) against stft8192_kernel (bit 32768).  Magnitudes of both within 2e-6 of the
+    oracle's STFT, the same pip_track candidates (count, and sorted pitches / magnitudes against the oracle's f64
+    interpolation), identical tuning, features within 1e-5, nothing outside the chroma features touched.  Songs sit
+    at every offset mod 4 of one device buffer (CUE-style slices), so all four rotations and both edge paths run."""
+    songs = [pcm_song, pcm_piano, pcm_song[1:], pcm_song[2:90001], pcm_piano[3:]] + _extra_tracks(84, 4, 25, 61)
+    try:
+        B.native.set_variant(STFT_V1)
+        st0, f0 = B.native.analyze_batch(songs, 2)
+        _, _, taps0 = B.native.analyze_taps(pcm_piano, 2)
+        B.native.set_variant(0)
+        st, f = B.native.analyze_batch(songs, 2)
+        _, _, taps = B.native.analyze_taps(pcm_piano, 2)
+        assert (st0 == 0).all() and (st == 0).all()
+        assert np.abs(f - f0).max() < 1e-5, np.abs(f - f0).max(0)
+        assert np.array_equal(f[:, :10], f0[:, :10])
+        S = O.stft(pcm_piano, 8192, 2205)
+        assert np.abs(taps["stft8192"].T - S).max() / S.max() < 2e-6
+        assert np.abs(taps0["stft8192"].T - S).max() / S.max() < 2e-6
+        assert taps["tuning"] == taps0["tuning"]
+        assert taps["n_peaks"] == taps0["n_peaks"]
+        # unaligned slices of ONE device buffer through the device API: offsets 0, 1, 2, 3 mod 4
+        import torch
+        flat = torch.from_numpy(np.concatenate([pcm_song, pcm_piano])).to(DEV)
+        offs = [0, 1, 2, 3, len(pcm_song) + 1, len(pcm_song) + 6]
+        lens = [50001, 50002, 60003, 70000, 40001, 44444]
+        out = torch.zeros((len(offs), 23), dtype=torch.float32, device=DEV)
+        B.native.analyze_batch_device(flat.data_ptr(), offs, lens, 2, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        host = flat.cpu().numpy()
+        for i, (o, l) in enumerate(zip(offs, lens)):
+            rc, want = O.analyze(host[o:o + l], 2)
+            assert rc == 0 and _close(got[i], want).all(), (i, np.abs(got[i] - want).max())
+    finally:
+        B.native.set_variant(0)
+
+
+def test_device_chroma_filter_tables():
+    """chroma_filter_table_kernel: the device's filterbank (the f64 table the f32 contraction weights are rounded
+    from) against the oracle's chroma_filter for tunings {-0.5, -0.05, 0, 0.49} at the reference's own 1e-9
+    (src/chroma.rs:705-714, data/chroma-filter.npy pins the oracle in tests/test_oracle_golden.py)."""
+    for idx in (0, 45, 50, 99):
+        tuning = (-50.0 + idx) / 100.0
+        got = B.native.chroma_filter(idx)
+        want = O.chroma_filter(8192, tuning)
+        assert got.shape == want.shape == (12, 4097)
+        assert np.abs(got - want).max() < 1e-9, (idx, np.abs(got - want).max())
