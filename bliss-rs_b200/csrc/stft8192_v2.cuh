@@ -4,8 +4,10 @@
 //
 //   * TMA staging.  One elected thread streams the frame's 8192 samples global -> shared with ONE 1-D bulk copy
 //     (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP), issued a whole frame ahead: no sample or window load
-//     ever touches the LSU, no register is held across the load latency.  The finished magnitude row leaves the
-//     same way (shared -> global bulk store of 4 100 floats): no global store wavefronts either.
+//     ever touches the LSU, no register is held across the load latency.  (The first cut also sent the finished
+//     magnitude row out as a shared -> global bulk store; measured on B200 the CTA then sat at a barrier waiting
+//     for the store's reads of the row -- 12 % of all stall samples, profiles/ncu_r02_stft8192v2_first_128songs.md
+//     -- so the magnitudes now leave the registers as 128-byte warp stores and only bins < 1536 are staged for pip_track.)
 //   * Alignment by rotation.  A frame starts at any sample (hop 2205, arbitrary song offsets); the bulk copy
 //     starts at the 16-byte boundary below it and the frame is transformed ROTATED by r = start & 3 samples,
 //     y'[m] = y[(m - r) mod 8192]: |DFT| is unchanged, every load is an aligned 128-bit one, and the only samples
@@ -36,10 +38,10 @@ constexpr int THREADS = 128;
 constexpr int ITEMS_PER_CTA = 4;           // work items (of K3_FRAMES_PER_CTA = 4 frames each) one CTA walks
 constexpr int Y_CPX = 258 * 16;            // 4128 complex = 33 024 B
 constexpr int X_FLOATS = 8256;             // 8192 + 4 staged samples, rounded to the size of Y
-constexpr int ROW_FLOATS = 4100;           // 4097 magnitudes rounded up to 16 bytes (bulk store granularity)
+constexpr int PIP_FLOATS = 1536;           // magnitudes of bins 0..1535 staged for pip_track (centre bins 57..1483)
 constexpr float KSCALE = 1073741824.f;     // 2^30 carried by the window
 constexpr float KINV = 0.5f / 1073741824.f;  // takes it out again, with the 1/2 of the real-input untangling
-constexpr size_t SMEM_BYTES = (size_t)X_FLOATS * 4 + (size_t)Y_CPX * 8 + 256;
+constexpr size_t SMEM_BYTES = (size_t)X_FLOATS * 4 + (size_t)Y_CPX * 8 + (size_t)PIP_FLOATS * 4 + 512;
 constexpr int PHASE_OFF = 2 * (8192 + 4 * 256);  // float offset of the [4][128][8] rotated-phase table behind the Hann tables
 
 // exp(-2 pi i A / 4096), A = 1..15 (f64-rounded-to-f32): the rotation between a thread's two pass-1 columns
@@ -89,21 +91,11 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned b
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// shared -> global bulk store (one bulk group per call)
-__device__ __forceinline__ void bulk_store(void *dst, const void *src, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #else
 inline void mbar_init(unsigned long long *, int) {}
 inline void mbar_arrive(unsigned long long *) {}
 inline void mbar_wait(unsigned long long *, unsigned) {}
 inline void bulk_load(void *dst, const void *src, unsigned bytes, unsigned long long *) { memcpy(dst, src, bytes); }
-inline void bulk_store(void *dst, const void *src, unsigned bytes) { memcpy(dst, src, bytes); }
-inline void bulk_store_wait_read() {}
-inline void fence_async_smem() {}
 #endif
 
 struct FrameDesc {           // what the CTA needs to know about one frame (written by thread 0, one frame ahead)
@@ -116,6 +108,7 @@ struct FrameDesc {           // what the CTA needs to know about one frame (writ
 // thread 0's cursor over the CTA's frames: items [item, item_end) of K3_FRAMES_PER_CTA consecutive frames each
 struct Cursor {   // lives in shared memory: only thread 0 touches it
     unsigned int item, item_end;
+    unsigned int song_item0, song_item1;  // the items [song_item0, song_item1) belong to song si
     int f, fend, si;
     SongDesc sd;
 };
@@ -123,9 +116,13 @@ struct Cursor {   // lives in shared memory: only thread 0 touches it
 __device__ __forceinline__ bool cursor_load_item(Cursor &c, const SongDesc *songs, const unsigned int *frame_prefix,
                                                  int n_songs, int frames_per_item) {
     while (c.item < c.item_end) {
-        c.si = find_song(frame_prefix, n_songs, c.item);
-        c.sd = songs[c.si];
-        c.f = (int)(c.item - frame_prefix[c.si]) * frames_per_item;
+        if (c.item < c.song_item0 || c.item >= c.song_item1) {  // another song: the only global loads of the cursor
+            c.si = find_song(frame_prefix, n_songs, c.item);
+            c.sd = songs[c.si];
+            c.song_item0 = frame_prefix[c.si];
+            c.song_item1 = frame_prefix[c.si + 1];
+        }
+        c.f = (int)(c.item - c.song_item0) * frames_per_item;
         c.fend = min(c.f + frames_per_item, (int)c.sd.n_c_comp);
         if (c.f < c.fend) return true;
         c.item++;
@@ -192,38 +189,20 @@ BLISS_HD void untangle_pair(cpx zk, cpx zm, cpx w, float &mag_k, float &mag_m) {
     mag_m = mag_of(padd(e, cpx{-p.y, p.x}));
 }
 
+// bins k = u + 256 C (from the thread's column) and 4096 - k (from its mirror column): straight to the spill row
+// (consecutive threads -> consecutive floats: 128-byte warp stores); bins < 1536 also to the pip_track buffer
 template <int C>
-BLISS_HD void epilogue_generic(const cpx (&v1)[16], const cpx (&v2)[16], cpx wt, float *lo, float *hi, float &mx) {
+BLISS_HD void epilogue_generic(const cpx (&v1)[16], const cpx (&v2)[16], cpx wt, float *glo, float *ghi, float *plo,
+                               float *phi, float &mx) {
     if constexpr (C < 16) {
         float a, b;
         untangle_pair(v1[bitrev(C, 4)], v2[bitrev(15 - C, 4)], mul_tw<C, 32>(wt), a, b);
-        lo[256 * C] = a;    // k = u + 256 C
-        hi[-256 * C] = b;   // 4096 - k
+        glo[256 * C] = a;    // k = u + 256 C
+        ghi[-256 * C] = b;   // 4096 - k
+        if constexpr (C < 6) plo[256 * C] = a;
+        if constexpr (C >= 10) phi[-256 * C] = b;
         mx = fmaxf(mx, fmaxf(a, b));
-        epilogue_generic<C + 1>(v1, v2, wt, lo, hi, mx);
-    }
-}
-// thread 0: column 0 (self-mirrored: k = 256 C <-> 256 (16 - C)) in v1, column 128 (k = 128 + 256 C <-> 128 + 256 (15 - C)) in v2
-template <int C>
-BLISS_HD void epilogue_col0(const cpx (&v1)[16], float *row, float &mx) {
-    if constexpr (C < 8) {
-        float a, b;
-        untangle_pair(v1[bitrev(C, 4)], v1[bitrev((16 - C) & 15, 4)], mul_tw<C, 32>(cpx{1.f, 0.f}), a, b);
-        row[256 * C] = a;          // C = 0: X[0] = Re Z0 + Im Z0 ...
-        row[4096 - 256 * C] = b;   // ... and X[4096] = Re Z0 - Im Z0
-        mx = fmaxf(mx, fmaxf(a, b));
-        epilogue_col0<C + 1>(v1, row, mx);
-    }
-}
-template <int C>
-BLISS_HD void epilogue_col128(const cpx (&v2)[16], cpx w128, float *row, float &mx) {
-    if constexpr (C < 8) {
-        float a, b;
-        untangle_pair(v2[bitrev(C, 4)], v2[bitrev(15 - C, 4)], mul_tw<C, 32>(w128), a, b);
-        row[128 + 256 * C] = a;
-        row[4096 - 128 - 256 * C] = b;
-        mx = fmaxf(mx, fmaxf(a, b));
-        epilogue_col128<C + 1>(v2, w128, row, mx);
+        epilogue_generic<C + 1>(v1, v2, wt, glo, ghi, plo, phi, mx);
     }
 }
 
@@ -242,8 +221,10 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
     extern __shared__ __align__(128) unsigned char s2_smem[];
 #endif
     float *X = reinterpret_cast<float *>(s2_smem);                    // staged samples (bulk-copy destination)
-    cpx *Y = reinterpret_cast<cpx *>(s2_smem + s2::X_FLOATS * 4);    // FFT buffer, then the magnitude row
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(s2_smem + s2::X_FLOATS * 4 + s2::Y_CPX * 8);
+    cpx *Y = reinterpret_cast<cpx *>(s2_smem + s2::X_FLOATS * 4);    // FFT buffer (three passes in place)
+    float *P = reinterpret_cast<float *>(s2_smem + s2::X_FLOATS * 4 + s2::Y_CPX * 8);  // magnitudes of bins < 1536 for pip_track
+    cpx *S0 = reinterpret_cast<cpx *>(P + s2::PIP_FLOATS);                             // thread 0's two self-mirrored columns (32 cpx)
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(S0 + 32);
     __shared__ s2::FrameDesc s_fd[2];
     __shared__ s2::Cursor cur;  // thread 0's cursor over the CTA's frames
     __shared__ float s_red[s2::THREADS / 32];
@@ -272,6 +253,7 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
         s2::mbar_init(bar, 1);
         cur.item = blockIdx.x * (unsigned)s2::ITEMS_PER_CTA;
         cur.item_end = min(cur.item + (unsigned)s2::ITEMS_PER_CTA, total_items);
+        cur.song_item0 = cur.song_item1 = 0u;
         s_fd[0].valid = 0;
         s_fd[1].valid = 0;
         if (s2::cursor_load_item(cur, songs, frame_prefix, n_songs, frames_per_item)) {
@@ -382,7 +364,6 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
             }
         }
         // ---- pass 3 on the thread's column and its mirror column; untangling in registers --------------------------
-        float *row = reinterpret_cast<float *>(Y);
         float mx = 0.f;
         {
             cpx v1[16], v2[16];
@@ -395,36 +376,64 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
                 v2[2 * c] = cpx{b.x, b.y};
                 v2[2 * c + 1] = cpx{b.z, b.w};
             }
-            __syncthreads();  // B3: everyone holds its columns; Y becomes the magnitude row
             fft_dif<16>(v1);
             fft_dif<16>(v2);
+            float *grow = fd.row;
             if (u != 0) {
-                s2::epilogue_generic<0>(v1, v2, wt, row + u, row + 4096 - u, mx);
+                s2::epilogue_generic<0>(v1, v2, wt, grow + u, grow + 4096 - u, P + u, P + 4096 - u, mx);
             } else {
-                s2::epilogue_col0<0>(v1, row, mx);
-                float mid, dummy;  // the self-mirrored bin 2048: W8192^2048 = -i
-                s2::untangle_pair(v1[bitrev(8, 4)], v1[bitrev(8, 4)], cpx{0.f, -1.f}, mid, dummy);
-                row[2048] = mid;
-                mx = fmaxf(mx, mid);
-                s2::epilogue_col128<0>(v2, wt, row, mx);
+                // thread 0's columns 0 and 128 mirror onto themselves: 17 pairs, handed to lanes 0..16 of this warp
+#pragma unroll
+                for (int c = 0; c < 16; c++) {
+                    S0[c] = v1[bitrev(c, 4)];        // Z[256 c]
+                    S0[16 + c] = v2[bitrev(c, 4)];   // Z[128 + 256 c]
+                }
             }
+        }
+        if (u < 32) {  // warp 0
+            __syncwarp();
+            if (lane < 17) {
+                // lane L <= 8: k = 256 L <-> 4096 - k (L = 0: X[0] and X[4096], L = 8: the self-mirrored bin 2048);
+                // L >= 9:  k = 128 + 256 (L - 9) <-> 4096 - k.  W8192^k = W64^j, j = k / 128 = tw1[k1 = j][b = 64]
+                const bool c0 = lane <= 8;
+                const int C = c0 ? lane : lane - 9;
+                const cpx zk = c0 ? S0[C] : S0[16 + C];
+                const cpx zm = c0 ? S0[(16 - C) & 15] : S0[16 + 15 - C];
+                const int jw = c0 ? 2 * C : 2 * C + 1;
+                cpx w = cpx{0.f, -1.f};  // W64^16
+                if (jw < 16) {
+                    const float2 t = __ldg(reinterpret_cast<const float2 *>(tw1) + 256 * jw + 64);
+                    w = cpx{t.x, t.y};
+                }
+                float a, b;
+                s2::untangle_pair(zk, zm, w, a, b);
+                const int k = c0 ? 256 * C : 128 + 256 * C;
+                float *grow = fd.row;
+                grow[k] = a;
+                grow[4096 - k] = b;
+                if (k < s2::PIP_FLOATS) P[k] = a;
+                if (4096 - k < s2::PIP_FLOATS) P[4096 - k] = b;
+                mx = fmaxf(mx, fmaxf(a, b));
+            }
+            __syncwarp();
         }
         // frame maximum (pip_track's ref_value = 0.1 * max over all bins, chroma.rs:289-293)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if (lane == 0) s_red[u >> 5] = mx;
-        s2::fence_async_smem();  // the row is read by the bulk store (async proxy)
-        __syncthreads();         // B4
-        if (u == 0) s2::bulk_store(fd.row, row, s2::ROW_FLOATS * 4);
+        __syncthreads();  // B3: bins < 1536 and the warp maxima are in shared memory; every pass-3 load of Y is done
         // ---- pip_track on centre bins 57..1483 (beginning = 56, end = 1486 for n_fft = 8192): 12 centres per thread -
         {
             const float fmx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
             const double ref = 0.1 * (double)fmx;
-            float m[16];
+            // (double)elem > ref for an f32 elem  <=>  elem > thr, thr = the largest f32 that is <= ref
+            float thr = (float)ref;
+            if ((double)thr > ref) thr = __uint_as_float(__float_as_uint(thr) - 1u);  // ref >= 0: one ulp down (0 stays 0: fmx = 0 has no peaks)
             unsigned int flags = 0;
-            const int b0 = 56 + 12 * u;  // m[i] = row[b0 + i]; centre c = b0 + 1 + i
+            const int b0 = 56 + 12 * u;  // this thread's centres c = b0 + 1 + i, i < 12
             if (u < 119) {
-                const float4 *q = reinterpret_cast<const float4 *>(row + b0);
+                float m[16];
+                const float4 *q = reinterpret_cast<const float4 *>(P + b0);
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const float4 t = q[i];
@@ -433,8 +442,9 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
 #pragma unroll
                 for (int i = 0; i < 12; i++) {
                     const float before = m[i], elem = m[i + 1], after = m[i + 2];
-                    if (b0 + 1 + i <= 1483 && after <= elem && before < elem && (double)elem > ref) flags |= 1u << i;
+                    if (after <= elem && before < elem && elem > thr && (fmx > 0.f)) flags |= 1u << i;
                 }
+                if (u == 118) flags &= 0x7ffu;  // centre 1484 is past the last one (1483)
             }
             const int cnt = __popc(flags);
             unsigned int incl = (unsigned)cnt;
@@ -448,22 +458,24 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
             if (lane == 0 && wtot) wbase = atomicAdd(cand_count + fd.si, wtot);  // one reservation per warp: order is free (chroma.rs:361-391)
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
             unsigned long long dst = fd.cand_off + wbase + (incl - (unsigned)cnt);
-#pragma unroll
-            for (int i = 0; i < 12; i++) {
-                if (flags & (1u << i)) {
-                    const double before = (double)m[i], elem = (double)m[i + 1], after = (double)m[i + 2];
-                    const double avg = 0.5 * (after - before);
-                    double shift = 2. * elem - after - before;
-                    if (fabs(shift) < 2.2250738585072014e-308) shift += 1.;
-                    shift = avg / shift;
-                    cand_pitch[dst] = ((double)(b0 + 1 + i) + shift) * (double)SAMPLE_RATE / 8192.0;
-                    cand_mag[dst] = elem + 0.5 * avg * shift;
-                    dst++;
-                }
+            while (flags) {
+                const int i = __ffs(flags) - 1;
+                flags &= flags - 1;
+                const int c = b0 + 1 + i;
+                const double before = (double)P[c - 1], elem = (double)P[c], after = (double)P[c + 1];
+                const double avg = 0.5 * (after - before);
+                double shift = 2. * elem - after - before;
+                if (fabs(shift) < 2.2250738585072014e-308) shift += 1.;
+                shift = avg / shift;
+                // the residue bin of pitch_tuning (log2 / fmod in f64) is left to tuning_kernel; here only the
+                // interpolation of chroma.rs:317-326
+                cand_pitch[dst] = ((double)c + shift) * (double)SAMPLE_RATE / 8192.0;
+                cand_mag[dst] = elem + 0.5 * avg * shift;
+                dst++;
             }
         }
-        if (u == 0) s2::bulk_store_wait_read();  // the row has left Y
-        __syncthreads();  // B5: the next frame's pass 1 overwrites Y
+        // no barrier here: the next writes to Y / P / s_red / s_fd[ph] sit behind the next frame's B1 or B2, which no
+        // warp passes before every warp has left this frame
     }
 }
 
