@@ -153,7 +153,9 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": val, "unit": "songs/s", "cores": cores, "kind": "port",
                          "sample": "%d x 3-min synthetic tracks per step, %d steps, %d threads (C oracle, "
                                    "-O3 -march=native, full complex FFT per frame like the reference)"
-                                   % (n_songs, args.steps, cores)},
+                                   % (n_songs, args.steps, cores),
+                         "note": "C port of the reference's algorithm, not the Rust crate (no Rust toolchain here): rustfft's "
+                                 "AVX kernels are expected to be 2-3x faster per FFT (BASELINE.md section 2)"},
         "e2e": {"value": val, "unit": "songs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -170,6 +172,143 @@ _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 
 
+def stft_microbench(nat, torch, pcm, offs, S, stream, peak, peak_src):
+    """BASELINE.json configs[2]: 512-point hanningz STFT, hop 256 (= PVocTempo, src/aubio.rs:338-425), 257 magnitudes
+    per frame materialised in HBM, over >= 10 000 tracks: the step's resident tracks are looped (stated), each pass
+    re-reads every sample from HBM (the input is far larger than L2)."""
+    n_t = (TRACK_SAMPLES - 512) // 256 + 1
+    R = min(S, 1024)
+    try:
+        mags = torch.empty((R * n_t, 257), dtype=torch.float32, device=pcm.device)
+    except Exception as e:  # no room next to the analysis scratch: say so rather than fail the bench line
+        return {"skipped": "no HBM for the magnitude buffer: %s" % str(e)[:80]}
+    lens = [TRACK_SAMPLES] * R
+    passes = max(1, -(-10000 // R))
+    nat.stft512_mag_device(pcm.data_ptr(), offs[:R], lens, mags.data_ptr(), stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(passes):
+        nat.stft512_mag_device(pcm.data_ptr(), offs[:R], lens, mags.data_ptr(), stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    tracks = passes * R
+    rd = tracks * TRACK_SAMPLES * 4 / 1e9 / (ms / 1e3)
+    wr = tracks * n_t * 257 * 4 / 1e9 / (ms / 1e3)
+    del mags
+    torch.cuda.empty_cache()
+    return {"workload": "configs[2]: 512-pt hanningz STFT, hop 256, 257 magnitudes per frame written to HBM",
+            "tracks": tracks, "resident_tracks": R, "passes": passes,
+            "looped_resident": "the %d resident tracks (%.1f GB, far larger than L2) are re-read from HBM %d times"
+                               % (R, R * TRACK_SAMPLES * 4 / 1e9, passes),
+            "ms_total": ms, "tracks_per_s": tracks / (ms / 1e3), "read_gbs": rd, "write_gbs": wr,
+            "frac_read": rd / peak, "frac_read_write": (rd + wr) / peak, "peak_gbs": peak, "peak_source": peak_src}
+
+
+def _gpu_numa_cpus(torch, d):
+    """CPUs of the NUMA node GPU d hangs off (sysfs; None when the container hides it)."""
+    try:
+        pr = torch.cuda.get_device_properties(d)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        return node, (cpus & os.sched_getaffinity(0)) or None
+    except Exception:
+        return None, None
+
+
+def measure_e2e(nat, torch, world, ES, host_songs, feats_ref, args, dim):
+    """songs/s through bliss_b200_analyze_batch[_s16] from pinned host memory, one call for all `world` GPUs, plus the
+    box's plain-copy H2D ceiling measured the same way (all GPUs copying at once from the same buffers)."""
+    n_dev = nat.init_devices(world) if world > 1 else 1
+    # one pinned copy of the ES songs per NUMA node that hosts a GPU, allocated and touched from that node's CPUs
+    all_cpus = os.sched_getaffinity(0)
+    node_of, bufs = {}, {}
+    for d in range(n_dev):
+        node, cpus = _gpu_numa_cpus(torch, d)
+        node_of[d] = node if node is not None else -1
+        if node_of[d] not in bufs:
+            try:
+                if cpus:
+                    os.sched_setaffinity(0, cpus)
+                b = torch.empty(ES * TRACK_SAMPLES, dtype=torch.float32, pin_memory=True)
+                b.copy_(host_songs)
+            finally:
+                os.sched_setaffinity(0, all_cpus)
+            bufs[node_of[d]] = b
+    # song k of a call goes to device k % n_dev (equal lengths: the library's longest-first deal is round-robin)
+    n_call = ES * n_dev
+    ptrs = (ctypes.c_void_p * n_call)(*[bufs[node_of[k % n_dev]].data_ptr() + 4 * (k // n_dev) * TRACK_SAMPLES
+                                        for k in range(n_call)])
+    hlens = (ctypes.c_uint64 * n_call)(*([TRACK_SAMPLES] * n_call))
+    out = np.zeros((n_call, dim), np.float32)
+    status = np.zeros(n_call, np.int32)
+    nat.analyze_batch_ptrs(ptrs, hlens, 2, out, status)  # warm-up (allocations on every device)
+    steps = max(2, min(args.steps, 4))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        nat.analyze_batch_ptrs(ptrs, hlens, 2, out, status)
+    dt = time.perf_counter() - t0
+    want = np.repeat(feats_ref, n_dev, axis=0)  # call song k = resident song k // n_dev
+    # the plain-copy ceiling of the same transfer pattern: every GPU copies its ES songs at once, nothing else runs
+    ceil_gbs = None
+    try:
+        dsts = [torch.empty(ES * TRACK_SAMPLES, dtype=torch.float32, device="cuda:%d" % d) for d in range(n_dev)]
+        strs = [torch.cuda.Stream(device=d) for d in range(n_dev)]
+
+        def copy_all():
+            for d in range(n_dev):
+                with torch.cuda.stream(strs[d]):
+                    dsts[d].copy_(bufs[node_of[d]], non_blocking=True)
+            for d in range(n_dev):
+                strs[d].synchronize()
+        copy_all()
+        tc = time.perf_counter()
+        for _ in range(3):
+            copy_all()
+        ceil_gbs = 3 * n_dev * ES * TRACK_SAMPLES * 4 / 1e9 / (time.perf_counter() - tc)
+        del dsts
+        torch.cuda.empty_cache()
+    except Exception as e:
+        print("[bench] H2D ceiling not measured: %s" % e, file=sys.stderr)
+    gbs = n_call * steps * TRACK_SAMPLES * 4 / 1e9 / dt
+    e2e = {"value": n_call * steps / dt, "unit": "songs/s", "h2d_bytes_per_step": n_call * TRACK_SAMPLES * 4,
+           "d2h_bytes_per_step": n_call * dim * 4, "songs_per_step": n_call, "steps": steps, "devices": n_dev,
+           "bitwise_equal_to_device_path": bool(np.array_equal(out, want)) and bool((status == 0).all()),
+           "h2d_gbs": gbs, "h2d_ceiling_gbs": ceil_gbs, "frac_of_h2d_ceiling": (gbs / ceil_gbs) if ceil_gbs else None,
+           "numa_nodes_of_gpus": [node_of[d] for d in range(n_dev)],
+           "note": "ONE bliss_b200_analyze_batch call from one process over %d GPU(s) (bliss_b200_init_devices), pinned host "
+                   "buffers local to each GPU's NUMA node; PCIe-bound (15.9 MB per song): see frac_of_h2d_ceiling" % n_dev}
+    # 16-bit sources: bliss_b200_analyze_batch_s16 (s16 -> f32 on the device, half the PCIe bytes).  Reported next to
+    # `e2e`, never instead of it: BASELINE.json's metric is quoted on f32 PCM.
+    bufs16 = {k: torch.empty(ES * TRACK_SAMPLES, dtype=torch.int16, pin_memory=True) for k in bufs}
+    for k in bufs:
+        bufs16[k].copy_((bufs[k] * 32767.0).round().to(torch.int16))
+    ptrs16 = (ctypes.c_void_p * n_call)(*[bufs16[node_of[k % n_dev]].data_ptr() + 2 * (k // n_dev) * TRACK_SAMPLES
+                                          for k in range(n_call)])
+    out16 = np.zeros((n_call, dim), np.float32)
+    nat.analyze_batch_s16_ptrs(ptrs16, hlens, 2, out16, status)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        nat.analyze_batch_s16_ptrs(ptrs16, hlens, 2, out16, status)
+    dt16 = time.perf_counter() - t0
+    # the same samples converted on the host and sent as f32 must give the same bits
+    for k in bufs:
+        bufs[k].copy_(bufs16[k].to(torch.float32) / 32768.0)
+    nat.analyze_batch_ptrs(ptrs, hlens, 2, out, status)
+    e2e_s16 = {"value": n_call * steps / dt16, "unit": "songs/s", "h2d_bytes_per_step": n_call * TRACK_SAMPLES * 2,
+               "d2h_bytes_per_step": n_call * dim * 4, "songs_per_step": n_call, "steps": steps, "devices": n_dev,
+               "bitwise_equal_to_f32_path": bool(np.array_equal(out16, out)),
+               "note": "bliss_b200_analyze_batch_s16: signed 16-bit mono 22 050 Hz samples, x/32768 on the device"}
+    return e2e, e2e_s16
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,6 +317,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--songs-per-gpu", type=int, default=SONGS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="2 = BASELINE.json configs[1] (the bench line the driver reads); 4 = configs[3] (100 k tracks, "
+                         "waves, fused gather, all-pairs row blocks: bench_config4.py); 5 = configs[4] (Zipf mixed-duration "
+                         "corpus end to end through ONE multi-device call + playlist order vs the oracle: bench_config5.py)")
     ap.add_argument("--kernels-only", action="store_true",
                     help="A/B runs: device-timed value + per-kernel times only (no e2e legs, no CPU baseline)")
     ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"],
@@ -189,6 +332,15 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.config == 4:
+        import bench_config4
+        sys.argv = [sys.argv[0]]
+        os.dup2(_REAL_STDOUT, 1)
+        return bench_config4.main()
+    if args.config == 5:
+        import bench_config5
+        os.dup2(_REAL_STDOUT, 1)
+        return bench_config5.main(["--gpus", str(max(args.gpus, world))] + (["--songs", os.environ["BLISS_CFG5_SONGS"]] if os.environ.get("BLISS_CFG5_SONGS") else []))
 
     import torch
     import torch.distributed as dist
@@ -378,15 +530,25 @@ def main():
                     traffic_detail[k] = ent[k]
         except Exception:
             traffic = traffic_detail = None
+    step_read_gbs = S * TRACK_SAMPLES * 4 / 1e9 / (ms / args.steps / 1e3)  # every PCM byte once per step / step time
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["algorithmic_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": dom["algorithmic_gbs"] / peak, "traffic": traffic,
+                "traffic_source": "static: ncu capture committed under profiles/ (not re-measured in this run)",
                 "traffic_detail": traffic_detail, "peak_source": peak_src,
+                "step_read_gbs": step_read_gbs, "step_read_frac": step_read_gbs / peak,
+                "step_read_note": "BASELINE.md section 3: songs x 4N bytes / step time / HBM peak (per GPU); the FFT kernels "
+                                  "are FP32-pipe bound, so this sits far below 1 by construction",
                 "avg_launch_ms": dom["avg_ms"], "share_of_step": dom["share"],
                 "note": "FFT work: the kernel is FP32-pipe / shared-memory bound at algorithmic-minimum traffic "
                         "(DESIGN.md); the HBM roofline is reported because BASELINE.json fixes it",
                 "kernels": kernels}
 
     # ---- e2e: the C-ABI call with pinned HOST buffers (H2D + D2H inside the timed region) --
+    # ---- STFT-only micro-benchmark (BASELINE.json configs[2]; the "STFT HBM GB/s" half of the metric) -------------
+    stft_micro = None
+    if world == 1 and not args.kernels_only:
+        stft_micro = stft_microbench(nat, torch, pcm, offs, S, stream, peak, peak_src)
+
     if args.kernels_only:
         if rank == 0:
             _emit({"metric": METRIC, "value": value, "unit": "songs/s", "n_gpus": world, "steps": args.steps,
@@ -401,73 +563,58 @@ def main():
                 gather.destroy()
             dist.destroy_process_group()
         return
-    ES = min(E2E_SONGS, S)
-    host = torch.empty(ES * TRACK_SAMPLES, dtype=torch.float32, pin_memory=True)
-    for i in range(ES):
-        host[i * TRACK_SAMPLES:(i + 1) * TRACK_SAMPLES].copy_(pcm[offs[i]:offs[i] + TRACK_SAMPLES])
-    torch.cuda.synchronize()
-    ptrs = (ctypes.c_void_p * ES)(*[host.data_ptr() + 4 * i * TRACK_SAMPLES for i in range(ES)])
-    hlens = (ctypes.c_uint64 * ES)(*([TRACK_SAMPLES] * ES))
-    e2e_out = np.zeros((ES, dim), np.float32)
-    e2e_status = np.zeros(ES, np.int32)
-    nat.analyze_batch_ptrs(ptrs, hlens, 2, e2e_out, e2e_status)  # warm-up (allocations)
-    barrier()
-    e2e_steps = max(2, min(args.steps, 4))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        nat.analyze_batch_ptrs(ptrs, hlens, 2, e2e_out, e2e_status)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    te = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * ES * e2e_steps / float(te.item())
-    e2e_match = bool(np.array_equal(e2e_out, feats[:ES].cpu().numpy()))
-    e2e = {"value": e2e_val, "unit": "songs/s", "h2d_bytes_per_step": ES * TRACK_SAMPLES * 4,
-           "d2h_bytes_per_step": ES * dim * 4, "songs_per_step": ES, "steps": e2e_steps,
-           "bitwise_equal_to_device_path": e2e_match,
-           "note": "bliss_b200_analyze_batch on pinned host buffers; PCIe-bound (15.9 MB per song)"}
 
-    # ---- e2e for 16-bit sources: bliss_b200_analyze_batch_s16 (s16 -> f32 on the device, half the PCIe bytes).
-    # Reported next to `e2e`, never instead of it: BASELINE.json's metric is quoted on f32 PCM.
-    e2e_s16 = None
-    if world == 1:
-        host16 = torch.empty(ES * TRACK_SAMPLES, dtype=torch.int16, pin_memory=True)
-        host16.copy_((host * 32767.0).round().to(torch.int16))
-        ptrs16 = (ctypes.c_void_p * ES)(*[host16.data_ptr() + 2 * i * TRACK_SAMPLES for i in range(ES)])
-        s16_out = np.zeros((ES, dim), np.float32)
-        nat.analyze_batch_s16_ptrs(ptrs16, hlens, 2, s16_out, e2e_status)  # warm-up (allocations)
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            nat.analyze_batch_s16_ptrs(ptrs16, hlens, 2, s16_out, e2e_status)
-        torch.cuda.synchronize()
-        dt16 = time.perf_counter() - t0
-        # same samples converted on the host and sent as f32: must give the same bits
-        host.copy_(host16.to(torch.float32) / 32768.0)
-        nat.analyze_batch_ptrs(ptrs, hlens, 2, e2e_out, e2e_status)
-        e2e_s16 = {"value": ES * e2e_steps / dt16, "unit": "songs/s", "h2d_bytes_per_step": ES * TRACK_SAMPLES * 2,
-                   "d2h_bytes_per_step": ES * dim * 4, "songs_per_step": ES, "steps": e2e_steps,
-                   "bitwise_equal_to_f32_path": bool(np.array_equal(s16_out, e2e_out)),
-                   "note": "bliss_b200_analyze_batch_s16: signed 16-bit mono 22 050 Hz samples, x/32768 on the device"}
-        del host16
+    # ---- e2e: the C-ABI call with pinned HOST buffers (H2D + D2H inside the timed region) -------------------------
+    # ONE process drives every GPU (bliss_b200_init_devices): the reference is one process (worker threads + a channel,
+    # src/song/decoder.rs:282-331), so that is what its drop-in has to be measured through.  Under torchrun rank 0 owns
+    # the call; the other ranks free their GPUs and wait on a CPU (gloo) barrier -- an NCCL barrier would spin on the
+    # very SMs being measured.
+    ES = min(E2E_SONGS, S)
+    host_songs = torch.empty(ES * TRACK_SAMPLES, dtype=torch.float32)
+    if rank == 0:
+        for i in range(ES):
+            host_songs[i * TRACK_SAMPLES:(i + 1) * TRACK_SAMPLES].copy_(pcm[offs[i]:offs[i] + TRACK_SAMPLES])
+    feats_ref = feats[:ES].cpu().numpy()
+    cpu_songs = cpu_feats = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_cpu = min(max(4 * (os.cpu_count() or 1), 64), 256, S)  # a few seconds of wall on all cores (tens of core-seconds)
+        cpu_songs = [pcm[offs[i]:offs[i] + TRACK_SAMPLES].cpu().numpy() for i in range(n_cpu)]
+        cpu_feats = feats[:n_cpu].cpu().numpy()
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
+    if gather:
+        gather.destroy()
+        gather = None
+    del pcm, dmat, all_feats
+    torch.cuda.synchronize()
+    if rank != 0:
+        nat.shutdown()      # this rank's context and scratch leave its GPU: rank 0 opens its own context there
+    torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier(group=cpu_group)
+    e2e = e2e_s16 = None
+    if rank == 0:
+        e2e, e2e_s16 = measure_e2e(nat, torch, world, ES, host_songs, feats_ref, args, dim)
+    if world > 1:
+        dist.barrier(group=cpu_group)
 
     # ---- CPU baseline (oracle = port of the reference algorithm) on rank 0, bounded sample ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if cpu_songs is not None:
         from oracle import oracle as O
         cores = os.cpu_count() or 1
-        n_cpu = min(max(4 * cores, 64), 256)  # a few seconds of wall on all cores (tens of core-seconds)
-        songs = [pcm[offs[i]:offs[i] + TRACK_SAMPLES].cpu().numpy() for i in range(min(n_cpu, S))]
         t0 = time.perf_counter()
-        ost, ofe = O.analyze_batch(songs, 2, n_threads=cores)
+        ost, ofe = O.analyze_batch(cpu_songs, 2, n_threads=cores)
         dtc = time.perf_counter() - t0
-        gf = feats[:len(songs)].cpu().numpy()
-        err = np.abs(gf - ofe)
+        err = np.abs(cpu_feats - ofe)
         tol = 1e-4 * np.maximum(1.0, np.abs(ofe))
-        cpu = {"value": len(songs) / dtc, "unit": "songs/s", "cores": cores, "kind": "port",
+        cpu = {"value": len(cpu_songs) / dtc, "unit": "songs/s", "cores": cores, "kind": "port",
                "sample": "%d of the same synthetic 3-min tracks (D2H-copied), %d threads, %.1f s wall"
-                         % (len(songs), cores, dtc),
+                         % (len(cpu_songs), cores, dtc),
+               "note": "C port of the reference's algorithm (plain radix FFT, -O3 -march=native), not the Rust crate: "
+                       "rustfft's AVX kernels are expected to be 2-3x faster per FFT (BASELINE.md section 2), so the "
+                       "speed-up over the crate itself is that much lower than value / cpu_baseline.value",
                "parity_max_abs_err": float(err.max()), "parity_within_1e-4": bool((err <= tol).all()),
+               "parity_per_feature_max_abs_err": [float(v) for v in err.max(0)],
                "parity_tempo_mismatches": int((err[:, 0] > 1e-3).sum())}
 
     if rank == 0:
@@ -481,15 +628,13 @@ def main():
                        "kernel_variant_mask": int(os.environ.get("BLISS_B200_VARIANT", "0") or 0), "parallelism": "songs sharded %d-way" % world,
                        "l2": "inputs (%.1f GB PCM per GPU) are far larger than the 126 MB L2; no flush needed"
                              % (S * TRACK_SAMPLES * 4 / 1e9)},
-            "e2e": e2e, "e2e_s16": e2e_s16, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "per_rank": per_rank,
+            "e2e": e2e, "e2e_s16": e2e_s16, "stft_microbench": stft_micro, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "per_rank": per_rank,
             "gather": gather_info,
             "gpu_launches": int(lz.item()), "bitwise_reproducible_across_steps": bool(deterministic.item()),
         }
         _emit(line)
     if world > 1:
-        dist.barrier()
-        if gather:
-            gather.destroy()
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
 
 

@@ -134,6 +134,13 @@ def init_devices(n_devices=0):
     return int(n)
 
 
+def shutdown():
+    """bliss_b200_shutdown: every context, stream and device buffer of this process is released."""
+    global _inited_device
+    load().bliss_b200_shutdown()
+    _inited_device = None
+
+
 def device_count():
     return int(load().bliss_b200_device_count())
 
