@@ -47,7 +47,7 @@ int launch_s16_to_f32(const short *, float *, size_t, cudaStream_t);
 int launch_pcm_to_mono(const void *, float *, size_t, int, unsigned int, cudaStream_t);
 int launch_gather_barrier(unsigned int *const *, int, int, unsigned int, unsigned long long, cudaStream_t);
 int launch_distance_matrix(const float *, unsigned int, const float *, unsigned int, int, int, const float *,
-                           float *, cudaStream_t);
+                           float *, cudaStream_t, unsigned int ones_mask, int variant);
 int launch_seed_distance(const float *, unsigned int, const float *, unsigned int, int, int, const float *,
                          float *, cudaStream_t);
 size_t sort_temp_bytes(unsigned int);
@@ -149,6 +149,7 @@ struct Ctx {
     cudaEvent_t ev_begin = nullptr;
     size_t ws_limit = 0;
     int variant = 0;  // BLISS_B200_VARIANT, see common.cuh
+    unsigned int metric_ones = 0;  // bit i: diagonal weight i of the metric last prepared is exactly 1 (prepare_metric)
     // constant tables
     DevBuf t_win512, t_twA, t_hann8k, t_tw4k, t_tw2, t_tw8k, t_tw64, t_filt, t_filt32;
     WaveSet ws[N_SETS];
@@ -609,6 +610,7 @@ int prepare_metric(int metric, const float *m, uint32_t dim, cudaStream_t st, in
     if (metric == BLISS_B200_METRIC_COSINE) { mode = 2; return 0; }
     if (metric != BLISS_B200_METRIC_MAHALANOBIS) { g_last_error = "unknown metric"; return BLISS_B200_E_ARG; }
     mode = 0;
+    g.metric_ones = 0xffffffffu;
     if (!m) return 0;
     bool diag = true;
     for (uint32_t i = 0; i < dim && diag; i++)
@@ -617,7 +619,11 @@ int prepare_metric(int metric, const float *m, uint32_t dim, cudaStream_t st, in
     CK(g.metric.ensure((size_t)dim * dim * 4 + 256));
     if (diag) {
         std::vector<float> w(dim);
-        for (uint32_t i = 0; i < dim; i++) w[i] = m[(size_t)i * dim + i];
+        g.metric_ones = 0;
+        for (uint32_t i = 0; i < dim; i++) {
+            w[i] = m[(size_t)i * dim + i];
+            if (w[i] == 1.0f && i < 32) g.metric_ones |= 1u << i;
+        }
         // pageable source: the runtime stages it before returning, so `w` may go out of scope
         CK(cudaMemcpyAsync(g.metric.p, w.data(), dim * 4, cudaMemcpyHostToDevice, st));
     } else {
@@ -1448,7 +1454,7 @@ int bliss_b200_distance_matrix_device(const float *d_rows, uint32_t n_rows, cons
     int rc = prepare_metric(metric, m, dim, st, mode, d_w);
     if (rc) return rc;
     ProfScope p(K_DIST, st);
-    const int nl = launch_distance_matrix(d_rows, n_rows, d_cols, n_cols, (int)dim, mode, d_w, d_out, st);
+    const int nl = launch_distance_matrix(d_rows, n_rows, d_cols, n_cols, (int)dim, mode, d_w, d_out, st, g.metric_ones, g.variant);
     p.done(nl);
     if (nl < 0) { g_last_error = "unsupported dim"; return BLISS_B200_E_ARG; }
     CK(cudaGetLastError());
@@ -1469,7 +1475,7 @@ static int distance_matrix_host_locked(const float *rows, uint32_t n_rows, const
     if (rc) return rc;
     ProfScope p(K_DIST, st);
     const int nl = launch_distance_matrix(g.misc[0].as<float>(), n_rows, g.misc[1].as<float>(), n_cols, (int)dim,
-                                          mode, d_w, g.misc[2].as<float>(), st);
+                                          mode, d_w, g.misc[2].as<float>(), st, g.metric_ones, g.variant);
     p.done(nl);
     if (nl < 0) { g_last_error = "unsupported dim"; return BLISS_B200_E_ARG; }
     CK(cudaMemcpyAsync(out, g.misc[2].p, (size_t)n_rows * n_cols * 4, cudaMemcpyDeviceToHost, st));

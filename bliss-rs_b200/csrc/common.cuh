@@ -86,6 +86,7 @@ enum {
     // back to the kernel measured in round 1, like bits 1..32.
     VARIANT_PVOC_V1 = 16384,   // pvoc512: the round-1 kernel (with its promoted cuts) instead of pvoc512v2_kernel
     VARIANT_STFT_V1 = 32768,   // stft8192: the round-1 kernel (with its promoted cuts) instead of stft8192v2_kernel (bits 1 and 32 imply it)
+    VARIANT_OLD_DIST = 65536,  // distance matrix: the round-1 scalar kernel instead of distance_matrix_diag_kernel
     VARIANT_PROMOTED = 64 | 128 | 256 | 512 | 1024 | 2048 | 4096 | 8192,
 };
 

@@ -111,6 +111,83 @@ distance_matrix_kernel(const float *__restrict__ rows, unsigned int n_rows,
     }
 }
 
+// ---- diagonal-metric fast path (round 2) -----------------------------------------------------------------------
+// The metrics the crate ships are diagonal (src/lib.rs:168-178, 209-234): sqrt(sum_i w_i d_i^2), evaluated by ndarray
+// as unrolled_dot(d * w, d).  Same arithmetic as pair_distance (every product and every sum rounded on its own, in
+// ndarray's order), two columns per thread carried as ONE packed f32x2 lane pair:
+//   d = a - b                FADD2 (the row value is a scalar broadcast operand)
+//   t = d * w_i              FMUL2, skipped where w_i == 1 (x * 1 is exact: 9 of the 23 v2 weights, all of v1's)
+//   q = t * d                FMUL2
+//   p_k = p_k * 1 + q        FFMA2 with the constant 1: one rounding of the exact p_k + q, i.e. the reference's
+//                            separate add -- written as an FMA because ptxas contracts mul.f32x2 + add.f32x2 into one
+//                            FFMA2 (a fused product, other bits), which it cannot do to an FMA
+// The first round of the eight partial sums is p_k = q (0 + q is exact).  82 packed FP instructions per two pairs
+// instead of ~190 scalar ones: the kernel moves from issue-bound to the FP32 pipe (83 roundings per pair cannot fuse).
+#ifndef BLISS_HOST_EMUL  // (the host emulation keeps running the scalar kernel, whose bits this one must reproduce)
+// ONES: compile-time mask of the features whose weight is exactly 1 (0 = none known: every product is made)
+template <int DIM, unsigned int ONES>
+__global__ void __launch_bounds__(128)
+distance_matrix_diag_kernel(const float *__restrict__ rows, unsigned int n_rows, const float *__restrict__ cols,
+                            unsigned int n_cols, const float *__restrict__ w, float *__restrict__ out, float one_rt) {
+    constexpr int TR = 64, NT = 128, PITCH = (DIM + 3) / 4 * 4;
+    // 1.0f as a RUN-TIME value: with the literal, ptxas simplifies fma(p, 1, q) to p + q and then contracts the
+    // product behind q into it (FFMA2: a fused product, not the reference's bits) -- seen in the SASS
+    const cpx one = cpx{one_rt, one_rt};
+    __shared__ __align__(16) float s_a[TR][PITCH];
+    const unsigned int r0 = blockIdx.y * TR, c0 = blockIdx.x * (2 * NT);
+    for (int e = threadIdx.x; e < TR * PITCH; e += NT) {
+        const unsigned int r = r0 + e / PITCH;
+        const int i = e % PITCH;
+        s_a[e / PITCH][i] = (r < n_rows && i < DIM) ? rows[(size_t)r * DIM + i] : 0.f;
+    }
+    const unsigned int ca = c0 + threadIdx.x, cb = c0 + (unsigned)NT + threadIdx.x;
+    cpx v[DIM], wv[DIM];  // (column ca, column cb) per feature; weights as (w_i, w_i)
+#pragma unroll
+    for (int i = 0; i < DIM; i++) {
+        v[i].x = ca < n_cols ? __ldg(cols + (size_t)ca * DIM + i) : 0.f;
+        v[i].y = cb < n_cols ? __ldg(cols + (size_t)cb * DIM + i) : 0.f;
+        const float wi = w ? __ldg(w + i) : 1.f;
+        wv[i] = cpx{wi, wi};
+    }
+    __syncthreads();
+    const unsigned int nr = min((unsigned)TR, n_rows - r0);
+#pragma unroll 1
+    for (unsigned int lr = 0; lr < nr; lr++) {
+        float a[PITCH];
+        const float4 *ra = reinterpret_cast<const float4 *>(s_a[lr]);
+#pragma unroll
+        for (int k = 0; k < PITCH / 4; k++) {
+            const float4 t4 = ra[k];
+            a[4 * k] = t4.x; a[4 * k + 1] = t4.y; a[4 * k + 2] = t4.z; a[4 * k + 3] = t4.w;
+        }
+        cpx p[8], sum = cpx{0.f, 0.f};
+        constexpr int BODY = DIM / 8 * 8;
+#pragma unroll
+        for (int i = 0; i < DIM; i++) {
+            const cpx d = psub(cpx{a[i], a[i]}, v[i]);
+            const cpx t = ((ONES >> i) & 1u) ? d : pmul(d, wv[i]);
+            const cpx q = pmul(t, d);
+            if (i < 8) {
+                p[i] = q;  // 0 + q
+            } else if (i < BODY) {
+                p[i & 7] = pfma(p[i & 7], one, q);
+            } else {
+                if (i == BODY) {  // ndarray: sum = ((p0 + p4) + (p1 + p5)) + (p2 + p6)) + (p3 + p7), then the tail in order
+                    sum = padd(p[0], p[4]);
+                    sum = padd(sum, padd(p[1], p[5]));
+                    sum = padd(sum, padd(p[2], p[6]));
+                    sum = padd(sum, padd(p[3], p[7]));
+                }
+                sum = pfma(sum, one, q);
+            }
+        }
+        float *o = out + (size_t)(r0 + lr) * n_cols;
+        if (ca < n_cols) __stcs(o + ca, __fsqrt_rn(sum.x));
+        if (cb < n_cols) __stcs(o + cb, __fsqrt_rn(sum.y));
+    }
+}
+#endif  // BLISS_HOST_EMUL
+
 // any dim <= MAX_DIM: one thread per output (used for custom metrics on other vector sizes)
 __global__ void __launch_bounds__(256)
 distance_matrix_generic_kernel(const float *__restrict__ rows, unsigned int n_rows,
@@ -191,9 +268,32 @@ nearest_alive_kernel(const float *__restrict__ cur, unsigned int n_cur, const fl
 }
 
 // ---- launchers ---------------------------------------------------------------
+// ones_mask: bit i set where the diagonal weight w_i is exactly 1 (or no weights at all); variant bit
+// VARIANT_OLD_DIST (65536) keeps the round-1 kernel for A/B and for the bit-exactness test of the packed one
 int launch_distance_matrix(const float *rows, unsigned int n_rows, const float *cols, unsigned int n_cols,
-                           int dim, int mode, const float *w_or_m, float *out, cudaStream_t st) {
+                           int dim, int mode, const float *w_or_m, float *out, cudaStream_t st, unsigned int ones_mask,
+                           int variant) {
+    const bool DIST_DIAG_FAST_PATH = (variant & VARIANT_OLD_DIST) == 0;
+    (void)ones_mask;
+    (void)DIST_DIAG_FAST_PATH;
     if (n_rows == 0 || n_cols == 0) return 0;
+#ifndef BLISS_HOST_EMUL
+    if (mode == 0 && (dim == 23 || dim == 20) && (DIST_DIAG_FAST_PATH)) {  // diagonal metric: the packed kernel
+        dim3 g2((n_cols + 255u) / 256u, (n_rows + 63u) / 64u);
+        constexpr unsigned int V2_ONES = 0x3FEu;  // VERSION2_WEIGHTS (src/lib.rs:209-234): w_1 .. w_9 = 1
+        const unsigned int all = (1u << dim) - 1u;
+        if (!w_or_m) ones_mask = all;
+        if (dim == 23) {
+            if ((ones_mask & all) == all) BLISS_LAUNCH((distance_matrix_diag_kernel<23, 0x7FFFFFu>), g2, 128, 0, st, rows, n_rows, cols, n_cols, w_or_m, out, 1.0f);
+            else if ((ones_mask & V2_ONES) == V2_ONES) BLISS_LAUNCH((distance_matrix_diag_kernel<23, V2_ONES>), g2, 128, 0, st, rows, n_rows, cols, n_cols, w_or_m, out, 1.0f);
+            else BLISS_LAUNCH((distance_matrix_diag_kernel<23, 0u>), g2, 128, 0, st, rows, n_rows, cols, n_cols, w_or_m, out, 1.0f);
+        } else {
+            if ((ones_mask & all) == all) BLISS_LAUNCH((distance_matrix_diag_kernel<20, 0xFFFFFu>), g2, 128, 0, st, rows, n_rows, cols, n_cols, w_or_m, out, 1.0f);
+            else BLISS_LAUNCH((distance_matrix_diag_kernel<20, 0u>), g2, 128, 0, st, rows, n_rows, cols, n_cols, w_or_m, out, 1.0f);
+        }
+        return 1;
+    }
+#endif
     dim3 grid((n_cols + 255u) / 256u, (n_rows + 31u) / 32u);
     if (dim == 23) BLISS_LAUNCH(distance_matrix_kernel<23>, grid, 128, 0, st, rows, n_rows, cols, n_cols, mode, w_or_m, out);
     else if (dim == 20) BLISS_LAUNCH(distance_matrix_kernel<20>, grid, 128, 0, st, rows, n_rows, cols, n_cols, mode, w_or_m, out);
