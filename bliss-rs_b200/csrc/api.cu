@@ -558,6 +558,19 @@ int build_tables() {
                 hann[2 * (8192 + 4 * 256) + (size_t)(r * 128 + t) * 8 + j] = (float)cos(ph);
                 hann[2 * (8192 + 4 * 256) + (size_t)(r * 128 + t) * 8 + 4 + j] = (float)sin(ph);
             }
+    // stft8192v3_kernel (stft8192_v3.cuh): one column per thread, frame rotated by r = 0..1 samples, [r][thread < 256]
+    // {cos phi_0, cos phi_1, sin phi_0, sin phi_1}, phi_j = 2 pi (2 thread + j - r) / 8192
+    {
+        const size_t off3 = hann.size();
+        hann.resize(off3 + 2 * 256 * 4);
+        for (int r = 0; r < 2; r++)
+            for (int t = 0; t < 256; t++)
+                for (int j = 0; j < 2; j++) {
+                    const double ph = 2.0 * M_PI * (double)(2 * t + j - r) / 8192.0;
+                    hann[off3 + (size_t)(r * 256 + t) * 4 + j] = (float)cos(ph);
+                    hann[off3 + (size_t)(r * 256 + t) * 4 + 2 + j] = (float)sin(ph);
+                }
+    }
     // pass-1 twiddles [k1][b] = W4096^(b k1), pass-2 twiddles [k2][j] = W256^(j k2), and W8192^t, t < 256
     // (real-FFT untangling): rfft8192.cuh
     std::vector<cpx> tw4(4096), tw2(256), tw(256);

@@ -8,6 +8,7 @@
 #include "rfft8192.cuh"
 #include "rfft8192_r64.cuh"
 #include "stft8192_v2.cuh"
+#include "stft8192_v3.cuh"
 
 namespace bliss {
 
@@ -1248,16 +1249,25 @@ int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int 
                     const cpx *tw8192, const cpx *tw64, float *mags, double *cand_mag, double *cand_pitch,
                     unsigned int *cand_count, int variant, cudaStream_t st) {
     if (total_frames == 0) return 0;
-    if ((variant & (VARIANT_STFT_V1 | VARIANT_R64 | VARIANT_OLD_EPILOGUE)) == 0) {  // the round-2 kernel (stft8192_v2.cuh)
-#ifndef BLISS_HOST_EMUL
+    if ((variant & (VARIANT_STFT_V1 | VARIANT_R64 | VARIANT_OLD_EPILOGUE)) == 0) {  // the round-2 kernels
         // > 48 KB of dynamic shared memory is an opt-in, per device: set on every launch
-        if (cudaFuncSetAttribute(stft8192v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2::SMEM_BYTES) != cudaSuccess)
-            return -1;
-#endif
         const unsigned int grid = (total_frames + s2::ITEMS_PER_CTA - 1) / s2::ITEMS_PER_CTA;
         const int fpi = K3_FRAMES_PER_CTA;
-        BLISS_LAUNCH(stft8192v2_kernel, grid, s2::THREADS, s2::SMEM_BYTES, st, pcm, songs, frame_prefix, n_songs, total_frames, fpi, hann,
-                     tw1, tw2, tw8192, mags, cand_mag, cand_pitch, cand_count);
+        if (variant & VARIANT_STFT_V2) {  // 128 threads, two columns per thread (stft8192_v2.cuh)
+#ifndef BLISS_HOST_EMUL
+            if (cudaFuncSetAttribute(stft8192v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2::SMEM_BYTES) != cudaSuccess)
+                return -1;
+#endif
+            BLISS_LAUNCH(stft8192v2_kernel, grid, s2::THREADS, s2::SMEM_BYTES, st, pcm, songs, frame_prefix, n_songs, total_frames, fpi, hann,
+                         tw1, tw2, tw8192, mags, cand_mag, cand_pitch, cand_count);
+        } else {                          // 256 threads, one column per thread (stft8192_v3.cuh)
+#ifndef BLISS_HOST_EMUL
+            if (cudaFuncSetAttribute(stft8192v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3::SMEM_BYTES) != cudaSuccess)
+                return -1;
+#endif
+            BLISS_LAUNCH(stft8192v3_kernel, grid, s3::THREADS, s3::SMEM_BYTES, st, pcm, songs, frame_prefix, n_songs, total_frames, fpi, hann,
+                         tw1, tw2, tw8192, mags, cand_mag, cand_pitch, cand_count);
+        }
         return 1;
     }
     if (variant & VARIANT_R64) {

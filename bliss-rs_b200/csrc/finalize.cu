@@ -5,8 +5,12 @@
 //    loudness(mean,std), chroma x13 (x10 for v1)]
 // Restates SpectralDesc::get_* (timbral.rs:57-122), ZeroCrossingRateDesc::get_value
 // (:248-252), LoudnessDesc::get_value (misc.rs:51-65), ChromaDesc::get_values
-// (chroma.rs:97-132).  Means / population std-devs are accumulated in f64 (the
-// reference's f32 running sums are themselves only ~1e-6 accurate).
+// (chroma.rs:97-132).  The four MEANS are the reference's own `utils::mean` (utils.rs:66-68): a plain sequential f32
+// sum -- restated as such (one thread per array walks it in order), because on a long song that sum's rounding is
+// systematic, not noise: 103 356 roll-off values of a 10-minute track, all multiples of 43.07 Hz, are added to an
+// accumulator near 5e8 (ulp 32) and the reference's mean ends up 3.3e-4 (normalised) away from the exact one
+// (measured on BASELINE configs[4], profiles/config5_r02_*.json).  The population std-devs stay two-pass f64 (ndarray's
+// one-pass f32 Welford agrees with that to ~1e-5 on the same corpus).
 #include "common.cuh"
 
 namespace bliss {
@@ -68,6 +72,7 @@ finalize_kernel(const SongDesc *__restrict__ songs, const float *__restrict__ ce
                 int version, float *__restrict__ out, unsigned int out_base, const PeerRows peers) {
     __shared__ double s_tmp[K9_THREADS / 32];
     __shared__ double s_feat[10];
+    __shared__ float s_seq[4];  // utils::mean of centroid / roll-off / flatness / loudness: sequential f32 sums
     __shared__ float o[24];  // the finished row; stored to `out` and to every peer at the end
     const SongDesc sd = songs[blockIdx.x];
     const int dim = version == 1 ? 20 : 23;
@@ -77,19 +82,36 @@ finalize_kernel(const SongDesc *__restrict__ songs, const float *__restrict__ ce
         store_row(o, dim, out, out_base, peers);
         return;
     }
+    if (threadIdx.x < 4) {  // `input.iter().sum::<f32>() / len as f32`, in order (loads run ahead of the add chain)
+        const float *v = threadIdx.x == 0 ? centroid + sd.s_off : threadIdx.x == 1 ? rolloff + sd.s_off
+                       : threadIdx.x == 2 ? flatness + sd.s_off : loud_ms + sd.l_off;
+        const unsigned int n = threadIdx.x < 3 ? sd.n_s : sd.n_l;
+        float acc = 0.f;
+        unsigned int i = 0;
+        for (; i + 8 <= n; i += 8) {
+            float t[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) t[k] = v[i + k];
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc = __fadd_rn(acc, t[k]);
+        }
+        for (; i < n; i++) acc = __fadd_rn(acc, v[i]);
+        s_seq[threadIdx.x] = acc / (float)n;
+    }
     float m, s;
     const float half_sr = (float)SAMPLE_RATE / 2.f;
-    mean_std(centroid + sd.s_off, sd.n_s, s_tmp, m, s);
-    if (threadIdx.x == 0) { o[2] = normalize(m, 0.f, half_sr); o[3] = normalize(s, 0.f, half_sr); }
+    mean_std(centroid + sd.s_off, sd.n_s, s_tmp, m, s);  // (its barriers publish s_seq)
+    if (threadIdx.x == 0) { o[2] = normalize(s_seq[0], 0.f, half_sr); o[3] = normalize(s, 0.f, half_sr); }
     mean_std(rolloff + sd.s_off, sd.n_s, s_tmp, m, s);
-    if (threadIdx.x == 0) { o[4] = normalize(m, 0.f, half_sr); o[5] = normalize(s, 0.f, half_sr); }
+    if (threadIdx.x == 0) { o[4] = normalize(s_seq[1], 0.f, half_sr); o[5] = normalize(s, 0.f, half_sr); }
     mean_std(flatness + sd.s_off, sd.n_s, s_tmp, m, s);
     if (threadIdx.x == 0) {  // timbral.rs:104-122
-        o[6] = 2.f * (m - 0.f) / (1.f - 0.f) - 1.f;
+        o[6] = 2.f * (s_seq[2] - 0.f) / (1.f - 0.f) - 1.f;
         o[7] = 2.f * (s - 0.f) / (1.f - 0.f) - 1.f;
     }
     mean_std(loud_ms + sd.l_off, sd.n_l, s_tmp, m, s);
     if (threadIdx.x == 0) {  // misc.rs:51-65
+        m = s_seq[3];
         if (m < 1e-9f) m = 1e-9f;
         if (s < 1e-9f) s = 1e-9f;
         o[8] = normalize(10.0f * log10f(m), -90.f, 0.f);

@@ -98,6 +98,19 @@ int main(int argc, char **argv) {
                 hann[2 * (8192 + 4 * 256) + (size_t)(r * 128 + t) * 8 + j] = (float)cos(ph);
                 hann[2 * (8192 + 4 * 256) + (size_t)(r * 128 + t) * 8 + 4 + j] = (float)sin(ph);
             }
+    // stft8192v3_kernel (stft8192_v3.cuh): one column per thread, frame rotated by r = 0..1 samples, [r][thread < 256]
+    // {cos phi_0, cos phi_1, sin phi_0, sin phi_1}, phi_j = 2 pi (2 thread + j - r) / 8192
+    {
+        const size_t off3 = hann.size();
+        hann.resize(off3 + 2 * 256 * 4);
+        for (int r = 0; r < 2; r++)
+            for (int t = 0; t < 256; t++)
+                for (int j = 0; j < 2; j++) {
+                    const double ph = 2.0 * M_PI * (double)(2 * t + j - r) / 8192.0;
+                    hann[off3 + (size_t)(r * 256 + t) * 4 + j] = (float)cos(ph);
+                    hann[off3 + (size_t)(r * 256 + t) * 4 + 2 + j] = (float)sin(ph);
+                }
+    }
     std::vector<cpx> tw4(4096), tw2(256), tw8(256);
     for (int k1 = 0; k1 < 16; k1++)
         for (int b = 0; b < 256; b++) {
@@ -239,6 +252,26 @@ int main(int argc, char **argv) {
             std::sort(cp.begin(), cp.end());
             dump("peak_mags_v2", cm);
             dump("peak_pitches_v2", cp);
+        }
+        {   // stft8192v3_kernel (round 2): 256 threads, one column per thread, mirror halves exchanged through the buffer
+            std::vector<float> mags((size_t)sd.n_c_comp * CH_STRIDE, -7.f);
+            std::vector<double> cm((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.), cp((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.);
+            std::vector<unsigned> cc(1, 0u);
+            emu::launch((ctas + s3::ITEMS_PER_CTA - 1) / s3::ITEMS_PER_CTA, s3::THREADS, [&] {
+                stft8192v3_kernel(x.data(), songs.data(), fp.data(), 1, ctas, K3_FRAMES_PER_CTA, hann.data(), tw4.data(), tw2.data(),
+                                  tw8.data(), mags.data(), cm.data(), cp.data(), cc.data());
+            }, s3::SMEM_BYTES);
+            std::vector<float> dense((size_t)sd.n_c_comp * CH_BINS);
+            for (unsigned f = 0; f < sd.n_c_comp; f++)
+                memcpy(&dense[(size_t)f * CH_BINS], &mags[(size_t)f * CH_STRIDE], CH_BINS * 4);
+            dump("stft8192_v3", dense);
+            dump("peaks_v3", cc);
+            cm.resize(cc[0]);
+            cp.resize(cc[0]);
+            std::sort(cm.begin(), cm.end());
+            std::sort(cp.begin(), cp.end());
+            dump("peak_mags_v3", cm);
+            dump("peak_pitches_v3", cp);
         }
         run_stft("default", stft8192_kernel<true>);
         run_stft("v64", stft8192_kernel<true, K3V_TWPROD>);

@@ -931,3 +931,27 @@ def test_device_chroma_filter_tables():
         want = O.chroma_filter(8192, tuning)
         assert got.shape == want.shape == (12, 4097)
         assert np.abs(got - want).max() < 1e-9, (idx, np.abs(got - want).max())
+
+
+def test_packed_distance_kernel_is_bit_identical_to_the_scalar_one():
+    """distance_matrix_diag_kernel (f32x2: two columns per thread, products and sums rounded separately -- the add is
+    an FMA by a run-time 1.0 so that ptxas cannot contract it) against the round-1 scalar kernel (bit 65536) and the
+    oracle, bit for bit, for the v2 weights, the identity (v1) and an arbitrary diagonal metric, on shapes that leave
+    partial tiles."""
+    rng = np.random.default_rng(11)
+    for dim, m in ((23, B.native.feature_weights(2)), (20, None), (23, np.diag(rng.uniform(0.1, 2.0, 23)).astype(np.float32)),
+                   (20, B.native.feature_weights(1))):
+        rows = (rng.uniform(-1, 1, (131, dim))).astype(np.float32)
+        cols = (rng.uniform(-1, 1, (517, dim))).astype(np.float32)
+        rows[3] = cols[5]          # an exact zero distance
+        cols[7] = cols[5] + np.float32(1e-6)
+        try:
+            B.native.set_variant(65536)
+            want = B.native.distance_matrix(rows, cols, m=m)
+        finally:
+            B.native.set_variant(0)
+        got = B.native.distance_matrix(rows, cols, m=m)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (dim, np.abs(got - want).max())
+        ref = np.array([[O.mahalanobis_distance(r, c, m if m is not None else np.eye(dim, dtype=np.float32)) for c in cols[:40]]
+                        for r in rows[:9]], np.float32)
+        assert np.array_equal(got[:9, :40].view(np.uint32), ref.view(np.uint32))
