@@ -417,6 +417,9 @@ def distance(a, b, metric=METRIC_MAHALANOBIS, m=None):
 def distance_matrix(rows, cols, metric=METRIC_MAHALANOBIS, m=None):
     L = lib()
     rows, cols = _f32c(np.atleast_2d(rows)), _f32c(np.atleast_2d(cols))
+    if rows.shape[0] == 0 or cols.shape[0] == 0:
+        return np.zeros((rows.shape[0], cols.shape[0]), np.float32)
+    _same_dim(rows, cols, "distance_matrix")
     dim = rows.shape[1]
     metric, m, mp = _metric_args(metric, m, dim)
     out = np.zeros((rows.shape[0], cols.shape[0]), np.float32)
@@ -432,9 +435,20 @@ def distance_matrix_device(d_rows, n_rows, d_cols, n_cols, dim, d_out, metric=ME
     check(L.bliss_b200_distance_matrix_device(d_rows, n_rows, d_cols, n_cols, dim, metric, mp, d_out, stream_ptr))
 
 
+def _same_dim(a, b, what):
+    """the reference panics on vectors of different lengths (ndarray dot / sub): refuse them before the device reads
+    `dim` floats per row of both"""
+    if a.ndim != 2 or b.ndim != 2 or a.shape[1] != b.shape[1]:
+        raise NativeError("%s: feature vectors of different lengths (%s vs %s) -- analyses of different "
+                          "features_version?" % (what, a.shape, b.shape))
+
+
 def closest_to_songs(seeds, cands, metric=METRIC_MAHALANOBIS, m=None):
     L = lib()
     seeds, cands = _f32c(np.atleast_2d(seeds)), _f32c(np.atleast_2d(cands))
+    if seeds.size == 0:  # no seed: every key is the empty sum 0, the stable order is the input order
+        return np.arange(cands.shape[0], dtype=np.uint32), np.zeros(cands.shape[0], np.float32)
+    _same_dim(seeds, cands, "closest_to_songs")
     dim = cands.shape[1]
     metric, m, mp = _metric_args(metric, m, dim)
     order = np.zeros(cands.shape[0], np.uint32)
@@ -447,6 +461,9 @@ def closest_to_songs(seeds, cands, metric=METRIC_MAHALANOBIS, m=None):
 def song_to_song(seeds, cands, metric=METRIC_MAHALANOBIS, m=None):
     L = lib()
     seeds, cands = _f32c(np.atleast_2d(seeds)), _f32c(np.atleast_2d(cands))
+    if seeds.size == 0:
+        raise NativeError("song_to_song needs at least one initial song")
+    _same_dim(seeds, cands, "song_to_song")
     dim = cands.shape[1]
     metric, m, mp = _metric_args(metric, m, dim)
     order = np.zeros(cands.shape[0], np.uint32)

@@ -1490,7 +1490,8 @@ static int distance_matrix_host_locked(const float *rows, uint32_t n_rows, const
     const int nl = launch_distance_matrix(g.misc[0].as<float>(), n_rows, g.misc[1].as<float>(), n_cols, (int)dim,
                                           mode, d_w, g.misc[2].as<float>(), st, g.metric_ones, g.variant);
     p.done(nl);
-    if (nl < 0) { g_last_error = "unsupported dim"; return BLISS_B200_E_ARG; }
+    if (nl < 0) { g_last_error = "unsupported dim or too many rows in one call"; return BLISS_B200_E_ARG; }
+    CK(cudaGetLastError());  // an invalid launch configuration must not come back as a zero-filled matrix
     CK(cudaMemcpyAsync(out, g.misc[2].p, (size_t)n_rows * n_cols * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return BLISS_B200_OK;
@@ -1560,9 +1561,17 @@ int bliss_b200_closest_to_songs(const float *seeds, uint32_t n_seeds, const floa
                                 g.misc[3].as<unsigned long long>() + n_cands, g.misc[4].p, tmp_bytes,
                                 g.misc[5].as<unsigned int>(), st);
     p.done(nl);
+    CK(cudaGetLastError());
+    std::vector<float> hk;  // the keys come back either way: a NaN distance is an error, not an order
+    if (!keys) { hk.resize(n_cands); keys = hk.data(); }
     CK(cudaMemcpyAsync(order, g.misc[5].p, (size_t)n_cands * 4, cudaMemcpyDeviceToHost, st));
-    if (keys) CK(cudaMemcpyAsync(keys, g.misc[2].p, (size_t)n_cands * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(keys, g.misc[2].p, (size_t)n_cands * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < n_cands; i++)
+        if (keys[i] != keys[i]) {  // the reference's n32(distance) panics on NaN (src/playlist.rs:267)
+            g_last_error = "NaN distance for candidate " + std::to_string(i) + " (NaN features or metric)";
+            return BLISS_B200_E_ARG;
+        }
     return BLISS_B200_OK;
 }
 

@@ -1253,14 +1253,14 @@ int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int 
         // > 48 KB of dynamic shared memory is an opt-in, per device: set on every launch
         const unsigned int grid = (total_frames + s2::ITEMS_PER_CTA - 1) / s2::ITEMS_PER_CTA;
         const int fpi = K3_FRAMES_PER_CTA;
-        if (variant & VARIANT_STFT_V2) {  // 128 threads, two columns per thread (stft8192_v2.cuh)
+        if ((variant & VARIANT_STFT_V3) == 0) {  // 128 threads, two columns per thread (stft8192_v2.cuh): the default
 #ifndef BLISS_HOST_EMUL
             if (cudaFuncSetAttribute(stft8192v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2::SMEM_BYTES) != cudaSuccess)
                 return -1;
 #endif
             BLISS_LAUNCH(stft8192v2_kernel, grid, s2::THREADS, s2::SMEM_BYTES, st, pcm, songs, frame_prefix, n_songs, total_frames, fpi, hann,
                          tw1, tw2, tw8192, mags, cand_mag, cand_pitch, cand_count);
-        } else {                          // 256 threads, one column per thread (stft8192_v3.cuh)
+        } else {  // 256 threads, one column per thread (stft8192_v3.cuh): same speed on B200 (profiles/ncu_r02_stft8192v3_128songs.md)
 #ifndef BLISS_HOST_EMUL
             if (cudaFuncSetAttribute(stft8192v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3::SMEM_BYTES) != cudaSuccess)
                 return -1;

@@ -87,7 +87,7 @@ enum {
     VARIANT_PVOC_V1 = 16384,   // pvoc512: the round-1 kernel (with its promoted cuts) instead of pvoc512v2_kernel
     VARIANT_STFT_V1 = 32768,   // stft8192: the round-1 kernel (with its promoted cuts) instead of stft8192v2_kernel (bits 1 and 32 imply it)
     VARIANT_OLD_DIST = 65536,  // distance matrix: the round-1 scalar kernel instead of distance_matrix_diag_kernel
-    VARIANT_STFT_V2 = 131072,  // stft8192: the 128-thread / two-column round-2 kernel instead of the 256-thread one
+    VARIANT_STFT_V3 = 131072,  // stft8192: the 256-thread / one-column kernel (stft8192_v3.cuh) instead of the 128-thread / two-column one; measured at the same 21.8 ms
     VARIANT_PROMOTED = 64 | 128 | 256 | 512 | 1024 | 2048 | 4096 | 8192,
 };
 

@@ -193,9 +193,10 @@ __global__ void __launch_bounds__(256)
 distance_matrix_generic_kernel(const float *__restrict__ rows, unsigned int n_rows,
                                const float *__restrict__ cols, unsigned int n_cols, int dim, int mode,
                                const float *__restrict__ w_or_m, float *__restrict__ out) {
-    const unsigned int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (c >= n_cols || r >= n_rows) return;
-    out[(size_t)r * n_cols + c] = pair_distance<0>(rows + (size_t)r * dim, cols + (size_t)c * dim, dim, mode, w_or_m);
+    const unsigned int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    for (unsigned int r = blockIdx.y; r < n_rows; r += gridDim.y)  // grid.y is capped at 65535: rows are strided over it
+        out[(size_t)r * n_cols + c] = pair_distance<0>(rows + (size_t)r * dim, cols + (size_t)c * dim, dim, mode, w_or_m);
 }
 
 // keys[j] = sum_i dist(seed_i, cand_j), seeds visited in order (Iterator::sum, playlist.rs:56-58)
@@ -294,10 +295,11 @@ int launch_distance_matrix(const float *rows, unsigned int n_rows, const float *
         return 1;
     }
 #endif
+    if (n_rows > 32u * 65535u) return -1;  // (2 M rows per call: the callers block their rows long before that)
     dim3 grid((n_cols + 255u) / 256u, (n_rows + 31u) / 32u);
     if (dim == 23) BLISS_LAUNCH(distance_matrix_kernel<23>, grid, 128, 0, st, rows, n_rows, cols, n_cols, mode, w_or_m, out);
     else if (dim == 20) BLISS_LAUNCH(distance_matrix_kernel<20>, grid, 128, 0, st, rows, n_rows, cols, n_cols, mode, w_or_m, out);
-    else if (dim <= MAX_DIM) BLISS_LAUNCH(distance_matrix_generic_kernel, dim3((n_cols + 255u) / 256u, n_rows), 256, 0, st, rows, n_rows, cols, n_cols, dim, mode, w_or_m, out);
+    else if (dim <= MAX_DIM) BLISS_LAUNCH(distance_matrix_generic_kernel, dim3((n_cols + 255u) / 256u, n_rows < 65535u ? n_rows : 65535u), 256, 0, st, rows, n_rows, cols, n_cols, dim, mode, w_or_m, out);
     else return -1;
     return 1;
 }

@@ -82,21 +82,31 @@ finalize_kernel(const SongDesc *__restrict__ songs, const float *__restrict__ ce
         store_row(o, dim, out, out_base, peers);
         return;
     }
-    if (threadIdx.x < 4) {  // `input.iter().sum::<f32>() / len as f32`, in order (loads run ahead of the add chain)
-        const float *v = threadIdx.x == 0 ? centroid + sd.s_off : threadIdx.x == 1 ? rolloff + sd.s_off
-                       : threadIdx.x == 2 ? flatness + sd.s_off : loud_ms + sd.l_off;
-        const unsigned int n = threadIdx.x < 3 ? sd.n_s : sd.n_l;
-        float acc = 0.f;
-        unsigned int i = 0;
-        for (; i + 8 <= n; i += 8) {
-            float t[8];
+    {   // `input.iter().sum::<f32>() / len as f32`, in order: warp w walks array w.  A lane loads every 32nd value
+        // (coalesced, four rows of 32 in flight, the next four requested before this group's adds) and the running sum
+        // takes them in index order through shuffles; rows past the end are +0.0f, which leaves an f32 sum unchanged.
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (w < 4) {
+            const float *v = w == 0 ? centroid + sd.s_off : w == 1 ? rolloff + sd.s_off : w == 2 ? flatness + sd.s_off
+                                                                                                 : loud_ms + sd.l_off;
+            const unsigned int n = w < 3 ? sd.n_s : sd.n_l;
+            float acc = 0.f, t[4], nx[4];
 #pragma unroll
-            for (int k = 0; k < 8; k++) t[k] = v[i + k];
+            for (int r = 0; r < 4; r++) nx[r] = (32u * r + lane < n) ? v[32u * r + lane] : 0.f;
+            for (unsigned int base = 0; base < n; base += 128u) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) acc = __fadd_rn(acc, t[k]);
+                for (int r = 0; r < 4; r++) {
+                    t[r] = nx[r];
+                    const unsigned int i = base + 128u + 32u * r + lane;
+                    nx[r] = (i < n) ? v[i] : 0.f;
+                }
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int k = 0; k < 32; k++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, t[r], k));
+            }
+            if (lane == 0) s_seq[w] = acc / (float)n;
         }
-        for (; i < n; i++) acc = __fadd_rn(acc, v[i]);
-        s_seq[threadIdx.x] = acc / (float)n;
     }
     float m, s;
     const float half_sr = (float)SAMPLE_RATE / 2.f;

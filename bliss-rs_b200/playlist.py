@@ -114,7 +114,14 @@ def _as_metric(metric_builder) -> _Metric:
     if isinstance(metric_builder, _Metric):
         return metric_builder
     raise TypeError("this backend runs distances on the GPU: pass euclidean_distance, cosine_distance or a "
-                    "mahalanobis_distance_builder(m) metric")
+                    "mahalanobis_distance_builder(m) metric (a plain callable f(a, b) -> float is accepted by the "
+                    "playlist functions and evaluated on the host, as the reference evaluates it)")
+
+
+def _is_host_callable(metric_builder) -> bool:
+    """the reference takes any Fn(&Array1, &Array1) -> f32 (src/playlist.rs:41-44): such a callable cannot run on the
+    device and is applied on the host with the reference's own (stable / first-minimum) walk"""
+    return callable(metric_builder) and not isinstance(metric_builder, _Metric)
 
 
 def distance_matrix(rows, cols, metric_builder=euclidean_distance) -> np.ndarray:
@@ -128,6 +135,12 @@ def closest_to_songs(initial_songs: Sequence, candidate_songs: Sequence, metric_
     cands = list(candidate_songs)
     if not cands:
         return []
+    if _is_host_callable(metric_builder):
+        seeds, vc = _vectors(initial_songs), _vectors(cands)
+        keys = np.array([np.float32(sum(np.float32(metric_builder(sv, c)) for sv in seeds)) for c in vc], np.float32)
+        if np.isnan(keys).any():
+            raise ValueError("NaN distance (the reference's n32() panics)")
+        return [cands[i] for i in np.argsort(keys, kind="stable")]
     mt = _as_metric(metric_builder)
     order, _ = native.closest_to_songs(_vectors(initial_songs), _vectors(cands), mt.metric, mt.m)
     return [cands[i] for i in order]
@@ -138,6 +151,15 @@ def song_to_song(initial_songs: Sequence, candidate_songs: Sequence, metric_buil
     cands = list(candidate_songs)
     if not cands:
         return []
+    if _is_host_callable(metric_builder):
+        cur, vc = list(_vectors(initial_songs)), _vectors(cands)
+        alive, order = list(range(len(cands))), []
+        while alive:
+            keys = [np.float32(sum(np.float32(metric_builder(sv, vc[j])) for sv in cur)) for j in alive]
+            k = int(np.argmin(np.asarray(keys, np.float32)))  # first minimum, as ndarray-stats argmin
+            order.append(alive.pop(k))
+            cur = [vc[order[-1]]]
+        return [cands[i] for i in order]
     mt = _as_metric(metric_builder)
     order = native.song_to_song(_vectors(initial_songs), _vectors(cands), mt.metric, mt.m)
     return [cands[i] for i in order]
@@ -148,18 +170,45 @@ def dedup_playlist(playlist: Iterable, distance_threshold: Optional[float] = Non
     return dedup_playlist_custom_distance(playlist, distance_threshold, euclidean_distance)
 
 
+class _BandDistances:
+    """d(i, j), j > i, for a walk that only ever looks a little ahead of i: rows are fetched from the device in blocks
+    of `rows` songs against the next rows + band candidates (bounded memory: never n x n), and a look-ahead beyond the
+    band (a long run of duplicates) falls back to one 1 x rows call.  A plain callable metric is evaluated on the host
+    pair by pair, as the reference does."""
+
+    def __init__(self, songs, vec, mt, rows=256, band=32):
+        self.songs, self.vec, self.mt, self.rows, self.band = songs, vec, mt, rows, band
+        self.block_lo, self.block = -1, None
+        self.far_i, self.far_lo, self.far = -1, -1, None
+
+    def __call__(self, i, j):
+        if callable(self.mt) and not isinstance(self.mt, _Metric):
+            return np.float32(self.mt(self.vec[i], self.vec[j]))
+        lo = (i // self.rows) * self.rows
+        if j - lo - 1 < self.rows + self.band:
+            if self.block_lo != lo:
+                hi = min(len(self.vec), lo + self.rows)
+                self.block = native.distance_matrix(self.vec[lo:hi], self.vec[lo + 1:lo + 1 + self.rows + self.band],
+                                                    self.mt.metric, self.mt.m)
+                self.block_lo = lo
+            return self.block[i - lo, j - lo - 1]
+        if self.far_i != i or not (self.far_lo <= j < self.far_lo + self.rows):
+            self.far = native.distance_matrix(self.vec[i:i + 1], self.vec[j:j + self.rows], self.mt.metric, self.mt.m)[0]
+            self.far_i, self.far_lo = i, j
+        return self.far[j - self.far_lo]
+
+
 def dedup_playlist_custom_distance(playlist: Iterable, distance_threshold: Optional[float],
                                    metric_builder) -> Iterator:
     """src/playlist.rs:367-402: drops a song when it is closer than the threshold to the
-    last kept song, or has the same non-empty title and artist.  Distances to the
-    successor are computed for the whole playlist in one device call."""
+    last kept song, or has the same non-empty title and artist.  Only the distances the walk
+    looks at are computed, in bounded blocks on the device (_BandDistances)."""
     songs = list(playlist)
     if not songs:
         return iter(())
     thr = np.float32(0.05 if distance_threshold is None else distance_threshold)
-    mt = _as_metric(metric_builder)
-    vec = _vectors(songs)
-    dm = native.distance_matrix(vec, vec, mt.metric, mt.m) if len(songs) > 1 else None
+    mt = metric_builder if (callable(metric_builder) and not isinstance(metric_builder, _Metric)) else _as_metric(metric_builder)
+    dist = _BandDistances(songs, _vectors(songs), mt)
 
     def gen():
         i = 0
@@ -171,7 +220,7 @@ def dedup_playlist_custom_distance(playlist: Iterable, distance_threshold: Optio
                 same_tags = (getattr(s1, "title", None) is not None and getattr(s2, "title", None) is not None
                              and getattr(s1, "artist", None) is not None and getattr(s2, "artist", None) is not None
                              and s1.title == s2.title and s1.artist == s2.artist)
-                if dm[i, j] < thr or same_tags:
+                if dist(i, j) < thr or same_tags:
                     j += 1
                     continue
                 break

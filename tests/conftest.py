@@ -13,6 +13,27 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _cuda_available():
+    if os.environ.get("BLISS_B200_SO"):  # the host-emulated TEST build of the library stands in for the device
+        return True
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a box without CUDA: every test that needs the device is SKIPPED (not an error), so host-side
+    regressions are not buried under 35 'no CUDA device' failures."""
+    if _cuda_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (there is no CPU fallback in the product path)")
+    for item in items:
+        if "gpu" in item.keywords or os.path.basename(str(item.fspath)).startswith("test_gpu_"):
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden():
     g = np.load(os.path.join(ROOT, "tests", "golden", "golden.npz"))

@@ -652,6 +652,7 @@ def test_wav_files_through_the_decoder_pipeline(tmp_path, golden, pcm_piano):
 # process with a time limit.
 
 
+STFT_V3 = 131072  # BLISS_B200_VARIANT bit: stft8192v3_kernel (256 threads, one column per thread) instead of stft8192v2_kernel
 STFT_V1 = 32768  # BLISS_B200_VARIANT bit: the round-1 stft8192_kernel (its cuts are bits 64 / 128 / 4096 / 8192) instead of stftv2
 PVOC_V1 = 16384  # BLISS_B200_VARIANT bit: the round-1 pvoc512_kernel (its cuts are bits 512 / 1024 / 2048) instead of pvoc512v2_kernel
 
@@ -893,17 +894,18 @@ def test_stft8192v2_against_the_round1_kernel(pcm_song, pcm_piano):
         B.native.set_variant(STFT_V1)
         st0, f0 = B.native.analyze_batch(songs, 2)
         _, _, taps0 = B.native.analyze_taps(pcm_piano, 2)
-        B.native.set_variant(0)
-        st, f = B.native.analyze_batch(songs, 2)
-        _, _, taps = B.native.analyze_taps(pcm_piano, 2)
-        assert (st0 == 0).all() and (st == 0).all()
-        assert np.abs(f - f0).max() < 1e-5, np.abs(f - f0).max(0)
-        assert np.array_equal(f[:, :10], f0[:, :10])
         S = O.stft(pcm_piano, 8192, 2205)
-        assert np.abs(taps["stft8192"].T - S).max() / S.max() < 2e-6
         assert np.abs(taps0["stft8192"].T - S).max() / S.max() < 2e-6
-        assert taps["tuning"] == taps0["tuning"]
-        assert taps["n_peaks"] == taps0["n_peaks"]
+        for mask in (STFT_V3, 0):  # the 256-thread / one-column cut of the same design, then the default (128 threads)
+            B.native.set_variant(mask)
+            st, f = B.native.analyze_batch(songs, 2)
+            _, _, taps = B.native.analyze_taps(pcm_piano, 2)
+            assert (st0 == 0).all() and (st == 0).all()
+            assert np.abs(f - f0).max() < 1e-5, (mask, np.abs(f - f0).max(0))
+            assert np.array_equal(f[:, :10], f0[:, :10])
+            assert np.abs(taps["stft8192"].T - S).max() / S.max() < 2e-6
+            assert taps["tuning"] == taps0["tuning"]
+            assert taps["n_peaks"] == taps0["n_peaks"]
         # unaligned slices of ONE device buffer through the device API: offsets 0, 1, 2, 3 mod 4
         import torch
         flat = torch.from_numpy(np.concatenate([pcm_song, pcm_piano])).to(DEV)
