@@ -8,6 +8,7 @@ use std::sync::Once;
 #[link(name = "bliss_b200")]
 extern "C" {
     fn bliss_b200_init(device: c_int) -> c_int;
+    fn bliss_b200_init_devices(n_devices: c_int) -> c_int;
     fn bliss_b200_last_error() -> *const c_char;
     fn bliss_b200_feature_count(features_version: u16) -> u32;
     fn bliss_b200_analyze(pcm: *const f32, n_samples: u64, features_version: u16, out: *mut f32) -> c_int;
@@ -27,10 +28,15 @@ extern "C" {
 }
 
 static INIT: Once = Once::new();
+/// BLISS_B200_DEVICE=<n> pins the process to one GPU; otherwise every visible B200 is used: the crate is ONE process
+/// (src/song/decoder.rs:282-331), so one `bliss_b200_analyze_batch` call deals its songs over all devices inside the
+/// library (longest first, one host thread + copy stream per device) and the batcher below does not change.
 fn ensure_init() {
     INIT.call_once(|| unsafe {
-        let dev = std::env::var("BLISS_B200_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
-        assert_eq!(bliss_b200_init(dev), 0, "bliss_b200_init failed (no CPU fallback exists)");
+        match std::env::var("BLISS_B200_DEVICE").ok().and_then(|s| s.parse().ok()) {
+            Some(dev) => assert_eq!(bliss_b200_init(dev), 0, "bliss_b200_init failed (no CPU fallback exists)"),
+            None => assert!(bliss_b200_init_devices(0) > 0, "bliss_b200_init_devices failed (no CPU fallback exists)"),
+        }
     });
 }
 
