@@ -415,11 +415,11 @@ def distance(a, b, metric=METRIC_MAHALANOBIS, m=None):
 
 
 def distance_matrix(rows, cols, metric=METRIC_MAHALANOBIS, m=None):
-    L = lib()
     rows, cols = _f32c(np.atleast_2d(rows)), _f32c(np.atleast_2d(cols))
     if rows.shape[0] == 0 or cols.shape[0] == 0:
         return np.zeros((rows.shape[0], cols.shape[0]), np.float32)
     _same_dim(rows, cols, "distance_matrix")
+    L = lib()
     dim = rows.shape[1]
     metric, m, mp = _metric_args(metric, m, dim)
     out = np.zeros((rows.shape[0], cols.shape[0]), np.float32)
@@ -444,11 +444,11 @@ def _same_dim(a, b, what):
 
 
 def closest_to_songs(seeds, cands, metric=METRIC_MAHALANOBIS, m=None):
-    L = lib()
     seeds, cands = _f32c(np.atleast_2d(seeds)), _f32c(np.atleast_2d(cands))
     if seeds.size == 0:  # no seed: every key is the empty sum 0, the stable order is the input order
         return np.arange(cands.shape[0], dtype=np.uint32), np.zeros(cands.shape[0], np.float32)
     _same_dim(seeds, cands, "closest_to_songs")
+    L = lib()
     dim = cands.shape[1]
     metric, m, mp = _metric_args(metric, m, dim)
     order = np.zeros(cands.shape[0], np.uint32)
@@ -459,11 +459,11 @@ def closest_to_songs(seeds, cands, metric=METRIC_MAHALANOBIS, m=None):
 
 
 def song_to_song(seeds, cands, metric=METRIC_MAHALANOBIS, m=None):
-    L = lib()
     seeds, cands = _f32c(np.atleast_2d(seeds)), _f32c(np.atleast_2d(cands))
     if seeds.size == 0:
         raise NativeError("song_to_song needs at least one initial song")
     _same_dim(seeds, cands, "song_to_song")
+    L = lib()
     dim = cands.shape[1]
     metric, m, mp = _metric_args(metric, m, dim)
     order = np.zeros(cands.shape[0], np.uint32)

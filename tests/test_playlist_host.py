@@ -58,3 +58,60 @@ def test_closest_album_to_group_like_the_reference(monkeypatch, version):
     assert [s.path for s in got] == ["path-to-first", "path-to-third", "near-1", "near-2", "far-1", "far-2"]
     with pytest.raises(B.ProviderError):
         P.closest_album_to_group([], pool)
+
+
+def _songs(vals, version=B.FeaturesVersion.Version2, **kw):
+    n = version.feature_count()
+    return [B.Song(path="p%d" % i, analysis=B.Analysis([v] * n, version), features_version=version, **kw) for i, v in enumerate(vals)]
+
+
+def test_plain_callable_metrics_run_on_the_host():
+    """The reference takes any Fn(&Array1, &Array1) -> f32 (src/playlist.rs:41-44); such a callable cannot run on the
+    device: the playlist functions evaluate it on the host with the reference's own walks (stable sort of the summed
+    keys, first minimum of the chain).  No device call is made (this test runs without a GPU)."""
+    manhattan = lambda a, b: float(np.abs(a - b).sum())
+    songs = _songs([0.5, -0.2, 0.9, 0.5, 0.1])
+    seed = _songs([0.45])
+    got = P.closest_to_songs(seed, songs, manhattan)
+    assert [s.path for s in got] == ["p0", "p3", "p4", "p2", "p1"]       # the tie p0 / p3 keeps the input order
+    chain = P.song_to_song(seed, songs, manhattan)
+    assert [s.path for s in chain] == ["p0", "p3", "p2", "p4", "p1"]     # 0.5, 0.5, then the nearest to the last one
+    with pytest.raises(ValueError):
+        P.closest_to_songs(seed, songs, lambda a, b: float("nan"))
+    kept = list(P.dedup_playlist_custom_distance(_songs([0.0, 0.001, 0.002, 0.5, 0.501, 0.9]), 0.05, manhattan))
+    assert [s.path for s in kept] == ["p0", "p3", "p5"]
+
+
+def test_dedup_walk_never_builds_the_full_matrix(monkeypatch):
+    """dedup used to build an n x n matrix.  The walk now fetches bounded blocks (rows x (rows + band))
+    and falls back to 1 x rows calls for a run of duplicates longer than the band; the result is the reference's
+    (src/playlist.rs:367-402) and no call is larger than the block."""
+    calls = []
+
+    def fake_distance_matrix(rows, cols, metric, m):
+        calls.append((rows.shape[0], cols.shape[0]))
+        return np.sqrt(((rows[:, None, :] - cols[None, :, :]) ** 2).sum(-1)).astype(np.float32)
+    monkeypatch.setattr(P.native, "distance_matrix", fake_distance_matrix)
+    vals = [0.0] * 50 + [1.0] + [2.0 + 0.1 * i for i in range(700)] + [100.0] * 3
+    songs = _songs(vals)
+    kept = [s.path for s in P.dedup_playlist_custom_distance(songs, 0.05, P.euclidean_distance)]
+    want, i = [], 0
+    while i < len(vals):           # the reference's peek loop on the same distances
+        j = i + 1
+        while j < len(vals) and abs(vals[i] - vals[j]) * np.sqrt(23) < 0.05:
+            j += 1
+        want.append("p%d" % i)
+        i = j
+    assert kept == want
+    assert max(r * c for r, c in calls) <= 256 * (256 + 32) and len(calls) < 20
+    # same title + artist: dropped whatever the distance
+    tagged = _songs([0.0, 5.0, 9.0], title="t", artist="a")
+    assert [s.path for s in P.dedup_playlist_custom_distance(tagged, 0.05, P.euclidean_distance)] == ["p0"]
+
+
+def test_vectors_of_different_versions_are_refused():
+    from bliss_rs_b200 import _native as N
+    v1, v2 = np.zeros((2, 20), np.float32), np.zeros((3, 23), np.float32)
+    for fn in (N.closest_to_songs, N.song_to_song, N.distance_matrix):
+        with pytest.raises(N.NativeError, match="different lengths"):
+            fn(v1, v2)
