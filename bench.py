@@ -335,12 +335,10 @@ def main():
     if args.config == 4:
         import bench_config4
         sys.argv = [sys.argv[0]]
-        os.dup2(_REAL_STDOUT, 1)
-        return bench_config4.main()
+        return bench_config4.main(emit=_emit)  # (stdout stays on stderr: NCCL prints its banner there)
     if args.config == 5:
         import bench_config5
-        os.dup2(_REAL_STDOUT, 1)
-        return bench_config5.main(["--gpus", str(max(args.gpus, world))] + (["--songs", os.environ["BLISS_CFG5_SONGS"]] if os.environ.get("BLISS_CFG5_SONGS") else []))
+        return bench_config5.main(emit=_emit, argv=["--gpus", str(max(args.gpus, world))] + (["--songs", os.environ["BLISS_CFG5_SONGS"]] if os.environ.get("BLISS_CFG5_SONGS") else []))
 
     import torch
     import torch.distributed as dist

@@ -11,7 +11,7 @@ Timed on the device, max over ranks: the analysis of every wave (rows go straigh
 through peer memory, bliss_b200_analyze_batch_device_scatter; --gather nccl = one all_gather_into_tensor at the
 end), the epoch barrier and the distance row block.  One JSON line on rank 0.
 
-Written at the end of round 1 after the GPU budget was spent: NOT RUN YET (bench.py is the measured benchmark).
+Run on 8 B200s in round 2: profiles/config4_r02_8gpu_100k.json (also reachable as `bench.py --config 4`).
 """
 import argparse
 import json
@@ -24,7 +24,7 @@ TRACK = 3 * 60 * 22050
 BASE_SEED = 20260926
 
 
-def main():
+def main(emit=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--total-songs", type=int, default=100000)
     ap.add_argument("--wave", type=int, default=1024)
@@ -123,7 +123,7 @@ def main():
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
     if rank == 0:
         a_ms, d_ms = float(t[0]), float(t[1])
-        print(json.dumps({
+        (emit or (lambda d: print(json.dumps(d), flush=True)))({
             "bench": "configs[3]: %d tracks round-robin over %d GPUs, rows to every rank, all-pairs distance" % (n_total, world),
             "n_gpus": world, "songs": n_total, "waves_per_rank": waves, "wave_songs": W,
             "analysis_ms_max_over_ranks": a_ms, "exchange_plus_distance_ms_max_over_ranks": d_ms,
@@ -131,7 +131,7 @@ def main():
             "distance_pairs_per_s": (row_hi - row_lo) * n_total * world / (d_ms / 1e3),
             "exchange": "p2p-fused" if gather else ("nccl" if world > 1 else "none"),
             "checks_ok": bool(okt.item()),
-            "note": "PCM generated on the device between waves (untimed); %d distinct tracks per wave" % args.distinct}))
+            "note": "PCM generated on the device between waves (untimed); %d distinct tracks per wave" % args.distinct})
     if world > 1:
         dist.barrier()
         if gather:

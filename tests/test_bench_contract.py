@@ -34,7 +34,7 @@ def test_reference_arm_prints_one_contract_line():
 
 def test_committed_bench_lines_keep_the_contract():
     metric = _baseline()["metric"]
-    for name, n in (("bench_r01_1gpu.json", 1), ("bench_r01_2gpu.json", 2), ("bench_r01_8gpu.json", 8)):
+    for name, n in (("bench_r02_1gpu.json", 1), ("bench_r02_2gpu.json", 2), ("bench_r02_8gpu.json", 8)):
         d = json.load(open(os.path.join(ROOT, "profiles", name)))
         for k in BASE + ("roofline", "cpu_baseline", "clocks"):
             assert k in d, (name, k)
@@ -45,8 +45,22 @@ def test_committed_bench_lines_keep_the_contract():
         assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
         e = d["e2e"]
         assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
+        assert e["devices"] == n and e["bitwise_equal_to_device_path"] is True  # ONE call of one process over all n GPUs
+        assert 0.5 < e["frac_of_h2d_ceiling"] <= 1.05
+        assert 0 < r["step_read_frac"] < 1 and "static" in r["traffic_source"]
         c = d["clocks"]
         assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
         assert c["sm_mhz"] >= 0.9 * c["sm_max_mhz"]
-    cb = json.load(open(os.path.join(ROOT, "profiles", "bench_r01_1gpu.json")))["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and cb["parity_within_1e-4"] is True
+    one = json.load(open(os.path.join(ROOT, "profiles", "bench_r02_1gpu.json")))
+    cb = one["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and cb["parity_within_1e-4"] is True and cb["note"]
+    sm = one["stft_microbench"]  # BASELINE.json configs[2]: >= 10 000 tracks, looped-resident stated, fractions of the measured peak
+    assert sm["tracks"] >= 10000 and sm["looped_resident"] and sm["frac_read"] >= 0.25 and sm["frac_read_write"] > sm["frac_read"]
+    for name in ("config4_r02_8gpu_100k.json", "config5_r02_8gpu_20k.json"):
+        c = json.load(open(os.path.join(ROOT, "profiles", name)))
+        assert c["n_gpus"] == 8
+    c4 = json.load(open(os.path.join(ROOT, "profiles", "config4_r02_8gpu_100k.json")))
+    assert c4["songs"] == 100000 and c4["checks_ok"] is True and c4["exchange"] == "p2p-fused"
+    c5 = json.load(open(os.path.join(ROOT, "profiles", "config5_r02_8gpu_20k.json")))
+    assert c5["songs"] >= 20000 and c5["all_ok"] and c5["parity_subset"]["within_1e-4"] and c5["parity_subset"]["songs"] >= 2000
+    assert c5["playlist_from_seed"]["first_k_exact"] and c5["playlist_from_seed"]["kendall_tau"] > 0.999
