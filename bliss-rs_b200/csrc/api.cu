@@ -25,6 +25,10 @@ int launch_pvoc512(const float *, const SongDesc *, const unsigned int *, int, u
                    float *, float *, float *, float *, int, cudaStream_t);
 int launch_stft512_mags(const float *, const SongDesc *, const unsigned int *, int, unsigned int, int,
                         PvocTables, float *, int, cudaStream_t);
+void configure_kernels_spectral();
+void configure_kernels_chroma();
+void configure_kernels_tempo();
+void configure_kernels_finalize();
 int launch_timedomain(const float *, const SongDesc *, const unsigned int *, int, unsigned int, float *,
                       float *, unsigned int *, cudaStream_t);
 int launch_peakpick(const float *, const SongDesc *, const unsigned int *, int, unsigned int, float *,
@@ -149,6 +153,7 @@ struct Ctx {
     cudaEvent_t ev_begin = nullptr;
     size_t ws_limit = 0;
     int variant = 0;  // BLISS_B200_VARIANT, see common.cuh
+    int launch_order = 0;  // BLISS_B200_ORDER: which chain of a wave is enqueued first (run_wave)
     unsigned int metric_ones = 0;  // bit i: diagonal weight i of the metric last prepared is exactly 1 (prepare_metric)
     // constant tables
     DevBuf t_win512, t_twA, t_hann8k, t_tw4k, t_tw2, t_tw8k, t_tw64, t_filt, t_filt32;
@@ -246,7 +251,8 @@ void plan_wave(const uint64_t *offsets, const uint64_t *n_samples, uint32_t firs
     for (uint32_t i = 0; i < count; i++) total_pairs += geom_of(n_samples[first + i]).n_t;
     // enough warp-items to fill 148 SMs x 16 warps a few times over, runs as long as possible
     uint64_t r = total_pairs / (148ull * 16ull * 4ull);
-    w.pairs_per_item = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(8, r));
+    w.pairs_per_item = (uint32_t)std::min<uint64_t>(128, std::max<uint64_t>(8, r));  // (128 against 64: -0.6 % on 1024 tracks, profiles/knobs_r02.md)
+    if (const char *e = getenv("BLISS_B200_PVOC_PAIRS")) w.pairs_per_item = (uint32_t)std::max(4, atoi(e));  // experiments
     w.k1_prefix.assign(count + 1, 0);
     w.chunk_prefix.assign(count + 1, 0);
     w.t_prefix.assign(count + 1, 0);
@@ -377,43 +383,85 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
     // kernel's CUDA-event duration is its own and not inflated by the kernel it would overlap with)
     CK(cudaEventRecord(S.ev_fork, st));
     CK(cudaStreamWaitEvent(sb, S.ev_fork, 0));
-    { ProfScope p(K_STFT8K, sb);
-      const int nl = launch_stft8192(d_pcm, dv.sd, dv.pair_prefix, n, w.pair_prefix[n], g.t_hann8k.as<float>(),
-                                     g.t_tw4k.as<cpx>(), g.t_tw2.as<cpx>(), g.t_tw8k.as<cpx>(), g.t_tw64.as<cpx>(), S.mags.as<float>(), S.cand_mag.as<double>(),
-                                     S.cand_pitch.as<double>(), S.cand_count.as<unsigned int>(), g.variant, sb);
-      p.done(nl);
-      if (nl < 0) {
-          g_last_error = "cudaFuncSetAttribute(stft8192v2_kernel, MaxDynamicSharedMemorySize) failed";
-          return BLISS_B200_E_CUDA;
-      } }
-    { ProfScope p(K_TIME, st);
-      p.done(launch_timedomain(d_pcm, dv.sd, dv.chunk_prefix, n, w.chunk_prefix[n], S.loud.as<float>(),
-                               S.eb.as<float>(), S.zcr.as<unsigned int>(), st)); }
-    { ProfScope p(K_PVOC, st);
-      const int nl = launch_pvoc512(d_pcm, dv.sd, dv.k1_prefix, n, w.k1_prefix[n], (int)w.pairs_per_item, pvoc_tables(),
-                                    S.cent.as<float>(), S.roll.as<float>(), S.flat.as<float>(), S.flux.as<float>(), g.variant, st);
-      p.done(nl);
-      if (nl < 0) {
-          g_last_error = "cudaFuncSetAttribute(pvoc512v2_kernel, MaxDynamicSharedMemorySize) failed";
-          return BLISS_B200_E_CUDA;
-      } }
-    { ProfScope p(K_TUNING, sb);
-      p.done(launch_tuning(S.cand_mag.as<double>(), S.cand_pitch.as<double>(),
-                           S.cand_count.as<unsigned int>(), dv.sd, n, S.tuning.as<int>(), g.variant, sb)); }
-    { ProfScope p(K_PEAK, st);
-      p.done(launch_peakpick(S.flux.as<float>(), dv.sd, dv.t_prefix, n, w.t_prefix[n], S.thr.as<float>(), st)); }
-    { ProfScope p(K_CHROMA, sb);
-      const int nl = launch_chroma(S.mags.as<float>(), dv.sd, dv.tile_prefix, n, w.tile_prefix[n], g.t_filt32.as<float>(),
-                                   S.tuning.as<int>(), S.tiles.as<double>(), debug ? S.chroma_dbg.as<double>() : nullptr,
-                                   g.variant, sb);
-      p.done(nl);
-      if (nl < 0) {  // the opt-in to > 48 KB of dynamic shared memory was refused
-          g_last_error = "cudaFuncSetAttribute(chroma_pipe_kernel, MaxDynamicSharedMemorySize) failed";
-          return BLISS_B200_E_CUDA;
-      } }
-    { ProfScope p(K_BEAT, st);
-      p.done(launch_beattrack(S.thr.as<float>(), S.eb.as<float>(), dv.sd, n, S.bpm.as<float>(),
-                              S.tempo.as<float>(), S.bpm_count.as<unsigned int>(), g.variant, st)); }
+    // The order in which the two chains are ENQUEUED decides which one the block scheduler serves first: each FFT kernel
+    // fills every SM on its own (shared memory / registers), so the chains overlap only where one of them runs a
+    // latency-bound kernel.  g.launch_order (BLISS_B200_ORDER): 0 = chroma STFT first, then the tempo / timbral chain
+    // interleaved (round 1), 1 = the whole tempo / timbral chain first (the beat tracker then runs under the chroma
+    // STFT), 2 = the whole chroma chain first.
+    auto k_stft = [&]() -> int {
+        ProfScope p(K_STFT8K, sb);
+        const int nl = launch_stft8192(d_pcm, dv.sd, dv.pair_prefix, n, w.pair_prefix[n], g.t_hann8k.as<float>(),
+                                       g.t_tw4k.as<cpx>(), g.t_tw2.as<cpx>(), g.t_tw8k.as<cpx>(), g.t_tw64.as<cpx>(), S.mags.as<float>(), S.cand_mag.as<double>(),
+                                       S.cand_pitch.as<double>(), S.cand_count.as<unsigned int>(), g.variant, sb);
+        p.done(nl);
+        if (nl < 0) {
+            g_last_error = "cudaFuncSetAttribute(stft8192v2_kernel, MaxDynamicSharedMemorySize) failed";
+            return BLISS_B200_E_CUDA;
+        }
+        return 0;
+    };
+    auto k_time_pvoc = [&]() -> int {
+        { ProfScope p(K_TIME, st);
+          p.done(launch_timedomain(d_pcm, dv.sd, dv.chunk_prefix, n, w.chunk_prefix[n], S.loud.as<float>(),
+                                   S.eb.as<float>(), S.zcr.as<unsigned int>(), st)); }
+        ProfScope p(K_PVOC, st);
+        const int nl = launch_pvoc512(d_pcm, dv.sd, dv.k1_prefix, n, w.k1_prefix[n], (int)w.pairs_per_item, pvoc_tables(),
+                                      S.cent.as<float>(), S.roll.as<float>(), S.flat.as<float>(), S.flux.as<float>(), g.variant, st);
+        p.done(nl);
+        if (nl < 0) {
+            g_last_error = "cudaFuncSetAttribute(pvoc512v2_kernel, MaxDynamicSharedMemorySize) failed";
+            return BLISS_B200_E_CUDA;
+        }
+        return 0;
+    };
+    auto k_tuning = [&]() {
+        ProfScope p(K_TUNING, sb);
+        p.done(launch_tuning(S.cand_mag.as<double>(), S.cand_pitch.as<double>(),
+                             S.cand_count.as<unsigned int>(), dv.sd, n, S.tuning.as<int>(), g.variant, sb));
+    };
+    auto k_peak = [&]() {
+        ProfScope p(K_PEAK, st);
+        p.done(launch_peakpick(S.flux.as<float>(), dv.sd, dv.t_prefix, n, w.t_prefix[n], S.thr.as<float>(), st));
+    };
+    auto k_chroma = [&]() -> int {
+        ProfScope p(K_CHROMA, sb);
+        const int nl = launch_chroma(S.mags.as<float>(), dv.sd, dv.tile_prefix, n, w.tile_prefix[n], g.t_filt32.as<float>(),
+                                     S.tuning.as<int>(), S.tiles.as<double>(), debug ? S.chroma_dbg.as<double>() : nullptr,
+                                     g.variant, sb);
+        p.done(nl);
+        if (nl < 0) {  // the opt-in to > 48 KB of dynamic shared memory was refused
+            g_last_error = "cudaFuncSetAttribute(chroma_pipe_kernel, MaxDynamicSharedMemorySize) failed";
+            return BLISS_B200_E_CUDA;
+        }
+        return 0;
+    };
+    auto k_beat = [&]() {
+        ProfScope p(K_BEAT, st);
+        p.done(launch_beattrack(S.thr.as<float>(), S.eb.as<float>(), dv.sd, n, S.bpm.as<float>(),
+                                S.tempo.as<float>(), S.bpm_count.as<unsigned int>(), g.variant, st));
+    };
+    if (g.launch_order == 1) {
+        if (k_time_pvoc()) return BLISS_B200_E_CUDA;
+        k_peak();
+        k_beat();
+        if (k_stft()) return BLISS_B200_E_CUDA;
+        k_tuning();
+        if (k_chroma()) return BLISS_B200_E_CUDA;
+    } else if (g.launch_order == 2) {
+        if (k_stft()) return BLISS_B200_E_CUDA;
+        k_tuning();
+        if (k_chroma()) return BLISS_B200_E_CUDA;
+        if (k_time_pvoc()) return BLISS_B200_E_CUDA;
+        k_peak();
+        k_beat();
+    } else {
+        if (k_stft()) return BLISS_B200_E_CUDA;
+        if (k_time_pvoc()) return BLISS_B200_E_CUDA;
+        k_tuning();
+        k_peak();
+        if (k_chroma()) return BLISS_B200_E_CUDA;
+        k_beat();
+    }
     CK(cudaEventRecord(S.ev_join, sb));
     CK(cudaStreamWaitEvent(st, S.ev_join, 0));
     { ProfScope p(K_FINAL, st);
@@ -712,10 +760,19 @@ static int init_ctx_locked(int device) {
     g.ws_limit = (size_t)((double)total_b * 0.40);
     g.variant = VARIANT_PROMOTED;  // user mask 0
     if (const char *e = getenv("BLISS_B200_VARIANT")) g.variant = atoi(e) ^ VARIANT_PROMOTED;
+    if (const char *e = getenv("BLISS_B200_ORDER")) g.launch_order = atoi(e);
 #ifdef BLISS_HOST_EMUL
     fprintf(stderr, "[bliss_b200] HOST-EMULATED TEST BUILD (tests/cpu_emul): kernels run on the CPU, thread by thread. "
                     "Not a product path -- the product library is built by nvcc and needs a B200.\n");
 #endif
+    // One carve-out (all shared) for every kernel was tried so that kernels of the two chains could share an SM: no
+    // overlap appeared and timedomain_kernel lost its L1 (2.49 -> 3.25 ms), profiles/knobs_r02.md: off unless asked for.
+    if (getenv("BLISS_B200_MAX_SHARED_CARVEOUT")) {
+        configure_kernels_spectral();
+        configure_kernels_chroma();
+        configure_kernels_tempo();
+        configure_kernels_finalize();
+    }
     int rc = build_tables();
     if (rc) return rc;
     g.inited = true;

@@ -4,6 +4,10 @@
 //   K5  chroma_stft contraction 12 x 4097 . 4097 x frames in f64 (chroma.rs:393-412)
 //       fused with normalize_feature_sequence / extract_interval_features (:137-188)
 //   plus the table of all 100 possible chroma filterbanks (chroma.rs:197-267).
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "rfft8192.cuh"
 #include "rfft8192_r64.cuh"
@@ -1251,21 +1255,25 @@ int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int 
     if (total_frames == 0) return 0;
     if ((variant & (VARIANT_STFT_V1 | VARIANT_R64 | VARIANT_OLD_EPILOGUE)) == 0) {  // the round-2 kernels
         // > 48 KB of dynamic shared memory is an opt-in, per device: set on every launch
-        const unsigned int grid = (total_frames + s2::ITEMS_PER_CTA - 1) / s2::ITEMS_PER_CTA;
+        // work items (of four frames) per CTA: as many as still leave ~4 CTAs per resident slot (148 SMs x 3), at most 16
+        // (16 against 4 on 1024 tracks: 21.50 against 21.77 ms, profiles/knobs_r02.md); BLISS_B200_STFT_ITEMS overrides
+        static const int ipc_env = [] { const char *e = getenv("BLISS_B200_STFT_ITEMS"); return e ? atoi(e) : 0; }();
+        const int ipc = ipc_env > 0 ? ipc_env : (int)std::min<unsigned int>(16u, std::max<unsigned int>(1u, total_frames / (148u * 3u * 4u)));
+        const unsigned int grid = (total_frames + ipc - 1) / ipc;
         const int fpi = K3_FRAMES_PER_CTA;
         if ((variant & VARIANT_STFT_V3) == 0) {  // 128 threads, two columns per thread (stft8192_v2.cuh): the default
 #ifndef BLISS_HOST_EMUL
             if (cudaFuncSetAttribute(stft8192v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2::SMEM_BYTES) != cudaSuccess)
                 return -1;
 #endif
-            BLISS_LAUNCH(stft8192v2_kernel, grid, s2::THREADS, s2::SMEM_BYTES, st, pcm, songs, frame_prefix, n_songs, total_frames, fpi, hann,
+            BLISS_LAUNCH(stft8192v2_kernel, grid, s2::THREADS, s2::SMEM_BYTES, st, pcm, songs, frame_prefix, n_songs, total_frames, fpi, ipc, hann,
                          tw1, tw2, tw8192, mags, cand_mag, cand_pitch, cand_count);
         } else {  // 256 threads, one column per thread (stft8192_v3.cuh): same speed on B200 (profiles/ncu_r02_stft8192v3_128songs.md)
 #ifndef BLISS_HOST_EMUL
             if (cudaFuncSetAttribute(stft8192v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3::SMEM_BYTES) != cudaSuccess)
                 return -1;
 #endif
-            BLISS_LAUNCH(stft8192v3_kernel, grid, s3::THREADS, s3::SMEM_BYTES, st, pcm, songs, frame_prefix, n_songs, total_frames, fpi, hann,
+            BLISS_LAUNCH(stft8192v3_kernel, grid, s3::THREADS, s3::SMEM_BYTES, st, pcm, songs, frame_prefix, n_songs, total_frames, fpi, ipc, hann,
                          tw1, tw2, tw8192, mags, cand_mag, cand_pitch, cand_count);
         }
         return 1;
@@ -1339,6 +1347,21 @@ int launch_chroma(const float *mags, const SongDesc *songs, const unsigned int *
                                                                      tuning_idx, tile_partials, chroma_dbg);
     }
     return 1;
+}
+
+// Every kernel of a wave asks for the SAME L1 / shared-memory split (all shared): kernels with different carve-outs
+// cannot share an SM, and the latency-bound kernels of one chain are meant to run under the FFT kernels of the other
+// (api.cu run_wave).  Called once per device from bliss_b200_init.
+#ifndef BLISS_HOST_EMUL
+#define BLISS_MAX_SHARED(kern) (void)cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)
+#else
+#define BLISS_MAX_SHARED(kern) (void)0
+#endif
+void configure_kernels_chroma() {
+    BLISS_MAX_SHARED(stft8192v2_kernel);
+    BLISS_MAX_SHARED(stft8192v3_kernel);
+    BLISS_MAX_SHARED(tuning_select_kernel);
+    BLISS_MAX_SHARED(chroma_pipe_kernel);
 }
 
 }  // namespace bliss

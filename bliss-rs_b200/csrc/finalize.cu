@@ -172,4 +172,14 @@ int launch_finalize(const SongDesc *songs, int n_songs, const float *centroid, c
     return 1;
 }
 
+// Every kernel of a wave asks for the SAME L1 / shared-memory split (all shared): kernels with different carve-outs
+// cannot share an SM, and the latency-bound kernels of one chain are meant to run under the FFT kernels of the other
+// (api.cu run_wave).  Called once per device from bliss_b200_init.
+#ifndef BLISS_HOST_EMUL
+#define BLISS_MAX_SHARED(kern) (void)cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)
+#else
+#define BLISS_MAX_SHARED(kern) (void)0
+#endif
+void configure_kernels_finalize() { BLISS_MAX_SHARED(finalize_kernel); }
+
 }  // namespace bliss

@@ -954,4 +954,18 @@ int launch_timedomain(const float *pcm, const SongDesc *songs, const unsigned in
     return 1;
 }
 
+// Every kernel of a wave asks for the SAME L1 / shared-memory split (all shared): kernels with different carve-outs
+// cannot share an SM, and the latency-bound kernels of one chain are meant to run under the FFT kernels of the other
+// (api.cu run_wave).  Called once per device from bliss_b200_init.
+#ifndef BLISS_HOST_EMUL
+#define BLISS_MAX_SHARED(kern) (void)cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)
+#else
+#define BLISS_MAX_SHARED(kern) (void)0
+#endif
+void configure_kernels_spectral() {
+    BLISS_MAX_SHARED(pvoc512v2_kernel);
+    BLISS_MAX_SHARED(timedomain_kernel);
+    BLISS_MAX_SHARED(stft512_pairs_kernel);
+}
+
 }  // namespace bliss

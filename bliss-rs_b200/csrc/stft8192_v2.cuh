@@ -211,7 +211,7 @@ BLISS_HD void epilogue_generic(const cpx (&v1)[16], const cpx (&v2)[16], cpx wt,
 __global__ void __launch_bounds__(s2::THREADS, 3)
 stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
                   const unsigned int *__restrict__ frame_prefix, int n_songs, unsigned int total_items,
-                  int frames_per_item, const float *__restrict__ hann /* + s2::PHASE_OFF: [4][128][8] */,
+                  int frames_per_item, int items_per_cta, const float *__restrict__ hann /* + s2::PHASE_OFF: [4][128][8] */,
                   const cpx *__restrict__ tw1 /*[16][256] W4096^(b k1)*/, const cpx *__restrict__ tw2g /*[16][16] W256^(j k2)*/,
                   const cpx *__restrict__ tw8192, float *__restrict__ mags, double *__restrict__ cand_mag,
                   double *__restrict__ cand_pitch, unsigned int *__restrict__ cand_count) {
@@ -251,8 +251,8 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
     // ---- thread 0: first frame of this CTA, its copy ---------------------------------------------------------
     if (u == 0) {
         s2::mbar_init(bar, 1);
-        cur.item = blockIdx.x * (unsigned)s2::ITEMS_PER_CTA;
-        cur.item_end = min(cur.item + (unsigned)s2::ITEMS_PER_CTA, total_items);
+        cur.item = blockIdx.x * (unsigned)items_per_cta;
+        cur.item_end = min(cur.item + (unsigned)items_per_cta, total_items);
         cur.song_item0 = cur.song_item1 = 0u;
         s_fd[0].valid = 0;
         s_fd[1].valid = 0;

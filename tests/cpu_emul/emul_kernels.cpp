@@ -238,7 +238,7 @@ int main(int argc, char **argv) {
             std::vector<double> cm((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.), cp((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.);
             std::vector<unsigned> cc(1, 0u);
             emu::launch((ctas + s2::ITEMS_PER_CTA - 1) / s2::ITEMS_PER_CTA, s2::THREADS, [&] {
-                stft8192v2_kernel(x.data(), songs.data(), fp.data(), 1, ctas, K3_FRAMES_PER_CTA, hann.data(), tw4.data(), tw2.data(),
+                stft8192v2_kernel(x.data(), songs.data(), fp.data(), 1, ctas, K3_FRAMES_PER_CTA, s2::ITEMS_PER_CTA, hann.data(), tw4.data(), tw2.data(),
                                   tw8.data(), mags.data(), cm.data(), cp.data(), cc.data());
             }, s2::SMEM_BYTES);
             std::vector<float> dense((size_t)sd.n_c_comp * CH_BINS);
@@ -258,7 +258,7 @@ int main(int argc, char **argv) {
             std::vector<double> cm((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.), cp((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.);
             std::vector<unsigned> cc(1, 0u);
             emu::launch((ctas + s3::ITEMS_PER_CTA - 1) / s3::ITEMS_PER_CTA, s3::THREADS, [&] {
-                stft8192v3_kernel(x.data(), songs.data(), fp.data(), 1, ctas, K3_FRAMES_PER_CTA, hann.data(), tw4.data(), tw2.data(),
+                stft8192v3_kernel(x.data(), songs.data(), fp.data(), 1, ctas, K3_FRAMES_PER_CTA, s3::ITEMS_PER_CTA, hann.data(), tw4.data(), tw2.data(),
                                   tw8.data(), mags.data(), cm.data(), cp.data(), cc.data());
             }, s3::SMEM_BYTES);
             std::vector<float> dense((size_t)sd.n_c_comp * CH_BINS);
