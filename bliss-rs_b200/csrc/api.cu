@@ -37,7 +37,7 @@ int launch_beattrack(const float *, const float *, const SongDesc *, int, float 
                      cudaStream_t);
 int launch_chroma_filter_table(double *, float *, cudaStream_t);
 int launch_stft8192(const float *, const SongDesc *, const unsigned int *, int, unsigned int, const float *,
-                    const cpx *, const cpx *, const cpx *, const cpx *, float *, double *, double *, unsigned int *, int,
+                    const cpx *, const cpx *, const cpx *, float *, double *, double *, unsigned int *, int,
                     cudaStream_t);
 int launch_tuning(const double *, const double *, const unsigned int *, const SongDesc *, int, int *, int,
                   cudaStream_t);
@@ -156,7 +156,7 @@ struct Ctx {
     int launch_order = 0;  // BLISS_B200_ORDER: which chain of a wave is enqueued first (run_wave)
     unsigned int metric_ones = 0;  // bit i: diagonal weight i of the metric last prepared is exactly 1 (prepare_metric)
     // constant tables
-    DevBuf t_win512, t_twA, t_hann8k, t_tw4k, t_tw2, t_tw8k, t_tw64, t_filt, t_filt32;
+    DevBuf t_win512, t_twA, t_hann8k, t_tw4k, t_tw2, t_tw8k, t_filt, t_filt32;
     WaveSet ws[N_SETS];
     int next_set = 0;
     // host-API staging
@@ -391,7 +391,7 @@ int run_wave(const float *d_pcm, const WavePlan &w, int version, float *d_out, u
     auto k_stft = [&]() -> int {
         ProfScope p(K_STFT8K, sb);
         const int nl = launch_stft8192(d_pcm, dv.sd, dv.pair_prefix, n, w.pair_prefix[n], g.t_hann8k.as<float>(),
-                                       g.t_tw4k.as<cpx>(), g.t_tw2.as<cpx>(), g.t_tw8k.as<cpx>(), g.t_tw64.as<cpx>(), S.mags.as<float>(), S.cand_mag.as<double>(),
+                                       g.t_tw4k.as<cpx>(), g.t_tw2.as<cpx>(), g.t_tw8k.as<cpx>(), S.mags.as<float>(), S.cand_mag.as<double>(),
                                        S.cand_pitch.as<double>(), S.cand_count.as<unsigned int>(), g.variant, sb);
         p.done(nl);
         if (nl < 0) {
@@ -636,15 +636,6 @@ int build_tables() {
         const double a = -2.0 * M_PI * (double)m / 8192.0;
         tw[m] = cpx{(float)cos(a), (float)sin(a)};
     }
-    // radix-64 cut of the same transform (rfft8192_r64.cuh): [k1][b] = W4096^(b k1), b, k1 < 64
-    std::vector<cpx> tw64(4096);
-    for (int k1 = 0; k1 < 64; k1++)
-        for (int b = 0; b < 64; b++) {
-            const double a = -2.0 * M_PI * (double)(b * k1) / 4096.0;
-            tw64[k1 * 64 + b] = cpx{(float)cos(a), (float)sin(a)};
-        }
-    CK(g.t_tw64.ensure(tw64.size() * sizeof(cpx)));
-    CK(cudaMemcpy(g.t_tw64.p, tw64.data(), tw64.size() * sizeof(cpx), cudaMemcpyHostToDevice));
     CK(g.t_win512.ensure(win.size() * 4));
     CK(g.t_twA.ensure(twA.size() * sizeof(cpx)));
     CK(g.t_hann8k.ensure(hann.size() * 4));
@@ -826,7 +817,7 @@ static void shutdown_ctx() {  // the calling thread's current context
     if (!g.inited) return;
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
-    DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw4k, &g.t_tw2, &g.t_tw8k, &g.t_tw64, &g.t_filt, &g.t_filt32,
+    DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw4k, &g.t_tw2, &g.t_tw8k, &g.t_filt, &g.t_filt32,
                      &g.pcm[0], &g.pcm[1], &g.pcm[2], &g.pcm[3], &g.raw16[0], &g.raw16[1], &g.raw16[2], &g.raw16[3], &g.feats, &g.metric, &g.misc[0], &g.misc[1],
                      &g.misc[2], &g.misc[3], &g.misc[4], &g.misc[5]};
     for (DevBuf *b : all) b->release();

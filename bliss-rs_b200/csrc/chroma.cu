@@ -10,7 +10,6 @@
 
 #include "common.cuh"
 #include "rfft8192.cuh"
-#include "rfft8192_r64.cuh"
 #include "stft8192_v2.cuh"
 #include "stft8192_v3.cuh"
 
@@ -372,211 +371,6 @@ stft8192_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ song
     }
     __syncthreads();  // the magnitudes in `buf` were read by pip_track; the next frame overwrites them
     }  // frames of this CTA
-}
-
-// ---------------------------------------------------------------------------
-// K3 as 4096 = 64 x 64 (rfft8192_r64.cuh): one CTA of 64 threads per frame, two in-register radix-64
-// passes, 33 KB of shared memory, <= 200 registers => 5 CTAs per SM.  Same outputs as stft8192_kernel
-// (magnitude spill rows, pip_track candidates; the candidates of a frame come out in another order,
-// which nothing downstream depends on).
-// ---------------------------------------------------------------------------
-constexpr int K3R_THREADS = 64;
-
-template <int K2>
-__device__ __forceinline__ void r64_epilogue_pairs(const cpx (&u)[64], const cpx *pm, bool t0, cpx wt, float *gm_lo,
-                                                   float *gm_hi, float (&own)[24], float &mx) {
-    if constexpr (K2 < 32) {
-        cpx zm = pm[r64::P * (31 - K2)];
-        if (K2 == 0 && t0) zm = u[0];  // bin 0 pairs with bin 4096 = Z[0] itself
-        float a, b;
-        r8k::untangle_mag_pair(u[bitrev(K2, 6)], zm, mul_tw256<2 * K2>(wt), a, b);  // W8192^(k1 + 64 k2) = W8192^k1 W128^k2
-        gm_lo[64 * K2] = a;
-        gm_hi[-64 * K2] = b;
-        mx = fmaxf(mx, fmaxf(a, b));
-        if constexpr (K2 < 24) own[K2] = a;  // bins < 1536: what pip_track looks at
-        r64_epilogue_pairs<K2 + 1>(u, pm, t0, wt, gm_lo, gm_hi, own, mx);
-    }
-}
-
-template <int Q>
-__device__ __forceinline__ void window_synth64(cpx (&v)[64], cpx cw, cpx sw) {
-    if constexpr (Q < 64) {
-        v[Q] = pmul(v[Q], r8k::hann_pair64<Q>(cw, sw));
-        window_synth64<Q + 1>(v, cw, sw);
-    }
-}
-
-// VAR: K3V_WINSYN / K3V_ODDSHIFT as in stft8192_kernel (experimental; 0 = the measured radix-64 kernel).  The kernel
-// stalled on the 128 sample + 64 window loads at the head of each frame: with both cuts a thread issues 64 aligned
-// 64-bit sample loads and one 16-byte phase load instead.
-template <int VAR = 0>
-__global__ void __launch_bounds__(K3R_THREADS, 5)
-stft8192_r64_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
-                    const unsigned int *__restrict__ frame_prefix, int n_songs,
-                    const float *__restrict__ hann, const cpx *__restrict__ tw64 /*[64][64] W4096^(b k1)*/,
-                    const cpx *__restrict__ tw8192, float *__restrict__ mags,
-                    double *__restrict__ cand_mag, double *__restrict__ cand_pitch,
-                    unsigned int *__restrict__ cand_count) {
-    __shared__ __align__(16) cpx buf[r64::BUF_CPX];
-    __shared__ cpx s_twf[16 * 64];  // the thread's pass-1 twiddle factors (rfft8192_r64.cuh)
-    __shared__ float s_red[K3R_THREADS / 32];
-    __shared__ unsigned int s_scan[K3R_THREADS / 32];
-    __shared__ unsigned int s_base;
-
-    const int tid = threadIdx.x;
-    const unsigned int item = blockIdx.x;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {  // A[a] = W4096^(8 a b) = tw64[8a][b],  C[c] = W4096^(c b) = tw64[c][b]
-        s_twf[64 * i + tid] = tw64[64 * (8 * i) + tid];
-        s_twf[64 * (8 + i) + tid] = tw64[64 * i + tid];
-    }
-    const int si = find_song(frame_prefix, n_songs, item);
-    const SongDesc sd = songs[si];
-    const int fbase = (int)(item - frame_prefix[si]) * K3_FRAMES_PER_CTA;
-    const float *x = pcm + sd.pcm_off;
-    const int n = (int)sd.n;
-    const unsigned int mag_row0 = (unsigned int)sd.mag_off;
-    const int fend = min(fbase + K3_FRAMES_PER_CTA, (int)sd.n_c_comp);
-    // (each thread reads back only the column it wrote: no barrier needed for s_twf)
-#pragma unroll 1
-    for (int f = fbase; f < fend; f++) {
-        const int s0 = CH_HOP * f - 4096;  // the frame covers samples s0 .. s0+8191 of the reflect-padded song
-        const bool interior = (s0 >= 0) && (s0 + 8191 < n);
-        {   // pass 1: z[nn] = w[2nn] x[2nn] + i w[2nn+1] x[2nn+1], nn = tid + 64 q
-            cpx v[64];
-            const float2 *ph = reinterpret_cast<const float2 *>(hann) + tid;
-            if constexpr ((VAR & K3V_WINSYN) != 0) {
-                float4 pw = __ldg(reinterpret_cast<const float4 *>(hann + K3_HANN_PHASE) + tid);
-                if (interior) {
-                    const float *pa = x + s0 + 2 * tid;
-                    const bool aligned = (reinterpret_cast<size_t>(pa) & 7) == 0;
-                    if (aligned || (VAR & K3V_ODDSHIFT) != 0) {
-                        // odd-start frames are transformed rotated by one sample (see K3V_ODDSHIFT): aligned pairs
-                        const float2 *pa2 = reinterpret_cast<const float2 *>(aligned ? pa : pa - 1);
-                        if (!aligned) pw = __ldg(reinterpret_cast<const float4 *>(hann + K3_HANN_SHIFT_PHASE) + tid);
-#pragma unroll
-                        for (int q = 0; q < 64; q++) {
-                            const float2 xx = __ldg(pa2 + 64 * q);
-                            v[q] = cpx{xx.x, xx.y};
-                        }
-                        if (!aligned && tid == 0) v[0].x = __ldg(x + s0 + 8191);  // y'[0] = y[8191]
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 64; q++) v[q] = cpx{__ldg(pa + 128 * q), __ldg(pa + 128 * q + 1)};
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 64; q++) {
-                        const long long i0 = (long long)s0 + 2 * (tid + 64 * q);
-                        v[q] = cpx{r8k::reflect_sample(x, n, i0), r8k::reflect_sample(x, n, i0 + 1)};
-                    }
-                }
-                window_synth64<0>(v, cpx{pw.x, pw.y}, cpx{pw.z, pw.w});
-            } else if (interior) {
-                const float *pa = x + s0 + 2 * tid;
-                if ((reinterpret_cast<size_t>(pa) & 7) == 0) {
-                    const float2 *pa2 = reinterpret_cast<const float2 *>(pa);
-#pragma unroll
-                    for (int q = 0; q < 64; q++) {
-                        const float2 w = __ldg(ph + 64 * q);
-                        const float2 xx = __ldg(pa2 + 64 * q);
-                        v[q] = pmul(cpx{xx.x, xx.y}, cpx{w.x, w.y});
-                    }
-                } else if constexpr ((VAR & K3V_ODDSHIFT) != 0) {
-                    const float2 *pa2 = reinterpret_cast<const float2 *>(pa - 1);
-                    const float2 *phs = reinterpret_cast<const float2 *>(hann + K3_HANN_SHIFT) + tid;
-#pragma unroll
-                    for (int q = 0; q < 64; q++) {
-                        const float2 w = __ldg(phs + 64 * q);
-                        float2 xx = __ldg(pa2 + 64 * q);
-                        if (q == 0 && tid == 0) xx.x = __ldg(x + s0 + 8191);  // y'[0] = y[8191]
-                        v[q] = pmul(cpx{xx.x, xx.y}, cpx{w.x, w.y});
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 64; q++) {
-                        const float2 w = __ldg(ph + 64 * q);
-                        v[q] = pmul(cpx{__ldg(pa + 128 * q), __ldg(pa + 128 * q + 1)}, cpx{w.x, w.y});
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 64; q++) {
-                    const float2 w = __ldg(ph + 64 * q);
-                    const long long i0 = (long long)s0 + 2 * (tid + 64 * q);
-                    v[q] = pmul(cpx{r8k::reflect_sample(x, n, i0), r8k::reflect_sample(x, n, i0 + 1)}, cpx{w.x, w.y});
-                }
-            }
-            r64::pass1_store_factored(tid, v, s_twf, buf);
-        }
-        __syncthreads();
-        float own[24], mx = 0.f;  // own[k2] = |X[tid + 64 k2]|
-        float *gm = mags + (size_t)(mag_row0 + (unsigned int)f) * CH_STRIDE;
-        {
-            cpx u[64];
-            r64::pass2_regs(tid, u, buf);
-            __syncthreads();  // every row has been read: the mirror halves may overwrite the buffer
-            r64::publish_upper(tid, u, buf);
-            __syncthreads();
-            const cpx wt = tw8192[tid];
-            const cpx *pm = buf + r64::mirror_base(tid);
-            r64_epilogue_pairs<0>(u, pm, tid == 0, wt, gm + tid, gm + 4096 - tid, own, mx);
-            if (tid == 0) {  // the self-mirrored bin 2048: W8192^2048 = -i
-                const float mid = r8k::untangle_mag(u[bitrev(32, 6)], u[bitrev(32, 6)], cpx{0.f, -1.f});
-                gm[2048] = mid;
-                mx = fmaxf(mx, mid);
-            }
-        }
-        __syncthreads();  // mirror values read; reuse buf for the magnitudes pip_track looks at
-        float *sm = reinterpret_cast<float *>(buf);
-#pragma unroll
-        for (int k2 = 0; k2 < 24; k2++) sm[tid + 64 * k2] = own[k2];
-        // frame maximum (pip_track's ref_value = 0.1 * max over all bins, chroma.rs:289-293)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if ((tid & 31) == 0) s_red[tid >> 5] = mx;
-        __syncthreads();
-        const float fmx = fmaxf(s_red[0], s_red[1]);
-
-        // pip_track on centre bins 57..1483: the thread tests its OWN bins k = tid + 64 k2 (chroma.rs:295-331)
-        const double ref = 0.1 * (double)fmx;
-        unsigned int flags = 0;
-#pragma unroll
-        for (int k2 = 0; k2 < 24; k2++) {
-            const int c = tid + 64 * k2;
-            if (c >= 57 && c <= 1483) {
-                const float before = sm[c - 1], elem = own[k2], after = sm[c + 1];
-                if (after <= elem && before < elem && (double)elem > ref) flags |= 1u << k2;
-            }
-        }
-        const int cnt = __popc(flags);
-        unsigned int incl = (unsigned)cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((tid & 31) >= o) incl += t;
-        }
-        if ((tid & 31) == 31) s_scan[tid >> 5] = incl;
-        __syncthreads();
-        const unsigned int woff = (tid >> 5) ? s_scan[0] : 0u, tot = s_scan[0] + s_scan[1];
-        if (tid == 0 && tot) s_base = atomicAdd(cand_count + si, tot);
-        __syncthreads();
-        unsigned long long dst = sd.cand_off + s_base + woff + (incl - (unsigned)cnt);
-        while (flags) {
-            const int k2 = __ffs(flags) - 1;
-            flags &= flags - 1;
-            const int c = tid + 64 * k2;
-            const double before = (double)sm[c - 1], elem = (double)sm[c], after = (double)sm[c + 1];
-            const double avg = 0.5 * (after - before);
-            double shift = 2. * elem - after - before;
-            if (fabs(shift) < 2.2250738585072014e-308) shift += 1.;
-            shift = avg / shift;
-            cand_pitch[dst] = ((double)c + shift) * (double)SAMPLE_RATE / 8192.0;
-            cand_mag[dst] = elem + 0.5 * avg * shift;
-            dst++;
-        }
-        __syncthreads();  // the magnitudes in `buf` were read by pip_track; the next frame overwrites them
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1250,10 +1044,10 @@ constexpr size_t K5P_SMEM = (size_t)K5P_STAGES * CH_TILE_FRAMES * K5P_PITCH * 4 
 // frame_prefix counts groups of K3_FRAMES_PER_CTA (= 4) frames per song
 int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int *frame_prefix, int n_songs,
                     unsigned int total_frames, const float *hann, const cpx *tw1, const cpx *tw2,
-                    const cpx *tw8192, const cpx *tw64, float *mags, double *cand_mag, double *cand_pitch,
+                    const cpx *tw8192, float *mags, double *cand_mag, double *cand_pitch,
                     unsigned int *cand_count, int variant, cudaStream_t st) {
     if (total_frames == 0) return 0;
-    if ((variant & (VARIANT_STFT_V1 | VARIANT_R64 | VARIANT_OLD_EPILOGUE)) == 0) {  // the round-2 kernels
+    if ((variant & (VARIANT_STFT_V1 | VARIANT_OLD_EPILOGUE)) == 0) {  // the round-2 kernels
         // > 48 KB of dynamic shared memory is an opt-in, per device: set on every launch
         // work items (of four frames) per CTA: as many as still leave ~4 CTAs per resident slot (148 SMs x 3), at most 16
         // (16 against 4 on 1024 tracks: 21.50 against 21.77 ms, profiles/knobs_r02.md); BLISS_B200_STFT_ITEMS overrides
@@ -1278,18 +1072,7 @@ int launch_stft8192(const float *pcm, const SongDesc *songs, const unsigned int 
         }
         return 1;
     }
-    if (variant & VARIANT_R64) {
-        auto go64 = [&](auto kern) {
-            BLISS_LAUNCH(kern, total_frames, K3R_THREADS, 0, st, pcm, songs, frame_prefix, n_songs, hann, tw64, tw8192, mags,
-                         cand_mag, cand_pitch, cand_count);
-        };
-        const bool ws = (variant & VARIANT_WINSYN) != 0, os = (variant & VARIANT_ODDSHIFT) != 0;
-        if (ws && os) go64(stft8192_r64_kernel<K3V_WINSYN | K3V_ODDSHIFT>);
-        else if (ws) go64(stft8192_r64_kernel<K3V_WINSYN>);
-        else if (os) go64(stft8192_r64_kernel<K3V_ODDSHIFT>);
-        else go64(stft8192_r64_kernel<0>);
-    }
-    else if (variant & VARIANT_OLD_EPILOGUE)
+    if (variant & VARIANT_OLD_EPILOGUE)
         BLISS_LAUNCH(stft8192_kernel<false>, total_frames, K3_THREADS, 0, st, pcm, songs, frame_prefix, n_songs, hann, tw1, tw2,
                                                                     tw8192, mags, cand_mag, cand_pitch, cand_count);
     else {

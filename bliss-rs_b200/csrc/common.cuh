@@ -70,7 +70,8 @@ enum {
     VARIANT_OLD_CHROMA = 4,    // chroma_kernel: thread-per-frame tiles staged through shared memory
     VARIANT_OLD_ACF = 8,       // beattrack_kernel: one autocorrelation lag at a time, scalar loads
     VARIANT_BT512 = 16,        // beattrack_kernel: 512 threads per song (3 songs per SM) instead of 128 (8 per SM)
-    VARIANT_R64 = 32,          // stft8192: 4096 = 64 x 64, two radix-64 passes by 64 threads per frame (experimental)
+    // (bit 32 was the radix-64 x radix-64 cut of the chroma STFT: measured slower twice -- 28.5 against 28.1 ms in round 1,
+    // 26.5 against 24.3 ms with its load cuts in round 2, profiles/ab_r02.md -- and removed)
     VARIANT_TWPROD = 64,       // stft8192: pass-1 twiddles from 4 loads + 11 products instead of 15 loads (experimental)
     VARIANT_STFT_PAIRS = 256,  // STFT micro-benchmark: hop-256 frames j, j+1 share one FFT, 128-byte magnitude stores (experimental)
     VARIANT_PV_TWPROD = 512,   // pvoc512: phase-A twiddles from 4 per-lane registers + 11 products instead of 15 smem loads per pair (experimental)

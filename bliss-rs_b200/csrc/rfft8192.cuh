@@ -89,13 +89,6 @@ BLISS_HD cpx hann_pair(cpx cw, cpx sw) {
     return pfma(cw, cpx{a, a}, pfma(sw, cpx{b, b}, cpx{0.5f, 0.5f}));
 }
 
-// the same for the radix-64 cut (rfft8192_r64.cuh): n = 2 (tid + 64 Q), the step between a thread's pairs is 2 pi / 64
-template <int Q>
-BLISS_HD cpx hann_pair64(cpx cw, cpx sw) {
-    constexpr float a = -0.5f * cos256(4 * Q), b = 0.5f * sin256(4 * Q);
-    return pfma(cw, cpx{a, a}, pfma(sw, cpx{b, b}, cpx{0.5f, 0.5f}));
-}
-
 // pass 2: butterfly b in [0,256): blk = b>>4 (k1), j = b&15; radix 16 at stride 16 inside the
 // 256-block;  pad(256 blk + j + 16 q) = 273 blk + j + 17 q;  twiddle tw2[k2][j] = W256^(j k2)
 // (a 2 KB table the kernel keeps in shared memory)

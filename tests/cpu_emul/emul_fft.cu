@@ -8,7 +8,6 @@
 #include <vector>
 
 #include "../../bliss-rs_b200/csrc/rfft8192.cuh"
-#include "../../bliss-rs_b200/csrc/rfft8192_r64.cuh"
 #include "../../bliss-rs_b200/csrc/pvoc512.cuh"
 
 using namespace bliss;
@@ -258,86 +257,6 @@ int main() {
             if (!(err16 == err16)) { printf("LAY16 epilogue read an unpublished slot\n"); return 17; }
             printf("rfft8192 without the per-16 padding (LAY16): max rel err %.3e, mirror values identical\n", err16);
             worst = fmax(worst, err16);
-        }
-        // ---- 4096 = 64 x 64: two radix-64 passes, 64 "threads" (rfft8192_r64.cuh) ----
-        {
-            std::vector<cpx> tw64(4096);
-            for (int k1 = 0; k1 < 64; k1++)
-                for (int b = 0; b < 64; b++) {
-                    const double ang = -2.0 * M_PI * (double)(b * k1) / 4096.0;
-                    tw64[64 * k1 + b] = cpx{(float)cos(ang), (float)sin(ang)};
-                }
-            std::vector<cpx> buf3(r64::BUF_CPX);
-            for (int b = 0; b < 64; b++) {
-                cpx v[64];
-                for (int q = 0; q < 64; q++) {
-                    const int nn = b + 64 * q;
-                    v[q] = cpx{(float)a[2 * nn], (float)a[2 * nn + 1]};
-                }
-                r64::pass1_store(b, v, tw64.data(), buf3.data());
-            }
-            {   // the factored-twiddle form of pass 1 must store (nearly) the same values
-                std::vector<cpx> twf(16 * 64), buf4(r64::BUF_CPX);
-                for (int i = 0; i < 8; i++)
-                    for (int b = 0; b < 64; b++) {
-                        twf[64 * i + b] = tw64[64 * (8 * i) + b];
-                        twf[64 * (8 + i) + b] = tw64[64 * i + b];
-                    }
-                for (int b = 0; b < 64; b++) {
-                    cpx v[64];
-                    for (int q = 0; q < 64; q++) {
-                        const int nn = b + 64 * q;
-                        v[q] = cpx{(float)a[2 * nn], (float)a[2 * nn + 1]};
-                    }
-                    r64::pass1_store_factored(b, v, twf.data(), buf4.data());
-                }
-                double dmax = 0, vmax = 0;
-                for (int k1 = 0; k1 < 64; k1++)
-                    for (int b = 0; b < 64; b++) {
-                        const cpx p = buf3[r64::P * k1 + b], q = buf4[r64::P * k1 + b];
-                        dmax = fmax(dmax, fmax(fabs(p.x - q.x), fabs(p.y - q.y)));
-                        vmax = fmax(vmax, fmax(fabs(p.x), fabs(p.y)));
-                    }
-                printf("r64 factored pass-1 twiddles: max diff %.3e of %.3e\n", dmax, vmax);
-                if (dmax > 2e-6 * vmax) { printf("factored twiddles disagree\n"); return 8; }
-                buf3 = buf4;  // continue with the form the kernel uses
-            }
-            static cpx regs64[64][64];
-            for (int k1 = 0; k1 < 64; k1++) r64::pass2_regs(k1, regs64[k1], buf3.data());
-            for (auto &e : buf3) e = cpx{NAN, NAN};  // only what publish_upper writes may be read afterwards
-            for (int t = 0; t < 64; t++) r64::publish_upper(t, regs64[t], buf3.data());
-            std::vector<int> hit(4097, 0);
-            double err3 = 0;
-            for (int k1 = 0; k1 < 64; k1++) {
-                const cpx *pm = buf3.data() + r64::mirror_base(k1);
-                for (int k2 = 0; k2 < 32; k2++) {
-                    const int k = k1 + 64 * k2;
-                    const cpx zk = regs64[k1][bitrev(k2, 6)];
-                    const cpx zm = (k1 == 0 && k2 == 0) ? regs64[0][0] : pm[r64::P * (31 - k2)];
-                    const cpx chk = r8k::z_value(buf.data(), (4096 - k) & 4095);  // radix-16 result as the reference
-                    if (fabs(zm.x - chk.x) > 2e-3f || fabs(zm.y - chk.y) > 2e-3f || !(zm.x == zm.x)) {
-                        printf("r64 mirror addressing mismatch k=%d (%g %g) vs (%g %g)\n", k, zm.x, zm.y, chk.x, chk.y);
-                        return 6;
-                    }
-                    const cpx w = cmul(tw8[k1], cpx{(float)cos(-2.0 * M_PI * k2 / 128.0), (float)sin(-2.0 * M_PI * k2 / 128.0)});
-                    float mk, mm;
-                    r8k::untangle_mag_pair(zk, zm, w, mk, mm);
-                    hit[k]++;
-                    hit[4096 - k]++;
-                    err3 = fmax(err3, fabs(mk - ma[k]) / scale);
-                    err3 = fmax(err3, fabs(mm - ma[4096 - k]) / scale);
-                }
-            }
-            {
-                const cpx z = regs64[0][bitrev(32, 6)];  // bin 2048 mirrors onto itself
-                const float mg = r8k::untangle_mag(z, z, cpx{0.f, -1.f});
-                hit[2048]++;
-                err3 = fmax(err3, fabs(mg - ma[2048]) / scale);
-            }
-            for (int k = 0; k <= 4096; k++)
-                if (hit[k] != 1) { printf("r64 epilogue: bin %d produced %d times\n", k, hit[k]); return 7; }
-            printf("rfft8192 as 64 x 64 (two radix-64 passes): max rel err %.3e\n", err3);
-            worst = fmax(worst, err3);
         }
         // ---- VARIANT_TWPROD: pass-1 twiddles from 4 loads + 11 products store (nearly) what 15 loads store ----
         {

@@ -281,34 +281,6 @@ int main(int argc, char **argv) {
         run_stft("v8192", stft8192_kernel<true, K3V_ODDSHIFT>);
         run_stft("v12480", stft8192_kernel<true, K3V_TWPROD | K3V_WINSYN | K3V_LAY16 | K3V_ODDSHIFT>);
         run_stft("old_epilogue", stft8192_kernel<false>);
-        // the radix-64 cut of the same transform (64 threads per frame) and its experimental load cuts
-        std::vector<cpx> tw64(4096);
-        for (int k1 = 0; k1 < 64; k1++)
-            for (int b = 0; b < 64; b++) {
-                const double a = -2.0 * M_PI * (double)(b * k1) / 4096.0;
-                tw64[k1 * 64 + b] = cpx{(float)cos(a), (float)sin(a)};
-            }
-        auto run_r64 = [&](const char *tag, auto kern) {
-            std::vector<float> mags((size_t)sd.n_c_comp * CH_STRIDE, -7.f);
-            std::vector<double> cm((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.), cp((size_t)sd.n_c_comp * CH_MAX_PEAKS, 0.);
-            std::vector<unsigned> cc(1, 0u);
-            emu::launch(ctas, K3R_THREADS, [&] {
-                kern(x.data(), songs.data(), fp.data(), 1, hann.data(), tw64.data(), tw8.data(), mags.data(), cm.data(), cp.data(),
-                     cc.data());
-            });
-            std::vector<float> dense((size_t)sd.n_c_comp * CH_BINS);
-            for (unsigned f = 0; f < sd.n_c_comp; f++)
-                memcpy(&dense[(size_t)f * CH_BINS], &mags[(size_t)f * CH_STRIDE], CH_BINS * 4);
-            dump((std::string("stft8192_") + tag).c_str(), dense);
-            dump((std::string("peaks_") + tag).c_str(), cc);
-            cp.resize(cc[0]);
-            std::sort(cp.begin(), cp.end());
-            dump((std::string("peak_pitches_") + tag).c_str(), cp);
-        };
-        run_r64("r64", stft8192_r64_kernel<0>);
-        run_r64("r64_v128", stft8192_r64_kernel<K3V_WINSYN>);
-        run_r64("r64_v8192", stft8192_r64_kernel<K3V_ODDSHIFT>);
-        run_r64("r64_v8320", stft8192_r64_kernel<K3V_WINSYN | K3V_ODDSHIFT>);
     }
     // ---- the whole path, kernel after kernel as run_wave (api.cu) enqueues them: 23 features ------------------
     {
