@@ -56,8 +56,17 @@ inline std::vector<float> feature_weights(FeaturesVersion v) {  // src/lib.rs:16
 }
 
 namespace detail {
-inline void ensure_init(int device = 0) {
-    static const int rc = bliss_b200_init(device);
+// BLISS_B200_DEVICE=<n> pins the process to one GPU; otherwise every visible B200 is opened and the host-buffer calls
+// (analyze_batch, the decoder pipeline) shard one call's songs over all of them inside the library
+// (bliss_b200_init_devices): the crate is one process, src/song/decoder.rs:282-331.
+inline void ensure_init(int device = -1) {
+    static const int rc = [device] {
+        int dev = device;
+        if (const char *e = std::getenv("BLISS_B200_DEVICE")) dev = std::atoi(e);
+        if (dev >= 0) return bliss_b200_init(dev);
+        const int n = bliss_b200_init_devices(0);
+        return n > 0 ? BLISS_B200_OK : n;
+    }();
     if (rc != BLISS_B200_OK)
         throw BlissError(BlissError::AnalysisError, std::string("b200 backend unavailable (no CPU fallback): ") +
                                                         bliss_b200_strerror(rc) + ": " + bliss_b200_last_error());

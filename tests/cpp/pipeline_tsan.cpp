@@ -17,6 +17,7 @@ static std::atomic<bool> g_fail_calls{false};
 
 extern "C" {
 int bliss_b200_init(int) { return BLISS_B200_OK; }
+int bliss_b200_init_devices(int) { return 1; }
 const char *bliss_b200_strerror(int) { return "stub"; }
 const char *bliss_b200_last_error(void) { return "stub failure"; }
 int bliss_b200_analyze_batch_pcm(const void *const *, const uint64_t *, uint32_t, int, uint32_t, uint32_t, uint16_t, float *, int32_t *) {
