@@ -523,7 +523,7 @@ def main():
                               "algorithmic_gb_per_launch": alg.get(dom["kernel"], 0) * S / 1e9,
                               "source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum)"}
             # what the same ncu capture says the kernel is actually bound by (percent of peak)
-            for k in ("l1tex_data_pipe_pct", "issue_active_pct", "dram_pct", "lts_pct"):
+            for k in ("l1tex_data_pipe_pct", "issue_active_pct", "fma_pipe_pct", "dram_pct", "lts_pct"):
                 if k in ent:
                     traffic_detail[k] = ent[k]
         except Exception:
@@ -537,8 +537,9 @@ def main():
                 "step_read_note": "BASELINE.md section 3: songs x 4N bytes / step time / HBM peak (per GPU); the FFT kernels "
                                   "are FP32-pipe bound, so this sits far below 1 by construction",
                 "avg_launch_ms": dom["avg_ms"], "share_of_step": dom["share"],
-                "note": "FFT work: the kernel is FP32-pipe / shared-memory bound at algorithmic-minimum traffic "
-                        "(DESIGN.md); the HBM roofline is reported because BASELINE.json fixes it",
+                "note": "FFT work: at algorithmic-minimum traffic the kernel sits on the SM (FP32 pipe ~55 %, L1 / shared-memory "
+                        "data pipe ~47 %, issue ~44 % in the ncu capture: no pipe saturated, latency between barriers; "
+                        "DESIGN.md section 4); the HBM roofline is reported because BASELINE.json fixes it",
                 "kernels": kernels}
 
     # ---- e2e: the C-ABI call with pinned HOST buffers (H2D + D2H inside the timed region) --

@@ -221,7 +221,7 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
         for (int e = tid; e < winlen; e += BT) sh.dfrev[winlen - 1 - e] = sh.df[e] * sh.dfwv[e];
         // vec_autocorr, aubio.rs:819-828:  acf[i] = sum_{j < 512-i} df[j] df[j+i] / (512 - i), each lag's sum in
         // the reference's order (j ascending, un-fused multiply and add).
-        if (scalar_acf) {  // VARIANT_OLD_ACF: one lag at a time, two scalar loads per multiply-add
+        if (scalar_acf == 1) {  // VARIANT_OLD_ACF: one lag at a time, two scalar loads per multiply-add
             for (int lag = tid; lag < winlen; lag += BT) {
                 float tmp = 0.f;
                 const float *a = sh.df, *b = sh.df + lag;
@@ -236,6 +236,48 @@ beattrack_kernel(const float *__restrict__ thr, const float *__restrict__ block_
                 }
                 for (; j < cnt; j++) tmp += a[j] * b[j];
                 sh.acf[lag] = tmp / (float)cnt;
+            }
+        } else if (scalar_acf == 0) {
+            // Balanced cut (round 2).  With four consecutive lags per thread the work per thread falls linearly with
+            // the lag (128 .. 1 blocks): warp 0 of EVERY resident CTA carries 40 % of its song's multiply-adds, and warp w
+            // of every CTA lives on sub-partition w -- one of the SM's four schedulers did 4 x the work of another
+            // (the kernel's 3.0 ms were that scheduler's queue).  Here thread t owns the lag pair (2t, 2t + 1) AND its
+            // mirror pair (510 - 2t, 511 - 2t): 1026 multiply-adds for every thread, all four warps alike.  Each lag's
+            // sum keeps the reference's order (j ascending, un-fused multiply and add): bit-identical results.
+            for (int t = tid; t < 128; t += BT) {
+                const float4 *df4 = reinterpret_cast<const float4 *>(sh.df);
+                const float2 *df2 = reinterpret_cast<const float2 *>(sh.df);
+#pragma unroll 1
+                for (int half = 0; half < 2; half++) {
+                    const int i0 = half == 0 ? 2 * t : 510 - 2 * t;  // even: lags i0, i0 + 1
+                    float acc0 = 0.f, acc1 = 0.f;
+                    // blocks of four j with every term of both lags inside the frame: 4 jq + 3 + (i0 + 1) <= 511
+                    const int nblk = (i0 <= 507) ? (507 - i0) / 4 + 1 : 0;
+                    float2 w01 = df2[i0 / 2];                                    // df[i0 + j .. i0 + j + 3], j = 0
+                    float2 w23 = (i0 / 2 + 1 < 256) ? df2[i0 / 2 + 1] : make_float2(0.f, 0.f);
+                    for (int jq = 0; jq < nblk; jq++) {
+                        const float4 a = df4[jq];
+                        const float2 w45 = df2[i0 / 2 + 2 * jq + 2];             // df[i0 + j + 4], df[i0 + j + 5]
+                        const float2 w67 = (i0 / 2 + 2 * jq + 3 < 256) ? df2[i0 / 2 + 2 * jq + 3] : make_float2(0.f, 0.f);
+                        const float p00 = a.x * w01.x, p01 = a.x * w01.y;
+                        const float p10 = a.y * w01.y, p11 = a.y * w23.x;
+                        const float p20 = a.z * w23.x, p21 = a.z * w23.y;
+                        const float p30 = a.w * w23.y, p31 = a.w * w45.x;
+                        acc0 += p00; acc1 += p01;
+                        acc0 += p10; acc1 += p11;
+                        acc0 += p20; acc1 += p21;
+                        acc0 += p30; acc1 += p31;
+                        w01 = w45;
+                        w23 = w67;
+                    }
+                    // the last terms, in order: j = 4 nblk .. 511 - i0 (lag i0) / 510 - i0 (lag i0 + 1)
+                    for (int j = 4 * nblk; j + i0 <= 511; j++) {
+                        acc0 += sh.df[j] * sh.df[j + i0];
+                        if (j + i0 + 1 <= 511) acc1 += sh.df[j] * sh.df[j + i0 + 1];
+                    }
+                    sh.acf[i0] = acc0 / (float)(winlen - i0);
+                    sh.acf[i0 + 1] = acc1 / (float)(winlen - i0 - 1);
+                }
             }
         } else {
             // Thread t < 128 owns the four consecutive lags 4t..4t+3 and walks j in blocks of four: one
@@ -499,7 +541,8 @@ int launch_beattrack(const float *thr, const float *block_energy, const SongDesc
                      float *bpm_list, float *tempo_feature, unsigned int *bpm_count, int variant,
                      cudaStream_t st) {
     if (n_songs == 0) return 0;
-    const int scalar_acf = (variant & VARIANT_OLD_ACF) ? 1 : 0;
+    // 0 = balanced lag pairs (round 2), 1 = one lag at a time (VARIANT_OLD_ACF), 2 = four consecutive lags per thread (round 1)
+    const int scalar_acf = (variant & VARIANT_OLD_ACF) ? 1 : (variant & VARIANT_ACF_4LAGS) ? 2 : 0;
     if (variant & VARIANT_BT512)
         BLISS_LAUNCH(beattrack_kernel<512>, n_songs, 512, 0, st, thr, block_energy, songs, bpm_list, tempo_feature, bpm_count,
                                                        scalar_acf);

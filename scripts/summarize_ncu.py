@@ -57,7 +57,9 @@ def main():
         import json
         import re
         # bench.py's kernel ids (api.cu kKernelNames) for the current kernels
-        alias = {"chroma_pipe_kernel": "chroma_kernel", "tuning_select_kernel": "tuning_kernel"}
+        alias = {"chroma_pipe_kernel": "chroma_kernel", "tuning_select_kernel": "tuning_kernel",
+                 "stft8192v2_kernel": "stft8192_kernel", "stft8192v3_kernel": "stft8192_kernel",
+                 "pvoc512v2_kernel": "pvoc512_kernel", "distance_matrix_diag_kernel": "distance_kernels"}
         tr = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full (%s), one launch = %d "
                           "synthetic 3-min songs; bench.py scales bytes_per_song by the songs per launch" % (out, songs),
               "songs_per_launch": songs}
@@ -73,6 +75,7 @@ def main():
                         # issue slots, DRAM, L2
                         "l1tex_data_pipe_pct": pct("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
                         "issue_active_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                        "fma_pipe_pct": pct("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
                         "dram_pct": pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
                         "lts_pct": pct("lts__throughput.avg.pct_of_peak_sustained_elapsed")}
         json.dump(tr, open(sys.argv[4], "w"), indent=1)

@@ -304,6 +304,22 @@ int main(int argc, char **argv) {
             emu::launch(1, 128, [&] {
                 beattrack_kernel<128>(thr.data(), eb.data(), songs.data(), bpm.data(), tempo.data(), nbpm.data(), 0);
             });
+            {   // the three autocorrelation cuts of beattrack_kernel (0 balanced lag pairs, 1 one lag at a time, 2 four
+                // consecutive lags per thread) keep every lag's sum in the reference's order: the same bits
+                std::vector<float> all;
+                for (int mode = 0; mode < 3; mode++) {
+                    std::vector<float> b2(bpm.size(), 0.f), t2(1, 0.f);
+                    std::vector<unsigned> n2(1, 0u);
+                    emu::launch(1, 128, [&] {
+                        beattrack_kernel<128>(thr.data(), eb.data(), songs.data(), b2.data(), t2.data(), n2.data(), mode);
+                    });
+                    all.push_back(t2[0]);
+                    all.push_back((float)n2[0]);
+                    for (unsigned i = 0; i < n2[0] && i < 64; i++) all.push_back(b2[i]);
+                    all.push_back(-12345.f);
+                }
+                dump((std::string("acf_modes_") + tag).c_str(), all);
+            }
             // chroma chain
             const unsigned ctas = (sd.n_c_comp + K3_FRAMES_PER_CTA - 1) / K3_FRAMES_PER_CTA;
             const std::vector<unsigned> fp = {0u, ctas};

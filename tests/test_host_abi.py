@@ -431,6 +431,12 @@ def test_kernel_sources_reproduce_the_reference_golden_vector(tmp_path, golden):
         assert np.abs(f - golden["expected_analysis_v2"]).max() < 1e-5, (tag, f)
         assert np.abs(f - want).max() < 1e-5, (tag, np.abs(f - want).max())
         assert int(tuning_idx) == 45 and n_bpm > 0 and abs(tempo - want[0]) < 1e-6  # tuning -0.05 (src/chroma.rs:657-665)
+    # beattrack_kernel's three autocorrelation cuts (balanced lag pairs = the default, one lag at a time, four consecutive
+    # lags per thread) keep every lag's sum in the reference's order: tempo, count and every BPM of the list bit for bit
+    modes = np.split(a := np.fromfile(str(tmp_path / "acf_modes_default"), np.float32), np.nonzero(a == np.float32(-12345.0))[0] + 1)[:3]
+    assert len(modes) == 3 and modes[0].size > 10
+    for m in modes[1:]:
+        assert np.array_equal(m.view(np.uint32), modes[0].view(np.uint32))
 
 
 def test_distance_kernel_sources_are_bit_exact_on_the_host(tmp_path):
