@@ -249,7 +249,15 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
     const int base2 = (u == 0) ? 128 : 258 * ((16 - pA) & 15) + 16 * (pA ? 15 - pB : 16 - pB);
 
     // ---- thread 0: first frame of this CTA, its copy ---------------------------------------------------------
-    if (u == 0) {
+    // The CTA's bookkeeping thread (frame cursor, bulk copies): lane 0 of warp (blockIdx.x & 3).  Warp w of every CTA
+    // lives on the SM's sub-partition w; thread 0 already carries the self-mirrored columns, so the role rotates over
+    // the CTAs of an SM instead of piling onto one scheduler.
+#ifdef S2_ROTATE_LEADER
+    const bool leader = u == 32 * (int)(blockIdx.x & 3u);
+#else
+    const bool leader = u == 0;
+#endif
+    if (leader) {
         s2::mbar_init(bar, 1);
         cur.item = blockIdx.x * (unsigned)items_per_cta;
         cur.item_end = min(cur.item + (unsigned)items_per_cta, total_items);
@@ -268,7 +276,7 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
         const int n = s_fd[0].n, s0 = s_fd[0].s0;
         for (int m = u; m < 8192; m += s2::THREADS) X[m] = r8k::reflect_sample(x, n, (long long)s0 + m);
         __syncthreads();
-        if (u == 0) s2::mbar_arrive(bar);
+        if (leader) s2::mbar_arrive(bar);
     }
 
     for (unsigned int it = 0;; it++) {
@@ -321,7 +329,7 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
             s2::p1_store<15>(v1, v2, cmul(t7, t8), y4);
         }
         __syncthreads();  // B1: Y complete, X consumed
-        if (u == 0) {     // next frame: descriptor + bulk copy, a whole frame ahead
+        if (leader) {     // next frame: descriptor + bulk copy, a whole frame ahead
             s2::FrameDesc &nd = s_fd[ph ^ 1];
             nd.valid = 0;
             cur.f++;
@@ -360,7 +368,7 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
                 const float *x = nd.x;
                 const int n = nd.n, s0 = nd.s0;
                 for (int m = u; m < 8192; m += s2::THREADS) X[m] = r8k::reflect_sample(x, n, (long long)s0 + m);
-                if (u == 0) s2::mbar_arrive(bar);  // (the barriers below order the fill before the next frame's loads)
+                if (leader) s2::mbar_arrive(bar);  // (the barriers below order the fill before the next frame's loads)
             }
         }
         // ---- pass 3 on the thread's column and its mirror column; untangling in registers --------------------------
@@ -431,6 +439,31 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
             if ((double)thr > ref) thr = __uint_as_float(__float_as_uint(thr) - 1u);  // ref >= 0: one ulp down (0 stays 0: fmx = 0 has no peaks)
             unsigned int flags = 0;
             const int b0 = 56 + 12 * u;  // this thread's centres c = b0 + 1 + i, i < 12
+#ifdef S2_PIP_THRESHOLD_FIRST
+            if (u < 119) {
+                // a candidate stands above a tenth of the frame maximum: few bins do, so that test goes first (one
+                // compare per centre) and the two neighbour compares run for the survivors only
+                float m[16];
+                const float4 *q = reinterpret_cast<const float4 *>(P + b0);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 t = q[i];
+                    m[4 * i] = t.x; m[4 * i + 1] = t.y; m[4 * i + 2] = t.z; m[4 * i + 3] = t.w;
+                }
+                unsigned int hot = 0;
+#pragma unroll
+                for (int i = 0; i < 12; i++)
+                    if (m[i + 1] > thr) hot |= 1u << i;
+                if (u == 118) hot &= 0x7ffu;  // centre 1484 is past the last one (1483)
+                if (!(fmx > 0.f)) hot = 0u;
+                while (hot) {
+                    const int i = __ffs(hot) - 1;
+                    hot &= hot - 1;
+                    const float before = P[b0 + i], elem = P[b0 + i + 1], after = P[b0 + i + 2];
+                    if (after <= elem && before < elem) flags |= 1u << i;
+                }
+            }
+#else
             if (u < 119) {
                 float m[16];
                 const float4 *q = reinterpret_cast<const float4 *>(P + b0);
@@ -446,6 +479,7 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
                 }
                 if (u == 118) flags &= 0x7ffu;  // centre 1484 is past the last one (1483)
             }
+#endif
             const int cnt = __popc(flags);
             unsigned int incl = (unsigned)cnt;
 #pragma unroll
