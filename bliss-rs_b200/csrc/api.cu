@@ -251,7 +251,7 @@ void plan_wave(const uint64_t *offsets, const uint64_t *n_samples, uint32_t firs
     for (uint32_t i = 0; i < count; i++) total_pairs += geom_of(n_samples[first + i]).n_t;
     // enough warp-items to fill 148 SMs x 16 warps a few times over, runs as long as possible
     uint64_t r = total_pairs / (148ull * 16ull * 4ull);
-    w.pairs_per_item = (uint32_t)std::min<uint64_t>(128, std::max<uint64_t>(8, r));  // (128 against 64: -0.6 % on 1024 tracks, profiles/knobs_r02.md)
+    w.pairs_per_item = (uint32_t)std::min<uint64_t>(256, std::max<uint64_t>(8, r));  // (256 against 64: -1 % on 1024 tracks, profiles/knobs_r02.md)
     if (const char *e = getenv("BLISS_B200_PVOC_PAIRS")) w.pairs_per_item = (uint32_t)std::max(4, atoi(e));  // experiments
     w.k1_prefix.assign(count + 1, 0);
     w.chunk_prefix.assign(count + 1, 0);

@@ -249,14 +249,9 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
     const int base2 = (u == 0) ? 128 : 258 * ((16 - pA) & 15) + 16 * (pA ? 15 - pB : 16 - pB);
 
     // ---- thread 0: first frame of this CTA, its copy ---------------------------------------------------------
-    // The CTA's bookkeeping thread (frame cursor, bulk copies): lane 0 of warp (blockIdx.x & 3).  Warp w of every CTA
-    // lives on the SM's sub-partition w; thread 0 already carries the self-mirrored columns, so the role rotates over
-    // the CTAs of an SM instead of piling onto one scheduler.
-#ifdef S2_ROTATE_LEADER
-    const bool leader = u == 32 * (int)(blockIdx.x & 3u);
-#else
+    // The CTA's bookkeeping thread (frame cursor, bulk copies).  (Rotating the role over the warps by CTA -- warp w of
+    // every CTA lives on sub-partition w -- was measured: no difference, profiles/knobs_r02.md.)
     const bool leader = u == 0;
-#endif
     if (leader) {
         s2::mbar_init(bar, 1);
         cur.item = blockIdx.x * (unsigned)items_per_cta;
@@ -439,31 +434,8 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
             if ((double)thr > ref) thr = __uint_as_float(__float_as_uint(thr) - 1u);  // ref >= 0: one ulp down (0 stays 0: fmx = 0 has no peaks)
             unsigned int flags = 0;
             const int b0 = 56 + 12 * u;  // this thread's centres c = b0 + 1 + i, i < 12
-#ifdef S2_PIP_THRESHOLD_FIRST
-            if (u < 119) {
-                // a candidate stands above a tenth of the frame maximum: few bins do, so that test goes first (one
-                // compare per centre) and the two neighbour compares run for the survivors only
-                float m[16];
-                const float4 *q = reinterpret_cast<const float4 *>(P + b0);
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float4 t = q[i];
-                    m[4 * i] = t.x; m[4 * i + 1] = t.y; m[4 * i + 2] = t.z; m[4 * i + 3] = t.w;
-                }
-                unsigned int hot = 0;
-#pragma unroll
-                for (int i = 0; i < 12; i++)
-                    if (m[i + 1] > thr) hot |= 1u << i;
-                if (u == 118) hot &= 0x7ffu;  // centre 1484 is past the last one (1483)
-                if (!(fmx > 0.f)) hot = 0u;
-                while (hot) {
-                    const int i = __ffs(hot) - 1;
-                    hot &= hot - 1;
-                    const float before = P[b0 + i], elem = P[b0 + i + 1], after = P[b0 + i + 2];
-                    if (after <= elem && before < elem) flags |= 1u << i;
-                }
-            }
-#else
+            // (testing `elem > thr` first and the neighbours only for the survivors was measured: the divergent loop costs
+            // more than the 24 compares it saves, 22.5 against 21.5 ms, profiles/knobs_r02.md)
             if (u < 119) {
                 float m[16];
                 const float4 *q = reinterpret_cast<const float4 *>(P + b0);
@@ -479,7 +451,6 @@ stft8192v2_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
                 }
                 if (u == 118) flags &= 0x7ffu;  // centre 1484 is past the last one (1483)
             }
-#endif
             const int cnt = __popc(flags);
             unsigned int incl = (unsigned)cnt;
 #pragma unroll

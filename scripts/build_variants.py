@@ -16,9 +16,6 @@ VARIANTS = {
     "nopacked": ["-DBLISS_NO_PACKED_FP"],  # scalar FADD/FMUL/FFMA butterflies instead of the f32x2 forms
     "stride4104": ["-DBLISS_CH_STRIDE=4104"],  # round 1's pitch (rows 32 bytes off the 128-byte lines); 4128 is the default now
     # chroma_pipe_kernel's cp.async ring: 3 stages (3 CTAs per SM) is the default
-    # stft8192v2_kernel experiments (measured in round 2: both lose, profiles/knobs_r02.md)
-    "s2rot": ["-DS2_ROTATE_LEADER"],
-    "s2hot": ["-DS2_PIP_THRESHOLD_FIRST"],
     "k5p4": ["-DK5P_STAGES_N=4"],
     "k5p2": ["-DK5P_STAGES_N=2"],
 }

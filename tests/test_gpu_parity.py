@@ -957,3 +957,31 @@ def test_packed_distance_kernel_is_bit_identical_to_the_scalar_one():
         ref = np.array([[O.mahalanobis_distance(r, c, m if m is not None else np.eye(dim, dtype=np.float32)) for c in cols[:40]]
                         for r in rows[:9]], np.float32)
         assert np.array_equal(got[:9, :40].view(np.uint32), ref.view(np.uint32))
+
+
+def test_bench_corpus_256_three_minute_tracks_against_the_oracle():
+    """SURVEY section 8(d) config 2 at full size: 256 of the 3-minute bench tracks (the generator and seed of bench.py)
+    through the device path against the oracle on all host threads: max / median error per feature, tempo and tuning
+    flips.  Bar: every feature within 1e-4 (relative to max(1, |oracle|)); at most one tempo decision on an edge."""
+    import os
+    n_tracks, n = 256, 3 * 60 * 22050
+    pcm, offs, lens = synth.gen_corpus_flat(20260925, list(range(n_tracks)), [n] * n_tracks, device=DEV)
+    out = torch.zeros((n_tracks, 23), dtype=torch.float32, device=DEV)
+    st = B.native.analyze_batch_device(pcm.data_ptr(), offs, lens, 2, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    feats = out.cpu().numpy()
+    songs = [pcm[o:o + n].cpu().numpy() for o in offs]
+    del pcm
+    ost, ofe = O.analyze_batch(songs, 2, n_threads=os.cpu_count() or 8)
+    assert (st == 0).all() and (ost == 0).all()
+    err = np.abs(feats - ofe)
+    rel = err / np.maximum(1.0, np.abs(ofe))
+    print("256 x 3-min tracks: max abs err per feature   ", np.array2string(err.max(axis=0), precision=1))
+    print("256 x 3-min tracks: median abs err per feature", np.array2string(np.median(err, axis=0), precision=1))
+    tempo_flips = int((err[:, 0] > 1e-3).sum())
+    chroma_off = int((err[:, 10:].max(axis=1) > 1e-3).sum())  # a flipped tuning bin moves every chroma feature
+    print("tempo decisions differing: %d / %d, tuning decisions differing: %d" % (tempo_flips, n_tracks, chroma_off))
+    assert tempo_flips <= 1 and chroma_off == 0
+    ok = rel <= TOL
+    ok[err[:, 0] > 1e-3, 0] = True
+    assert ok.all(), (np.argwhere(~ok)[:5], rel.max())
