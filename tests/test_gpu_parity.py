@@ -985,3 +985,40 @@ def test_bench_corpus_256_three_minute_tracks_against_the_oracle():
     ok = rel <= TOL
     ok[err[:, 0] > 1e-3, 0] = True
     assert ok.all(), (np.argwhere(~ok)[:5], rel.max())
+
+
+def test_chroma_stft_frame_edges_and_alignments():
+    """stft8192v2_kernel's staging decisions, swept: an interior frame is bulk-copied from the 16-byte boundary below
+    its first sample (rotation r = start & 3) unless the copy would run past the song's end, in which case -- like the
+    reflect-padded frames at both ends -- it is filled by hand.  Songs of lengths around every boundary of that logic
+    (8192 + k, and lengths that put the last interior frame 0..4 samples short of the end), at every offset mod 4 of
+    one device buffer, against the oracle; and the same through the one-column kernel."""
+    rng = np.random.default_rng(5)
+    lens = [8192 + k for k in range(0, 9)] + [4096 + 2205 * 3 + 4096 + k for k in range(-5, 6)] + \
+           [4096 + 2205 * 7 + 4096 + k for k in (-3, -2, -1, 0, 1, 2, 3)] + [30011, 44100 + 1, 65537, 2205 * 20, 2205 * 20 + 1]
+    songs = [(0.3 * rng.standard_normal(n) + 0.2 * np.sin(2 * np.pi * 440.0 * np.arange(n) / 22050.0)).astype(np.float32) for n in lens]
+    flat, offs, pos = [], [], 0
+    for i, x in enumerate(songs):
+        pad = (i % 4)  # arbitrary alignment: consecutive songs start at every offset mod 4
+        flat.append(np.zeros(pad, np.float32))
+        pos += pad
+        offs.append(pos)
+        flat.append(x)
+        pos += len(x)
+    buf = torch.from_numpy(np.concatenate(flat + [np.zeros(8, np.float32)])).to(DEV)
+    want = [O.analyze(x, 2) for x in songs]
+    try:
+        for mask in (0, STFT_V3):
+            B.native.set_variant(mask)
+            out = torch.zeros((len(songs), 23), dtype=torch.float32, device=DEV)
+            st = B.native.analyze_batch_device(buf.data_ptr(), offs, lens, 2, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            got = out.cpu().numpy()
+            assert (st == 0).all()
+            for i, (rc, w) in enumerate(want):
+                assert rc == 0
+                ok = _close(got[i], w)
+                assert ok[10:].all(), (mask, lens[i], offs[i] % 4, np.abs(got[i] - w)[10:].max())   # the chroma features
+                assert ok[:10].all(), (mask, lens[i], np.abs(got[i] - w)[:10].max())
+    finally:
+        B.native.set_variant(0)
