@@ -912,8 +912,8 @@ def test_stft8192v2_against_the_round1_kernel(pcm_song, pcm_piano):
         offs = [0, 1, 2, 3, len(pcm_song) + 1, len(pcm_song) + 6]
         lens = [50001, 50002, 60003, 70000, 40001, 44444]
         out = torch.zeros((len(offs), 23), dtype=torch.float32, device=DEV)
-        B.native.analyze_batch_device(flat.data_ptr(), offs, lens, 2, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        torch.cuda.synchronize()
+        B.native.analyze_batch_device(flat.data_ptr(), offs, lens, 2, out.data_ptr(), None)
+        _sync()
         got = out.cpu().numpy()
         host = flat.cpu().numpy()
         for i, (o, l) in enumerate(zip(offs, lens)):
@@ -1011,8 +1011,8 @@ def test_chroma_stft_frame_edges_and_alignments():
         for mask in (0, STFT_V3):
             B.native.set_variant(mask)
             out = torch.zeros((len(songs), 23), dtype=torch.float32, device=DEV)
-            st = B.native.analyze_batch_device(buf.data_ptr(), offs, lens, 2, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
-            torch.cuda.synchronize()
+            st = B.native.analyze_batch_device(buf.data_ptr(), offs, lens, 2, out.data_ptr(), None)
+            _sync()
             got = out.cpu().numpy()
             assert (st == 0).all()
             for i, (rc, w) in enumerate(want):

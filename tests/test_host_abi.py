@@ -391,7 +391,8 @@ def test_c_abi_on_the_host_emulated_library(tmp_path):
     so = _build_host_emulated_library(tmp_path)
     env = dict(os.environ, BLISS_B200_SO=so, CUDA_VISIBLE_DEVICES="")
     pick = ("golden_clip_v2 or too_short or s16_ingest or pcm_feed or distance_known or distance_matrix_bit or "
-            "closest_to_songs or dedup or stft512_magnitudes or experimental_stft_pair or cue_style or wav_files or library_playlists")
+            "closest_to_songs or dedup or stft512_magnitudes or experimental_stft_pair or cue_style or wav_files or library_playlists "
+            "or frame_edges or chroma_filter or packed_distance")
     # the C++17 host mirror (include/bliss_b200.hpp: Song, Decoder, WavDecoder, analyze_batch[_s16|_pcm], playlist) end to
     # end, started first and left running beside the Python slice
     exe = str(tmp_path / "host_mirror_emu")
