@@ -38,6 +38,7 @@ SYMBOLS = [
     "bliss_b200_strerror",
     "bliss_b200_last_error", "bliss_b200_feature_count", "bliss_b200_analyze", "bliss_b200_analyze_batch",
     "bliss_b200_analyze_batch_s16", "bliss_b200_analyze_batch_pcm", "bliss_b200_pcm_to_mono",
+    "bliss_b200_resample", "bliss_b200_resampled_len",
     "bliss_b200_analyze_batch_device", "bliss_b200_feature_weights", "bliss_b200_distance",
     "bliss_b200_distance_matrix", "bliss_b200_distance_matrix_device", "bliss_b200_closest_to_songs",
     "bliss_b200_song_to_song", "bliss_b200_stft512_mag_device", "bliss_b200_analyze_taps", "bliss_b200_chroma_filter",
@@ -75,6 +76,9 @@ def load():
     L.bliss_b200_analyze_batch_s16.argtypes = [vp, u64p, C.c_uint32, C.c_uint16, vp, i32p]
     L.bliss_b200_analyze_batch_pcm.argtypes = [vp, u64p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint16, vp, i32p]
     L.bliss_b200_pcm_to_mono.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint32, vp]
+    L.bliss_b200_resample.argtypes = [vp, C.c_uint64, C.c_uint32, vp, C.c_uint64, u64p]
+    L.bliss_b200_resampled_len.argtypes = [C.c_uint64, C.c_uint32]
+    L.bliss_b200_resampled_len.restype = C.c_uint64
     L.bliss_b200_analyze_batch_device.argtypes = [vp, u64p, u64p, C.c_uint32, C.c_uint16, vp, i32p, vp]
     L.bliss_b200_feature_weights.argtypes = [C.c_uint16, vp]
     L.bliss_b200_distance.argtypes = [vp, vp, C.c_uint32, C.c_int, vp, f32p]
@@ -230,6 +234,13 @@ def analyze_batch_s16_ptrs(ptrs, lens, version, out, status):
                                          status.ctypes.data_as(C.POINTER(C.c_int32))))
 
 
+def analyze_batch_pcm_ptrs(ptrs, n_frames, fmt, channels, sample_rate, version, out, status):
+    """raw form used by bench.py: ptrs/n_frames are ctypes arrays over pinned host buffers of interleaved frames"""
+    L = lib()
+    check(L.bliss_b200_analyze_batch_pcm(ptrs, n_frames, len(n_frames), int(fmt), int(channels), int(sample_rate), version,
+                                         out.ctypes.data, status.ctypes.data_as(C.POINTER(C.c_int32))))
+
+
 PCM_S16, PCM_S32, PCM_F32 = 1, 2, 3
 _PCM_FORMATS = {np.dtype(np.int16): PCM_S16, np.dtype(np.int32): PCM_S32, np.dtype(np.float32): PCM_F32}
 
@@ -248,7 +259,8 @@ def _frames(a):
 
 def analyze_batch_pcm(frames, sample_rate=22050, version=2):
     """interleaved frames as the codec delivers them ([n_frames, channels] int16 / int32 / float32 arrays of ONE
-    format and channel count, 22 050 Hz): sample-format conversion and down-mix run on the device"""
+    format, channel count and sample rate): sample-format conversion, down-mix and -- for a rate other than
+    22 050 Hz -- the sample-rate conversion run on the device"""
     L = lib()
     arrs = [_frames(f) for f in frames]
     n = len(arrs)
@@ -273,6 +285,23 @@ def pcm_to_mono(frames):
     out = np.zeros(a.shape[0], np.float32)
     check(L.bliss_b200_pcm_to_mono(a.ctypes.data if a.size else None, a.shape[0], fmt, a.shape[1], out.ctypes.data))
     return out
+
+
+def resampled_len(n_samples, sample_rate):
+    """length of an n_samples signal at sample_rate once at 22 050 Hz (src/song/decoder/symphonia.rs:379-380)"""
+    return int(load().bliss_b200_resampled_len(int(n_samples), int(sample_rate)))
+
+
+def resample(pcm, sample_rate):
+    """mono f32 at sample_rate -> mono f32 at 22 050 Hz on the device (bliss_b200_resample: parity unpinned against
+    the reference's swresample / rubato, checked against scipy.signal.resample_poly)"""
+    L = lib()
+    pcm = _f32c(pcm)
+    n = C.c_uint64(0)
+    out = np.zeros(resampled_len(pcm.size, sample_rate), np.float32)
+    check(L.bliss_b200_resample(pcm.ctypes.data if pcm.size else None, pcm.size, int(sample_rate),
+                                out.ctypes.data if out.size else None, out.size, C.byref(n)))
+    return out[:n.value]
 
 
 def analyze(pcm, version=2):

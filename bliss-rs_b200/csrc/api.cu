@@ -49,6 +49,8 @@ int launch_finalize(const SongDesc *, int, const float *, const float *, const f
 int launch_wave_setup(const void *, void *, size_t, unsigned int *, unsigned int *, unsigned int, cudaStream_t);
 int launch_s16_to_f32(const short *, float *, size_t, cudaStream_t);
 int launch_pcm_to_mono(const void *, float *, size_t, int, unsigned int, cudaStream_t);
+int launch_resample(const float *, float *, const void *, const unsigned int *, unsigned int, unsigned int, const float *,
+                    unsigned int, unsigned int, unsigned int, unsigned int, int, cudaStream_t);
 int launch_gather_barrier(unsigned int *const *, int, int, unsigned int, unsigned long long, cudaStream_t);
 int launch_distance_matrix(const float *, unsigned int, const float *, unsigned int, int, int, const float *,
                            float *, cudaStream_t, unsigned int ones_mask, int variant);
@@ -149,7 +151,7 @@ struct Ctx {
     std::mutex mu;
     bool inited = false;
     int device = -1;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, conv_stream = nullptr;
     cudaEvent_t ev_begin = nullptr;
     size_t ws_limit = 0;
     int variant = 0;  // BLISS_B200_VARIANT, see common.cuh
@@ -161,6 +163,12 @@ struct Ctx {
     int next_set = 0;
     // host-API staging
     DevBuf pcm[4], raw16[4], feats, metric, misc[6];
+    // sample-rate conversion (design_resampler / enqueue_resample): the filter of the rate last used, the mono input of
+    // each ring slot at its own rate, and each slot's job table (pinned host copy + device copy)
+    DevBuf rs_tab, rs_in[4], rs_jobs[4];
+    void *rs_host[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t rs_host_cap[4] = {0, 0, 0, 0};
+    uint32_t rs_rate = 0, rs_up = 0, rs_down = 0, rs_taps4 = 0, rs_pre = 0;
     // profiling
     bool profiling = false;
     struct EvPair { cudaEvent_t a, b; int kid; };
@@ -727,6 +735,7 @@ static int init_ctx_locked(int device) {
     g.device = device;
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.conv_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&g.ev_begin, cudaEventDisableTiming));
     // BLISS_B200_STREAM_PRIORITY (experiment; measured flat in round 2, profiles/ab_r02.md; default 0 = both chains at
     // the same priority): 1 = the tempo / timbral chain's stream is preferred by the block scheduler, 2 = the chroma chain's
@@ -819,8 +828,15 @@ static void shutdown_ctx() {  // the calling thread's current context
     cudaDeviceSynchronize();
     DevBuf *all[] = {&g.t_win512, &g.t_twA, &g.t_hann8k, &g.t_tw4k, &g.t_tw2, &g.t_tw8k, &g.t_filt, &g.t_filt32,
                      &g.pcm[0], &g.pcm[1], &g.pcm[2], &g.pcm[3], &g.raw16[0], &g.raw16[1], &g.raw16[2], &g.raw16[3], &g.feats, &g.metric, &g.misc[0], &g.misc[1],
-                     &g.misc[2], &g.misc[3], &g.misc[4], &g.misc[5]};
+                     &g.misc[2], &g.misc[3], &g.misc[4], &g.misc[5], &g.rs_tab, &g.rs_in[0], &g.rs_in[1], &g.rs_in[2], &g.rs_in[3],
+                     &g.rs_jobs[0], &g.rs_jobs[1], &g.rs_jobs[2], &g.rs_jobs[3]};
     for (DevBuf *b : all) b->release();
+    for (int i = 0; i < 4; i++) {
+        if (g.rs_host[i]) cudaFreeHost(g.rs_host[i]);
+        g.rs_host[i] = nullptr;
+        g.rs_host_cap[i] = 0;
+    }
+    g.rs_rate = 0;
     for (auto &S : g.ws) {
         S.release();
         cudaStreamDestroy(S.main);
@@ -836,6 +852,7 @@ static void shutdown_ctx() {  // the calling thread's current context
     g.ev_pool.clear();
     cudaStreamDestroy(g.stream);
     cudaStreamDestroy(g.copy_stream);
+    cudaStreamDestroy(g.conv_stream);
     cudaEventDestroy(g.ev_begin);
     g.inited = false;
 }
@@ -1079,16 +1096,120 @@ int bliss_b200_gather_destroy(bliss_b200_gather *ga) {
 struct HostPcm {
     int fmt;            // BLISS_B200_PCM_*
     uint32_t channels;
+    uint32_t rate = (uint32_t)SAMPLE_RATE;
     size_t frame_bytes() const { return (size_t)(fmt == BLISS_B200_PCM_S16 ? 2 : 4) * channels; }
-    bool direct() const { return fmt == BLISS_B200_PCM_F32 && channels == 1; }
+    bool mono_f32() const { return fmt == BLISS_B200_PCM_F32 && channels == 1; }
+    bool resample() const { return rate != (uint32_t)SAMPLE_RATE; }
+    bool direct() const { return mono_f32() && !resample(); }
 };
+
+// ---- sample-rate conversion to 22 050 Hz: the filter and the job table (kernel: wave_setup.cu) ----------------------
+// scipy.signal.resample_poly's design, restated (scipy/signal/_signaltools.py resample_poly + _fir_filter_design.py
+// firwin; oracle/resample.py is the numpy statement the tests check both against):
+//   up / down = 22050 / rate in lowest terms, m = max(up, down), half = 10 m,
+//   h[k] = (1/m) sinc((k - half) / m) kaiser_5(k), k = 0 .. 2 half, scaled to sum 1, times up;
+//   down - half mod down zeros in front so that the delay is a whole number of outputs (pre_remove of them dropped).
+// Laid out by phase for the kernel: row p = h'[p], h'[p + up], ... (taps4 floats, zero-filled).
+static double bessel_i0(double x) {
+    double sum = 1.0, term = 1.0;
+    const double q = 0.25 * x * x;
+    for (int k = 1; k < 500; k++) {
+        term *= q / ((double)k * (double)k);
+        sum += term;
+        if (term < 1e-17 * sum) break;
+    }
+    return sum;
+}
+
+static uint64_t resample_len(uint64_t n, uint32_t rate) {  // src/song/decoder/symphonia.rs:379-380
+    if (rate == (uint32_t)SAMPLE_RATE) return n;
+    return (uint64_t)std::ceil((double)SAMPLE_RATE / (double)rate * (double)n);
+}
+
+static int design_resampler(uint32_t rate) {  // into the calling context; a no-op for the rate last designed
+    if (g.rs_rate == rate) return BLISS_B200_OK;
+    uint32_t a = (uint32_t)SAMPLE_RATE, b = rate;
+    while (b) { const uint32_t t = a % b; a = b; b = t; }
+    const uint32_t up = (uint32_t)SAMPLE_RATE / a, down = rate / a;
+    const uint64_t m = std::max(up, down), half = 10 * m, numtaps = 2 * half + 1;
+    std::vector<double> h(numtaps);
+    const double pi = 3.14159265358979323846, i0b = bessel_i0(5.0);
+    double sum = 0.0;
+    for (uint64_t k = 0; k < numtaps; k++) {
+        const double x = ((double)k - (double)half) / (double)m;
+        const double sinc = k == half ? 1.0 : std::sin(pi * x) / (pi * x);
+        const double r = ((double)k - (double)half) / (double)half;
+        const double w = bessel_i0(5.0 * std::sqrt(std::max(0.0, 1.0 - r * r))) / i0b;
+        h[k] = sinc / (double)m * w;
+        sum += h[k];
+    }
+    const uint64_t pre_pad = down - half % down, L = pre_pad + numtaps;
+    const uint32_t taps4 = (uint32_t)align_up((size_t)((L + up - 1) / up), 4);
+    std::vector<float> tab((size_t)up * taps4, 0.f);
+    for (uint32_t p = 0; p < up; p++)
+        for (uint32_t t = 0; t < taps4; t++) {
+            const uint64_t k = (uint64_t)p + (uint64_t)t * up;
+            if (k >= pre_pad && k < L) tab[(size_t)p * taps4 + t] = (float)(h[k - pre_pad] / sum * (double)up);
+        }
+    CK(cudaDeviceSynchronize());  // a table of another rate may still be in use
+    CK(g.rs_tab.ensure(tab.size() * 4));
+    CK(cudaMemcpy(g.rs_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    g.rs_rate = rate;
+    g.rs_up = up;
+    g.rs_down = down;
+    g.rs_taps4 = taps4;
+    g.rs_pre = (uint32_t)((half + pre_pad) / down);
+    return BLISS_B200_OK;
+}
+
+// One chunk's conversions: song i reads in[in_off[i] .. +in_len[i]) and writes out[out_off[i] .. +out_len[i]).  The job
+// table goes through ring slot `slot`'s pinned host copy and is pulled onto the device by a kernel (wave_setup.cu says
+// why); the caller guarantees that the slot's previous conversion has finished.
+struct ResampleJobHost { unsigned long long in_off, in_len, out_off, out_len; };
+static int enqueue_resample(int slot, const float *in, float *out, const std::vector<ResampleJobHost> &jobs_in, cudaStream_t st) {
+    std::vector<ResampleJobHost> jobs;
+    std::vector<unsigned int> prefix;
+    unsigned long long tiles = 0;
+    for (const auto &j : jobs_in) {
+        if (j.out_len == 0) continue;
+        jobs.push_back(j);
+        prefix.push_back((unsigned int)tiles);
+        tiles += (j.out_len + 1023) / 1024;
+    }
+    if (jobs.empty()) return BLISS_B200_OK;
+    if (tiles >= 0x7fffffffull) { g_last_error = "resampler: chunk too large"; return BLISS_B200_E_ARG; }
+    prefix.push_back((unsigned int)tiles);
+    const size_t jb = jobs.size() * sizeof(ResampleJobHost), bytes = align_up(jb + prefix.size() * 4, 16);
+    if (g.rs_host_cap[slot] < bytes) {
+        if (g.rs_host[slot]) CK(cudaFreeHost(g.rs_host[slot]));
+        g.rs_host[slot] = nullptr;
+        g.rs_host_cap[slot] = 0;
+        CK(cudaMallocHost(&g.rs_host[slot], bytes * 2));
+        g.rs_host_cap[slot] = bytes * 2;
+    }
+    memcpy(g.rs_host[slot], jobs.data(), jb);
+    memcpy(static_cast<char *>(g.rs_host[slot]) + jb, prefix.data(), prefix.size() * 4);
+    CK(g.rs_jobs[slot].ensure(bytes));
+    g.launches += (unsigned long long)launch_wave_setup(g.rs_host[slot], g.rs_jobs[slot].p, bytes, nullptr, nullptr, 0, st);
+    const int launched = launch_resample(in, out, g.rs_jobs[slot].p,
+                                         reinterpret_cast<const unsigned int *>(g.rs_jobs[slot].as<char>() + jb),
+                                         (unsigned int)jobs.size(), (unsigned int)tiles, g.rs_tab.as<float>(), g.rs_up, g.rs_down,
+                                         g.rs_taps4, g.rs_pre, (g.variant & VARIANT_RESAMPLE_V1) ? 1 : 0, st);
+    if (launched < 0) { g_last_error = "resampler: the filter table does not fit the kernel's shared memory"; return BLISS_B200_E_CUDA; }
+    g.launches += (unsigned long long)launched;
+    CK(cudaGetLastError());
+    return BLISS_B200_OK;
+}
 
 static int analyze_host_locked(const void *const *pcm_v, const uint64_t *n_samples, uint32_t n_songs,
                                uint16_t ver, float *out, int32_t *status, bool debug,
                                HostPcm hp = HostPcm{BLISS_B200_PCM_F32, 1}) {
     const char *const *pcm = reinterpret_cast<const char *const *>(pcm_v);
-    const bool kRaw = !hp.direct();
+    const bool kRaw = !hp.mono_f32();  // frames land in the raw staging buffer and are converted / down-mixed there
+    const bool kRs = hp.resample();    // ... and the mono signal is at another rate: converted into the PCM buffer
     const size_t fb = hp.frame_bytes();
+    if (kRs)
+        if (int rc_d = design_resampler(hp.rate)) return rc_d;
     const uint32_t dim = bliss_b200_feature_count(ver);
     CK(g.feats.ensure((size_t)n_songs * dim * 4));
     // The path is PCIe-bound (15.9 MB per 3-min song).  Songs travel in chunks through a ring of FOUR
@@ -1113,38 +1234,56 @@ static int analyze_host_locked(const void *const *pcm_v, const uint64_t *n_sampl
     std::vector<size_t> tr_bytes;
     size_t done_bytes = 0;
     constexpr int NBUF = 4;
-    cudaEvent_t ev_copy[NBUF], ev_done[NBUF][N_SETS];
-    bool done_used[NBUF][N_SETS];
+    cudaEvent_t ev_copy[NBUF], ev_raw[NBUF], ev_done[NBUF][N_SETS];
+    bool done_used[NBUF][N_SETS], copy_used[NBUF] = {false, false, false, false};
+    // The conversions behind a chunk's copy (sample format, down-mix, sample rate) run on their own stream: on the copy
+    // stream they would hold back the next chunk's copy for as long as they take (measured: 16-bit mono sources 6 424 ->
+    // 6 614 songs/s, CD-format sources 1 528 -> 1 602 songs/s; BLISS_B200_CONV_ON_COPY_STREAM=1 goes back).
+    const bool conv_apart = (kRaw || kRs) && !getenv("BLISS_B200_CONV_ON_COPY_STREAM");
     for (int i = 0; i < NBUF; i++) {
         CK(cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_raw[i], cudaEventDisableTiming));
         for (int k = 0; k < N_SETS; k++) {
             CK(cudaEventCreateWithFlags(&ev_done[i][k], cudaEventDisableTiming));
             done_used[i][k] = false;
         }
     }
-    std::vector<uint64_t> offs, lens;
+    // offs / lens: the songs of the chunk at 22 050 Hz in the PCM buffer; offs_in / lens_in: as they arrive (the same
+    // numbers unless the call resamples)
+    std::vector<uint64_t> offs, lens, offs_in, lens_in;
+    std::vector<ResampleJobHost> jobs;
     uint32_t first = 0;
     int c = 0, rc = BLISS_B200_OK;
     while (first < n_songs && rc == BLISS_B200_OK) {
         // chunk = as many songs as fit the PCM budget (at least one)
         const size_t budget = std::min<size_t>(chunk_budget, c < 8 ? ((size_t)64 << 20) << c : chunk_budget);
-        size_t samples = 0;
+        size_t samples = 0, samples_in = 0;
         uint32_t count = 0;
         offs.clear();
         lens.clear();
+        offs_in.clear();
+        lens_in.clear();
         while (first + count < n_songs) {
-            const size_t len = align_up((size_t)n_samples[first + count], 4);
-            if (count > 0 && (samples + len) * std::max<size_t>(4, fb) > budget) break;  // the larger of the two buffers
+            const uint64_t n_in = n_samples[first + count], n_22k = resample_len(n_in, hp.rate);
+            const size_t len = align_up((size_t)n_22k, 4), len_in = align_up((size_t)n_in, 4);
+            // the largest of the buffers involved
+            if (count > 0 && std::max((samples + len) * 4, (samples_in + len_in) * std::max<size_t>(4, fb)) > budget) break;
             offs.push_back(samples);
-            lens.push_back(n_samples[first + count]);
+            lens.push_back(n_22k);
+            offs_in.push_back(samples_in);
+            lens_in.push_back(n_in);
             samples += len;
+            samples_in += len_in;
             count++;
         }
         const int b = c % NBUF;
         for (int k = 0; k < N_SETS; k++)  // buffer b free again (also: the host may reallocate it)
             if (done_used[b][k]) CK(cudaEventSynchronize(ev_done[b][k]));
+        if (copy_used[b]) CK(cudaEventSynchronize(ev_copy[b]));  // the slot's staging buffers and job table as well
         CK(g.pcm[b].ensure(std::max<size_t>(samples, 4) * 4));
-        if (kRaw) CK(g.raw16[b].ensure(std::max<size_t>(samples, 4) * fb));
+        if (kRaw) CK(g.raw16[b].ensure(std::max<size_t>(samples_in, 4) * fb));
+        if (kRs) CK(g.rs_in[b].ensure(std::max<size_t>(samples_in, 4) * 4));
+        float *const mono = kRs ? g.rs_in[b].as<float>() : g.pcm[b].as<float>();  // where the mono f32 signal lands
         if (trace) {
             cudaEvent_t e;
             CK(cudaEventCreate(&e));
@@ -1152,31 +1291,41 @@ static int analyze_host_locked(const void *const *pcm_v, const uint64_t *n_sampl
             tr_cb.push_back(e);
         }
         for (uint32_t i = 0; i < count;) {
-            if (lens[i] == 0) { i++; continue; }
+            if (lens_in[i] == 0) { i++; continue; }
             if (!pcm[first + i]) { g_last_error = "null pcm pointer"; rc = BLISS_B200_E_ARG; break; }
             // songs that sit back to back in host memory (one big decoded buffer) go as ONE copy
             uint32_t j = i;
-            size_t run = (size_t)lens[i];
-            while (j + 1 < count && lens[j + 1] > 0 && (lens[j] & 3u) == 0 &&
-                   pcm[first + j + 1] == pcm[first + j] + (size_t)lens[j] * fb) {
+            size_t run = (size_t)lens_in[i];
+            while (j + 1 < count && lens_in[j + 1] > 0 && (lens_in[j] & 3u) == 0 &&
+                   pcm[first + j + 1] == pcm[first + j] + (size_t)lens_in[j] * fb) {
                 j++;
-                run += (size_t)lens[j];
+                run += (size_t)lens_in[j];
             }
-            void *dst = kRaw ? (void *)(g.raw16[b].as<char>() + (size_t)offs[i] * fb) : (void *)(g.pcm[b].as<float>() + offs[i]);
+            void *dst = kRaw ? (void *)(g.raw16[b].as<char>() + (size_t)offs_in[i] * fb) : (void *)(mono + offs_in[i]);
             CK(cudaMemcpyAsync(dst, pcm[first + i], run * fb, cudaMemcpyHostToDevice, g.copy_stream));
             i = j + 1;
         }
         if (rc) break;
-        if (kRaw) {  // same frame offsets in both buffers; runs behind the copies on the copy stream
+        cudaStream_t cs = g.copy_stream;  // where the chunk becomes ready
+        if (conv_apart) {
+            CK(cudaEventRecord(ev_raw[b], g.copy_stream));
+            CK(cudaStreamWaitEvent(g.conv_stream, ev_raw[b], 0));
+            cs = g.conv_stream;
+        }
+        if (kRaw) {  // same frame offsets in both buffers; runs behind the chunk's copies
             if (hp.fmt == BLISS_B200_PCM_S16 && hp.channels == 1)
-                g.launches += (unsigned long long)launch_s16_to_f32(g.raw16[b].as<short>(), g.pcm[b].as<float>(), samples,
-                                                                   g.copy_stream);
+                g.launches += (unsigned long long)launch_s16_to_f32(g.raw16[b].as<short>(), mono, samples_in, cs);
             else
-                g.launches += (unsigned long long)launch_pcm_to_mono(g.raw16[b].p, g.pcm[b].as<float>(), samples, hp.fmt,
-                                                                    hp.channels, g.copy_stream);
+                g.launches += (unsigned long long)launch_pcm_to_mono(g.raw16[b].p, mono, samples_in, hp.fmt, hp.channels, cs);
             CK(cudaGetLastError());
         }
-        CK(cudaEventRecord(ev_copy[b], g.copy_stream));
+        if (kRs) {  // mono at hp.rate -> the PCM buffer at 22 050 Hz
+            jobs.clear();
+            for (uint32_t i = 0; i < count; i++) jobs.push_back(ResampleJobHost{offs_in[i], lens_in[i], offs[i], lens[i]});
+            if ((rc = enqueue_resample(b, mono, g.pcm[b].as<float>(), jobs, cs)) != BLISS_B200_OK) break;
+        }
+        CK(cudaEventRecord(ev_copy[b], cs));
+        copy_used[b] = true;
         if (trace) {
             cudaEvent_t e;
             CK(cudaEventCreate(&e));
@@ -1238,6 +1387,7 @@ static int analyze_host_locked(const void *const *pcm_v, const uint64_t *n_sampl
     }
     for (int i = 0; i < NBUF; i++) {
         cudaEventDestroy(ev_copy[i]);
+        cudaEventDestroy(ev_raw[i]);
         for (int k = 0; k < N_SETS; k++) cudaEventDestroy(ev_done[i][k]);
     }
     for (auto *v : {&tr_cb, &tr_ce, &tr_done})
@@ -1350,9 +1500,9 @@ static int check_pcm_format(int fmt, uint32_t channels, uint32_t sample_rate) {
         g_last_error = "channel count " + std::to_string(channels) + " outside 1.." + std::to_string(BLISS_B200_PCM_MAX_CHANNELS);
         return BLISS_B200_E_ARG;
     }
-    if (sample_rate != (uint32_t)SAMPLE_RATE) {
-        g_last_error = "sample rate " + std::to_string(sample_rate) + " Hz: this library holds no resampler, the decoder "
-                       "must deliver 22050 Hz (src/lib.rs:143)";
+    if (sample_rate < BLISS_B200_MIN_SAMPLE_RATE || sample_rate > BLISS_B200_MAX_SAMPLE_RATE) {
+        g_last_error = "sample rate " + std::to_string(sample_rate) + " Hz outside " + std::to_string(BLISS_B200_MIN_SAMPLE_RATE) +
+                       ".." + std::to_string(BLISS_B200_MAX_SAMPLE_RATE);
         return BLISS_B200_E_UNSUPPORTED;
     }
     return 0;
@@ -1364,14 +1514,47 @@ int bliss_b200_analyze_batch_pcm(const void *const *pcm, const uint64_t *n_frame
         if (check_version(ver)) return BLISS_B200_E_ARG;
         if (int rc = check_pcm_format(sample_format, channels, sample_rate)) return rc;
         if (!pcm || !n_frames || !out) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
-        return analyze_host_multi(pcm, n_frames, n_songs, ver, out, status, HostPcm{sample_format, channels});
+        return analyze_host_multi(pcm, n_frames, n_songs, ver, out, status, HostPcm{sample_format, channels, sample_rate});
     }
     REQUIRE_INIT();
     if (check_version(ver)) return BLISS_B200_E_ARG;
     if (int rc = check_pcm_format(sample_format, channels, sample_rate)) return rc;
     if (n_songs == 0) return BLISS_B200_OK;
     if (!pcm || !n_frames || !out) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
-    return analyze_host_locked(pcm, n_frames, n_songs, ver, out, status, false, HostPcm{sample_format, channels});
+    return analyze_host_locked(pcm, n_frames, n_songs, ver, out, status, false, HostPcm{sample_format, channels, sample_rate});
+}
+
+uint64_t bliss_b200_resampled_len(uint64_t n_samples, uint32_t sample_rate) {
+    if (sample_rate < BLISS_B200_MIN_SAMPLE_RATE || sample_rate > BLISS_B200_MAX_SAMPLE_RATE) return 0;
+    return resample_len(n_samples, sample_rate);
+}
+
+int bliss_b200_resample(const float *pcm, uint64_t n_samples, uint32_t sample_rate, float *out, uint64_t out_capacity,
+                        uint64_t *n_out) {
+    REQUIRE_INIT();
+    if (int rc = check_pcm_format(BLISS_B200_PCM_F32, 1, sample_rate)) return rc;
+    const uint64_t n_22k = resample_len(n_samples, sample_rate);
+    if (n_out) *n_out = n_22k;
+    if (n_22k == 0) return BLISS_B200_OK;
+    if (!pcm || !out) { g_last_error = "null pointer"; return BLISS_B200_E_ARG; }
+    if (out_capacity < n_22k) {
+        g_last_error = "output buffer holds " + std::to_string(out_capacity) + " samples, " + std::to_string(n_22k) + " needed";
+        return BLISS_B200_E_ARG;
+    }
+    if (sample_rate == (uint32_t)SAMPLE_RATE) {
+        memcpy(out, pcm, (size_t)n_samples * 4);
+        return BLISS_B200_OK;
+    }
+    if (int rc = design_resampler(sample_rate)) return rc;
+    CK(cudaDeviceSynchronize());  // ring slot 0 belongs to this call alone
+    CK(g.rs_in[0].ensure(align_up((size_t)n_samples, 4) * 4));
+    CK(g.pcm[0].ensure(align_up((size_t)n_22k, 4) * 4));
+    CK(cudaMemcpyAsync(g.rs_in[0].p, pcm, (size_t)n_samples * 4, cudaMemcpyHostToDevice, g.stream));
+    const std::vector<ResampleJobHost> jobs{ResampleJobHost{0, n_samples, 0, n_22k}};
+    if (int rc = enqueue_resample(0, g.rs_in[0].as<float>(), g.pcm[0].as<float>(), jobs, g.stream)) return rc;
+    CK(cudaMemcpyAsync(out, g.pcm[0].p, (size_t)n_22k * 4, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return BLISS_B200_OK;
 }
 
 int bliss_b200_pcm_to_mono(const void *pcm, uint64_t n_frames, int sample_format, uint32_t channels, float *out) {

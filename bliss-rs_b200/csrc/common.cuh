@@ -90,6 +90,7 @@ enum {
     VARIANT_OLD_DIST = 65536,  // distance matrix: the round-1 scalar kernel instead of distance_matrix_diag_kernel
     VARIANT_STFT_V3 = 131072,  // stft8192: the 256-thread / one-column kernel (stft8192_v3.cuh) instead of the 128-thread / two-column one; measured at the same 21.8 ms
     VARIANT_ACF_4LAGS = 262144, // beattrack_kernel: round 1's autocorrelation (four consecutive lags per thread) instead of the balanced lag pairs
+    VARIANT_RESAMPLE_V1 = 524288, // resampler: the first cut (one output per thread, filter rows from global memory) instead of the decimation / shared-table kernels
     VARIANT_PROMOTED = 64 | 128 | 256 | 512 | 1024 | 2048 | 4096 | 8192,
 };
 

@@ -128,6 +128,9 @@ class BlissCue:
             except BlissError as e:
                 entries.append(e)
                 continue
+            if decoded.pcm_frames is not None and decoded.pcm_rate != SAMPLE_RATE:
+                # the sheet's indices count 22 050 Hz samples (:212-213): such a file is cut after its conversion
+                decoded = PreAnalyzedSong(path=decoded.path, duration=decoded.duration, sample_array=decoded.mono())
             packed = decoded.pcm_frames is not None
             samples = decoded.pcm_frames if packed else np.asarray(decoded.sample_array, np.float32)
             total = len(samples)

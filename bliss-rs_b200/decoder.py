@@ -1,13 +1,14 @@
 """A concrete `Decoder` for the one family of sources this backend can take without the crate's decoders: RIFF/WAVE
-PCM files that already run at 22 050 Hz (src/lib.rs:143).
+PCM files.
 
-The reference's decoders (src/song/decoder/ffmpeg.rs, symphonia.rs) do three things to such a file: unpack the
-codec's frames, convert the sample format to f32 and down-mix to mono; nothing is resampled.  `WavDecoder.decode`
-does the first on the host (a RIFF chunk walk) and leaves the packed frames in `PreAnalyzedSong.pcm_frames`; the other
-two run on the device behind the copy (`bliss_b200_analyze_batch_pcm`: x * 2^-15 / x * 2^-31, c L + c R with
-c = (float)sqrt(1/2), mean in channel order for more channels), so `Decoder.analyze_paths` sends the file's own bytes
-over PCIe.  Any other sample rate is a DecodingError: there is no resampler on this side of the boundary (DESIGN.md
-section 7) -- such files stay with the crate's decoders.
+The reference's decoders (src/song/decoder/ffmpeg.rs, symphonia.rs) do four things to such a file: unpack the
+codec's frames, convert the sample format to f32, down-mix to mono and resample to 22 050 Hz (src/lib.rs:143).
+`WavDecoder.decode` does the first on the host (a RIFF chunk walk) and leaves the packed frames in
+`PreAnalyzedSong.pcm_frames` (their rate in `pcm_rate`); the others run on the device behind the copy
+(`bliss_b200_analyze_batch_pcm`: x * 2^-15 / x * 2^-31, c L + c R with c = (float)sqrt(1/2), mean in channel order for
+more channels, then the polyphase resampler of bliss_b200_resample), so `Decoder.analyze_paths` sends the file's own
+bytes over PCIe.  Files at 22 050 Hz are bit-identical to the reference's decoders' output; at other rates the
+resampler is this backend's own (parity unpinned: DESIGN.md section 7).
 
 Sample widths, as ffmpeg's pcm decoders deliver them (libavcodec/pcm.c behind ffmpeg.rs:190-360):
   8 bit unsigned  -> (x - 128) * 2^-7   (carried as s16: (x - 128) << 8)
@@ -20,9 +21,10 @@ import struct
 
 import numpy as np
 
-from .song import SAMPLE_RATE, Decoder, DecodingError, PreAnalyzedSong
+from .song import Decoder, DecodingError, PreAnalyzedSong
 
 MAX_CHANNELS = 8  # BLISS_B200_PCM_MAX_CHANNELS, include/bliss_b200.h
+MIN_SAMPLE_RATE, MAX_SAMPLE_RATE = 1000, 768000  # BLISS_B200_MIN_SAMPLE_RATE / _MAX_SAMPLE_RATE
 
 
 def _riff_wave(raw: bytes):
@@ -54,9 +56,8 @@ class WavDecoder(Decoder):
                 tag, channels, rate, bits, raw = _riff_wave(f.read())
         except (OSError, ValueError, struct.error) as e:
             raise DecodingError("while opening format for file '%s': %s." % (path, e))
-        if rate != SAMPLE_RATE:
-            raise DecodingError("file '%s' runs at %d Hz: this backend holds no resampler, only %d Hz sources are taken."
-                                % (path, rate, SAMPLE_RATE))
+        if not MIN_SAMPLE_RATE <= rate <= MAX_SAMPLE_RATE:
+            raise DecodingError("file '%s' runs at %d Hz (%d..%d are taken)." % (path, rate, MIN_SAMPLE_RATE, MAX_SAMPLE_RATE))
         if not 1 <= channels <= MAX_CHANNELS:
             raise DecodingError("file '%s' has %d channels (1..%d are taken)." % (path, channels, MAX_CHANNELS))
         if not ((tag == 1 and bits in (8, 16, 24, 32)) or (tag == 3 and bits == 32)):
@@ -76,4 +77,4 @@ class WavDecoder(Decoder):
         else:
             frames = np.frombuffer(raw, "<i4").astype(np.int32, copy=False)
         frames = np.ascontiguousarray(frames.reshape(n, channels))
-        return PreAnalyzedSong(path=str(path), duration=n / float(rate), pcm_frames=frames)
+        return PreAnalyzedSong(path=str(path), duration=n / float(rate), pcm_frames=frames, pcm_rate=int(rate))

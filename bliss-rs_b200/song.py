@@ -253,9 +253,10 @@ def analyze_batch(sample_arrays: Sequence, analysis_options: AnalysisOptions = N
 
 def analyze_batch_pcm(frames: Sequence, sample_rate: int = SAMPLE_RATE, analysis_options: AnalysisOptions = None) -> List:
     """analyze_batch for sources the codec delivers as interleaved [n_frames, channels] int16 / int32 / float32
-    frames at 22 050 Hz: the decoders' sample-format conversion and down-mix (src/song/decoder/ffmpeg.rs:36-109,
-    symphonia.rs:260-300) run on the device.  One format and channel count per call; any other sample rate raises
-    (resampling stays with the decoder)."""
+    frames: the decoders' sample-format conversion and down-mix (src/song/decoder/ffmpeg.rs:36-109,
+    symphonia.rs:260-300) and, for a sample_rate other than 22 050 Hz, the conversion to 22 050 Hz
+    (bliss_b200_resample: parity unpinned against swresample / rubato) run on the device.  One format, channel count
+    and rate per call."""
     analysis_options = analysis_options or AnalysisOptions()
     ver = FeaturesVersion(analysis_options.features_version)
     status, feats = native.analyze_batch_pcm(frames, sample_rate, int(ver))
@@ -264,19 +265,20 @@ def analyze_batch_pcm(frames: Sequence, sample_rate: int = SAMPLE_RATE, analysis
 
 def analyze_decoded(songs: Sequence["PreAnalyzedSong"], analysis_options: AnalysisOptions = None) -> List:
     """One batch of decoded songs -> one entry per song (Analysis | BlissError).  Songs that carry sample_array go
-    through analyze_batch; songs that carry packed frames are grouped by (sample format, channel count) -- one
-    bliss_b200_analyze_batch_pcm call takes one of each -- and converted on the device."""
+    through analyze_batch; songs that carry packed frames are grouped by (sample format, channel count, sample rate)
+    -- one bliss_b200_analyze_batch_pcm call takes one of each -- and converted on the device."""
     out: List = [None] * len(songs)
     groups = {}
     for i, p in enumerate(songs):
         f = p.pcm_frames
-        key = None if f is None else (np.asarray(f).dtype.str, 1 if np.asarray(f).ndim == 1 else np.asarray(f).shape[1])
+        key = None if f is None else (np.asarray(f).dtype.str, 1 if np.asarray(f).ndim == 1 else np.asarray(f).shape[1],
+                                      int(p.pcm_rate))
         groups.setdefault(key, []).append(i)
     for key, idx in groups.items():
         if key is None:
             res = analyze_batch([songs[i].sample_array for i in idx], analysis_options)
         else:
-            res = analyze_batch_pcm([songs[i].pcm_frames for i in idx], SAMPLE_RATE, analysis_options)
+            res = analyze_batch_pcm([songs[i].pcm_frames for i in idx], key[2], analysis_options)
         for i, r in zip(idx, res):
             out[i] = r
     return out
@@ -308,15 +310,19 @@ class PreAnalyzedSong:
     genre: Optional[str] = None
     duration: float = 0.0
     sample_array: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
-    #: Not in the reference.  A decoder whose source already runs at 22 050 Hz may leave the codec's packed frames
-    #: here ([n_frames, channels] int16 / int32 / float32) instead of filling sample_array: sample-format conversion
-    #: and down-mix then run on the device behind the copy (bliss_b200_analyze_batch_pcm),
+    #: Not in the reference.  A decoder may leave the codec's packed frames here ([n_frames, channels] int16 / int32 /
+    #: float32, at pcm_rate Hz) instead of filling sample_array: sample-format conversion, down-mix and the conversion
+    #: to 22 050 Hz then run on the device behind the copy (bliss_b200_analyze_batch_pcm),
     #: and e.g. 16-bit mono material sends half the bytes over PCIe.
     pcm_frames: Optional[np.ndarray] = None
+    pcm_rate: int = SAMPLE_RATE
 
     def mono(self) -> np.ndarray:
-        """sample_array as the reference's decoders would have filled it (src/song/decoder.rs:64)"""
-        return self.sample_array if self.pcm_frames is None else pcm_to_mono(self.pcm_frames)
+        """sample_array as this backend's decode steps fill it (src/song/decoder.rs:64)"""
+        if self.pcm_frames is None:
+            return self.sample_array
+        m = pcm_to_mono(self.pcm_frames)
+        return m if self.pcm_rate == SAMPLE_RATE else native.resample(m, self.pcm_rate)
 
     def to_song_with_options(self, analysis_options: AnalysisOptions) -> Song:
         """src/song/decoder.rs:85-100"""

@@ -109,19 +109,36 @@ int bliss_b200_analyze_batch_s16(const int16_t *const *pcm, const uint64_t *n_sa
  *                      src/song/decoder/symphonia.rs:260-262; pinned by the decoder test of
  *                      data/s16_stereo_22_5kHz.flac, src/song/decoder/ffmpeg.rs:447-452)
  *   > 2 channels       mean of the channels in channel order (src/song/decoder/symphonia.rs:289-299)
- * pcm[i]: n_frames[i] frames of `channels` samples; one format per call.  sample_rate must be 22050: there is no
- * resampler here (E_UNSUPPORTED otherwise; swresample / rubato stay on the decoder's side of the boundary).
- * Results are bit-identical to bliss_b200_analyze_batch on the output of bliss_b200_pcm_to_mono. */
+ *   sample_rate        other than 22 050 Hz: the mono signal is converted on the device behind the down-mix
+ *                      (bliss_b200_resample below says how, and what that is and is not pinned against)
+ * pcm[i]: n_frames[i] frames of `channels` samples; one format and one rate per call.  Results are bit-identical
+ * to bliss_b200_analyze_batch on the output of bliss_b200_pcm_to_mono (then bliss_b200_resample). */
 #define BLISS_B200_PCM_S16 1
 #define BLISS_B200_PCM_S32 2
 #define BLISS_B200_PCM_F32 3
 #define BLISS_B200_PCM_MAX_CHANNELS 8
+#define BLISS_B200_MIN_SAMPLE_RATE 1000u
+#define BLISS_B200_MAX_SAMPLE_RATE 768000u
 int bliss_b200_analyze_batch_pcm(const void *const *pcm, const uint64_t *n_frames, uint32_t n_songs,
                                  int sample_format, uint32_t channels, uint32_t sample_rate,
                                  uint16_t features_version, float *out, int32_t *status);
 /* The conversion alone (host in, host out): what PreAnalyzedSong::sample_array (src/song/decoder.rs:64) holds
  * for such a source.  out: n_frames floats. */
 int bliss_b200_pcm_to_mono(const void *pcm, uint64_t n_frames, int sample_format, uint32_t channels, float *out);
+
+/* Sample-rate conversion of a mono f32 signal to 22 050 Hz (host in, host out): the step between the down-mix and
+ * Song::analyze in the reference's decoders -- swresample in the ffmpeg decoder (src/song/decoder/ffmpeg.rs:36-109),
+ * rubato's synchronous FFT resampler in the symphonia decoder (src/song/decoder/symphonia.rs:304-404).  PARITY
+ * UNPINNED: both are third-party libraries outside the reference's tree, they do not agree with each other sample
+ * for sample (the reference compares its two decoders through tolerances), and neither can run here.  What this
+ * computes is the textbook rational-ratio polyphase resampler in the form scipy.signal.resample_poly(x, 22050, rate)
+ * publishes it (Kaiser beta 5 windowed sinc, half length 10 max(up, down), cut-off at the lower Nyquist frequency,
+ * delay removed), which the tests check it against to f32 rounding; the output length is the symphonia decoder's,
+ * ceil(22050 / rate * n) (:379-380), also returned by bliss_b200_resampled_len.
+ * out_capacity: floats `out` can hold; *n_out (may be NULL) receives the length.  22 050 Hz in is a copy. */
+uint64_t bliss_b200_resampled_len(uint64_t n_samples, uint32_t sample_rate);
+int bliss_b200_resample(const float *pcm, uint64_t n_samples, uint32_t sample_rate, float *out, uint64_t out_capacity,
+                        uint64_t *n_out);
 
 /* Same, PCM already resident in device memory: song i is d_pcm[offsets[i] .. offsets[i]+n_samples[i]).
  * d_pcm must be 16-byte aligned; offsets/n_samples/status are HOST arrays; d_out is a DEVICE

@@ -228,6 +228,17 @@ inline std::vector<float> pcm_to_mono(const void *frames, uint64_t n_frames, Pcm
     return out;
 }
 
+// mono f32 at sample_rate -> 22 050 Hz on the device (bliss_b200_resample: parity unpinned against the reference's
+// swresample / rubato, see include/bliss_b200.h)
+inline std::vector<float> resample(const std::vector<float> &mono, uint32_t sample_rate) {
+    detail::ensure_init();
+    std::vector<float> out(bliss_b200_resampled_len(mono.size(), sample_rate));
+    uint64_t n = 0;
+    detail::check_call(bliss_b200_resample(mono.data(), mono.size(), sample_rate, out.data(), out.size(), &n));
+    out.resize(n);
+    return out;
+}
+
 // src/song/decoder.rs:34-67
 struct PreAnalyzedSong {
     std::string path;
@@ -235,22 +246,25 @@ struct PreAnalyzedSong {
     std::optional<int> track_number, disc_number;
     double duration_s = 0.;
     std::vector<float> sample_array;  // mono f32le 22 050 Hz
-    // Not in the reference.  A decoder whose source already runs at 22 050 Hz may leave the codec's packed
-    // interleaved frames here instead of filling sample_array (pcm_channels > 0 says so): sample-format conversion
-    // and down-mix then run on the device behind the copy (analyze_batch_pcm), and e.g. 16-bit mono material sends
-    // half the bytes over PCIe.
+    // Not in the reference.  A decoder may leave the codec's packed interleaved frames here (at pcm_rate Hz) instead
+    // of filling sample_array (pcm_channels > 0 says so): sample-format conversion, down-mix and the conversion to
+    // 22 050 Hz then run on the device behind the copy (analyze_batch_pcm), and e.g. 16-bit mono material sends half
+    // the bytes over PCIe.
     std::vector<unsigned char> pcm_frames;
     PcmFormat pcm_format = PcmFormat::F32;
     uint32_t pcm_channels = 0;
+    uint32_t pcm_rate = SAMPLE_RATE;
     uint64_t n_frames() const { return pcm_channels ? pcm_frames.size() / ((pcm_format == PcmFormat::S16 ? 2 : 4) * pcm_channels) : sample_array.size(); }
-    std::vector<float> mono() const {  // sample_array as the reference's decoders would have filled it
-        return pcm_channels ? pcm_to_mono(pcm_frames.data(), n_frames(), pcm_format, pcm_channels) : sample_array;
+    std::vector<float> mono() const {  // sample_array as this backend's decode steps fill it
+        if (!pcm_channels) return sample_array;
+        std::vector<float> m = pcm_to_mono(pcm_frames.data(), n_frames(), pcm_format, pcm_channels);
+        return pcm_rate == SAMPLE_RATE ? m : resample(m, pcm_rate);
     }
 };
 
 // One batch of decoded songs -> one entry per song.  Songs that carry sample_array go through analyze_batch; songs
-// that carry packed frames are grouped by (sample format, channel count) -- one bliss_b200_analyze_batch_pcm call
-// takes one of each.
+// that carry packed frames are grouped by (sample format, channel count, sample rate) -- one
+// bliss_b200_analyze_batch_pcm call takes one of each.
 inline std::vector<AnalysisResult> analyze_decoded(const std::vector<PreAnalyzedSong> &songs, const AnalysisOptions &o = {}) {
     std::vector<AnalysisResult> out(songs.size(), AnalysisResult(BlissError(BlissError::AnalysisError, "not analysed")));
     std::vector<char> done(songs.size(), 0);
@@ -259,7 +273,7 @@ inline std::vector<AnalysisResult> analyze_decoded(const std::vector<PreAnalyzed
         const PreAnalyzedSong &lead = songs[first];
         std::vector<size_t> idx;
         for (size_t i = first; i < songs.size(); i++)
-            if (!done[i] && songs[i].pcm_channels == lead.pcm_channels && (lead.pcm_channels == 0 || songs[i].pcm_format == lead.pcm_format)) {
+            if (!done[i] && songs[i].pcm_channels == lead.pcm_channels && (lead.pcm_channels == 0 || (songs[i].pcm_format == lead.pcm_format && songs[i].pcm_rate == lead.pcm_rate))) {
                 idx.push_back(i);
                 done[i] = 1;
             }
@@ -273,7 +287,7 @@ inline std::vector<AnalysisResult> analyze_decoded(const std::vector<PreAnalyzed
         } else {
             std::vector<const void *> ptrs;
             for (size_t i : idx) ptrs.push_back(songs[i].pcm_frames.data());
-            res = analyze_batch_pcm(ptrs, lens, lead.pcm_format, lead.pcm_channels, BLISS_B200_SAMPLE_RATE, o);
+            res = analyze_batch_pcm(ptrs, lens, lead.pcm_format, lead.pcm_channels, lead.pcm_rate, o);
         }
         for (size_t k = 0; k < idx.size(); k++) out[idx[k]] = std::move(res[k]);
     }
@@ -436,7 +450,7 @@ class WavDecoder : public Decoder {
             o = body + len + (len & 1);
         }
         if (!channels || !data_off) throw fail("no fmt / data chunk");
-        if (rate != SAMPLE_RATE) throw fail("runs at " + std::to_string(rate) + " Hz: this backend holds no resampler, only 22050 Hz sources are taken");
+        if (rate < BLISS_B200_MIN_SAMPLE_RATE || rate > BLISS_B200_MAX_SAMPLE_RATE) throw fail("runs at " + std::to_string(rate) + " Hz");
         if (channels > BLISS_B200_PCM_MAX_CHANNELS) throw fail(std::to_string(channels) + " channels");
         const bool pcm = tag == 1 && (bits == 8 || bits == 16 || bits == 24 || bits == 32), flt = tag == 3 && bits == 32;
         if (!pcm && !flt) throw fail("encoding " + std::to_string(tag) + " with " + std::to_string(bits) + " bits per sample");
@@ -446,6 +460,7 @@ class WavDecoder : public Decoder {
         p.path = path;
         p.duration_s = static_cast<double>(n) / rate;
         p.pcm_channels = channels;
+        p.pcm_rate = rate;
         p.pcm_format = flt ? PcmFormat::F32 : (bits <= 16 ? PcmFormat::S16 : PcmFormat::S32);
         p.pcm_frames.resize(count * (bits <= 16 ? 2 : 4));
         if (bits == 16 || bits == 32) {
@@ -589,6 +604,12 @@ class BlissCue {
             } catch (const BlissError &e) {
                 out.emplace_back(e);
                 continue;
+            }
+            if (decoded.pcm_channels && decoded.pcm_rate != SAMPLE_RATE) {
+                // the sheet's indices count 22 050 Hz samples (:212-213): such a file is cut after its conversion
+                decoded.sample_array = decoded.mono();
+                decoded.pcm_frames.clear();
+                decoded.pcm_channels = 0;
             }
             const size_t total = decoded.n_frames();
             if (total == 0) {

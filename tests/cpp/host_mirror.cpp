@@ -180,10 +180,16 @@ int main() {
         auto rmo = analyze_batch({mono.data()}, {mono.size()});
         if (std::get<Analysis>(rst[0]).as_vec() != std::get<Analysis>(rmo[0]).as_vec()) return 16;
         try {
-            analyze_batch_pcm({st.data()}, {q.size()}, PcmFormat::S16, 2, 44100);
-            return 17;  // no resampler: must refuse
+            analyze_batch_pcm({st.data()}, {q.size()}, PcmFormat::S16, 2, 999);
+            return 17;  // outside BLISS_B200_MIN_SAMPLE_RATE .. _MAX_SAMPLE_RATE: must refuse
         } catch (const BlissError &) {
         }
+        // the same frames taken as 44.1 kHz material: down-mix + resampler + analysis in one call = the three steps apart
+        const std::vector<float> mono_cd = resample(mono, 44100);
+        if (mono_cd.size() != (mono.size() + 1) / 2 || bliss_b200_resampled_len(mono.size(), 44100) != mono_cd.size()) return 18;
+        auto rcd = analyze_batch_pcm({st.data()}, {q.size()}, PcmFormat::S16, 2, 44100);
+        auto rcd2 = analyze_batch({mono_cd.data()}, {mono_cd.size()});
+        if (std::get<Analysis>(rcd[0]).as_vec() != std::get<Analysis>(rcd2[0]).as_vec()) return 19;
         // WavDecoder: 22 050 Hz WAV files through the decoder pipeline, the file's own frames converted on the device
         {
             const char *tmp = std::getenv("TMPDIR");
@@ -210,7 +216,7 @@ int main() {
             const std::vector<std::string> wavs = {
                 write_wav("mono16.wav", 1, 1, 22050, 16, q.data(), 2 * q.size()), write_wav("stereo16.wav", 1, 2, 22050, 16, st.data(), 2 * st.size()),
                 write_wav("mono24.wav", 1, 1, 22050, 24, s24.data(), s24.size()), write_wav("float.wav", 3, 1, 22050, 32, back.data(), 4 * back.size()),
-                write_wav("cd.wav", 1, 1, 44100, 16, q.data(), 2 * q.size()), dir + "_missing.wav"};
+                write_wav("cd.wav", 1, 2, 44100, 16, st.data(), 2 * st.size()), dir + "_missing.wav"};
             WavDecoder wd;
             AnalysisOptions o2;
             o2.number_cores = 2;
@@ -227,12 +233,13 @@ int main() {
                     if (name == "stereo16.wav" && v != std::get<Analysis>(rst[0]).as_vec()) return 52;
                     if (name == "mono24.wav" && v != std::get<Analysis>(r24[0]).as_vec()) return 53;
                     if (name == "float.wav" && v != std::get<Analysis>(r32[0]).as_vec()) return 54;
-                    if (std::fabs(song->duration_s - 6.0) > 1e-9) return 55;
+                    if (name == "cd.wav" && v != std::get<Analysis>(rcd[0]).as_vec()) return 59;
+                    if (std::fabs(song->duration_s - (name == "cd.wav" ? 3.0 : 6.0)) > 1e-9) return 55;
                 } else {
-                    refused += std::get<BlissError>(r.second).kind == BlissError::DecodingError && (name == "cd.wav" || name == "missing.wav");
+                    refused += std::get<BlissError>(r.second).kind == BlissError::DecodingError && (name == "missing.wav");
                 }
             }
-            if (songs_ok != 4 || refused != 2) return 56;
+            if (songs_ok != 5 || refused != 1) return 56;
             if (wd.song_from_path(wavs[1]).analysis->as_vec() != std::get<Analysis>(rst[0]).as_vec()) return 57;
             if (wd.decode(wavs[1]).mono() != mono) return 58;
             // a CUE sheet over the stereo file: both tracks are slices of one decoded buffer, analysed in one call, and

@@ -23,6 +23,9 @@ const char *bliss_b200_last_error(void) { return "stub failure"; }
 int bliss_b200_analyze_batch_pcm(const void *const *, const uint64_t *, uint32_t, int, uint32_t, uint32_t, uint16_t, float *, int32_t *) {
     return BLISS_B200_E_ARG;  // not used by this program (no song carries packed frames)
 }
+int bliss_b200_pcm_to_mono(const void *, uint64_t, int, uint32_t, float *) { return BLISS_B200_E_ARG; }  // likewise
+uint64_t bliss_b200_resampled_len(uint64_t n, uint32_t) { return n; }
+int bliss_b200_resample(const float *, uint64_t, uint32_t, float *, uint64_t, uint64_t *) { return BLISS_B200_E_ARG; }
 uint32_t bliss_b200_feature_count(uint16_t v) { return v == 2 ? 23u : v == 1 ? 20u : 0u; }
 int bliss_b200_analyze_batch(const float *const *pcm, const uint64_t *n, uint32_t n_songs, uint16_t ver, float *out, int32_t *status) {
     if (g_in_call.fetch_add(1) != 0) g_overlapping_calls++;

@@ -539,10 +539,84 @@ def test_pcm_feed_matches_the_decoders_conversion(golden):
     st_6, f_6 = B.native.analyze_batch_pcm(six, 22050, 2)
     st_m, f_m = B.native.analyze_batch([O.pcm_to_mono(six[0])], 2)
     assert np.array_equal(f_6, f_m)
-    with pytest.raises(B.native.NativeError, match="22050"):          # no resampler on this side of the boundary
-        B.native.analyze_batch_pcm(songs[:1], 44100, 2)
+    with pytest.raises(B.native.NativeError, match="sample rate"):
+        B.native.analyze_batch_pcm(songs[:1], 999, 2)
     with pytest.raises(B.native.NativeError):
         B.native.analyze_batch_pcm([np.zeros((9000, 9), np.int16)], 22050, 2)
+
+
+RESAMPLE_V1 = 524288  # VARIANT_RESAMPLE_V1, common.cuh
+
+
+def test_resample_kernel_against_the_oracle():
+    """bliss_b200_resample: the polyphase resampler of the decode-side feed (wave_setup.cu resample_kernel) against
+    oracle/resample.py (scipy.signal.resample_poly's algorithm, pinned against scipy in tests/test_resample.py) --
+    PARITY UNPINNED against the reference's swresample / rubato, see the header.  Same f32 coefficients, f32 FMA sums
+    on the device against f64 sums in the oracle: 2e-6 x the signal's peak.  Rates: the common ones, up- and
+    down-sampling, a pair with a large `up`; lengths: empty, one sample, shorter than the filter, ragged."""
+    from oracle import resample as R
+    rng = np.random.default_rng(5)
+    cases = [(44100, 20001), (48000, 30011), (32000, 7777), (96000, 50000), (88200, 12345), (11025, 4097), (8000, 3001),
+             (16000, 6000), (24000, 5000), (22051, 3000), (44100, 0), (44100, 1), (48000, 7), (8000, 2), (22050, 1234),
+             (44100, 2048), (44100, 2049), (44100, 4 * 1024 * 2 + 3), (88200, 4096 * 3 + 5), (88200, 9), (44100, 45)]
+    if EMULATED:
+        cases = [(44100, 6001), (44100, 2049), (88200, 4101), (48000, 5003), (8000, 1501), (44100, 0), (48000, 7), (22050, 100)]
+    for rate, n in cases:
+        x = rng.standard_normal(n).astype(np.float32)
+        got, want = B.native.resample(x, rate), R.resample(x, rate)
+        assert got.shape == want.shape == (R.resampled_len(n, rate),), (rate, n, got.shape, want.shape)
+        assert B.native.resampled_len(n, rate) == want.size
+        if n:
+            err = np.abs(got.astype(np.float64) - want).max()
+            assert err <= 2e-6 * max(1.0, float(np.abs(x).max())), (rate, n, err)
+        # the first cut of the kernel (one output per thread, filter rows from global memory) against the kernel the
+        # ratio picks: the shared-table kernel sums in the same order (same bits), the decimation kernels (44.1 /
+        # 88.2 kHz) sum phase by phase
+        prev = B.native.set_variant(RESAMPLE_V1)
+        try:
+            first_cut = B.native.resample(x, rate)
+        finally:
+            B.native.set_variant(prev)
+        if rate in (44100, 88200):
+            assert n == 0 or np.abs(first_cut - got).max() <= 2e-6 * max(1.0, float(np.abs(x).max()))
+        else:
+            assert np.array_equal(first_cut.view(np.uint32), got.view(np.uint32)), (rate, n)
+    # what a resampler is for: a 1 kHz tone at 48 kHz comes out as the 1 kHz tone at 22 050 Hz, a 15 kHz tone
+    # (above the new Nyquist frequency) does not come out
+    t48 = np.arange(48000 if not EMULATED else 9600, dtype=np.float64) / 48000.0
+    low = B.native.resample(np.sin(2 * np.pi * 1000.0 * t48).astype(np.float32), 48000)
+    t22 = np.arange(low.size, dtype=np.float64) / 22050.0
+    assert np.abs(low[500:-500] - np.sin(2 * np.pi * 1000.0 * t22)[500:-500]).max() < 2e-3
+    high = B.native.resample(np.sin(2 * np.pi * 15000.0 * t48).astype(np.float32), 48000)
+    assert np.abs(high[500:-500]).max() < 1e-2
+    with pytest.raises(B.native.NativeError, match="sample rate"):
+        B.native.resample(np.zeros(10, np.float32), 1 << 20)
+
+
+def test_resample_feed_is_the_two_steps_fused(golden):
+    """bliss_b200_analyze_batch_pcm at a rate other than 22 050 Hz: down-mix, resampler and analysis behind one copy.
+    Bit-identical to analysing bliss_b200_resample(bliss_b200_pcm_to_mono(frames)); the features are those the
+    oracle computes from the oracle's resampled signal (1e-4); a song that is too short AFTER the conversion is
+    status 1; several songs of ragged lengths share a chunk."""
+    from oracle import resample as R
+    st = golden["pcm_s16_stereo"]                                     # taken as if it ran at 44 100 Hz
+    piano = np.ascontiguousarray(np.repeat(golden["pcm_piano"][:, None], 2, axis=1))
+    songs = [st, piano, st[:16001], st[:20000], st[:0]] if not EMULATED else [st[:60000], st[:16001], st[:0]]
+    for rate in ((44100, 48000) if not EMULATED else (44100,)):
+        st_p, f_p = B.native.analyze_batch_pcm(songs, rate, 2)
+        monos = [B.native.resample(B.native.pcm_to_mono(x), rate) for x in songs]
+        st_f, f_f = B.native.analyze_batch(monos, 2)
+        assert np.array_equal(st_p, st_f) and list(st_p) == [0 if m.size >= 8192 else 1 for m in monos]
+        assert np.array_equal(f_p[st_p == 0].view(np.uint32), f_f[st_f == 0].view(np.uint32))
+        rc, want = O.analyze(R.resample(O.pcm_to_mono(songs[0]), rate), 2)
+        _report("resampled feed %d Hz" % rate, f_p[0], want)
+        assert rc == 0 and _close(f_p[0], want).all()
+    # mono f32 at another rate takes the direct copy into the resampler's input
+    x = synth.gen_track(3, 0, 22050 * (8 if not EMULATED else 2), device=DEV).cpu().numpy()
+    up = R.resample(x, 11025)                                          # taken as 11 025 Hz material: twice the samples
+    st_m, f_m = B.native.analyze_batch_pcm([x[:, None]], 11025, 2)
+    st_d, f_d = B.native.analyze_batch([B.native.resample(x, 11025)], 2)
+    assert st_m[0] == 0 and np.array_equal(f_m, f_d) and up.size == 2 * x.size
 
 
 def test_library_playlists_run_on_the_distance_kernels(tmp_path):
@@ -593,11 +667,12 @@ def test_library_playlists_run_on_the_distance_kernels(tmp_path):
 
 
 def test_wav_files_through_the_decoder_pipeline(tmp_path, golden, pcm_piano):
-    """File -> features: 22 050 Hz WAV files through WavDecoder.analyze_paths (decoding threads, one batcher, packed
-    frames converted and down-mixed on the device).  The 16-bit mono file is data/piano.wav's content, so its row
-    must be Song::analyze of the decoder's f32 samples (ffmpeg.rs:523-527 pins those) bit for bit; the stereo and
-    24-bit files must equal the analysis of the oracle's conversion of the same frames; a 44.1 kHz file and a short
-    one are error items of the same call."""
+    """File -> features: WAV files through WavDecoder.analyze_paths (decoding threads, one batcher, packed frames
+    converted, down-mixed and -- the 44.1 kHz one -- resampled on the device).  The 16-bit mono file is
+    data/piano.wav's content, so its row must be Song::analyze of the decoder's f32 samples (ffmpeg.rs:523-527 pins
+    those) bit for bit; the stereo and 24-bit files must equal the analysis of the oracle's conversion of the same
+    frames; the 44.1 kHz file that of bliss_b200_resample's output; an unreadable file and a short one are error
+    items of the same call."""
     import wave
 
     def write(name, frames, width, rate=22050):
@@ -616,13 +691,17 @@ def test_wav_files_through_the_decoder_pipeline(tmp_path, golden, pcm_piano):
     st = np.stack([s16, np.roll(s16, 7) // 2], 1).astype(np.int16)
     s24 = s16.astype(np.int32) * 256 + 37
     paths = [write("piano.wav", s16, 2), write("stereo.wav", st, 2), write("piano24.wav", s24, 3),
-             write("cd.wav", s16, 2, rate=44100), write("short.wav", s16[:4000], 2)]
+             write("cd.wav", s16, 2, rate=44100), str(tmp_path / "junk.wav"), write("short.wav", s16[:4000], 2)]
+    (tmp_path / "junk.wav").write_bytes(b"RIFF....WAVEnothing")
     got = dict(B.WavDecoder.analyze_paths_with_options(paths, B.AnalysisOptions(number_cores=2)))
-    assert len(got) == 5
+    assert len(got) == 6
     assert np.array_equal(got[paths[0]].analysis.as_arr1(), B.Song.analyze(pcm_piano).as_arr1())
     assert np.array_equal(got[paths[1]].analysis.as_arr1(), B.Song.analyze(O.pcm_to_mono(st)).as_arr1())
     assert np.array_equal(got[paths[2]].analysis.as_arr1(), B.Song.analyze(O.pcm_to_mono(s24 * 256)).as_arr1())
-    assert isinstance(got[paths[3]], B.DecodingError) and isinstance(got[paths[4]], B.AnalysisError)
+    cd = B.native.resample(O.pcm_to_mono(s16), 44100)
+    assert cd.size == (s16.size + 1) // 2 and abs(got[paths[3]].duration - s16.size / 44100.0) < 1e-9
+    assert np.array_equal(got[paths[3]].analysis.as_arr1(), B.Song.analyze(cd).as_arr1())
+    assert isinstance(got[paths[4]], B.DecodingError) and isinstance(got[paths[5]], B.AnalysisError)
     assert abs(got[paths[0]].duration - s16.size / 22050.0) < 1e-9
     # a CUE sheet over one of the files (src/cue.rs:208-243): both tracks are slices of ONE decoded buffer analysed in one
     # call; each must be Song::analyze of that slice of the decoder's samples, bit for bit
@@ -637,12 +716,12 @@ def test_wav_files_through_the_decoder_pipeline(tmp_path, golden, pcm_piano):
     # ... and on into the reference's on-disk format (src/library.rs:500-529, 1544-1670): files -> decoder threads ->
     # GPU batches -> SQLite rows; the two refused files are rows of the failed-song kind, a second run is a no-op
     lib = B.library.Library(str(tmp_path / "songs.db"), decoder=B.WavDecoder)
-    assert lib.update_library(paths) == (3, 2)
+    assert lib.update_library(paths) == (4, 2)
     stored = {s.bliss_song.path: s.bliss_song.analysis.as_arr1() for s in lib.songs_from_library()}
-    assert sorted(stored) == sorted(paths[:3])
-    for p in paths[:3]:
+    assert sorted(stored) == sorted(paths[:4])
+    for p in paths[:4]:
         assert np.array_equal(stored[p], got[p].analysis.as_arr1())
-    assert sorted(f.song_path for f in lib.get_failed_songs()) == sorted(paths[3:])
+    assert sorted(f.song_path for f in lib.get_failed_songs()) == sorted(paths[4:])
     lib.close()
 
 

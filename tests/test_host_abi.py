@@ -198,9 +198,10 @@ def _write_wav(path, frames, width, rate=22050):
 
 
 def test_wav_decoder_keeps_the_codecs_frames(tmp_path, golden, monkeypatch):
-    """bliss-rs_b200/decoder.py: a 22 050 Hz RIFF/WAVE PCM file is unpacked on the host and nothing else -- the frames
-    reach bliss_b200_analyze_batch_pcm as the file holds them; other rates and unreadable files are DecodingErrors
-    (items of analyze_paths); a batch that mixes formats is split into one call per (format, channel count)."""
+    """bliss-rs_b200/decoder.py: a RIFF/WAVE PCM file is unpacked on the host and nothing else -- the frames reach
+    bliss_b200_analyze_batch_pcm as the file holds them, with the file's sample rate; unreadable files are
+    DecodingErrors (items of analyze_paths); a batch that mixes formats is split into one call per (format, channel
+    count, sample rate)."""
     s16 = golden["pcm_piano"][:30000]                       # data/piano.wav is such a file (ffmpeg.rs:523-527)
     rng = np.random.default_rng(1)
     st = np.stack([s16, (s16 // 3).astype(np.int16)], 1)
@@ -229,13 +230,17 @@ def test_wav_decoder_keeps_the_codecs_frames(tmp_path, golden, monkeypatch):
     assert np.array_equal(B.WavDecoder.decode(str(tmp_path / "mono32.wav")).pcm_frames[:, 0], s24 * 256)
     d8 = B.WavDecoder.decode(str(tmp_path / "mono8.wav")).pcm_frames
     assert d8.dtype == np.int16 and np.array_equal(d8[:, 0], (u8 - 128) * 256)   # pcm_u8: (x - 128) * 2^-7
-    for bad in ("cd.wav", "junk.wav", "missing.wav"):
+    dcd = B.WavDecoder.decode(str(tmp_path / "cd.wav"))
+    assert dcd.pcm_rate == 44100 and d.pcm_rate == 22050 and np.array_equal(dcd.pcm_frames[:, 0], s16)
+    assert abs(dcd.duration - 30000 / 44100) < 1e-9
+    _write_wav(tmp_path / "slow.wav", s16[:100], 2, rate=500)
+    for bad in ("slow.wav", "junk.wav", "missing.wav"):
         with pytest.raises(B.DecodingError):
             B.WavDecoder.decode(str(tmp_path / bad))
     calls = []
 
     def fake_pcm(frames, sample_rate=22050, opts=None):
-        calls.append(("pcm", frames[0].dtype.str, frames[0].shape[1], len(frames)))
+        calls.append(("pcm", frames[0].dtype.str, frames[0].shape[1], len(frames)) + ((sample_rate,) if sample_rate != 22050 else ()))
         return [B.Analysis(np.full(23, f.shape[1] + f.dtype.itemsize / 10)) for f in frames]
 
     def fake_f32(arrays, opts=None):
@@ -248,10 +253,10 @@ def test_wav_decoder_keeps_the_codecs_frames(tmp_path, golden, monkeypatch):
     got = dict(B.WavDecoder.analyze_paths_with_options([str(tmp_path / n) for n in names], B.AnalysisOptions(number_cores=1)))
     assert len(got) == len(names)
     tag = {n: (got[str(tmp_path / n)].analysis.as_arr1()[0] if isinstance(got[str(tmp_path / n)], B.Song) else None) for n in names}
-    assert tag["cd.wav"] is None and tag["junk.wav"] is None
+    assert tag["junk.wav"] is None and round(float(tag["cd.wav"]), 1) == 1.2
     assert [round(float(tag[n]), 1) for n in ("mono16.wav", "stereo16.wav", "mono24.wav", "mono8.wav", "mono32.wav")] == \
         [1.2, 2.2, 1.4, 1.2, 1.4]                                       # every row back with its own song
-    assert sorted(calls) == [("pcm", "<i2", 1, 2), ("pcm", "<i2", 2, 1), ("pcm", "<i4", 1, 2)]
+    assert sorted(calls) == [("pcm", "<i2", 1, 1, 44100), ("pcm", "<i2", 1, 2), ("pcm", "<i2", 2, 1), ("pcm", "<i4", 1, 2)]
     # songs that carry sample_array keep going through analyze_batch, in the same batch
     calls.clear()
     mixed = [B.PreAnalyzedSong(path="a", sample_array=np.zeros(9000, np.float32)), B.WavDecoder.decode(str(tmp_path / "mono16.wav"))]
@@ -392,7 +397,7 @@ def test_c_abi_on_the_host_emulated_library(tmp_path):
     env = dict(os.environ, BLISS_B200_SO=so, CUDA_VISIBLE_DEVICES="")
     pick = ("golden_clip_v2 or too_short or s16_ingest or pcm_feed or distance_known or distance_matrix_bit or "
             "closest_to_songs or dedup or stft512_magnitudes or experimental_stft_pair or cue_style or wav_files or library_playlists "
-            "or frame_edges or chroma_filter or packed_distance")
+            "or frame_edges or chroma_filter or packed_distance or resample")
     # the C++17 host mirror (include/bliss_b200.hpp: Song, Decoder, WavDecoder, analyze_batch[_s16|_pcm], playlist) end to
     # end, started first and left running beside the Python slice
     exe = str(tmp_path / "host_mirror_emu")
