@@ -49,8 +49,9 @@ int launch_finalize(const SongDesc *, int, const float *, const float *, const f
 int launch_wave_setup(const void *, void *, size_t, unsigned int *, unsigned int *, unsigned int, cudaStream_t);
 int launch_s16_to_f32(const short *, float *, size_t, cudaStream_t);
 int launch_pcm_to_mono(const void *, float *, size_t, int, unsigned int, cudaStream_t);
+ResamplePlan resample_plan(unsigned int up, unsigned int down, unsigned int taps4_needed, int variant);
 int launch_resample(const float *, float *, const void *, const unsigned int *, unsigned int, unsigned int, const float *,
-                    unsigned int, unsigned int, unsigned int, unsigned int, int, cudaStream_t);
+                    unsigned int, unsigned int, unsigned int, const ResamplePlan &, cudaStream_t);
 int launch_gather_barrier(unsigned int *const *, int, int, unsigned int, unsigned long long, cudaStream_t);
 int launch_distance_matrix(const float *, unsigned int, const float *, unsigned int, int, int, const float *,
                            float *, cudaStream_t, unsigned int ones_mask, int variant);
@@ -1144,7 +1145,8 @@ static int design_resampler(uint32_t rate) {  // into the calling context; a no-
         sum += h[k];
     }
     const uint64_t pre_pad = down - half % down, L = pre_pad + numtaps;
-    const uint32_t taps4 = (uint32_t)align_up((size_t)((L + up - 1) / up), 4);
+    // the row length the ratio's kernel wants (a few sizes exist for the register-resident kernel; rows are zero-filled)
+    const uint32_t taps4 = resample_plan(up, down, (uint32_t)align_up((size_t)((L + up - 1) / up), 4), 0).taps4;
     std::vector<float> tab((size_t)up * taps4, 0.f);
     for (uint32_t p = 0; p < up; p++)
         for (uint32_t t = 0; t < taps4; t++) {
@@ -1167,6 +1169,7 @@ static int design_resampler(uint32_t rate) {  // into the calling context; a no-
 // why); the caller guarantees that the slot's previous conversion has finished.
 struct ResampleJobHost { unsigned long long in_off, in_len, out_off, out_len; };
 static int enqueue_resample(int slot, const float *in, float *out, const std::vector<ResampleJobHost> &jobs_in, cudaStream_t st) {
+    const ResamplePlan plan = resample_plan(g.rs_up, g.rs_down, g.rs_taps4, (g.variant & VARIANT_RESAMPLE_V1) ? 1 : 0);
     std::vector<ResampleJobHost> jobs;
     std::vector<unsigned int> prefix;
     unsigned long long tiles = 0;
@@ -1174,7 +1177,7 @@ static int enqueue_resample(int slot, const float *in, float *out, const std::ve
         if (j.out_len == 0) continue;
         jobs.push_back(j);
         prefix.push_back((unsigned int)tiles);
-        tiles += (j.out_len + 1023) / 1024;
+        tiles += (j.out_len + plan.tile_out - 1) / plan.tile_out;
     }
     if (jobs.empty()) return BLISS_B200_OK;
     if (tiles >= 0x7fffffffull) { g_last_error = "resampler: chunk too large"; return BLISS_B200_E_ARG; }
@@ -1194,7 +1197,7 @@ static int enqueue_resample(int slot, const float *in, float *out, const std::ve
     const int launched = launch_resample(in, out, g.rs_jobs[slot].p,
                                          reinterpret_cast<const unsigned int *>(g.rs_jobs[slot].as<char>() + jb),
                                          (unsigned int)jobs.size(), (unsigned int)tiles, g.rs_tab.as<float>(), g.rs_up, g.rs_down,
-                                         g.rs_taps4, g.rs_pre, (g.variant & VARIANT_RESAMPLE_V1) ? 1 : 0, st);
+                                         g.rs_pre, plan, st);
     if (launched < 0) { g_last_error = "resampler: the filter table does not fit the kernel's shared memory"; return BLISS_B200_E_CUDA; }
     g.launches += (unsigned long long)launched;
     CK(cudaGetLastError());

@@ -94,6 +94,13 @@ enum {
     VARIANT_PROMOTED = 64 | 128 | 256 | 512 | 1024 | 2048 | 4096 | 8192,
 };
 
+// Sample-rate conversion (wave_setup.cu): which kernel serves a ratio, its tile size and the row length of its table
+enum { RS_KIND_FIRST_CUT = 0, RS_KIND_GENERAL = 1, RS_KIND_DECIMATE = 2, RS_KIND_PERIODIC = 3, RS_KIND_FIRST_CUT_TILED = 4 };
+struct ResamplePlan {
+    int kind;
+    unsigned int tile_out, taps4, nb;
+};
+
 // Song lookup for flat work lists: largest s with prefix[s] <= item (prefix has n_songs+1
 // entries, prefix[n_songs] = total).  Starts from the proportional guess -- exact for equal-length
 // songs, where it costs one round trip instead of log2(n_songs) dependent loads -- and falls

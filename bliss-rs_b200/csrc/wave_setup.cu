@@ -286,21 +286,199 @@ resample_decimate_kernel(const float *__restrict__ in, float *__restrict__ out, 
     }
 }
 
-// variant: 0 = pick the kernel for the ratio, 1 = the general kernel with the table in global memory (the first cut,
-// kept as the cross-check of the other two: tests/test_gpu_parity.py)
+// Any ratio whose `down` is a multiple of 4 and whose `up` fits a CTA (48 / 96 / 32 / 24 / 16 / 12 / 8 kHz ...).
+// Outputs j = r + up k (k = 0, 1, ...) share the filter row AND the alignment of their input window: their inputs
+// sit exactly k down samples apart.  So thread r keeps its row in REGISTERS for the whole tile -- re-indexed once so
+// that it lines up with the 16-byte-aligned window that contains x[i0 - T4 + 1 .. i0] (c'[u] = row[T4 - 1 + o - u],
+// o = the window's misalignment, constant over k because 4 | down) -- and each output is T4/4 + 1 aligned 16-byte
+// shared loads of x (staged once per CTA, coalesced, zero-filled outside the song) and as many FMAs as taps + 4.
+// No per-FMA load is left: the first cut issues one load per operand.  nb periods run side by side in a CTA
+// (thread = r + up b), RS_PERIODS_PER_THREAD outputs per thread.
+constexpr int RS_PERIODS_PER_THREAD = 16;
+
+// c[u] = row[T4 - 1 + O - u] for u = 0 .. T4 + 3 (zero outside the row)
+template <int T4, int O>
+__device__ __forceinline__ void resample_place_row(const float4 *__restrict__ row4, float (&c)[T4 + 4]) {
+#pragma unroll
+    for (int u = 0; u < T4 + 4; u++) c[u] = 0.f;
+#pragma unroll
+    for (int n = 0; n < T4 / 4; n++) {
+        const float4 v = __ldg(row4 + n);
+        c[T4 - 1 + O - 4 * n] = v.x;      // t = 4 n
+        c[T4 - 2 + O - 4 * n] = v.y;
+        c[T4 - 3 + O - 4 * n] = v.z;
+        c[T4 - 4 + O - 4 * n] = v.w;
+    }
+}
+
+template <int T4>
+__global__ void __launch_bounds__(512)
+resample_periodic_kernel(const float *__restrict__ in, float *__restrict__ out, const ResampleJob *__restrict__ jobs,
+                         const unsigned int *__restrict__ tile_prefix, unsigned int n_jobs, const float *__restrict__ tab,
+                         unsigned int up, unsigned int down, unsigned int pre_remove, unsigned int nb, unsigned int x_floats) {
+    constexpr int NW = T4 / 4 + 1;
+#ifdef BLISS_HOST_EMUL
+    unsigned char *rs_smem = emu::dynamic_smem();
+#else
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+#endif
+    float *xs = reinterpret_cast<float *>(rs_smem);
+    const unsigned int ji = resample_find_job(tile_prefix, n_jobs, blockIdx.x);
+    const ResampleJob job = jobs[ji];
+    const unsigned long long tile_out = (unsigned long long)up * nb * RS_PERIODS_PER_THREAD;
+    const unsigned long long j_first = (unsigned long long)(blockIdx.x - tile_prefix[ji]) * tile_out;  // a multiple of up
+    const unsigned long long base_q = (j_first + pre_remove) * down;
+    const long long first0 = (long long)(base_q / up) - (T4 - 1);
+    const long long x0 = first0 - (((first0 % 4) + 4) % 4);  // the tile's first input sample (may be negative), 4-aligned
+    const float *x = in + job.in_off;
+    for (unsigned int li = threadIdx.x * 4; li < x_floats; li += blockDim.x * 4) {
+        const long long i = x0 + li;
+        float4 v;
+        if (i >= 0 && i + 4 <= (long long)job.in_len) {
+            v = *reinterpret_cast<const float4 *>(x + i);
+        } else {
+            v.x = (i >= 0 && i < (long long)job.in_len) ? x[i] : 0.f;
+            v.y = (i + 1 >= 0 && i + 1 < (long long)job.in_len) ? x[i + 1] : 0.f;
+            v.z = (i + 2 >= 0 && i + 2 < (long long)job.in_len) ? x[i + 2] : 0.f;
+            v.w = (i + 3 >= 0 && i + 3 < (long long)job.in_len) ? x[i + 3] : 0.f;
+        }
+        *reinterpret_cast<float4 *>(xs + li) = v;
+    }
+    __syncthreads();
+    const unsigned int b = threadIdx.x / up, r = threadIdx.x - b * up;
+    if (b >= nb) return;
+    const unsigned long long qr = base_q + (unsigned long long)r * down;
+    const unsigned long long i0 = qr / up;
+    const unsigned int p = (unsigned int)(qr - i0 * up);
+    const long long first = (long long)i0 - (T4 - 1);
+    const int o = (int)(((first % 4) + 4) % 4);
+    const unsigned int lo = (unsigned int)((first - o) - x0);
+    float c[4 * NW];
+    {   // the row comes in as T4/4 16-byte loads; one of four fully unrolled placements puts it where the window wants it
+        const float4 *row4 = reinterpret_cast<const float4 *>(tab + (size_t)p * T4);
+        switch (o) {
+        case 0: resample_place_row<T4, 0>(row4, c); break;
+        case 1: resample_place_row<T4, 1>(row4, c); break;
+        case 2: resample_place_row<T4, 2>(row4, c); break;
+        default: resample_place_row<T4, 3>(row4, c); break;
+        }
+    }
+#pragma unroll 1
+    for (int kk = 0; kk < RS_PERIODS_PER_THREAD; kk++) {
+        const unsigned int k = b + nb * (unsigned int)kk;
+        const unsigned long long j = j_first + r + (unsigned long long)up * k;
+        if (j >= job.out_len) break;
+        const float4 *w = reinterpret_cast<const float4 *>(xs + lo + (size_t)k * down);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int n = 0; n < NW; n++) {
+            const float4 v = w[n];
+            a0 = fmaf(c[4 * n], v.x, a0);
+            a1 = fmaf(c[4 * n + 1], v.y, a1);
+            a2 = fmaf(c[4 * n + 2], v.z, a2);
+            a3 = fmaf(c[4 * n + 3], v.w, a3);
+        }
+        out[job.out_off + j] = (a0 + a1) + (a2 + a3);
+    }
+}
+
+// Which kernel serves a ratio, the size of its tiles (the host builds the chunk's tile prefix from it) and the row
+// length its table is laid out with (a periodic kernel exists for a few row lengths; rows are zero-filled up to it).
+static const unsigned int kPeriodicTaps[] = {24, 32, 48, 64, 92};
+
+ResamplePlan resample_plan(unsigned int up, unsigned int down, unsigned int taps4_needed, int variant) {
+    ResamplePlan pl;
+    pl.kind = RS_KIND_GENERAL;
+    pl.tile_out = 1024;
+    pl.taps4 = taps4_needed;
+    pl.nb = 0;
+    if (up == 1 && (down == 2 || down == 4) && taps4_needed == 22 * down) {
+        pl.kind = RS_KIND_DECIMATE;
+    } else if (up > 1 && up <= 448 && down % 4 == 0) {
+        for (unsigned int t : kPeriodicTaps)
+            if (t >= taps4_needed) {
+                pl.kind = RS_KIND_PERIODIC;
+                pl.taps4 = t;
+                pl.nb = up >= 224 ? 1 : 224 / up;
+                pl.tile_out = up * pl.nb * RS_PERIODS_PER_THREAD;
+                break;
+            }
+    }
+    if (pl.kind == RS_KIND_GENERAL && (size_t)up * pl.taps4 * 4 > RS_MAX_SMEM_TABLE) pl.kind = RS_KIND_FIRST_CUT;
+    if (variant) {  // the first cut on the same table and tiles
+        if (pl.kind == RS_KIND_DECIMATE || pl.kind == RS_KIND_GENERAL) pl.kind = RS_KIND_FIRST_CUT;
+        else if (pl.kind == RS_KIND_PERIODIC) pl.kind = RS_KIND_FIRST_CUT_TILED;
+    }
+    return pl;
+}
+
+// One output per thread over tiles of any size (RS_KIND_FIRST_CUT_TILED: the first cut on a periodic kernel's tiles)
+__global__ void __launch_bounds__(256)
+resample_first_cut_tiled_kernel(const float *__restrict__ in, float *__restrict__ out, const ResampleJob *__restrict__ jobs,
+                                const unsigned int *__restrict__ tile_prefix, unsigned int n_jobs, const float *__restrict__ tab,
+                                unsigned int up, unsigned int down, unsigned int taps4, unsigned int pre_remove, unsigned int tile_out) {
+    const unsigned int ji = resample_find_job(tile_prefix, n_jobs, blockIdx.x);
+    const ResampleJob job = jobs[ji];
+    const unsigned long long j_first = (unsigned long long)(blockIdx.x - tile_prefix[ji]) * tile_out;
+    for (unsigned int jj = threadIdx.x; jj < tile_out; jj += blockDim.x) {
+        const unsigned long long j = j_first + jj;
+        if (j >= job.out_len) break;
+        const unsigned long long q = (j + pre_remove) * down;
+        const unsigned long long i0 = q / up;
+        const unsigned int p = (unsigned int)(q - i0 * up);
+        out[job.out_off + j] = resample_one(in + job.in_off, job.in_len, reinterpret_cast<const float4 *>(tab) + (size_t)p * (taps4 >> 2), i0, taps4);
+    }
+}
+
+template <int T4>
+static int launch_periodic(const float *in, float *out, const ResampleJob *jobs, const unsigned int *tile_prefix, unsigned int n_jobs,
+                           unsigned int n_tiles, const float *tab, unsigned int up, unsigned int down, unsigned int pre_remove,
+                           unsigned int nb, cudaStream_t st) {
+    const unsigned int x_floats = nb * RS_PERIODS_PER_THREAD * down + 4 * (T4 / 4 + 1) + 8;
+    const size_t smem = (size_t)x_floats * 4;
+    const unsigned int threads = (up * nb + 31u) / 32u * 32u;
+#ifndef BLISS_HOST_EMUL
+    if (smem > 200 * 1024) return -1;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(resample_periodic_kernel<T4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return -1;
+#endif
+    BLISS_LAUNCH(resample_periodic_kernel<T4>, n_tiles, threads, smem, st, in, out, jobs, tile_prefix, n_jobs, tab, up, down, pre_remove,
+                 nb, x_floats);
+    return 1;
+}
+
+// n_tiles counts tiles of plan.tile_out outputs (the tile prefix the host built from the same plan)
 int launch_resample(const float *in, float *out, const void *jobs_v, const unsigned int *tile_prefix, unsigned int n_jobs,
-                    unsigned int n_tiles, const float *tab, unsigned int up, unsigned int down, unsigned int taps4,
-                    unsigned int pre_remove, int variant, cudaStream_t st) {
+                    unsigned int n_tiles, const float *tab, unsigned int up, unsigned int down, unsigned int pre_remove,
+                    const ResamplePlan &pl, cudaStream_t st) {
     if (n_jobs == 0 || n_tiles == 0) return 0;
     const ResampleJob *jobs = static_cast<const ResampleJob *>(jobs_v);
-    if (variant == 0 && up == 1 && (down == 2 || down == 4) && taps4 == 22 * down) {
+    const unsigned int taps4 = pl.taps4;
+    switch (pl.kind) {
+    case RS_KIND_DECIMATE:
         if (down == 2) BLISS_LAUNCH(resample_decimate_kernel<2>, n_tiles, 256, 0, st, in, out, jobs, tile_prefix, n_jobs, tab, pre_remove);
         else BLISS_LAUNCH(resample_decimate_kernel<4>, n_tiles, 256, 0, st, in, out, jobs, tile_prefix, n_jobs, tab, pre_remove);
         return 1;
+    case RS_KIND_PERIODIC:
+        switch (taps4) {
+        case 24: return launch_periodic<24>(in, out, jobs, tile_prefix, n_jobs, n_tiles, tab, up, down, pre_remove, pl.nb, st);
+        case 32: return launch_periodic<32>(in, out, jobs, tile_prefix, n_jobs, n_tiles, tab, up, down, pre_remove, pl.nb, st);
+        case 48: return launch_periodic<48>(in, out, jobs, tile_prefix, n_jobs, n_tiles, tab, up, down, pre_remove, pl.nb, st);
+        case 64: return launch_periodic<64>(in, out, jobs, tile_prefix, n_jobs, n_tiles, tab, up, down, pre_remove, pl.nb, st);
+        case 92: return launch_periodic<92>(in, out, jobs, tile_prefix, n_jobs, n_tiles, tab, up, down, pre_remove, pl.nb, st);
+        default: return -1;
+        }
+    case RS_KIND_FIRST_CUT_TILED:
+        BLISS_LAUNCH(resample_first_cut_tiled_kernel, n_tiles, 256, 0, st, in, out, jobs, tile_prefix, n_jobs, tab, up, down, taps4,
+                     pre_remove, pl.tile_out);
+        return 1;
+    default:
+        break;
     }
     const unsigned int grid = (n_tiles + RS_TILES_PER_CTA - 1) / RS_TILES_PER_CTA;
     const size_t table_bytes = (size_t)up * taps4 * 4;
-    if (variant == 0 && table_bytes <= RS_MAX_SMEM_TABLE) {
+    if (pl.kind == RS_KIND_GENERAL) {
 #ifndef BLISS_HOST_EMUL
         if (table_bytes > 48 * 1024 &&
             cudaFuncSetAttribute(resample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes) != cudaSuccess)

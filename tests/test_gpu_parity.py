@@ -558,9 +558,11 @@ def test_resample_kernel_against_the_oracle():
     rng = np.random.default_rng(5)
     cases = [(44100, 20001), (48000, 30011), (32000, 7777), (96000, 50000), (88200, 12345), (11025, 4097), (8000, 3001),
              (16000, 6000), (24000, 5000), (22051, 3000), (44100, 0), (44100, 1), (48000, 7), (8000, 2), (22050, 1234),
-             (44100, 2048), (44100, 2049), (44100, 4 * 1024 * 2 + 3), (88200, 4096 * 3 + 5), (88200, 9), (44100, 45)]
+             (44100, 2048), (44100, 2049), (44100, 4 * 1024 * 2 + 3), (88200, 4096 * 3 + 5), (88200, 9), (44100, 45),
+             (48000, 3528 * 320 // 147 * 2 + 11), (12000, 9000), (64000, 70001), (192000, 40000), (37800, 20000), (48000, 1)]
     if EMULATED:
-        cases = [(44100, 6001), (44100, 2049), (88200, 4101), (48000, 5003), (8000, 1501), (44100, 0), (48000, 7), (22050, 100)]
+        cases = [(44100, 6001), (44100, 2049), (88200, 4101), (48000, 9003), (8000, 1501), (44100, 0), (48000, 7), (22050, 100),
+                 (11025, 1000), (96000, 6000), (32000, 3000)]
     for rate, n in cases:
         x = rng.standard_normal(n).astype(np.float32)
         got, want = B.native.resample(x, rate), R.resample(x, rate)
@@ -570,17 +572,18 @@ def test_resample_kernel_against_the_oracle():
             err = np.abs(got.astype(np.float64) - want).max()
             assert err <= 2e-6 * max(1.0, float(np.abs(x).max())), (rate, n, err)
         # the first cut of the kernel (one output per thread, filter rows from global memory) against the kernel the
-        # ratio picks: the shared-table kernel sums in the same order (same bits), the decimation kernels (44.1 /
-        # 88.2 kHz) sum phase by phase
+        # ratio picks: the shared-table kernel (11 025 Hz here) sums in the same order (same bits); the decimation
+        # kernels (44.1 / 88.2 kHz) sum phase by phase and the register-resident kernel (4 | down) in four strands
         prev = B.native.set_variant(RESAMPLE_V1)
         try:
             first_cut = B.native.resample(x, rate)
         finally:
             B.native.set_variant(prev)
-        if rate in (44100, 88200):
-            assert n == 0 or np.abs(first_cut - got).max() <= 2e-6 * max(1.0, float(np.abs(x).max()))
-        else:
+        if rate in (11025, 22051, 22050):
             assert np.array_equal(first_cut.view(np.uint32), got.view(np.uint32)), (rate, n)
+        else:
+            assert first_cut.shape == got.shape
+            assert n == 0 or np.abs(first_cut - got).max() <= 2e-6 * max(1.0, float(np.abs(x).max())), (rate, n)
     # what a resampler is for: a 1 kHz tone at 48 kHz comes out as the 1 kHz tone at 22 050 Hz, a 15 kHz tone
     # (above the new Nyquist frequency) does not come out
     t48 = np.arange(48000 if not EMULATED else 9600, dtype=np.float64) / 48000.0
