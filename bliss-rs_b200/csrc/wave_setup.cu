@@ -66,8 +66,8 @@ int launch_s16_to_f32(const short *in, float *out, size_t n, cudaStream_t st) {
 }
 
 // ---- interleaved PCM -> mono f32 (bliss_b200_analyze_batch_pcm, bliss_b200_pcm_to_mono) ------------------
-// The sample-format and down-mix steps of the reference's decoders for sources that already run at
-// 22 050 Hz (a resampler is not part of this library):
+// The sample-format and down-mix steps of the reference's decoders (the sample-rate conversion that follows them for
+// sources at another rate is further down):
 //   s16 -> flt   x * 2^-15, s32 -> flt   x * 2^-31      swresample's conversions behind
 //                                                       src/song/decoder/ffmpeg.rs:36-109 (symphonia's
 //                                                       `sample as f32 / 32768.0` rounds identically)

@@ -100,9 +100,9 @@ int bliss_b200_analyze_batch(const float *const *pcm, const uint64_t *n_samples,
 int bliss_b200_analyze_batch_s16(const int16_t *const *pcm, const uint64_t *n_samples, uint32_t n_songs,
                                  uint16_t features_version, float *out, int32_t *status);
 
-/* Decode-side feed, general form: interleaved frames as the container's codec delivers them, for sources that
- * already run at 22 050 Hz -- the sample-format conversion and the down-mix to mono of the reference's decoders
- * run on the device behind each chunk's copy:
+/* Decode-side feed, general form: interleaved frames as the container's codec delivers them -- the sample-format
+ * conversion, the down-mix to mono and the conversion to 22 050 Hz of the reference's decoders run on the device
+ * behind each chunk's copy:
  *   s16 / s32 -> f32   x * 2^-15 / x * 2^-31 (swresample's conversions, src/song/decoder/ffmpeg.rs:36-109;
  *                      symphonia's `as f32 / 32768.0` rounds identically)
  *   2 channels         c L + c R with c = (float)sqrt(1/2) (swresample's stereo -> mono matrix for float output,

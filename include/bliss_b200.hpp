@@ -416,12 +416,13 @@ class Decoder {
     }
 };
 
-// A concrete Decoder for the one family of sources this backend takes without the crate's decoders: RIFF/WAVE files
-// that already run at 22 050 Hz (src/lib.rs:143).  The reference's decoders unpack such a file, convert the sample
-// format to f32 and down-mix; nothing is resampled.  decode() does the first on the host and leaves the packed frames
-// in PreAnalyzedSong::pcm_frames, the rest runs on the device.  Widths as ffmpeg's pcm decoders deliver them:
+// A concrete Decoder for the one family of sources this backend takes without the crate's decoders: RIFF/WAVE PCM
+// files.  The reference's decoders unpack such a file, convert the sample format to f32, down-mix and resample to
+// 22 050 Hz (src/lib.rs:143).  decode() does the first on the host and leaves the packed frames in
+// PreAnalyzedSong::pcm_frames (their rate in pcm_rate), the rest runs on the device (the resampler's parity against
+// swresample / rubato is unpinned, include/bliss_b200.h).  Widths as ffmpeg's pcm decoders deliver them:
 // u8 -> (x - 128) 2^-7 (carried as s16), s16 -> x 2^-15, s24 -> x 2^-23 (carried as s32: x << 8), s32 -> x 2^-31,
-// IEEE f32 as it is.  Any other rate or encoding throws DecodingError: no resampler lives on this side of the boundary.
+// IEEE f32 as it is.  Any other encoding throws DecodingError.
 class WavDecoder : public Decoder {
   public:
     PreAnalyzedSong decode(const std::string &path) override {
