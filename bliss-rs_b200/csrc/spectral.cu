@@ -812,14 +812,23 @@ stft512_pairs_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__
 //   256-sample block energy -> silence test of Tempo::do_ (aubio.rs:1258-1276, :1431)
 // ---------------------------------------------------------------------------
 constexpr int TD_CHUNKS_PER_WARP = 8;
+// Footprint: 128 threads x <= 56 registers, no shared memory -- what an SM has LEFT beside three CTAs of the chroma STFT
+// (3 x 128 x 152 registers, 218 of 227 KB of shared memory).  The idea was that this HBM-bound kernel, enqueued behind
+// the compute-bound STFT, trickles through underneath it.  Measured (profiles/knobs_r02.md): it does not, at 56 / 48 /
+// 40 / 32 registers, with or without a common carve-out; the step stays the sum of its kernels.  The cut is kept because
+// it is the faster one alone (2.43 against 2.50 ms per 1024 tracks, same bits).
+constexpr int TD_THREADS = 128;
+#ifndef BLISS_TD_MIN_BLOCKS
+#define BLISS_TD_MIN_BLOCKS 9  // <= 56 registers
+#endif
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TD_THREADS, BLISS_TD_MIN_BLOCKS)
 timedomain_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ songs,
                   const unsigned int *__restrict__ group_prefix, int n_songs,
                   unsigned int total_groups, float *__restrict__ loud_ms,
                   float *__restrict__ block_energy, unsigned int *__restrict__ zcr_count) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned int item = blockIdx.x * 8u + (unsigned)warp;
+    const unsigned int item = blockIdx.x * (unsigned)(TD_THREADS / 32) + (unsigned)warp;
     if (item >= total_groups) return;
     const int si = find_song(group_prefix, n_songs, item);
     const SongDesc sd = songs[si];
@@ -835,44 +844,49 @@ timedomain_kernel(const float *__restrict__ pcm, const SongDesc *__restrict__ so
         const unsigned int len = min(1024u, n - base);
         const bool has_prev = base > 0;
         float eb[4] = {0.f, 0.f, 0.f, 0.f};
-        // all eight 16-byte loads of the lane are issued before anything consumes them
-        float v[8][4];
-        if (len == 1024u && ((sd.pcm_off + base) & 3ull) == 0) {
-            const float4 *p4 = reinterpret_cast<const float4 *>(x + base) + lane;
+        const bool fast = len == 1024u && ((sd.pcm_off + base) & 3ull) == 0;
+        // two halves of four rows: the four 16-byte loads of a half are issued before anything consumes them
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const float4 t = __ldg(p4 + 32 * k);
-                v[k][0] = t.x; v[k][1] = t.y; v[k][2] = t.z; v[k][3] = t.w;
-            }
-        } else {
+        for (int h = 0; h < 2; h++) {
+            float v[4][4];
+            if (fast) {
+                const float4 *p4 = reinterpret_cast<const float4 *>(x + base) + lane + 128 * h;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const unsigned int p = 4u * lane + 128u * k;
-#pragma unroll
-                for (int i = 0; i < 4; i++) v[k][i] = (p + i < len) ? __ldg(x + base + p + i) : 0.f;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const unsigned int p = 4u * lane + 128u * k;
-            float e = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; i++) e += v[k][i] * v[k][i];
-            eb[k >> 1] += e;
-            // predecessor of v[k][0]: previous lane's last sample; lane 0 takes the previous row's tail
-            float pred = __shfl_up_sync(0xffffffffu, v[k][3], 1);
-            if (lane == 0) pred = prev_tail;
-            const bool have_pred = (k > 0) || (lane > 0) || has_prev;
-            float before = pred;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if (p + i < len) {
-                    const bool valid_pair = (i > 0) || have_pred;
-                    if (valid_pair && ((before > 0.f) != (v[k][i] > 0.f))) crossings++;
+                for (int k = 0; k < 4; k++) {
+                    const float4 t = __ldg(p4 + 32 * k);
+                    v[k][0] = t.x; v[k][1] = t.y; v[k][2] = t.z; v[k][3] = t.w;
                 }
-                before = v[k][i];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned int p = 4u * lane + 128u * (4 * h + k);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[k][i] = (p + i < len) ? __ldg(x + base + p + i) : 0.f;
+                }
             }
-            prev_tail = __shfl_sync(0xffffffffu, v[k][3], 31);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                const int k = 4 * h + kk;
+                const unsigned int p = 4u * lane + 128u * k;
+                float e = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; i++) e += v[kk][i] * v[kk][i];
+                eb[k >> 1] += e;
+                // predecessor of v[k][0]: previous lane's last sample; lane 0 takes the previous row's tail
+                float pred = __shfl_up_sync(0xffffffffu, v[kk][3], 1);
+                if (lane == 0) pred = prev_tail;
+                const bool have_pred = (k > 0) || (lane > 0) || has_prev;
+                float before = pred;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (p + i < len) {
+                        const bool valid_pair = (i > 0) || have_pred;
+                        if (valid_pair && ((before > 0.f) != (v[kk][i] > 0.f))) crossings++;
+                    }
+                    before = v[kk][i];
+                }
+                prev_tail = __shfl_sync(0xffffffffu, v[kk][3], 31);
+            }
         }
 #pragma unroll
         for (int b = 0; b < 4; b++) eb[b] = warp_sum(eb[b]);
@@ -948,8 +962,9 @@ int launch_timedomain(const float *pcm, const SongDesc *songs, const unsigned in
                       int n_songs, unsigned int total_groups, float *loud_ms, float *block_energy,
                       unsigned int *zcr_count, cudaStream_t st) {
     if (total_groups == 0) return 0;
-    const unsigned int grid = (total_groups + 7u) / 8u;
-    BLISS_LAUNCH(timedomain_kernel, grid, 256, 0, st, pcm, songs, group_prefix, n_songs, total_groups, loud_ms,
+    const unsigned int per_cta = TD_THREADS / 32;
+    const unsigned int grid = (total_groups + per_cta - 1u) / per_cta;
+    BLISS_LAUNCH(timedomain_kernel, grid, TD_THREADS, 0, st, pcm, songs, group_prefix, n_songs, total_groups, loud_ms,
                                             block_energy, zcr_count);
     return 1;
 }

@@ -18,6 +18,10 @@ VARIANTS = {
     # chroma_pipe_kernel's cp.async ring: 3 stages (3 CTAs per SM) is the default
     "k5p4": ["-DK5P_STAGES_N=4"],
     "k5p2": ["-DK5P_STAGES_N=2"],
+    # timedomain_kernel's register cap (65536 / (128 x min blocks)): does it fit beside three chroma-STFT CTAs?
+    "td48": ["-DBLISS_TD_MIN_BLOCKS=10"],
+    "td40": ["-DBLISS_TD_MIN_BLOCKS=12"],
+    "td32": ["-DBLISS_TD_MIN_BLOCKS=16"],
 }
 
 

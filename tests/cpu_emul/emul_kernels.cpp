@@ -174,7 +174,7 @@ int main(int argc, char **argv) {
         const std::vector<unsigned> gp = {0u, groups};
         std::vector<float> loud(sd.n_l, -7.f), eb(n / 256 + 1, -7.f);
         std::vector<unsigned> zcr(1, 0u);
-        emu::launch((groups + 7) / 8, 256, [&] {
+        emu::launch((groups + 3) / 4, TD_THREADS, [&] {
             timedomain_kernel(x.data(), songs.data(), gp.data(), 1, groups, loud.data(), eb.data(), zcr.data());
         });
         dump("loudness_chunks", loud);
@@ -293,7 +293,7 @@ int main(int argc, char **argv) {
             std::vector<float> loud(sd.n_l, 0.f), eb(n / 256 + 1, 0.f), cen(sd.n_s), rol(sd.n_s), fla(sd.n_s), flux(sd.n_t),
                 thr(sd.n_t), bpm(sd.n_t / 16 + 16, 0.f), tempo(1, 0.f);
             std::vector<unsigned> zcr(1, 0u), nbpm(1, 0u);
-            emu::launch((groups + 7) / 8, 256, [&] {
+            emu::launch((groups + 3) / 4, TD_THREADS, [&] {
                 timedomain_kernel(x.data(), songs.data(), gp.data(), 1, groups, loud.data(), eb.data(), zcr.data());
             });
             emu::launch((items + 7) / 8, 256, [&] {
@@ -420,7 +420,7 @@ int main(int argc, char **argv) {
             std::vector<unsigned> zcr(k, 0u), nbpm(k, 0u), cc(k, 0u);
             std::vector<double> cm(cands + 1, 0.), cp(cands + 1, 0.), partials(tiles * 10 + 10, 0.);
             std::vector<int> tuning(k, 0);
-            emu::launch((chp[k] + 7) / 8, 256, [&] { timedomain_kernel(x.data(), bs.data(), chp.data(), k, chp[k], loud.data(), eb.data(), zcr.data()); });
+            emu::launch((chp[k] + 3) / 4, TD_THREADS, [&] { timedomain_kernel(x.data(), bs.data(), chp.data(), k, chp[k], loud.data(), eb.data(), zcr.data()); });
             emu::launch((k1p[k] + 7) / 8, 256, [&] {
                 pvoc_kern(x.data(), bs.data(), k1p.data(), k, k1p[k], bppi, tab, cen.data(), rol.data(), fla.data(), flux.data(), nullptr);
             }, 8 * pv2::WARP_SMEM_BYTES);
