@@ -897,8 +897,18 @@ chroma_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs
 #ifndef K5P_STAGES_N
 #define K5P_STAGES_N 3
 #endif
+#ifndef K5P_SWIZZLE
+#define K5P_SWIZZLE 1
+#endif
 constexpr int K5P_STAGES = K5P_STAGES_N;
-constexpr int K5P_PITCH = K5_KT + 4;  // floats per staged row
+// Staged row: exactly 64 B, its four 16-byte chunks permuted by (row >> 1) & 3 -- conflict-free for the quarter-warp
+// 128-bit loads AND for the LDGSTS writes (K5P_SWIZZLE 0: the first layout, 16 floats + 4 of padding, pitch 80 B,
+// whose writes were not).  A stage is 16 instead of 20 KB, and under a 128-register cap FOUR CTAs share an SM.
+// Measured on 1024 tracks (scripts/gpu_r02_v.sh, gpu_r02_w.sh): padded rows, 3 CTAs 6.85 ms; swizzled, 3 CTAs 5.93;
+// swizzled, 4 CTAs 5.81 (the step: 52.05 -> 51.15 -> 50.61 ms).  A fourth or only two stages change nothing any more
+// (5.91 / 5.79 ms): the loads are no longer what the kernel waits for.  Same arithmetic, same bits.
+constexpr int K5P_PITCH = K5P_SWIZZLE ? K5_KT : K5_KT + 4;
+__host__ __device__ constexpr int k5p_swz(int row) { return K5P_SWIZZLE ? ((row >> 1) & 3) : 0; }
 
 #ifdef BLISS_HOST_EMUL  // host emulation: the copy happens on the spot (a legal completion time for cp.async)
 inline void cp_async16(void *smem, const void *gmem, int src_bytes) {
@@ -919,7 +929,10 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 #endif
 
-__global__ void __launch_bounds__(K5_THREADS, K5P_STAGES_N == 3 ? 3 : 2)
+#ifndef K5P_MIN_BLOCKS
+#define K5P_MIN_BLOCKS (K5P_SWIZZLE ? (K5P_STAGES_N <= 3 ? 4 : 3) : (K5P_STAGES_N == 3 ? 3 : 2))
+#endif
+__global__ void __launch_bounds__(K5_THREADS, K5P_MIN_BLOCKS)
 chroma_pipe_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ songs,
                    const unsigned int *__restrict__ tile_prefix, int n_songs,
                    const float *__restrict__ filt_table, const int *__restrict__ tuning_idx,
@@ -948,7 +961,7 @@ chroma_pipe_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ 
     // staging map: thread copies 16-byte chunk (tid & 3) of rows (tid >> 2) + 32 i, i = 0..7
     const int st_c = tid & 3, st_r = tid >> 2;
     auto issue = [&](int stage, int k0) {
-        float *dst = s_s + (size_t)stage * CH_TILE_FRAMES * K5P_PITCH + st_r * K5P_PITCH + 4 * st_c;
+        float *dst = s_s + (size_t)stage * CH_TILE_FRAMES * K5P_PITCH + st_r * K5P_PITCH + 4 * (st_c ^ k5p_swz(st_r));  // (rows st_r + 32 i share the permutation)
         const float *src = S + (size_t)st_r * CH_STRIDE + k0 + 4 * st_c;
 #pragma unroll
         for (int i = 0; i < CH_TILE_FRAMES / 32; i++)  // rows past nrows: nothing is read, zeros are written
@@ -978,6 +991,7 @@ chroma_pipe_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ 
         const float4 *va = reinterpret_cast<const float4 *>(s_s + (size_t)buf * CH_TILE_FRAMES * K5P_PITCH + tid * K5P_PITCH);
         const float4 *vb = reinterpret_cast<const float4 *>(s_s + (size_t)buf * CH_TILE_FRAMES * K5P_PITCH + (tid + 128) * K5P_PITCH);
         const float4 *wq = reinterpret_cast<const float4 *>(s_w + buf * K5_KT * 12);
+        const int sw = k5p_swz(tid);  // rows tid and tid + 128 share it
         // (frame a, frame b) ride one FFMA2 per chroma row: .x = frame tid, .y = frame tid + 128; each half is
         // exactly the scalar fmaf(w, s^2, p) of the previous kernel
         cpx p[12];
@@ -985,7 +999,7 @@ chroma_pipe_kernel(const float *__restrict__ mags, const SongDesc *__restrict__ 
         for (int c = 0; c < 12; c++) p[c] = cpx{0.f, 0.f};
 #pragma unroll
         for (int g4 = 0; g4 < K5_KT / 4; g4++) {
-            const float4 a4 = va[g4], b4 = vb[g4];
+            const float4 a4 = va[g4 ^ sw], b4 = vb[g4 ^ sw];
             const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int j = 0; j < 4; j++) {

@@ -16,8 +16,13 @@ VARIANTS = {
     "nopacked": ["-DBLISS_NO_PACKED_FP"],  # scalar FADD/FMUL/FFMA butterflies instead of the f32x2 forms
     "stride4104": ["-DBLISS_CH_STRIDE=4104"],  # round 1's pitch (rows 32 bytes off the 128-byte lines); 4128 is the default now
     # chroma_pipe_kernel's cp.async ring: 3 stages (3 CTAs per SM) is the default
-    "k5p4": ["-DK5P_STAGES_N=4"],
-    "k5p2": ["-DK5P_STAGES_N=2"],
+    "k5p4": ["-DK5P_STAGES_N=4", "-DK5P_SWIZZLE=0"],
+    "k5p2": ["-DK5P_STAGES_N=2", "-DK5P_SWIZZLE=0"],
+    # rows of exactly 64 B (chunk swizzle instead of padding) at four CTAs per SM are the default now; the steps there:
+    "k5p3pad": ["-DK5P_STAGES_N=3", "-DK5P_SWIZZLE=0"],                       # round 2's first layout (pitch 80 B, 3 CTAs)
+    "k5p3sw": ["-DK5P_STAGES_N=3", "-DK5P_SWIZZLE=1", "-DK5P_MIN_BLOCKS=3"],  # swizzle alone
+    "k5p4sw": ["-DK5P_STAGES_N=4", "-DK5P_SWIZZLE=1"],                        # ... a fourth stage
+    "k5p2sw4": ["-DK5P_STAGES_N=2", "-DK5P_SWIZZLE=1", "-DK5P_MIN_BLOCKS=4"],  # two stages at four CTAs
     # timedomain_kernel's register cap (65536 / (128 x min blocks)): does it fit beside three chroma-STFT CTAs?
     "td48": ["-DBLISS_TD_MIN_BLOCKS=10"],
     "td40": ["-DBLISS_TD_MIN_BLOCKS=12"],
