@@ -312,8 +312,8 @@ def measure_e2e(nat, torch, world, ES, host_songs, feats_ref, args, dim):
     # bytes per song; the resampler's parity against the reference's swresample / rubato is unpinned.
     e2e_cd = None
     try:
-        n_cd = max(n_dev, min(ES, 32) // n_dev * n_dev)   # songs of this leg (31.8 MB each)
-        per = n_cd // n_dev
+        per = min(ES, 32)                                 # songs per device in this leg (31.8 MB each)
+        n_cd = per * n_dev
         cd = {}
         for k in bufs:
             t = bufs[k][:per * TRACK_SAMPLES].view(per, TRACK_SAMPLES)
