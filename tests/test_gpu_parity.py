@@ -559,10 +559,11 @@ def test_resample_kernel_against_the_oracle():
     cases = [(44100, 20001), (48000, 30011), (32000, 7777), (96000, 50000), (88200, 12345), (11025, 4097), (8000, 3001),
              (16000, 6000), (24000, 5000), (22051, 3000), (44100, 0), (44100, 1), (48000, 7), (8000, 2), (22050, 1234),
              (44100, 2048), (44100, 2049), (44100, 4 * 1024 * 2 + 3), (88200, 4096 * 3 + 5), (88200, 9), (44100, 45),
-             (48000, 3528 * 320 // 147 * 2 + 11), (12000, 9000), (64000, 70001), (192000, 40000), (37800, 20000), (48000, 1)]
+             (48000, 3528 * 320 // 147 * 2 + 11), (12000, 9000), (64000, 70001), (192000, 40000), (37800, 20000), (48000, 1), (29400, 30000), (58800, 40000),
+             (176400, 50000), (1000, 2000), (768000, 100000)]
     if EMULATED:
         cases = [(44100, 6001), (44100, 2049), (88200, 4101), (48000, 9003), (8000, 1501), (44100, 0), (48000, 7), (22050, 100),
-                 (11025, 1000), (96000, 6000), (32000, 3000)]
+                 (11025, 1000), (96000, 6000), (32000, 3000), (29400, 3000), (58800, 4000)]
     for rate, n in cases:
         x = rng.standard_normal(n).astype(np.float32)
         got, want = B.native.resample(x, rate), R.resample(x, rate)
