@@ -615,6 +615,19 @@ def test_resample_feed_is_the_two_steps_fused(golden):
         rc, want = O.analyze(R.resample(O.pcm_to_mono(songs[0]), rate), 2)
         _report("resampled feed %d Hz" % rate, f_p[0], want)
         assert rc == 0 and _close(f_p[0], want).all()
+    if EMULATED:
+        # the chunked host path with the staging ring re-used (1 MB chunks: four songs each): offsets of the input-rate and
+        # the 22 050 Hz buffers, job tables per ring slot.  (On a GPU the bench's e2e_cd leg is the multi-chunk case.)
+        import os
+        rng = np.random.default_rng(3)
+        many = [rng.integers(-20000, 20000, (n, 2), dtype=np.int16) for n in (60000, 45001, 90003, 17000, 0, 70000, 52000, 61001, 40000)]
+        os.environ["BLISS_B200_CHUNK_MB"] = "1"
+        try:
+            st_c, f_c = B.native.analyze_batch_pcm(many, 48000, 2)
+        finally:
+            del os.environ["BLISS_B200_CHUNK_MB"]
+        st_1, f_1 = B.native.analyze_batch([B.native.resample(B.native.pcm_to_mono(x), 48000) for x in many], 2)
+        assert np.array_equal(st_c, st_1) and np.array_equal(f_c[st_c == 0].view(np.uint32), f_1[st_1 == 0].view(np.uint32))
     # mono f32 at another rate takes the direct copy into the resampler's input
     x = synth.gen_track(3, 0, 22050 * (8 if not EMULATED else 2), device=DEV).cpu().numpy()
     up = R.resample(x, 11025)                                          # taken as 11 025 Hz material: twice the samples
